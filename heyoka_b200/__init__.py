@@ -1,0 +1,606 @@
+"""heyoka_b200 — B200-native batch Taylor integrator (drop-in for heyoka's taylor_adaptive_batch<double>).
+
+This Python package is a thin ctypes mirror of the C ABI in include/heyoka_b200.h, shaped after the
+reference's C++ API (include/heyoka/taylor.hpp:780-1121) so that the parity tests read like the
+reference's own tests (test/taylor_adaptive_batch.cpp). The product is the native library
+(heyoka_b200/lib/libheyoka_b200.so: host C++ front end + hand-written sm_100a CUDA kernels); there is no
+Python or CPU fallback for the compute path: if the library is missing, importing fails loudly.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _capi
+from ._capi import lib, check, HyError  # noqa: F401
+
+__all__ = [
+    "expression", "make_vars", "par", "time", "sin", "cos", "tanh", "exp", "log", "sqrt", "square", "pow", "sum",
+    "prod", "model", "taylor_adaptive_batch", "taylor_outcome", "Program", "Batch", "order_from_tol", "HyError",
+]
+
+
+class taylor_outcome:
+    """include/heyoka/taylor.hpp:142-155."""
+    success = -4294967297
+    step_limit = -4294967298
+    time_limit = -4294967299
+    err_nf_state = -4294967300
+    cb_stop = -4294967301
+
+
+# ------------------------------------------------------------------------------------------------
+# Expressions
+# ------------------------------------------------------------------------------------------------
+class expression:
+    __slots__ = ("_h",)
+
+    def __init__(self, value=0.0, _handle=None):
+        if _handle is not None:
+            self._h = int(_handle.value if isinstance(_handle, C.c_void_p) else _handle)
+        elif isinstance(value, expression):
+            self._h = _capi.ex_checked(lib.hy_ex_copy(value._h))
+        elif isinstance(value, str):
+            self._h = _capi.ex_checked(lib.hy_ex_var(value.encode()))
+        else:
+            self._h = _capi.ex_checked(lib.hy_ex_num(float(value)))
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            lib.hy_ex_free(h)
+            self._h = None
+
+    @staticmethod
+    def _wrap(x):
+        return x if isinstance(x, expression) else expression(x)
+
+    def _bin(self, op, other, swap=False):
+        o = expression._wrap(other)
+        a, b = (o, self) if swap else (self, o)
+        return expression(_handle=_capi.ex_checked(lib.hy_ex_binary(op.encode(), a._h, b._h)))
+
+    def __add__(self, o):
+        return self._bin("+", o)
+
+    def __radd__(self, o):
+        return self._bin("+", o, True)
+
+    def __sub__(self, o):
+        return self._bin("-", o)
+
+    def __rsub__(self, o):
+        return self._bin("-", o, True)
+
+    def __mul__(self, o):
+        return self._bin("*", o)
+
+    def __rmul__(self, o):
+        return self._bin("*", o, True)
+
+    def __truediv__(self, o):
+        return self._bin("/", o)
+
+    def __rtruediv__(self, o):
+        return self._bin("/", o, True)
+
+    def __pow__(self, o):
+        return self._bin("^", o)
+
+    def __neg__(self):
+        return expression(_handle=_capi.ex_checked(lib.hy_ex_binary(b"n", self._h, None)))
+
+    def __pos__(self):
+        return self
+
+    def __repr__(self):
+        n = lib.hy_ex_str(self._h, None, 0)
+        buf = C.create_string_buffer(n + 1)
+        lib.hy_ex_str(self._h, buf, n + 1)
+        return buf.value.decode()
+
+
+def _func(name, *args):
+    keep = [expression._wrap(a) for a in args]  # keep temporaries alive
+    arr = (C.c_void_p * len(keep))(*[k._h for k in keep])
+    return expression(_handle=_capi.ex_checked(lib.hy_ex_func(name.encode(), arr, len(keep))))
+
+
+def make_vars(*names):
+    return tuple(expression(n) for n in names)
+
+
+class _Par:
+    def __getitem__(self, idx):
+        return expression(_handle=_capi.ex_checked(lib.hy_ex_par(int(idx))))
+
+
+par = _Par()
+time = expression(_handle=_capi.ex_checked(lib.hy_ex_time()))
+
+
+def sin(e):
+    return _func("sin", e)
+
+
+def cos(e):
+    return _func("cos", e)
+
+
+def tanh(e):
+    return _func("tanh", e)
+
+
+def exp(e):
+    return _func("exp", e)
+
+
+def log(e):
+    return _func("log", e)
+
+
+def sqrt(e):
+    return _func("sqrt", e)
+
+
+def square(e):
+    return _func("square", e)
+
+
+def pow(b, e):  # noqa: A001
+    return expression._wrap(b) ** e
+
+
+def sum(terms):  # noqa: A001
+    return _func("sum", *terms)
+
+
+def prod(terms):
+    return _func("prod", *terms)
+
+
+class model:
+    """model::nbody / pendulum / ffnn (src/model/*.cpp)."""
+
+    @staticmethod
+    def nbody(n, masses=None, Gconst=1.0):
+        lhs = (C.c_void_p * (6 * n))()
+        rhs = (C.c_void_p * (6 * n))()
+        if masses is None:
+            check(lib.hy_model_nbody(n, None, 0, float(Gconst), lhs, rhs))
+        else:
+            m = np.ascontiguousarray(masses, dtype=np.float64)
+            check(lib.hy_model_nbody(n, m.ctypes.data_as(C.POINTER(C.c_double)), len(m), float(Gconst), lhs, rhs))
+        return [(expression(_handle=lhs[i]), expression(_handle=rhs[i])) for i in range(6 * n)]
+
+    @staticmethod
+    def pendulum(gconst=1.0, length=1.0):
+        lhs = (C.c_void_p * 2)()
+        rhs = (C.c_void_p * 2)()
+        check(lib.hy_model_pendulum(float(gconst), float(length), lhs, rhs))
+        return [(expression(_handle=lhs[i]), expression(_handle=rhs[i])) for i in range(2)]
+
+    @staticmethod
+    def ffnn(inputs, nn_hidden, n_out, activations, nn_wb=None):
+        ids = {"identity": 0, "tanh": 1, "sin": 2, "exp": 3}
+        ins = [expression._wrap(i) for i in inputs]
+        arr = (C.c_void_p * len(ins))(*[i._h for i in ins])
+        hid = (C.c_uint32 * len(nn_hidden))(*nn_hidden)
+        act = (C.c_int * len(activations))(*[ids[a] for a in activations])
+        out = (C.c_void_p * n_out)()
+        if nn_wb is None:
+            check(lib.hy_model_ffnn(arr, len(ins), hid, len(nn_hidden), n_out, act, None, 0, out))
+        else:
+            wb = np.ascontiguousarray(nn_wb, dtype=np.float64)
+            check(lib.hy_model_ffnn(arr, len(ins), hid, len(nn_hidden), n_out, act,
+                                    wb.ctypes.data_as(C.POINTER(C.c_double)), len(wb), out))
+        return [expression(_handle=out[i]) for i in range(n_out)]
+
+
+def order_from_tol(tol):
+    o = C.c_uint32()
+    check(lib.hy_order_from_tol(float(tol), C.byref(o)))
+    return o.value
+
+
+# ------------------------------------------------------------------------------------------------
+# Program
+# ------------------------------------------------------------------------------------------------
+class Program:
+    """The lowered Taylor decomposition of an ODE system (include/heyoka_b200.h, section B)."""
+
+    def __init__(self, sys, tol=0.0, high_accuracy=False, _handle=None):
+        if _handle is not None:
+            self._h = _handle
+        else:
+            n = len(sys)
+            self._keep = [(expression._wrap(lhs), expression._wrap(rhs)) for lhs, rhs in sys]
+            lhs = (C.c_void_p * n)(*[p[0]._h for p in self._keep])
+            rhs = (C.c_void_p * n)(*[p[1]._h for p in self._keep])
+            h = C.c_void_p()
+            check(lib.hy_program_from_sys(lhs, rhs, n, float(tol), int(bool(high_accuracy)), C.byref(h)))
+            self._h = h
+        d = _capi.hy_program_desc()
+        check(lib.hy_program_get_desc(self._h, C.byref(d)))
+        self.desc = d
+        self.n_eq, self.n_uvars, self.n_pars, self.order = d.n_eq, d.n_uvars, d.n_pars, d.order
+        self.high_accuracy = bool(d.high_accuracy)
+
+    @classmethod
+    def from_arrays(cls, n_eq, n_uvars, n_pars, order, ops, args, consts, sv_defs, high_accuracy=False):
+        ops = np.ascontiguousarray(ops, dtype=np.uint32).reshape(-1, 4)
+        args = np.ascontiguousarray(args, dtype=np.uint32)
+        consts = np.ascontiguousarray(consts, dtype=np.float64)
+        sv_defs = np.ascontiguousarray(sv_defs, dtype=np.uint32)
+        d = _capi.hy_program_desc()
+        d.n_eq, d.n_uvars, d.n_pars, d.order = n_eq, n_uvars, n_pars, order
+        d.n_args, d.n_consts, d.high_accuracy = len(args), len(consts), int(high_accuracy)
+        d.ops = ops.ctypes.data_as(C.c_void_p)
+        d.args = args.ctypes.data_as(C.c_void_p)
+        d.consts = consts.ctypes.data_as(C.c_void_p)
+        d.sv_defs = sv_defs.ctypes.data_as(C.c_void_p)
+        h = C.c_void_p()
+        check(lib.hy_program_create(C.byref(d), C.byref(h)))
+        return cls(None, _handle=h)
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            lib.hy_program_destroy(h)
+            self._h = None
+
+    @property
+    def dc_size(self):
+        return lib.hy_program_dc_size(self._h)
+
+    def dc_str(self):
+        n = lib.hy_program_dc_str(self._h, None, 0)
+        buf = C.create_string_buffer(n + 1)
+        lib.hy_program_dc_str(self._h, buf, n + 1)
+        return buf.value.decode()
+
+    def costs(self):
+        a, b, c = C.c_double(), C.c_double(), C.c_double()
+        check(lib.hy_program_costs(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return {"b_min": a.value, "b_tape": b.value, "flops": c.value}
+
+    def ops_array(self):
+        n = self.n_uvars - self.n_eq
+        return np.ctypeslib.as_array(C.cast(self.desc.ops, C.POINTER(C.c_uint32)), shape=(n, 4)).copy()
+
+
+# ------------------------------------------------------------------------------------------------
+# Batch (device-resident)
+# ------------------------------------------------------------------------------------------------
+def _dptr(a):
+    return None if a is None else a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+class Batch:
+    """Device-resident integrator state + kernels (include/heyoka_b200.h, section C)."""
+
+    def __init__(self, program, batch, device=-1):
+        self.program = program
+        self.n = int(batch)
+        h = C.c_void_p()
+        check(lib.hy_batch_create(program._h, self.n, int(device), C.byref(h)))
+        self._h = h
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            lib.hy_batch_destroy(h)
+            self._h = None
+
+    def set_stream(self, cuda_stream):
+        check(lib.hy_batch_set_stream(self._h, C.c_void_p(int(cuda_stream))))
+
+    def set_launch_config(self, block_threads=0, blocks_per_sm=0):
+        check(lib.hy_batch_set_launch_config(self._h, int(block_threads), int(blocks_per_sm)))
+
+    def sync(self):
+        check(lib.hy_batch_sync(self._h))
+
+    def upload(self, state=None, pars=None, t_hi=None, t_lo=None):
+        f = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float64)  # noqa: E731
+        s, p, th, tl = f(state), f(pars), f(t_hi), f(t_lo)
+        check(lib.hy_batch_upload(self._h, _dptr(s), _dptr(p), _dptr(th), _dptr(tl)))
+
+    def download(self):
+        P = self.program
+        state = np.empty((P.n_eq, self.n))
+        t_hi, t_lo, last_h = np.empty(self.n), np.empty(self.n), np.empty(self.n)
+        check(lib.hy_batch_download(self._h, _dptr(state), _dptr(t_hi), _dptr(t_lo), _dptr(last_h)))
+        return state, t_hi, t_lo, last_h
+
+    def step_res(self):
+        oc, h = np.empty(self.n, dtype=np.int64), np.empty(self.n)
+        check(lib.hy_batch_download_step_res(self._h, oc.ctypes.data_as(C.POINTER(C.c_int64)), _dptr(h)))
+        return oc, h
+
+    def prop_res(self):
+        oc = np.empty(self.n, dtype=np.int64)
+        mn, mx = np.empty(self.n), np.empty(self.n)
+        ns = np.empty(self.n, dtype=np.uint64)
+        check(lib.hy_batch_download_prop_res(self._h, oc.ctypes.data_as(C.POINTER(C.c_int64)), _dptr(mn), _dptr(mx),
+                                             ns.ctypes.data_as(C.POINTER(C.c_uint64))))
+        return oc, mn, mx, ns
+
+    def tc(self):
+        P = self.program
+        out = np.empty((P.n_eq, P.order + 1, self.n))
+        check(lib.hy_batch_download_tc(self._h, _dptr(out)))
+        return out
+
+    def ptrs(self):
+        p = _capi.hy_batch_ptrs()
+        check(lib.hy_batch_get_ptrs(self._h, C.byref(p)))
+        return p
+
+    def step(self, max_delta_t=None, backward=False, write_tc=False):
+        m = None if max_delta_t is None else np.ascontiguousarray(max_delta_t, dtype=np.float64)
+        check(lib.hy_batch_step(self._h, _dptr(m), 0, int(backward), int(write_tc)))
+
+    def propagate_until(self, t_hi, t_lo=None, max_delta_t=None, max_steps=0, write_tc=False):
+        f = lambda a: None if a is None else np.ascontiguousarray(np.broadcast_to(a, (self.n,)), dtype=np.float64)  # noqa
+        th, tl, m = f(t_hi), f(t_lo), f(max_delta_t)
+        check(lib.hy_batch_propagate_until(self._h, _dptr(th), _dptr(tl), _dptr(m), int(max_steps), int(write_tc)))
+
+    def propagate_until_dev(self, d_t_hi, d_t_lo=0, d_max_delta_t=0, max_steps=0, write_tc=False):
+        flag = C.c_int()
+        vp = lambda x: C.cast(C.c_void_p(int(x) if x else None), C.POINTER(C.c_double))  # noqa: E731
+        check(lib.hy_batch_propagate_until_dev(self._h, vp(d_t_hi), vp(d_t_lo), vp(d_max_delta_t), int(max_steps),
+                                               int(write_tc), C.byref(flag)))
+        return flag.value
+
+    def d_output(self, tau):
+        P = self.program
+        tau = np.ascontiguousarray(np.broadcast_to(tau, (self.n,)), dtype=np.float64)
+        out = np.empty((P.n_eq, self.n))
+        check(lib.hy_batch_d_output(self._h, _dptr(tau), _dptr(out)))
+        return out
+
+    def launch_count(self):
+        n = C.c_uint64()
+        check(lib.hy_batch_launch_count(self._h, C.byref(n)))
+        return n.value
+
+
+# ------------------------------------------------------------------------------------------------
+# taylor_adaptive_batch: host-mirrored integrator with the reference's surface.
+# ------------------------------------------------------------------------------------------------
+class taylor_adaptive_batch:
+    """Mirror of heyoka::taylor_adaptive_batch<double> (include/heyoka/taylor.hpp:780-1121).
+
+    The integrator owns host arrays (state [n_eq, batch], pars [n_pars, batch], time) that the user may
+    modify between calls; like the reference's raw-pointer contract they are re-uploaded at every
+    step()/propagate_*() entry and refreshed on exit.
+    """
+
+    def __init__(self, sys, state, batch_size, time=0.0, tol=0.0, high_accuracy=False, compact_mode=False, pars=None,
+                 device=-1, t_events=None, nt_events=None, parallel_mode=False):
+        batch_size = int(batch_size)
+        if batch_size == 0:
+            raise ValueError("The batch size in an adaptive Taylor integrator cannot be zero")
+        if t_events or nt_events:
+            raise NotImplementedError("Event detection is not supported by the B200 batch integrator")
+        self._prog = Program(sys, tol=tol, high_accuracy=high_accuracy)
+        P = self._prog
+        state = np.array(state, dtype=np.float64)
+        # Size checks of finalise_ctor_impl(), src/taylor_adaptive_batch.cpp:164-274.
+        if state.size != P.n_eq * batch_size:
+            raise ValueError(
+                "Inconsistent sizes detected in the initialization of an adaptive Taylor integrator in batch mode: "
+                "the state vector has a dimension of %d and a batch size of %d, while the number of equations is %d"
+                % (state.size, batch_size, P.n_eq))
+        self._state = state.reshape(P.n_eq, batch_size).copy()
+        tm = np.broadcast_to(np.asarray(time, dtype=np.float64), (batch_size,)) if np.ndim(time) == 0 else \
+            np.asarray(time, dtype=np.float64)
+        if tm.size != batch_size:
+            raise ValueError(
+                "Invalid initial time vector specified in the construction of an adaptive Taylor integrator in batch "
+                "mode: the batch size is %d, but the number of specified initial times is %d" % (batch_size, tm.size))
+        if not np.all(np.isfinite(self._state)):
+            raise ValueError("A non-finite value was detected in the initial state of an adaptive Taylor integrator")
+        if not np.all(np.isfinite(tm)):
+            raise ValueError("A non-finite initial time was detected in the initialisation of an adaptive Taylor "
+                             "integrator")
+        self._t_hi = tm.copy()
+        self._t_lo = np.zeros(batch_size)
+        if pars is None:
+            self._pars = np.zeros((P.n_pars, batch_size))
+        else:
+            pars = np.array(pars, dtype=np.float64)
+            if pars.size != P.n_pars * batch_size:
+                raise ValueError(
+                    "Invalid number of parameter values passed to the constructor of an adaptive Taylor integrator in "
+                    "batch mode: %d parameter value(s) were passed, but the ODE system contains %d parameter(s) (in "
+                    "batches of %d)" % (pars.size, P.n_pars, batch_size))
+            self._pars = pars.reshape(P.n_pars, batch_size).copy()
+        self._tol = float(tol) if tol > 0 else float(np.finfo(np.float64).eps)
+        self._batch_size = batch_size
+        self._compact_mode = bool(compact_mode)
+        self._b = Batch(P, batch_size, device)
+        self._last_h = np.zeros(batch_size)
+        self._step_res = None
+        self._prop_res = None
+        self._tc = None
+
+    # --- getters -------------------------------------------------------------------------------
+    def get_batch_size(self):
+        return self._batch_size
+
+    def get_order(self):
+        return self._prog.order
+
+    def get_tol(self):
+        return self._tol
+
+    def get_high_accuracy(self):
+        return self._prog.high_accuracy
+
+    def get_compact_mode(self):
+        return self._compact_mode
+
+    def get_dim(self):
+        return self._prog.n_eq
+
+    @property
+    def state(self):
+        return self._state
+
+    @property
+    def pars(self):
+        return self._pars
+
+    @property
+    def time(self):
+        return self._t_hi
+
+    @property
+    def dtime(self):
+        return self._t_hi, self._t_lo
+
+    def set_time(self, t):
+        t = np.broadcast_to(np.asarray(t, dtype=np.float64), (self._batch_size,)) if np.ndim(t) == 0 else np.asarray(t)
+        if t.size != self._batch_size:
+            raise ValueError("Invalid number of new times specified in a Taylor integrator in batch mode: the batch "
+                             "size is %d, but the number of specified times is %d" % (self._batch_size, t.size))
+        self._t_hi = np.array(t, dtype=np.float64)
+        self._t_lo = np.zeros(self._batch_size)
+
+    def set_dtime(self, hi, lo):
+        hi = np.broadcast_to(np.asarray(hi, dtype=np.float64), (self._batch_size,)).copy()
+        lo = np.broadcast_to(np.asarray(lo, dtype=np.float64), (self._batch_size,)).copy()
+        # Normalise like set_dtime(), src/taylor_adaptive_batch.cpp:2180-2232.
+        if np.any(np.abs(hi) < np.abs(lo)):
+            raise ValueError("The first component of a double-length time must not be smaller in magnitude than the "
+                             "second")
+        s = hi + lo
+        self._t_lo = (hi - s) + lo
+        self._t_hi = s
+
+    @property
+    def last_h(self):
+        return self._last_h
+
+    @property
+    def step_res(self):
+        return self._step_res
+
+    @property
+    def propagate_res(self):
+        return self._prop_res
+
+    @property
+    def tc(self):
+        return self._tc
+
+    def get_decomposition_str(self):
+        return self._prog.dc_str()
+
+    # --- stepping ------------------------------------------------------------------------------
+    def _push(self):
+        self._b.upload(self._state, self._pars if self._prog.n_pars else None, self._t_hi, self._t_lo)
+
+    def _pull(self, wtc):
+        self._state, self._t_hi, self._t_lo, self._last_h = self._b.download()
+        if wtc:
+            self._tc = self._b.tc()
+
+    def step(self, max_delta_ts=None, write_tc=False):
+        if max_delta_ts is not None:
+            m = np.asarray(max_delta_ts, dtype=np.float64)
+            if m.size != self._batch_size:
+                raise ValueError("Invalid number of max timesteps specified in a Taylor integrator in batch mode: the "
+                                 "batch size is %d, but the number of specified timesteps is %d"
+                                 % (self._batch_size, m.size))
+            if np.any(np.isnan(m)):
+                raise ValueError("Cannot use a nan max_delta_t in the step() function of an adaptive Taylor "
+                                 "integrator in batch mode")
+            max_delta_ts = m
+        self._push()
+        self._b.step(max_delta_ts, backward=False, write_tc=write_tc)
+        self._pull(write_tc)
+        oc, h = self._b.step_res()
+        self._step_res = list(zip(oc.tolist(), h.tolist()))
+
+    def step_backward(self, write_tc=False):
+        self._push()
+        self._b.step(None, backward=True, write_tc=write_tc)
+        self._pull(write_tc)
+        oc, h = self._b.step_res()
+        self._step_res = list(zip(oc.tolist(), h.tolist()))
+
+    def propagate_until(self, ts, max_steps=0, max_delta_t=None, write_tc=False, callback=None, c_output=False):
+        if callback is not None or c_output:
+            raise NotImplementedError("Callbacks and continuous output are not supported by the fused propagate kernel")
+        n = self._batch_size
+        if np.ndim(ts) == 0:
+            th, tl = np.full(n, float(ts)), None
+        elif isinstance(ts, tuple):
+            th, tl = np.asarray(ts[0], dtype=np.float64), np.asarray(ts[1], dtype=np.float64)
+        else:
+            th, tl = np.asarray(ts, dtype=np.float64), None
+        if th.size != n:
+            raise ValueError("Invalid number of time limits specified in a Taylor integrator in batch mode: the batch "
+                             "size is %d, but the number of specified time limits is %d" % (n, th.size))
+        if not (np.all(np.isfinite(self._t_hi)) and np.all(np.isfinite(self._t_lo))):
+            raise ValueError("Cannot invoke the propagate_until() function of an adaptive Taylor integrator in batch "
+                             "mode if one of the current times is not finite")
+        if max_delta_t is not None:
+            md = np.broadcast_to(np.asarray(max_delta_t, dtype=np.float64), (n,)) if np.ndim(max_delta_t) == 0 else \
+                np.asarray(max_delta_t, dtype=np.float64)
+            if md.size != n:
+                raise ValueError("Invalid number of max timesteps specified in a Taylor integrator in batch mode: the "
+                                 "batch size is %d, but the number of specified timesteps is %d" % (n, md.size))
+            max_delta_t = md
+        self._push()
+        self._b.propagate_until(th, tl, max_delta_t, max_steps, write_tc)
+        self._pull(write_tc)
+        oc, mn, mx, ns = self._b.prop_res()
+        self._prop_res = list(zip(oc.tolist(), mn.tolist(), mx.tolist(), ns.tolist()))
+
+    def propagate_for(self, delta_ts, **kw):
+        n = self._batch_size
+        d = np.broadcast_to(np.asarray(delta_ts, dtype=np.float64), (n,)) if np.ndim(delta_ts) == 0 else \
+            np.asarray(delta_ts, dtype=np.float64)
+        if d.size != n:
+            raise ValueError("Invalid number of time intervals specified in a Taylor integrator in batch mode: the "
+                             "batch size is %d, but the number of specified time intervals is %d" % (n, d.size))
+        hi, lo = _dfloat_add(self._t_hi, self._t_lo, d, np.zeros(n))
+        self.propagate_until((hi, lo), **kw)
+
+    def update_d_output(self, t, rel_time=False):
+        """Dense output at time(s) t from the last written tc (src/taylor_adaptive_batch.cpp:2251-2327)."""
+        n = self._batch_size
+        t = np.broadcast_to(np.asarray(t, dtype=np.float64), (n,))
+        if rel_time:
+            tau = t
+        else:
+            # tau = t - (time - last_h), in double-length arithmetic.
+            hi, lo = _dfloat_add(self._t_hi, self._t_lo, -self._last_h, np.zeros(n))
+            tau, _ = _dfloat_add(t, np.zeros(n), -hi, -lo)
+        return self._b.d_output(tau)
+
+
+def _eft_knuth(a, b):
+    x = a + b
+    z = x - a
+    y = (a - (x - z)) + (b - z)
+    return x, y
+
+
+def _eft_dekker(a, b):
+    x = a + b
+    y = (a - x) + b
+    return x, y
+
+
+def _dfloat_add(ahi, alo, bhi, blo):
+    """include/heyoka/detail/dfloat.hpp:151-169."""
+    xh, yh = _eft_knuth(ahi, bhi)
+    xl, yl = _eft_knuth(alo, blo)
+    u, v = _eft_dekker(xh, yh + xl)
+    u, v = _eft_dekker(u, v + yl)
+    return u, v

@@ -1,0 +1,88 @@
+"""Build the native library (host C++ + sm_100a CUDA) in-tree with nvcc.
+
+    python -m heyoka_b200.build [--force]
+
+Output: heyoka_b200/lib/libheyoka_b200.so (git-ignored, travels to the GPU box with the snapshot).
+nvcc cross-compiles for sm_100a without a GPU. -fmad=false: the only fused multiply-adds are the
+explicit fma() calls in csrc/recurrences.cuh (see the floating-point contract there).
+"""
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+CSRC = os.path.join(HERE, "csrc")
+LIBDIR = os.path.join(HERE, "lib")
+OBJDIR = os.path.join(ROOT, "build", "obj")
+LIB = os.path.join(LIBDIR, "libheyoka_b200.so")
+
+HOST_SOURCES = ["expression.cpp", "decompose.cpp", "model.cpp", "lower.cpp", "capi_host.cpp", "taylor_adaptive_batch.cpp"]
+CUDA_SOURCES = ["batch.cu"]
+
+NVCC_ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+COMMON = ["-std=c++17", "-O3", "-I" + os.path.join(ROOT, "include"), "-I" + CSRC]
+
+
+def _nvcc():
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found: cannot build heyoka_b200 (there is no CPU fallback)")
+
+
+def _deps_newer(target, deps):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
+
+
+def _all_headers():
+    hdrs = []
+    for base in (CSRC, os.path.join(ROOT, "include")):
+        for dp, _, fns in os.walk(base):
+            hdrs += [os.path.join(dp, f) for f in fns if f.endswith((".h", ".hpp", ".cuh"))]
+    return hdrs
+
+
+def build(force=False, verbose=True):
+    nvcc = _nvcc()
+    os.makedirs(LIBDIR, exist_ok=True)
+    os.makedirs(OBJDIR, exist_ok=True)
+    hdrs = _all_headers()
+    objs = []
+    rebuilt = False
+    for src in HOST_SOURCES + CUDA_SOURCES:
+        path = os.path.join(CSRC, src)
+        if not os.path.exists(path):
+            continue
+        obj = os.path.join(OBJDIR, src + ".o")
+        objs.append(obj)
+        if force or _deps_newer(obj, [path] + hdrs):
+            if src.endswith(".cu"):
+                cmd = [nvcc] + NVCC_ARCH + COMMON + ["-lineinfo", "-fmad=false", "-Xcompiler", "-fPIC",
+                                                       "-Xptxas", "-v", "-c", path, "-o", obj]
+            else:
+                cmd = [nvcc] + COMMON + ["-Xcompiler", "-fPIC,-Wall,-Wextra", "-c", path, "-o", obj]
+            if verbose:
+                print(" ".join(cmd), flush=True)
+            res = subprocess.run(cmd, capture_output=True, text=True)
+            if verbose and res.stderr:
+                print(res.stderr, file=sys.stderr)
+            if res.returncode != 0:
+                raise RuntimeError("compilation of %s failed:\n%s\n%s" % (src, res.stdout, res.stderr))
+            rebuilt = True
+    if rebuilt or not os.path.exists(LIB):
+        cmd = [nvcc] + NVCC_ARCH + ["-shared", "-o", LIB] + objs
+        if verbose:
+            print(" ".join(cmd), flush=True)
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError("link failed:\n%s\n%s" % (res.stdout, res.stderr))
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv))

@@ -1,0 +1,21 @@
+// Shared between the C ABI translation units: error plumbing.
+#ifndef HEYOKA_B200_CSRC_CAPI_COMMON_HPP
+#define HEYOKA_B200_CSRC_CAPI_COMMON_HPP
+
+#include <stdexcept>
+#include <string>
+
+namespace heyoka_b200::detail
+{
+
+struct cuda_error : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+
+void set_last_error(const std::string &);
+// To be called inside a catch (...) block: stores the message, returns the HY_ERR_* code.
+int translate_exception();
+
+} // namespace heyoka_b200::detail
+
+#endif

@@ -1,0 +1,246 @@
+/* heyoka_b200 — C ABI of the B200-native batch Taylor integrator.
+ *
+ * This is the drop-in boundary for heyoka's taylor_adaptive_batch<double> hot path
+ * (bluescarni/heyoka @ 9c91f71). The reference funnels every step through three JIT-compiled C
+ * function pointers (include/heyoka/detail/ta_jit_data.hpp:35-43):
+ *
+ *   void step   (double *state, const double *pars, const double *time, double *h_inout, double *tc_or_null);
+ *   void step_cm(..., void *tape);
+ *   void d_out_f(double *out, const double *tc, const double *h);
+ *
+ * called from src/taylor_adaptive_batch.cpp:691-698 (step) and :2288,2324 (dense output). The
+ * functions below keep those semantics with three differences: (i) the arrays live in device
+ * memory (HBM) owned by an hy_batch, (ii) the per-lane host bookkeeping that follows the JIT call
+ * in the reference (double-length time update, finiteness scan, outcome; src/taylor_adaptive_batch.cpp:702-727)
+ * and the whole propagate_until() loop (:1372-1527) run inside the kernels, (iii) instead of LLVM IR
+ * the Taylor decomposition is lowered to a flat opcode program (hy_program) interpreted by
+ * hand-written sm_100a kernels. No LLVM, no JIT, no CPU fallback: every compute entry point fails
+ * with HY_ERR_CUDA if no CUDA device is usable.
+ *
+ * All functions return HY_OK (0) or a negative error code; hy_last_error() returns a thread-local
+ * message. No exceptions cross this boundary. All arrays are batch-innermost, exactly like the
+ * reference's host layout: state[var * batch + lane], pars[par * batch + lane]
+ * (src/taylor_adaptive_batch.cpp:679, src/taylor_01.cpp:227-230), tc[(var * (order + 1) + o) * batch + lane]
+ * (src/taylor_00.cpp:574-580).
+ */
+#ifndef HEYOKA_B200_H
+#define HEYOKA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HY_OK 0
+#define HY_ERR_INVALID_ARG (-1) /* maps to std::invalid_argument in the C++ shim */
+#define HY_ERR_NOT_IMPLEMENTED (-2) /* maps to heyoka::not_implemented_error (include/heyoka/exceptions.hpp:19) */
+#define HY_ERR_CUDA (-3) /* CUDA runtime failure / no device */
+#define HY_ERR_OVERFLOW (-4) /* maps to std::overflow_error */
+
+const char *hy_last_error(void);
+const char *hy_version(void);
+
+/* taylor_outcome (include/heyoka/taylor.hpp:142-155): int64, success = -2^32 - 1, ... */
+#define HY_OUTCOME_SUCCESS (-4294967297LL)
+#define HY_OUTCOME_STEP_LIMIT (-4294967298LL)
+#define HY_OUTCOME_TIME_LIMIT (-4294967299LL)
+#define HY_OUTCOME_ERR_NF_STATE (-4294967300LL)
+#define HY_OUTCOME_CB_STOP (-4294967301LL)
+
+/* ------------------------------------------------------------------------------------------------
+ * A. Symbolic front end: opaque expression handles.
+ *    Replaces: include/heyoka/expression.hpp (construction API), src/expression_ops.cpp,
+ *    src/math/{sum,prod,pow,sin,cos,tanh,exp,log,time}.cpp builders.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct hy_ex hy_ex;
+
+hy_ex *hy_ex_num(double v);
+hy_ex *hy_ex_var(const char *name);
+hy_ex *hy_ex_par(uint32_t idx);
+hy_ex *hy_ex_time(void);
+/* op: '+', '-', '*', '/' (binary, src/expression_ops.cpp:56-92), 'n' = unary minus (b ignored), '^' = pow. */
+hy_ex *hy_ex_binary(char op, const hy_ex *a, const hy_ex *b);
+/* name: "sin","cos","tanh","exp","log","sqrt","square" (unary); "sum","prod" (n-ary). */
+hy_ex *hy_ex_func(const char *name, const hy_ex *const *args, uint32_t n_args);
+hy_ex *hy_ex_copy(const hy_ex *);
+void hy_ex_free(hy_ex *);
+/* Writes a NUL-terminated rendering into buf (truncated to buf_len); returns the full length. */
+size_t hy_ex_str(const hy_ex *, char *buf, size_t buf_len);
+
+/* Model builders (src/model/nbody.cpp:53-173, src/model/pendulum.cpp:24-29, src/model/ffnn.cpp:70-142).
+ * They fill lhs[i]/rhs[i] (caller frees each with hy_ex_free). */
+int hy_model_nbody(uint32_t n, const double *masses, uint32_t n_masses, double G, hy_ex **lhs, hy_ex **rhs /* 6n each */);
+int hy_model_pendulum(double g, double l, hy_ex **lhs, hy_ex **rhs /* 2 each */);
+/* act: per layer 0 = identity, 1 = tanh, 2 = sin, 3 = exp. nn_wb == NULL -> weights/biases are par[0..). */
+int hy_model_ffnn(const hy_ex *const *inputs, uint32_t n_in, const uint32_t *nn_hidden, uint32_t n_hidden, uint32_t n_out,
+                  const int *act, const double *nn_wb, uint32_t n_wb, hy_ex **out /* n_out */);
+
+/* ------------------------------------------------------------------------------------------------
+ * B. Program: the lowered Taylor decomposition.
+ *    Replaces: taylor_decompose_sys() src/taylor_01.cpp:847-1008 (host, restated), the compact-mode
+ *    call tables of src/taylor_02.cpp:830-953 and the LLVM emission of src/taylor_00/01/02.cpp.
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Argument reference: bits 31-30 kind, bits 29-0 index. */
+#define HY_REF_VAR 0u /* index of a u variable          */
+#define HY_REF_NUM 1u /* index into the constant pool   */
+#define HY_REF_PAR 2u /* index of a runtime parameter   */
+#define HY_REF(kind, idx) (((uint32_t)(kind) << 30) | (uint32_t)(idx))
+#define HY_REF_KIND(r) ((r) >> 30)
+#define HY_REF_IDX(r) ((r) & 0x3fffffffu)
+
+/* One elementary operation = the definition of one u variable. The recurrence each opcode runs is
+ * documented next to its device implementation (heyoka_b200/csrc/recurrences.cuh) with the reference
+ * file:line it restates. Suffix letters give the kinds of (a, b): V = u variable index, N = constant
+ * pool index, P = parameter index. */
+enum hy_opcode {
+    HY_OP_SUM = 0,  /* a = offset into args[], b = number of terms (<= 8 after splitting)      */
+    HY_OP_SUM_SQ,   /* a = offset into args[], b = number of terms                             */
+    HY_OP_SUB_VV,
+    HY_OP_SUB_VN,
+    HY_OP_SUB_NV,
+    HY_OP_SUB_VP,
+    HY_OP_SUB_PV,
+    HY_OP_NEG,      /* prod(-1, a)                                                             */
+    HY_OP_MUL_VV,
+    HY_OP_MUL_NV,   /* a = constant, b = variable                                              */
+    HY_OP_MUL_PV,   /* a = parameter, b = variable                                             */
+    HY_OP_DIV_VV,
+    HY_OP_DIV_NV,
+    HY_OP_DIV_PV,
+    HY_OP_DIV_VN,
+    HY_OP_DIV_VP,
+    HY_OP_SQUARE,   /* pow(a, 2)                                                               */
+    HY_OP_SQRT,     /* pow(a, 1/2)                                                             */
+    HY_OP_POW_VN,   /* pow(a, consts[b]); c = (eval_algo << 8) | n, see HY_POW_*               */
+    HY_OP_POW_VP,   /* pow(a, par[b])                                                          */
+    HY_OP_SIN,      /* a = argument, c = hidden dependency (the u variable holding cos(a))     */
+    HY_OP_COS,      /* a = argument, c = hidden dependency (the u variable holding sin(a))     */
+    HY_OP_TANH,     /* a = argument, c = hidden dependency (the u variable holding tanh(a)^2)  */
+    HY_OP_EXP,
+    HY_OP_LOG,
+    HY_OP_TIME,
+    HY_OP_CFUNC,    /* all arguments are numbers/params: a = function (hy_cfunc), b = offset into
+                       args[], c = number of arguments. Order 0: evaluate; higher orders: 0.
+                       (include/heyoka/detail/taylor_common.hpp:88-157)                        */
+    HY_OP_COUNT
+};
+
+/* Order-0 evaluation strategy of pow(x, number), src/math/pow.cpp:292-355. */
+#define HY_POW_GENERAL 0u
+#define HY_POW_POS_SMALL_INT 1u
+#define HY_POW_NEG_SMALL_INT 2u
+#define HY_POW_POS_SMALL_HALF 3u
+#define HY_POW_NEG_SMALL_HALF 4u
+
+enum hy_cfunc { HY_CF_IDENTITY = 0, HY_CF_SUM, HY_CF_PROD, HY_CF_SUB, HY_CF_DIV, HY_CF_POW, HY_CF_SUM_SQ,
+                HY_CF_SIN, HY_CF_COS, HY_CF_TANH, HY_CF_EXP, HY_CF_LOG };
+
+typedef struct hy_op {
+    uint32_t opcode;
+    uint32_t a, b, c;
+} hy_op;
+
+typedef struct hy_program_desc {
+    uint32_t n_eq;     /* number of state variables / equations                                 */
+    uint32_t n_uvars;  /* state variables + elementary u variables (ops[i] defines u_{n_eq + i}) */
+    uint32_t n_pars;   /* number of runtime parameters                                          */
+    uint32_t order;    /* Taylor order p                                                        */
+    uint32_t n_args;
+    uint32_t n_consts;
+    int32_t high_accuracy; /* 0: Horner update, 1: compensated summation (src/taylor_00.cpp:355-460) */
+    int32_t reserved;
+    const hy_op *ops;        /* n_uvars - n_eq entries, in evaluation order                     */
+    const uint32_t *args;    /* argument references for n-ary ops                               */
+    const double *consts;    /* constant pool                                                   */
+    const uint32_t *sv_defs; /* n_eq references: d(x_i)/dt is a u variable, a number or a param */
+} hy_program_desc;
+
+typedef struct hy_program hy_program;
+
+/* taylor_order_from_tol(): max(2, ceil(-ln(tol)/2 + 1)), include/heyoka/detail/taylor_common.hpp:165-191. */
+int hy_order_from_tol(double tol, uint32_t *order);
+
+/* Decompose + lower an ODE system x_i' = rhs_i. tol <= 0 selects machine epsilon
+ * (src/taylor_adaptive_batch.cpp:237-241). Unsupported functions -> HY_ERR_NOT_IMPLEMENTED. */
+int hy_program_from_sys(const hy_ex *const *lhs, const hy_ex *const *rhs, uint32_t n_eq, double tol,
+                        int high_accuracy, hy_program **out);
+/* Build from raw arrays (validated: indices in range, ops only read earlier u variables). */
+int hy_program_create(const hy_program_desc *desc, hy_program **out);
+/* Borrowed view of the program's arrays (valid until hy_program_destroy). */
+int hy_program_get_desc(const hy_program *, hy_program_desc *out);
+/* Size of the reference-shaped decomposition, n_eq + n_ops + n_eq (test/taylor_decompose.cpp:38-101). */
+uint32_t hy_program_dc_size(const hy_program *);
+/* Text dump of the decomposition ("u_5 = prod(u_1, u_3) [deps: ...]"), for diagnostics and tests. */
+size_t hy_program_dc_str(const hy_program *, char *buf, size_t buf_len);
+/* Algorithmic bytes per lane-step, SURVEY.md §8(d): B_min = 8(2 n_eq + n_pars + 7),
+ * B_tape = B_min + 16(n_uvars p + n_eq); flops = double-precision operations per lane-step. */
+int hy_program_costs(const hy_program *, double *b_min, double *b_tape, double *flops);
+void hy_program_destroy(hy_program *);
+
+/* ------------------------------------------------------------------------------------------------
+ * C. Batch: device-resident integrator state + the step / propagate kernels.
+ *    Replaces: the JIT'd `step` (src/taylor_00.cpp:712-865), step_impl() bookkeeping
+ *    (src/taylor_adaptive_batch.cpp:632-727), propagate_until_impl() (:1136-1534), d_out_f
+ *    (src/taylor_01.cpp:1015-1185), i_data buffers (src/detail/i_data.cpp).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct hy_batch hy_batch;
+
+/* device < 0: current CUDA device. Allocates state, pars, time (hi/lo), last_h, results, tc, scratch. */
+int hy_batch_create(const hy_program *, uint32_t batch, int device, hy_batch **out);
+void hy_batch_destroy(hy_batch *);
+/* cudaStream_t on which copies and kernels are enqueued (default: the legacy default stream). */
+int hy_batch_set_stream(hy_batch *, void *cuda_stream);
+int hy_batch_sync(hy_batch *);
+
+/* Host <-> device copies (any pointer may be NULL = leave untouched / don't fetch). */
+int hy_batch_upload(hy_batch *, const double *state, const double *pars, const double *t_hi, const double *t_lo);
+int hy_batch_download(hy_batch *, double *state, double *t_hi, double *t_lo, double *last_h);
+int hy_batch_download_step_res(hy_batch *, int64_t *outcome, double *h);
+int hy_batch_download_prop_res(hy_batch *, int64_t *outcome, double *min_h, double *max_h, uint64_t *n_steps);
+int hy_batch_download_tc(hy_batch *, double *tc /* n_eq * (order + 1) * batch */);
+
+/* Device pointers of the resident arrays, for zero-copy use (torch / NCCL gathers). */
+typedef struct hy_batch_ptrs {
+    double *state, *pars, *t_hi, *t_lo, *last_h, *tc, *d_out;
+    int64_t *step_outcome;
+    int64_t *prop_outcome;
+    double *prop_min_h, *prop_max_h;
+    uint64_t *prop_n_steps;
+} hy_batch_ptrs;
+int hy_batch_get_ptrs(hy_batch *, hy_batch_ptrs *out);
+
+/* One step for every lane. max_delta_t: host array of `batch` signed limits (sign = direction), or
+ * NULL for +inf (backward != 0: -inf), like step()/step_backward()/step(vec)
+ * (src/taylor_adaptive_batch.cpp:1039-1078). If max_delta_t_on_device != 0 the pointer is a device pointer. */
+int hy_batch_step(hy_batch *, const double *max_delta_t, int max_delta_t_on_device, int backward, int write_tc);
+
+/* Propagate every lane to its own final time (double-length t_final = hi + lo; lo may be NULL).
+ * max_delta_t: host array of positive per-lane limits or NULL (= +inf). max_steps == 0: unlimited.
+ * Per-lane semantics follow src/taylor_adaptive_batch.cpp:1372-1527; see DESIGN.md for the two global
+ * exits (non-finite state in any lane, iteration limit), which are reproduced by a bounded re-run.
+ * Results: hy_batch_download_prop_res(). */
+int hy_batch_propagate_until(hy_batch *, const double *t_final_hi, const double *t_final_lo, const double *max_delta_t,
+                             uint64_t max_steps, int write_tc);
+/* Same, with device-resident inputs (no host traffic): used by the bench's device-timed leg. */
+int hy_batch_propagate_until_dev(hy_batch *, const double *d_t_final_hi, const double *d_t_final_lo,
+                                 const double *d_max_delta_t, uint64_t max_steps, int write_tc, int *any_nf_or_limit);
+
+/* Dense output from the last written tc: out[var * batch + lane] = sum_o tc[var][o][lane] * tau[lane]^o
+ * (src/taylor_01.cpp:1015-1185; tau relative to the start of the last step). out/tau are host arrays. */
+int hy_batch_d_output(hy_batch *, const double *tau, double *out);
+
+/* Kernel launch statistics since creation (bench.py's gpu_launches). */
+int hy_batch_launch_count(const hy_batch *, uint64_t *n_launches);
+/* Name + average duration bookkeeping is done by the caller with CUDA events on the batch's stream. */
+
+/* Tuning knobs (0 = keep default): threads per block and blocks per SM of the persistent kernels. */
+int hy_batch_set_launch_config(hy_batch *, uint32_t block_threads, uint32_t blocks_per_sm);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif

@@ -1,0 +1,28 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+if os.path.dirname(os.path.abspath(__file__)) not in sys.path:
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: test needs a CUDA device (run on the B200 box)")
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _built_library():
+    # The native library must exist before anything imports heyoka_b200 (nvcc cross-compiles without a GPU).
+    lib = os.path.join(ROOT, "heyoka_b200", "lib", "libheyoka_b200.so")
+    if not os.path.exists(lib):
+        sys.path.insert(0, os.path.join(ROOT, "heyoka_b200"))
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("hb_build", os.path.join(ROOT, "heyoka_b200", "build.py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        mod.build(verbose=False)
+    yield

@@ -1,0 +1,143 @@
+"""Loader for the CPU oracle (oracle/taylor_oracle.c) — TEST INFRASTRUCTURE.
+
+Only tests/, __graft_entry__.smoke() and bench.py's CPU legs import this. The library is built by
+oracle/Makefile into oracle/_build/ (two ISA levels; the one matching the host CPU is loaded). If the
+prebuilt library is missing it is built on the spot with gcc (a one-second compile).
+"""
+import ctypes as C
+import os
+import subprocess
+from concurrent.futures import ThreadPoolExecutor
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+
+PAIRWISE = 1  # default-mode (non-compact) summation order of the reference
+FMA = 2       # sequential + fused multiply-add: the order the CUDA kernels use
+SEQ = 0       # compact-mode summation order, no contraction
+
+_dp = C.POINTER(C.c_double)
+
+
+def _cpu_has_avx512():
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("flags"):
+                    fl = line.split()
+                    return all(x in fl for x in ("avx512f", "avx512dq", "avx512bw", "avx512vl", "avx512cd"))
+    except OSError:
+        pass
+    return False
+
+
+def isa_level():
+    return "v4" if _cpu_has_avx512() else "v3"
+
+
+def _load():
+    path = os.path.join(ORACLE_DIR, "_build", "liboracle_%s.so" % isa_level())
+    src = os.path.join(ORACLE_DIR, "taylor_oracle.c")
+    if not os.path.exists(path) or os.path.getmtime(path) < os.path.getmtime(src):
+        subprocess.run(["make", "-C", ORACLE_DIR], check=True, capture_output=True)
+    return C.CDLL(path)
+
+
+lib = _load()
+
+
+def _desc_ptr(program):
+    return C.byref(program.desc)
+
+
+def _arr(a):
+    return a.ctypes.data_as(_dp)
+
+
+def jet(program, state, pars=None, t_hi=None, lane=0, mode=FMA):
+    """Full tape of one lane: array [order + 1, n_uvars]."""
+    P = program
+    state = np.ascontiguousarray(state, dtype=np.float64).reshape(P.n_eq, -1)
+    batch = state.shape[1]
+    pars = np.zeros((max(P.n_pars, 1), batch)) if pars is None else np.ascontiguousarray(pars, dtype=np.float64)
+    t_hi = np.zeros(batch) if t_hi is None else np.ascontiguousarray(t_hi, dtype=np.float64)
+    out = np.empty((P.order + 1, P.n_uvars))
+    rc = lib.oracle_jet_w1(_desc_ptr(P), C.c_uint32(batch), _arr(state), _arr(pars), _arr(t_hi), C.c_uint32(lane),
+                           _arr(out), C.c_int(mode))
+    assert rc == 0
+    return out
+
+
+class OracleIntegrator:
+    """CPU restatement of taylor_adaptive_batch<double>: same arrays, same semantics, lock-step lanes."""
+
+    def __init__(self, program, state, batch, pars=None, time=0.0, mode=FMA, width=1):
+        P = self.P = program
+        self.n = batch
+        self.mode = mode
+        self.w = width
+        self.state = np.array(state, dtype=np.float64).reshape(P.n_eq, batch).copy()
+        self.pars = np.zeros((max(P.n_pars, 1), batch)) if pars is None else \
+            np.array(pars, dtype=np.float64).reshape(P.n_pars, batch).copy()
+        self.t_hi = np.broadcast_to(np.asarray(time, dtype=np.float64), (batch,)).copy()
+        self.t_lo = np.zeros(batch)
+        self.last_h = np.zeros(batch)
+        self.tc = np.zeros((P.n_eq, P.order + 1, batch))
+        self.step_outcome = np.zeros(batch, dtype=np.int64)
+        self.prop_outcome = np.zeros(batch, dtype=np.int64)
+        self.min_h = np.zeros(batch)
+        self.max_h = np.zeros(batch)
+        self.n_steps = np.zeros(batch, dtype=np.uint64)
+
+    def _fn(self, name):
+        return getattr(lib, "%s_w%d" % (name, self.w))
+
+    def step(self, max_delta_t=None, backward=False, write_tc=False, lanes=None):
+        n = self.n
+        if max_delta_t is None:
+            max_delta_t = np.full(n, -np.inf if backward else np.inf)
+        mdt = np.ascontiguousarray(np.broadcast_to(max_delta_t, (n,)), dtype=np.float64)
+        b, e = lanes if lanes is not None else (0, n)
+        rc = self._fn("oracle_step_full")(
+            _desc_ptr(self.P), C.c_uint32(n), C.c_uint32(b), C.c_uint32(e), _arr(self.state), _arr(self.pars),
+            _arr(self.t_hi), _arr(self.t_lo), _arr(mdt), _arr(self.last_h),
+            self.step_outcome.ctypes.data_as(C.POINTER(C.c_int64)), _arr(self.tc) if write_tc else None,
+            C.c_int(self.mode))
+        assert rc == 0
+
+    def propagate_until(self, t_hi, t_lo=None, max_delta_t=None, max_steps=0, write_tc=False, lockstep=True,
+                        n_threads=1):
+        n = self.n
+        th = np.ascontiguousarray(np.broadcast_to(t_hi, (n,)), dtype=np.float64)
+        tl = None if t_lo is None else np.ascontiguousarray(np.broadcast_to(t_lo, (n,)), dtype=np.float64)
+        md = None if max_delta_t is None else np.ascontiguousarray(np.broadcast_to(max_delta_t, (n,)), dtype=np.float64)
+        fn = self._fn("oracle_propagate_until")
+
+        def run(b, e):
+            rc = fn(_desc_ptr(self.P), C.c_uint32(n), C.c_uint32(b), C.c_uint32(e), _arr(self.state), _arr(self.pars),
+                    _arr(self.t_hi), _arr(self.t_lo), _arr(th), None if tl is None else _arr(tl),
+                    None if md is None else _arr(md), C.c_uint64(max_steps), _arr(self.last_h),
+                    self.prop_outcome.ctypes.data_as(C.POINTER(C.c_int64)), _arr(self.min_h), _arr(self.max_h),
+                    self.n_steps.ctypes.data_as(C.POINTER(C.c_uint64)), _arr(self.tc) if write_tc else None,
+                    C.c_int(self.mode), C.c_int(1 if lockstep else 0))
+            assert rc == 0
+
+        if n_threads <= 1 or lockstep:
+            run(0, n)
+        else:
+            # Disjoint lane ranges (multiples of the vector width) on a thread pool; ctypes drops the GIL.
+            w = max(self.w, 1)
+            per = -(-n // n_threads)
+            per = -(-per // w) * w
+            ranges = [(b, min(b + per, n)) for b in range(0, n, per)]
+            with ThreadPoolExecutor(max_workers=n_threads) as ex:
+                list(ex.map(lambda r: run(*r), ranges))
+
+    def d_output(self, tau):
+        tau = np.ascontiguousarray(np.broadcast_to(tau, (self.n,)), dtype=np.float64)
+        out = np.empty((self.P.n_eq, self.n))
+        rc = lib.oracle_d_output_w1(_desc_ptr(self.P), C.c_uint32(self.n), _arr(self.tc), _arr(tau), _arr(out))
+        assert rc == 0
+        return out
