@@ -47,7 +47,7 @@ class expression:
 
     def __del__(self):
         h = getattr(self, "_h", None)
-        if h:
+        if h and lib is not None:
             lib.hy_ex_free(h)
             self._h = None
 
@@ -245,7 +245,7 @@ class Program:
 
     def __del__(self):
         h = getattr(self, "_h", None)
-        if h:
+        if h and lib is not None:
             lib.hy_program_destroy(h)
             self._h = None
 
@@ -288,7 +288,7 @@ class Batch:
 
     def __del__(self):
         h = getattr(self, "_h", None)
-        if h:
+        if h and lib is not None:
             lib.hy_batch_destroy(h)
             self._h = None
 

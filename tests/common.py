@@ -1,0 +1,123 @@
+"""Shared helpers for the parity tests: systems named by BASELINE.json's configs + tolerances."""
+import json
+import os
+
+import numpy as np
+
+import heyoka_b200 as hb
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+EPS = np.finfo(np.float64).eps
+
+
+def golden(name):
+    with open(os.path.join(GOLDEN, name)) as f:
+        return json.load(f)
+
+
+def approx(a, b, tol_eps):
+    """test/test_utils.hpp:68-80 `approximately`: |a - b| <= eps * tol * max(|a|, |b|) (absolute near zero)."""
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    scale = np.maximum(np.maximum(np.abs(a), np.abs(b)), 1e-300)
+    return np.all(np.abs(a - b) <= EPS * tol_eps * scale)
+
+
+def sig_digits_equal(val, printed, digits=6):
+    """A value printed with `digits` significant digits matches `val`."""
+    val, printed = np.asarray(val, dtype=np.float64), np.asarray(printed, dtype=np.float64)
+    tol = 0.6 * 10.0 ** (np.floor(np.log10(np.maximum(np.abs(printed), 1e-300))) - (digits - 1))
+    return np.all(np.abs(val - printed) <= tol + 1e-300)
+
+
+def decimals_equal(val, printed, decimals=6):
+    """A value printed in fixed notation with `decimals` decimals matches `val`."""
+    val, printed = np.asarray(val, dtype=np.float64), np.asarray(printed, dtype=np.float64)
+    return np.all(np.abs(val - printed) <= 0.6 * 10.0 ** (-decimals))
+
+
+# ---- systems ------------------------------------------------------------------------------------
+def sys_pendulum():
+    x, v = hb.make_vars("x", "v")
+    return [(x, v), (v, -9.8 * hb.sin(x))]
+
+
+def sys_tutorial():
+    """x' = v, v' = cos(t) - par[0]*v - sin(x) (tutorial/batch_mode.cpp:52-62)."""
+    x, v = hb.make_vars("x", "v")
+    return [(x, v), (v, hb.cos(hb.time) - hb.par[0] * v - hb.sin(x))]
+
+
+OUTER_SS_MASSES = [1.00000597682, 1 / 1047.355, 1 / 3501.6, 1 / 22869., 1 / 19314., 7.4074074e-09]
+OUTER_SS_G = 0.01720209895 * 0.01720209895 * 365 * 365
+
+# benchmark/outer_ss_long_term_batch.cpp:75-94 (positions in AU, velocities in AU/day, scaled by 365 below).
+_OUTER_SS_IC = [
+    # Sun.
+    -4.06428567034226e-3, -6.08813756435987e-3, -1.66162304225834e-6, +6.69048890636161e-6, -6.33922479583593e-6,
+    -3.13202145590767e-9,
+    # Jupiter.
+    +3.40546614227466e+0, +3.62978190075864e+0, +3.42386261766577e-2, -5.59797969310664e-3, +5.51815399480116e-3,
+    -2.66711392865591e-6,
+    # Saturn.
+    +6.60801554403466e+0, +6.38084674585064e+0, -1.36145963724542e-1, -4.17354020307064e-3, +3.99723751748116e-3,
+    +1.67206320571441e-5,
+    # Uranus.
+    +1.11636331405597e+1, +1.60373479057256e+1, +3.61783279369958e-1, -3.25884806151064e-3, +2.06438412905916e-3,
+    -2.17699042180559e-5,
+    # Neptune.
+    -3.01777243405203e+1, +1.91155314998064e+0, -1.53887595621042e-1, -2.17471785045538e-4, -3.11361111025884e-3,
+    +3.58344705491441e-5,
+    # Pluto.
+    -2.13858977531573e+1, +3.20719104739886e+1, +2.49245689556096e+0, -1.76936577252484e-3, -2.06720938381724e-3,
+    +6.58091931493844e-4,
+]
+
+
+def outer_ss_ic():
+    ic = np.array(_OUTER_SS_IC).reshape(6, 6).copy()
+    ic[:, 3:] *= 365.
+    return ic.reshape(-1)
+
+
+def sys_outer_ss():
+    return hb.model.nbody(6, masses=OUTER_SS_MASSES, Gconst=OUTER_SS_G)
+
+
+def outer_ss_batch_state(batch, perturb=1e-3, seed=42):
+    """Perturbed copies of the outer Solar System (rule of benchmark/outer_ss_long_term_batch.cpp:103-108:
+    x += |x| * U(-1, 1) * perturb, applied in memory order var-major / batch-minor; numpy RNG instead of
+    std::mt19937 since only the distribution matters for throughput and parity uses the same arrays)."""
+    rng = np.random.default_rng(seed)
+    ic = outer_ss_ic()
+    st = np.repeat(ic[:, None], batch, axis=1)
+    st += np.abs(st) * rng.uniform(-1., 1., st.shape) * perturb
+    return st
+
+
+def sys_two_body():
+    return hb.model.nbody(2, masses=[1., 0.])
+
+
+def two_body_batch_state(batch, seed=7):
+    """Circular orbits of radius a ~ U(0.5, 2) around a unit mass at rest (benchmark/two_body_step_batch.cpp:41-55)."""
+    rng = np.random.default_rng(seed)
+    a = rng.uniform(0.5, 2.0, batch)
+    st = np.zeros((12, batch))
+    st[6] = a              # x_1
+    st[10] = a ** -0.5     # vy_1
+    return st
+
+
+def kep_to_cart(a, e, inc, om, Om, nu, mu):
+    """test/test_utils.hpp:204-233 (Keplerian elements -> Cartesian state)."""
+    p = a * (1 - e * e)
+    r = p / (1 + e * np.cos(nu))
+    x_p, y_p = r * np.cos(nu), r * np.sin(nu)
+    h = np.sqrt(mu * p)
+    vx_p, vy_p = -mu / h * np.sin(nu), mu / h * (e + np.cos(nu))
+    cO, sO, co, so, ci, si = np.cos(Om), np.sin(Om), np.cos(om), np.sin(om), np.cos(inc), np.sin(inc)
+    R = np.array([[cO * co - sO * so * ci, -cO * so - sO * co * ci], [sO * co + cO * so * ci, -sO * so + cO * co * ci],
+                  [so * si, co * si]])
+    pos = R @ np.array([x_p, y_p])
+    vel = R @ np.array([vx_p, vy_p])
+    return pos, vel

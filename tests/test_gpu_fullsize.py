@@ -1,0 +1,81 @@
+"""Full-size configurations of BASELINE.json, checked through size-independent properties (the oracle
+is too slow at these sizes) plus a random sample of lanes against the oracle."""
+import numpy as np
+import pytest
+
+import heyoka_b200 as hb
+import oracle
+from common import (OUTER_SS_G, OUTER_SS_MASSES, outer_ss_batch_state, sys_outer_ss, sys_two_body,
+                    two_body_batch_state)
+
+pytestmark = pytest.mark.gpu
+
+
+def nbody_energy(st, masses, G):
+    """Total energy per lane; st is [6 * n_bodies, batch] with (x, y, z, vx, vy, vz) per body."""
+    n = len(masses)
+    pos = st.reshape(n, 6, -1)[:, :3]
+    vel = st.reshape(n, 6, -1)[:, 3:]
+    e = sum(0.5 * masses[i] * np.sum(vel[i] ** 2, axis=0) for i in range(n))
+    for i in range(n):
+        for j in range(i + 1, n):
+            e -= G * masses[i] * masses[j] / np.sqrt(np.sum((pos[i] - pos[j]) ** 2, axis=0))
+    return e
+
+
+def test_two_body_single_step_2pow24():
+    """two_body_step_batch: 16,777,216 lanes, one step. Circular orbits of radius a around a unit mass:
+    after the step the massless body is still on the circle, has advanced by h * a^-3/2 radians, and the
+    chosen h scales like the orbital period."""
+    batch = 1 << 24
+    st = two_body_batch_state(batch)
+    a = st[6].copy()
+    P = hb.Program(sys_two_body())
+    b = hb.Batch(P, batch)
+    b.upload(st, None, np.zeros(batch), np.zeros(batch))
+    b.step()
+    new, t_hi, t_lo, h = b.download()
+    oc, _ = b.step_res()
+    assert np.all(oc == hb.taylor_outcome.success)
+    assert np.array_equal(t_hi, h) and np.all(t_lo == 0)
+    r = np.sqrt(new[6] ** 2 + new[7] ** 2)
+    assert np.max(np.abs(r / a - 1)) < 1e-14
+    ang = np.arctan2(new[7], new[6])
+    assert np.max(np.abs(ang - h * a ** -1.5)) < 1e-14
+    assert np.all(new[:6] == 0) and np.all(new[8] == 0)
+    # h / period is the same for every lane up to rounding (scale invariance of the estimator in the
+    # relative-tolerance regime a > 1; in the absolute regime a <= 1 it only depends on a)
+    big = a > 1.
+    ratio = h[big] * a[big] ** -1.5
+    assert np.ptp(ratio) / np.mean(ratio) < 1e-12
+    # a random sample of lanes against the oracle
+    idx = np.random.default_rng(0).choice(batch, 64, replace=False)
+    o = oracle.OracleIntegrator(P, st[:, idx], 64, mode=oracle.FMA)
+    o.step()
+    assert np.max(np.abs(o.last_h / h[idx] - 1)) < 1e-13
+    assert np.max(np.abs(o.state - new[:, idx])) < 1e-13
+
+
+def test_outer_ss_2pow20_energy_and_sample():
+    """outer_ss_long_term_batch at the full batch of 1,048,576 lanes, short horizon (5 years): every lane
+    conserves energy to rounding, lands exactly on the final time, and a random sample of lanes matches
+    the oracle step for step."""
+    batch = 1 << 20
+    st = outer_ss_batch_state(batch)
+    P = hb.Program(sys_outer_ss(), high_accuracy=True)
+    b = hb.Batch(P, batch)
+    b.upload(st, None, np.zeros(batch), np.zeros(batch))
+    b.propagate_until(5.0)
+    new, t_hi, t_lo, _ = b.download()
+    oc, mn, mx, ns = b.prop_res()
+    assert np.all(oc == hb.taylor_outcome.time_limit)
+    assert np.all(t_hi == 5.0)
+    assert ns.min() >= 10 and ns.max() <= 30
+    e0 = nbody_energy(st, OUTER_SS_MASSES, OUTER_SS_G)
+    e1 = nbody_energy(new, OUTER_SS_MASSES, OUTER_SS_G)
+    assert np.max(np.abs(e1 / e0 - 1)) < 5e-15 * 20
+    idx = np.random.default_rng(1).choice(batch, 48, replace=False)
+    o = oracle.OracleIntegrator(P, st[:, idx], 48, mode=oracle.FMA)
+    o.propagate_until(5.0)
+    assert np.array_equal(o.n_steps, ns[idx])
+    assert np.max(np.abs(o.state - new[:, idx]) / np.maximum(np.abs(o.state), 1e-6)) < 1e-12

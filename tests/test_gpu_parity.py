@@ -1,0 +1,254 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs.
+
+Tolerances. All arithmetic of the jet is + - * / sqrt and explicit fma in the same order on both sides
+(oracle mode FMA), so the Taylor coefficients of N-body systems agree to the last bit or two; the
+differences come from the math library (pow in the step-size estimate, sin/cos/tanh/exp/log at order 0:
+CUDA libdevice vs glibc, both <= 2 ulp). Stated bounds: one step 1e-13 relative (100-1000 eps, like
+test/taylor_adaptive_batch.cpp:143), long propagations 1e-12 relative on the final state with IDENTICAL
+step counts (BASELINE.json north_star).
+"""
+import numpy as np
+import pytest
+
+import heyoka_b200 as hb
+import oracle
+from common import (OUTER_SS_G, OUTER_SS_MASSES, approx, decimals_equal, golden, outer_ss_batch_state, outer_ss_ic,
+                    sig_digits_equal, sys_outer_ss, sys_pendulum, sys_tutorial, sys_two_body, two_body_batch_state)
+
+pytestmark = pytest.mark.gpu
+
+OC = {"success": hb.taylor_outcome.success, "time_limit": hb.taylor_outcome.time_limit}
+
+
+def rel_err(a, b, floor=1e-6):
+    a, b = np.asarray(a), np.asarray(b)
+    return np.max(np.abs(a - b) / np.maximum(np.abs(b), floor))
+
+
+def test_tutorial_batch_mode_gpu():
+    """doc/tut_batch_mode.rst end to end on the GPU (same fixture that pins the oracle)."""
+    g = golden("tut_batch_mode.json")
+    ta = hb.taylor_adaptive_batch(sys_tutorial(), [g["x0"], g["v0"]], 4, pars=[g["alpha"]])
+    assert ta.get_order() == 20
+
+    ta.step()
+    assert [r[0] for r in ta.step_res] == [OC[r["outcome"]] for r in g["first_step"]]
+    assert sig_digits_equal([r[1] for r in ta.step_res], [r["h"] for r in g["first_step"]])
+    assert decimals_equal(ta.state, g["states"][0])
+    assert decimals_equal(ta.time, g["times"][0])
+
+    ta.step(g["clamped_step_limits"])
+    assert [r[0] for r in ta.step_res] == [OC[r["outcome"]] for r in g["clamped_step"]]
+    assert [r[1] for r in ta.step_res] == g["clamped_step_limits"]
+    assert decimals_equal(ta.state, g["states"][1])
+
+    ta.propagate_for(g["propagate_for"]["delta_ts"])
+    res = g["propagate_for"]["res"]
+    assert [r[0] for r in ta.propagate_res] == [OC[r["outcome"]] for r in res]
+    assert [r[3] for r in ta.propagate_res] == [r["n_steps"] for r in res]
+    assert sig_digits_equal([r[1] for r in ta.propagate_res], [r["min_h"] for r in res])
+    assert sig_digits_equal([r[2] for r in ta.propagate_res], [r["max_h"] for r in res])
+    assert decimals_equal(ta.state, g["states"][2])
+    assert decimals_equal(ta.time, g["times"][2])
+
+    ta.propagate_until(g["propagate_until"]["ts"])
+    res = g["propagate_until"]["res"]
+    assert [r[3] for r in ta.propagate_res] == [r["n_steps"] for r in res]
+    assert decimals_equal(ta.state, g["states"][3])
+    assert np.all(ta.time == np.array(g["propagate_until"]["ts"]))
+
+    ta.step(write_tc=True)
+    assert sig_digits_equal(ta.tc, g["tc_after_final_step"], 7)
+
+
+def _step_parity(sys, state, batch, pars=None, time=0.0, ha=False, n_steps=3, tol=1e-13, max_delta_t=None):
+    P = hb.Program(sys, high_accuracy=ha)
+    o = oracle.OracleIntegrator(P, state, batch, pars=pars, time=time, mode=oracle.FMA)
+    ta = hb.taylor_adaptive_batch(sys, state, batch, pars=pars, time=time, high_accuracy=ha)
+    for _ in range(n_steps):
+        o.step(max_delta_t, write_tc=True)
+        ta.step(max_delta_t, write_tc=True)
+        assert rel_err(ta.last_h, o.last_h) < tol
+        assert rel_err(ta.state, o.state) < tol
+        assert rel_err(ta.tc, o.tc, floor=1e-30) < 1e-9  # high orders are tiny and cancel: looser relative bound
+        assert np.array_equal([r[0] for r in ta.step_res], o.step_outcome)
+        assert rel_err(ta.time, o.t_hi) < tol
+        # keep the two sides on the same trajectory: identical inputs for the next step
+        ta._state[:] = o.state
+        ta._t_hi[:] = o.t_hi
+        ta._t_lo[:] = o.t_lo
+
+
+@pytest.mark.parametrize("ha", [False, True])
+@pytest.mark.parametrize("batch", [1, 4, 33, 70])
+def test_step_parity_pendulum(ha, batch):
+    rng = np.random.default_rng(1)
+    st = np.stack([rng.uniform(-1, 1, batch), rng.uniform(-1, 1, batch)])
+    _step_parity(sys_pendulum(), st, batch, ha=ha)
+
+
+@pytest.mark.parametrize("ha", [False, True])
+def test_step_parity_tutorial_system(ha):
+    rng = np.random.default_rng(2)
+    batch = 37
+    st = np.stack([rng.uniform(-1, 1, batch), rng.uniform(1, 2, batch)])
+    pars = rng.uniform(0.05, 0.2, (1, batch))
+    tm = rng.uniform(0, 10, batch)
+    _step_parity(sys_tutorial(), st, batch, pars=pars, time=tm, ha=ha)
+
+
+@pytest.mark.parametrize("ha", [False, True])
+def test_step_parity_two_body(ha):
+    _step_parity(sys_two_body(), two_body_batch_state(50), 50, ha=ha)
+
+
+@pytest.mark.parametrize("ha", [False, True])
+@pytest.mark.parametrize("batch", [3, 45])
+def test_step_parity_outer_ss(ha, batch):
+    _step_parity(sys_outer_ss(), outer_ss_batch_state(batch), batch, ha=ha, n_steps=2)
+
+
+def test_step_backward_and_limits():
+    st = outer_ss_batch_state(8)
+    P = hb.Program(sys_outer_ss())
+    o = oracle.OracleIntegrator(P, st, 8, mode=oracle.FMA)
+    ta = hb.taylor_adaptive_batch(sys_outer_ss(), st, 8)
+    o.step(backward=True)
+    ta.step_backward()
+    assert np.all(ta.last_h < 0)
+    assert rel_err(ta.last_h, o.last_h) < 1e-13 and rel_err(ta.state, o.state) < 1e-13
+    lim = np.array([1e-3, -1e-3, 0.0, 1e3, -1e3, 2e-3, 5e-4, -5e-4])
+    o.step(lim)
+    ta.step(lim)
+    assert np.array_equal([r[0] for r in ta.step_res], o.step_outcome)
+    assert rel_err(ta.state, o.state) < 1e-13
+    assert np.all(ta.last_h[[0, 1, 2, 5, 6, 7]] == lim[[0, 1, 2, 5, 6, 7]])
+
+
+@pytest.mark.parametrize("ha", [False, True])
+def test_propagate_parity_outer_ss(ha):
+    """100 years of the perturbed outer Solar System: identical step counts, final state to 1e-12."""
+    batch = 40
+    st = outer_ss_batch_state(batch)
+    P = hb.Program(sys_outer_ss(), high_accuracy=ha)
+    o = oracle.OracleIntegrator(P, st, batch, mode=oracle.FMA)
+    ta = hb.taylor_adaptive_batch(sys_outer_ss(), st, batch, high_accuracy=ha)
+    o.propagate_until(100.)
+    ta.propagate_until(100.)
+    assert np.all(ta.time == 100.)
+    assert np.array_equal([r[3] for r in ta.propagate_res], o.n_steps)
+    assert np.all(np.array([r[0] for r in ta.propagate_res]) == hb.taylor_outcome.time_limit)
+    assert rel_err(ta.state, o.state) < 1e-12
+    assert rel_err([r[1] for r in ta.propagate_res], o.min_h) < 1e-12
+    assert rel_err([r[2] for r in ta.propagate_res], o.max_h) < 1e-12
+    # backwards to where we started: test/back_and_forth.cpp style round trip.
+    ta.propagate_until(0.)
+    assert np.all(ta.time == 0.)
+    assert rel_err(ta.state, st) < 1e-11
+
+
+def test_propagate_exact_step_counts_gpu():
+    """test/taylor_adaptive_batch.cpp:586-598 on the GPU."""
+    ta = hb.taylor_adaptive_batch(sys_pendulum(), [[0.05, 0.06], [0.025, 0.026]], 2)
+    ta2 = hb.taylor_adaptive_batch(sys_pendulum(), [[0.05, 0.06], [0.025, 0.026]], 2)
+    ta.propagate_until([10., 11.], max_delta_t=[1e-4, 5e-5])
+    ta2.propagate_until([10., 11.])
+    assert np.all(ta.time == [10., 11.])
+    assert [r[3] for r in ta.propagate_res] == [100000, 220000]
+    assert all(r[0] == hb.taylor_outcome.time_limit for r in ta.propagate_res)
+    assert approx(ta.state, ta2.state, 1000.)
+    # backwards with propagate_for (:640-652)
+    ta.propagate_for([-10., -11.], max_delta_t=[1e-4, 5e-5])
+    assert np.all(ta.time == [0., 0.])
+    assert [r[3] for r in ta.propagate_res] == [100000, 220000]
+
+
+def test_propagate_per_lane_times_and_dfloat():
+    batch = 35
+    rng = np.random.default_rng(5)
+    st = np.stack([rng.uniform(-1, 1, batch), rng.uniform(-1, 1, batch)])
+    t0 = rng.uniform(-5, 5, batch)
+    tf = t0 + rng.uniform(-20, 20, batch)
+    tf[3] = t0[3]  # zero-length propagation
+    P = hb.Program(sys_pendulum())
+    o = oracle.OracleIntegrator(P, st, batch, time=t0, mode=oracle.FMA)
+    ta = hb.taylor_adaptive_batch(sys_pendulum(), st, batch, time=t0)
+    o.propagate_until(tf)
+    ta.propagate_until(tf)
+    assert np.array_equal(ta.time, tf) and np.array_equal(o.t_hi, tf)
+    assert np.array_equal([r[3] for r in ta.propagate_res], o.n_steps)
+    assert ta.propagate_res[3][3] == 0
+    assert rel_err(ta.state, o.state) < 1e-12
+
+
+def test_global_exits_match_reference_semantics():
+    """max_steps counts iterations and turns EVERY outcome into step_limit; a non-finite lane stops EVERY
+    lane at that iteration (src/taylor_adaptive_batch.cpp:1462-1467, :1516-1526). Checked against the
+    oracle's lock-step loop."""
+    batch = 6
+    st = outer_ss_batch_state(batch)
+    P = hb.Program(sys_outer_ss())
+
+    # iteration limit
+    o = oracle.OracleIntegrator(P, st, batch, mode=oracle.FMA)
+    ta = hb.taylor_adaptive_batch(sys_outer_ss(), st, batch)
+    tf = np.array([0.5, 100., 100., 2.0, 100., 100.])
+    o.propagate_until(tf, max_steps=7)
+    ta.propagate_until(tf, max_steps=7)
+    assert np.all(o.prop_outcome == hb.taylor_outcome.step_limit)
+    assert [r[0] for r in ta.propagate_res] == [hb.taylor_outcome.step_limit] * batch
+    assert np.array_equal([r[3] for r in ta.propagate_res], o.n_steps)
+    assert rel_err(ta.time, o.t_hi) < 1e-13 and rel_err(ta.state, o.state) < 1e-12
+
+    # non-finite state: put two bodies of lane 2 on top of each other after a few steps' worth of time by
+    # making lane 2 start from a collision configuration (distance 0 -> r^-3 = inf -> NaN).
+    st2 = st.copy()
+    st2[6:9, 2] = st2[0:3, 2]
+    o = oracle.OracleIntegrator(P, st2, batch, mode=oracle.FMA)
+    ta = hb.taylor_adaptive_batch(sys_outer_ss(), st2, batch)
+    o.propagate_until(100.)
+    ta.propagate_until(100.)
+    assert int(o.prop_outcome[2]) == hb.taylor_outcome.err_nf_state
+    assert np.array_equal([r[0] for r in ta.propagate_res], o.prop_outcome)
+    assert np.array_equal([r[3] for r in ta.propagate_res], o.n_steps)
+    ok = [0, 1, 3, 4, 5]
+    assert rel_err(ta.state[:, ok], o.state[:, ok]) < 1e-12
+    assert rel_err(ta.time[ok], o.t_hi[ok]) < 1e-13
+
+
+def test_dense_output():
+    batch = 9
+    st = outer_ss_batch_state(batch)
+    P = hb.Program(sys_outer_ss(), high_accuracy=True)
+    o = oracle.OracleIntegrator(P, st, batch, mode=oracle.FMA)
+    ta = hb.taylor_adaptive_batch(sys_outer_ss(), st, batch, high_accuracy=True)
+    o.step(write_tc=True)
+    ta.step(write_tc=True)
+    tau = 0.37 * o.last_h
+    ref = o.d_output(tau)
+    got = ta.update_d_output(tau, rel_time=True)
+    assert rel_err(got, ref) < 1e-13
+    # at tau = h the dense output reproduces the new state; at tau = 0 the old one
+    assert rel_err(ta.update_d_output(ta.last_h, rel_time=True), ta.state) < 1e-13
+    assert rel_err(ta.update_d_output(0., rel_time=True), st) < 1e-15
+
+
+def test_raw_program_interface_matches():
+    """hy_program_create() from raw arrays gives the same results as the symbolic path."""
+    P = hb.Program(sys_two_body())
+    d = P.desc
+    import ctypes as C
+    n_ops = P.n_uvars - P.n_eq
+    args = np.ctypeslib.as_array(C.cast(d.args, C.POINTER(C.c_uint32)), shape=(max(d.n_args, 1),))[:d.n_args]
+    consts = np.ctypeslib.as_array(C.cast(d.consts, C.POINTER(C.c_double)), shape=(max(d.n_consts, 1),))[:d.n_consts]
+    sv = np.ctypeslib.as_array(C.cast(d.sv_defs, C.POINTER(C.c_uint32)), shape=(P.n_eq,))
+    P2 = hb.Program.from_arrays(P.n_eq, P.n_uvars, P.n_pars, P.order, P.ops_array(), args, consts, sv)
+    st = two_body_batch_state(10)
+    res = []
+    for prog in (P, P2):
+        b = hb.Batch(prog, 10)
+        b.upload(st, None, np.zeros(10), np.zeros(10))
+        b.step()
+        res.append(b.download()[0])
+    assert np.array_equal(res[0], res[1])
+    assert n_ops == 21 - 12

@@ -1,0 +1,143 @@
+"""Pin the CPU oracle against the reference's own known answers (CPU only, no CUDA calls).
+
+Fixtures:
+  1. doc/tut_batch_mode.rst printed output (tests/golden/tut_batch_mode.json)
+  2. README.md scalar pendulum (tests/golden/readme_pendulum.json)
+  4. test/timestep_check.cpp:33-86 (step-size formula recomputed from the Taylor coefficients)
+  5. test/taylor_adaptive_batch.cpp:586-598 (exact step counts under max_delta_t, exact final times)
+All three summation modes of the oracle must satisfy them, like the reference sweeps compact_mode/opt_level.
+"""
+import numpy as np
+import pytest
+
+import heyoka_b200 as hb
+import oracle
+from common import (approx, decimals_equal, golden, outer_ss_ic, sig_digits_equal, sys_outer_ss, sys_pendulum, sys_tutorial)
+
+MODES = [oracle.PAIRWISE, oracle.SEQ, oracle.FMA]
+OC = {"success": hb.taylor_outcome.success, "time_limit": hb.taylor_outcome.time_limit}
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_readme_pendulum(mode):
+    g = golden("readme_pendulum.json")
+    P = hb.Program(sys_pendulum())
+    assert P.order == 20
+    o = oracle.OracleIntegrator(P, [g["x0"], g["v0"]], 1, mode=mode)
+    o.propagate_until(g["t"])
+    assert o.t_hi[0] == 10.0
+    assert sig_digits_equal(o.state[0, 0], g["x"])
+    assert sig_digits_equal(o.state[1, 0], g["v"])
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_tutorial_batch_mode(mode):
+    g = golden("tut_batch_mode.json")
+    P = hb.Program(sys_tutorial())
+    assert (P.n_eq, P.n_pars, P.order) == (2, 1, 20)
+    o = oracle.OracleIntegrator(P, [g["x0"], g["v0"]], 4, pars=[g["alpha"]], mode=mode)
+
+    # step()
+    o.step()
+    assert [int(x) for x in o.step_outcome] == [OC[r["outcome"]] for r in g["first_step"]]
+    assert sig_digits_equal(o.last_h, [r["h"] for r in g["first_step"]])
+    assert decimals_equal(o.state, g["states"][0])
+    assert decimals_equal(o.t_hi, g["times"][0])
+
+    # step(max_delta_ts)
+    o.step(g["clamped_step_limits"])
+    assert [int(x) for x in o.step_outcome] == [OC[r["outcome"]] for r in g["clamped_step"]]
+    assert np.all(o.last_h == np.array(g["clamped_step_limits"]))
+    assert decimals_equal(o.state, g["states"][1])
+    assert decimals_equal(o.t_hi, g["times"][1])
+
+    # propagate_for({10, 11, 12, 13}): final time in double-length arithmetic.
+    hi, lo = hb._dfloat_add(o.t_hi, o.t_lo, np.array(g["propagate_for"]["delta_ts"]), np.zeros(4))
+    o.propagate_until(hi, lo)
+    res = g["propagate_for"]["res"]
+    assert [int(x) for x in o.prop_outcome] == [OC[r["outcome"]] for r in res]
+    assert [int(x) for x in o.n_steps] == [r["n_steps"] for r in res]          # 34, 38, 41, 44
+    assert sig_digits_equal(o.min_h, [r["min_h"] for r in res])
+    assert sig_digits_equal(o.max_h, [r["max_h"] for r in res])
+    assert decimals_equal(o.state, g["states"][2])
+    assert decimals_equal(o.t_hi, g["times"][2])
+
+    # propagate_until({20, 21, 22, 23})
+    o.propagate_until(g["propagate_until"]["ts"])
+    res = g["propagate_until"]["res"]
+    assert [int(x) for x in o.n_steps] == [r["n_steps"] for r in res]          # 40, 38, 35, 34
+    assert sig_digits_equal(o.min_h, [r["min_h"] for r in res])
+    assert sig_digits_equal(o.max_h, [r["max_h"] for r in res])
+    assert decimals_equal(o.state, g["states"][3])
+    assert np.all(o.t_hi == np.array(g["propagate_until"]["ts"]))
+
+    # step(true): the full order-20 array of Taylor coefficients, [var][order][batch].
+    o.step(write_tc=True)
+    assert sig_digits_equal(o.tc, g["tc_after_final_step"], 7)
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_exact_step_counts_under_max_delta_t(mode):
+    """test/taylor_adaptive_batch.cpp:586-598: max_delta_t = {1e-4, 5e-5} up to t = {10, 11} takes exactly
+    100000 / 220000 non-zero steps and lands exactly on the final times."""
+    P = hb.Program(sys_pendulum())
+    o = oracle.OracleIntegrator(P, [[0.05, 0.06], [0.025, 0.026]], 2, mode=mode)
+    o.propagate_until([10., 11.], max_delta_t=[1e-4, 5e-5])
+    assert np.all(o.t_hi == [10., 11.])
+    assert [int(x) for x in o.n_steps] == [100000, 220000]
+    assert np.all(o.prop_outcome == hb.taylor_outcome.time_limit)
+    # ... and agrees with the unclamped propagation to 1000 eps (same test, :600-603).
+    o2 = oracle.OracleIntegrator(P, [[0.05, 0.06], [0.025, 0.026]], 2, mode=mode)
+    o2.propagate_until([10., 11.])
+    assert approx(o.state, o2.state, 1000.)
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("ha", [False, True])
+def test_timestep_formula(mode, ha):
+    """test/timestep_check.cpp:33-86: h recomputed from the Taylor coefficients with Jorba's formula."""
+    P = hb.Program(sys_outer_ss(), high_accuracy=ha)
+    assert (P.n_eq, P.n_uvars, P.order) == (36, 234, 20)
+    o = oracle.OracleIntegrator(P, outer_ss_ic(), 1, mode=mode)
+    order = P.order
+    for _ in range(10):
+        o.step(write_tc=True)
+        assert int(o.step_outcome[0]) == hb.taylor_outcome.success
+        tc = o.tc[:, :, 0]
+        max_abs_state = np.max(np.abs(tc[:, 0]))
+        max_abs_o = np.max(np.abs(tc[:, order]))
+        max_abs_om1 = np.max(np.abs(tc[:, order - 1]))
+        num = 1. if max_abs_state <= 1 else max_abs_state
+        rho_o = (num / max_abs_o) ** (1. / order)
+        rho_om1 = (num / max_abs_om1) ** (1. / (order - 1))
+        rho_m = min(rho_o, rho_om1)
+        h = rho_m * np.exp(-7. / 10 / (order - 1)) / (np.exp(1.) * np.exp(1.))
+        assert approx(o.last_h[0], h, 100.)
+
+
+def test_modes_agree_outer_ss():
+    """The three summation modes agree to rounding over a few hundred steps (the reference's own
+    compact-vs-default comparisons use 100-1000 eps)."""
+    P = hb.Program(sys_outer_ss(), high_accuracy=True)
+    res = []
+    for mode in MODES:
+        o = oracle.OracleIntegrator(P, outer_ss_ic(), 1, mode=mode)
+        o.propagate_until(100.)
+        res.append((o.state.copy(), int(o.n_steps[0])))
+    assert res[0][1] == res[1][1] == res[2][1]
+    for s, _ in res[1:]:
+        assert np.max(np.abs(s - res[0][0]) / np.maximum(np.abs(res[0][0]), 1e-3)) < 1e-12
+
+
+def test_vector_width_port_matches_scalar():
+    """The 8-lane timed port (oracle_*_w8) computes the same thing as the scalar oracle."""
+    from common import outer_ss_batch_state
+    P = hb.Program(sys_outer_ss(), high_accuracy=True)
+    st = outer_ss_batch_state(13, perturb=1e-3)
+    a = oracle.OracleIntegrator(P, st, 13, mode=oracle.FMA, width=1)
+    b = oracle.OracleIntegrator(P, st, 13, mode=oracle.FMA, width=8)
+    a.propagate_until(20.)
+    b.propagate_until(20., lockstep=False, n_threads=2)
+    assert np.array_equal(a.n_steps, b.n_steps)
+    assert np.max(np.abs(a.state - b.state) / np.maximum(np.abs(a.state), 1e-3)) < 1e-13
+    assert np.all(b.t_hi == 20.)
