@@ -137,10 +137,20 @@ def cpu_sample_lanes(args, cores):
 
 
 def host_cores():
+    """Usable host cores: the affinity mask, capped by the cgroup CPU quota (the GPU boxes show 128 logical CPUs
+    but run under a 16-CPU quota; oversubscribing it only adds scheduling noise)."""
     try:
-        return len(os.sched_getaffinity(0))
+        n = len(os.sched_getaffinity(0))
     except AttributeError:
-        return os.cpu_count() or 1
+        n = os.cpu_count() or 1
+    try:
+        with open("/sys/fs/cgroup/cpu.max") as f:
+            quota, period = f.read().split()
+        if quota != "max":
+            n = max(1, min(n, int(float(quota) / float(period) + 0.5)))
+    except (OSError, ValueError):
+        pass
+    return n
 
 
 def run_reference(args):

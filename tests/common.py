@@ -35,6 +35,15 @@ def decimals_equal(val, printed, decimals=6):
     return np.all(np.abs(val - printed) <= 0.6 * 10.0 ** (-decimals))
 
 
+def nbody_rel_err(a, b):
+    """Final-state agreement for N-body states [6 n_bodies, batch]: per body and lane, the error of the position
+    (velocity) vector relative to the norm of that vector. (Component-wise relative error is meaningless for
+    components that pass through zero, e.g. the Sun's barycentric coordinates ~1e-5 AU.)"""
+    a = np.asarray(a).reshape(-1, 2, 3, np.asarray(a).shape[-1])
+    b = np.asarray(b).reshape(a.shape)
+    return float(np.max(np.linalg.norm(a - b, axis=2) / np.linalg.norm(b, axis=2)))
+
+
 # ---- systems ------------------------------------------------------------------------------------
 def sys_pendulum():
     x, v = hb.make_vars("x", "v")

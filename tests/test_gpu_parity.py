@@ -12,7 +12,7 @@ import pytest
 
 import heyoka_b200 as hb
 import oracle
-from common import (OUTER_SS_G, OUTER_SS_MASSES, approx, decimals_equal, golden, outer_ss_batch_state, outer_ss_ic,
+from common import (OUTER_SS_G, OUTER_SS_MASSES, approx, decimals_equal, golden, nbody_rel_err, outer_ss_batch_state, outer_ss_ic,
                     sig_digits_equal, sys_outer_ss, sys_pendulum, sys_tutorial, sys_two_body, two_body_batch_state)
 
 pytestmark = pytest.mark.gpu
@@ -21,8 +21,19 @@ OC = {"success": hb.taylor_outcome.success, "time_limit": hb.taylor_outcome.time
 
 
 def rel_err(a, b, floor=1e-6):
+    """Component-wise relative error (with an absolute floor)."""
     a, b = np.asarray(a), np.asarray(b)
     return np.max(np.abs(a - b) / np.maximum(np.abs(b), floor))
+
+
+def tc_err(tc_a, tc_b, h):
+    """Error of the Taylor coefficients weighted by their contribution to the state: |d tc[o]| |h|^o relative
+    to the state's magnitude. (High-order coefficients are tiny and the result of cancelling sums: their
+    component-wise relative accuracy is ~1e-9 in the reference too, while their weight in the step is < 1 ulp.)"""
+    order = tc_a.shape[1] - 1
+    w = np.abs(h)[None, None, :] ** np.arange(order + 1)[None, :, None]
+    scale = np.maximum(np.max(np.abs(tc_b[:, 0, :]), axis=0), 1e-3)[None, None, :]
+    return np.max(np.abs(tc_a - tc_b) * w / scale)
 
 
 def test_tutorial_batch_mode_gpu():
@@ -70,7 +81,7 @@ def _step_parity(sys, state, batch, pars=None, time=0.0, ha=False, n_steps=3, to
         ta.step(max_delta_t, write_tc=True)
         assert rel_err(ta.last_h, o.last_h) < tol
         assert rel_err(ta.state, o.state) < tol
-        assert rel_err(ta.tc, o.tc, floor=1e-30) < 1e-9  # high orders are tiny and cancel: looser relative bound
+        assert tc_err(ta.tc, o.tc, o.last_h) < tol
         assert np.array_equal([r[0] for r in ta.step_res], o.step_outcome)
         assert rel_err(ta.time, o.t_hi) < tol
         # keep the two sides on the same trajectory: identical inputs for the next step
@@ -138,13 +149,13 @@ def test_propagate_parity_outer_ss(ha):
     assert np.all(ta.time == 100.)
     assert np.array_equal([r[3] for r in ta.propagate_res], o.n_steps)
     assert np.all(np.array([r[0] for r in ta.propagate_res]) == hb.taylor_outcome.time_limit)
-    assert rel_err(ta.state, o.state) < 1e-12
+    assert nbody_rel_err(ta.state, o.state) < 1e-12
     assert rel_err([r[1] for r in ta.propagate_res], o.min_h) < 1e-12
     assert rel_err([r[2] for r in ta.propagate_res], o.max_h) < 1e-12
     # backwards to where we started: test/back_and_forth.cpp style round trip.
     ta.propagate_until(0.)
     assert np.all(ta.time == 0.)
-    assert rel_err(ta.state, st) < 1e-11
+    assert nbody_rel_err(ta.state, st) < 1e-11
 
 
 def test_propagate_exact_step_counts_gpu():
