@@ -298,6 +298,18 @@ class Batch:
     def set_launch_config(self, block_threads=0, blocks_per_sm=0):
         check(lib.hy_batch_set_launch_config(self._h, int(block_threads), int(blocks_per_sm)))
 
+    def set_kernel(self, tape="auto", lanes_per_cta=0, lanes_per_thread=0, block_threads=0, blocks_per_sm=0):
+        mode = {"auto": 0, "hbm": 1, "smem": 2}[tape]
+        check(lib.hy_batch_set_kernel(self._h, mode, int(lanes_per_cta), int(lanes_per_thread), int(block_threads),
+                                      int(blocks_per_sm)))
+
+    def kernel_info(self):
+        ki = _capi.hy_kernel_info()
+        check(lib.hy_batch_get_kernel(self._h, C.byref(ki)))
+        d = {f[0]: getattr(ki, f[0]) for f in ki._fields_}
+        d["tape"] = {1: "hbm", 2: "smem"}.get(ki.tape_mode, "?")
+        return d
+
     def sync(self):
         check(lib.hy_batch_sync(self._h))
 
@@ -378,7 +390,7 @@ class taylor_adaptive_batch:
     """
 
     def __init__(self, sys, state, batch_size, time=0.0, tol=0.0, high_accuracy=False, compact_mode=False, pars=None,
-                 device=-1, t_events=None, nt_events=None, parallel_mode=False):
+                 device=-1, t_events=None, nt_events=None, parallel_mode=False, kernel=None):
         batch_size = int(batch_size)
         if batch_size == 0:
             raise ValueError("The batch size in an adaptive Taylor integrator cannot be zero")
@@ -421,6 +433,8 @@ class taylor_adaptive_batch:
         self._batch_size = batch_size
         self._compact_mode = bool(compact_mode)
         self._b = Batch(P, batch_size, device)
+        if kernel is not None:
+            self._b.set_kernel(**kernel)
         self._last_h = np.zeros(batch_size)
         self._step_res = None
         self._prop_res = None

@@ -39,6 +39,13 @@ class hy_batch_ptrs(C.Structure):
                                           "prop_outcome", "prop_min_h", "prop_max_h", "prop_n_steps")]
 
 
+class hy_kernel_info(C.Structure):
+    _fields_ = [("tape_mode", C.c_int32), ("lanes_per_cta", C.c_uint32), ("lanes_per_thread", C.c_uint32),
+                ("block_threads", C.c_uint32), ("blocks_per_sm", C.c_uint32), ("grid", C.c_uint32),
+                ("smem_bytes", C.c_uint64), ("tape_slots_per_lane", C.c_uint32), ("n_segments", C.c_uint32),
+                ("n_sms", C.c_uint32)]
+
+
 _dp = C.POINTER(C.c_double)
 _vp = C.c_void_p
 _vpp = C.POINTER(C.c_void_p)
@@ -84,6 +91,8 @@ SIGNATURES = {
     "hy_batch_d_output": (C.c_int, [_vp, _dp, _dp]),
     "hy_batch_launch_count": (C.c_int, [_vp, C.POINTER(C.c_uint64)]),
     "hy_batch_set_launch_config": (C.c_int, [_vp, C.c_uint32, C.c_uint32]),
+    "hy_batch_set_kernel": (C.c_int, [_vp, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]),
+    "hy_batch_get_kernel": (C.c_int, [_vp, C.POINTER(hy_kernel_info)]),
 }
 
 for _name, (_res, _args) in SIGNATURES.items():

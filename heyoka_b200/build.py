@@ -18,7 +18,8 @@ LIBDIR = os.path.join(HERE, "lib")
 OBJDIR = os.path.join(ROOT, "build", "obj")
 LIB = os.path.join(LIBDIR, "libheyoka_b200.so")
 
-HOST_SOURCES = ["expression.cpp", "decompose.cpp", "model.cpp", "lower.cpp", "capi_host.cpp", "taylor_adaptive_batch.cpp"]
+HOST_SOURCES = ["expression.cpp", "decompose.cpp", "model.cpp", "lower.cpp", "smem_plan.cpp", "capi_host.cpp",
+                "taylor_adaptive_batch.cpp"]
 CUDA_SOURCES = ["batch.cu"]
 
 NVCC_ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]

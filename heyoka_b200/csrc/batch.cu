@@ -1,22 +1,12 @@
-// C ABI, device part (include/heyoka_b200.h section C): device-resident batch state and the
-// persistent step / propagate kernels for sm_100a.
-//
-// Execution model ("G1"): one thread owns one lane (one ODE system of the batch); a warp
-// therefore owns 32 consecutive lanes, and every global access of the warp — state, parameters, the
-// derivative tape — is one coalesced 256-byte row. Warps are persistent: each one repeatedly claims a
-// chunk of 32 lanes from an atomic counter, runs those lanes to completion (one step, or the whole
-// propagate_until() loop), and moves on. All lanes of a warp execute the same opcode program, so the
-// interpreter's control flow is warp-uniform. The tape of a warp (n_uvars * (order + 1) rows of 32
-// doubles) lives in a per-warp slab of a scratch buffer in HBM and is re-used for every chunk.
-//
-// Replaces: the JIT'd step function (src/taylor_00.cpp:712-865), step_impl()
-// (src/taylor_adaptive_batch.cpp:632-727), propagate_until_impl() (:1136-1534), d_out_f
-// (src/taylor_01.cpp:1015-1185).
+// C ABI, device part (include/heyoka_b200.h section C): device-resident batch state, kernel selection and
+// launches. The kernels themselves are in kernels.cuh.
 #include <heyoka_b200.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <limits>
 #include <new>
 #include <stdexcept>
@@ -24,14 +14,15 @@
 #include <vector>
 
 #include <cuda_runtime.h>
-#include <math_constants.h>
 
 #include "capi_common.hpp"
 #include "device_program.cuh"
+#include "kernels.cuh"
 #include "program.hpp"
-#include "recurrences.cuh"
+#include "smem_plan.hpp"
 
 namespace hy = heyoka_b200;
+namespace dev = heyoka_b200::dev;
 using hy::detail::cuda_error;
 using hy::detail::translate_exception;
 
@@ -43,220 +34,47 @@ using hy::detail::translate_exception;
         }                                                                                                              \
     } while (0)
 
-namespace heyoka_b200::dev
+// ------------------------------------------------------------------------------------------------
+// Cooperative-kernel dispatch over (lanes per CTA, lanes per thread).
+// ------------------------------------------------------------------------------------------------
+namespace
 {
 
-// A warp's private view of its tape slab: row `slot` holds the 32 lanes' values of one coefficient.
-struct warp_tape {
-    double *base; // slab + lane-in-warp
-    __device__ __forceinline__ double ld(std::uint32_t slot) const
-    {
-        return base[static_cast<std::size_t>(slot) * 32u];
-    }
-    __device__ __forceinline__ void st(std::uint32_t slot, double v) const
-    {
-        base[static_cast<std::size_t>(slot) * 32u] = v;
-    }
+using coop_fn = void (*)(dev::program, dev::coop_tables, dev::batch, dev::run_args);
+
+struct coop_variant {
+    int L, N;
+    coop_fn step, prop;
 };
 
-__device__ __forceinline__ bool lane_state_nonfinite(const program &P, const batch &D, std::uint32_t lane)
-{
-    bool nf = false;
-    for (std::uint32_t i = 0; i < P.n_eq; ++i) {
-        nf = nf || !isfinite(D.state[static_cast<std::size_t>(i) * D.n + lane]);
+#define HY_COOP(L, N)                                                                                                  \
+    coop_variant                                                                                                       \
+    {                                                                                                                  \
+        L, N, dev::k_coop<L, N, false>, dev::k_coop<L, N, true>                                                        \
     }
-    return nf;
-}
 
-__device__ __forceinline__ std::uint32_t claim_chunk(unsigned int *counter)
+const coop_variant coop_variants[] = {HY_COOP(1, 1),  HY_COOP(2, 1),  HY_COOP(4, 1),  HY_COOP(8, 1), HY_COOP(16, 1),
+                                      HY_COOP(32, 1), HY_COOP(2, 2),  HY_COOP(4, 2),  HY_COOP(8, 2), HY_COOP(16, 2),
+                                      HY_COOP(32, 2)};
+#undef HY_COOP
+
+const coop_variant *find_variant(int L, int N)
 {
-    unsigned int c = 0;
-    if ((threadIdx.x & 31u) == 0u) {
-        c = atomicAdd(counter, 1u);
-    }
-    return __shfl_sync(0xffffffffu, c, 0);
-}
-
-// ------------------------------------------------------------------------------------------------
-// One step for every lane: step()/step_backward()/step(max_delta_ts) + the bookkeeping of step_impl().
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-    k_step(program P, batch D, double *scratch, std::size_t slab_doubles, unsigned int *counter,
-           const double *max_delta_t, double default_max_delta_t, int write_tc)
-{
-    const std::uint32_t lane_in_warp = threadIdx.x & 31u;
-    const std::size_t warp_global = (static_cast<std::size_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-    const warp_tape tape{scratch + warp_global * slab_doubles + lane_in_warp};
-    const std::uint32_t n_chunks = (D.n + 31u) / 32u;
-
-    for (std::uint32_t chunk = claim_chunk(counter); chunk < n_chunks; chunk = claim_chunk(counter)) {
-        const std::uint32_t lane_raw = chunk * 32u + lane_in_warp;
-        const bool valid = lane_raw < D.n;
-        const std::uint32_t lane = valid ? lane_raw : D.n - 1u;
-
-        const double mdt = max_delta_t != nullptr ? max_delta_t[lane] : default_max_delta_t;
-        const dfl t0{D.t_hi[lane], D.t_lo[lane]};
-        const lane_ctx c{lane, D.n, D.pars, t0.hi};
-
-        compute_jet(P, c, tape, D.state);
-        const double h = determine_h(P, tape, mdt);
-        update_state(P, c, tape, h, D.state, write_tc ? D.tc : nullptr, valid);
-
-        if (valid) {
-            const dfl nt = dfl_add(t0, dfl{h, 0.});
-            D.t_hi[lane] = nt.hi;
-            D.t_lo[lane] = nt.lo;
-            D.last_h[lane] = h;
-            const bool nf = !(isfinite(nt.hi) && isfinite(nt.lo)) || lane_state_nonfinite(P, D, lane);
-            D.step_outcome[lane]
-                = nf ? HY_OUTCOME_ERR_NF_STATE : (h == mdt ? HY_OUTCOME_TIME_LIMIT : HY_OUTCOME_SUCCESS);
+    for (const auto &v : coop_variants) {
+        if (v.L == L && v.N == N) {
+            return &v;
         }
     }
+    return nullptr;
 }
 
-// ------------------------------------------------------------------------------------------------
-// propagate_until(): every lane loops to its own final time (src/taylor_adaptive_batch.cpp:1372-1527,
-// per-lane part). iter_cap == 0: unlimited. replay != 0: the cap reproduces a global early exit, lanes
-// that hit it keep the outcome of their last step instead of step_limit.
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-    k_propagate(program P, batch D, double *scratch, std::size_t slab_doubles, unsigned int *counter,
-                const double *tf_hi, const double *tf_lo, const double *max_delta_t, unsigned long long iter_cap,
-                int replay, int write_tc, run_flags *flags)
+std::size_t coop_smem_bytes(std::uint32_t n_slots, int L)
 {
-    const std::uint32_t lane_in_warp = threadIdx.x & 31u;
-    const std::size_t warp_global = (static_cast<std::size_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-    const warp_tape tape{scratch + warp_global * slab_doubles + lane_in_warp};
-    const std::uint32_t n_chunks = (D.n + 31u) / 32u;
-
-    for (std::uint32_t chunk = claim_chunk(counter); chunk < n_chunks; chunk = claim_chunk(counter)) {
-        const std::uint32_t lane_raw = chunk * 32u + lane_in_warp;
-        const bool valid = lane_raw < D.n;
-        const std::uint32_t lane = valid ? lane_raw : D.n - 1u;
-
-        const dfl tf{tf_hi[lane], tf_lo != nullptr ? tf_lo[lane] : 0.};
-        const double mdt = max_delta_t != nullptr ? max_delta_t[lane] : CUDART_INF;
-        dfl t{D.t_hi[lane], D.t_lo[lane]};
-        dfl rem = dfl_sub(tf, t);
-        // Integration direction, fixed at the start (src/taylor_adaptive_batch.cpp:1265-1273).
-        const bool dir = dfl_ge0(rem);
-
-        unsigned long long ts_count = 0, iter = 0;
-        double min_h = CUDART_INF, max_h = 0., last_h = 0.;
-        long long outcome = HY_OUTCOME_TIME_LIMIT;
-        bool running = true;
-
-        while (__any_sync(0xffffffffu, running)) {
-            // Time limit of this step (src/taylor_adaptive_batch.cpp:1378-1387). A lane that is not
-            // running takes a zero-length step: the jet is computed (keeps the warp converged) but
-            // nothing is written.
-            const dfl lim = dir ? (dfl_lt(rem, dfl{mdt, 0.}) ? rem : dfl{mdt, 0.})
-                                : (dfl_lt(rem, dfl{-mdt, 0.}) ? dfl{-mdt, 0.} : rem);
-            const double cur_max = running ? lim.hi : 0.;
-
-            const lane_ctx c{lane, D.n, D.pars, t.hi};
-            compute_jet(P, c, tape, D.state);
-            const double h = determine_h(P, tape, cur_max);
-            const bool wr = running && valid;
-            update_state(P, c, tape, h, D.state, write_tc ? D.tc : nullptr, wr);
-
-            if (running) {
-                t = dfl_add(t, dfl{h, 0.});
-                last_h = h;
-                ++iter;
-                const bool nf = !(isfinite(t.hi) && isfinite(t.lo)) || lane_state_nonfinite(P, D, lane);
-                if (nf) {
-                    outcome = HY_OUTCOME_ERR_NF_STATE;
-                    running = false;
-                    if (valid) {
-                        atomicOr(&flags->any_nf, 1u);
-                        atomicMin(&flags->min_nf_iter, iter);
-                    }
-                } else {
-                    const bool time_limit = (h == cur_max);
-                    outcome = time_limit ? HY_OUTCOME_TIME_LIMIT : HY_OUTCOME_SUCCESS;
-                    ts_count += (h != 0.) ? 1u : 0u;
-                    if (!time_limit) {
-                        const double ah = fabs(h);
-                        min_h = fmin(min_h, ah);
-                        max_h = fmax(max_h, ah);
-                    }
-                    if (h == rem.hi) {
-                        // Final time reached (the outcome is necessarily time_limit).
-                        rem = dfl{0., 0.};
-                        running = false;
-                    } else {
-                        rem = dfl_sub(tf, t);
-                        if (iter == iter_cap) {
-                            running = false;
-                            if (!replay) {
-                                outcome = HY_OUTCOME_STEP_LIMIT;
-                                if (valid) {
-                                    atomicOr(&flags->any_limit, 1u);
-                                }
-                            }
-                        }
-                    }
-                }
-            }
-        }
-
-        if (valid) {
-            D.t_hi[lane] = t.hi;
-            D.t_lo[lane] = t.lo;
-            D.last_h[lane] = last_h;
-            D.prop_outcome[lane] = outcome;
-            D.prop_min_h[lane] = min_h;
-            D.prop_max_h[lane] = max_h;
-            D.prop_n_steps[lane] = ts_count;
-        }
-    }
+    const std::size_t extra = 3u * L * sizeof(double) + L * sizeof(int) + 16u;
+    return static_cast<std::size_t>(n_slots) * L * sizeof(double) + extra;
 }
 
-__global__ void k_fill_outcome(long long *out, std::uint32_t n, long long value)
-{
-    const std::uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) {
-        out[i] = value;
-    }
-}
-
-// Dense output (src/taylor_01.cpp:1015-1185): Horner, or compensated summation in high-accuracy mode.
-__global__ void k_d_output(std::uint32_t n_eq, std::uint32_t order, int high_accuracy, std::uint32_t n, const double *tc,
-                           const double *tau, double *out)
-{
-    const std::uint32_t lane = blockIdx.x * blockDim.x + threadIdx.x;
-    if (lane >= n) {
-        return;
-    }
-    const double h = tau[lane];
-    for (std::uint32_t i = 0; i < n_eq; ++i) {
-        const double *cf = tc + static_cast<std::size_t>(i) * (order + 1u) * n + lane;
-        double res;
-        if (!high_accuracy) {
-            res = cf[static_cast<std::size_t>(order) * n];
-            for (std::uint32_t o = 1; o <= order; ++o) {
-                res = fma(res, h, cf[static_cast<std::size_t>(order - o) * n]);
-            }
-        } else {
-            res = cf[0];
-            double comp = 0., cur_h = h;
-            for (std::uint32_t o = 1; o <= order; ++o) {
-                const double tmp = __dmul_rn(cf[static_cast<std::size_t>(o) * n], cur_h);
-                const double y = __dsub_rn(tmp, comp);
-                const double tt = __dadd_rn(res, y);
-                comp = __dsub_rn(__dsub_rn(tt, res), y);
-                res = tt;
-                cur_h = __dmul_rn(cur_h, h);
-            }
-        }
-        out[static_cast<std::size_t>(i) * n + lane] = res;
-    }
-}
-
-} // namespace heyoka_b200::dev
-
-namespace dev = heyoka_b200::dev;
+} // namespace
 
 // ------------------------------------------------------------------------------------------------
 // Host object.
@@ -265,14 +83,21 @@ struct hy_batch {
     int device = 0;
     cudaStream_t stream = nullptr;
     std::uint32_t n = 0;
-    std::uint32_t n_eq = 0, n_pars = 0, order = 0;
+    std::uint32_t n_eq = 0, n_pars = 0, order = 0, n_uvars = 0;
     bool high_accuracy = false;
 
-    // Device copies of the program arrays.
+    // Device copies of the program arrays ("hbm" encoding) ...
     uint4 *d_ops = nullptr;
     std::uint32_t *d_args = nullptr, *d_sv_defs = nullptr;
     double *d_consts = nullptr;
     dev::program prog{};
+    // ... and of the cooperative plan.
+    hy::detail::smem_plan plan;
+    uint4 *d_c_ops = nullptr;
+    std::uint32_t *d_c_args = nullptr, *d_c_sv_defs = nullptr, *d_c_dst = nullptr, *d_c_seg = nullptr,
+                  *d_c_sv_rows = nullptr;
+    dev::program c_prog{};
+    dev::coop_tables c_tabs{};
 
     // Resident arrays.
     double *d_state = nullptr, *d_pars = nullptr, *d_t_hi = nullptr, *d_t_lo = nullptr, *d_last_h = nullptr,
@@ -282,23 +107,34 @@ struct hy_batch {
     unsigned long long *d_prop_n_steps = nullptr;
 
     // Scratch.
-    double *d_scratch = nullptr; // per-warp tape slabs
+    double *d_scratch = nullptr; // per-warp tape slabs ("hbm" strategy only, allocated on demand)
     std::size_t slab_doubles = 0;
     double *d_tmp = nullptr;      // 3 * n doubles: staged per-lane inputs (t_final hi/lo, max_delta_t)
     double *d_snapshot = nullptr; // state + time snapshot for the global-exit replay
     unsigned int *d_counter = nullptr;
     dev::run_flags *d_flags = nullptr;
 
-    // Launch geometry.
-    std::uint32_t block_threads = 256, blocks_per_sm = 0, n_sms = 0, grid = 0;
+    // Kernel selection / launch geometry.
+    std::uint32_t n_sms = 0;
+    std::size_t smem_per_block_max = 0, smem_per_sm = 0;
+    int mode = 0;           // 1 = hbm, 2 = coop (resolved)
+    const coop_variant *cv = nullptr;
+    std::uint32_t c_threads = 0, c_grid = 0, c_ctas_per_sm = 0;
+    std::size_t c_smem = 0;
+    std::uint32_t h_threads = 256, h_blocks_per_sm = 0, h_grid = 0;
     std::uint64_t n_launches = 0;
 
     ~hy_batch();
     void free_all() noexcept;
-    void alloc_scratch();
     dev::batch view() const;
     template <typename T>
     T *dalloc(std::size_t count);
+    template <typename T>
+    T *dupload(const std::vector<T> &v);
+    void configure(int want_mode, int L, int N, std::uint32_t threads, std::uint32_t blocks_per_sm);
+    void setup_hbm(std::uint32_t threads, std::uint32_t blocks_per_sm);
+    bool setup_coop(int L, int N, std::uint32_t threads, std::uint32_t ctas_per_sm);
+    void launch(bool prop, const dev::run_args &R);
 };
 
 template <typename T>
@@ -309,16 +145,28 @@ T *hy_batch::dalloc(std::size_t count)
     return static_cast<T *>(p);
 }
 
+template <typename T>
+T *hy_batch::dupload(const std::vector<T> &v)
+{
+    T *p = dalloc<T>(v.size());
+    if (!v.empty()) {
+        HY_CUDA_CHECK(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    }
+    return p;
+}
+
 void hy_batch::free_all() noexcept
 {
-    for (void *p : {static_cast<void *>(d_ops), static_cast<void *>(d_args), static_cast<void *>(d_sv_defs),
-                    static_cast<void *>(d_consts), static_cast<void *>(d_state), static_cast<void *>(d_pars),
-                    static_cast<void *>(d_t_hi), static_cast<void *>(d_t_lo), static_cast<void *>(d_last_h),
-                    static_cast<void *>(d_tc), static_cast<void *>(d_d_out), static_cast<void *>(d_step_outcome),
-                    static_cast<void *>(d_prop_outcome), static_cast<void *>(d_prop_min_h),
-                    static_cast<void *>(d_prop_max_h), static_cast<void *>(d_prop_n_steps),
-                    static_cast<void *>(d_scratch), static_cast<void *>(d_tmp), static_cast<void *>(d_snapshot),
-                    static_cast<void *>(d_counter), static_cast<void *>(d_flags)}) {
+    for (void *p :
+         {static_cast<void *>(d_ops), static_cast<void *>(d_args), static_cast<void *>(d_sv_defs),
+          static_cast<void *>(d_consts), static_cast<void *>(d_c_ops), static_cast<void *>(d_c_args),
+          static_cast<void *>(d_c_sv_defs), static_cast<void *>(d_c_dst), static_cast<void *>(d_c_seg),
+          static_cast<void *>(d_c_sv_rows), static_cast<void *>(d_state), static_cast<void *>(d_pars),
+          static_cast<void *>(d_t_hi), static_cast<void *>(d_t_lo), static_cast<void *>(d_last_h),
+          static_cast<void *>(d_tc), static_cast<void *>(d_d_out), static_cast<void *>(d_step_outcome),
+          static_cast<void *>(d_prop_outcome), static_cast<void *>(d_prop_min_h), static_cast<void *>(d_prop_max_h),
+          static_cast<void *>(d_prop_n_steps), static_cast<void *>(d_scratch), static_cast<void *>(d_tmp),
+          static_cast<void *>(d_snapshot), static_cast<void *>(d_counter), static_cast<void *>(d_flags)}) {
         if (p != nullptr) {
             cudaFree(p);
         }
@@ -353,22 +201,129 @@ dev::batch hy_batch::view() const
     return b;
 }
 
-void hy_batch::alloc_scratch()
+void hy_batch::setup_hbm(std::uint32_t threads, std::uint32_t blocks_per_sm)
 {
+    if (threads != 0u) {
+        if (threads % 32u != 0u || threads > 256u) {
+            throw std::invalid_argument("block_threads must be a multiple of 32 not larger than 256");
+        }
+        h_threads = threads;
+    }
+    if (blocks_per_sm == 0u) {
+        int occ = 0;
+        HY_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dev::k_hbm<true>,
+                                                                    static_cast<int>(h_threads), 0));
+        blocks_per_sm = static_cast<std::uint32_t>(std::max(occ, 1));
+    }
+    h_blocks_per_sm = blocks_per_sm;
+
     // One slab per resident warp; never more warps than chunks of 32 lanes.
-    const std::uint32_t warps_per_block = block_threads / 32u;
+    const std::uint32_t warps_per_block = h_threads / 32u;
     const std::uint32_t n_chunks = (n + 31u) / 32u;
-    std::uint32_t blocks = n_sms * blocks_per_sm;
     const std::uint32_t needed_blocks = (n_chunks + warps_per_block - 1u) / warps_per_block;
-    blocks = std::max(1u, std::min(blocks, needed_blocks));
-    grid = blocks;
+    h_grid = std::max(1u, std::min(n_sms * h_blocks_per_sm, needed_blocks));
 
     if (d_scratch != nullptr) {
         HY_CUDA_CHECK(cudaFree(d_scratch));
         d_scratch = nullptr;
     }
-    const std::size_t n_warps = static_cast<std::size_t>(blocks) * warps_per_block;
-    d_scratch = dalloc<double>(n_warps * slab_doubles);
+    slab_doubles = static_cast<std::size_t>(n_uvars) * (order + 1u) * 32u;
+    d_scratch = dalloc<double>(static_cast<std::size_t>(h_grid) * warps_per_block * slab_doubles);
+    mode = 1;
+}
+
+// Returns false if the requested / any configuration does not fit in shared memory.
+bool hy_batch::setup_coop(int L, int N, std::uint32_t threads, std::uint32_t ctas_per_sm)
+{
+    const std::size_t reserve = 1024u; // per-block reservation of the driver
+    if (L == 0) {
+        // Maximise the lanes resident per SM; prefer >= 2 CTAs per SM (one computes while the other waits at
+        // a barrier), then the larger L (more uniform warps).
+        std::uint32_t best_lanes = 0;
+        for (const int cand : {32, 16, 8, 4, 2, 1}) {
+            const auto bytes = coop_smem_bytes(plan.n_slots, cand);
+            if (bytes > smem_per_block_max) {
+                continue;
+            }
+            const auto ctas = std::min<std::size_t>(smem_per_sm / (bytes + reserve), 8u);
+            if (ctas == 0u) {
+                continue;
+            }
+            const auto lanes = static_cast<std::uint32_t>(ctas * cand);
+            if (lanes > best_lanes) {
+                best_lanes = lanes;
+                L = cand;
+            }
+        }
+        if (L == 0) {
+            return false;
+        }
+    }
+    if (N == 0) {
+        N = 1;
+    }
+    const auto *v = find_variant(L, N);
+    if (v == nullptr) {
+        throw std::invalid_argument("Unsupported cooperative kernel configuration L = " + std::to_string(L)
+                                    + ", N = " + std::to_string(N));
+    }
+    const auto bytes = coop_smem_bytes(plan.n_slots, L);
+    if (bytes > smem_per_block_max) {
+        return false;
+    }
+    if (threads == 0u) {
+        const std::uint32_t items = std::max(plan.max_seg_width, n_eq) * static_cast<std::uint32_t>(L / N);
+        threads = std::min(256u, std::max(32u, (items + 31u) / 32u * 32u));
+    }
+    if (threads % 32u != 0u || threads > 256u || threads < static_cast<std::uint32_t>(L)) {
+        throw std::invalid_argument("Invalid number of threads for the cooperative kernel");
+    }
+    for (auto fn : {v->step, v->prop}) {
+        HY_CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes)));
+    }
+    if (ctas_per_sm == 0u) {
+        int occ = 0;
+        HY_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, v->prop, static_cast<int>(threads), bytes));
+        ctas_per_sm = static_cast<std::uint32_t>(std::max(occ, 1));
+    }
+    cv = v;
+    c_threads = threads;
+    c_smem = bytes;
+    c_ctas_per_sm = ctas_per_sm;
+    const std::uint32_t n_chunks = (n + static_cast<std::uint32_t>(L) - 1u) / static_cast<std::uint32_t>(L);
+    c_grid = std::max(1u, std::min(n_sms * ctas_per_sm, n_chunks));
+    mode = 2;
+    return true;
+}
+
+void hy_batch::configure(int want_mode, int L, int N, std::uint32_t threads, std::uint32_t blocks_per_sm)
+{
+    if (want_mode == 1) {
+        setup_hbm(threads, blocks_per_sm);
+        return;
+    }
+    if (setup_coop(L, N, threads, blocks_per_sm)) {
+        return;
+    }
+    if (want_mode == 2) {
+        throw std::invalid_argument("The derivative tape of this system (" + std::to_string(plan.n_slots)
+                                    + " doubles per lane) does not fit in shared memory");
+    }
+    setup_hbm(threads, blocks_per_sm);
+}
+
+void hy_batch::launch(bool prop, const dev::run_args &R)
+{
+    HY_CUDA_CHECK(cudaMemsetAsync(d_counter, 0, sizeof(unsigned int), stream));
+    if (mode == 2) {
+        (prop ? cv->prop : cv->step)<<<c_grid, c_threads, c_smem, stream>>>(c_prog, c_tabs, view(), R);
+    } else if (prop) {
+        dev::k_hbm<true><<<h_grid, h_threads, 0, stream>>>(prog, view(), R, d_scratch, slab_doubles);
+    } else {
+        dev::k_hbm<false><<<h_grid, h_threads, 0, stream>>>(prog, view(), R, d_scratch, slab_doubles);
+    }
+    HY_CUDA_CHECK(cudaGetLastError());
+    ++n_launches;
 }
 
 namespace
@@ -389,11 +344,6 @@ struct device_guard {
     }
 };
 
-void launch_reset(hy_batch *b)
-{
-    HY_CUDA_CHECK(cudaMemsetAsync(b->d_counter, 0, sizeof(unsigned int), b->stream));
-}
-
 // Stage a host (or device) array of n doubles into slot `slot` of d_tmp; returns the device pointer.
 const double *stage(hy_batch *b, const double *src, int on_device, std::uint32_t slot)
 {
@@ -406,17 +356,6 @@ const double *stage(hy_batch *b, const double *src, int on_device, std::uint32_t
     double *dst = b->d_tmp + static_cast<std::size_t>(slot) * b->n;
     HY_CUDA_CHECK(cudaMemcpyAsync(dst, src, sizeof(double) * b->n, cudaMemcpyHostToDevice, b->stream));
     return dst;
-}
-
-void run_propagate(hy_batch *b, const double *d_tf_hi, const double *d_tf_lo, const double *d_mdt,
-                   unsigned long long iter_cap, int replay, int write_tc)
-{
-    launch_reset(b);
-    dev::k_propagate<<<b->grid, b->block_threads, 0, b->stream>>>(b->prog, b->view(), b->d_scratch, b->slab_doubles,
-                                                                  b->d_counter, d_tf_hi, d_tf_lo, d_mdt, iter_cap,
-                                                                  replay, write_tc, b->d_flags);
-    HY_CUDA_CHECK(cudaGetLastError());
-    ++b->n_launches;
 }
 
 int propagate_impl(hy_batch *b, const double *d_tf_hi, const double *d_tf_lo, const double *d_mdt, uint64_t max_steps,
@@ -435,7 +374,16 @@ int propagate_impl(hy_batch *b, const double *d_tf_hi, const double *d_tf_lo, co
     const dev::run_flags init{0u, 0u, ~0ull};
     HY_CUDA_CHECK(cudaMemcpyAsync(b->d_flags, &init, sizeof(init), cudaMemcpyHostToDevice, b->stream));
 
-    run_propagate(b, d_tf_hi, d_tf_lo, d_mdt, max_steps, 0, write_tc);
+    dev::run_args R{};
+    R.max_delta_t = d_mdt;
+    R.tf_hi = d_tf_hi;
+    R.tf_lo = d_tf_lo;
+    R.iter_cap = max_steps;
+    R.replay = 0;
+    R.write_tc = write_tc;
+    R.flags = b->d_flags;
+    R.counter = b->d_counter;
+    b->launch(true, R);
 
     dev::run_flags fl{};
     HY_CUDA_CHECK(cudaMemcpyAsync(&fl, b->d_flags, sizeof(fl), cudaMemcpyDeviceToHost, b->stream));
@@ -446,7 +394,6 @@ int propagate_impl(hy_batch *b, const double *d_tf_hi, const double *d_tf_lo, co
         // (src/taylor_adaptive_batch.cpp:1462-1467). Lanes are independent, so re-running from the
         // snapshot with the iteration count capped at that index reproduces it exactly (the index is
         // never beyond max_steps, because the first run was capped there).
-        const unsigned long long cap = fl.min_nf_iter;
         HY_CUDA_CHECK(cudaMemcpyAsync(b->d_state, b->d_snapshot, sizeof(double) * state_doubles,
                                       cudaMemcpyDeviceToDevice, b->stream));
         HY_CUDA_CHECK(cudaMemcpyAsync(b->d_t_hi, b->d_snapshot + state_doubles, sizeof(double) * b->n,
@@ -454,7 +401,9 @@ int propagate_impl(hy_batch *b, const double *d_tf_hi, const double *d_tf_lo, co
         HY_CUDA_CHECK(cudaMemcpyAsync(b->d_t_lo, b->d_snapshot + state_doubles + b->n, sizeof(double) * b->n,
                                       cudaMemcpyDeviceToDevice, b->stream));
         HY_CUDA_CHECK(cudaMemcpyAsync(b->d_flags, &init, sizeof(init), cudaMemcpyHostToDevice, b->stream));
-        run_propagate(b, d_tf_hi, d_tf_lo, d_mdt, cap, 1, write_tc);
+        R.iter_cap = fl.min_nf_iter;
+        R.replay = 1;
+        b->launch(true, R);
         HY_CUDA_CHECK(cudaMemcpyAsync(&fl, b->d_flags, sizeof(fl), cudaMemcpyDeviceToHost, b->stream));
         HY_CUDA_CHECK(cudaStreamSynchronize(b->stream));
     }
@@ -513,25 +462,21 @@ int hy_batch_create(const hy_program *p, uint32_t batch, int device, hy_batch **
         b->n_eq = p->n_eq;
         b->n_pars = p->n_pars;
         b->order = p->order;
+        b->n_uvars = p->n_uvars;
         b->high_accuracy = p->high_accuracy;
 
         cudaDeviceProp prop{};
         HY_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
         b->n_sms = static_cast<std::uint32_t>(prop.multiProcessorCount);
+        b->smem_per_block_max = prop.sharedMemPerBlockOptin;
+        b->smem_per_sm = prop.sharedMemPerMultiprocessor;
 
-        // Program arrays.
+        // Program arrays, "hbm" encoding.
         static_assert(sizeof(hy_op) == sizeof(uint4), "hy_op must be 16 bytes");
-        b->d_ops = b->dalloc<uint4>(p->ops.size());
-        b->d_args = b->dalloc<std::uint32_t>(p->args.size());
-        b->d_consts = b->dalloc<double>(p->consts.size());
-        b->d_sv_defs = b->dalloc<std::uint32_t>(p->sv_defs.size());
-        HY_CUDA_CHECK(cudaMemcpy(b->d_ops, p->ops.data(), p->ops.size() * sizeof(hy_op), cudaMemcpyHostToDevice));
-        HY_CUDA_CHECK(cudaMemcpy(b->d_args, p->args.data(), p->args.size() * sizeof(std::uint32_t),
-                                 cudaMemcpyHostToDevice));
-        HY_CUDA_CHECK(cudaMemcpy(b->d_consts, p->consts.data(), p->consts.size() * sizeof(double),
-                                 cudaMemcpyHostToDevice));
-        HY_CUDA_CHECK(cudaMemcpy(b->d_sv_defs, p->sv_defs.data(), p->sv_defs.size() * sizeof(std::uint32_t),
-                                 cudaMemcpyHostToDevice));
+        b->d_ops = reinterpret_cast<uint4 *>(b->dupload(p->ops));
+        b->d_args = b->dupload(p->args);
+        b->d_consts = b->dupload(p->consts);
+        b->d_sv_defs = b->dupload(p->sv_defs);
 
         auto &P = b->prog;
         P.n_eq = p->n_eq;
@@ -548,6 +493,24 @@ int hy_batch_create(const hy_program *p, uint32_t batch, int device, hy_batch **
         P.args = b->d_args;
         P.consts = b->d_consts;
         P.sv_defs = b->d_sv_defs;
+
+        // Cooperative plan.
+        b->plan = hy::detail::make_smem_plan(*p);
+        b->d_c_ops = reinterpret_cast<uint4 *>(b->dupload(b->plan.ops));
+        b->d_c_args = b->dupload(b->plan.args);
+        b->d_c_sv_defs = b->dupload(b->plan.sv_defs);
+        b->d_c_dst = b->dupload(b->plan.dst);
+        b->d_c_seg = b->dupload(b->plan.seg_offsets);
+        b->d_c_sv_rows = b->dupload(b->plan.sv_rows);
+        b->c_prog = P;
+        b->c_prog.ops = b->d_c_ops;
+        b->c_prog.args = b->d_c_args;
+        b->c_prog.sv_defs = b->d_c_sv_defs;
+        b->c_tabs.dst = b->d_c_dst;
+        b->c_tabs.seg_offsets = b->d_c_seg;
+        b->c_tabs.sv_rows = b->d_c_sv_rows;
+        b->c_tabs.n_segments = b->plan.n_segments;
+        b->c_tabs.n_slots = b->plan.n_slots;
 
         // Resident arrays.
         const std::size_t n = batch;
@@ -575,13 +538,13 @@ int hy_batch_create(const hy_program *p, uint32_t batch, int device, hy_batch **
         HY_CUDA_CHECK(cudaMemset(b->d_last_h, 0, sizeof(double) * n));
         HY_CUDA_CHECK(cudaMemset(b->d_tc, 0, sizeof(double) * tc_size));
 
-        // Launch geometry: as many resident 256-thread blocks per SM as the kernel allows.
-        b->slab_doubles = static_cast<std::size_t>(p->n_uvars) * (p->order + 1u) * 32u;
-        int occ = 0;
-        HY_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dev::k_propagate,
-                                                                    static_cast<int>(b->block_threads), 0));
-        b->blocks_per_sm = static_cast<std::uint32_t>(std::max(occ, 1));
-        b->alloc_scratch();
+        // Kernel selection: HEYOKA_B200_TAPE = hbm | smem overrides the automatic choice.
+        int want = 0;
+        if (const char *env = std::getenv("HEYOKA_B200_TAPE")) {
+            const std::string s{env};
+            want = s == "hbm" ? 1 : (s == "smem" ? 2 : 0);
+        }
+        b->configure(want, 0, 0, 0, 0);
 
         *out = b;
         return HY_OK;
@@ -621,21 +584,53 @@ int hy_batch_set_launch_config(hy_batch *b, uint32_t block_threads, uint32_t blo
 {
     try {
         device_guard guard(b->device);
-        if (block_threads != 0u) {
-            if (block_threads % 32u != 0u || block_threads > 256u) {
-                throw std::invalid_argument("block_threads must be a multiple of 32 not larger than 256");
-            }
-            b->block_threads = block_threads;
-        }
-        if (blocks_per_sm != 0u) {
-            b->blocks_per_sm = blocks_per_sm;
-        }
         HY_CUDA_CHECK(cudaStreamSynchronize(b->stream));
-        b->alloc_scratch();
+        const int L = b->cv != nullptr && b->mode == 2 ? b->cv->L : 0;
+        const int N = b->cv != nullptr && b->mode == 2 ? b->cv->N : 0;
+        b->configure(b->mode, L, N, block_threads, blocks_per_sm);
         return HY_OK;
     } catch (...) {
         return translate_exception();
     }
+}
+
+int hy_batch_set_kernel(hy_batch *b, int tape_mode, uint32_t lanes_per_cta, uint32_t lanes_per_thread,
+                        uint32_t block_threads, uint32_t blocks_per_sm)
+{
+    try {
+        if (b == nullptr) {
+            throw std::invalid_argument("Null batch");
+        }
+        if (tape_mode < 0 || tape_mode > 2) {
+            throw std::invalid_argument("Invalid tape mode");
+        }
+        device_guard guard(b->device);
+        HY_CUDA_CHECK(cudaStreamSynchronize(b->stream));
+        b->configure(tape_mode, static_cast<int>(lanes_per_cta), static_cast<int>(lanes_per_thread), block_threads,
+                     blocks_per_sm);
+        return HY_OK;
+    } catch (...) {
+        return translate_exception();
+    }
+}
+
+int hy_batch_get_kernel(const hy_batch *b, hy_kernel_info *out)
+{
+    if (b == nullptr || out == nullptr) {
+        hy::detail::set_last_error("Null pointer passed to hy_batch_get_kernel()");
+        return HY_ERR_INVALID_ARG;
+    }
+    out->tape_mode = b->mode;
+    out->lanes_per_cta = b->mode == 2 ? static_cast<uint32_t>(b->cv->L) : 32u;
+    out->lanes_per_thread = b->mode == 2 ? static_cast<uint32_t>(b->cv->N) : 1u;
+    out->block_threads = b->mode == 2 ? b->c_threads : b->h_threads;
+    out->blocks_per_sm = b->mode == 2 ? b->c_ctas_per_sm : b->h_blocks_per_sm;
+    out->grid = b->mode == 2 ? b->c_grid : b->h_grid;
+    out->smem_bytes = b->mode == 2 ? static_cast<uint64_t>(b->c_smem) : 0u;
+    out->tape_slots_per_lane = b->mode == 2 ? b->plan.n_slots : b->n_uvars * (b->order + 1u);
+    out->n_segments = b->plan.n_segments;
+    out->n_sms = b->n_sms;
+    return HY_OK;
 }
 
 int hy_batch_upload(hy_batch *b, const double *state, const double *pars, const double *t_hi, const double *t_lo)
@@ -783,13 +778,14 @@ int hy_batch_step(hy_batch *b, const double *max_delta_t, int on_device, int bac
                 }
             }
         }
-        const double *d_mdt = stage(b, max_delta_t, on_device, 0);
-        const double def = backward ? -std::numeric_limits<double>::infinity() : std::numeric_limits<double>::infinity();
-        launch_reset(b);
-        dev::k_step<<<b->grid, b->block_threads, 0, b->stream>>>(b->prog, b->view(), b->d_scratch, b->slab_doubles,
-                                                                 b->d_counter, d_mdt, def, write_tc);
-        HY_CUDA_CHECK(cudaGetLastError());
-        ++b->n_launches;
+        dev::run_args R{};
+        R.max_delta_t = stage(b, max_delta_t, on_device, 0);
+        R.default_max_delta_t
+            = backward ? -std::numeric_limits<double>::infinity() : std::numeric_limits<double>::infinity();
+        R.write_tc = write_tc;
+        R.flags = b->d_flags;
+        R.counter = b->d_counter;
+        b->launch(false, R);
         return HY_OK;
     } catch (...) {
         return translate_exception();
@@ -849,8 +845,7 @@ int hy_batch_d_output(hy_batch *b, const double *tau, double *out)
     try {
         device_guard guard(b->device);
         const double *d_tau = stage(b, tau, 0, 0);
-        dev::k_d_output<<<(b->n + 127u) / 128u, 128, 0, b->stream>>>(b->n_eq, b->order, b->high_accuracy ? 1 : 0, b->n,
-                                                                     b->d_tc, d_tau, b->d_d_out);
+        dev::k_d_output<<<(b->n + 127u) / 128u, 128, 0, b->stream>>>(b->prog, b->n, b->d_tc, d_tau, b->d_d_out);
         HY_CUDA_CHECK(cudaGetLastError());
         ++b->n_launches;
         if (out != nullptr) {

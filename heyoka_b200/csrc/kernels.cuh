@@ -1,0 +1,629 @@
+// The sm_100a kernels of the batch Taylor integrator. Two storage strategies for the derivative tape:
+//
+// "coop" (shared-memory tape, the fast path): a CTA owns L lanes and keeps their tape in shared memory
+//   ([slot][L] doubles, only what is re-read at later orders keeps its history, see smem_plan.hpp). The
+//   threads of the CTA share the work of every dependency segment: one work item = one u variable x N
+//   adjacent lanes, items of a segment are independent, a __syncthreads() separates segments and orders
+//   (the same structure as the reference's compact mode, src/taylor_02.cpp:1147-1185, with its parallel
+//   mode's idea of spreading a segment over workers, src/taylor_01.cpp:1220-1247). HBM traffic per step is
+//   the state in/out plus the state variables' coefficients streamed to tc. CTAs are persistent and claim
+//   groups of L lanes from an atomic counter; a group runs its whole propagate_until() loop in one go.
+//
+// "hbm" (tape in HBM, the fallback for programs whose tape does not fit in shared memory, e.g. N = 32
+//   bodies): one thread per lane, a warp owns 32 consecutive lanes, every access is a coalesced 256-byte
+//   row of the warp's private slab; warps are persistent and claim chunks of 32 lanes.
+//
+// Replaces: the JIT'd step function (src/taylor_00.cpp:712-865), step_impl() bookkeeping
+// (src/taylor_adaptive_batch.cpp:632-727), propagate_until_impl() (:1136-1534), d_out_f
+// (src/taylor_01.cpp:1015-1185).
+#ifndef HEYOKA_B200_CSRC_KERNELS_CUH
+#define HEYOKA_B200_CSRC_KERNELS_CUH
+
+#include <cstdint>
+
+#include <cuda_runtime.h>
+#include <math_constants.h>
+
+#include "device_program.cuh"
+#include "recurrences.cuh"
+
+namespace heyoka_b200::dev
+{
+
+// Arguments of a step / propagate launch.
+struct run_args {
+    // step
+    const double *max_delta_t; // per lane, or nullptr
+    double default_max_delta_t;
+    // propagate
+    const double *tf_hi, *tf_lo;
+    unsigned long long iter_cap; // 0 = unlimited
+    int replay;
+    int write_tc;
+    run_flags *flags;
+    unsigned int *counter;
+};
+
+// Extra tables of the cooperative kernels (device pointers).
+struct coop_tables {
+    const std::uint32_t *dst;         // row reference of each op's result
+    const std::uint32_t *seg_offsets; // n_segments + 1
+    const std::uint32_t *sv_rows;     // row reference of each state variable
+    std::uint32_t n_segments;
+    std::uint32_t n_slots;
+};
+
+// ================================================================================================
+// Per-lane bookkeeping shared by both strategies.
+// ================================================================================================
+
+// State of one lane inside propagate_until() (src/taylor_adaptive_batch.cpp:1256-1273, :1402-1460).
+struct lane_prop {
+    dfl t, rem, tf;
+    double mdt, min_h, max_h, last_h;
+    unsigned long long ts_count, iter;
+    long long outcome;
+    bool dir, running;
+
+    __device__ __forceinline__ void init(const batch &D, const run_args &R, std::uint32_t lane)
+    {
+        tf = dfl{R.tf_hi[lane], R.tf_lo != nullptr ? R.tf_lo[lane] : 0.};
+        mdt = R.max_delta_t != nullptr ? R.max_delta_t[lane] : CUDART_INF;
+        t = dfl{D.t_hi[lane], D.t_lo[lane]};
+        rem = dfl_sub(tf, t);
+        dir = dfl_ge0(rem); // fixed at the start
+        ts_count = 0;
+        iter = 0;
+        min_h = CUDART_INF;
+        max_h = 0.;
+        last_h = 0.;
+        outcome = HY_OUTCOME_TIME_LIMIT;
+        running = true;
+    }
+
+    // The signed limit of the next step; 0 for a lane that is done (zero-length step, nothing written).
+    __device__ __forceinline__ double cur_max() const
+    {
+        return running ? step_limit(dir, rem, mdt) : 0.;
+    }
+
+    // After a step of size h (state already written); nf = non-finite state detected.
+    __device__ __forceinline__ void advance(double h, double used_max, bool state_nf, const run_args &R, bool valid)
+    {
+        t = dfl_add(t, dfl{h, 0.});
+        last_h = h;
+        ++iter;
+        const bool nf = !(isfinite(t.hi) && isfinite(t.lo)) || state_nf;
+        if (nf) {
+            outcome = HY_OUTCOME_ERR_NF_STATE;
+            running = false;
+            if (valid) {
+                atomicOr(&R.flags->any_nf, 1u);
+                atomicMin(&R.flags->min_nf_iter, iter);
+            }
+            return;
+        }
+        const bool time_limit = (h == used_max);
+        outcome = time_limit ? HY_OUTCOME_TIME_LIMIT : HY_OUTCOME_SUCCESS;
+        ts_count += (h != 0.) ? 1u : 0u;
+        if (!time_limit) {
+            const double ah = fabs(h);
+            min_h = fmin(min_h, ah);
+            max_h = fmax(max_h, ah);
+        }
+        if (h == rem.hi) {
+            // Final time reached (the outcome is necessarily time_limit).
+            rem = dfl{0., 0.};
+            running = false;
+        } else {
+            rem = dfl_sub(tf, t);
+            if (iter == R.iter_cap) {
+                running = false;
+                if (!R.replay) {
+                    outcome = HY_OUTCOME_STEP_LIMIT;
+                    if (valid) {
+                        atomicOr(&R.flags->any_limit, 1u);
+                    }
+                }
+            }
+        }
+    }
+
+    __device__ __forceinline__ void store(const batch &D, std::uint32_t lane) const
+    {
+        D.t_hi[lane] = t.hi;
+        D.t_lo[lane] = t.lo;
+        D.last_h[lane] = last_h;
+        D.prop_outcome[lane] = outcome;
+        D.prop_min_h[lane] = min_h;
+        D.prop_max_h[lane] = max_h;
+        D.prop_n_steps[lane] = ts_count;
+    }
+};
+
+__device__ __forceinline__ bool lane_state_nonfinite(const program &P, const batch &D, std::uint32_t lane)
+{
+    bool nf = false;
+    for (std::uint32_t i = 0; i < P.n_eq; ++i) {
+        nf = nf || !isfinite(D.state[static_cast<std::size_t>(i) * D.n + lane]);
+    }
+    return nf;
+}
+
+// ================================================================================================
+// "hbm" strategy.
+// ================================================================================================
+struct hbm_tape {
+    double *base; // warp slab + lane-in-warp
+    std::uint32_t pp1;
+    const double *pars;
+    std::uint32_t batch, lane;
+    double tm;
+
+    struct row_t {
+        double *p;
+        __device__ __forceinline__ vd<1> at(std::uint32_t o) const
+        {
+            return vd<1>{{p[static_cast<std::size_t>(o) * 32u]}};
+        }
+        __device__ __forceinline__ void set(std::uint32_t o, const vd<1> &v) const
+        {
+            p[static_cast<std::size_t>(o) * 32u] = v.v[0];
+        }
+    };
+    __device__ __forceinline__ row_t row(std::uint32_t u) const
+    {
+        return row_t{base + static_cast<std::size_t>(u) * pp1 * 32u};
+    }
+    __device__ __forceinline__ vd<1> par(std::uint32_t idx) const
+    {
+        return vd<1>{{__ldg(pars + static_cast<std::size_t>(idx) * batch + lane)}};
+    }
+    __device__ __forceinline__ vd<1> time() const
+    {
+        return vd<1>{{tm}};
+    }
+};
+
+// The whole jet of the lane: orders 0..p-1 of every u variable, order p of the state variables
+// (evaluation order of src/taylor_02.cpp:1147-1185: per order, state variables first, then the others).
+__device__ __forceinline__ void hbm_jet(const program &P, const hbm_tape &t, const double *state)
+{
+    for (std::uint32_t i = 0; i < P.n_eq; ++i) {
+        t.row(i).set(0u, vd<1>{{state[static_cast<std::size_t>(i) * t.batch + t.lane]}});
+    }
+    for (std::uint32_t n = 0; n < P.order; ++n) {
+        if (n > 0u) {
+            for (std::uint32_t i = 0; i < P.n_eq; ++i) {
+                t.row(i).set(n, sv_diff<1>(P, t, __ldg(P.sv_defs + i), n));
+            }
+        }
+        for (std::uint32_t k = 0; k < P.n_ops; ++k) {
+            const uint4 op = __ldg(P.ops + k);
+            const auto self = t.row(P.n_eq + k);
+            self.set(n, diff_op<1>(P, t, op, self, n));
+        }
+    }
+    for (std::uint32_t i = 0; i < P.n_eq; ++i) {
+        t.row(i).set(P.order, sv_diff<1>(P, t, __ldg(P.sv_defs + i), P.order));
+    }
+}
+
+__device__ __forceinline__ double hbm_determine_h(const program &P, const hbm_tape &t, double max_delta_t)
+{
+    const std::uint32_t p = P.order;
+    double m0, mp, mp1;
+    {
+        const auto r = t.row(0);
+        m0 = fabs(r.at(0).v[0]);
+        mp = fabs(r.at(p).v[0]);
+        mp1 = fabs(r.at(p - 1u).v[0]);
+    }
+    for (std::uint32_t i = 1; i < P.n_eq; ++i) {
+        const auto r = t.row(i);
+        m0 = std_max(m0, fabs(r.at(0).v[0]));
+        mp = std_max(mp, fabs(r.at(p).v[0]));
+        mp1 = std_max(mp1, fabs(r.at(p - 1u).v[0]));
+    }
+    return h_from_norms(P, m0, mp, mp1, max_delta_t);
+}
+
+__device__ __forceinline__ void hbm_update_state(const program &P, const hbm_tape &t, double h, double *state, double *tc,
+                                                 bool write)
+{
+    const std::uint32_t pp1 = P.order + 1u;
+    for (std::uint32_t i = 0; i < P.n_eq; ++i) {
+        const auto r = t.row(i);
+        const double res = eval_poly(P, [&r](std::uint32_t o) { return r.at(o).v[0]; }, h);
+        if (write) {
+            state[static_cast<std::size_t>(i) * t.batch + t.lane] = res;
+            if (tc != nullptr) {
+                for (std::uint32_t o = 0; o < pp1; ++o) {
+                    tc[(static_cast<std::size_t>(i) * pp1 + o) * t.batch + t.lane] = r.at(o).v[0];
+                }
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ std::uint32_t claim_chunk_warp(unsigned int *counter)
+{
+    unsigned int c = 0;
+    if ((threadIdx.x & 31u) == 0u) {
+        c = atomicAdd(counter, 1u);
+    }
+    return __shfl_sync(0xffffffffu, c, 0);
+}
+
+template <bool PROP>
+__global__ void __launch_bounds__(256) k_hbm(program P, batch D, run_args R, double *scratch, std::size_t slab_doubles)
+{
+    const std::uint32_t lane_in_warp = threadIdx.x & 31u;
+    const std::size_t warp_global = (static_cast<std::size_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    double *slab = scratch + warp_global * slab_doubles + lane_in_warp;
+    const std::uint32_t n_chunks = (D.n + 31u) / 32u;
+
+    for (std::uint32_t chunk = claim_chunk_warp(R.counter); chunk < n_chunks; chunk = claim_chunk_warp(R.counter)) {
+        const std::uint32_t lane_raw = chunk * 32u + lane_in_warp;
+        const bool valid = lane_raw < D.n;
+        const std::uint32_t lane = valid ? lane_raw : D.n - 1u;
+        hbm_tape tape{slab, P.order + 1u, D.pars, D.n, lane, 0.};
+
+        if constexpr (!PROP) {
+            const double mdt = R.max_delta_t != nullptr ? R.max_delta_t[lane] : R.default_max_delta_t;
+            const dfl t0{D.t_hi[lane], D.t_lo[lane]};
+            tape.tm = t0.hi;
+            hbm_jet(P, tape, D.state);
+            const double h = hbm_determine_h(P, tape, mdt);
+            hbm_update_state(P, tape, h, D.state, R.write_tc ? D.tc : nullptr, valid);
+            if (valid) {
+                const dfl nt = dfl_add(t0, dfl{h, 0.});
+                D.t_hi[lane] = nt.hi;
+                D.t_lo[lane] = nt.lo;
+                D.last_h[lane] = h;
+                const bool nf = !(isfinite(nt.hi) && isfinite(nt.lo)) || lane_state_nonfinite(P, D, lane);
+                D.step_outcome[lane]
+                    = nf ? HY_OUTCOME_ERR_NF_STATE : (h == mdt ? HY_OUTCOME_TIME_LIMIT : HY_OUTCOME_SUCCESS);
+            }
+        } else {
+            lane_prop lp;
+            lp.init(D, R, lane);
+            while (__any_sync(0xffffffffu, lp.running)) {
+                // A lane that is done takes a zero-length step: the jet is computed (the warp stays
+                // converged) but nothing is written.
+                const double cur_max = lp.cur_max();
+                tape.tm = lp.t.hi;
+                hbm_jet(P, tape, D.state);
+                const double h = hbm_determine_h(P, tape, cur_max);
+                hbm_update_state(P, tape, h, D.state, R.write_tc ? D.tc : nullptr, lp.running && valid);
+                if (lp.running) {
+                    lp.advance(h, cur_max, lane_state_nonfinite(P, D, lane), R, valid);
+                }
+            }
+            if (valid) {
+                lp.store(D, lane);
+            }
+        }
+    }
+}
+
+// ================================================================================================
+// "coop" strategy.
+// ================================================================================================
+template <int L, int N>
+struct smem_tape {
+    double *base; // shared-memory tape + first lane of this thread's group
+    const double *pars;
+    std::uint32_t batch;
+    std::uint32_t glane[N]; // global lane indices (clamped to valid lanes)
+    vd<N> tm;
+
+    struct row_t {
+        double *p;
+        std::uint32_t mask;
+        __device__ __forceinline__ vd<N> at(std::uint32_t o) const
+        {
+            const double *q = p + (o & mask) * L;
+            vd<N> r;
+            if constexpr (N == 2) {
+                const double2 x = *reinterpret_cast<const double2 *>(q);
+                r.v[0] = x.x;
+                r.v[1] = x.y;
+            } else {
+#pragma unroll
+                for (int i = 0; i < N; ++i) {
+                    r.v[i] = q[i];
+                }
+            }
+            return r;
+        }
+        __device__ __forceinline__ void set(std::uint32_t o, const vd<N> &v) const
+        {
+            double *q = p + (o & mask) * L;
+            if constexpr (N == 2) {
+                *reinterpret_cast<double2 *>(q) = make_double2(v.v[0], v.v[1]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < N; ++i) {
+                    q[i] = v.v[i];
+                }
+            }
+        }
+    };
+    // ref = (first slot << 2) | kind; kind 0: one slot (mask 0), 1: two slots on the order's parity
+    // (mask 1), 2: one slot per order (mask ~0).
+    __device__ __forceinline__ row_t row(std::uint32_t ref) const
+    {
+        const std::uint32_t kind = ref & 3u;
+        return row_t{base + (ref >> 2) * L, kind == 2u ? 0xffffffffu : kind};
+    }
+    __device__ __forceinline__ vd<N> par(std::uint32_t idx) const
+    {
+        vd<N> r;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            r.v[i] = __ldg(pars + static_cast<std::size_t>(idx) * batch + glane[i]);
+        }
+        return r;
+    }
+    __device__ __forceinline__ vd<N> time() const
+    {
+        return tm;
+    }
+};
+
+// Shared-memory layout of a cooperative CTA: tape[n_slots][L], then per-lane scalars.
+template <int L>
+struct coop_smem {
+    double *tape;
+    double *time, *cur_max, *h;
+    int *running;
+    unsigned int *chunk;
+
+    __device__ __forceinline__ coop_smem(double *smem, std::uint32_t n_slots)
+    {
+        tape = smem;
+        time = smem + static_cast<std::size_t>(n_slots) * L;
+        cur_max = time + L;
+        h = cur_max + L;
+        running = reinterpret_cast<int *>(h + L);
+        chunk = reinterpret_cast<unsigned int *>(running + L);
+    }
+    static constexpr std::size_t extra_bytes = 3u * L * sizeof(double) + L * sizeof(int) + 16u;
+};
+
+// Jet of the L lanes starting at global lane `lane0`; the state variables' coefficients go to tc.
+template <int L, int N>
+__device__ __forceinline__ void coop_jet(const program &P, const coop_tables &X, const batch &D,
+                                         const coop_smem<L> &S, std::uint32_t lane0)
+{
+    constexpr std::uint32_t G = L / N; // lane groups per CTA
+    const std::uint32_t tid = threadIdx.x, nthr = blockDim.x;
+    const std::uint32_t pp1 = P.order + 1u;
+
+    const auto make_tape = [&](std::uint32_t g) {
+        smem_tape<L, N> t;
+        t.base = S.tape + g * N;
+        t.pars = D.pars;
+        t.batch = D.n;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            const std::uint32_t l = lane0 + g * N + i;
+            t.glane[i] = l < D.n ? l : D.n - 1u;
+            t.tm.v[i] = S.time[g * N + i];
+        }
+        return t;
+    };
+    // Stream the coefficient of state variable sv at order n to tc (valid lanes only).
+    const auto write_tc = [&](std::uint32_t sv, std::uint32_t n, std::uint32_t g, const vd<N> &v) {
+        double *dst = D.tc + (static_cast<std::size_t>(sv) * pp1 + n) * D.n;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            const std::uint32_t l = lane0 + g * N + i;
+            if (l < D.n) {
+                dst[l] = v.v[i];
+            }
+        }
+    };
+
+    // Order 0 of the state variables: the state itself.
+    for (std::uint32_t it = tid; it < P.n_eq * G; it += nthr) {
+        const std::uint32_t sv = it / G, g = it % G;
+        const auto t = make_tape(g);
+        vd<N> v;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            v.v[i] = D.state[static_cast<std::size_t>(sv) * D.n + t.glane[i]];
+        }
+        t.row(__ldg(X.sv_rows + sv)).set(0u, v);
+        write_tc(sv, 0u, g, v);
+    }
+    __syncthreads();
+
+    for (std::uint32_t n = 0; n <= P.order; ++n) {
+        if (n > 0u) {
+            // State variables: x^[n] = (rhs)^[n-1] / n.
+            for (std::uint32_t it = tid; it < P.n_eq * G; it += nthr) {
+                const std::uint32_t sv = it / G, g = it % G;
+                const auto t = make_tape(g);
+                const vd<N> v = sv_diff<N>(P, t, __ldg(P.sv_defs + sv), n);
+                t.row(__ldg(X.sv_rows + sv)).set(n, v);
+                write_tc(sv, n, g, v);
+            }
+            __syncthreads();
+        }
+        if (n == P.order) {
+            break;
+        }
+        // The other u variables, one dependency segment at a time.
+        for (std::uint32_t s = 0; s < X.n_segments; ++s) {
+            const std::uint32_t b = __ldg(X.seg_offsets + s), e = __ldg(X.seg_offsets + s + 1u);
+            for (std::uint32_t it = tid; it < (e - b) * G; it += nthr) {
+                const std::uint32_t k = b + it / G, g = it % G;
+                const auto t = make_tape(g);
+                const uint4 op = __ldg(P.ops + k);
+                const auto self = t.row(__ldg(X.dst + k));
+                self.set(n, diff_op<N>(P, t, op, self, n));
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// Step-size estimate of lane `l` (CTA-local index) from the coefficients streamed to tc.
+template <int L>
+__device__ __forceinline__ double coop_determine_h(const program &P, const batch &D, std::uint32_t glane,
+                                                   double max_delta_t)
+{
+    const std::uint32_t pp1 = P.order + 1u, p = P.order;
+    const double *tc = D.tc + glane;
+    double m0 = fabs(tc[0]), mp = fabs(tc[static_cast<std::size_t>(p) * D.n]),
+           mp1 = fabs(tc[static_cast<std::size_t>(p - 1u) * D.n]);
+    for (std::uint32_t i = 1; i < P.n_eq; ++i) {
+        const double *c = tc + static_cast<std::size_t>(i) * pp1 * D.n;
+        m0 = std_max(m0, fabs(c[0]));
+        mp = std_max(mp, fabs(c[static_cast<std::size_t>(p) * D.n]));
+        mp1 = std_max(mp1, fabs(c[static_cast<std::size_t>(p - 1u) * D.n]));
+    }
+    return h_from_norms(P, m0, mp, mp1, max_delta_t);
+}
+
+// State update of the CTA's lanes: item = (state variable, lane); S.h holds the step sizes, S.running
+// which lanes may be written.
+template <int L>
+__device__ __forceinline__ void coop_update_state(const program &P, const batch &D, const coop_smem<L> &S,
+                                                  std::uint32_t lane0)
+{
+    const std::uint32_t pp1 = P.order + 1u;
+    for (std::uint32_t it = threadIdx.x; it < P.n_eq * L; it += blockDim.x) {
+        const std::uint32_t sv = it / L, l = it % L;
+        const std::uint32_t glane = lane0 + l;
+        if (glane < D.n && S.running[l]) {
+            const double *c = D.tc + static_cast<std::size_t>(sv) * pp1 * D.n + glane;
+            const std::size_t n = D.n;
+            const double res = eval_poly(P, [c, n](std::uint32_t o) { return c[static_cast<std::size_t>(o) * n]; },
+                                         S.h[l]);
+            D.state[static_cast<std::size_t>(sv) * D.n + glane] = res;
+        }
+    }
+}
+
+template <int L>
+__device__ __forceinline__ std::uint32_t claim_chunk_cta(unsigned int *counter, const coop_smem<L> &S)
+{
+    __syncthreads();
+    if (threadIdx.x == 0u) {
+        *S.chunk = atomicAdd(counter, 1u);
+    }
+    __syncthreads();
+    return *S.chunk;
+}
+
+template <int L, int N, bool PROP>
+__global__ void __launch_bounds__(256) k_coop(program P, coop_tables X, batch D, run_args R)
+{
+    extern __shared__ __align__(16) double smem_raw[];
+    const coop_smem<L> S(smem_raw, X.n_slots);
+    const std::uint32_t tid = threadIdx.x;
+    const std::uint32_t n_chunks = (D.n + L - 1u) / L;
+    const bool owner = tid < L;
+
+    for (std::uint32_t chunk = claim_chunk_cta<L>(R.counter, S); chunk < n_chunks;
+         chunk = claim_chunk_cta<L>(R.counter, S)) {
+        const std::uint32_t lane0 = chunk * L;
+        // Owner threads (one per lane) do the scalar bookkeeping of their lane.
+        const std::uint32_t lane_raw = lane0 + tid;
+        const bool valid = owner && lane_raw < D.n;
+        const std::uint32_t lane = (owner && lane_raw < D.n) ? lane_raw : D.n - 1u;
+
+        if constexpr (!PROP) {
+            double mdt = 0.;
+            dfl t0{0., 0.};
+            if (owner) {
+                mdt = R.max_delta_t != nullptr ? R.max_delta_t[lane] : R.default_max_delta_t;
+                t0 = dfl{D.t_hi[lane], D.t_lo[lane]};
+                S.time[tid] = t0.hi;
+                S.running[tid] = 1;
+            }
+            __syncthreads();
+            coop_jet<L, N>(P, X, D, S, lane0);
+            double h = 0.;
+            if (owner) {
+                h = coop_determine_h<L>(P, D, lane, mdt);
+                S.h[tid] = h;
+            }
+            __syncthreads();
+            coop_update_state<L>(P, D, S, lane0);
+            __syncthreads();
+            if (valid) {
+                const dfl nt = dfl_add(t0, dfl{h, 0.});
+                D.t_hi[lane] = nt.hi;
+                D.t_lo[lane] = nt.lo;
+                D.last_h[lane] = h;
+                const bool nf = !(isfinite(nt.hi) && isfinite(nt.lo)) || lane_state_nonfinite(P, D, lane);
+                D.step_outcome[lane]
+                    = nf ? HY_OUTCOME_ERR_NF_STATE : (h == mdt ? HY_OUTCOME_TIME_LIMIT : HY_OUTCOME_SUCCESS);
+            }
+        } else {
+            lane_prop lp;
+            lp.running = false;
+            if (owner) {
+                lp.init(D, R, lane);
+            }
+            int any = 1;
+            while (any) {
+                double cur_max = 0.;
+                if (owner) {
+                    cur_max = lp.cur_max();
+                    S.time[tid] = lp.t.hi;
+                    S.running[tid] = lp.running ? 1 : 0;
+                }
+                __syncthreads();
+                coop_jet<L, N>(P, X, D, S, lane0);
+                double h = 0.;
+                if (owner) {
+                    h = coop_determine_h<L>(P, D, lane, cur_max);
+                    S.h[tid] = h;
+                }
+                __syncthreads();
+                coop_update_state<L>(P, D, S, lane0);
+                __syncthreads();
+                if (owner && lp.running) {
+                    lp.advance(h, cur_max, lane_state_nonfinite(P, D, lane), R, valid);
+                }
+                any = __syncthreads_or(owner && lp.running ? 1 : 0);
+            }
+            if (valid) {
+                lp.store(D, lane);
+            }
+        }
+    }
+}
+
+__global__ void k_fill_outcome(long long *out, std::uint32_t n, long long value)
+{
+    const std::uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        out[i] = value;
+    }
+}
+
+// Dense output (src/taylor_01.cpp:1015-1185): Horner, or compensated summation in high-accuracy mode.
+__global__ void k_d_output(program P, std::uint32_t n, const double *tc, const double *tau, double *out)
+{
+    const std::uint32_t lane = blockIdx.x * blockDim.x + threadIdx.x;
+    if (lane >= n) {
+        return;
+    }
+    const double h = tau[lane];
+    const std::size_t nn = n;
+    for (std::uint32_t i = 0; i < P.n_eq; ++i) {
+        const double *c = tc + static_cast<std::size_t>(i) * (P.order + 1u) * n + lane;
+        out[static_cast<std::size_t>(i) * n + lane]
+            = eval_poly(P, [c, nn](std::uint32_t o) { return c[static_cast<std::size_t>(o) * nn]; }, h);
+    }
+}
+
+} // namespace heyoka_b200::dev
+
+#endif

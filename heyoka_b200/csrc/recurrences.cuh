@@ -1,5 +1,5 @@
 // Device recurrences: one normalised Taylor derivative ("coefficient") of one u variable at one order,
-// for the lane owned by the calling thread. Each opcode is the hand-written counterpart of one
+// for the N adjacent lanes owned by the calling thread. Each opcode is the hand-written counterpart of one
 // taylor_c_diff_func_* of the reference (compact-mode, i.e. running-accumulator, summation order):
 //
 //   sum / sub                       src/math/sum.cpp:250-371, src/detail/sub.cpp:180-398
@@ -16,8 +16,12 @@
 // fma(a, b, acc) (a contraction LLVM is allowed to make in the reference, src/llvm_state.cpp:842-845);
 // everything else rounds after each operation. tests/ compare against the oracle's sequential+FMA mode.
 //
-// The Tape policy gives access to the lane's private column of the derivative tape:
-//   double ld(slot), void st(slot, v), with slot = u * (order + 1) + o.
+// Storage is abstracted by a Tape policy (two implementations, see batch.cu):
+//   tape.row(ref) -> Row          the coefficients of one u variable for this thread's lanes
+//   row.at(o)     -> vd<N>        coefficient of order o          row.set(o, v)
+//   tape.par(idx), tape.time()    runtime parameter / time of the lanes
+// `ref` is whatever the program stores in an op's operand fields: a u-variable index for the HBM tape,
+// a packed slot reference for the shared-memory tape.
 #ifndef HEYOKA_B200_CSRC_RECURRENCES_CUH
 #define HEYOKA_B200_CSRC_RECURRENCES_CUH
 
@@ -28,33 +32,123 @@
 namespace heyoka_b200::dev
 {
 
-struct lane_ctx {
-    std::uint32_t lane;  // global lane index (clamped to a valid lane)
-    std::uint32_t batch; // number of lanes = stride of the batch-innermost arrays
-    const double *pars;
-    double time;         // t_hi of the lane at the beginning of the step
+// N adjacent lanes' worth of doubles, with element-wise arithmetic.
+template <int N>
+struct vd {
+    double v[N];
 };
 
-__device__ __forceinline__ double load_par(const lane_ctx &c, std::uint32_t idx)
+#define HY_VD_BINOP(op)                                                                                                \
+    template <int N>                                                                                                   \
+    __device__ __forceinline__ vd<N> operator op(const vd<N> &a, const vd<N> &b)                                       \
+    {                                                                                                                  \
+        vd<N> r;                                                                                                       \
+        _Pragma("unroll") for (int i = 0; i < N; ++i) r.v[i] = a.v[i] op b.v[i];                                       \
+        return r;                                                                                                      \
+    }                                                                                                                  \
+    template <int N>                                                                                                   \
+    __device__ __forceinline__ vd<N> operator op(const vd<N> &a, double b)                                             \
+    {                                                                                                                  \
+        vd<N> r;                                                                                                       \
+        _Pragma("unroll") for (int i = 0; i < N; ++i) r.v[i] = a.v[i] op b;                                            \
+        return r;                                                                                                      \
+    }                                                                                                                  \
+    template <int N>                                                                                                   \
+    __device__ __forceinline__ vd<N> operator op(double a, const vd<N> &b)                                             \
+    {                                                                                                                  \
+        vd<N> r;                                                                                                       \
+        _Pragma("unroll") for (int i = 0; i < N; ++i) r.v[i] = a op b.v[i];                                            \
+        return r;                                                                                                      \
+    }
+
+HY_VD_BINOP(+)
+HY_VD_BINOP(-)
+HY_VD_BINOP(*)
+HY_VD_BINOP(/)
+#undef HY_VD_BINOP
+
+template <int N>
+__device__ __forceinline__ vd<N> operator-(const vd<N> &a)
 {
-    return __ldg(c.pars + static_cast<std::size_t>(idx) * c.batch + c.lane);
+    vd<N> r;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        r.v[i] = -a.v[i];
+    }
+    return r;
 }
 
-__device__ __forceinline__ double numpar_val(const program &P, const lane_ctx &c, std::uint32_t ref)
+template <int N>
+__device__ __forceinline__ vd<N> splat(double x)
 {
-    return HY_REF_KIND(ref) == HY_REF_NUM ? __ldg(P.consts + HY_REF_IDX(ref)) : load_par(c, HY_REF_IDX(ref));
+    vd<N> r;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        r.v[i] = x;
+    }
+    return r;
+}
+
+// fma(a, b, c) element-wise; scalar first factor overload for the weighted sums.
+template <int N>
+__device__ __forceinline__ vd<N> vfma(const vd<N> &a, const vd<N> &b, const vd<N> &c)
+{
+    vd<N> r;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        r.v[i] = ::fma(a.v[i], b.v[i], c.v[i]);
+    }
+    return r;
+}
+template <int N>
+__device__ __forceinline__ vd<N> vfma(double a, const vd<N> &b, const vd<N> &c)
+{
+    vd<N> r;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        r.v[i] = ::fma(a, b.v[i], c.v[i]);
+    }
+    return r;
+}
+
+#define HY_VD_MAP1(name, fn)                                                                                           \
+    template <int N>                                                                                                   \
+    __device__ __forceinline__ vd<N> name(const vd<N> &a)                                                              \
+    {                                                                                                                  \
+        vd<N> r;                                                                                                       \
+        _Pragma("unroll") for (int i = 0; i < N; ++i) r.v[i] = fn(a.v[i]);                                             \
+        return r;                                                                                                      \
+    }
+HY_VD_MAP1(vsqrt, ::sqrt)
+HY_VD_MAP1(vsin, ::sin)
+HY_VD_MAP1(vcos, ::cos)
+HY_VD_MAP1(vtanh, ::tanh)
+HY_VD_MAP1(vexp, ::exp)
+HY_VD_MAP1(vlog, ::log)
+#undef HY_VD_MAP1
+
+template <int N>
+__device__ __forceinline__ vd<N> vpow(const vd<N> &a, const vd<N> &b)
+{
+    vd<N> r;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        r.v[i] = ::pow(a.v[i], b.v[i]);
+    }
+    return r;
 }
 
 // pairwise_reduce() of up to 8 values (src/detail/llvm_helpers_algo.cpp:271-308), registers only.
-__device__ __forceinline__ double pairwise8(double (&v)[8], std::uint32_t n)
+template <int N>
+__device__ __forceinline__ vd<N> pairwise8(vd<N> (&v)[8], std::uint32_t n)
 {
-    double w[4];
+    vd<N> w[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         w[i] = (2 * i + 1 < static_cast<int>(n)) ? v[2 * i] + v[2 * i + 1] : v[2 * i];
     }
     const std::uint32_t m = (n + 1u) / 2u;
-    double x[2];
+    vd<N> x[2];
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
         x[i] = (2 * i + 1 < static_cast<int>(m)) ? w[2 * i] + w[2 * i + 1] : w[2 * i];
@@ -63,42 +157,43 @@ __device__ __forceinline__ double pairwise8(double (&v)[8], std::uint32_t n)
     return (m2 > 1u) ? x[0] + x[1] : x[0];
 }
 
-// sum_{j=j0..j1} A^[n-j] B^[j]; sa_n = slot of A at order n, sb_0 = slot of B at order 0.
-template <typename Tape>
-__device__ __forceinline__ double conv_plain(const Tape &t, std::uint32_t sa_n, std::uint32_t sb_0, std::uint32_t j0,
-                                             std::uint32_t j1)
+// sum_{j=j0..j1} A^[n-j] B^[j].
+template <int N, typename Row>
+__device__ __forceinline__ vd<N> conv_plain(const Row &A, const Row &B, std::uint32_t n, std::uint32_t j0,
+                                            std::uint32_t j1)
 {
-    double acc = 0.;
+    vd<N> acc = splat<N>(0.);
     if (j1 + 1u > j0) {
 #pragma unroll 4
         for (std::uint32_t j = j0; j <= j1; ++j) {
-            acc = fma(t.ld(sa_n - j), t.ld(sb_0 + j), acc);
+            acc = vfma(A.at(n - j), B.at(j), acc);
         }
     }
     return acc;
 }
 
 // sum_{j=j0..j1} j * (A^[n-j] B^[j]).
-template <typename Tape>
-__device__ __forceinline__ double conv_jw(const Tape &t, std::uint32_t sa_n, std::uint32_t sb_0, std::uint32_t j0,
-                                          std::uint32_t j1)
+template <int N, typename Row>
+__device__ __forceinline__ vd<N> conv_jw(const Row &A, const Row &B, std::uint32_t n, std::uint32_t j0,
+                                         std::uint32_t j1)
 {
-    double acc = 0.;
+    vd<N> acc = splat<N>(0.);
     if (j1 + 1u > j0) {
 #pragma unroll 4
         for (std::uint32_t j = j0; j <= j1; ++j) {
-            acc = fma(static_cast<double>(j), t.ld(sa_n - j) * t.ld(sb_0 + j), acc);
+            acc = vfma(static_cast<double>(j), A.at(n - j) * B.at(j), acc);
         }
     }
     return acc;
 }
 
 // Exponentiation by squaring with the reference's association order (src/math/pow.cpp:136-152).
-__device__ inline double pow_ebs(double base, std::uint32_t e)
+template <int N>
+__device__ inline vd<N> pow_ebs(vd<N> base, std::uint32_t e)
 {
-    double mult[6];
+    vd<N> mult[6];
     int nm = 0;
-    double b = base;
+    vd<N> b = base;
     while (e > 1u) {
         if (e & 1u) {
             mult[nm++] = b;
@@ -108,14 +203,16 @@ __device__ inline double pow_ebs(double base, std::uint32_t e)
         }
         b = b * b;
     }
-    double r = (e == 0u) ? 1. : b;
+    vd<N> r = (e == 0u) ? splat<N>(1.) : b;
     for (int i = nm - 1; i >= 0; --i) {
         r = mult[i] * r;
     }
     return r;
 }
 
-__device__ inline double pow_eval(std::uint32_t algo, double x, double expo)
+// Order-0 evaluation of pow(x, expo) (src/math/pow.cpp:292-355).
+template <int N>
+__device__ inline vd<N> pow_eval(std::uint32_t algo, const vd<N> &x, const vd<N> &expo)
 {
     const std::uint32_t type = algo >> 8, n = algo & 0xffu;
     switch (type) {
@@ -124,11 +221,11 @@ __device__ inline double pow_eval(std::uint32_t algo, double x, double expo)
         case HY_POW_NEG_SMALL_INT:
             return 1. / pow_ebs(x, n);
         case HY_POW_POS_SMALL_HALF:
-            return pow_ebs(::sqrt(x), n);
+            return pow_ebs(vsqrt(x), n);
         case HY_POW_NEG_SMALL_HALF:
-            return 1. / pow_ebs(::sqrt(x), n);
+            return 1. / pow_ebs(vsqrt(x), n);
         default:
-            return ::pow(x, expo);
+            return vpow(x, expo);
     }
 }
 
@@ -155,16 +252,24 @@ __device__ inline std::uint32_t pow_algo_of(double e)
     return HY_POW_GENERAL << 8;
 }
 
-// Functions whose arguments are all numbers/params: evaluated at order 0 only.
-__device__ inline double cfunc_eval(const program &P, const lane_ctx &c, const uint4 &op)
+// Value of a number/param reference (taylor_codegen_numparam, src/taylor_01.cpp:201-234).
+template <int N, typename Tape>
+__device__ __forceinline__ vd<N> numpar_val(const program &P, const Tape &t, std::uint32_t ref)
 {
-    double v[8];
-    const std::uint32_t n = op.z;
+    return HY_REF_KIND(ref) == HY_REF_NUM ? splat<N>(__ldg(P.consts + HY_REF_IDX(ref))) : t.par(HY_REF_IDX(ref));
+}
+
+// Functions whose arguments are all numbers/params: evaluated at order 0 only.
+template <int N, typename Tape>
+__device__ inline vd<N> cfunc_eval(const program &P, const Tape &t, std::uint32_t fn, std::uint32_t arg_off,
+                                   std::uint32_t n)
+{
+    vd<N> v[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-        v[k] = (k < static_cast<int>(n)) ? numpar_val(P, c, __ldg(P.args + op.y + k)) : 0.;
+        v[k] = (k < static_cast<int>(n)) ? numpar_val<N>(P, t, __ldg(P.args + arg_off + k)) : splat<N>(0.);
     }
-    switch (op.x) {
+    switch (fn) {
         case HY_CF_IDENTITY:
             return v[0];
         case HY_CF_SUM:
@@ -176,8 +281,9 @@ __device__ inline double cfunc_eval(const program &P, const lane_ctx &c, const u
         case HY_CF_DIV:
             return v[0] / v[1];
         case HY_CF_POW: {
-            const std::uint32_t eref = __ldg(P.args + op.y + 1u);
-            const std::uint32_t algo = HY_REF_KIND(eref) == HY_REF_NUM ? pow_algo_of(v[1]) : (HY_POW_GENERAL << 8);
+            const std::uint32_t eref = __ldg(P.args + arg_off + 1u);
+            const std::uint32_t algo
+                = HY_REF_KIND(eref) == HY_REF_NUM ? pow_algo_of(v[1].v[0]) : (HY_POW_GENERAL << 8);
             return pow_eval(algo, v[0], v[1]);
         }
         case HY_CF_SUM_SQ:
@@ -187,40 +293,41 @@ __device__ inline double cfunc_eval(const program &P, const lane_ctx &c, const u
             }
             return pairwise8(v, n);
         case HY_CF_SIN:
-            return ::sin(v[0]);
+            return vsin(v[0]);
         case HY_CF_COS:
-            return ::cos(v[0]);
+            return vcos(v[0]);
         case HY_CF_TANH:
-            return ::tanh(v[0]);
+            return vtanh(v[0]);
         case HY_CF_EXP:
-            return ::exp(v[0]);
+            return vexp(v[0]);
         case HY_CF_LOG:
-            return ::log(v[0]);
+            return vlog(v[0]);
     }
-    return 0.;
+    return splat<N>(0.);
 }
 
-// The order-n coefficient of u variable `u_idx` defined by `op`. pp1 = order + 1 (slot stride).
-template <typename Tape>
-__device__ __forceinline__ double diff_op(const program &P, const lane_ctx &c, const Tape &t, const uint4 &op,
-                                          std::uint32_t u_idx, std::uint32_t n)
+// The order-n coefficient of the u variable defined by `op` (op.x = opcode, op.y/z/w = a/b/c operand
+// fields). `self` is the row of the u variable being defined (read by the self-referential recurrences).
+template <int N, typename Tape, typename Row>
+__device__ __forceinline__ vd<N> diff_op(const program &P, const Tape &t, const uint4 &op, const Row &self,
+                                         std::uint32_t n)
 {
-    const std::uint32_t pp1 = P.order + 1u;
+    using V = vd<N>;
     const std::uint32_t a = op.y, b = op.z, dep = op.w;
 
     switch (op.x) {
         case HY_OP_SUM: {
             // a^[n] = pairwise sum of the terms' order-n coefficients; numbers/params only at n = 0.
-            double v[8];
+            V v[8];
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
-                v[k] = 0.;
+                v[k] = splat<N>(0.);
                 if (k < static_cast<int>(b)) {
                     const std::uint32_t ref = __ldg(P.args + a + k);
                     if (HY_REF_KIND(ref) == HY_REF_VAR) {
-                        v[k] = t.ld(HY_REF_IDX(ref) * pp1 + n);
+                        v[k] = t.row(HY_REF_IDX(ref)).at(n);
                     } else if (n == 0u) {
-                        v[k] = numpar_val(P, c, ref);
+                        v[k] = numpar_val<N>(P, t, ref);
                     }
                 }
             }
@@ -228,113 +335,113 @@ __device__ __forceinline__ double diff_op(const program &P, const lane_ctx &c, c
         }
         case HY_OP_SUM_SQ: {
             // Per term the square recurrence, then a pairwise sum over the terms.
-            double v[8];
+            V v[8];
             const bool odd = (n & 1u) != 0u;
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
-                v[k] = 0.;
+                v[k] = splat<N>(0.);
                 if (k < static_cast<int>(b)) {
                     const std::uint32_t ref = __ldg(P.args + a + k);
                     if (HY_REF_KIND(ref) == HY_REF_VAR) {
-                        const std::uint32_t s0 = HY_REF_IDX(ref) * pp1;
+                        const Row A = t.row(HY_REF_IDX(ref));
                         if (odd) {
-                            v[k] = conv_plain(t, s0 + n, s0, 0u, (n - 1u) / 2u);
+                            v[k] = conv_plain<N>(A, A, n, 0u, (n - 1u) / 2u);
                         } else {
-                            const double ak2 = t.ld(s0 + n / 2u);
-                            const double sq = ak2 * ak2;
+                            const V ak2 = A.at(n / 2u);
+                            const V sq = ak2 * ak2;
                             if (n > 0u) {
-                                const double acc = conv_plain(t, s0 + n, s0, 0u, (n - 2u) / 2u);
+                                const V acc = conv_plain<N>(A, A, n, 0u, (n - 2u) / 2u);
                                 v[k] = (acc + acc) + sq;
                             } else {
                                 v[k] = sq;
                             }
                         }
                     } else if (n == 0u) {
-                        const double val = numpar_val(P, c, ref);
+                        const V val = numpar_val<N>(P, t, ref);
                         v[k] = val * val;
                     }
                 }
             }
-            const double r = pairwise8(v, b);
+            const V r = pairwise8(v, b);
             return odd ? r + r : r;
         }
         case HY_OP_SUB_VV:
-            return t.ld(a * pp1 + n) - t.ld(b * pp1 + n);
+            return t.row(a).at(n) - t.row(b).at(n);
         case HY_OP_SUB_VN: {
-            const double v = t.ld(a * pp1 + n);
+            const V v = t.row(a).at(n);
             return n == 0u ? v - __ldg(P.consts + b) : v;
         }
         case HY_OP_SUB_VP: {
-            const double v = t.ld(a * pp1 + n);
-            return n == 0u ? v - load_par(c, b) : v;
+            const V v = t.row(a).at(n);
+            return n == 0u ? v - t.par(b) : v;
         }
         case HY_OP_SUB_NV: {
-            const double v = t.ld(b * pp1 + n);
+            const V v = t.row(b).at(n);
             return n == 0u ? __ldg(P.consts + a) - v : -v;
         }
         case HY_OP_SUB_PV: {
-            const double v = t.ld(b * pp1 + n);
-            return n == 0u ? load_par(c, a) - v : -v;
+            const V v = t.row(b).at(n);
+            return n == 0u ? t.par(a) - v : -v;
         }
         case HY_OP_NEG:
-            return -t.ld(a * pp1 + n);
+            return -t.row(a).at(n);
         case HY_OP_MUL_NV:
-            return __ldg(P.consts + a) * t.ld(b * pp1 + n);
+            return __ldg(P.consts + a) * t.row(b).at(n);
         case HY_OP_MUL_PV:
-            return load_par(c, a) * t.ld(b * pp1 + n);
+            return t.par(a) * t.row(b).at(n);
         case HY_OP_MUL_VV:
             // sum_{j=0..n} b^[n-j] c^[j]
-            return conv_plain(t, a * pp1 + n, b * pp1, 0u, n);
+            return conv_plain<N>(t.row(a), t.row(b), n, 0u, n);
         case HY_OP_DIV_VV:
         case HY_OP_DIV_NV:
         case HY_OP_DIV_PV: {
             // (b^[n] - sum_{j=1..n} a^[n-j] c^[j]) / c^[0], a = this u variable; numerator = -sum if b is constant.
-            const double c0 = t.ld(b * pp1);
+            const Row C = t.row(b);
+            const V c0 = C.at(0u);
             if (n == 0u) {
-                const double num = op.x == HY_OP_DIV_VV ? t.ld(a * pp1)
-                                                        : (op.x == HY_OP_DIV_NV ? __ldg(P.consts + a) : load_par(c, a));
+                const V num = op.x == HY_OP_DIV_VV ? t.row(a).at(0u)
+                                                   : (op.x == HY_OP_DIV_NV ? splat<N>(__ldg(P.consts + a)) : t.par(a));
                 return num / c0;
             }
-            const double acc = conv_plain(t, u_idx * pp1 + n, b * pp1, 1u, n);
+            const V acc = conv_plain<N>(self, C, n, 1u, n);
             if (op.x == HY_OP_DIV_VV) {
-                return (t.ld(a * pp1 + n) - acc) / c0;
+                return (t.row(a).at(n) - acc) / c0;
             }
             return (-acc) / c0;
         }
         case HY_OP_DIV_VN:
-            return t.ld(a * pp1 + n) / __ldg(P.consts + b);
+            return t.row(a).at(n) / __ldg(P.consts + b);
         case HY_OP_DIV_VP:
-            return t.ld(a * pp1 + n) / load_par(c, b);
+            return t.row(a).at(n) / t.par(b);
         case HY_OP_SQUARE: {
-            const std::uint32_t s0 = a * pp1;
+            const Row A = t.row(a);
             if (n == 0u) {
-                const double b0 = t.ld(s0);
+                const V b0 = A.at(0u);
                 return b0 * b0;
             }
             if (n & 1u) {
-                const double r = conv_plain(t, s0 + n, s0, 0u, (n - 1u) / 2u);
+                const V r = conv_plain<N>(A, A, n, 0u, (n - 1u) / 2u);
                 return r + r;
             }
-            const double ak2 = t.ld(s0 + n / 2u);
-            const double sq = ak2 * ak2;
-            const double r = conv_plain(t, s0 + n, s0, 0u, (n - 2u) / 2u);
+            const V ak2 = A.at(n / 2u);
+            const V sq = ak2 * ak2;
+            const V r = conv_plain<N>(A, A, n, 0u, (n - 2u) / 2u);
             return (r + r) + sq;
         }
         case HY_OP_SQRT: {
             // (b^[n] - 2 sum_{j=1..} a^[n-j] a^[j] - [n even] (a^[n/2])^2) / (2 a^[0]), a = this u variable.
             if (n == 0u) {
-                return ::sqrt(t.ld(a * pp1));
+                return vsqrt(t.row(a).at(0u));
             }
-            const std::uint32_t s0 = u_idx * pp1;
-            double div = t.ld(s0);
+            V div = self.at(0u);
             div = div + div;
-            double fac = t.ld(a * pp1 + n);
+            V fac = t.row(a).at(n);
             const bool even = (n & 1u) == 0u;
             const std::uint32_t upper = (n - (even ? 2u : 1u)) / 2u;
-            double acc = conv_plain(t, s0 + n, s0, 1u, upper);
+            V acc = conv_plain<N>(self, self, n, 1u, upper);
             acc = acc + acc;
             if (even) {
-                const double tmp = t.ld(s0 + n / 2u);
+                const V tmp = self.at(n / 2u);
                 fac = fac - tmp * tmp;
             }
             fac = fac - acc;
@@ -343,104 +450,79 @@ __device__ __forceinline__ double diff_op(const program &P, const lane_ctx &c, c
         case HY_OP_POW_VN:
         case HY_OP_POW_VP: {
             // (1 / (n b0)) sum_{j=0..n-1} [n alpha - j (alpha + 1)] b^[n-j] a^[j], a = this u variable.
-            const double alpha = op.x == HY_OP_POW_VN ? __ldg(P.consts + b) : load_par(c, b);
-            const std::uint32_t sb = a * pp1;
+            const V alpha = op.x == HY_OP_POW_VN ? splat<N>(__ldg(P.consts + b)) : t.par(b);
+            const Row B = t.row(a);
             if (n == 0u) {
-                return pow_eval(op.x == HY_OP_POW_VN ? dep : (HY_POW_GENERAL << 8), t.ld(sb), alpha);
+                return pow_eval(op.x == HY_OP_POW_VN ? dep : (HY_POW_GENERAL << 8), B.at(0u), alpha);
             }
-            const std::uint32_t sa0 = u_idx * pp1;
-            const double nd = static_cast<double>(n), ap1 = alpha + 1.;
-            const double n_alpha = nd * alpha;
-            double acc = 0.;
+            const double nd = static_cast<double>(n);
+            const V ap1 = alpha + 1.;
+            const V n_alpha = nd * alpha;
+            V acc = splat<N>(0.);
 #pragma unroll 4
             for (std::uint32_t j = 0; j < n; ++j) {
-                const double fac = n_alpha - static_cast<double>(j) * ap1;
-                acc = fma(fac, t.ld(sb + n - j) * t.ld(sa0 + j), acc);
+                const V fac = n_alpha - static_cast<double>(j) * ap1;
+                acc = vfma(fac, B.at(n - j) * self.at(j), acc);
             }
-            return acc / (nd * t.ld(sb));
+            return acc / (nd * B.at(0u));
         }
         case HY_OP_SIN:
-            // (1/n) sum_{j=1..n} j c^[n-j] b^[j], c = ::cos(b) (hidden dependency).
+            // (1/n) sum_{j=1..n} j c^[n-j] b^[j], c = cosine of b (hidden dependency).
             if (n == 0u) {
-                return ::sin(t.ld(a * pp1));
+                return vsin(t.row(a).at(0u));
             }
-            return conv_jw(t, dep * pp1 + n, a * pp1, 1u, n) / static_cast<double>(n);
+            return conv_jw<N>(t.row(dep), t.row(a), n, 1u, n) / static_cast<double>(n);
         case HY_OP_COS:
-            // sum / (-n), with s = ::sin(b) as hidden dependency.
+            // sum / (-n), with s = sine of b as hidden dependency.
             if (n == 0u) {
-                return ::cos(t.ld(a * pp1));
+                return vcos(t.row(a).at(0u));
             }
-            return conv_jw(t, dep * pp1 + n, a * pp1, 1u, n) / (-static_cast<double>(n));
-        case HY_OP_TANH:
-            // b^[n] - (1/n) sum_{j=1..n} j c^[n-j] b^[j], c = ::tanh(b)^2 (hidden dependency).
+            return conv_jw<N>(t.row(dep), t.row(a), n, 1u, n) / (-static_cast<double>(n));
+        case HY_OP_TANH: {
+            // b^[n] - (1/n) sum_{j=1..n} j c^[n-j] b^[j], c = tanh(b)^2 (hidden dependency).
+            const Row B = t.row(a);
             if (n == 0u) {
-                return ::tanh(t.ld(a * pp1));
+                return vtanh(B.at(0u));
             }
-            return t.ld(a * pp1 + n) - conv_jw(t, dep * pp1 + n, a * pp1, 1u, n) / static_cast<double>(n);
+            return B.at(n) - conv_jw<N>(t.row(dep), B, n, 1u, n) / static_cast<double>(n);
+        }
         case HY_OP_EXP:
             // (1/n) sum_{j=1..n} j a^[n-j] b^[j], a = this u variable.
             if (n == 0u) {
-                return ::exp(t.ld(a * pp1));
+                return vexp(t.row(a).at(0u));
             }
-            return conv_jw(t, u_idx * pp1 + n, a * pp1, 1u, n) / static_cast<double>(n);
+            return conv_jw<N>(self, t.row(a), n, 1u, n) / static_cast<double>(n);
         case HY_OP_LOG: {
             // (n b^[n] - sum_{j=1..n-1} j b^[n-j] a^[j]) / (n b^[0]), a = this u variable.
+            const Row B = t.row(a);
             if (n == 0u) {
-                return ::log(t.ld(a * pp1));
+                return vlog(B.at(0u));
             }
             const double nd = static_cast<double>(n);
-            const double nb0 = nd * t.ld(a * pp1);
-            double ret = nd * t.ld(a * pp1 + n);
+            const V nb0 = nd * B.at(0u);
+            V ret = nd * B.at(n);
             if (n > 1u) {
-                ret = ret - conv_jw(t, a * pp1 + n, u_idx * pp1, 1u, n - 1u);
+                ret = ret - conv_jw<N>(B, self, n, 1u, n - 1u);
             }
             return ret / nb0;
         }
         case HY_OP_TIME:
-            return n == 0u ? c.time : (n == 1u ? 1. : 0.);
+            return n == 0u ? t.time() : (n == 1u ? splat<N>(1.) : splat<N>(0.));
         case HY_OP_CFUNC:
-            return n == 0u ? cfunc_eval(P, c, op) : 0.;
+            return n == 0u ? cfunc_eval<N>(P, t, a, b, dep) : splat<N>(0.);
     }
-    return 0.;
+    return splat<N>(0.);
 }
 
-// Order-n (n >= 1) coefficient of state variable sv: (u_rhs)^[n-1] / n, a true division
-// (src/taylor_02.cpp:245-287); constant right-hand sides only contribute at n == 1.
-template <typename Tape>
-__device__ __forceinline__ double sv_diff(const program &P, const lane_ctx &c, const Tape &t, std::uint32_t sv,
-                                          std::uint32_t n)
+// Order-n (n >= 1) coefficient of a state variable whose first derivative is `ref`: (u_rhs)^[n-1] / n, a true
+// division (src/taylor_02.cpp:245-287); constant right-hand sides only contribute at n == 1.
+template <int N, typename Tape>
+__device__ __forceinline__ vd<N> sv_diff(const program &P, const Tape &t, std::uint32_t ref, std::uint32_t n)
 {
-    const std::uint32_t ref = __ldg(P.sv_defs + sv);
     if (HY_REF_KIND(ref) == HY_REF_VAR) {
-        return t.ld(HY_REF_IDX(ref) * (P.order + 1u) + n - 1u) / static_cast<double>(n);
+        return t.row(HY_REF_IDX(ref)).at(n - 1u) / static_cast<double>(n);
     }
-    return n == 1u ? numpar_val(P, c, ref) : 0.;
-}
-
-// The whole jet of the lane: orders 0..p-1 of every u variable, order p of the state variables
-// (evaluation order of src/taylor_02.cpp:1147-1185: per order, state variables first, then the others).
-template <typename Tape>
-__device__ __forceinline__ void compute_jet(const program &P, const lane_ctx &c, const Tape &t, const double *state)
-{
-    const std::uint32_t pp1 = P.order + 1u;
-
-    for (std::uint32_t i = 0; i < P.n_eq; ++i) {
-        t.st(i * pp1, state[static_cast<std::size_t>(i) * c.batch + c.lane]);
-    }
-    for (std::uint32_t n = 0; n < P.order; ++n) {
-        if (n > 0u) {
-            for (std::uint32_t i = 0; i < P.n_eq; ++i) {
-                t.st(i * pp1 + n, sv_diff(P, c, t, i, n));
-            }
-        }
-        for (std::uint32_t k = 0; k < P.n_ops; ++k) {
-            const uint4 op = __ldg(P.ops + k);
-            t.st((P.n_eq + k) * pp1 + n, diff_op(P, c, t, op, P.n_eq + k, n));
-        }
-    }
-    for (std::uint32_t i = 0; i < P.n_eq; ++i) {
-        t.st(i * pp1 + P.order, sv_diff(P, c, t, i, P.order));
-    }
+    return n == 1u ? numpar_val<N>(P, t, ref) : splat<N>(0.);
 }
 
 // std::max / std::min semantics of the reference's llvm_max/llvm_min (src/detail/llvm_helpers_cmp.cpp:313-329).
@@ -453,18 +535,10 @@ __device__ __forceinline__ double std_min(double a, double b)
     return (b < a) ? b : a;
 }
 
-// taylor_determine_h() (src/taylor_00.cpp:102-273): Jorba-Zou step size from the infinity norms of the
-// state and of the two highest-order coefficients, clamped to |max_delta_t|, signed like max_delta_t.
-template <typename Tape>
-__device__ __forceinline__ double determine_h(const program &P, const Tape &t, double max_delta_t)
+// taylor_determine_h() (src/taylor_00.cpp:102-273) from the three infinity norms: Jorba-Zou step size,
+// clamped to |max_delta_t|, signed like max_delta_t.
+__device__ __forceinline__ double h_from_norms(const program &P, double m0, double mp, double mp1, double max_delta_t)
 {
-    const std::uint32_t pp1 = P.order + 1u, p = P.order;
-    double m0 = fabs(t.ld(0)), mp = fabs(t.ld(p)), mp1 = fabs(t.ld(p - 1u));
-    for (std::uint32_t i = 1; i < P.n_eq; ++i) {
-        m0 = std_max(m0, fabs(t.ld(i * pp1)));
-        mp = std_max(mp, fabs(t.ld(i * pp1 + p)));
-        mp1 = std_max(mp1, fabs(t.ld(i * pp1 + p - 1u)));
-    }
     const double num_rho = (m0 <= 1.) ? 1. : m0;
     const double rho_o = ::pow(num_rho / mp, P.inv_p);
     const double rho_om1 = ::pow(num_rho / mp1, P.inv_pm1);
@@ -474,42 +548,31 @@ __device__ __forceinline__ double determine_h(const program &P, const Tape &t, d
     return (max_delta_t < 0.) ? -h : h;
 }
 
-// State update: Horner (src/taylor_00.cpp:279-351) or compensated summation of the monomials
-// (src/taylor_00.cpp:355-460) when high_accuracy; optionally the tc copy (src/taylor_00.cpp:467-584).
-template <typename Tape>
-__device__ __forceinline__ void update_state(const program &P, const lane_ctx &c, const Tape &t, double h, double *state,
-                                             double *tc, bool write)
+// Evaluation of one Taylor polynomial at h: Horner (src/taylor_00.cpp:279-351) or compensated summation of
+// the monomials (src/taylor_00.cpp:355-460) when high_accuracy. cf(o) returns the order-o coefficient.
+template <typename F>
+__device__ __forceinline__ double eval_poly(const program &P, const F &cf, double h)
 {
-    const std::uint32_t pp1 = P.order + 1u, p = P.order;
-    for (std::uint32_t i = 0; i < P.n_eq; ++i) {
-        const std::uint32_t s0 = i * pp1;
-        double res;
-        if (!P.high_accuracy) {
-            res = t.ld(s0 + p);
-            for (std::uint32_t o = 1; o <= p; ++o) {
-                res = fma(res, h, t.ld(s0 + p - o));
-            }
-        } else {
-            res = t.ld(s0);
-            double comp = 0., cur_h = h;
-            for (std::uint32_t o = 1; o <= p; ++o) {
-                const double tmp = __dmul_rn(t.ld(s0 + o), cur_h);
-                const double y = __dsub_rn(tmp, comp);
-                const double tt = __dadd_rn(res, y);
-                comp = __dsub_rn(__dsub_rn(tt, res), y);
-                res = tt;
-                cur_h = __dmul_rn(cur_h, h);
-            }
+    const std::uint32_t p = P.order;
+    double res;
+    if (!P.high_accuracy) {
+        res = cf(p);
+        for (std::uint32_t o = 1; o <= p; ++o) {
+            res = ::fma(res, h, cf(p - o));
         }
-        if (write) {
-            state[static_cast<std::size_t>(i) * c.batch + c.lane] = res;
-            if (tc != nullptr) {
-                for (std::uint32_t o = 0; o <= p; ++o) {
-                    tc[(static_cast<std::size_t>(i) * pp1 + o) * c.batch + c.lane] = t.ld(s0 + o);
-                }
-            }
+    } else {
+        res = cf(0u);
+        double comp = 0., cur_h = h;
+        for (std::uint32_t o = 1; o <= p; ++o) {
+            const double tmp = __dmul_rn(cf(o), cur_h);
+            const double y = __dsub_rn(tmp, comp);
+            const double tt = __dadd_rn(res, y);
+            comp = __dsub_rn(__dsub_rn(tt, res), y);
+            res = tt;
+            cur_h = __dmul_rn(cur_h, h);
         }
     }
+    return res;
 }
 
 // Double-length time arithmetic (include/heyoka/detail/dfloat.hpp:104-169).
@@ -549,6 +612,14 @@ __device__ __forceinline__ bool dfl_lt(dfl x, dfl y)
 __device__ __forceinline__ bool dfl_ge0(dfl x)
 {
     return (x.hi > 0.) || (x.hi == 0. && x.lo >= 0.);
+}
+
+// Time limit of a propagate_until() step (src/taylor_adaptive_batch.cpp:1378-1387).
+__device__ __forceinline__ double step_limit(bool dir, dfl rem, double mdt)
+{
+    const dfl lim = dir ? (dfl_lt(rem, dfl{mdt, 0.}) ? rem : dfl{mdt, 0.})
+                        : (dfl_lt(rem, dfl{-mdt, 0.}) ? dfl{-mdt, 0.} : rem);
+    return lim.hi;
 }
 
 } // namespace heyoka_b200::dev

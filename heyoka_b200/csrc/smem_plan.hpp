@@ -1,0 +1,45 @@
+// Host-side planning for the shared-memory ("cooperative") kernels: dependency segments, history
+// analysis, slot assignment.
+//
+// The reference does the equivalent bookkeeping for its compact mode: taylor_segment_dc()
+// (src/taylor_02.cpp:105-207) splits the decomposition into segments of mutually independent u variables,
+// and the tape holds every u variable at every order (src/taylor_02.cpp:1227-1233). Here the tape has to
+// fit in the 227 KB of shared memory of an SM, so only what is re-read at a LATER order keeps its history:
+//   H  ("history")   operands of convolution-type recurrences: p (or p + 1) slots, one per order
+//   SV (state var)   two slots, ping-pong on the order's parity (order n is built from order n - 1)
+//   T  ("transient") everything that is only consumed at the order at which it is produced: one slot
+// The coefficients of the state variables of every order are streamed to the tc array in HBM (they are
+// needed again only once, for the step-size estimate and the state update).
+#ifndef HEYOKA_B200_CSRC_SMEM_PLAN_HPP
+#define HEYOKA_B200_CSRC_SMEM_PLAN_HPP
+
+#include <cstdint>
+#include <vector>
+
+#include "program.hpp"
+
+namespace heyoka_b200::detail
+{
+
+// Packed row reference: (first slot << 2) | kind.
+constexpr std::uint32_t ROW_T = 0u, ROW_SV = 1u, ROW_H = 2u;
+
+struct smem_plan {
+    std::uint32_t n_slots = 0;  // doubles of shared memory per lane
+    std::uint32_t n_segments = 0;
+    std::uint32_t max_seg_width = 0;
+    // Ops in execution order (segment by segment, grouped by opcode inside a segment); operand fields that
+    // referred to u variables are row references.
+    std::vector<hy_op> ops;
+    std::vector<std::uint32_t> dst;         // row reference of the u variable each op defines
+    std::vector<std::uint32_t> seg_offsets; // n_segments + 1 offsets into ops
+    std::vector<std::uint32_t> args;        // n-ary argument table, variable entries -> row references
+    std::vector<std::uint32_t> sv_defs;     // idem for the state variables' derivatives
+    std::vector<std::uint32_t> sv_rows;     // row reference of each state variable
+};
+
+smem_plan make_smem_plan(const hy_program &);
+
+} // namespace heyoka_b200::detail
+
+#endif

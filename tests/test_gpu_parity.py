@@ -19,6 +19,19 @@ pytestmark = pytest.mark.gpu
 
 OC = {"success": hb.taylor_outcome.success, "time_limit": hb.taylor_outcome.time_limit}
 
+# Every parity test runs on both tape strategies and a few cooperative-kernel shapes (see kernels.cuh).
+KERNELS = {
+    "hbm": dict(tape="hbm"),
+    "smem-auto": dict(tape="smem"),
+    "smem-L8N2": dict(tape="smem", lanes_per_cta=8, lanes_per_thread=2),
+    "smem-L2N1": dict(tape="smem", lanes_per_cta=2, lanes_per_thread=1, block_threads=64),
+}
+
+
+@pytest.fixture(params=list(KERNELS), scope="module")
+def kernel(request):
+    return KERNELS[request.param]
+
 
 def rel_err(a, b, floor=1e-6):
     """Component-wise relative error (with an absolute floor)."""
@@ -36,10 +49,10 @@ def tc_err(tc_a, tc_b, h):
     return np.max(np.abs(tc_a - tc_b) * w / scale)
 
 
-def test_tutorial_batch_mode_gpu():
+def test_tutorial_batch_mode_gpu(kernel):
     """doc/tut_batch_mode.rst end to end on the GPU (same fixture that pins the oracle)."""
     g = golden("tut_batch_mode.json")
-    ta = hb.taylor_adaptive_batch(sys_tutorial(), [g["x0"], g["v0"]], 4, pars=[g["alpha"]])
+    ta = hb.taylor_adaptive_batch(sys_tutorial(), [g["x0"], g["v0"]], 4, pars=[g["alpha"]], kernel=kernel)
     assert ta.get_order() == 20
 
     ta.step()
@@ -72,10 +85,10 @@ def test_tutorial_batch_mode_gpu():
     assert sig_digits_equal(ta.tc, g["tc_after_final_step"], 7)
 
 
-def _step_parity(sys, state, batch, pars=None, time=0.0, ha=False, n_steps=3, tol=1e-13, max_delta_t=None):
+def _step_parity(kernel, sys, state, batch, pars=None, time=0.0, ha=False, n_steps=3, tol=1e-13, max_delta_t=None):
     P = hb.Program(sys, high_accuracy=ha)
     o = oracle.OracleIntegrator(P, state, batch, pars=pars, time=time, mode=oracle.FMA)
-    ta = hb.taylor_adaptive_batch(sys, state, batch, pars=pars, time=time, high_accuracy=ha)
+    ta = hb.taylor_adaptive_batch(sys, state, batch, pars=pars, time=time, high_accuracy=ha, kernel=kernel)
     for _ in range(n_steps):
         o.step(max_delta_t, write_tc=True)
         ta.step(max_delta_t, write_tc=True)
@@ -92,38 +105,38 @@ def _step_parity(sys, state, batch, pars=None, time=0.0, ha=False, n_steps=3, to
 
 @pytest.mark.parametrize("ha", [False, True])
 @pytest.mark.parametrize("batch", [1, 4, 33, 70])
-def test_step_parity_pendulum(ha, batch):
+def test_step_parity_pendulum(kernel, ha, batch):
     rng = np.random.default_rng(1)
     st = np.stack([rng.uniform(-1, 1, batch), rng.uniform(-1, 1, batch)])
-    _step_parity(sys_pendulum(), st, batch, ha=ha)
+    _step_parity(kernel, sys_pendulum(), st, batch, ha=ha)
 
 
 @pytest.mark.parametrize("ha", [False, True])
-def test_step_parity_tutorial_system(ha):
+def test_step_parity_tutorial_system(kernel, ha):
     rng = np.random.default_rng(2)
     batch = 37
     st = np.stack([rng.uniform(-1, 1, batch), rng.uniform(1, 2, batch)])
     pars = rng.uniform(0.05, 0.2, (1, batch))
     tm = rng.uniform(0, 10, batch)
-    _step_parity(sys_tutorial(), st, batch, pars=pars, time=tm, ha=ha)
+    _step_parity(kernel, sys_tutorial(), st, batch, pars=pars, time=tm, ha=ha)
 
 
 @pytest.mark.parametrize("ha", [False, True])
-def test_step_parity_two_body(ha):
-    _step_parity(sys_two_body(), two_body_batch_state(50), 50, ha=ha)
+def test_step_parity_two_body(kernel, ha):
+    _step_parity(kernel, sys_two_body(), two_body_batch_state(50), 50, ha=ha)
 
 
 @pytest.mark.parametrize("ha", [False, True])
 @pytest.mark.parametrize("batch", [3, 45])
-def test_step_parity_outer_ss(ha, batch):
-    _step_parity(sys_outer_ss(), outer_ss_batch_state(batch), batch, ha=ha, n_steps=2)
+def test_step_parity_outer_ss(kernel, ha, batch):
+    _step_parity(kernel, sys_outer_ss(), outer_ss_batch_state(batch), batch, ha=ha, n_steps=2)
 
 
-def test_step_backward_and_limits():
+def test_step_backward_and_limits(kernel):
     st = outer_ss_batch_state(8)
     P = hb.Program(sys_outer_ss())
     o = oracle.OracleIntegrator(P, st, 8, mode=oracle.FMA)
-    ta = hb.taylor_adaptive_batch(sys_outer_ss(), st, 8)
+    ta = hb.taylor_adaptive_batch(sys_outer_ss(), st, 8, kernel=kernel)
     o.step(backward=True)
     ta.step_backward()
     assert np.all(ta.last_h < 0)
@@ -137,13 +150,13 @@ def test_step_backward_and_limits():
 
 
 @pytest.mark.parametrize("ha", [False, True])
-def test_propagate_parity_outer_ss(ha):
+def test_propagate_parity_outer_ss(kernel, ha):
     """100 years of the perturbed outer Solar System: identical step counts, final state to 1e-12."""
     batch = 40
     st = outer_ss_batch_state(batch)
     P = hb.Program(sys_outer_ss(), high_accuracy=ha)
     o = oracle.OracleIntegrator(P, st, batch, mode=oracle.FMA)
-    ta = hb.taylor_adaptive_batch(sys_outer_ss(), st, batch, high_accuracy=ha)
+    ta = hb.taylor_adaptive_batch(sys_outer_ss(), st, batch, high_accuracy=ha, kernel=kernel)
     o.propagate_until(100.)
     ta.propagate_until(100.)
     assert np.all(ta.time == 100.)
@@ -158,10 +171,10 @@ def test_propagate_parity_outer_ss(ha):
     assert nbody_rel_err(ta.state, st) < 1e-11
 
 
-def test_propagate_exact_step_counts_gpu():
+def test_propagate_exact_step_counts_gpu(kernel):
     """test/taylor_adaptive_batch.cpp:586-598 on the GPU."""
-    ta = hb.taylor_adaptive_batch(sys_pendulum(), [[0.05, 0.06], [0.025, 0.026]], 2)
-    ta2 = hb.taylor_adaptive_batch(sys_pendulum(), [[0.05, 0.06], [0.025, 0.026]], 2)
+    ta = hb.taylor_adaptive_batch(sys_pendulum(), [[0.05, 0.06], [0.025, 0.026]], 2, kernel=kernel)
+    ta2 = hb.taylor_adaptive_batch(sys_pendulum(), [[0.05, 0.06], [0.025, 0.026]], 2, kernel=kernel)
     ta.propagate_until([10., 11.], max_delta_t=[1e-4, 5e-5])
     ta2.propagate_until([10., 11.])
     assert np.all(ta.time == [10., 11.])
@@ -174,7 +187,7 @@ def test_propagate_exact_step_counts_gpu():
     assert [r[3] for r in ta.propagate_res] == [100000, 220000]
 
 
-def test_propagate_per_lane_times_and_dfloat():
+def test_propagate_per_lane_times_and_dfloat(kernel):
     batch = 35
     rng = np.random.default_rng(5)
     st = np.stack([rng.uniform(-1, 1, batch), rng.uniform(-1, 1, batch)])
@@ -183,7 +196,7 @@ def test_propagate_per_lane_times_and_dfloat():
     tf[3] = t0[3]  # zero-length propagation
     P = hb.Program(sys_pendulum())
     o = oracle.OracleIntegrator(P, st, batch, time=t0, mode=oracle.FMA)
-    ta = hb.taylor_adaptive_batch(sys_pendulum(), st, batch, time=t0)
+    ta = hb.taylor_adaptive_batch(sys_pendulum(), st, batch, time=t0, kernel=kernel)
     o.propagate_until(tf)
     ta.propagate_until(tf)
     assert np.array_equal(ta.time, tf) and np.array_equal(o.t_hi, tf)
@@ -192,7 +205,7 @@ def test_propagate_per_lane_times_and_dfloat():
     assert rel_err(ta.state, o.state) < 1e-12
 
 
-def test_global_exits_match_reference_semantics():
+def test_global_exits_match_reference_semantics(kernel):
     """max_steps counts iterations and turns EVERY outcome into step_limit; a non-finite lane stops EVERY
     lane at that iteration (src/taylor_adaptive_batch.cpp:1462-1467, :1516-1526). Checked against the
     oracle's lock-step loop."""
@@ -202,7 +215,7 @@ def test_global_exits_match_reference_semantics():
 
     # iteration limit
     o = oracle.OracleIntegrator(P, st, batch, mode=oracle.FMA)
-    ta = hb.taylor_adaptive_batch(sys_outer_ss(), st, batch)
+    ta = hb.taylor_adaptive_batch(sys_outer_ss(), st, batch, kernel=kernel)
     tf = np.array([0.5, 100., 100., 2.0, 100., 100.])
     o.propagate_until(tf, max_steps=7)
     ta.propagate_until(tf, max_steps=7)
@@ -216,7 +229,7 @@ def test_global_exits_match_reference_semantics():
     st2 = st.copy()
     st2[6:9, 2] = st2[0:3, 2]
     o = oracle.OracleIntegrator(P, st2, batch, mode=oracle.FMA)
-    ta = hb.taylor_adaptive_batch(sys_outer_ss(), st2, batch)
+    ta = hb.taylor_adaptive_batch(sys_outer_ss(), st2, batch, kernel=kernel)
     o.propagate_until(100.)
     ta.propagate_until(100.)
     assert int(o.prop_outcome[2]) == hb.taylor_outcome.err_nf_state
@@ -227,12 +240,12 @@ def test_global_exits_match_reference_semantics():
     assert rel_err(ta.time[ok], o.t_hi[ok]) < 1e-13
 
 
-def test_dense_output():
+def test_dense_output(kernel):
     batch = 9
     st = outer_ss_batch_state(batch)
     P = hb.Program(sys_outer_ss(), high_accuracy=True)
     o = oracle.OracleIntegrator(P, st, batch, mode=oracle.FMA)
-    ta = hb.taylor_adaptive_batch(sys_outer_ss(), st, batch, high_accuracy=True)
+    ta = hb.taylor_adaptive_batch(sys_outer_ss(), st, batch, high_accuracy=True, kernel=kernel)
     o.step(write_tc=True)
     ta.step(write_tc=True)
     tau = 0.37 * o.last_h
@@ -263,3 +276,18 @@ def test_raw_program_interface_matches():
         res.append(b.download()[0])
     assert np.array_equal(res[0], res[1])
     assert n_ops == 21 - 12
+
+
+def test_kernel_selection_info():
+    """Automatic selection: shared-memory tape for the 6-body system (3 x 4 lanes per SM), HBM tape when the
+    tape cannot fit (32 bodies)."""
+    b = hb.Batch(hb.Program(sys_outer_ss(), high_accuracy=True), 64)
+    ki = b.kernel_info()
+    assert ki["tape"] == "smem" and ki["tape_slots_per_lane"] < 234 * 21 / 2
+    assert ki["smem_bytes"] <= 227 * 1024
+    b.set_kernel("hbm")
+    assert b.kernel_info()["tape"] == "hbm"
+    big = hb.Batch(hb.Program(hb.model.nbody(32)), 32)
+    assert big.kernel_info()["tape"] == "hbm"
+    with pytest.raises(ValueError, match="does not fit in shared memory"):
+        big.set_kernel("smem")
