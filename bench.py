@@ -43,6 +43,9 @@ def parse_args():
     ap.add_argument("--perturb", type=float, default=1e-3)
     ap.add_argument("--cpu-lanes", type=int, default=0, help="lanes of the CPU sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--tape", default="auto", choices=["auto", "hbm", "smem"])
+    ap.add_argument("--lanes-per-warp", type=int, default=0)
+    ap.add_argument("--lanes-per-thread", type=int, default=0)
     ap.add_argument("--block-threads", type=int, default=0)
     ap.add_argument("--blocks-per-sm", type=int, default=0)
     return ap.parse_args()
@@ -211,8 +214,9 @@ def main():
     b = hb.Batch(P, n, device=local_rank)
     stream = torch.cuda.current_stream()
     b.set_stream(stream.cuda_stream)
-    if args.block_threads or args.blocks_per_sm:
-        b.set_launch_config(args.block_threads, args.blocks_per_sm)
+    if args.tape != "auto" or args.lanes_per_warp or args.lanes_per_thread or args.block_threads or args.blocks_per_sm:
+        b.set_kernel(args.tape, args.lanes_per_warp, args.lanes_per_thread, args.block_threads, args.blocks_per_sm)
+    kinfo = b.kernel_info()
     ptrs = b.ptrs()
 
     # Device-resident inputs: initial state, final times; torch owns these buffers.
@@ -356,7 +360,9 @@ def main():
                 "parallelism": "lanes sharded across %d GPU(s), final-state all_gather" % world,
             },
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                         "traffic": None, "peak_kind": peak_kind, "kernel": "k_propagate",
+                         "traffic": None, "peak_kind": peak_kind,
+                         "kernel": "k_coop<L=%d,N=%d,prop>" % (kinfo["lanes_per_warp"], kinfo["lanes_per_thread"])
+                         if kinfo["tape"] == "smem" else "k_hbm<prop>", "kernel_config": kinfo,
                          "kernel_ms": k_ms, "b_tape_bytes_per_lane_step": costs["b_tape"],
                          "b_min_bytes_per_lane_step": costs["b_min"],
                          "frac_b_min": lane_steps_rank * costs["b_min"] / (k_ms * 1e-3) / 1e9 / peak,

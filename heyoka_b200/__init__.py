@@ -298,9 +298,9 @@ class Batch:
     def set_launch_config(self, block_threads=0, blocks_per_sm=0):
         check(lib.hy_batch_set_launch_config(self._h, int(block_threads), int(blocks_per_sm)))
 
-    def set_kernel(self, tape="auto", lanes_per_cta=0, lanes_per_thread=0, block_threads=0, blocks_per_sm=0):
+    def set_kernel(self, tape="auto", lanes_per_warp=0, lanes_per_thread=0, block_threads=0, blocks_per_sm=0):
         mode = {"auto": 0, "hbm": 1, "smem": 2}[tape]
-        check(lib.hy_batch_set_kernel(self._h, mode, int(lanes_per_cta), int(lanes_per_thread), int(block_threads),
+        check(lib.hy_batch_set_kernel(self._h, mode, int(lanes_per_warp), int(lanes_per_thread), int(block_threads),
                                       int(blocks_per_sm)))
 
     def kernel_info(self):

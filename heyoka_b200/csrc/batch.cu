@@ -53,9 +53,9 @@ struct coop_variant {
         L, N, dev::k_coop<L, N, false>, dev::k_coop<L, N, true>                                                        \
     }
 
-const coop_variant coop_variants[] = {HY_COOP(1, 1),  HY_COOP(2, 1),  HY_COOP(4, 1),  HY_COOP(8, 1), HY_COOP(16, 1),
-                                      HY_COOP(32, 1), HY_COOP(2, 2),  HY_COOP(4, 2),  HY_COOP(8, 2), HY_COOP(16, 2),
-                                      HY_COOP(32, 2)};
+const coop_variant coop_variants[] = {HY_COOP(1, 1),  HY_COOP(2, 1),  HY_COOP(4, 1),  HY_COOP(8, 1),  HY_COOP(16, 1),
+                                      HY_COOP(32, 1), HY_COOP(2, 2),  HY_COOP(4, 2),  HY_COOP(8, 2),  HY_COOP(16, 2),
+                                      HY_COOP(32, 2), HY_COOP(4, 4),  HY_COOP(8, 4),  HY_COOP(16, 4), HY_COOP(32, 4)};
 #undef HY_COOP
 
 const coop_variant *find_variant(int L, int N)
@@ -68,10 +68,11 @@ const coop_variant *find_variant(int L, int N)
     return nullptr;
 }
 
-std::size_t coop_smem_bytes(std::uint32_t n_slots, int L)
+// Shared memory of one warp owning L lanes (must match dev::coop_smem<L>::warp_doubles()).
+std::size_t coop_warp_bytes(std::uint32_t n_slots, int L)
 {
-    const std::size_t extra = 3u * L * sizeof(double) + L * sizeof(int) + 16u;
-    return static_cast<std::size_t>(n_slots) * L * sizeof(double) + extra;
+    const std::size_t l = static_cast<std::size_t>(L);
+    return (static_cast<std::size_t>(n_slots) * l + 2u * l + (l + 1u) / 2u + 1u) / 2u * 2u * sizeof(double);
 }
 
 } // namespace
@@ -233,50 +234,63 @@ void hy_batch::setup_hbm(std::uint32_t threads, std::uint32_t blocks_per_sm)
 }
 
 // Returns false if the requested / any configuration does not fit in shared memory.
+// L = lanes per warp, N = lanes per thread, threads = 32 x warps per block.
 bool hy_batch::setup_coop(int L, int N, std::uint32_t threads, std::uint32_t ctas_per_sm)
 {
     const std::size_t reserve = 1024u; // per-block reservation of the driver
-    if (L == 0) {
-        // Maximise the lanes resident per SM; prefer >= 2 CTAs per SM (one computes while the other waits at
-        // a barrier), then the larger L (more uniform warps).
-        std::uint32_t best_lanes = 0;
-        for (const int cand : {32, 16, 8, 4, 2, 1}) {
-            const auto bytes = coop_smem_bytes(plan.n_slots, cand);
-            if (bytes > smem_per_block_max) {
-                continue;
-            }
-            const auto ctas = std::min<std::size_t>(smem_per_sm / (bytes + reserve), 8u);
-            if (ctas == 0u) {
-                continue;
-            }
-            const auto lanes = static_cast<std::uint32_t>(ctas * cand);
-            if (lanes > best_lanes) {
-                best_lanes = lanes;
-                L = cand;
-            }
-        }
-        if (L == 0) {
-            return false;
-        }
-    }
     if (N == 0) {
         N = 1;
     }
+    if (L == 0) {
+        // Lanes per warp: enough of them that an average dependency segment gives work to most of the
+        // 32 threads (one work item = one u variable x N lanes), as long as at least 4 warps fit on an SM.
+        const double avg_width = static_cast<double>(plan.ops.size()) / std::max(1u, plan.n_segments);
+        for (const int cand : {1, 2, 4, 8, 16, 32}) {
+            if (cand < N) {
+                continue;
+            }
+            const auto bytes = coop_warp_bytes(plan.n_slots, cand);
+            if (bytes + reserve > smem_per_block_max || smem_per_sm / (bytes + reserve / 4u) < 4u) {
+                break;
+            }
+            L = cand;
+            if (avg_width * cand / N >= 20.) {
+                break;
+            }
+        }
+        if (L == 0) {
+            // Not even 4 warps of the smallest shape fit: take whatever fits at all.
+            if (coop_warp_bytes(plan.n_slots, N) + reserve > smem_per_block_max) {
+                return false;
+            }
+            L = N;
+        }
+    }
     const auto *v = find_variant(L, N);
     if (v == nullptr) {
-        throw std::invalid_argument("Unsupported cooperative kernel configuration L = " + std::to_string(L)
-                                    + ", N = " + std::to_string(N));
+        throw std::invalid_argument("Unsupported cooperative kernel configuration: " + std::to_string(L)
+                                    + " lanes per warp, " + std::to_string(N) + " lanes per thread");
     }
-    const auto bytes = coop_smem_bytes(plan.n_slots, L);
-    if (bytes > smem_per_block_max) {
+    const auto warp_bytes = coop_warp_bytes(plan.n_slots, L);
+    if (warp_bytes + reserve > smem_per_block_max) {
         return false;
     }
+    // Registers allow ~40 warps per SM (48 registers/thread); shared memory usually far fewer.
+    const std::size_t warps_fit = std::min<std::size_t>(smem_per_sm / warp_bytes, 40u);
     if (threads == 0u) {
-        const std::uint32_t items = std::max(plan.max_seg_width, n_eq) * static_cast<std::uint32_t>(L / N);
-        threads = std::min(256u, std::max(32u, (items + 31u) / 32u * 32u));
+        // Keep the number of CTAs per SM moderate (<= 16): W warps per block.
+        std::size_t W = std::max<std::size_t>(1u, (warps_fit + 15u) / 16u);
+        while (W > 1u && W * warp_bytes + reserve > smem_per_block_max) {
+            --W;
+        }
+        threads = static_cast<std::uint32_t>(32u * std::min<std::size_t>(W, 8u));
     }
-    if (threads % 32u != 0u || threads > 256u || threads < static_cast<std::uint32_t>(L)) {
+    if (threads % 32u != 0u || threads == 0u || threads > 256u) {
         throw std::invalid_argument("Invalid number of threads for the cooperative kernel");
+    }
+    const std::size_t bytes = static_cast<std::size_t>(threads / 32u) * warp_bytes;
+    if (bytes + reserve > smem_per_block_max) {
+        return false;
     }
     for (auto fn : {v->step, v->prop}) {
         HY_CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes)));
@@ -290,8 +304,9 @@ bool hy_batch::setup_coop(int L, int N, std::uint32_t threads, std::uint32_t cta
     c_threads = threads;
     c_smem = bytes;
     c_ctas_per_sm = ctas_per_sm;
-    const std::uint32_t n_chunks = (n + static_cast<std::uint32_t>(L) - 1u) / static_cast<std::uint32_t>(L);
-    c_grid = std::max(1u, std::min(n_sms * ctas_per_sm, n_chunks));
+    const std::uint32_t lanes_per_block = static_cast<std::uint32_t>(L) * (threads / 32u);
+    const std::uint32_t n_blocks_needed = (n + lanes_per_block - 1u) / lanes_per_block;
+    c_grid = std::max(1u, std::min(n_sms * ctas_per_sm, n_blocks_needed));
     mode = 2;
     return true;
 }
@@ -594,7 +609,7 @@ int hy_batch_set_launch_config(hy_batch *b, uint32_t block_threads, uint32_t blo
     }
 }
 
-int hy_batch_set_kernel(hy_batch *b, int tape_mode, uint32_t lanes_per_cta, uint32_t lanes_per_thread,
+int hy_batch_set_kernel(hy_batch *b, int tape_mode, uint32_t lanes_per_warp, uint32_t lanes_per_thread,
                         uint32_t block_threads, uint32_t blocks_per_sm)
 {
     try {
@@ -606,7 +621,7 @@ int hy_batch_set_kernel(hy_batch *b, int tape_mode, uint32_t lanes_per_cta, uint
         }
         device_guard guard(b->device);
         HY_CUDA_CHECK(cudaStreamSynchronize(b->stream));
-        b->configure(tape_mode, static_cast<int>(lanes_per_cta), static_cast<int>(lanes_per_thread), block_threads,
+        b->configure(tape_mode, static_cast<int>(lanes_per_warp), static_cast<int>(lanes_per_thread), block_threads,
                      blocks_per_sm);
         return HY_OK;
     } catch (...) {
@@ -621,7 +636,7 @@ int hy_batch_get_kernel(const hy_batch *b, hy_kernel_info *out)
         return HY_ERR_INVALID_ARG;
     }
     out->tape_mode = b->mode;
-    out->lanes_per_cta = b->mode == 2 ? static_cast<uint32_t>(b->cv->L) : 32u;
+    out->lanes_per_warp = b->mode == 2 ? static_cast<uint32_t>(b->cv->L) : 32u;
     out->lanes_per_thread = b->mode == 2 ? static_cast<uint32_t>(b->cv->N) : 1u;
     out->block_threads = b->mode == 2 ? b->c_threads : b->h_threads;
     out->blocks_per_sm = b->mode == 2 ? b->c_ctas_per_sm : b->h_blocks_per_sm;

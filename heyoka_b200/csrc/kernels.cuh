@@ -162,6 +162,15 @@ struct hbm_tape {
 
     struct row_t {
         double *p;
+        static constexpr std::uint32_t stride = 32u;
+        __device__ __forceinline__ static vd<1> load(const double *q)
+        {
+            return vd<1>{{*q}};
+        }
+        __device__ __forceinline__ const double *hptr(std::uint32_t o) const
+        {
+            return p + static_cast<std::size_t>(o) * 32u;
+        }
         __device__ __forceinline__ vd<1> at(std::uint32_t o) const
         {
             return vd<1>{{p[static_cast<std::size_t>(o) * 32u]}};
@@ -308,11 +317,14 @@ __global__ void __launch_bounds__(256) k_hbm(program P, batch D, run_args R, dou
 }
 
 // ================================================================================================
-// "coop" strategy.
+// "coop" strategy: warp-cooperative, tape in shared memory.
+// A warp owns L lanes and a private slice of shared memory; its 32 threads are (32 / G) workers x G lane
+// groups of N lanes (G = L / N). Segments and orders are separated by __syncwarp() only: warps never
+// wait for each other, the SM interleaves them.
 // ================================================================================================
 template <int L, int N>
 struct smem_tape {
-    double *base; // shared-memory tape + first lane of this thread's group
+    double *base; // the warp's tape + first lane of this thread's group
     const double *pars;
     std::uint32_t batch;
     std::uint32_t glane[N]; // global lane indices (clamped to valid lanes)
@@ -321,14 +333,21 @@ struct smem_tape {
     struct row_t {
         double *p;
         std::uint32_t mask;
-        __device__ __forceinline__ vd<N> at(std::uint32_t o) const
+        static constexpr std::uint32_t stride = L;
+        __device__ __forceinline__ static vd<N> load(const double *q)
         {
-            const double *q = p + (o & mask) * L;
             vd<N> r;
             if constexpr (N == 2) {
                 const double2 x = *reinterpret_cast<const double2 *>(q);
                 r.v[0] = x.x;
                 r.v[1] = x.y;
+            } else if constexpr (N == 4) {
+                const double2 x = *reinterpret_cast<const double2 *>(q);
+                const double2 y = *reinterpret_cast<const double2 *>(q + 2);
+                r.v[0] = x.x;
+                r.v[1] = x.y;
+                r.v[2] = y.x;
+                r.v[3] = y.y;
             } else {
 #pragma unroll
                 for (int i = 0; i < N; ++i) {
@@ -337,11 +356,23 @@ struct smem_tape {
             }
             return r;
         }
+        // Address of the order-o coefficient of a HISTORY row (convolution operands always are).
+        __device__ __forceinline__ const double *hptr(std::uint32_t o) const
+        {
+            return p + o * L;
+        }
+        __device__ __forceinline__ vd<N> at(std::uint32_t o) const
+        {
+            return load(p + (o & mask) * L);
+        }
         __device__ __forceinline__ void set(std::uint32_t o, const vd<N> &v) const
         {
             double *q = p + (o & mask) * L;
             if constexpr (N == 2) {
                 *reinterpret_cast<double2 *>(q) = make_double2(v.v[0], v.v[1]);
+            } else if constexpr (N == 4) {
+                *reinterpret_cast<double2 *>(q) = make_double2(v.v[0], v.v[1]);
+                *reinterpret_cast<double2 *>(q + 2) = make_double2(v.v[2], v.v[3]);
             } else {
 #pragma unroll
                 for (int i = 0; i < N; ++i) {
@@ -372,24 +403,25 @@ struct smem_tape {
     }
 };
 
-// Shared-memory layout of a cooperative CTA: tape[n_slots][L], then per-lane scalars.
+// Shared memory of one warp: tape[n_slots][L], then per-lane scalars.
 template <int L>
 struct coop_smem {
     double *tape;
-    double *time, *cur_max, *h;
+    double *time, *h;
     int *running;
-    unsigned int *chunk;
 
-    __device__ __forceinline__ coop_smem(double *smem, std::uint32_t n_slots)
+    __device__ __forceinline__ coop_smem(double *smem, std::uint32_t n_slots, std::uint32_t warp_in_block)
     {
-        tape = smem;
-        time = smem + static_cast<std::size_t>(n_slots) * L;
-        cur_max = time + L;
-        h = cur_max + L;
+        tape = smem + static_cast<std::size_t>(warp_in_block) * warp_doubles(n_slots);
+        time = tape + static_cast<std::size_t>(n_slots) * L;
+        h = time + L;
         running = reinterpret_cast<int *>(h + L);
-        chunk = reinterpret_cast<unsigned int *>(running + L);
     }
-    static constexpr std::size_t extra_bytes = 3u * L * sizeof(double) + L * sizeof(int) + 16u;
+    // Doubles of shared memory per warp (tape + scalars, kept 16-byte aligned).
+    __host__ __device__ static constexpr std::size_t warp_doubles(std::uint32_t n_slots)
+    {
+        return (static_cast<std::size_t>(n_slots) * L + 2u * L + (L + 1u) / 2u + 1u) / 2u * 2u;
+    }
 };
 
 // Jet of the L lanes starting at global lane `lane0`; the state variables' coefficients go to tc.
@@ -397,25 +429,25 @@ template <int L, int N>
 __device__ __forceinline__ void coop_jet(const program &P, const coop_tables &X, const batch &D,
                                          const coop_smem<L> &S, std::uint32_t lane0)
 {
-    constexpr std::uint32_t G = L / N; // lane groups per CTA
-    const std::uint32_t tid = threadIdx.x, nthr = blockDim.x;
+    constexpr std::uint32_t G = L / N; // lane groups per warp
+    const std::uint32_t tid = threadIdx.x & 31u;
+    constexpr std::uint32_t nthr = 32u;
     const std::uint32_t pp1 = P.order + 1u;
 
-    const auto make_tape = [&](std::uint32_t g) {
-        smem_tape<L, N> t;
-        t.base = S.tape + g * N;
-        t.pars = D.pars;
-        t.batch = D.n;
+    // This thread always works on the same lane group: g = tid % G.
+    smem_tape<L, N> t;
+    const std::uint32_t g = tid % G;
+    t.base = S.tape + g * N;
+    t.pars = D.pars;
+    t.batch = D.n;
 #pragma unroll
-        for (int i = 0; i < N; ++i) {
-            const std::uint32_t l = lane0 + g * N + i;
-            t.glane[i] = l < D.n ? l : D.n - 1u;
-            t.tm.v[i] = S.time[g * N + i];
-        }
-        return t;
-    };
+    for (int i = 0; i < N; ++i) {
+        const std::uint32_t l = lane0 + g * N + i;
+        t.glane[i] = l < D.n ? l : D.n - 1u;
+        t.tm.v[i] = S.time[g * N + i];
+    }
     // Stream the coefficient of state variable sv at order n to tc (valid lanes only).
-    const auto write_tc = [&](std::uint32_t sv, std::uint32_t n, std::uint32_t g, const vd<N> &v) {
+    const auto write_tc = [&](std::uint32_t sv, std::uint32_t n, const vd<N> &v) {
         double *dst = D.tc + (static_cast<std::size_t>(sv) * pp1 + n) * D.n;
 #pragma unroll
         for (int i = 0; i < N; ++i) {
@@ -426,31 +458,29 @@ __device__ __forceinline__ void coop_jet(const program &P, const coop_tables &X,
         }
     };
 
-    // Order 0 of the state variables: the state itself.
+    // Order 0 of the state variables: the state itself. (it % G == g because nthr is a multiple of G.)
     for (std::uint32_t it = tid; it < P.n_eq * G; it += nthr) {
-        const std::uint32_t sv = it / G, g = it % G;
-        const auto t = make_tape(g);
+        const std::uint32_t sv = it / G;
         vd<N> v;
 #pragma unroll
         for (int i = 0; i < N; ++i) {
             v.v[i] = D.state[static_cast<std::size_t>(sv) * D.n + t.glane[i]];
         }
         t.row(__ldg(X.sv_rows + sv)).set(0u, v);
-        write_tc(sv, 0u, g, v);
+        write_tc(sv, 0u, v);
     }
-    __syncthreads();
+    __syncwarp();
 
     for (std::uint32_t n = 0; n <= P.order; ++n) {
         if (n > 0u) {
             // State variables: x^[n] = (rhs)^[n-1] / n.
             for (std::uint32_t it = tid; it < P.n_eq * G; it += nthr) {
-                const std::uint32_t sv = it / G, g = it % G;
-                const auto t = make_tape(g);
+                const std::uint32_t sv = it / G;
                 const vd<N> v = sv_diff<N>(P, t, __ldg(P.sv_defs + sv), n);
                 t.row(__ldg(X.sv_rows + sv)).set(n, v);
-                write_tc(sv, n, g, v);
+                write_tc(sv, n, v);
             }
-            __syncthreads();
+            __syncwarp();
         }
         if (n == P.order) {
             break;
@@ -459,19 +489,17 @@ __device__ __forceinline__ void coop_jet(const program &P, const coop_tables &X,
         for (std::uint32_t s = 0; s < X.n_segments; ++s) {
             const std::uint32_t b = __ldg(X.seg_offsets + s), e = __ldg(X.seg_offsets + s + 1u);
             for (std::uint32_t it = tid; it < (e - b) * G; it += nthr) {
-                const std::uint32_t k = b + it / G, g = it % G;
-                const auto t = make_tape(g);
+                const std::uint32_t k = b + it / G;
                 const uint4 op = __ldg(P.ops + k);
                 const auto self = t.row(__ldg(X.dst + k));
                 self.set(n, diff_op<N>(P, t, op, self, n));
             }
-            __syncthreads();
+            __syncwarp();
         }
     }
 }
 
-// Step-size estimate of lane `l` (CTA-local index) from the coefficients streamed to tc.
-template <int L>
+// Step-size estimate of one lane from the coefficients streamed to tc.
 __device__ __forceinline__ double coop_determine_h(const program &P, const batch &D, std::uint32_t glane,
                                                    double max_delta_t)
 {
@@ -488,14 +516,14 @@ __device__ __forceinline__ double coop_determine_h(const program &P, const batch
     return h_from_norms(P, m0, mp, mp1, max_delta_t);
 }
 
-// State update of the CTA's lanes: item = (state variable, lane); S.h holds the step sizes, S.running
+// State update of the warp's lanes: item = (state variable, lane); S.h holds the step sizes, S.running
 // which lanes may be written.
 template <int L>
 __device__ __forceinline__ void coop_update_state(const program &P, const batch &D, const coop_smem<L> &S,
                                                   std::uint32_t lane0)
 {
     const std::uint32_t pp1 = P.order + 1u;
-    for (std::uint32_t it = threadIdx.x; it < P.n_eq * L; it += blockDim.x) {
+    for (std::uint32_t it = threadIdx.x & 31u; it < P.n_eq * L; it += 32u) {
         const std::uint32_t sv = it / L, l = it % L;
         const std::uint32_t glane = lane0 + l;
         if (glane < D.n && S.running[l]) {
@@ -508,33 +536,21 @@ __device__ __forceinline__ void coop_update_state(const program &P, const batch 
     }
 }
 
-template <int L>
-__device__ __forceinline__ std::uint32_t claim_chunk_cta(unsigned int *counter, const coop_smem<L> &S)
-{
-    __syncthreads();
-    if (threadIdx.x == 0u) {
-        *S.chunk = atomicAdd(counter, 1u);
-    }
-    __syncthreads();
-    return *S.chunk;
-}
-
 template <int L, int N, bool PROP>
 __global__ void __launch_bounds__(256) k_coop(program P, coop_tables X, batch D, run_args R)
 {
     extern __shared__ __align__(16) double smem_raw[];
-    const coop_smem<L> S(smem_raw, X.n_slots);
-    const std::uint32_t tid = threadIdx.x;
+    const std::uint32_t tid = threadIdx.x & 31u;
+    const coop_smem<L> S(smem_raw, X.n_slots, threadIdx.x >> 5);
     const std::uint32_t n_chunks = (D.n + L - 1u) / L;
     const bool owner = tid < L;
 
-    for (std::uint32_t chunk = claim_chunk_cta<L>(R.counter, S); chunk < n_chunks;
-         chunk = claim_chunk_cta<L>(R.counter, S)) {
+    for (std::uint32_t chunk = claim_chunk_warp(R.counter); chunk < n_chunks; chunk = claim_chunk_warp(R.counter)) {
         const std::uint32_t lane0 = chunk * L;
         // Owner threads (one per lane) do the scalar bookkeeping of their lane.
         const std::uint32_t lane_raw = lane0 + tid;
         const bool valid = owner && lane_raw < D.n;
-        const std::uint32_t lane = (owner && lane_raw < D.n) ? lane_raw : D.n - 1u;
+        const std::uint32_t lane = valid ? lane_raw : D.n - 1u;
 
         if constexpr (!PROP) {
             double mdt = 0.;
@@ -545,16 +561,16 @@ __global__ void __launch_bounds__(256) k_coop(program P, coop_tables X, batch D,
                 S.time[tid] = t0.hi;
                 S.running[tid] = 1;
             }
-            __syncthreads();
+            __syncwarp();
             coop_jet<L, N>(P, X, D, S, lane0);
             double h = 0.;
             if (owner) {
-                h = coop_determine_h<L>(P, D, lane, mdt);
+                h = coop_determine_h(P, D, lane, mdt);
                 S.h[tid] = h;
             }
-            __syncthreads();
+            __syncwarp();
             coop_update_state<L>(P, D, S, lane0);
-            __syncthreads();
+            __syncwarp();
             if (valid) {
                 const dfl nt = dfl_add(t0, dfl{h, 0.});
                 D.t_hi[lane] = nt.hi;
@@ -570,33 +586,32 @@ __global__ void __launch_bounds__(256) k_coop(program P, coop_tables X, batch D,
             if (owner) {
                 lp.init(D, R, lane);
             }
-            int any = 1;
-            while (any) {
+            while (__any_sync(0xffffffffu, owner && lp.running)) {
                 double cur_max = 0.;
                 if (owner) {
                     cur_max = lp.cur_max();
                     S.time[tid] = lp.t.hi;
                     S.running[tid] = lp.running ? 1 : 0;
                 }
-                __syncthreads();
+                __syncwarp();
                 coop_jet<L, N>(P, X, D, S, lane0);
                 double h = 0.;
                 if (owner) {
-                    h = coop_determine_h<L>(P, D, lane, cur_max);
+                    h = coop_determine_h(P, D, lane, cur_max);
                     S.h[tid] = h;
                 }
-                __syncthreads();
+                __syncwarp();
                 coop_update_state<L>(P, D, S, lane0);
-                __syncthreads();
+                __syncwarp();
                 if (owner && lp.running) {
                     lp.advance(h, cur_max, lane_state_nonfinite(P, D, lane), R, valid);
                 }
-                any = __syncthreads_or(owner && lp.running ? 1 : 0);
             }
             if (valid) {
                 lp.store(D, lane);
             }
         }
+        __syncwarp();
     }
 }
 

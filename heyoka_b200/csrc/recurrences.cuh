@@ -157,16 +157,21 @@ __device__ __forceinline__ vd<N> pairwise8(vd<N> (&v)[8], std::uint32_t n)
     return (m2 > 1u) ? x[0] + x[1] : x[0];
 }
 
-// sum_{j=j0..j1} A^[n-j] B^[j].
+// sum_{j=j0..j1} A^[n-j] B^[j]. A and B are history rows: walked with two pointers (strides known at
+// compile time, so the unrolled loop addresses with immediates).
 template <int N, typename Row>
 __device__ __forceinline__ vd<N> conv_plain(const Row &A, const Row &B, std::uint32_t n, std::uint32_t j0,
                                             std::uint32_t j1)
 {
     vd<N> acc = splat<N>(0.);
     if (j1 + 1u > j0) {
+        const double *pa = A.hptr(n - j0), *pb = B.hptr(j0);
+        constexpr int S = static_cast<int>(Row::stride);
 #pragma unroll 4
         for (std::uint32_t j = j0; j <= j1; ++j) {
-            acc = vfma(A.at(n - j), B.at(j), acc);
+            acc = vfma(Row::load(pa), Row::load(pb), acc);
+            pa -= S;
+            pb += S;
         }
     }
     return acc;
@@ -179,9 +184,13 @@ __device__ __forceinline__ vd<N> conv_jw(const Row &A, const Row &B, std::uint32
 {
     vd<N> acc = splat<N>(0.);
     if (j1 + 1u > j0) {
+        const double *pa = A.hptr(n - j0), *pb = B.hptr(j0);
+        constexpr int S = static_cast<int>(Row::stride);
 #pragma unroll 4
         for (std::uint32_t j = j0; j <= j1; ++j) {
-            acc = vfma(static_cast<double>(j), A.at(n - j) * B.at(j), acc);
+            acc = vfma(static_cast<double>(j), Row::load(pa) * Row::load(pb), acc);
+            pa -= S;
+            pb += S;
         }
     }
     return acc;
@@ -459,10 +468,14 @@ __device__ __forceinline__ vd<N> diff_op(const program &P, const Tape &t, const 
             const V ap1 = alpha + 1.;
             const V n_alpha = nd * alpha;
             V acc = splat<N>(0.);
+            const double *pb = B.hptr(n), *pa = self.hptr(0u);
+            constexpr int S = static_cast<int>(Row::stride);
 #pragma unroll 4
             for (std::uint32_t j = 0; j < n; ++j) {
                 const V fac = n_alpha - static_cast<double>(j) * ap1;
-                acc = vfma(fac, B.at(n - j) * self.at(j), acc);
+                acc = vfma(fac, Row::load(pb) * Row::load(pa), acc);
+                pb -= S;
+                pa += S;
             }
             return acc / (nd * B.at(0u));
         }

@@ -71,7 +71,7 @@ def test_outer_ss_2pow20_energy_and_sample():
     oc, mn, mx, ns = b.prop_res()
     assert np.all(oc == hb.taylor_outcome.time_limit)
     assert np.all(t_hi == 5.0)
-    assert ns.min() >= 10 and ns.max() <= 30
+    assert ns.min() >= 5 and ns.max() <= 30
     e0 = nbody_energy(st, OUTER_SS_MASSES, OUTER_SS_G)
     e1 = nbody_energy(new, OUTER_SS_MASSES, OUTER_SS_G)
     assert np.max(np.abs(e1 / e0 - 1)) < 5e-15 * 20

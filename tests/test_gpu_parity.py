@@ -23,8 +23,9 @@ OC = {"success": hb.taylor_outcome.success, "time_limit": hb.taylor_outcome.time
 KERNELS = {
     "hbm": dict(tape="hbm"),
     "smem-auto": dict(tape="smem"),
-    "smem-L8N2": dict(tape="smem", lanes_per_cta=8, lanes_per_thread=2),
-    "smem-L2N1": dict(tape="smem", lanes_per_cta=2, lanes_per_thread=1, block_threads=64),
+    "smem-L8N2": dict(tape="smem", lanes_per_warp=8, lanes_per_thread=2),
+    "smem-L2N1": dict(tape="smem", lanes_per_warp=2, lanes_per_thread=1, block_threads=64),
+    "smem-L4N4": dict(tape="smem", lanes_per_warp=4, lanes_per_thread=4, block_threads=32),
 }
 
 
