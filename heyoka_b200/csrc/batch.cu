@@ -96,7 +96,7 @@ struct hy_batch {
     hy::detail::smem_plan plan;
     uint4 *d_c_ops = nullptr;
     std::uint32_t *d_c_args = nullptr, *d_c_sv_defs = nullptr, *d_c_dst = nullptr, *d_c_seg = nullptr,
-                  *d_c_sv_rows = nullptr;
+                  *d_c_sv_rows = nullptr, *d_c_aux = nullptr;
     dev::program c_prog{};
     dev::coop_tables c_tabs{};
 
@@ -162,7 +162,8 @@ void hy_batch::free_all() noexcept
          {static_cast<void *>(d_ops), static_cast<void *>(d_args), static_cast<void *>(d_sv_defs),
           static_cast<void *>(d_consts), static_cast<void *>(d_c_ops), static_cast<void *>(d_c_args),
           static_cast<void *>(d_c_sv_defs), static_cast<void *>(d_c_dst), static_cast<void *>(d_c_seg),
-          static_cast<void *>(d_c_sv_rows), static_cast<void *>(d_state), static_cast<void *>(d_pars),
+          static_cast<void *>(d_c_sv_rows), static_cast<void *>(d_c_aux), static_cast<void *>(d_state),
+          static_cast<void *>(d_pars),
           static_cast<void *>(d_t_hi), static_cast<void *>(d_t_lo), static_cast<void *>(d_last_h),
           static_cast<void *>(d_tc), static_cast<void *>(d_d_out), static_cast<void *>(d_step_outcome),
           static_cast<void *>(d_prop_outcome), static_cast<void *>(d_prop_min_h), static_cast<void *>(d_prop_max_h),
@@ -510,13 +511,19 @@ int hy_batch_create(const hy_program *p, uint32_t batch, int device, hy_batch **
         P.sv_defs = b->d_sv_defs;
 
         // Cooperative plan.
-        b->plan = hy::detail::make_smem_plan(*p);
+        // HEYOKA_B200_FUSE=0 disables the superinstructions (diagnostics / tests).
+        bool fuse = true;
+        if (const char *env = std::getenv("HEYOKA_B200_FUSE")) {
+            fuse = std::string{env} != "0";
+        }
+        b->plan = hy::detail::make_smem_plan(*p, fuse);
         b->d_c_ops = reinterpret_cast<uint4 *>(b->dupload(b->plan.ops));
         b->d_c_args = b->dupload(b->plan.args);
         b->d_c_sv_defs = b->dupload(b->plan.sv_defs);
         b->d_c_dst = b->dupload(b->plan.dst);
         b->d_c_seg = b->dupload(b->plan.seg_offsets);
         b->d_c_sv_rows = b->dupload(b->plan.sv_rows);
+        b->d_c_aux = b->dupload(b->plan.aux);
         b->c_prog = P;
         b->c_prog.ops = b->d_c_ops;
         b->c_prog.args = b->d_c_args;
@@ -524,6 +531,7 @@ int hy_batch_create(const hy_program *p, uint32_t batch, int device, hy_batch **
         b->c_tabs.dst = b->d_c_dst;
         b->c_tabs.seg_offsets = b->d_c_seg;
         b->c_tabs.sv_rows = b->d_c_sv_rows;
+        b->c_tabs.aux = b->d_c_aux;
         b->c_tabs.n_segments = b->plan.n_segments;
         b->c_tabs.n_slots = b->plan.n_slots;
 
@@ -644,6 +652,7 @@ int hy_batch_get_kernel(const hy_batch *b, hy_kernel_info *out)
     out->smem_bytes = b->mode == 2 ? static_cast<uint64_t>(b->c_smem) : 0u;
     out->tape_slots_per_lane = b->mode == 2 ? b->plan.n_slots : b->n_uvars * (b->order + 1u);
     out->n_segments = b->plan.n_segments;
+    out->n_fused = b->plan.n_fused;
     out->n_sms = b->n_sms;
     return HY_OK;
 }

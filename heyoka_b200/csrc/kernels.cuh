@@ -26,6 +26,7 @@
 
 #include "device_program.cuh"
 #include "recurrences.cuh"
+#include "fused.cuh"
 
 namespace heyoka_b200::dev
 {
@@ -49,6 +50,7 @@ struct coop_tables {
     const std::uint32_t *dst;         // row reference of each op's result
     const std::uint32_t *seg_offsets; // n_segments + 1
     const std::uint32_t *sv_rows;     // row reference of each state variable
+    const std::uint32_t *aux;         // operand tables of the superinstructions
     std::uint32_t n_segments;
     std::uint32_t n_slots;
 };
@@ -491,8 +493,12 @@ __device__ __forceinline__ void coop_jet(const program &P, const coop_tables &X,
             for (std::uint32_t it = tid; it < (e - b) * G; it += nthr) {
                 const std::uint32_t k = b + it / G;
                 const uint4 op = __ldg(P.ops + k);
-                const auto self = t.row(__ldg(X.dst + k));
-                self.set(n, diff_op<N>(P, t, op, self, n));
+                if (op.x >= FOP_FIRST) {
+                    fused_nbody_pair<N>(P, t, X.aux + op.y, op.z, op.w != 0u, n);
+                } else {
+                    const auto self = t.row(__ldg(X.dst + k));
+                    self.set(n, diff_op<N>(P, t, op, self, n));
+                }
             }
             __syncwarp();
         }

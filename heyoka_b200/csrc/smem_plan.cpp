@@ -2,6 +2,7 @@
 #include "smem_plan.hpp"
 
 #include <algorithm>
+#include <map>
 #include <numeric>
 #include <stdexcept>
 
@@ -90,9 +91,19 @@ op_uses uses_of(const hy_program &p, const hy_op &op)
     return u;
 }
 
+// One schedulable work item: an elementary op, or a fused group of them.
+struct item {
+    hy_op op;                        // for fused items: op.opcode = HY_FOP_*, op.a = offset into aux
+    std::uint32_t dst_u = 0;         // u variable defined (elementary ops)
+    std::vector<std::uint32_t> defs; // u variables this item defines
+    std::vector<std::uint32_t> deps; // u variables read at the current order, defined by OTHER items
+    std::uint32_t level = 0;
+    std::uint32_t first_op = 0;      // position of the first member op in the program (stable ordering)
+};
+
 } // namespace
 
-smem_plan make_smem_plan(const hy_program &p)
+smem_plan make_smem_plan(const hy_program &p, bool fuse)
 {
     smem_plan pl;
     const auto n_eq = p.n_eq, n_uvars = p.n_uvars, order = p.order;
@@ -100,17 +111,29 @@ smem_plan make_smem_plan(const hy_program &p)
 
     // ---- history analysis ----
     std::vector<char> hist(n_uvars, 0);
+    std::vector<std::vector<std::uint32_t>> users(n_uvars); // ops (indices) reading each u variable explicitly
     for (std::uint32_t i = 0; i < n_ops; ++i) {
         const auto &op = p.ops[i];
         const auto u = uses_of(p, op);
         for (const auto v : u.hist) {
             hist[v] = 1;
+            users[v].push_back(i);
+        }
+        for (const auto v : u.now) {
+            users[v].push_back(i);
         }
         if (u.self_hist) {
             hist[n_eq + i] = 1;
         }
         if (op.opcode == HY_OP_SIN || op.opcode == HY_OP_COS || op.opcode == HY_OP_TANH) {
             hist[op.c] = 1;
+            users[op.c].push_back(i); // keeps hidden dependencies out of any fusion
+        }
+    }
+    std::vector<char> is_sv_def(n_uvars, 0);
+    for (const auto ref : p.sv_defs) {
+        if (HY_REF_KIND(ref) == HY_REF_VAR) {
+            is_sv_def[HY_REF_IDX(ref)] = 1;
         }
     }
 
@@ -139,31 +162,8 @@ smem_plan make_smem_plan(const hy_program &p)
     pl.n_slots = next;
     pl.sv_rows.assign(row.begin(), row.begin() + n_eq);
 
-    // ---- segments (src/taylor_02.cpp:105-207): a new one starts when an op reads, at the current order,
-    // a u variable defined in the current segment. Hidden dependencies are not dependencies. ----
-    std::vector<std::uint32_t> seg_begin{0};
-    std::uint32_t cur_limit = n_eq;
-    for (std::uint32_t i = 0; i < n_ops; ++i) {
-        const auto u = uses_of(p, p.ops[i]);
-        bool dep = false;
-        for (const auto v : u.now) {
-            dep = dep || v >= cur_limit;
-        }
-        for (const auto v : u.hist) {
-            // convolution operands are read at order n too (e.g. b^[n] c^[0])
-            dep = dep || v >= cur_limit;
-        }
-        if (dep) {
-            seg_begin.push_back(i);
-            cur_limit = n_eq + i;
-        }
-    }
-    seg_begin.push_back(n_ops);
-    pl.n_segments = static_cast<std::uint32_t>(seg_begin.size() - 1u);
-
     // ---- n-ary argument table and state-variable definitions with row references ----
     pl.args = p.args;
-    // Which args entries belong to constant-function ops (no variables there) is irrelevant: only VAR refs change.
     for (auto &ref : pl.args) {
         if (HY_REF_KIND(ref) == HY_REF_VAR) {
             ref = HY_REF(HY_REF_VAR, row[HY_REF_IDX(ref)]);
@@ -176,16 +176,233 @@ smem_plan make_smem_plan(const hy_program &p)
         }
     }
 
-    // ---- ops: segment by segment, grouped by opcode inside a segment (warp-uniform control flow) ----
+    // ---- superinstructions: the gravitational pair interaction of model::nbody ----
+    // Pattern (src/model/nbody.cpp:97-153 after decomposition):
+    //   d_k = sub(x_k^j, x_k^i), k = 0..2;  r2 = sum_sq(d_0, d_1, d_2);  q = pow(r2, alpha);
+    //   f = c1 * q | -q | q;  m_k = d_k * f (either operand order);  optionally n_k = c2_k * m_k.
+    // All of it depends, at the current order, only on state variables, so one thread can run the whole chain
+    // for a pair. Every u variable keeps its own row and its own recurrence (bit-identical results).
+    std::vector<char> fused(n_ops, 0);
+    std::vector<item> items;
+    const auto op_of = [&](std::uint32_t u) -> const hy_op & { return p.ops[u - n_eq]; };
+    const auto only_users = [&](std::uint32_t u, std::vector<std::uint32_t> allowed) {
+        std::sort(allowed.begin(), allowed.end());
+        for (const auto x : users[u]) {
+            if (!std::binary_search(allowed.begin(), allowed.end(), x)) {
+                return false;
+            }
+        }
+        return true;
+    };
+    if (fuse) {
+        for (std::uint32_t qi = 0; qi < n_ops; ++qi) {
+            const auto &qop = p.ops[qi];
+            if (qop.opcode != HY_OP_POW_VN || qop.a < n_eq) {
+                continue;
+            }
+            const auto r2u = qop.a;
+            const auto &sop = op_of(r2u);
+            if (sop.opcode != HY_OP_SUM_SQ || sop.b != 3u || fused[r2u - n_eq]) {
+                continue;
+            }
+            std::uint32_t du[3];
+            bool ok = true;
+            for (std::uint32_t k = 0; k < 3u && ok; ++k) {
+                const auto ref = p.args[sop.a + k];
+                ok = HY_REF_KIND(ref) == HY_REF_VAR && HY_REF_IDX(ref) >= n_eq;
+                if (ok) {
+                    du[k] = HY_REF_IDX(ref);
+                    const auto &dop = op_of(du[k]);
+                    ok = dop.opcode == HY_OP_SUB_VV && dop.a < n_eq && dop.b < n_eq && !fused[du[k] - n_eq];
+                }
+            }
+            if (!ok || du[0] == du[1] || du[1] == du[2] || du[0] == du[2]) {
+                continue;
+            }
+            const auto qu = n_eq + qi;
+            // r2 is only read by the pow.
+            if (!only_users(r2u, {qi}) || is_sv_def[r2u]) {
+                continue;
+            }
+            // f: the single user of q that scales it, or q itself.
+            std::uint32_t fu = qu, fkind = 0 /* 0: q itself, 1: c1 * q, 2: -q */, c1 = 0;
+            if (users[qu].size() == 1u) {
+                const auto &fop = p.ops[users[qu][0]];
+                if (fop.opcode == HY_OP_MUL_NV && fop.b == qu) {
+                    fu = n_eq + users[qu][0];
+                    fkind = 1;
+                    c1 = fop.a;
+                } else if (fop.opcode == HY_OP_NEG && fop.a == qu) {
+                    fu = n_eq + users[qu][0];
+                    fkind = 2;
+                }
+            }
+            if (is_sv_def[qu] || is_sv_def[fu]) {
+                continue;
+            }
+            // m_k: the three products d_k * f. The users of f must be exactly these products, and every d_k
+            // must only be read by the sum_sq and by its product.
+            std::uint32_t mu[3] = {0, 0, 0};
+            std::vector<std::uint32_t> f_users;
+            for (std::uint32_t k = 0; k < 3u && ok; ++k) {
+                std::uint32_t found = 0, cnt = 0;
+                for (const auto x : users[du[k]]) {
+                    const auto &mop = p.ops[x];
+                    if (mop.opcode == HY_OP_MUL_VV
+                        && ((mop.a == du[k] && mop.b == fu) || (mop.b == du[k] && mop.a == fu))) {
+                        found = x;
+                        ++cnt;
+                    }
+                }
+                ok = cnt == 1u && only_users(du[k], {r2u - n_eq, found}) && !is_sv_def[du[k]] && !fused[found];
+                mu[k] = n_eq + found;
+                f_users.push_back(found);
+            }
+            if (!ok || !only_users(fu, f_users) || (fu != qu && !only_users(qu, {fu - n_eq}))) {
+                continue;
+            }
+            // All three products must have the same operand order (d * f or f * d): the pairing of the
+            // convolution indices depends on it.
+            {
+                const bool o0 = op_of(mu[0]).a == du[0], o1 = op_of(mu[1]).a == du[1], o2 = op_of(mu[2]).a == du[2];
+                if (o0 != o1 || o1 != o2) {
+                    continue;
+                }
+            }
+            // Optional second scaling n_k = c2_k * m_k: fused when every m_k has exactly one such reader
+            // (m_k keeps its own row: other readers, e.g. the sums, come at later levels).
+            std::uint32_t nu[3] = {0, 0, 0}, c2[3] = {0, 0, 0};
+            bool have_n = true;
+            for (std::uint32_t k = 0; k < 3u; ++k) {
+                std::uint32_t cnt = 0;
+                for (const auto x : users[mu[k]]) {
+                    const auto &nop = p.ops[x];
+                    if (nop.opcode == HY_OP_MUL_NV && nop.b == mu[k] && !fused[x]) {
+                        nu[k] = n_eq + x;
+                        c2[k] = nop.a;
+                        ++cnt;
+                    }
+                }
+                have_n = have_n && cnt == 1u;
+            }
+
+            // Build the fused item.
+            item it;
+            it.op.opcode = HY_FOP_NBODY_PAIR;
+            it.op.a = static_cast<std::uint32_t>(pl.aux.size());
+            it.op.b = fkind;
+            it.op.c = have_n ? 1u : 0u;
+            it.first_op = du[0] - n_eq;
+            for (std::uint32_t k = 0; k < 3u; ++k) {
+                const auto &dop = op_of(du[k]);
+                pl.aux.push_back(row[dop.a]);
+                pl.aux.push_back(row[dop.b]);
+                pl.aux.push_back(row[du[k]]);
+            }
+            pl.aux.push_back(row[r2u]);
+            pl.aux.push_back(row[qu]);
+            pl.aux.push_back(qop.b); // exponent (constant index)
+            pl.aux.push_back(qop.c); // order-0 evaluation algorithm
+            pl.aux.push_back(row[fu]);
+            pl.aux.push_back(c1);
+            for (std::uint32_t k = 0; k < 3u; ++k) {
+                const auto &mop = op_of(mu[k]);
+                pl.aux.push_back(row[mu[k]]);
+                pl.aux.push_back(mop.a == du[k] ? 0u : 1u); // operand order of the product (d * f or f * d)
+                pl.aux.push_back(have_n ? row[nu[k]] : 0u);
+                pl.aux.push_back(have_n ? c2[k] : 0u);
+            }
+            std::vector<std::uint32_t> members{du[0], du[1], du[2], r2u, qu, mu[0], mu[1], mu[2]};
+            if (fu != qu) {
+                members.push_back(fu);
+            }
+            if (have_n) {
+                members.insert(members.end(), {nu[0], nu[1], nu[2]});
+            }
+            for (const auto m : members) {
+                fused[m - n_eq] = 1;
+                it.defs.push_back(m);
+            }
+            items.push_back(std::move(it));
+            ++pl.n_fused;
+        }
+    }
+
+    // ---- the remaining elementary ops ----
+    for (std::uint32_t i = 0; i < n_ops; ++i) {
+        if (fused[i]) {
+            continue;
+        }
+        item it;
+        it.op = p.ops[i];
+        it.dst_u = n_eq + i;
+        it.defs = {n_eq + i};
+        it.first_op = i;
+        const auto u = uses_of(p, p.ops[i]);
+        for (const auto v : u.now) {
+            if (v >= n_eq) {
+                it.deps.push_back(v);
+            }
+        }
+        for (const auto v : u.hist) {
+            // convolution operands are read at order n too (e.g. b^[n] c^[0])
+            if (v >= n_eq) {
+                it.deps.push_back(v);
+            }
+        }
+        items.push_back(std::move(it));
+    }
+
+    // ---- level scheduling: an item runs one level after the last producer of what it reads at the current
+    // order. (The reference's taylor_segment_dc(), src/taylor_02.cpp:105-207, cuts the BFS-sorted list
+    // greedily; levels give the same or fewer synchronisation points. Hidden dependencies are not dependencies.)
+    std::vector<std::uint32_t> producer(n_uvars, ~0u);
+    for (std::uint32_t k = 0; k < items.size(); ++k) {
+        for (const auto d : items[k].defs) {
+            producer[d] = k;
+        }
+    }
+    std::sort(items.begin(), items.end(), [](const item &x, const item &y) { return x.first_op < y.first_op; });
+    for (std::uint32_t k = 0; k < items.size(); ++k) {
+        for (const auto d : items[k].defs) {
+            producer[d] = k;
+        }
+    }
+    // Items sorted by first_op: producers of elementary ops come earlier in program order, fused items only
+    // depend on state variables. One forward pass is enough, but iterate to a fixed point to be safe.
+    for (bool changed = true; changed;) {
+        changed = false;
+        for (auto &it : items) {
+            std::uint32_t lvl = 0;
+            for (const auto d : it.deps) {
+                lvl = std::max(lvl, items[producer[d]].level + 1u);
+            }
+            if (lvl != it.level) {
+                it.level = lvl;
+                changed = true;
+            }
+        }
+    }
+    std::uint32_t n_levels = 0;
+    for (const auto &it : items) {
+        n_levels = std::max(n_levels, it.level + 1u);
+    }
+    pl.n_segments = n_levels;
+
+    // ---- emit: level by level, grouped by opcode inside a level (warp-uniform control flow) ----
     pl.seg_offsets.push_back(0);
-    for (std::uint32_t s = 0; s < pl.n_segments; ++s) {
-        std::vector<std::uint32_t> idx(seg_begin[s + 1u] - seg_begin[s]);
-        std::iota(idx.begin(), idx.end(), seg_begin[s]);
-        std::stable_sort(idx.begin(), idx.end(),
-                         [&](std::uint32_t x, std::uint32_t y) { return p.ops[x].opcode < p.ops[y].opcode; });
-        pl.max_seg_width = std::max<std::uint32_t>(pl.max_seg_width, static_cast<std::uint32_t>(idx.size()));
-        for (const auto i : idx) {
-            auto op = p.ops[i];
+    for (std::uint32_t lvl = 0; lvl < n_levels; ++lvl) {
+        std::vector<const item *> cur;
+        for (const auto &it : items) {
+            if (it.level == lvl) {
+                cur.push_back(&it);
+            }
+        }
+        std::stable_sort(cur.begin(), cur.end(),
+                         [](const item *x, const item *y) { return x->op.opcode < y->op.opcode; });
+        pl.max_seg_width = std::max<std::uint32_t>(pl.max_seg_width, static_cast<std::uint32_t>(cur.size()));
+        for (const auto *it : cur) {
+            auto op = it->op;
             const auto var = [&](std::uint32_t &f) { f = row[f]; };
             switch (op.opcode) {
                 case HY_OP_SUB_VV:
@@ -222,11 +439,12 @@ smem_plan make_smem_plan(const hy_program &p)
                     var(op.c);
                     break;
                 default:
-                    // SUM / SUM_SQ / CFUNC go through the argument table, TIME has no operands.
+                    // SUM / SUM_SQ / CFUNC go through the argument table, TIME has no operands, fused
+                    // items carry row references in aux.
                     break;
             }
             pl.ops.push_back(op);
-            pl.dst.push_back(row[n_eq + i]);
+            pl.dst.push_back(op.opcode >= HY_FOP_FIRST ? 0u : row[it->dst_u]);
         }
         pl.seg_offsets.push_back(static_cast<std::uint32_t>(pl.ops.size()));
     }

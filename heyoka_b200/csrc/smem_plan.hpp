@@ -24,6 +24,13 @@ namespace heyoka_b200::detail
 // Packed row reference: (first slot << 2) | kind.
 constexpr std::uint32_t ROW_T = 0u, ROW_SV = 1u, ROW_H = 2u;
 
+// Superinstructions (internal to the plan, never part of a hy_program): opcodes >= HY_FOP_FIRST.
+//   HY_FOP_NBODY_PAIR  the gravitational pair interaction of model::nbody (src/model/nbody.cpp:97-153): 3 sub,
+//                      sum_sq, pow, optional scaling, 3 products, optional 3 scalings run by ONE work item.
+//                      op.a = offset into aux (27 words, see make_smem_plan()), op.b = kind of the scaling of
+//                      r^alpha (0 none, 1 constant, 2 negation), op.c = 1 if the products are rescaled.
+constexpr std::uint32_t HY_FOP_FIRST = 0x100u, HY_FOP_NBODY_PAIR = 0x100u;
+
 struct smem_plan {
     std::uint32_t n_slots = 0;  // doubles of shared memory per lane
     std::uint32_t n_segments = 0;
@@ -36,9 +43,11 @@ struct smem_plan {
     std::vector<std::uint32_t> args;        // n-ary argument table, variable entries -> row references
     std::vector<std::uint32_t> sv_defs;     // idem for the state variables' derivatives
     std::vector<std::uint32_t> sv_rows;     // row reference of each state variable
+    std::vector<std::uint32_t> aux;         // operand tables of the superinstructions
+    std::uint32_t n_fused = 0;              // number of superinstructions
 };
 
-smem_plan make_smem_plan(const hy_program &);
+smem_plan make_smem_plan(const hy_program &, bool fuse = true);
 
 } // namespace heyoka_b200::detail
 

@@ -251,7 +251,8 @@ typedef struct hy_kernel_info {
     uint32_t lanes_per_warp, lanes_per_thread, block_threads, blocks_per_sm, grid;
     uint64_t smem_bytes;          /* dynamic shared memory per CTA */
     uint32_t tape_slots_per_lane; /* doubles of tape per lane in the selected strategy */
-    uint32_t n_segments;          /* dependency segments of the decomposition (src/taylor_02.cpp:105-207) */
+    uint32_t n_segments;          /* dependency levels of the decomposition (cf. src/taylor_02.cpp:105-207) */
+    uint32_t n_fused;             /* superinstructions found by the planner (fused N-body pair interactions) */
     uint32_t n_sms;
 } hy_kernel_info;
 int hy_batch_get_kernel(const hy_batch *, hy_kernel_info *out);
