@@ -7,6 +7,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <limits>
 #include <new>
 #include <stdexcept>
@@ -40,7 +41,7 @@ using hy::detail::translate_exception;
 namespace
 {
 
-using coop_fn = void (*)(dev::program, dev::coop_tables, dev::batch, dev::run_args);
+using coop_fn = void (*)(dev::program, const std::uint32_t *, dev::batch, dev::run_args);
 
 struct coop_variant {
     int L, N;
@@ -66,6 +67,55 @@ const coop_variant *find_variant(int L, int N)
         }
     }
     return nullptr;
+}
+
+// The program tables of the cooperative kernels as one blob of 32-bit words (copied to shared memory by every
+// CTA): header (dev::coop_header), ops (8 words per item: opcode, a, b, c, destination row, 3 spare), level
+// offsets, n-ary argument table, superinstruction operand tables, constants (doubles), state-variable table
+// ({row, right-hand-side reference} per state variable).
+std::vector<std::uint32_t> make_plan_blob(const hy::detail::smem_plan &pl, const hy_program &p)
+{
+    std::vector<std::uint32_t> b(sizeof(dev::coop_header) / 4u, 0u);
+    const auto align = [&](std::size_t words) {
+        while (b.size() % words != 0u) {
+            b.push_back(0u);
+        }
+    };
+    dev::coop_header h{};
+    h.n_items = static_cast<std::uint32_t>(pl.ops.size());
+    h.n_segments = pl.n_segments;
+    h.n_eq = p.n_eq;
+    h.n_slots = pl.n_slots;
+    align(4);
+    h.off_ops = static_cast<std::uint32_t>(b.size());
+    for (std::size_t i = 0; i < pl.ops.size(); ++i) {
+        const auto &op = pl.ops[i];
+        b.insert(b.end(), {op.opcode, op.a, op.b, op.c, pl.dst[i], 0u, 0u, 0u});
+    }
+    h.off_seg = static_cast<std::uint32_t>(b.size());
+    b.insert(b.end(), pl.seg_offsets.begin(), pl.seg_offsets.end());
+    h.off_args = static_cast<std::uint32_t>(b.size());
+    b.insert(b.end(), pl.args.begin(), pl.args.end());
+    h.off_aux = static_cast<std::uint32_t>(b.size());
+    b.insert(b.end(), pl.aux.begin(), pl.aux.end());
+    align(2);
+    h.off_consts = static_cast<std::uint32_t>(b.size());
+    for (const double c : p.consts) {
+        std::uint32_t w[2];
+        std::memcpy(w, &c, sizeof(double));
+        b.push_back(w[0]);
+        b.push_back(w[1]);
+    }
+    align(2);
+    h.off_sv = static_cast<std::uint32_t>(b.size());
+    for (std::uint32_t i = 0; i < p.n_eq; ++i) {
+        b.push_back(pl.sv_rows[i]);
+        b.push_back(pl.sv_defs[i]);
+    }
+    align(4);
+    h.n_words = static_cast<std::uint32_t>(b.size());
+    std::memcpy(b.data(), &h, sizeof(h));
+    return b;
 }
 
 // Shared memory of one warp owning L lanes (must match dev::coop_smem<L>::warp_doubles()).
@@ -94,11 +144,8 @@ struct hy_batch {
     dev::program prog{};
     // ... and of the cooperative plan.
     hy::detail::smem_plan plan;
-    uint4 *d_c_ops = nullptr;
-    std::uint32_t *d_c_args = nullptr, *d_c_sv_defs = nullptr, *d_c_dst = nullptr, *d_c_seg = nullptr,
-                  *d_c_sv_rows = nullptr, *d_c_aux = nullptr;
-    dev::program c_prog{};
-    dev::coop_tables c_tabs{};
+    std::uint32_t *d_blob = nullptr;
+    std::size_t blob_bytes = 0; // rounded up to 16 bytes
 
     // Resident arrays.
     double *d_state = nullptr, *d_pars = nullptr, *d_t_hi = nullptr, *d_t_lo = nullptr, *d_last_h = nullptr,
@@ -160,9 +207,7 @@ void hy_batch::free_all() noexcept
 {
     for (void *p :
          {static_cast<void *>(d_ops), static_cast<void *>(d_args), static_cast<void *>(d_sv_defs),
-          static_cast<void *>(d_consts), static_cast<void *>(d_c_ops), static_cast<void *>(d_c_args),
-          static_cast<void *>(d_c_sv_defs), static_cast<void *>(d_c_dst), static_cast<void *>(d_c_seg),
-          static_cast<void *>(d_c_sv_rows), static_cast<void *>(d_c_aux), static_cast<void *>(d_state),
+          static_cast<void *>(d_consts), static_cast<void *>(d_blob), static_cast<void *>(d_state),
           static_cast<void *>(d_pars),
           static_cast<void *>(d_t_hi), static_cast<void *>(d_t_lo), static_cast<void *>(d_last_h),
           static_cast<void *>(d_tc), static_cast<void *>(d_d_out), static_cast<void *>(d_step_outcome),
@@ -251,7 +296,7 @@ bool hy_batch::setup_coop(int L, int N, std::uint32_t threads, std::uint32_t cta
                 continue;
             }
             const auto bytes = coop_warp_bytes(plan.n_slots, cand);
-            if (bytes + reserve > smem_per_block_max || smem_per_sm / (bytes + reserve / 4u) < 4u) {
+            if (blob_bytes + bytes + reserve > smem_per_block_max || (smem_per_sm - blob_bytes) / bytes < 4u) {
                 break;
             }
             L = cand;
@@ -261,7 +306,7 @@ bool hy_batch::setup_coop(int L, int N, std::uint32_t threads, std::uint32_t cta
         }
         if (L == 0) {
             // Not even 4 warps of the smallest shape fit: take whatever fits at all.
-            if (coop_warp_bytes(plan.n_slots, N) + reserve > smem_per_block_max) {
+            if (blob_bytes + coop_warp_bytes(plan.n_slots, N) + reserve > smem_per_block_max) {
                 return false;
             }
             L = N;
@@ -273,23 +318,19 @@ bool hy_batch::setup_coop(int L, int N, std::uint32_t threads, std::uint32_t cta
                                     + " lanes per warp, " + std::to_string(N) + " lanes per thread");
     }
     const auto warp_bytes = coop_warp_bytes(plan.n_slots, L);
-    if (warp_bytes + reserve > smem_per_block_max) {
+    if (blob_bytes > 24u * 1024u || blob_bytes + warp_bytes + reserve > smem_per_block_max) {
         return false;
     }
-    // Registers allow ~40 warps per SM (48 registers/thread); shared memory usually far fewer.
-    const std::size_t warps_fit = std::min<std::size_t>(smem_per_sm / warp_bytes, 40u);
     if (threads == 0u) {
-        // Keep the number of CTAs per SM moderate (<= 16): W warps per block.
-        std::size_t W = std::max<std::size_t>(1u, (warps_fit + 15u) / 16u);
-        while (W > 1u && W * warp_bytes + reserve > smem_per_block_max) {
-            --W;
-        }
-        threads = static_cast<std::uint32_t>(32u * std::min<std::size_t>(W, 8u));
+        // One CTA per SM holding as many warps as fit next to one copy of the tables (at most 16 warps;
+        // registers: 65536 / 512 threads = 128 per thread).
+        const std::size_t W = std::min<std::size_t>((smem_per_block_max - reserve - blob_bytes) / warp_bytes, 16u);
+        threads = static_cast<std::uint32_t>(32u * std::max<std::size_t>(W, 1u));
     }
-    if (threads % 32u != 0u || threads == 0u || threads > 256u) {
+    if (threads % 32u != 0u || threads == 0u || threads > 512u) {
         throw std::invalid_argument("Invalid number of threads for the cooperative kernel");
     }
-    const std::size_t bytes = static_cast<std::size_t>(threads / 32u) * warp_bytes;
+    const std::size_t bytes = blob_bytes + static_cast<std::size_t>(threads / 32u) * warp_bytes;
     if (bytes + reserve > smem_per_block_max) {
         return false;
     }
@@ -332,7 +373,7 @@ void hy_batch::launch(bool prop, const dev::run_args &R)
 {
     HY_CUDA_CHECK(cudaMemsetAsync(d_counter, 0, sizeof(unsigned int), stream));
     if (mode == 2) {
-        (prop ? cv->prop : cv->step)<<<c_grid, c_threads, c_smem, stream>>>(c_prog, c_tabs, view(), R);
+        (prop ? cv->prop : cv->step)<<<c_grid, c_threads, c_smem, stream>>>(prog, d_blob, view(), R);
     } else if (prop) {
         dev::k_hbm<true><<<h_grid, h_threads, 0, stream>>>(prog, view(), R, d_scratch, slab_doubles);
     } else {
@@ -517,23 +558,11 @@ int hy_batch_create(const hy_program *p, uint32_t batch, int device, hy_batch **
             fuse = std::string{env} != "0";
         }
         b->plan = hy::detail::make_smem_plan(*p, fuse);
-        b->d_c_ops = reinterpret_cast<uint4 *>(b->dupload(b->plan.ops));
-        b->d_c_args = b->dupload(b->plan.args);
-        b->d_c_sv_defs = b->dupload(b->plan.sv_defs);
-        b->d_c_dst = b->dupload(b->plan.dst);
-        b->d_c_seg = b->dupload(b->plan.seg_offsets);
-        b->d_c_sv_rows = b->dupload(b->plan.sv_rows);
-        b->d_c_aux = b->dupload(b->plan.aux);
-        b->c_prog = P;
-        b->c_prog.ops = b->d_c_ops;
-        b->c_prog.args = b->d_c_args;
-        b->c_prog.sv_defs = b->d_c_sv_defs;
-        b->c_tabs.dst = b->d_c_dst;
-        b->c_tabs.seg_offsets = b->d_c_seg;
-        b->c_tabs.sv_rows = b->d_c_sv_rows;
-        b->c_tabs.aux = b->d_c_aux;
-        b->c_tabs.n_segments = b->plan.n_segments;
-        b->c_tabs.n_slots = b->plan.n_slots;
+        {
+            const auto blob = make_plan_blob(b->plan, *p);
+            b->d_blob = b->dupload(blob);
+            b->blob_bytes = (blob.size() + 3u) / 4u * 16u;
+        }
 
         // Resident arrays.
         const std::size_t n = batch;

@@ -32,13 +32,13 @@ __device__ __forceinline__ void fused_nbody_pair(const program &P, const Tape &t
     Row D[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-        const V v = t.row(__ldg(aux + 3 * k)).at(n) - t.row(__ldg(aux + 3 * k + 1)).at(n);
-        D[k] = t.row(__ldg(aux + 3 * k + 2));
+        const V v = t.row(aux[3 * k]).at(n) - t.row(aux[3 * k + 1]).at(n);
+        D[k] = t.row(aux[3 * k + 2]);
         D[k].set(n, v);
     }
 
     // ---- r2^[n]: SUM_SQ over the three differences ----
-    const Row R2 = t.row(__ldg(aux + 9));
+    const Row R2 = t.row(aux[9]);
     {
         V v[3];
         const bool odd = (n & 1u) != 0u;
@@ -62,12 +62,12 @@ __device__ __forceinline__ void fused_nbody_pair(const program &P, const Tape &t
     }
 
     // ---- q^[n] = pow(r2, alpha) ----
-    const Row Q = t.row(__ldg(aux + 10));
+    const Row Q = t.row(aux[10]);
     V q;
     {
-        const V alpha = splat<N>(__ldg(P.consts + __ldg(aux + 11)));
+        const V alpha = splat<N>(t.cst(aux[11]));
         if (n == 0u) {
-            q = pow_eval(__ldg(aux + 12), R2.at(0u), alpha);
+            q = pow_eval(aux[12], R2.at(0u), alpha);
         } else {
             const double nd = static_cast<double>(n);
             const V ap1 = alpha + 1.;
@@ -89,12 +89,12 @@ __device__ __forceinline__ void fused_nbody_pair(const program &P, const Tape &t
     // ---- f^[n] ----
     Row F = Q;
     if (fkind != 0u) {
-        F = t.row(__ldg(aux + 13));
-        F.set(n, fkind == 1u ? __ldg(P.consts + __ldg(aux + 14)) * q : -q);
+        F = t.row(aux[13]);
+        F.set(n, fkind == 1u ? t.cst(aux[14]) * q : -q);
     }
 
     // ---- m_k^[n] = sum_j A^[n-j] B^[j] with (A, B) = (d_k, f) or (f, d_k); the f loads are shared ----
-    const bool f_first = __ldg(aux + 16) != 0u;
+    const bool f_first = aux[16] != 0u;
     V acc[3] = {splat<N>(0.), splat<N>(0.), splat<N>(0.)};
     if (!f_first) {
         const double *pf = F.hptr(0u);
@@ -127,9 +127,9 @@ __device__ __forceinline__ void fused_nbody_pair(const program &P, const Tape &t
     }
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-        t.row(__ldg(aux + 15 + 4 * k)).set(n, acc[k]);
+        t.row(aux[15 + 4 * k]).set(n, acc[k]);
         if (have_n) {
-            t.row(__ldg(aux + 17 + 4 * k)).set(n, __ldg(P.consts + __ldg(aux + 18 + 4 * k)) * acc[k]);
+            t.row(aux[17 + 4 * k]).set(n, t.cst(aux[18 + 4 * k]) * acc[k]);
         }
     }
 }

@@ -45,16 +45,6 @@ struct run_args {
     unsigned int *counter;
 };
 
-// Extra tables of the cooperative kernels (device pointers).
-struct coop_tables {
-    const std::uint32_t *dst;         // row reference of each op's result
-    const std::uint32_t *seg_offsets; // n_segments + 1
-    const std::uint32_t *sv_rows;     // row reference of each state variable
-    const std::uint32_t *aux;         // operand tables of the superinstructions
-    std::uint32_t n_segments;
-    std::uint32_t n_slots;
-};
-
 // ================================================================================================
 // Per-lane bookkeeping shared by both strategies.
 // ================================================================================================
@@ -161,6 +151,17 @@ struct hbm_tape {
     const double *pars;
     std::uint32_t batch, lane;
     double tm;
+    const std::uint32_t *args;
+    const double *consts;
+
+    __device__ __forceinline__ std::uint32_t arg(std::uint32_t i) const
+    {
+        return __ldg(args + i);
+    }
+    __device__ __forceinline__ double cst(std::uint32_t i) const
+    {
+        return __ldg(consts + i);
+    }
 
     struct row_t {
         double *p;
@@ -205,8 +206,9 @@ __device__ __forceinline__ void hbm_jet(const program &P, const hbm_tape &t, con
     }
     for (std::uint32_t n = 0; n < P.order; ++n) {
         if (n > 0u) {
+            const double nd = static_cast<double>(n), rcp = 1. / nd;
             for (std::uint32_t i = 0; i < P.n_eq; ++i) {
-                t.row(i).set(n, sv_diff<1>(P, t, __ldg(P.sv_defs + i), n));
+                t.row(i).set(n, sv_diff<1>(P, t, __ldg(P.sv_defs + i), n, nd, rcp));
             }
         }
         for (std::uint32_t k = 0; k < P.n_ops; ++k) {
@@ -215,8 +217,11 @@ __device__ __forceinline__ void hbm_jet(const program &P, const hbm_tape &t, con
             self.set(n, diff_op<1>(P, t, op, self, n));
         }
     }
-    for (std::uint32_t i = 0; i < P.n_eq; ++i) {
-        t.row(i).set(P.order, sv_diff<1>(P, t, __ldg(P.sv_defs + i), P.order));
+    {
+        const double nd = static_cast<double>(P.order), rcp = 1. / nd;
+        for (std::uint32_t i = 0; i < P.n_eq; ++i) {
+            t.row(i).set(P.order, sv_diff<1>(P, t, __ldg(P.sv_defs + i), P.order, nd, rcp));
+        }
     }
 }
 
@@ -278,7 +283,7 @@ __global__ void __launch_bounds__(256) k_hbm(program P, batch D, run_args R, dou
         const std::uint32_t lane_raw = chunk * 32u + lane_in_warp;
         const bool valid = lane_raw < D.n;
         const std::uint32_t lane = valid ? lane_raw : D.n - 1u;
-        hbm_tape tape{slab, P.order + 1u, D.pars, D.n, lane, 0.};
+        hbm_tape tape{slab, P.order + 1u, D.pars, D.n, lane, 0., P.args, P.consts};
 
         if constexpr (!PROP) {
             const double mdt = R.max_delta_t != nullptr ? R.max_delta_t[lane] : R.default_max_delta_t;
@@ -321,16 +326,36 @@ __global__ void __launch_bounds__(256) k_hbm(program P, batch D, run_args R, dou
 // ================================================================================================
 // "coop" strategy: warp-cooperative, tape in shared memory.
 // A warp owns L lanes and a private slice of shared memory; its 32 threads are (32 / G) workers x G lane
-// groups of N lanes (G = L / N). Segments and orders are separated by __syncwarp() only: warps never
-// wait for each other, the SM interleaves them.
+// groups of N lanes (G = L / N). Levels and orders are separated by __syncwarp() only: warps never wait
+// for each other, the SM interleaves them. The program tables (ops, argument tables, constants) are copied
+// once per CTA into shared memory, so that no global-memory latency sits on the per-item critical path.
 // ================================================================================================
+
+// Word offsets into the plan blob (see make_plan_blob() in batch.cu); the blob starts with this header.
+struct coop_header {
+    std::uint32_t n_words, n_items, n_segments, n_eq;
+    std::uint32_t off_ops, off_seg, off_args, off_aux;
+    std::uint32_t off_consts, off_sv, n_slots, pad;
+};
+
 template <int L, int N>
 struct smem_tape {
     double *base; // the warp's tape + first lane of this thread's group
+    const std::uint32_t *args;
+    const double *consts;
     const double *pars;
     std::uint32_t batch;
     std::uint32_t glane[N]; // global lane indices (clamped to valid lanes)
     vd<N> tm;
+
+    __device__ __forceinline__ std::uint32_t arg(std::uint32_t i) const
+    {
+        return args[i];
+    }
+    __device__ __forceinline__ double cst(std::uint32_t i) const
+    {
+        return consts[i];
+    }
 
     struct row_t {
         double *p;
@@ -358,18 +383,8 @@ struct smem_tape {
             }
             return r;
         }
-        // Address of the order-o coefficient of a HISTORY row (convolution operands always are).
-        __device__ __forceinline__ const double *hptr(std::uint32_t o) const
+        __device__ __forceinline__ static void store(double *q, const vd<N> &v)
         {
-            return p + o * L;
-        }
-        __device__ __forceinline__ vd<N> at(std::uint32_t o) const
-        {
-            return load(p + (o & mask) * L);
-        }
-        __device__ __forceinline__ void set(std::uint32_t o, const vd<N> &v) const
-        {
-            double *q = p + (o & mask) * L;
             if constexpr (N == 2) {
                 *reinterpret_cast<double2 *>(q) = make_double2(v.v[0], v.v[1]);
             } else if constexpr (N == 4) {
@@ -381,6 +396,19 @@ struct smem_tape {
                     q[i] = v.v[i];
                 }
             }
+        }
+        // Address of the order-o coefficient of a HISTORY row (convolution operands always are).
+        __device__ __forceinline__ const double *hptr(std::uint32_t o) const
+        {
+            return p + o * L;
+        }
+        __device__ __forceinline__ vd<N> at(std::uint32_t o) const
+        {
+            return load(p + (o & mask) * L);
+        }
+        __device__ __forceinline__ void set(std::uint32_t o, const vd<N> &v) const
+        {
+            store(p + (o & mask) * L, v);
         }
     };
     // ref = (first slot << 2) | kind; kind 0: one slot (mask 0), 1: two slots on the order's parity
@@ -412,9 +440,9 @@ struct coop_smem {
     double *time, *h;
     int *running;
 
-    __device__ __forceinline__ coop_smem(double *smem, std::uint32_t n_slots, std::uint32_t warp_in_block)
+    __device__ __forceinline__ coop_smem(double *warp_region, std::uint32_t n_slots)
     {
-        tape = smem + static_cast<std::size_t>(warp_in_block) * warp_doubles(n_slots);
+        tape = warp_region;
         time = tape + static_cast<std::size_t>(n_slots) * L;
         h = time + L;
         running = reinterpret_cast<int *>(h + L);
@@ -428,24 +456,32 @@ struct coop_smem {
 
 // Jet of the L lanes starting at global lane `lane0`; the state variables' coefficients go to tc.
 template <int L, int N>
-__device__ __forceinline__ void coop_jet(const program &P, const coop_tables &X, const batch &D,
-                                         const coop_smem<L> &S, std::uint32_t lane0)
+__device__ __forceinline__ void coop_jet(const program &P, const coop_header &H, const std::uint32_t *tab,
+                                         const batch &D, const coop_smem<L> &S, std::uint32_t lane0)
 {
     constexpr std::uint32_t G = L / N; // lane groups per warp
     const std::uint32_t tid = threadIdx.x & 31u;
     constexpr std::uint32_t nthr = 32u;
     const std::uint32_t pp1 = P.order + 1u;
+    const uint4 *ops = reinterpret_cast<const uint4 *>(tab + H.off_ops);
+    const std::uint32_t *seg = tab + H.off_seg;
+    const std::uint32_t *aux = tab + H.off_aux;
+    const uint2 *svt = reinterpret_cast<const uint2 *>(tab + H.off_sv); // {row of the state variable, rhs reference}
 
     // This thread always works on the same lane group: g = tid % G.
     smem_tape<L, N> t;
     const std::uint32_t g = tid % G;
     t.base = S.tape + g * N;
+    t.args = tab + H.off_args;
+    t.consts = reinterpret_cast<const double *>(tab + H.off_consts);
     t.pars = D.pars;
     t.batch = D.n;
+    bool lane_ok[N];
 #pragma unroll
     for (int i = 0; i < N; ++i) {
         const std::uint32_t l = lane0 + g * N + i;
-        t.glane[i] = l < D.n ? l : D.n - 1u;
+        lane_ok[i] = l < D.n;
+        t.glane[i] = lane_ok[i] ? l : D.n - 1u;
         t.tm.v[i] = S.time[g * N + i];
     }
     // Stream the coefficient of state variable sv at order n to tc (valid lanes only).
@@ -453,9 +489,8 @@ __device__ __forceinline__ void coop_jet(const program &P, const coop_tables &X,
         double *dst = D.tc + (static_cast<std::size_t>(sv) * pp1 + n) * D.n;
 #pragma unroll
         for (int i = 0; i < N; ++i) {
-            const std::uint32_t l = lane0 + g * N + i;
-            if (l < D.n) {
-                dst[l] = v.v[i];
+            if (lane_ok[i]) {
+                dst[t.glane[i]] = v.v[i];
             }
         }
     };
@@ -468,7 +503,7 @@ __device__ __forceinline__ void coop_jet(const program &P, const coop_tables &X,
         for (int i = 0; i < N; ++i) {
             v.v[i] = D.state[static_cast<std::size_t>(sv) * D.n + t.glane[i]];
         }
-        t.row(__ldg(X.sv_rows + sv)).set(0u, v);
+        t.row(svt[sv].x).set(0u, v);
         write_tc(sv, 0u, v);
     }
     __syncwarp();
@@ -476,10 +511,12 @@ __device__ __forceinline__ void coop_jet(const program &P, const coop_tables &X,
     for (std::uint32_t n = 0; n <= P.order; ++n) {
         if (n > 0u) {
             // State variables: x^[n] = (rhs)^[n-1] / n.
+            const double nd = static_cast<double>(n), rcp = 1. / nd;
             for (std::uint32_t it = tid; it < P.n_eq * G; it += nthr) {
                 const std::uint32_t sv = it / G;
-                const vd<N> v = sv_diff<N>(P, t, __ldg(P.sv_defs + sv), n);
-                t.row(__ldg(X.sv_rows + sv)).set(n, v);
+                const uint2 e = svt[sv];
+                const vd<N> v = sv_diff<N>(P, t, e.y, n, nd, rcp);
+                t.row(e.x).set(n, v);
                 write_tc(sv, n, v);
             }
             __syncwarp();
@@ -487,16 +524,16 @@ __device__ __forceinline__ void coop_jet(const program &P, const coop_tables &X,
         if (n == P.order) {
             break;
         }
-        // The other u variables, one dependency segment at a time.
-        for (std::uint32_t s = 0; s < X.n_segments; ++s) {
-            const std::uint32_t b = __ldg(X.seg_offsets + s), e = __ldg(X.seg_offsets + s + 1u);
+        // The other u variables, one dependency level at a time.
+        for (std::uint32_t s = 0; s < H.n_segments; ++s) {
+            const std::uint32_t b = seg[s], e = seg[s + 1u];
             for (std::uint32_t it = tid; it < (e - b) * G; it += nthr) {
                 const std::uint32_t k = b + it / G;
-                const uint4 op = __ldg(P.ops + k);
+                const uint4 op = ops[2u * k];
                 if (op.x >= FOP_FIRST) {
-                    fused_nbody_pair<N>(P, t, X.aux + op.y, op.z, op.w != 0u, n);
+                    fused_nbody_pair<N>(P, t, aux + op.y, op.z, op.w != 0u, n);
                 } else {
-                    const auto self = t.row(__ldg(X.dst + k));
+                    const auto self = t.row(ops[2u * k + 1u].x);
                     self.set(n, diff_op<N>(P, t, op, self, n));
                 }
             }
@@ -523,10 +560,10 @@ __device__ __forceinline__ double coop_determine_h(const program &P, const batch
 }
 
 // State update of the warp's lanes: item = (state variable, lane); S.h holds the step sizes, S.running
-// which lanes may be written.
+// which lanes may be written. Returns true if this thread produced a non-finite value for lane `l_out`.
 template <int L>
 __device__ __forceinline__ void coop_update_state(const program &P, const batch &D, const coop_smem<L> &S,
-                                                  std::uint32_t lane0)
+                                                  std::uint32_t lane0, unsigned &nf_mask)
 {
     const std::uint32_t pp1 = P.order + 1u;
     for (std::uint32_t it = threadIdx.x & 31u; it < P.n_eq * L; it += 32u) {
@@ -538,16 +575,32 @@ __device__ __forceinline__ void coop_update_state(const program &P, const batch 
             const double res = eval_poly(P, [c, n](std::uint32_t o) { return c[static_cast<std::size_t>(o) * n]; },
                                          S.h[l]);
             D.state[static_cast<std::size_t>(sv) * D.n + glane] = res;
+            if (!isfinite(res)) {
+                nf_mask |= 1u << l;
+            }
         }
     }
 }
 
 template <int L, int N, bool PROP>
-__global__ void __launch_bounds__(256) k_coop(program P, coop_tables X, batch D, run_args R)
+__global__ void __launch_bounds__(512) k_coop(program P, const std::uint32_t *blob, batch D, run_args R)
 {
     extern __shared__ __align__(16) double smem_raw[];
+    // Program tables: global -> shared, once per CTA.
+    std::uint32_t *tab = reinterpret_cast<std::uint32_t *>(smem_raw);
+    const std::uint32_t n_words = __ldg(blob);
+    for (std::uint32_t i = threadIdx.x; i < n_words; i += blockDim.x) {
+        tab[i] = __ldg(blob + i);
+    }
+    __syncthreads();
+    const coop_header H = *reinterpret_cast<const coop_header *>(tab);
+
     const std::uint32_t tid = threadIdx.x & 31u;
-    const coop_smem<L> S(smem_raw, X.n_slots, threadIdx.x >> 5);
+    // Tables rounded up to 16 bytes, then one region per warp.
+    const std::size_t tab_doubles = static_cast<std::size_t>(n_words + 3u) / 4u * 2u;
+    const coop_smem<L> S(smem_raw + tab_doubles
+                             + static_cast<std::size_t>(threadIdx.x >> 5) * coop_smem<L>::warp_doubles(H.n_slots),
+                         H.n_slots);
     const std::uint32_t n_chunks = (D.n + L - 1u) / L;
     const bool owner = tid < L;
 
@@ -568,21 +621,22 @@ __global__ void __launch_bounds__(256) k_coop(program P, coop_tables X, batch D,
                 S.running[tid] = 1;
             }
             __syncwarp();
-            coop_jet<L, N>(P, X, D, S, lane0);
+            coop_jet<L, N>(P, H, tab, D, S, lane0);
             double h = 0.;
             if (owner) {
                 h = coop_determine_h(P, D, lane, mdt);
                 S.h[tid] = h;
             }
             __syncwarp();
-            coop_update_state<L>(P, D, S, lane0);
-            __syncwarp();
+            unsigned nf_mask = 0u;
+            coop_update_state<L>(P, D, S, lane0, nf_mask);
+            nf_mask = __reduce_or_sync(0xffffffffu, nf_mask);
             if (valid) {
                 const dfl nt = dfl_add(t0, dfl{h, 0.});
                 D.t_hi[lane] = nt.hi;
                 D.t_lo[lane] = nt.lo;
                 D.last_h[lane] = h;
-                const bool nf = !(isfinite(nt.hi) && isfinite(nt.lo)) || lane_state_nonfinite(P, D, lane);
+                const bool nf = !(isfinite(nt.hi) && isfinite(nt.lo)) || ((nf_mask >> tid) & 1u) != 0u;
                 D.step_outcome[lane]
                     = nf ? HY_OUTCOME_ERR_NF_STATE : (h == mdt ? HY_OUTCOME_TIME_LIMIT : HY_OUTCOME_SUCCESS);
             }
@@ -600,17 +654,18 @@ __global__ void __launch_bounds__(256) k_coop(program P, coop_tables X, batch D,
                     S.running[tid] = lp.running ? 1 : 0;
                 }
                 __syncwarp();
-                coop_jet<L, N>(P, X, D, S, lane0);
+                coop_jet<L, N>(P, H, tab, D, S, lane0);
                 double h = 0.;
                 if (owner) {
                     h = coop_determine_h(P, D, lane, cur_max);
                     S.h[tid] = h;
                 }
                 __syncwarp();
-                coop_update_state<L>(P, D, S, lane0);
-                __syncwarp();
+                unsigned nf_mask = 0u;
+                coop_update_state<L>(P, D, S, lane0, nf_mask);
+                nf_mask = __reduce_or_sync(0xffffffffu, nf_mask);
                 if (owner && lp.running) {
-                    lp.advance(h, cur_max, lane_state_nonfinite(P, D, lane), R, valid);
+                    lp.advance(h, cur_max, ((nf_mask >> tid) & 1u) != 0u, R, valid);
                 }
             }
             if (valid) {

