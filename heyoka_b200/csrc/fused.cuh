@@ -19,7 +19,8 @@ constexpr std::uint32_t FOP_FIRST = 0x100u;
 //   q = pow(r2, alpha) (src/math/pow.cpp)               f = c1 q | -q | q (src/math/prod.cpp)
 //   m_k = d_k f (src/math/prod.cpp, var * var)          n_k = c2_k m_k (optional)
 // aux: [a_k, b_k, d_k] x 3, r2, q, alpha (constant index), order-0 pow algorithm, f, c1 (constant index),
-//      [m_k, operand order, n_k, c2_k (constant index)] x 3   (all rows as packed row references).
+//      [m_k, operand order, n_k, c2_k (constant index)] x 3   (rows as packed row references; d_k, r2, q, f are
+//      history rows and m_k, n_k single-slot rows by construction, so their masks are never decoded).
 template <int N, typename Tape>
 __device__ __forceinline__ void fused_nbody_pair(const program &P, const Tape &t, const std::uint32_t *aux,
                                                  std::uint32_t fkind, bool have_n, std::uint32_t n)
@@ -28,33 +29,51 @@ __device__ __forceinline__ void fused_nbody_pair(const program &P, const Tape &t
     using Row = typename Tape::row_t;
     constexpr int S = static_cast<int>(Row::stride);
 
-    // ---- d_k^[n] = b_k^[n] ... as SUB_VV: row(a).at(n) - row(b).at(n) ----
-    Row D[3];
+    // ---- d_k^[n] as SUB_VV: row(a).at(n) - row(b).at(n) ----
+    const double *d0[3]; // order-0 address of the three difference rows
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         const V v = t.row(aux[3 * k]).at(n) - t.row(aux[3 * k + 1]).at(n);
-        D[k] = t.row(aux[3 * k + 2]);
-        D[k].set(n, v);
+        const Row D = t.hrow(aux[3 * k + 2]);
+        d0[k] = D.hptr(0u);
+        Row::store(const_cast<double *>(d0[k]) + n * S, v);
     }
 
-    // ---- r2^[n]: SUM_SQ over the three differences ----
-    const Row R2 = t.row(aux[9]);
+    // ---- r2^[n]: SUM_SQ over the three differences; the three convolutions run interleaved (each keeps
+    // its own accumulator and its own summation order) ----
+    const Row R2 = t.hrow(aux[9]);
     {
-        V v[3];
         const bool odd = (n & 1u) != 0u;
+        V acc[3] = {splat<N>(0.), splat<N>(0.), splat<N>(0.)};
+        if (n > 0u) {
+            const std::uint32_t j1 = odd ? (n - 1u) / 2u : (n - 2u) / 2u;
+            const double *pa0 = d0[0] + n * S, *pa1 = d0[1] + n * S, *pa2 = d0[2] + n * S;
+            const double *pb0 = d0[0], *pb1 = d0[1], *pb2 = d0[2];
+#pragma unroll 2
+            for (std::uint32_t j = 0; j <= j1; ++j) {
+                acc[0] = vfma(Row::load(pa0), Row::load(pb0), acc[0]);
+                acc[1] = vfma(Row::load(pa1), Row::load(pb1), acc[1]);
+                acc[2] = vfma(Row::load(pa2), Row::load(pb2), acc[2]);
+                pa0 -= S;
+                pa1 -= S;
+                pa2 -= S;
+                pb0 += S;
+                pb1 += S;
+                pb2 += S;
+            }
+        }
+        V v[3];
+        if (odd) {
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            if (odd) {
-                v[k] = conv_plain<N>(D[k], D[k], n, 0u, (n - 1u) / 2u);
-            } else {
-                const V ak2 = D[k].at(n / 2u);
+            for (int k = 0; k < 3; ++k) {
+                v[k] = acc[k];
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const V ak2 = Row::load(d0[k] + (n / 2u) * S);
                 const V sq = ak2 * ak2;
-                if (n > 0u) {
-                    const V acc = conv_plain<N>(D[k], D[k], n, 0u, (n - 2u) / 2u);
-                    v[k] = (acc + acc) + sq;
-                } else {
-                    v[k] = sq;
-                }
+                v[k] = n > 0u ? (acc[k] + acc[k]) + sq : sq;
             }
         }
         const V r = (v[0] + v[1]) + v[2]; // pairwise_sum of three terms
@@ -62,7 +81,7 @@ __device__ __forceinline__ void fused_nbody_pair(const program &P, const Tape &t
     }
 
     // ---- q^[n] = pow(r2, alpha) ----
-    const Row Q = t.row(aux[10]);
+    const Row Q = t.hrow(aux[10]);
     V q;
     {
         const V alpha = splat<N>(t.cst(aux[11]));
@@ -89,7 +108,7 @@ __device__ __forceinline__ void fused_nbody_pair(const program &P, const Tape &t
     // ---- f^[n] ----
     Row F = Q;
     if (fkind != 0u) {
-        F = t.row(aux[13]);
+        F = t.hrow(aux[13]);
         F.set(n, fkind == 1u ? t.cst(aux[14]) * q : -q);
     }
 
@@ -98,7 +117,7 @@ __device__ __forceinline__ void fused_nbody_pair(const program &P, const Tape &t
     V acc[3] = {splat<N>(0.), splat<N>(0.), splat<N>(0.)};
     if (!f_first) {
         const double *pf = F.hptr(0u);
-        const double *pd0 = D[0].hptr(n), *pd1 = D[1].hptr(n), *pd2 = D[2].hptr(n);
+        const double *pd0 = d0[0] + n * S, *pd1 = d0[1] + n * S, *pd2 = d0[2] + n * S;
 #pragma unroll 4
         for (std::uint32_t j = 0; j <= n; ++j) {
             const V fj = Row::load(pf);
@@ -112,7 +131,7 @@ __device__ __forceinline__ void fused_nbody_pair(const program &P, const Tape &t
         }
     } else {
         const double *pf = F.hptr(n);
-        const double *pd0 = D[0].hptr(0u), *pd1 = D[1].hptr(0u), *pd2 = D[2].hptr(0u);
+        const double *pd0 = d0[0], *pd1 = d0[1], *pd2 = d0[2];
 #pragma unroll 4
         for (std::uint32_t j = 0; j <= n; ++j) {
             const V fj = Row::load(pf);
@@ -127,9 +146,9 @@ __device__ __forceinline__ void fused_nbody_pair(const program &P, const Tape &t
     }
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-        t.row(aux[15 + 4 * k]).set(n, acc[k]);
+        Row::store(const_cast<double *>(t.hrow(aux[15 + 4 * k]).hptr(0u)), acc[k]);
         if (have_n) {
-            t.row(aux[17 + 4 * k]).set(n, t.cst(aux[18 + 4 * k]) * acc[k]);
+            Row::store(const_cast<double *>(t.hrow(aux[17 + 4 * k]).hptr(0u)), t.cst(aux[18 + 4 * k]) * acc[k]);
         }
     }
 }

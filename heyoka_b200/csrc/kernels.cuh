@@ -411,12 +411,16 @@ struct smem_tape {
             store(p + (o & mask) * L, v);
         }
     };
-    // ref = (first slot << 2) | kind; kind 0: one slot (mask 0), 1: two slots on the order's parity
-    // (mask 1), 2: one slot per order (mask ~0).
+    // ref = (mask code << 27) | first slot (see smem_plan.hpp): mask = sign extension of the 3-bit code.
     __device__ __forceinline__ row_t row(std::uint32_t ref) const
     {
-        const std::uint32_t kind = ref & 3u;
-        return row_t{base + (ref >> 2) * L, kind == 2u ? 0xffffffffu : kind};
+        const std::uint32_t mask = static_cast<std::uint32_t>(static_cast<std::int32_t>(ref << 2) >> 29);
+        return row_t{base + (ref & 0x7ffffffu) * L, mask};
+    }
+    // A row known to be a history row / a single-slot row (superinstructions): no mask decoding.
+    __device__ __forceinline__ row_t hrow(std::uint32_t ref) const
+    {
+        return row_t{base + (ref & 0x7ffffffu) * L, 0xffffffffu};
     }
     __device__ __forceinline__ vd<N> par(std::uint32_t idx) const
     {

@@ -143,7 +143,7 @@ smem_plan make_smem_plan(const hy_program &p, bool fuse)
     std::vector<std::uint32_t> row(n_uvars, 0);
     std::uint32_t next = 0;
     const auto alloc = [&](std::uint32_t kind, std::uint32_t n) {
-        const auto r = (next << 2) | kind;
+        const auto r = (kind << ROW_SLOT_BITS) | next;
         next += n;
         return r;
     };
@@ -156,7 +156,7 @@ smem_plan make_smem_plan(const hy_program &p, bool fuse)
             row[i] = alloc(ROW_T, 1u);
         }
     }
-    if (next >= (1u << 29)) {
+    if (next >= (1u << ROW_SLOT_BITS)) {
         throw std::overflow_error("The Taylor tape is too large");
     }
     pl.n_slots = next;
@@ -284,6 +284,14 @@ smem_plan make_smem_plan(const hy_program &p, bool fuse)
                     }
                 }
                 have_n = have_n && cnt == 1u;
+            }
+
+            // The device code writes m_k / n_k as single-slot rows: they must not be history rows.
+            for (std::uint32_t k = 0; k < 3u; ++k) {
+                ok = ok && !hist[mu[k]] && (!have_n || !hist[nu[k]]);
+            }
+            if (!ok) {
+                continue;
             }
 
             // Build the fused item.

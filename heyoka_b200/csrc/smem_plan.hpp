@@ -21,8 +21,11 @@
 namespace heyoka_b200::detail
 {
 
-// Packed row reference: (first slot << 2) | kind.
-constexpr std::uint32_t ROW_T = 0u, ROW_SV = 1u, ROW_H = 2u;
+// Packed row reference (30 bits): (mask code << 27) | first slot. The order-o coefficient of a row lives in
+// slot `first + (o & mask)`, mask = sign-extended mask code: 0 (T, one slot), 1 (SV, two slots on the parity of
+// the order), ~0 (H, one slot per order). The device decodes the mask with one shift pair.
+constexpr std::uint32_t ROW_T = 0u, ROW_SV = 1u, ROW_H = 7u;
+constexpr std::uint32_t ROW_SLOT_BITS = 27u;
 
 // Superinstructions (internal to the plan, never part of a hy_program): opcodes >= HY_FOP_FIRST.
 //   HY_FOP_NBODY_PAIR  the gravitational pair interaction of model::nbody (src/model/nbody.cpp:97-153): 3 sub,
