@@ -105,22 +105,19 @@ __device__ __forceinline__ void fused_nbody_pair(const program &P, const Tape &t
         Q.set(n, q);
     }
 
-    // ---- f^[n] ----
-    Row F = Q;
-    if (fkind != 0u) {
-        F = t.hrow(aux[13]);
-        F.set(n, fkind == 1u ? t.cst(aux[14]) * q : -q);
-    }
-
-    // ---- m_k^[n] = sum_j A^[n-j] B^[j] with (A, B) = (d_k, f) or (f, d_k); the f loads are shared ----
+    // ---- m_k^[n] = sum_j A^[n-j] B^[j] with (A, B) = (d_k, f) or (f, d_k). f = c1 q (fkind 1), -q (2) or q
+    // (0) is not stored: f^[j] is recomputed from q^[j] (one rounding, the same value a stored row would
+    // hold), which frees a history row per pair. The f values are shared by the three products. ----
+    const double c1 = fkind == 1u ? t.cst(aux[14]) : 1.;
+    const auto f_of = [&](const V &qj) { return fkind == 1u ? c1 * qj : (fkind == 2u ? -qj : qj); };
     const bool f_first = aux[16] != 0u;
     V acc[3] = {splat<N>(0.), splat<N>(0.), splat<N>(0.)};
     if (!f_first) {
-        const double *pf = F.hptr(0u);
+        const double *pf = Q.hptr(0u);
         const double *pd0 = d0[0] + n * S, *pd1 = d0[1] + n * S, *pd2 = d0[2] + n * S;
 #pragma unroll 4
         for (std::uint32_t j = 0; j <= n; ++j) {
-            const V fj = Row::load(pf);
+            const V fj = f_of(Row::load(pf));
             acc[0] = vfma(Row::load(pd0), fj, acc[0]);
             acc[1] = vfma(Row::load(pd1), fj, acc[1]);
             acc[2] = vfma(Row::load(pd2), fj, acc[2]);
@@ -130,11 +127,11 @@ __device__ __forceinline__ void fused_nbody_pair(const program &P, const Tape &t
             pd2 -= S;
         }
     } else {
-        const double *pf = F.hptr(n);
+        const double *pf = Q.hptr(n);
         const double *pd0 = d0[0], *pd1 = d0[1], *pd2 = d0[2];
 #pragma unroll 4
         for (std::uint32_t j = 0; j <= n; ++j) {
-            const V fj = Row::load(pf);
+            const V fj = f_of(Row::load(pf));
             acc[0] = vfma(fj, Row::load(pd0), acc[0]);
             acc[1] = vfma(fj, Row::load(pd1), acc[1]);
             acc[2] = vfma(fj, Row::load(pd2), acc[2]);

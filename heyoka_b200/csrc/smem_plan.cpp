@@ -137,45 +137,6 @@ smem_plan make_smem_plan(const hy_program &p, bool fuse)
         }
     }
 
-    // ---- slot assignment ----
-    // Odd history stride: consecutive history rows then start in different shared-memory bank groups.
-    const std::uint32_t hstride = (order + 1u) | 1u;
-    std::vector<std::uint32_t> row(n_uvars, 0);
-    std::uint32_t next = 0;
-    const auto alloc = [&](std::uint32_t kind, std::uint32_t n) {
-        const auto r = (kind << ROW_SLOT_BITS) | next;
-        next += n;
-        return r;
-    };
-    for (std::uint32_t i = 0; i < n_uvars; ++i) {
-        if (hist[i]) {
-            row[i] = alloc(ROW_H, hstride);
-        } else if (i < n_eq) {
-            row[i] = alloc(ROW_SV, 2u);
-        } else {
-            row[i] = alloc(ROW_T, 1u);
-        }
-    }
-    if (next >= (1u << ROW_SLOT_BITS)) {
-        throw std::overflow_error("The Taylor tape is too large");
-    }
-    pl.n_slots = next;
-    pl.sv_rows.assign(row.begin(), row.begin() + n_eq);
-
-    // ---- n-ary argument table and state-variable definitions with row references ----
-    pl.args = p.args;
-    for (auto &ref : pl.args) {
-        if (HY_REF_KIND(ref) == HY_REF_VAR) {
-            ref = HY_REF(HY_REF_VAR, row[HY_REF_IDX(ref)]);
-        }
-    }
-    pl.sv_defs = p.sv_defs;
-    for (auto &ref : pl.sv_defs) {
-        if (HY_REF_KIND(ref) == HY_REF_VAR) {
-            ref = HY_REF(HY_REF_VAR, row[HY_REF_IDX(ref)]);
-        }
-    }
-
     // ---- superinstructions: the gravitational pair interaction of model::nbody ----
     // Pattern (src/model/nbody.cpp:97-153 after decomposition):
     //   d_k = sub(x_k^j, x_k^i), k = 0..2;  r2 = sum_sq(d_0, d_1, d_2);  q = pow(r2, alpha);
@@ -183,7 +144,10 @@ smem_plan make_smem_plan(const hy_program &p, bool fuse)
     // All of it depends, at the current order, only on state variables, so one thread can run the whole chain
     // for a pair. Every u variable keeps its own row and its own recurrence (bit-identical results).
     std::vector<char> fused(n_ops, 0);
+    std::vector<char> dropped(n_uvars, 0); // u variables that are never stored (recomputed inside a superinstruction)
     std::vector<item> items;
+    // aux entries that hold u-variable indices, to be translated into row references once slots are assigned
+    std::vector<std::size_t> aux_is_u;
     const auto op_of = [&](std::uint32_t u) -> const hy_op & { return p.ops[u - n_eq]; };
     const auto only_users = [&](std::uint32_t u, std::vector<std::uint32_t> allowed) {
         std::sort(allowed.begin(), allowed.end());
@@ -301,24 +265,35 @@ smem_plan make_smem_plan(const hy_program &p, bool fuse)
             it.op.b = fkind;
             it.op.c = have_n ? 1u : 0u;
             it.first_op = du[0] - n_eq;
+            const auto push_u = [&](std::uint32_t u) {
+                aux_is_u.push_back(pl.aux.size());
+                pl.aux.push_back(u);
+            };
             for (std::uint32_t k = 0; k < 3u; ++k) {
                 const auto &dop = op_of(du[k]);
-                pl.aux.push_back(row[dop.a]);
-                pl.aux.push_back(row[dop.b]);
-                pl.aux.push_back(row[du[k]]);
+                push_u(dop.a);
+                push_u(dop.b);
+                push_u(du[k]);
             }
-            pl.aux.push_back(row[r2u]);
-            pl.aux.push_back(row[qu]);
+            push_u(r2u);
+            push_u(qu);
             pl.aux.push_back(qop.b); // exponent (constant index)
             pl.aux.push_back(qop.c); // order-0 evaluation algorithm
-            pl.aux.push_back(row[fu]);
+            pl.aux.push_back(0u);    // (f is never stored: f^[j] = c1 q^[j] / -q^[j] is recomputed on the fly)
             pl.aux.push_back(c1);
             for (std::uint32_t k = 0; k < 3u; ++k) {
                 const auto &mop = op_of(mu[k]);
-                pl.aux.push_back(row[mu[k]]);
+                push_u(mu[k]);
                 pl.aux.push_back(mop.a == du[k] ? 0u : 1u); // operand order of the product (d * f or f * d)
-                pl.aux.push_back(have_n ? row[nu[k]] : 0u);
+                if (have_n) {
+                    push_u(nu[k]);
+                } else {
+                    pl.aux.push_back(0u);
+                }
                 pl.aux.push_back(have_n ? c2[k] : 0u);
+            }
+            if (fu != qu) {
+                dropped[fu] = 1;
             }
             std::vector<std::uint32_t> members{du[0], du[1], du[2], r2u, qu, mu[0], mu[1], mu[2]};
             if (fu != qu) {
@@ -359,6 +334,51 @@ smem_plan make_smem_plan(const hy_program &p, bool fuse)
             }
         }
         items.push_back(std::move(it));
+    }
+
+    // ---- slot assignment ----
+    // Odd history stride: consecutive history rows then start in different shared-memory bank groups.
+    const std::uint32_t hstride = (order + 1u) | 1u;
+    std::vector<std::uint32_t> row(n_uvars, 0);
+    std::uint32_t next = 0;
+    const auto alloc = [&](std::uint32_t kind, std::uint32_t n) {
+        const auto r = (kind << ROW_SLOT_BITS) | next;
+        next += n;
+        return r;
+    };
+    for (std::uint32_t i = 0; i < n_uvars; ++i) {
+        if (dropped[i]) {
+            row[i] = 0u;
+        } else if (hist[i]) {
+            row[i] = alloc(ROW_H, hstride);
+        } else if (i < n_eq) {
+            row[i] = alloc(ROW_SV, 2u);
+        } else {
+            row[i] = alloc(ROW_T, 1u);
+        }
+    }
+    if (next >= (1u << ROW_SLOT_BITS)) {
+        throw std::overflow_error("The Taylor tape is too large");
+    }
+    pl.n_slots = next;
+    pl.sv_rows.assign(row.begin(), row.begin() + n_eq);
+
+    // ---- n-ary argument table and state-variable definitions with row references ----
+    pl.args = p.args;
+    for (auto &ref : pl.args) {
+        if (HY_REF_KIND(ref) == HY_REF_VAR) {
+            ref = HY_REF(HY_REF_VAR, row[HY_REF_IDX(ref)]);
+        }
+    }
+    pl.sv_defs = p.sv_defs;
+    for (auto &ref : pl.sv_defs) {
+        if (HY_REF_KIND(ref) == HY_REF_VAR) {
+            ref = HY_REF(HY_REF_VAR, row[HY_REF_IDX(ref)]);
+        }
+    }
+
+    for (const auto pos : aux_is_u) {
+        pl.aux[pos] = row[pl.aux[pos]];
     }
 
     // ---- level scheduling: an item runs one level after the last producer of what it reads at the current
