@@ -90,7 +90,7 @@ std::vector<std::uint32_t> make_plan_blob(const hy::detail::smem_plan &pl, const
     h.off_ops = static_cast<std::uint32_t>(b.size());
     for (std::size_t i = 0; i < pl.ops.size(); ++i) {
         const auto &op = pl.ops[i];
-        b.insert(b.end(), {op.opcode, op.a, op.b, op.c, pl.dst[i], 0u, 0u, 0u});
+        b.insert(b.end(), {op.opcode, op.a, op.b, op.c, pl.dst[i], pl.svo[i], 0u, 0u});
     }
     h.off_seg = static_cast<std::uint32_t>(b.size());
     b.insert(b.end(), pl.seg_offsets.begin(), pl.seg_offsets.end());
@@ -107,11 +107,25 @@ std::vector<std::uint32_t> make_plan_blob(const hy::detail::smem_plan &pl, const
         b.push_back(w[1]);
     }
     align(2);
+    // Reciprocals 1 / k (IEEE division on the host) for the exact small-integer divisions.
+    h.off_rcp = static_cast<std::uint32_t>(b.size());
+    for (std::uint32_t k = 0; k <= p.order + 2u; ++k) {
+        const double r = k == 0u ? 0. : 1. / static_cast<double>(k);
+        std::uint32_t w[2];
+        std::memcpy(w, &r, sizeof(double));
+        b.push_back(w[0]);
+        b.push_back(w[1]);
+    }
+    align(4);
     h.off_sv = static_cast<std::uint32_t>(b.size());
     for (std::uint32_t i = 0; i < p.n_eq; ++i) {
-        b.push_back(pl.sv_rows[i]);
-        b.push_back(pl.sv_defs[i]);
+        b.insert(b.end(), {pl.sv_rows[i], pl.sv_defs[i], pl.sv_cover[i], pl.sv_parent[i]});
     }
+    h.off_svout = static_cast<std::uint32_t>(b.size());
+    b.insert(b.end(), pl.svout.begin(), pl.svout.end());
+    h.off_svphase = static_cast<std::uint32_t>(b.size());
+    h.n_svphase = static_cast<std::uint32_t>(pl.sv_phase.size());
+    b.insert(b.end(), pl.sv_phase.begin(), pl.sv_phase.end());
     align(4);
     h.n_words = static_cast<std::uint32_t>(b.size());
     std::memcpy(b.data(), &h, sizeof(h));

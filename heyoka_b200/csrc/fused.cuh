@@ -12,7 +12,7 @@
 namespace heyoka_b200::dev
 {
 
-constexpr std::uint32_t FOP_FIRST = 0x100u;
+constexpr std::uint32_t FOP_FIRST = 0x100u, FOP_NBODY_PAIR = 0x100u, FOP_SUM_T = 0x101u;
 
 // The gravitational pair interaction of model::nbody (src/model/nbody.cpp:97-153) at order n:
 //   d_k = x_k^j - x_k^i (src/detail/sub.cpp)            r2 = sum_sq(d_0, d_1, d_2) (src/detail/sum_sq.cpp)
@@ -21,9 +21,28 @@ constexpr std::uint32_t FOP_FIRST = 0x100u;
 // aux: [a_k, b_k, d_k] x 3, r2, q, alpha (constant index), order-0 pow algorithm, f, c1 (constant index),
 //      [m_k, operand order, n_k, c2_k (constant index)] x 3   (rows as packed row references; d_k, r2, q, f are
 //      history rows and m_k, n_k single-slot rows by construction, so their masks are never decoded).
+// A sum whose terms are all single-slot rows: args[off + k] is the slot of term k (pairwise summation of up to 8
+// terms, src/math/sum.cpp:250-371).
 template <int N, typename Tape>
+__device__ __forceinline__ vd<N> sum_single_slot(const Tape &t, std::uint32_t off, std::uint32_t cnt)
+{
+    using Row = typename Tape::row_t;
+    vd<N> v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        v[k] = splat<N>(0.);
+        if (k < static_cast<int>(cnt)) {
+            v[k] = Row::load(t.base + t.arg(off + k) * Row::stride);
+        }
+    }
+    return pairwise8(v, cnt);
+}
+
+// sv_out(offset, value, n): propagates a value that is the derivative of state variables (see coop_jet()).
+template <int N, typename Tape, typename SvOut>
 __device__ __forceinline__ void fused_nbody_pair(const program &P, const Tape &t, const std::uint32_t *aux,
-                                                 std::uint32_t fkind, bool have_n, std::uint32_t n)
+                                                 std::uint32_t fkind, bool have_n, std::uint32_t n,
+                                                 const SvOut &sv_out)
 {
     using V = vd<N>;
     using Row = typename Tape::row_t;
@@ -144,8 +163,15 @@ __device__ __forceinline__ void fused_nbody_pair(const program &P, const Tape &t
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         Row::store(const_cast<double *>(t.hrow(aux[15 + 4 * k]).hptr(0u)), acc[k]);
+        if (aux[27 + k] != 0u) {
+            sv_out(aux[27 + k], acc[k], n);
+        }
         if (have_n) {
-            Row::store(const_cast<double *>(t.hrow(aux[17 + 4 * k]).hptr(0u)), t.cst(aux[18 + 4 * k]) * acc[k]);
+            const V nk = t.cst(aux[18 + 4 * k]) * acc[k];
+            Row::store(const_cast<double *>(t.hrow(aux[17 + 4 * k]).hptr(0u)), nk);
+            if (aux[30 + k] != 0u) {
+                sv_out(aux[30 + k], nk, n);
+            }
         }
     }
 }

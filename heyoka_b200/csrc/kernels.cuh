@@ -335,7 +335,8 @@ __global__ void __launch_bounds__(256) k_hbm(program P, batch D, run_args R, dou
 struct coop_header {
     std::uint32_t n_words, n_items, n_segments, n_eq;
     std::uint32_t off_ops, off_seg, off_args, off_aux;
-    std::uint32_t off_consts, off_sv, n_slots, pad;
+    std::uint32_t off_consts, off_sv, n_slots, off_svout;
+    std::uint32_t off_svphase, n_svphase, off_rcp, pad;
 };
 
 template <int L, int N>
@@ -466,11 +467,14 @@ __device__ __forceinline__ void coop_jet(const program &P, const coop_header &H,
     constexpr std::uint32_t G = L / N; // lane groups per warp
     const std::uint32_t tid = threadIdx.x & 31u;
     constexpr std::uint32_t nthr = 32u;
-    const std::uint32_t pp1 = P.order + 1u;
+    const std::uint32_t pp1 = P.order + 1u, p = P.order;
     const uint4 *ops = reinterpret_cast<const uint4 *>(tab + H.off_ops);
     const std::uint32_t *seg = tab + H.off_seg;
     const std::uint32_t *aux = tab + H.off_aux;
-    const uint2 *svt = reinterpret_cast<const uint2 *>(tab + H.off_sv); // {row of the state variable, rhs reference}
+    const std::uint32_t *svout = tab + H.off_svout;
+    const std::uint32_t *svphase = tab + H.off_svphase;
+    const double *rcp = reinterpret_cast<const double *>(tab + H.off_rcp);
+    const uint4 *svt = reinterpret_cast<const uint4 *>(tab + H.off_sv); // {row, rhs reference, cover, parent}
 
     // This thread always works on the same lane group: g = tid % G.
     smem_tape<L, N> t;
@@ -498,35 +502,67 @@ __device__ __forceinline__ void coop_jet(const program &P, const coop_header &H,
             }
         }
     };
+    // State variables whose derivative is the value v = u^[n] just produced: x^[n+1] = v / (n + 1), and
+    // x2^[n+2] = x^[n+1] / (n + 2) for the state variables x2 that derive from x (see smem_plan.hpp).
+    const auto sv_out = [&](std::uint32_t off, const vd<N> &v, std::uint32_t n) {
+        const std::uint32_t *so = svout + off;
+        const std::uint32_t cnt = so[0];
+        vd<N> v1 = v;
+        for (std::uint32_t e = 0; e < cnt; ++e) {
+            const std::uint32_t sv = so[1u + 3u * e], rw = so[2u + 3u * e], depth = so[3u + 3u * e];
+            if (depth == 1u) {
+                v1 = div_small_int(v, n + 1u, static_cast<double>(n + 1u), rcp[n + 1u]);
+                t.row(rw).set(n + 1u, v1);
+                write_tc(sv, n + 1u, v1);
+            } else if (n + 2u <= p) {
+                const vd<N> v2 = div_small_int(v1, n + 2u, static_cast<double>(n + 2u), rcp[n + 2u]);
+                t.row(rw).set(n + 2u, v2);
+                write_tc(sv, n + 2u, v2);
+            }
+        }
+    };
 
-    // Order 0 of the state variables: the state itself. (it % G == g because nthr is a multiple of G.)
+    // Order 0 of the state variables: the state itself; order 1 of those that derive from another state
+    // variable (x^[1] = v^[0]). (it % G == g because nthr is a multiple of G.)
     for (std::uint32_t it = tid; it < P.n_eq * G; it += nthr) {
         const std::uint32_t sv = it / G;
+        const uint4 e = svt[sv];
         vd<N> v;
 #pragma unroll
         for (int i = 0; i < N; ++i) {
             v.v[i] = D.state[static_cast<std::size_t>(sv) * D.n + t.glane[i]];
         }
-        t.row(svt[sv].x).set(0u, v);
+        const auto r = t.row(e.x);
+        r.set(0u, v);
         write_tc(sv, 0u, v);
+        if (e.z == 2u) {
+            vd<N> vp;
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                vp.v[i] = D.state[static_cast<std::size_t>(e.w) * D.n + t.glane[i]];
+            }
+            r.set(1u, vp);
+            write_tc(sv, 1u, vp);
+        }
     }
     __syncwarp();
 
-    for (std::uint32_t n = 0; n <= P.order; ++n) {
-        if (n > 0u) {
-            // State variables: x^[n] = (rhs)^[n-1] / n.
-            const double nd = static_cast<double>(n), rcp = 1. / nd;
-            for (std::uint32_t it = tid; it < P.n_eq * G; it += nthr) {
-                const std::uint32_t sv = it / G;
-                const uint2 e = svt[sv];
-                const vd<N> v = sv_diff<N>(P, t, e.y, n, nd, rcp);
-                t.row(e.x).set(n, v);
-                write_tc(sv, n, v);
-            }
-            __syncwarp();
+    // The generic per-order pass for the state variables that no producer takes care of.
+    const auto sv_pass = [&](std::uint32_t n) {
+        const double nd = static_cast<double>(n), rc = rcp[n];
+        for (std::uint32_t it = tid; it < H.n_svphase * G; it += nthr) {
+            const std::uint32_t sv = svphase[it / G];
+            const uint4 e = svt[sv];
+            const vd<N> v = sv_diff<N>(P, t, e.y, n, nd, rc);
+            t.row(e.x).set(n, v);
+            write_tc(sv, n, v);
         }
-        if (n == P.order) {
-            break;
+        __syncwarp();
+    };
+
+    for (std::uint32_t n = 0; n < p; ++n) {
+        if (n > 0u && H.n_svphase != 0u) {
+            sv_pass(n);
         }
         // The other u variables, one dependency level at a time.
         for (std::uint32_t s = 0; s < H.n_segments; ++s) {
@@ -534,15 +570,28 @@ __device__ __forceinline__ void coop_jet(const program &P, const coop_header &H,
             for (std::uint32_t it = tid; it < (e - b) * G; it += nthr) {
                 const std::uint32_t k = b + it / G;
                 const uint4 op = ops[2u * k];
-                if (op.x >= FOP_FIRST) {
-                    fused_nbody_pair<N>(P, t, aux + op.y, op.z, op.w != 0u, n);
+                if (op.x == FOP_NBODY_PAIR) {
+                    fused_nbody_pair<N>(P, t, aux + op.y, op.z, op.w != 0u, n, sv_out);
                 } else {
-                    const auto self = t.row(ops[2u * k + 1u].x);
-                    self.set(n, diff_op<N>(P, t, op, self, n));
+                    const uint4 op2 = ops[2u * k + 1u];
+                    const auto self = t.row(op2.x);
+                    vd<N> v;
+                    if (op.x == FOP_SUM_T) {
+                        v = sum_single_slot<N>(t, op.y, op.z);
+                    } else {
+                        v = diff_op<N>(P, t, op, self, n);
+                    }
+                    self.set(n, v);
+                    if (op2.y != 0u) {
+                        sv_out(op2.y, v, n);
+                    }
                 }
             }
             __syncwarp();
         }
+    }
+    if (H.n_svphase != 0u) {
+        sv_pass(p);
     }
 }
 

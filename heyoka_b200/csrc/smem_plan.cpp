@@ -99,6 +99,7 @@ struct item {
     std::vector<std::uint32_t> deps; // u variables read at the current order, defined by OTHER items
     std::uint32_t level = 0;
     std::uint32_t first_op = 0;      // position of the first member op in the program (stable ordering)
+    std::uint32_t svo = 0;           // offset into svout (0 = none)
 };
 
 } // namespace
@@ -148,6 +149,11 @@ smem_plan make_smem_plan(const hy_program &p, bool fuse)
     std::vector<item> items;
     // aux entries that hold u-variable indices, to be translated into row references once slots are assigned
     std::vector<std::size_t> aux_is_u;
+    struct fused_out {
+        std::size_t aux_pos;
+        std::uint32_t u[6];
+    };
+    std::vector<fused_out> fused_outs;
     const auto op_of = [&](std::uint32_t u) -> const hy_op & { return p.ops[u - n_eq]; };
     const auto only_users = [&](std::uint32_t u, std::vector<std::uint32_t> allowed) {
         std::sort(allowed.begin(), allowed.end());
@@ -292,6 +298,10 @@ smem_plan make_smem_plan(const hy_program &p, bool fuse)
                 }
                 pl.aux.push_back(have_n ? c2[k] : 0u);
             }
+            // svout offsets of m_0..2, n_0..2 (filled in after level scheduling).
+            fused_outs.push_back({pl.aux.size(), {mu[0], mu[1], mu[2], have_n ? nu[0] : 0u, have_n ? nu[1] : 0u,
+                                                  have_n ? nu[2] : 0u}});
+            pl.aux.insert(pl.aux.end(), 6u, 0u);
             if (fu != qu) {
                 dropped[fu] = 1;
             }
@@ -417,6 +427,110 @@ smem_plan make_smem_plan(const hy_program &p, bool fuse)
     }
     pl.n_segments = n_levels;
 
+    // ---- state-variable propagation fused into the producers (see smem_plan.hpp) ----
+    {
+        // Highest level at which each state variable is read at the current order.
+        std::vector<std::int64_t> sv_read_level(n_eq, -1);
+        for (const auto &it : items) {
+            std::vector<std::uint32_t> reads;
+            if (it.op.opcode >= HY_FOP_FIRST) {
+                for (const auto d : it.defs) {
+                    const auto u = uses_of(p, op_of(d));
+                    reads.insert(reads.end(), u.now.begin(), u.now.end());
+                    reads.insert(reads.end(), u.hist.begin(), u.hist.end());
+                }
+            } else {
+                const auto u = uses_of(p, it.op);
+                reads.insert(reads.end(), u.now.begin(), u.now.end());
+                reads.insert(reads.end(), u.hist.begin(), u.hist.end());
+            }
+            for (const auto v : reads) {
+                if (v < n_eq) {
+                    sv_read_level[v] = std::max<std::int64_t>(sv_read_level[v], it.level);
+                }
+            }
+        }
+        pl.sv_cover.assign(n_eq, 0u);
+        pl.sv_parent.assign(n_eq, 0u);
+        std::vector<std::vector<std::uint32_t>> direct(n_uvars);   // u -> state variables with rhs u
+        std::vector<std::vector<std::uint32_t>> children(n_eq);    // s -> depth-2 state variables with rhs s
+        for (std::uint32_t s2 = 0; s2 < n_eq; ++s2) {
+            const auto ref = p.sv_defs[s2];
+            if (HY_REF_KIND(ref) == HY_REF_VAR && HY_REF_IDX(ref) >= n_eq && !dropped[HY_REF_IDX(ref)]) {
+                direct[HY_REF_IDX(ref)].push_back(s2);
+                pl.sv_cover[s2] = 1u;
+            }
+        }
+        for (std::uint32_t s2 = 0; s2 < n_eq; ++s2) {
+            const auto ref = p.sv_defs[s2];
+            if (HY_REF_KIND(ref) != HY_REF_VAR || HY_REF_IDX(ref) >= n_eq) {
+                continue;
+            }
+            const auto s1 = HY_REF_IDX(ref);
+            if (pl.sv_cover[s1] != 1u) {
+                continue;
+            }
+            // x_s2^[n+2] is written while order n is being processed, into the slot that holds x_s2^[n] unless
+            // s2 keeps its whole history: nobody may still read x_s2^[n] at or after the producer's level.
+            const auto prod_level = items[producer[HY_REF_IDX(p.sv_defs[s1])]].level;
+            if (!hist[s2] && sv_read_level[s2] >= static_cast<std::int64_t>(prod_level)) {
+                continue;
+            }
+            children[s1].push_back(s2);
+            pl.sv_cover[s2] = 2u;
+            pl.sv_parent[s2] = s1;
+        }
+        for (std::uint32_t s2 = 0; s2 < n_eq; ++s2) {
+            if (pl.sv_cover[s2] == 0u) {
+                pl.sv_phase.push_back(s2);
+            }
+        }
+        // svout lists.
+        std::vector<std::uint32_t> svo_of_u(n_uvars, 0u);
+        pl.svout.push_back(0u); // offset 0 is "none"
+        for (std::uint32_t u = n_eq; u < n_uvars; ++u) {
+            if (direct[u].empty()) {
+                continue;
+            }
+            svo_of_u[u] = static_cast<std::uint32_t>(pl.svout.size());
+            const auto cnt_pos = pl.svout.size();
+            pl.svout.push_back(0u);
+            std::uint32_t cnt = 0;
+            for (const auto s1 : direct[u]) {
+                pl.svout.insert(pl.svout.end(), {s1, row[s1], 1u});
+                ++cnt;
+                for (const auto s2 : children[s1]) {
+                    pl.svout.insert(pl.svout.end(), {s2, row[s2], 2u});
+                    ++cnt;
+                }
+            }
+            pl.svout[cnt_pos] = cnt;
+        }
+        for (const auto &fo : fused_outs) {
+            for (std::uint32_t k = 0; k < 6u; ++k) {
+                pl.aux[fo.aux_pos + k] = fo.u[k] != 0u ? svo_of_u[fo.u[k]] : 0u;
+            }
+        }
+        for (auto &it : items) {
+            it.svo = it.op.opcode >= HY_FOP_FIRST ? 0u : svo_of_u[it.dst_u];
+        }
+    }
+
+    // A sum whose terms are all single-slot rows: the argument table entries are the slots themselves.
+    for (auto &it : items) {
+        if (it.op.opcode != HY_OP_SUM) {
+            continue;
+        }
+        bool all_t = true;
+        for (std::uint32_t k = 0; k < it.op.b; ++k) {
+            const auto ref = p.args[it.op.a + k];
+            all_t = all_t && HY_REF_KIND(ref) == HY_REF_VAR && HY_REF_IDX(ref) >= n_eq && !hist[HY_REF_IDX(ref)];
+        }
+        if (all_t) {
+            it.op.opcode = HY_FOP_SUM_T;
+        }
+    }
+
     // ---- emit: level by level, grouped by opcode inside a level (warp-uniform control flow) ----
     pl.seg_offsets.push_back(0);
     for (std::uint32_t lvl = 0; lvl < n_levels; ++lvl) {
@@ -472,7 +586,8 @@ smem_plan make_smem_plan(const hy_program &p, bool fuse)
                     break;
             }
             pl.ops.push_back(op);
-            pl.dst.push_back(op.opcode >= HY_FOP_FIRST ? 0u : row[it->dst_u]);
+            pl.dst.push_back(op.opcode == HY_FOP_NBODY_PAIR ? 0u : row[it->dst_u]);
+            pl.svo.push_back(it->svo);
         }
         pl.seg_offsets.push_back(static_cast<std::uint32_t>(pl.ops.size()));
     }

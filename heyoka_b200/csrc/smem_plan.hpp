@@ -32,7 +32,10 @@ constexpr std::uint32_t ROW_SLOT_BITS = 27u;
 //                      sum_sq, pow, optional scaling, 3 products, optional 3 scalings run by ONE work item.
 //                      op.a = offset into aux (27 words, see make_smem_plan()), op.b = kind of the scaling of
 //                      r^alpha (0 none, 1 constant, 2 negation), op.c = 1 if the products are rescaled.
-constexpr std::uint32_t HY_FOP_FIRST = 0x100u, HY_FOP_NBODY_PAIR = 0x100u;
+//   HY_FOP_SUM_T       a sum whose terms are all single-slot rows (argument table entries = slots).
+constexpr std::uint32_t HY_FOP_FIRST = 0x100u, HY_FOP_NBODY_PAIR = 0x100u, HY_FOP_SUM_T = 0x101u;
+// Words per HY_FOP_NBODY_PAIR entry in aux: 27 operand words + 6 offsets into svout (m_0..2, n_0..2; 0 = none).
+constexpr std::uint32_t HY_FOP_NBODY_PAIR_AUX = 33u;
 
 struct smem_plan {
     std::uint32_t n_slots = 0;  // doubles of shared memory per lane
@@ -48,6 +51,13 @@ struct smem_plan {
     std::vector<std::uint32_t> sv_rows;     // row reference of each state variable
     std::vector<std::uint32_t> aux;         // operand tables of the superinstructions
     std::uint32_t n_fused = 0;              // number of superinstructions
+    // State-variable propagation fused into the producers. When u^[n] is the right-hand side of state variable
+    // s, the work item that produces it also writes x_s^[n+1] = u^[n] / (n + 1) (and x_s2^[n+2] for a state
+    // variable s2 whose derivative is s, e.g. positions whose derivative is a velocity): no separate pass and
+    // no synchronisation for those. svout: [count, (sv, row, depth) x count] lists, addressed by svo[] (one
+    // per op, 0 = none, else offset + 1). sv_cover[s]: 0 = handled by the generic per-order pass, 1 / 2 = depth
+    // of the fused propagation; sv_parent[s]: the state variable s derives from (depth 2).
+    std::vector<std::uint32_t> svout, svo, sv_cover, sv_parent, sv_phase;
 };
 
 smem_plan make_smem_plan(const hy_program &, bool fuse = true);
