@@ -1,0 +1,304 @@
+// heyoka_b200 — taylor_adaptive_batch<double>: the reference's batch integrator class, backed by the B200
+// kernels through the C ABI (include/heyoka_b200.h).
+//
+// Mirrors include/heyoka/taylor.hpp:780-1121 (bluescarni/heyoka @ 9c91f71) for T = double: same constructor
+// (system, state, batch size, kw::time / tol / high_accuracy / compact_mode / pars), same getters, step() /
+// step_backward() / step(max_delta_ts), propagate_for() / propagate_until() with kw::max_steps / max_delta_t /
+// callback / write_tc, get_step_res() / get_propagate_res(), update_d_output(), and ensemble_propagate_*_batch()
+// (include/heyoka/ensemble_propagate.hpp:220-269). Errors are the reference's exceptions with the reference's
+// messages (std::invalid_argument, not_implemented_error); numerical failure is taylor_outcome::err_nf_state.
+//
+// Ownership / raw-pointer contract (include/heyoka/taylor.hpp:974-977): the integrator owns host std::vector
+// mirrors of state, pars and time that the user may modify through get_state_data() / get_pars_data() between
+// calls; they are uploaded at every step()/propagate_*() entry and refreshed on exit. The device-resident
+// batch (hy_batch) is shared between copies only in its program: a copy gets its own device buffers.
+//
+// Not supported (out of the hot path): event detection (kw::t_events / kw::nt_events throw),
+// continuous output (kw::c_output = true throws), variational systems, serialisation. kw::compact_mode,
+// kw::parallel_mode, kw::parjit and the llvm_state options are accepted and ignored (there is no JIT).
+#ifndef HEYOKA_B200_TAYLOR_HPP
+#define HEYOKA_B200_TAYLOR_HPP
+
+#include <cstddef>
+#include <cstdint>
+#include <functional>
+#include <memory>
+#include <optional>
+#include <stdexcept>
+#include <tuple>
+#include <type_traits>
+#include <utility>
+#include <vector>
+
+#include <heyoka_b200.h>
+#include <heyoka_b200/expression.hpp>
+#include <heyoka_b200/kw.hpp>
+#include <heyoka_b200/taylor_decompose.hpp>
+
+namespace heyoka_b200
+{
+
+// include/heyoka/taylor.hpp:142-155.
+enum class taylor_outcome : std::int64_t {
+    success = HY_OUTCOME_SUCCESS,
+    step_limit = HY_OUTCOME_STEP_LIMIT,
+    time_limit = HY_OUTCOME_TIME_LIMIT,
+    err_nf_state = HY_OUTCOME_ERR_NF_STATE,
+    cb_stop = HY_OUTCOME_CB_STOP
+};
+
+// include/heyoka/exceptions.hpp:19.
+struct not_implemented_error final : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+
+template <typename T>
+class taylor_adaptive_batch;
+
+// Placeholder for the reference's continuous_output_batch<T> (not supported: propagate_*() always return an
+// empty optional).
+template <typename T>
+class continuous_output_batch
+{
+};
+
+// include/heyoka/step_callback.hpp:57-139 reduced to the call operator: bool(taylor_adaptive_batch<T> &).
+template <typename T>
+using step_callback_batch = std::function<bool(taylor_adaptive_batch<T> &)>;
+
+template <>
+class taylor_adaptive_batch<double>
+{
+public:
+    using value_type = double;
+
+private:
+    struct impl;
+    std::unique_ptr<impl> m_impl;
+
+    struct ctor_opts {
+        std::vector<double> time;
+        bool time_is_scalar = true;
+        double time_scalar = 0.;
+        std::optional<double> tol;
+        bool high_accuracy = false;
+        bool compact_mode = false;
+        std::vector<double> pars;
+        bool with_events = false;
+        int device = -1;
+    };
+    struct prop_opts {
+        std::size_t max_steps = 0;
+        std::vector<double> max_delta_t; // empty = +inf
+        step_callback_batch<double> cb;
+        bool write_tc = false;
+        bool c_output = false;
+    };
+
+    void finalise_ctor(std::vector<std::pair<expression, expression>>, std::vector<double>, std::uint32_t, ctor_opts);
+    void step_impl(const std::vector<double> *, bool backward, bool wtc);
+    std::tuple<std::optional<continuous_output_batch<double>>, step_callback_batch<double>>
+    propagate_until_impl(const std::vector<double> &hi, const std::vector<double> &lo, prop_opts);
+
+    template <typename... KwArgs>
+    static ctor_opts parse_ctor(const KwArgs &...kw_args)
+    {
+        static_assert(kw::allowed_tags<kw::time_tag, kw::tol_tag, kw::high_accuracy_tag, kw::compact_mode_tag,
+                                       kw::pars_tag, kw::parallel_mode_tag, kw::parjit_tag, kw::t_events_tag,
+                                       kw::nt_events_tag, kw::opt_level_tag, kw::fast_math_tag, kw::force_avx512_tag,
+                                       kw::slp_vectorize_tag, kw::mname_tag, kw::code_model_tag,
+                                       kw::device_tag>::template all<KwArgs...>(),
+                      "Invalid named argument(s) in the construction of a taylor_adaptive_batch");
+        ctor_opts o;
+        kw::visit(
+            kw::time,
+            [&o](const auto &v) {
+                if constexpr (std::is_arithmetic_v<std::decay_t<decltype(v)>>) {
+                    o.time_scalar = static_cast<double>(v);
+                } else {
+                    o.time_is_scalar = false;
+                    o.time.assign(std::begin(v), std::end(v));
+                }
+            },
+            kw_args...);
+        kw::visit(kw::tol, [&o](const auto &v) { o.tol = static_cast<double>(v); }, kw_args...);
+        kw::visit(kw::high_accuracy, [&o](const auto &v) { o.high_accuracy = static_cast<bool>(v); }, kw_args...);
+        kw::visit(kw::compact_mode, [&o](const auto &v) { o.compact_mode = static_cast<bool>(v); }, kw_args...);
+        kw::visit(kw::pars, [&o](const auto &v) { o.pars.assign(std::begin(v), std::end(v)); }, kw_args...);
+        kw::visit(kw::device, [&o](const auto &v) { o.device = static_cast<int>(v); }, kw_args...);
+        o.with_events = kw::has_tag<kw::t_events_tag, KwArgs...>() || kw::has_tag<kw::nt_events_tag, KwArgs...>();
+        return o;
+    }
+
+    template <typename... KwArgs>
+    prop_opts parse_prop(const KwArgs &...kw_args) const
+    {
+        static_assert(kw::allowed_tags<kw::max_steps_tag, kw::max_delta_t_tag, kw::callback_tag, kw::write_tc_tag,
+                                       kw::c_output_tag>::template all<KwArgs...>(),
+                      "Invalid named argument(s) in a propagate_*() call");
+        prop_opts o;
+        kw::visit(kw::max_steps, [&o](const auto &v) { o.max_steps = static_cast<std::size_t>(v); }, kw_args...);
+        kw::visit(
+            kw::max_delta_t,
+            [&o, this](const auto &v) {
+                if constexpr (std::is_arithmetic_v<std::decay_t<decltype(v)>>) {
+                    o.max_delta_t.assign(get_batch_size(), static_cast<double>(v));
+                } else {
+                    o.max_delta_t.assign(std::begin(v), std::end(v));
+                    if (o.max_delta_t.empty()) {
+                        // An empty vector means "no limit" (include/heyoka/taylor.hpp:733-776).
+                        return;
+                    }
+                    check_max_delta_t_size(o.max_delta_t.size());
+                }
+            },
+            kw_args...);
+        kw::visit(kw::callback, [&o](const auto &v) { o.cb = v; }, kw_args...);
+        kw::visit(kw::write_tc, [&o](const auto &v) { o.write_tc = static_cast<bool>(v); }, kw_args...);
+        kw::visit(kw::c_output, [&o](const auto &v) { o.c_output = static_cast<bool>(v); }, kw_args...);
+        return o;
+    }
+    void check_max_delta_t_size(std::size_t) const;
+
+public:
+    taylor_adaptive_batch();
+    template <typename... KwArgs>
+    explicit taylor_adaptive_batch(std::vector<std::pair<expression, expression>> sys, std::vector<double> state,
+                                   std::uint32_t batch_size, const KwArgs &...kw_args)
+        : taylor_adaptive_batch()
+    {
+        finalise_ctor(std::move(sys), std::move(state), batch_size, parse_ctor(kw_args...));
+    }
+    taylor_adaptive_batch(const taylor_adaptive_batch &);
+    taylor_adaptive_batch(taylor_adaptive_batch &&) noexcept;
+    taylor_adaptive_batch &operator=(const taylor_adaptive_batch &);
+    taylor_adaptive_batch &operator=(taylor_adaptive_batch &&) noexcept;
+    ~taylor_adaptive_batch();
+
+    [[nodiscard]] const taylor_dc_t &get_decomposition() const;
+    [[nodiscard]] std::uint32_t get_batch_size() const;
+    [[nodiscard]] std::uint32_t get_order() const;
+    [[nodiscard]] double get_tol() const;
+    [[nodiscard]] bool get_high_accuracy() const;
+    [[nodiscard]] bool get_compact_mode() const;
+    [[nodiscard]] std::uint32_t get_dim() const;
+    [[nodiscard]] const std::vector<std::pair<expression, expression>> &get_sys() const noexcept;
+
+    [[nodiscard]] const std::vector<double> &get_time() const;
+    [[nodiscard]] const double *get_time_data() const;
+    void set_time(const std::vector<double> &);
+    void set_time(double);
+    [[nodiscard]] std::pair<const std::vector<double> &, const std::vector<double> &> get_dtime() const;
+    void set_dtime(const std::vector<double> &, const std::vector<double> &);
+    void set_dtime(double, double);
+
+    [[nodiscard]] const std::vector<double> &get_state() const;
+    [[nodiscard]] const double *get_state_data() const;
+    [[nodiscard]] double *get_state_data();
+    [[nodiscard]] const std::vector<double> &get_pars() const;
+    [[nodiscard]] const double *get_pars_data() const;
+    [[nodiscard]] double *get_pars_data();
+
+    [[nodiscard]] const std::vector<double> &get_tc() const;
+    [[nodiscard]] const std::vector<double> &get_last_h() const;
+    [[nodiscard]] const std::vector<double> &get_d_output() const;
+    const std::vector<double> &update_d_output(const std::vector<double> &, bool rel_time = false);
+    const std::vector<double> &update_d_output(double, bool rel_time = false);
+    [[nodiscard]] bool with_events() const
+    {
+        return false;
+    }
+
+    void step(bool wtc = false);
+    void step_backward(bool wtc = false);
+    void step(const std::vector<double> &max_delta_ts, bool wtc = false);
+    [[nodiscard]] const std::vector<std::tuple<taylor_outcome, double>> &get_step_res() const;
+
+    template <typename... KwArgs>
+    std::tuple<std::optional<continuous_output_batch<double>>, step_callback_batch<double>>
+    propagate_until(const std::vector<double> &ts, const KwArgs &...kw_args)
+    {
+        return propagate_until_vec(ts, parse_prop(kw_args...));
+    }
+    template <typename... KwArgs>
+    std::tuple<std::optional<continuous_output_batch<double>>, step_callback_batch<double>>
+    propagate_until(double t, const KwArgs &...kw_args)
+    {
+        return propagate_until_vec(std::vector<double>(get_batch_size(), t), parse_prop(kw_args...));
+    }
+    template <typename... KwArgs>
+    std::tuple<std::optional<continuous_output_batch<double>>, step_callback_batch<double>>
+    propagate_for(const std::vector<double> &delta_ts, const KwArgs &...kw_args)
+    {
+        return propagate_for_vec(delta_ts, parse_prop(kw_args...));
+    }
+    template <typename... KwArgs>
+    std::tuple<std::optional<continuous_output_batch<double>>, step_callback_batch<double>>
+    propagate_for(double delta_t, const KwArgs &...kw_args)
+    {
+        return propagate_for_vec(std::vector<double>(get_batch_size(), delta_t), parse_prop(kw_args...));
+    }
+    [[nodiscard]] const std::vector<std::tuple<taylor_outcome, double, double, std::size_t>> &
+    get_propagate_res() const;
+
+    // Extensions: the device-resident batch behind this integrator, and kernel selection.
+    [[nodiscard]] hy_batch *get_device_batch();
+    void set_kernel(int tape_mode, std::uint32_t lanes_per_warp = 0, std::uint32_t lanes_per_thread = 0,
+                    std::uint32_t block_threads = 0, std::uint32_t blocks_per_sm = 0);
+
+private:
+    std::tuple<std::optional<continuous_output_batch<double>>, step_callback_batch<double>>
+    propagate_until_vec(const std::vector<double> &, prop_opts);
+    std::tuple<std::optional<continuous_output_batch<double>>, step_callback_batch<double>>
+    propagate_for_vec(const std::vector<double> &, prop_opts);
+};
+
+// ------------------------------------------------------------------------------------------------
+// Ensemble propagation (include/heyoka/ensemble_propagate.hpp:220-269, src/ensemble_propagate.cpp:192-311):
+// n_iter independent copies of an integrator, each customised by gen(ta, i), propagated and returned. The
+// reference runs them under TBB; here every member is a device-resident batch and members are launched one
+// after the other on the GPU(s) (members may be placed on different devices through gen()).
+// ------------------------------------------------------------------------------------------------
+template <typename... KwArgs>
+std::vector<std::tuple<taylor_adaptive_batch<double>, std::optional<continuous_output_batch<double>>,
+                       step_callback_batch<double>>>
+ensemble_propagate_until_batch(
+    const taylor_adaptive_batch<double> &ta, double t, std::size_t n_iter,
+    const std::function<taylor_adaptive_batch<double>(taylor_adaptive_batch<double>, std::size_t)> &gen,
+    const KwArgs &...kw_args)
+{
+    std::vector<std::tuple<taylor_adaptive_batch<double>, std::optional<continuous_output_batch<double>>,
+                           step_callback_batch<double>>>
+        retval;
+    retval.reserve(n_iter);
+    for (std::size_t i = 0; i < n_iter; ++i) {
+        auto local_ta = gen(ta, i);
+        auto res = local_ta.propagate_until(t, kw_args...);
+        retval.emplace_back(std::move(local_ta), std::move(std::get<0>(res)), std::move(std::get<1>(res)));
+    }
+    return retval;
+}
+
+template <typename... KwArgs>
+std::vector<std::tuple<taylor_adaptive_batch<double>, std::optional<continuous_output_batch<double>>,
+                       step_callback_batch<double>>>
+ensemble_propagate_for_batch(
+    const taylor_adaptive_batch<double> &ta, double delta_t, std::size_t n_iter,
+    const std::function<taylor_adaptive_batch<double>(taylor_adaptive_batch<double>, std::size_t)> &gen,
+    const KwArgs &...kw_args)
+{
+    std::vector<std::tuple<taylor_adaptive_batch<double>, std::optional<continuous_output_batch<double>>,
+                           step_callback_batch<double>>>
+        retval;
+    retval.reserve(n_iter);
+    for (std::size_t i = 0; i < n_iter; ++i) {
+        auto local_ta = gen(ta, i);
+        auto res = local_ta.propagate_for(delta_t, kw_args...);
+        retval.emplace_back(std::move(local_ta), std::move(std::get<0>(res)), std::move(std::get<1>(res)));
+    }
+    return retval;
+}
+
+} // namespace heyoka_b200
+
+#endif

@@ -1,0 +1,266 @@
+// C++ API tests for heyoka_b200::taylor_adaptive_batch<double>, written after the reference's own
+// test/taylor_adaptive_batch.cpp ("batch consistency" :105-144, "propagate for_until" :528-731, ctor errors
+// :955-1016) and test/ensemble_propagate.cpp:355-467. Run by tests/test_cpp_api.py.
+//
+//   test_batch_api cpu   -> argument validation only (no CUDA device needed)
+//   test_batch_api gpu   -> everything
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <functional>
+#include <iostream>
+#include <limits>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include <heyoka_b200/heyoka_b200.hpp>
+
+using namespace heyoka_b200;
+
+static int n_fail = 0;
+#define REQUIRE(cond)                                                                                                  \
+    do {                                                                                                               \
+        if (!(cond)) {                                                                                                 \
+            std::printf("REQUIRE failed at %s:%d: %s\n", __FILE__, __LINE__, #cond);                                   \
+            ++n_fail;                                                                                                  \
+        }                                                                                                              \
+    } while (0)
+#define REQUIRE_THROWS_MSG(expr, exc, msg)                                                                             \
+    do {                                                                                                               \
+        bool ok_ = false;                                                                                              \
+        try {                                                                                                          \
+            expr;                                                                                                      \
+        } catch (const exc &e_) {                                                                                      \
+            ok_ = std::string(e_.what()).find(msg) != std::string::npos;                                               \
+            if (!ok_) {                                                                                                \
+                std::printf("wrong message at %s:%d: %s\n", __FILE__, __LINE__, e_.what());                            \
+            }                                                                                                          \
+        } catch (...) {                                                                                                \
+        }                                                                                                              \
+        if (!ok_) {                                                                                                    \
+            std::printf("REQUIRE_THROWS failed at %s:%d: %s\n", __FILE__, __LINE__, #expr);                            \
+            ++n_fail;                                                                                                  \
+        }                                                                                                              \
+    } while (0)
+
+static bool approx(double a, double b, double tol_eps)
+{
+    const double eps = std::numeric_limits<double>::epsilon();
+    return std::abs(a - b) <= eps * tol_eps * std::max(std::abs(a), std::abs(b));
+}
+
+static void test_ctor_errors()
+{
+    auto [x, v] = make_vars("x", "v");
+    using ta_t = taylor_adaptive_batch<double>;
+    const std::vector<std::pair<expression, expression>> sys{prime(x) = v, prime(v) = -9.8 * sin(x)};
+
+    REQUIRE_THROWS_MSG((ta_t{sys, {0.05, 0.06, 0.025, 0.026}, 0u}), std::invalid_argument,
+                       "The batch size in an adaptive Taylor integrator cannot be zero");
+    REQUIRE_THROWS_MSG((ta_t{sys, {0.05, 0.06, 0.025}, 2u}), std::invalid_argument,
+                       "which is not a multiple of the batch size (2)");
+    REQUIRE_THROWS_MSG((ta_t{sys, {0.05, 0.06}, 2u}), std::invalid_argument,
+                       "the state vector has a dimension of 1 and a batch size of 2, while the number of equations is 2");
+    REQUIRE_THROWS_MSG((ta_t{sys, {0.05, 0.06, 0.025, 0.026}, 2u, kw::time = std::vector<double>{0.}}),
+                       std::invalid_argument, "the time vector has a size of 1, which is not equal to the batch size (2)");
+    REQUIRE_THROWS_MSG((ta_t{sys, {0.05, 0.06, 0.025, 0.026}, 2u, kw::tol = -1.}), std::invalid_argument,
+                       "The tolerance in an adaptive Taylor integrator must be finite and positive");
+    REQUIRE_THROWS_MSG((ta_t{{prime(x) = v, prime(v) = -par[0] * sin(x)}, {0.05, 0.06, 0.025, 0.026}, 2u,
+                             kw::pars = std::vector<double>{1.}}),
+                       std::invalid_argument,
+                       "1 parameter value(s) were passed, but the ODE system contains 1 parameter(s) (in batches of 2)");
+    REQUIRE_THROWS_MSG((ta_t{{prime(x) = v, prime(x) = x}, {0.05, 0.06, 0.025, 0.026}, 2u}), std::invalid_argument,
+                       "appears twice");
+    REQUIRE_THROWS_MSG((ta_t{sys, {0.05, 0.06, 0.025, 0.026}, 2u, kw::t_events = std::vector<int>{1}}),
+                       not_implemented_error, "Event detection is not supported");
+}
+
+static void test_batch_consistency()
+{
+    // test/taylor_adaptive_batch.cpp:105-144: forced damped pendulum, batch 4 vs 4 scalar-like runs (here: the
+    // same lanes run as four batches of size 1), 1000 eps.
+    auto [x, v] = make_vars("x", "v");
+    const std::vector<std::pair<expression, expression>> sys{prime(x) = v,
+                                                             prime(v) = cos(heyoka_b200::time) - .1 * v - sin(x)};
+    const std::vector<double> st{0.05, 0.06, 0.07, 0.08, 0.025, 0.026, 0.027, 0.028};
+    for (const bool ha : {false, true}) {
+        taylor_adaptive_batch<double> ta{sys, st, 4u, kw::high_accuracy = ha};
+        std::vector<taylor_adaptive_batch<double>> scal;
+        for (unsigned i = 0; i < 4u; ++i) {
+            scal.emplace_back(sys, std::vector<double>{st[i], st[4u + i]}, 1u, kw::high_accuracy = ha);
+        }
+        for (int step = 0; step < 200; ++step) {
+            ta.step();
+            for (unsigned i = 0; i < 4u; ++i) {
+                scal[i].step();
+                REQUIRE(std::get<0>(ta.get_step_res()[i]) == taylor_outcome::success);
+                REQUIRE(approx(ta.get_state()[i], scal[i].get_state()[0], 1000.));
+                REQUIRE(approx(ta.get_state()[4u + i], scal[i].get_state()[1], 1000.));
+                REQUIRE(approx(ta.get_time()[i], scal[i].get_time()[0], 1000.));
+            }
+        }
+    }
+}
+
+static void test_propagate_for_until()
+{
+    // test/taylor_adaptive_batch.cpp:528-731.
+    auto [x, v] = make_vars("x", "v");
+    for (const bool cm : {true, false}) {
+        auto ta = taylor_adaptive_batch<double>{
+            {prime(x) = v, prime(v) = -9.8 * sin(x)}, {0.05, 0.06, 0.025, 0.026}, 2u, kw::compact_mode = cm};
+        auto ta_copy = ta;
+
+        REQUIRE_THROWS_MSG(ta.propagate_until({0., std::numeric_limits<double>::infinity()}), std::invalid_argument,
+                           "A non-finite time was passed to the propagate_until() function of an adaptive "
+                           "Taylor integrator in batch mode");
+        REQUIRE_THROWS_MSG(ta.propagate_until({10., 11.}, kw::max_delta_t = std::vector<double>{1}),
+                           std::invalid_argument,
+                           "Invalid number of max timesteps specified in a Taylor integrator in batch mode: the batch "
+                           "size is 2, but the number of specified timesteps is 1");
+        REQUIRE_THROWS_MSG(
+            ta.propagate_until({10., 11.}, kw::max_delta_t = {1., std::numeric_limits<double>::quiet_NaN()}),
+            std::invalid_argument, "A nan max_delta_t was passed to the propagate_until() function");
+        REQUIRE_THROWS_MSG(ta.propagate_until({10., 11.}, kw::max_delta_t = {1., -1.}), std::invalid_argument,
+                           "A non-positive max_delta_t was passed to the propagate_until() function");
+        ta.set_time({0., std::numeric_limits<double>::lowest()});
+        REQUIRE_THROWS_MSG(ta.propagate_until({10., std::numeric_limits<double>::max()}), std::invalid_argument,
+                           "results in an overflow condition");
+        ta.set_time({0., 0.});
+
+        unsigned long counter0 = 0, counter1 = 0;
+        auto cb = [&counter0, &counter1](taylor_adaptive_batch<double> &t) {
+            if (t.get_last_h()[0] != 0) {
+                ++counter0;
+            }
+            if (t.get_last_h()[1] != 0) {
+                ++counter1;
+            }
+            return true;
+        };
+
+        // Callback path (host lock-step loop) with tiny max_delta_t: scaled down from the reference's 1e-4 / 5e-5
+        // to keep the per-step host round trips affordable; the fused device path below runs the original.
+        ta.propagate_until({1., 1.1}, kw::max_delta_t = {1e-2, 5e-3}, kw::callback = cb);
+        REQUIRE((ta.get_time() == std::vector<double>{1., 1.1}));
+        REQUIRE(counter0 == 100ul);
+        REQUIRE(counter1 == 220ul);
+        for (const auto &r : ta.get_propagate_res()) {
+            REQUIRE(std::get<0>(r) == taylor_outcome::time_limit);
+        }
+
+        // Same limits through the device loop (no callback): exact step counts 100000 / 220000 (:586-598).
+        auto ta2 = ta_copy;
+        ta2.propagate_until({10., 11.}, kw::max_delta_t = {1e-4, 5e-5});
+        ta_copy.propagate_until({10., 11.});
+        REQUIRE((ta2.get_time() == std::vector<double>{10., 11.}));
+        REQUIRE(std::get<3>(ta2.get_propagate_res()[0]) == 100000u);
+        REQUIRE(std::get<3>(ta2.get_propagate_res()[1]) == 220000u);
+        REQUIRE((ta_copy.get_time() == std::vector<double>{10., 11.}));
+        for (unsigned i = 0; i < 4u; ++i) {
+            REQUIRE(approx(ta2.get_state()[i], ta_copy.get_state()[i], 1000.));
+        }
+
+        // Scalar vs vector final time (:606-612).
+        auto c2 = ta_copy, c3 = ta_copy;
+        c2.propagate_until(20.);
+        c3.propagate_until({20., 20.});
+        REQUIRE(c2.get_state() == c3.get_state());
+        c2.propagate_for(5., kw::max_delta_t = 1e-2);
+        c3.propagate_for({5., 5.}, kw::max_delta_t = {1e-2, 1e-2});
+        REQUIRE(c2.get_state() == c3.get_state());
+        REQUIRE(c2.get_propagate_res() == c3.get_propagate_res());
+
+        // Callback interruption: all outcomes become cb_stop (:853-).
+        int n_calls = 0;
+        c2.propagate_for(10., kw::callback = [&n_calls](taylor_adaptive_batch<double> &) { return ++n_calls < 3; });
+        REQUIRE(n_calls == 3);
+        for (const auto &r : c2.get_propagate_res()) {
+            REQUIRE(std::get<0>(r) == taylor_outcome::cb_stop);
+        }
+        // max_steps: step_limit for everybody.
+        c3.propagate_for(10., kw::max_steps = 2u);
+        for (const auto &r : c3.get_propagate_res()) {
+            REQUIRE(std::get<0>(r) == taylor_outcome::step_limit);
+            REQUIRE(std::get<3>(r) == 2u);
+        }
+    }
+}
+
+static void test_ensemble()
+{
+    // test/ensemble_propagate.cpp:355-467: harmonic oscillator, members must equal sequential runs bit for bit.
+    auto [x, v] = make_vars("x", "v");
+    taylor_adaptive_batch<double> ta{{prime(x) = v, prime(v) = -x}, {0., 0., 1., 1.}, 2u};
+    const std::size_t n_iter = 16;
+    const auto gen = [](taylor_adaptive_batch<double> tac, std::size_t i) {
+        tac.get_state_data()[0] += i / 100.;
+        tac.get_state_data()[1] += i / 100.;
+        tac.get_state_data()[2] += i / 100.;
+        tac.get_state_data()[3] += i / 100.;
+        return tac;
+    };
+    auto res = ensemble_propagate_until_batch(ta, 20., n_iter, gen);
+    REQUIRE(res.size() == n_iter);
+    for (std::size_t i = 0; i < n_iter; ++i) {
+        auto seq = gen(ta, i);
+        seq.propagate_until(20.);
+        REQUIRE(std::get<0>(res[i]).get_state() == seq.get_state());
+        REQUIRE(std::get<0>(res[i]).get_time() == seq.get_time());
+        REQUIRE(std::get<0>(res[i]).get_propagate_res() == seq.get_propagate_res());
+    }
+}
+
+static void test_models_and_dense_output()
+{
+    const std::vector<double> masses{1.00000597682, 1 / 1047.355, 1 / 3501.6, 1 / 22869., 1 / 19314., 7.4074074e-09};
+    const double G = 0.01720209895 * 0.01720209895 * 365 * 365;
+    auto sys = model::nbody(6, kw::masses = masses, kw::Gconst = G);
+    REQUIRE(sys.size() == 36u);
+    std::vector<double> st(36u * 3u);
+    for (std::size_t i = 0; i < st.size(); ++i) {
+        st[i] = 0.1 + 0.37 * static_cast<double>((i * 7919u) % 101u) / 101.;
+    }
+    taylor_adaptive_batch<double> ta{sys, st, 3u, kw::high_accuracy = true, kw::tol = 1e-12};
+    REQUIRE(ta.get_order() == 15u);
+    REQUIRE(ta.get_decomposition().size() == 36u + 198u + 36u);
+    const auto st0 = ta.get_state();
+    ta.step(true);
+    const auto &h = ta.get_last_h();
+    // dense output at tau = h reproduces the state, at tau = 0 the previous state
+    auto d1 = ta.update_d_output(std::vector<double>(h.begin(), h.end()), true);
+    for (std::size_t i = 0; i < st.size(); ++i) {
+        REQUIRE(approx(d1[i], ta.get_state()[i], 100.));
+    }
+    auto d0 = ta.update_d_output(0., true);
+    for (std::size_t i = 0; i < st.size(); ++i) {
+        REQUIRE(d0[i] == st0[i]);
+    }
+    // tc[var][0][lane] is the state before the step (src/taylor_00.cpp:574-580 layout)
+    for (unsigned var = 0; var < 36u; ++var) {
+        for (unsigned l = 0; l < 3u; ++l) {
+            REQUIRE(ta.get_tc()[(var * 16u + 0u) * 3u + l] == st0[var * 3u + l]);
+        }
+    }
+    auto psys = model::pendulum(kw::gconst = 9.8, kw::length = 1.);
+    REQUIRE(psys.size() == 2u);
+}
+
+int main(int argc, char **argv)
+{
+    const bool gpu = argc > 1 && std::strcmp(argv[1], "gpu") == 0;
+    test_ctor_errors();
+    if (gpu) {
+        test_batch_consistency();
+        test_propagate_for_until();
+        test_ensemble();
+        test_models_and_dense_output();
+    }
+    if (n_fail == 0) {
+        std::printf("ALL PASSED (%s)\n", gpu ? "gpu" : "cpu");
+        return 0;
+    }
+    std::printf("%d FAILURES\n", n_fail);
+    return 1;
+}
