@@ -459,6 +459,50 @@ struct coop_smem {
     }
 };
 
+// Writes of state-variable coefficients: into the tape row and, streamed, into tc.
+template <int L, int N>
+struct sv_writer {
+    const smem_tape<L, N> &t;
+    double *tc;
+    const std::uint32_t *svout;
+    const double *rcp;
+    std::uint32_t pp1, n_batch, p;
+    bool lane_ok[N];
+
+    // Stream the coefficient of state variable sv at order n to tc (valid lanes only).
+    __device__ __forceinline__ void write_tc(std::uint32_t sv, std::uint32_t n, const vd<N> &v) const
+    {
+        double *dst = tc + (static_cast<std::size_t>(sv) * pp1 + n) * n_batch;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            if (lane_ok[i]) {
+                dst[t.glane[i]] = v.v[i];
+            }
+        }
+    }
+    // State variables whose derivative is the value v = u^[n] just produced: x^[n+1] = v / (n + 1), and
+    // x2^[n+2] = x^[n+1] / (n + 2) for the state variables x2 that derive from x (see smem_plan.hpp). Out of
+    // line: one copy of this code instead of one per call site (instruction cache).
+    __device__ __noinline__ void operator()(std::uint32_t off, const vd<N> &v, std::uint32_t n) const
+    {
+        const std::uint32_t *so = svout + off;
+        const std::uint32_t cnt = so[0];
+        vd<N> v1 = v;
+        for (std::uint32_t e = 0; e < cnt; ++e) {
+            const std::uint32_t sv = so[1u + 3u * e], rw = so[2u + 3u * e], depth = so[3u + 3u * e];
+            if (depth == 1u) {
+                v1 = div_small_int(v, n + 1u, static_cast<double>(n + 1u), rcp[n + 1u]);
+                t.row(rw).set(n + 1u, v1);
+                write_tc(sv, n + 1u, v1);
+            } else if (n + 2u <= p) {
+                const vd<N> v2 = div_small_int(v1, n + 2u, static_cast<double>(n + 2u), rcp[n + 2u]);
+                t.row(rw).set(n + 2u, v2);
+                write_tc(sv, n + 2u, v2);
+            }
+        }
+    }
+};
+
 // Jet of the L lanes starting at global lane `lane0`; the state variables' coefficients go to tc.
 template <int L, int N>
 __device__ __forceinline__ void coop_jet(const program &P, const coop_header &H, const std::uint32_t *tab,
@@ -492,35 +536,12 @@ __device__ __forceinline__ void coop_jet(const program &P, const coop_header &H,
         t.glane[i] = lane_ok[i] ? l : D.n - 1u;
         t.tm.v[i] = S.time[g * N + i];
     }
-    // Stream the coefficient of state variable sv at order n to tc (valid lanes only).
-    const auto write_tc = [&](std::uint32_t sv, std::uint32_t n, const vd<N> &v) {
-        double *dst = D.tc + (static_cast<std::size_t>(sv) * pp1 + n) * D.n;
+    const sv_writer<L, N> sv_out{t, D.tc, svout, rcp, pp1, D.n, p, {}};
 #pragma unroll
-        for (int i = 0; i < N; ++i) {
-            if (lane_ok[i]) {
-                dst[t.glane[i]] = v.v[i];
-            }
-        }
-    };
-    // State variables whose derivative is the value v = u^[n] just produced: x^[n+1] = v / (n + 1), and
-    // x2^[n+2] = x^[n+1] / (n + 2) for the state variables x2 that derive from x (see smem_plan.hpp).
-    const auto sv_out = [&](std::uint32_t off, const vd<N> &v, std::uint32_t n) {
-        const std::uint32_t *so = svout + off;
-        const std::uint32_t cnt = so[0];
-        vd<N> v1 = v;
-        for (std::uint32_t e = 0; e < cnt; ++e) {
-            const std::uint32_t sv = so[1u + 3u * e], rw = so[2u + 3u * e], depth = so[3u + 3u * e];
-            if (depth == 1u) {
-                v1 = div_small_int(v, n + 1u, static_cast<double>(n + 1u), rcp[n + 1u]);
-                t.row(rw).set(n + 1u, v1);
-                write_tc(sv, n + 1u, v1);
-            } else if (n + 2u <= p) {
-                const vd<N> v2 = div_small_int(v1, n + 2u, static_cast<double>(n + 2u), rcp[n + 2u]);
-                t.row(rw).set(n + 2u, v2);
-                write_tc(sv, n + 2u, v2);
-            }
-        }
-    };
+    for (int i = 0; i < N; ++i) {
+        const_cast<bool &>(sv_out.lane_ok[i]) = lane_ok[i];
+    }
+    const auto write_tc = [&](std::uint32_t sv, std::uint32_t n, const vd<N> &v) { sv_out.write_tc(sv, n, v); };
 
     // Order 0 of the state variables: the state itself; order 1 of those that derive from another state
     // variable (x^[1] = v^[0]). (it % G == g because nthr is a multiple of G.)

@@ -544,6 +544,12 @@ __device__ __forceinline__ double div_small_int(double x, std::uint32_t n)
     const double r = ::fma(-q, nd, x);
     return ::fma(r, y, q);
 }
+// The (cold) IEEE division fallback, kept out of line: the division routine is ~40 instructions and would be
+// inlined at every call site otherwise.
+__device__ __noinline__ double div_fallback(double x, double nd)
+{
+    return x / nd;
+}
 template <int N>
 __device__ __forceinline__ vd<N> div_small_int(const vd<N> &x, std::uint32_t n, double nd, double rcp)
 {
@@ -552,7 +558,7 @@ __device__ __forceinline__ vd<N> div_small_int(const vd<N> &x, std::uint32_t n, 
     for (int i = 0; i < N; ++i) {
         const double ax = fabs(x.v[i]);
         if (n > 64u || !(ax > 0x1p-900 && ax < 0x1p900)) {
-            out.v[i] = x.v[i] / nd;
+            out.v[i] = div_fallback(x.v[i], nd);
         } else {
             const double q = x.v[i] * rcp;
             const double r = ::fma(-q, nd, x.v[i]);

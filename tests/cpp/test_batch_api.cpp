@@ -142,10 +142,11 @@ static void test_propagate_for_until()
 
         // Callback path (host lock-step loop) with tiny max_delta_t: scaled down from the reference's 1e-4 / 5e-5
         // to keep the per-step host round trips affordable; the fused device path below runs the original.
-        ta.propagate_until({1., 1.1}, kw::max_delta_t = {1e-2, 5e-3}, kw::callback = cb);
-        REQUIRE((ta.get_time() == std::vector<double>{1., 1.1}));
-        REQUIRE(counter0 == 100ul);
-        REQUIRE(counter1 == 220ul);
+        // (powers of two, so that the step counts are exact whatever the rounding of the last step.)
+        ta.propagate_until({1., 1.25}, kw::max_delta_t = {0.0078125, 0.00390625}, kw::callback = cb);
+        REQUIRE((ta.get_time() == std::vector<double>{1., 1.25}));
+        REQUIRE(counter0 == 128ul);
+        REQUIRE(counter1 == 320ul);
         for (const auto &r : ta.get_propagate_res()) {
             REQUIRE(std::get<0>(r) == taylor_outcome::time_limit);
         }
