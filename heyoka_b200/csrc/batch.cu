@@ -571,7 +571,11 @@ int hy_batch_create(const hy_program *p, uint32_t batch, int device, hy_batch **
         if (const char *env = std::getenv("HEYOKA_B200_FUSE")) {
             fuse = std::string{env} != "0";
         }
-        b->plan = hy::detail::make_smem_plan(*p, fuse);
+        bool fuse_sv = true;
+        if (const char *env = std::getenv("HEYOKA_B200_FUSE_SV")) {
+            fuse_sv = std::string{env} != "0";
+        }
+        b->plan = hy::detail::make_smem_plan(*p, fuse, fuse_sv);
         {
             const auto blob = make_plan_blob(b->plan, *p);
             b->d_blob = b->dupload(blob);

@@ -481,9 +481,9 @@ struct sv_writer {
         }
     }
     // State variables whose derivative is the value v = u^[n] just produced: x^[n+1] = v / (n + 1), and
-    // x2^[n+2] = x^[n+1] / (n + 2) for the state variables x2 that derive from x (see smem_plan.hpp). Out of
-    // line: one copy of this code instead of one per call site (instruction cache).
-    __device__ __noinline__ void operator()(std::uint32_t off, const vd<N> &v, std::uint32_t n) const
+    // x2^[n+2] = x^[n+1] / (n + 2) for the state variables x2 that derive from x (see smem_plan.hpp).
+    // (Must stay inline: an out-of-line call would force the tape object into local memory.)
+    __device__ __forceinline__ void operator()(std::uint32_t off, const vd<N> &v, std::uint32_t n) const
     {
         const std::uint32_t *so = svout + off;
         const std::uint32_t cnt = so[0];

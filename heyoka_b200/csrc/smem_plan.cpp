@@ -104,7 +104,7 @@ struct item {
 
 } // namespace
 
-smem_plan make_smem_plan(const hy_program &p, bool fuse)
+smem_plan make_smem_plan(const hy_program &p, bool fuse, bool fuse_sv)
 {
     smem_plan pl;
     const auto n_eq = p.n_eq, n_uvars = p.n_uvars, order = p.order;
@@ -456,7 +456,7 @@ smem_plan make_smem_plan(const hy_program &p, bool fuse)
         std::vector<std::vector<std::uint32_t>> children(n_eq);    // s -> depth-2 state variables with rhs s
         for (std::uint32_t s2 = 0; s2 < n_eq; ++s2) {
             const auto ref = p.sv_defs[s2];
-            if (HY_REF_KIND(ref) == HY_REF_VAR && HY_REF_IDX(ref) >= n_eq && !dropped[HY_REF_IDX(ref)]) {
+            if (fuse_sv && HY_REF_KIND(ref) == HY_REF_VAR && HY_REF_IDX(ref) >= n_eq && !dropped[HY_REF_IDX(ref)]) {
                 direct[HY_REF_IDX(ref)].push_back(s2);
                 pl.sv_cover[s2] = 1u;
             }

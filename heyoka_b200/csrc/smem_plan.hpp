@@ -60,7 +60,7 @@ struct smem_plan {
     std::vector<std::uint32_t> svout, svo, sv_cover, sv_parent, sv_phase;
 };
 
-smem_plan make_smem_plan(const hy_program &, bool fuse = true);
+smem_plan make_smem_plan(const hy_program &, bool fuse = true, bool fuse_sv = true);
 
 } // namespace heyoka_b200::detail
 
