@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <limits>
+#include <memory>
 #include <new>
 #include <stdexcept>
 #include <string>
@@ -41,7 +42,7 @@ using hy::detail::translate_exception;
 namespace
 {
 
-using coop_fn = void (*)(dev::program, const std::uint32_t *, dev::batch, dev::run_args);
+using coop_fn = void (*)(dev::program, const std::uint32_t *, dev::batch, dev::run_args, double *);
 
 struct coop_variant {
     int L, N;
@@ -86,6 +87,7 @@ std::vector<std::uint32_t> make_plan_blob(const hy::detail::smem_plan &pl, const
     h.n_segments = pl.n_segments;
     h.n_eq = p.n_eq;
     h.n_slots = pl.n_slots;
+    h.n_gslots = pl.n_gslots;
     align(4);
     h.off_ops = static_cast<std::uint32_t>(b.size());
     for (std::size_t i = 0; i < pl.ops.size(); ++i) {
@@ -160,6 +162,11 @@ struct hy_batch {
     hy::detail::smem_plan plan;
     std::uint32_t *d_blob = nullptr;
     std::size_t blob_bytes = 0; // rounded up to 16 bytes
+    double *d_gscratch = nullptr; // overflow tape of the cooperative kernels (spilled private rows)
+    std::shared_ptr<const hy_program> prog_host; // kept for re-planning
+    bool opt_fuse = true, opt_fuse_sv = true;
+    int opt_spill = -1; // -1 automatic, 0 never, 1 always
+    void replan(bool spill);
 
     // Resident arrays.
     double *d_state = nullptr, *d_pars = nullptr, *d_t_hi = nullptr, *d_t_lo = nullptr, *d_last_h = nullptr,
@@ -221,7 +228,8 @@ void hy_batch::free_all() noexcept
 {
     for (void *p :
          {static_cast<void *>(d_ops), static_cast<void *>(d_args), static_cast<void *>(d_sv_defs),
-          static_cast<void *>(d_consts), static_cast<void *>(d_blob), static_cast<void *>(d_state),
+          static_cast<void *>(d_consts), static_cast<void *>(d_blob), static_cast<void *>(d_gscratch),
+          static_cast<void *>(d_state),
           static_cast<void *>(d_pars),
           static_cast<void *>(d_t_hi), static_cast<void *>(d_t_lo), static_cast<void *>(d_last_h),
           static_cast<void *>(d_tc), static_cast<void *>(d_d_out), static_cast<void *>(d_step_outcome),
@@ -293,13 +301,42 @@ void hy_batch::setup_hbm(std::uint32_t threads, std::uint32_t blocks_per_sm)
     mode = 1;
 }
 
+void hy_batch::replan(bool spill)
+{
+    plan = hy::detail::make_smem_plan(*prog_host, opt_fuse, opt_fuse_sv, spill);
+    const auto blob = make_plan_blob(plan, *prog_host);
+    if (d_blob != nullptr) {
+        HY_CUDA_CHECK(cudaFree(d_blob));
+        d_blob = nullptr;
+    }
+    d_blob = dupload(blob);
+    blob_bytes = (blob.size() + 3u) / 4u * 16u;
+}
+
 // Returns false if the requested / any configuration does not fit in shared memory.
 // L = lanes per warp, N = lanes per thread, threads = 32 x warps per block.
 bool hy_batch::setup_coop(int L, int N, std::uint32_t threads, std::uint32_t ctas_per_sm)
 {
     const std::size_t reserve = 1024u; // per-block reservation of the driver
     if (N == 0) {
-        N = 1;
+        // Two lanes per thread: the interpreter's per-item overhead is shared and the recurrences get ILP 2.
+        N = (L == 0 || L >= 2) ? 2 : 1;
+    }
+    // Spill the superinstructions' private history rows to the overflow tape when shared memory would
+    // otherwise allow fewer than 12 warps per SM (at the lanes-per-warp that will be used).
+    {
+        const bool have_spill = plan.n_gslots != 0u;
+        bool want_spill = have_spill;
+        if (opt_spill >= 0) {
+            want_spill = opt_spill != 0;
+        } else if (plan.n_fused != 0u && !have_spill) {
+            const int l_eff = L != 0 ? L : std::max(N, 1);
+            const auto fit = (smem_per_block_max - reserve - blob_bytes) / coop_warp_bytes(plan.n_slots, l_eff);
+            want_spill = fit < 12u;
+        }
+        if (want_spill != have_spill) {
+            replan(want_spill);
+        }
     }
     if (L == 0) {
         // Lanes per warp: enough of them that an average dependency segment gives work to most of the
@@ -314,7 +351,7 @@ bool hy_batch::setup_coop(int L, int N, std::uint32_t threads, std::uint32_t cta
                 break;
             }
             L = cand;
-            if (avg_width * cand / N >= 20.) {
+            if (avg_width * cand / N >= 12.) {
                 break;
             }
         }
@@ -356,6 +393,10 @@ bool hy_batch::setup_coop(int L, int N, std::uint32_t threads, std::uint32_t cta
         HY_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, v->prop, static_cast<int>(threads), bytes));
         ctas_per_sm = static_cast<std::uint32_t>(std::max(occ, 1));
     }
+    if (d_gscratch != nullptr) {
+        HY_CUDA_CHECK(cudaFree(d_gscratch));
+        d_gscratch = nullptr;
+    }
     cv = v;
     c_threads = threads;
     c_smem = bytes;
@@ -363,6 +404,10 @@ bool hy_batch::setup_coop(int L, int N, std::uint32_t threads, std::uint32_t cta
     const std::uint32_t lanes_per_block = static_cast<std::uint32_t>(L) * (threads / 32u);
     const std::uint32_t n_blocks_needed = (n + lanes_per_block - 1u) / lanes_per_block;
     c_grid = std::max(1u, std::min(n_sms * ctas_per_sm, n_blocks_needed));
+    if (plan.n_gslots != 0u) {
+        d_gscratch = dalloc<double>(static_cast<std::size_t>(c_grid) * (threads / 32u) * plan.n_gslots
+                                    * static_cast<std::size_t>(L));
+    }
     mode = 2;
     return true;
 }
@@ -387,7 +432,7 @@ void hy_batch::launch(bool prop, const dev::run_args &R)
 {
     HY_CUDA_CHECK(cudaMemsetAsync(d_counter, 0, sizeof(unsigned int), stream));
     if (mode == 2) {
-        (prop ? cv->prop : cv->step)<<<c_grid, c_threads, c_smem, stream>>>(prog, d_blob, view(), R);
+        (prop ? cv->prop : cv->step)<<<c_grid, c_threads, c_smem, stream>>>(prog, d_blob, view(), R, d_gscratch);
     } else if (prop) {
         dev::k_hbm<true><<<h_grid, h_threads, 0, stream>>>(prog, view(), R, d_scratch, slab_doubles);
     } else {
@@ -566,21 +611,19 @@ int hy_batch_create(const hy_program *p, uint32_t batch, int device, hy_batch **
         P.sv_defs = b->d_sv_defs;
 
         // Cooperative plan.
-        // HEYOKA_B200_FUSE=0 disables the superinstructions (diagnostics / tests).
-        bool fuse = true;
+        // HEYOKA_B200_FUSE=0 disables the superinstructions, HEYOKA_B200_FUSE_SV=0 the fused state-variable
+        // propagation, HEYOKA_B200_SPILL=0/1 forces the overflow tape off/on (diagnostics / tests).
         if (const char *env = std::getenv("HEYOKA_B200_FUSE")) {
-            fuse = std::string{env} != "0";
+            b->opt_fuse = std::string{env} != "0";
         }
-        bool fuse_sv = true;
         if (const char *env = std::getenv("HEYOKA_B200_FUSE_SV")) {
-            fuse_sv = std::string{env} != "0";
+            b->opt_fuse_sv = std::string{env} != "0";
         }
-        b->plan = hy::detail::make_smem_plan(*p, fuse, fuse_sv);
-        {
-            const auto blob = make_plan_blob(b->plan, *p);
-            b->d_blob = b->dupload(blob);
-            b->blob_bytes = (blob.size() + 3u) / 4u * 16u;
+        if (const char *env = std::getenv("HEYOKA_B200_SPILL")) {
+            b->opt_spill = std::string{env} != "0" ? 1 : 0;
         }
+        b->prog_host = std::make_shared<const hy_program>(*p);
+        b->replan(false);
 
         // Resident arrays.
         const std::size_t n = batch;

@@ -39,7 +39,8 @@ __device__ __forceinline__ vd<N> sum_single_slot(const Tape &t, std::uint32_t of
 }
 
 // sv_out(offset, value, n): propagates a value that is the derivative of state variables (see coop_jet()).
-template <int N, typename Tape, typename SvOut>
+// GLOBAL_RQ: the r^2 and r^alpha histories live in the overflow tape (global memory / L2) instead of shared memory.
+template <int N, bool GLOBAL_RQ, typename Tape, typename SvOut>
 __device__ __forceinline__ void fused_nbody_pair(const program &P, const Tape &t, const std::uint32_t *aux,
                                                  std::uint32_t fkind, bool have_n, std::uint32_t n,
                                                  const SvOut &sv_out)
@@ -60,7 +61,7 @@ __device__ __forceinline__ void fused_nbody_pair(const program &P, const Tape &t
 
     // ---- r2^[n]: SUM_SQ over the three differences; the three convolutions run interleaved (each keeps
     // its own accumulator and its own summation order) ----
-    const Row R2 = t.hrow(aux[9]);
+    const Row R2 = GLOBAL_RQ ? t.grow(aux[9]) : t.hrow(aux[9]);
     {
         const bool odd = (n & 1u) != 0u;
         V acc[3] = {splat<N>(0.), splat<N>(0.), splat<N>(0.)};
@@ -100,7 +101,7 @@ __device__ __forceinline__ void fused_nbody_pair(const program &P, const Tape &t
     }
 
     // ---- q^[n] = pow(r2, alpha) ----
-    const Row Q = t.hrow(aux[10]);
+    const Row Q = GLOBAL_RQ ? t.grow(aux[10]) : t.hrow(aux[10]);
     V q;
     {
         const V alpha = splat<N>(t.cst(aux[11]));

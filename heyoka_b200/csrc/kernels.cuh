@@ -336,12 +336,13 @@ struct coop_header {
     std::uint32_t n_words, n_items, n_segments, n_eq;
     std::uint32_t off_ops, off_seg, off_args, off_aux;
     std::uint32_t off_consts, off_sv, n_slots, off_svout;
-    std::uint32_t off_svphase, n_svphase, off_rcp, pad;
+    std::uint32_t off_svphase, n_svphase, off_rcp, n_gslots;
 };
 
 template <int L, int N>
 struct smem_tape {
-    double *base; // the warp's tape + first lane of this thread's group
+    double *base;  // the warp's tape + first lane of this thread's group
+    double *gbase; // idem for the overflow tape in global memory (nullptr if unused)
     const std::uint32_t *args;
     const double *consts;
     const double *pars;
@@ -422,6 +423,11 @@ struct smem_tape {
     __device__ __forceinline__ row_t hrow(std::uint32_t ref) const
     {
         return row_t{base + (ref & 0x7ffffffu) * L, 0xffffffffu};
+    }
+    // A history row of the overflow tape.
+    __device__ __forceinline__ row_t grow(std::uint32_t ref) const
+    {
+        return row_t{gbase + (ref & 0x7ffffffu) * L, 0xffffffffu};
     }
     __device__ __forceinline__ vd<N> par(std::uint32_t idx) const
     {
@@ -506,7 +512,7 @@ struct sv_writer {
 // Jet of the L lanes starting at global lane `lane0`; the state variables' coefficients go to tc.
 template <int L, int N>
 __device__ __forceinline__ void coop_jet(const program &P, const coop_header &H, const std::uint32_t *tab,
-                                         const batch &D, const coop_smem<L> &S, std::uint32_t lane0)
+                                         const batch &D, const coop_smem<L> &S, std::uint32_t lane0, double *gtape)
 {
     constexpr std::uint32_t G = L / N; // lane groups per warp
     const std::uint32_t tid = threadIdx.x & 31u;
@@ -524,6 +530,7 @@ __device__ __forceinline__ void coop_jet(const program &P, const coop_header &H,
     smem_tape<L, N> t;
     const std::uint32_t g = tid % G;
     t.base = S.tape + g * N;
+    t.gbase = gtape != nullptr ? gtape + g * N : nullptr;
     t.args = tab + H.off_args;
     t.consts = reinterpret_cast<const double *>(tab + H.off_consts);
     t.pars = D.pars;
@@ -592,7 +599,11 @@ __device__ __forceinline__ void coop_jet(const program &P, const coop_header &H,
                 const std::uint32_t k = b + it / G;
                 const uint4 op = ops[2u * k];
                 if (op.x == FOP_NBODY_PAIR) {
-                    fused_nbody_pair<N>(P, t, aux + op.y, op.z, op.w != 0u, n, sv_out);
+                    if (H.n_gslots != 0u) {
+                        fused_nbody_pair<N, true>(P, t, aux + op.y, op.z, op.w != 0u, n, sv_out);
+                    } else {
+                        fused_nbody_pair<N, false>(P, t, aux + op.y, op.z, op.w != 0u, n, sv_out);
+                    }
                 } else {
                     const uint4 op2 = ops[2u * k + 1u];
                     const auto self = t.row(op2.x);
@@ -657,7 +668,8 @@ __device__ __forceinline__ void coop_update_state(const program &P, const batch 
 }
 
 template <int L, int N, bool PROP>
-__global__ void __launch_bounds__(512) k_coop(program P, const std::uint32_t *blob, batch D, run_args R)
+__global__ void __launch_bounds__(512)
+    k_coop(program P, const std::uint32_t *blob, batch D, run_args R, double *gscratch)
 {
     extern __shared__ __align__(16) double smem_raw[];
     // Program tables: global -> shared, once per CTA.
@@ -677,6 +689,12 @@ __global__ void __launch_bounds__(512) k_coop(program P, const std::uint32_t *bl
                          H.n_slots);
     const std::uint32_t n_chunks = (D.n + L - 1u) / L;
     const bool owner = tid < L;
+    // The warp's slice of the overflow tape.
+    double *gtape = H.n_gslots != 0u
+                        ? gscratch
+                              + ((static_cast<std::size_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5)
+                                    * (static_cast<std::size_t>(H.n_gslots) * L)
+                        : nullptr;
 
     for (std::uint32_t chunk = claim_chunk_warp(R.counter); chunk < n_chunks; chunk = claim_chunk_warp(R.counter)) {
         const std::uint32_t lane0 = chunk * L;
@@ -695,7 +713,7 @@ __global__ void __launch_bounds__(512) k_coop(program P, const std::uint32_t *bl
                 S.running[tid] = 1;
             }
             __syncwarp();
-            coop_jet<L, N>(P, H, tab, D, S, lane0);
+            coop_jet<L, N>(P, H, tab, D, S, lane0, gtape);
             double h = 0.;
             if (owner) {
                 h = coop_determine_h(P, D, lane, mdt);
@@ -728,7 +746,7 @@ __global__ void __launch_bounds__(512) k_coop(program P, const std::uint32_t *bl
                     S.running[tid] = lp.running ? 1 : 0;
                 }
                 __syncwarp();
-                coop_jet<L, N>(P, H, tab, D, S, lane0);
+                coop_jet<L, N>(P, H, tab, D, S, lane0, gtape);
                 double h = 0.;
                 if (owner) {
                     h = coop_determine_h(P, D, lane, cur_max);

@@ -104,7 +104,7 @@ struct item {
 
 } // namespace
 
-smem_plan make_smem_plan(const hy_program &p, bool fuse, bool fuse_sv)
+smem_plan make_smem_plan(const hy_program &p, bool fuse, bool fuse_sv, bool spill_private)
 {
     smem_plan pl;
     const auto n_eq = p.n_eq, n_uvars = p.n_uvars, order = p.order;
@@ -146,6 +146,7 @@ smem_plan make_smem_plan(const hy_program &p, bool fuse, bool fuse_sv)
     // for a pair. Every u variable keeps its own row and its own recurrence (bit-identical results).
     std::vector<char> fused(n_ops, 0);
     std::vector<char> dropped(n_uvars, 0); // u variables that are never stored (recomputed inside a superinstruction)
+    std::vector<char> in_global(n_uvars, 0); // rows private to a superinstruction that live in the overflow tape
     std::vector<item> items;
     // aux entries that hold u-variable indices, to be translated into row references once slots are assigned
     std::vector<std::size_t> aux_is_u;
@@ -305,6 +306,10 @@ smem_plan make_smem_plan(const hy_program &p, bool fuse, bool fuse_sv)
             if (fu != qu) {
                 dropped[fu] = 1;
             }
+            if (spill_private) {
+                in_global[r2u] = 1;
+                in_global[qu] = 1;
+            }
             std::vector<std::uint32_t> members{du[0], du[1], du[2], r2u, qu, mu[0], mu[1], mu[2]};
             if (fu != qu) {
                 members.push_back(fu);
@@ -350,7 +355,7 @@ smem_plan make_smem_plan(const hy_program &p, bool fuse, bool fuse_sv)
     // Odd history stride: consecutive history rows then start in different shared-memory bank groups.
     const std::uint32_t hstride = (order + 1u) | 1u;
     std::vector<std::uint32_t> row(n_uvars, 0);
-    std::uint32_t next = 0;
+    std::uint32_t next = 0, gnext = 0;
     const auto alloc = [&](std::uint32_t kind, std::uint32_t n) {
         const auto r = (kind << ROW_SLOT_BITS) | next;
         next += n;
@@ -359,6 +364,10 @@ smem_plan make_smem_plan(const hy_program &p, bool fuse, bool fuse_sv)
     for (std::uint32_t i = 0; i < n_uvars; ++i) {
         if (dropped[i]) {
             row[i] = 0u;
+        } else if (in_global[i]) {
+            // Slot index in the overflow tape (only the superinstruction that owns the row knows about it).
+            row[i] = (ROW_H << ROW_SLOT_BITS) | gnext;
+            gnext += hstride;
         } else if (hist[i]) {
             row[i] = alloc(ROW_H, hstride);
         } else if (i < n_eq) {
@@ -371,6 +380,7 @@ smem_plan make_smem_plan(const hy_program &p, bool fuse, bool fuse_sv)
         throw std::overflow_error("The Taylor tape is too large");
     }
     pl.n_slots = next;
+    pl.n_gslots = gnext;
     pl.sv_rows.assign(row.begin(), row.begin() + n_eq);
 
     // ---- n-ary argument table and state-variable definitions with row references ----

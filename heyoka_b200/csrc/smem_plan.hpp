@@ -39,6 +39,10 @@ constexpr std::uint32_t HY_FOP_NBODY_PAIR_AUX = 33u;
 
 struct smem_plan {
     std::uint32_t n_slots = 0;  // doubles of shared memory per lane
+    // Doubles per lane of the overflow tape in HBM/L2: when shared memory is the limit on the number of
+    // resident warps, the rows that only a superinstruction reads (r^2 and r^alpha histories of the pair
+    // interaction) are moved out of shared memory (spill_private).
+    std::uint32_t n_gslots = 0;
     std::uint32_t n_segments = 0;
     std::uint32_t max_seg_width = 0;
     // Ops in execution order (segment by segment, grouped by opcode inside a segment); operand fields that
@@ -60,7 +64,7 @@ struct smem_plan {
     std::vector<std::uint32_t> svout, svo, sv_cover, sv_parent, sv_phase;
 };
 
-smem_plan make_smem_plan(const hy_program &, bool fuse = true, bool fuse_sv = true);
+smem_plan make_smem_plan(const hy_program &, bool fuse = true, bool fuse_sv = true, bool spill_private = false);
 
 } // namespace heyoka_b200::detail
 
