@@ -322,18 +322,13 @@ bool hy_batch::setup_coop(int L, int N, std::uint32_t threads, std::uint32_t cta
         // Two lanes per thread: the interpreter's per-item overhead is shared and the recurrences get ILP 2.
         N = (L == 0 || L >= 2) ? 2 : 1;
     }
-    // Spill the superinstructions' private history rows to the overflow tape when shared memory would
-    // otherwise allow fewer than 12 warps per SM (at the lanes-per-warp that will be used).
+    // Optional overflow tape (HEYOKA_B200_SPILL=1): the superinstructions' private history rows move from shared
+    // memory to global memory / L2, which lets 12 instead of 8 warps of the 6-body system reside on an SM.
+    // Measured slower (1.89e7 vs 2.47e7 lane-steps/s: the L2 latency lands on the serial pow recurrence), hence
+    // off by default; kept because it is what a system slightly too large for shared memory needs.
     {
         const bool have_spill = plan.n_gslots != 0u;
-        bool want_spill = have_spill;
-        if (opt_spill >= 0) {
-            want_spill = opt_spill != 0;
-        } else if (plan.n_fused != 0u && !have_spill) {
-            const int l_eff = L != 0 ? L : std::max(N, 1);
-            const auto fit = (smem_per_block_max - reserve - blob_bytes) / coop_warp_bytes(plan.n_slots, l_eff);
-            want_spill = fit < 12u;
-        }
+        const bool want_spill = opt_spill > 0;
         if (want_spill != have_spill) {
             replan(want_spill);
         }

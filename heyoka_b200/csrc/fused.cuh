@@ -23,19 +23,36 @@ constexpr std::uint32_t FOP_FIRST = 0x100u, FOP_NBODY_PAIR = 0x100u, FOP_SUM_T =
 //      history rows and m_k, n_k single-slot rows by construction, so their masks are never decoded).
 // A sum whose terms are all single-slot rows: args[off + k] is the slot of term k (pairwise summation of up to 8
 // terms, src/math/sum.cpp:250-371).
-template <int N, typename Tape>
-__device__ __forceinline__ vd<N> sum_single_slot(const Tape &t, std::uint32_t off, std::uint32_t cnt)
+template <int N, int CNT, typename Tape>
+__device__ __forceinline__ vd<N> sum_single_slot_fixed(const Tape &t, std::uint32_t off)
 {
     using Row = typename Tape::row_t;
     vd<N> v[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-        v[k] = splat<N>(0.);
-        if (k < static_cast<int>(cnt)) {
-            v[k] = Row::load(t.base + t.arg(off + k) * Row::stride);
-        }
+        v[k] = k < CNT ? Row::load(t.base + t.arg(off + k) * Row::stride) : splat<N>(0.);
     }
-    return pairwise8(v, cnt);
+    return pairwise8(v, static_cast<std::uint32_t>(CNT)); // CNT is a constant: the selects fold away
+}
+template <int N, typename Tape>
+__device__ __forceinline__ vd<N> sum_single_slot(const Tape &t, std::uint32_t off, std::uint32_t cnt)
+{
+    switch (cnt) {
+        case 2:
+            return sum_single_slot_fixed<N, 2>(t, off);
+        case 3:
+            return sum_single_slot_fixed<N, 3>(t, off);
+        case 4:
+            return sum_single_slot_fixed<N, 4>(t, off);
+        case 5:
+            return sum_single_slot_fixed<N, 5>(t, off);
+        case 6:
+            return sum_single_slot_fixed<N, 6>(t, off);
+        case 7:
+            return sum_single_slot_fixed<N, 7>(t, off);
+        default:
+            return sum_single_slot_fixed<N, 8>(t, off);
+    }
 }
 
 // sv_out(offset, value, n): propagates a value that is the derivative of state variables (see coop_jet()).
