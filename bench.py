@@ -59,6 +59,19 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0}, "fallback"
 
 
+def measured_traffic(kernel_kind, lane_steps_per_launch):
+    """DRAM bytes per launch of the dominant kernel, from the committed `ncu --set full` capture: the capture
+    (profiles/r1_traffic.json, written by profiles/summarise_ncu.py) holds dram__bytes_read.sum + dram__bytes_write.sum
+    and the lane-steps of the profiled launch; the traffic of this kernel is proportional to the lane-steps."""
+    path = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    try:
+        with open(path) as f:
+            t = json.load(f)[kernel_kind]
+        return float(t["dram_bytes"]) / float(t["lane_steps"]) * lane_steps_per_launch
+    except (OSError, KeyError, ValueError):
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -360,7 +373,7 @@ def main():
                 "parallelism": "lanes sharded across %d GPU(s), final-state all_gather" % world,
             },
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                         "traffic": None, "peak_kind": peak_kind,
+                         "traffic": measured_traffic(kinfo["tape"], lane_steps_rank), "peak_kind": peak_kind,
                          "kernel": "k_coop<L=%d,N=%d,prop>" % (kinfo["lanes_per_warp"], kinfo["lanes_per_thread"])
                          if kinfo["tape"] == "smem" else "k_hbm<prop>", "kernel_config": kinfo,
                          "kernel_ms": k_ms, "b_tape_bytes_per_lane_step": costs["b_tape"],

@@ -21,8 +21,12 @@ LIB = os.path.join(LIBDIR, "libheyoka_b200.so")
 HOST_SOURCES = ["expression.cpp", "decompose.cpp", "model.cpp", "lower.cpp", "smem_plan.cpp", "capi_host.cpp",
                 "taylor_adaptive_batch.cpp"]
 CUDA_SOURCES = ["batch.cu"]
+# The cooperative kernel is instantiated per (lanes per thread, max threads per CTA, generic ops) family, one
+# object each (built in parallel).
+COOP_FAMILIES = [(n, m, g) for n in (1, 2, 4) for m in (512, 256) for g in (1, 0)]
 
 NVCC_ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+CUDA_FLAGS = ["-lineinfo", "-fmad=false", "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 COMMON = ["-std=c++17", "-O3", "-I" + os.path.join(ROOT, "include"), "-I" + CSRC]
 
 
@@ -53,28 +57,38 @@ def build(force=False, verbose=True):
     os.makedirs(LIBDIR, exist_ok=True)
     os.makedirs(OBJDIR, exist_ok=True)
     hdrs = _all_headers()
-    objs = []
-    rebuilt = False
+    jobs = []  # (obj, deps, cmd)
     for src in HOST_SOURCES + CUDA_SOURCES:
         path = os.path.join(CSRC, src)
-        if not os.path.exists(path):
-            continue
         obj = os.path.join(OBJDIR, src + ".o")
-        objs.append(obj)
-        if force or _deps_newer(obj, [path] + hdrs):
-            if src.endswith(".cu"):
-                cmd = [nvcc] + NVCC_ARCH + COMMON + ["-lineinfo", "-fmad=false", "-Xcompiler", "-fPIC",
-                                                       "-Xptxas", "-v", "-c", path, "-o", obj]
-            else:
-                cmd = [nvcc] + COMMON + ["-Xcompiler", "-fPIC,-Wall,-Wextra", "-c", path, "-o", obj]
-            if verbose:
-                print(" ".join(cmd), flush=True)
-            res = subprocess.run(cmd, capture_output=True, text=True)
-            if verbose and res.stderr:
-                print(res.stderr, file=sys.stderr)
-            if res.returncode != 0:
-                raise RuntimeError("compilation of %s failed:\n%s\n%s" % (src, res.stdout, res.stderr))
-            rebuilt = True
+        if src.endswith(".cu"):
+            cmd = [nvcc] + NVCC_ARCH + COMMON + CUDA_FLAGS + ["-c", path, "-o", obj]
+        else:
+            cmd = [nvcc] + COMMON + ["-Xcompiler", "-fPIC,-Wall,-Wextra", "-c", path, "-o", obj]
+        jobs.append((obj, path, cmd))
+    inst = os.path.join(CSRC, "coop_inst.cu")
+    for n_lanes, maxt, gen in COOP_FAMILIES:
+        obj = os.path.join(OBJDIR, "coop_inst_n%d_%d_g%d.o" % (n_lanes, maxt, gen))
+        cmd = [nvcc] + NVCC_ARCH + COMMON + CUDA_FLAGS + ["-DHY_COOP_N=%d" % n_lanes, "-DHY_COOP_MAXT=%d" % maxt,
+                                                          "-DHY_COOP_GEN=%d" % gen, "-c", inst, "-o", obj]
+        jobs.append((obj, inst, cmd))
+    objs = [j[0] for j in jobs]
+    todo = [j for j in jobs if force or _deps_newer(j[0], [j[1]] + hdrs)]
+
+    def run(job):
+        if verbose:
+            print(" ".join(job[2]), flush=True)
+        res = subprocess.run(job[2], capture_output=True, text=True)
+        with open(job[0] + ".log", "w") as f:
+            f.write(res.stdout + res.stderr)  # ptxas -v resource usage
+        if res.returncode != 0:
+            raise RuntimeError("compilation of %s failed:\n%s\n%s" % (job[1], res.stdout, res.stderr))
+
+    if todo:
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=max(1, min(len(todo), os.cpu_count() or 1))) as ex:
+            list(ex.map(run, todo))
+    rebuilt = bool(todo)
     if rebuilt or not os.path.exists(LIB):
         cmd = [nvcc] + NVCC_ARCH + ["-shared", "-o", LIB] + objs
         if verbose:

@@ -18,8 +18,10 @@
 #include <cuda_runtime.h>
 
 #include "capi_common.hpp"
+#include "coop_variants.hpp"
 #include "device_program.cuh"
 #include "kernels.cuh"
+#include "small_kernels.cuh"
 #include "program.hpp"
 #include "smem_plan.hpp"
 
@@ -42,29 +44,30 @@ using hy::detail::translate_exception;
 namespace
 {
 
-using coop_fn = void (*)(dev::program, const std::uint32_t *, dev::batch, dev::run_args, double *);
+using hy::detail::coop_variant;
 
-struct coop_variant {
-    int L, N;
-    coop_fn step, prop;
-};
-
-#define HY_COOP(L, N)                                                                                                  \
-    coop_variant                                                                                                       \
-    {                                                                                                                  \
-        L, N, dev::k_coop<L, N, false>, dev::k_coop<L, N, true>                                                        \
-    }
-
-const coop_variant coop_variants[] = {HY_COOP(1, 1),  HY_COOP(2, 1),  HY_COOP(4, 1),  HY_COOP(8, 1),  HY_COOP(16, 1),
-                                      HY_COOP(32, 1), HY_COOP(2, 2),  HY_COOP(4, 2),  HY_COOP(8, 2),  HY_COOP(16, 2),
-                                      HY_COOP(32, 2), HY_COOP(4, 4),  HY_COOP(8, 4),  HY_COOP(16, 4), HY_COOP(32, 4)};
-#undef HY_COOP
-
-const coop_variant *find_variant(int L, int N)
+// maxt: 256 when the CTA has at most 8 warps (up to 255 registers per thread), else 512. gen: the plan contains
+// elementary ops (not only superinstructions).
+const coop_variant *find_variant(int L, int N, int maxt, bool gen)
 {
-    for (const auto &v : coop_variants) {
-        if (v.L == L && v.N == N) {
-            return &v;
+    const hy::detail::coop_family fams[] = {
+        hy::detail::coop_family_n1_512_g1(),
+        hy::detail::coop_family_n1_512_g0(),
+        hy::detail::coop_family_n1_256_g1(),
+        hy::detail::coop_family_n1_256_g0(),
+        hy::detail::coop_family_n2_512_g1(),
+        hy::detail::coop_family_n2_512_g0(),
+        hy::detail::coop_family_n2_256_g1(),
+        hy::detail::coop_family_n2_256_g0(),
+        hy::detail::coop_family_n4_512_g1(),
+        hy::detail::coop_family_n4_512_g0(),
+        hy::detail::coop_family_n4_256_g1(),
+        hy::detail::coop_family_n4_256_g0()};
+    for (const auto &f : fams) {
+        for (std::size_t i = 0; i < f.n; ++i) {
+            if (f.v[i].L == L && f.v[i].N == N && f.v[i].maxt == maxt && f.v[i].gen == gen) {
+                return f.v + i;
+            }
         }
     }
     return nullptr;
@@ -102,11 +105,17 @@ std::vector<std::uint32_t> make_plan_blob(const hy::detail::smem_plan &pl, const
     b.insert(b.end(), pl.aux.begin(), pl.aux.end());
     align(2);
     h.off_consts = static_cast<std::uint32_t>(b.size());
-    for (const double c : p.consts) {
+    const auto push_double = [&](double c) {
         std::uint32_t w[2];
         std::memcpy(w, &c, sizeof(double));
         b.push_back(w[0]);
         b.push_back(w[1]);
+    };
+    for (const double c : p.consts) {
+        push_double(c);
+    }
+    for (const double c : pl.extra_consts) {
+        push_double(c);
     }
     align(2);
     // Reciprocals 1 / k (IEEE division on the host) for the exact small-integer divisions.
@@ -358,23 +367,27 @@ bool hy_batch::setup_coop(int L, int N, std::uint32_t threads, std::uint32_t cta
             L = N;
         }
     }
-    const auto *v = find_variant(L, N);
-    if (v == nullptr) {
-        throw std::invalid_argument("Unsupported cooperative kernel configuration: " + std::to_string(L)
-                                    + " lanes per warp, " + std::to_string(N) + " lanes per thread");
-    }
     const auto warp_bytes = coop_warp_bytes(plan.n_slots, L);
     if (blob_bytes > 24u * 1024u || blob_bytes + warp_bytes + reserve > smem_per_block_max) {
         return false;
     }
     if (threads == 0u) {
-        // One CTA per SM holding as many warps as fit next to one copy of the tables (at most 16 warps;
-        // registers: 65536 / 512 threads = 128 per thread).
+        // One CTA per SM holding as many warps as fit next to one copy of the tables (at most 16 warps).
         const std::size_t W = std::min<std::size_t>((smem_per_block_max - reserve - blob_bytes) / warp_bytes, 16u);
         threads = static_cast<std::uint32_t>(32u * std::max<std::size_t>(W, 1u));
     }
     if (threads % 32u != 0u || threads == 0u || threads > 512u) {
         throw std::invalid_argument("Invalid number of threads for the cooperative kernel");
+    }
+    // Registers: 65536 / 512 threads = 128 per thread, 255 when the CTA has at most 256 threads.
+    bool gen = false;
+    for (const auto &op : plan.ops) {
+        gen = gen || op.opcode < hy::detail::HY_FOP_FIRST;
+    }
+    const auto *v = find_variant(L, N, threads <= 256u ? 256 : 512, gen);
+    if (v == nullptr) {
+        throw std::invalid_argument("Unsupported cooperative kernel configuration: " + std::to_string(L)
+                                    + " lanes per warp, " + std::to_string(N) + " lanes per thread");
     }
     const std::size_t bytes = blob_bytes + static_cast<std::size_t>(threads / 32u) * warp_bytes;
     if (bytes + reserve > smem_per_block_max) {

@@ -18,7 +18,7 @@ constexpr std::uint32_t FOP_FIRST = 0x100u, FOP_NBODY_PAIR = 0x100u, FOP_SUM_T =
 //   d_k = x_k^j - x_k^i (src/detail/sub.cpp)            r2 = sum_sq(d_0, d_1, d_2) (src/detail/sum_sq.cpp)
 //   q = pow(r2, alpha) (src/math/pow.cpp)               f = c1 q | -q | q (src/math/prod.cpp)
 //   m_k = d_k f (src/math/prod.cpp, var * var)          n_k = c2_k m_k (optional)
-// aux: [a_k, b_k, d_k] x 3, r2, q, alpha (constant index), order-0 pow algorithm, f, c1 (constant index),
+// aux: [a_k, b_k, d_k] x 3, r2, q, alpha (constant index), order-0 pow algorithm, table j (alpha + 1) (constant index), c1 (constant index),
 //      [m_k, operand order, n_k, c2_k (constant index)] x 3   (rows as packed row references; d_k, r2, q, f are
 //      history rows and m_k, n_k single-slot rows by construction, so their masks are never decoded).
 // A sum whose terms are all single-slot rows: args[off + k] is the slot of term k (pairwise summation of up to 8
@@ -126,14 +126,15 @@ __device__ __forceinline__ void fused_nbody_pair(const program &P, const Tape &t
             q = pow_eval(aux[12], R2.at(0u), alpha);
         } else {
             const double nd = static_cast<double>(n);
-            const V ap1 = alpha + 1.;
-            const V n_alpha = nd * alpha;
+            // fac_j = n alpha - j (alpha + 1): the products j (alpha + 1) come from a table (aux[13]).
+            const double n_alpha = nd * t.cst(aux[11]);
+            const double *jap1 = t.consts + aux[13];
             V acc = splat<N>(0.);
             const double *pb = R2.hptr(n), *pa = Q.hptr(0u);
 #pragma unroll 4
             for (std::uint32_t j = 0; j < n; ++j) {
-                const V fac = n_alpha - static_cast<double>(j) * ap1;
-                acc = vfma(fac, Row::load(pb) * Row::load(pa), acc);
+                const double fac = n_alpha - jap1[j];
+                acc = vfma(splat<N>(fac), Row::load(pb) * Row::load(pa), acc);
                 pb -= S;
                 pa += S;
             }
@@ -145,8 +146,9 @@ __device__ __forceinline__ void fused_nbody_pair(const program &P, const Tape &t
     // ---- m_k^[n] = sum_j A^[n-j] B^[j] with (A, B) = (d_k, f) or (f, d_k). f = c1 q (fkind 1), -q (2) or q
     // (0) is not stored: f^[j] is recomputed from q^[j] (one rounding, the same value a stored row would
     // hold), which frees a history row per pair. The f values are shared by the three products. ----
-    const double c1 = fkind == 1u ? t.cst(aux[14]) : 1.;
-    const auto f_of = [&](const V &qj) { return fkind == 1u ? c1 * qj : (fkind == 2u ? -qj : qj); };
+    // (Multiplications by 1 and -1 are exact: one code path for the three kinds.)
+    const double c1 = fkind == 1u ? t.cst(aux[14]) : (fkind == 2u ? -1. : 1.);
+    const auto f_of = [&](const V &qj) { return c1 * qj; };
     const bool f_first = aux[16] != 0u;
     V acc[3] = {splat<N>(0.), splat<N>(0.), splat<N>(0.)};
     if (!f_first) {

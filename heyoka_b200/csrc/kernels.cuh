@@ -510,7 +510,9 @@ struct sv_writer {
 };
 
 // Jet of the L lanes starting at global lane `lane0`; the state variables' coefficients go to tc.
-template <int L, int N>
+// GEN: the program contains elementary ops (false: superinstructions only; the interpreter of the elementary
+// recurrences is compiled out, which keeps the hot code small).
+template <int L, int N, bool GEN>
 __device__ __forceinline__ void coop_jet(const program &P, const coop_header &H, const std::uint32_t *tab,
                                          const batch &D, const coop_smem<L> &S, std::uint32_t lane0, double *gtape)
 {
@@ -608,9 +610,9 @@ __device__ __forceinline__ void coop_jet(const program &P, const coop_header &H,
                     const uint4 op2 = ops[2u * k + 1u];
                     const auto self = t.row(op2.x);
                     vd<N> v;
-                    if (op.x == FOP_SUM_T) {
+                    if (!GEN || op.x == FOP_SUM_T) {
                         v = sum_single_slot<N>(t, op.y, op.z);
-                    } else {
+                    } else if constexpr (GEN) {
                         v = diff_op<N>(P, t, op, self, n);
                     }
                     self.set(n, v);
@@ -627,48 +629,87 @@ __device__ __forceinline__ void coop_jet(const program &P, const coop_header &H,
     }
 }
 
-// Step-size estimate of one lane from the coefficients streamed to tc.
-__device__ __forceinline__ double coop_determine_h(const program &P, const batch &D, std::uint32_t glane,
+// Step-size estimate of the warp's lanes from the coefficients streamed to tc: the three infinity norms are
+// gathered by the whole warp (thread -> lane tid % L, state variables tid / L, tid / L + 32 / L, ...) and
+// reduced with shuffles; the owner threads (tid < L) get the step size of lane tid.
+// The sequential reference loop m = (m < |x|) ? |x| : m, started from |x_0|, yields NaN iff x_0 is NaN and
+// ignores every other NaN: that is fmax() over all the elements plus a check of the first one.
+template <int L>
+__device__ __forceinline__ double coop_determine_h(const program &P, const batch &D, std::uint32_t lane0,
                                                    double max_delta_t)
 {
+    const std::uint32_t tid = threadIdx.x & 31u, l = tid % L;
     const std::uint32_t pp1 = P.order + 1u, p = P.order;
+    const std::size_t n = D.n;
+    const std::uint32_t glane = lane0 + l < D.n ? lane0 + l : D.n - 1u;
     const double *tc = D.tc + glane;
-    double m0 = fabs(tc[0]), mp = fabs(tc[static_cast<std::size_t>(p) * D.n]),
-           mp1 = fabs(tc[static_cast<std::size_t>(p - 1u) * D.n]);
-    for (std::uint32_t i = 1; i < P.n_eq; ++i) {
-        const double *c = tc + static_cast<std::size_t>(i) * pp1 * D.n;
-        m0 = std_max(m0, fabs(c[0]));
-        mp = std_max(mp, fabs(c[static_cast<std::size_t>(p) * D.n]));
-        mp1 = std_max(mp1, fabs(c[static_cast<std::size_t>(p - 1u) * D.n]));
+    double m0 = 0., mp = 0., mp1 = 0.;
+    for (std::uint32_t sv = tid / L; sv < P.n_eq; sv += 32u / L) {
+        const double *c = tc + static_cast<std::size_t>(sv) * pp1 * n;
+        m0 = fmax(m0, fabs(c[0]));
+        mp = fmax(mp, fabs(c[static_cast<std::size_t>(p) * n]));
+        mp1 = fmax(mp1, fabs(c[static_cast<std::size_t>(p - 1u) * n]));
     }
-    return h_from_norms(P, m0, mp, mp1, max_delta_t);
+#pragma unroll
+    for (std::uint32_t off = 16u; off >= L; off >>= 1) {
+        m0 = fmax(m0, __shfl_xor_sync(0xffffffffu, m0, off));
+        mp = fmax(mp, __shfl_xor_sync(0xffffffffu, mp, off));
+        mp1 = fmax(mp1, __shfl_xor_sync(0xffffffffu, mp1, off));
+    }
+    double h = 0.;
+    if (tid < L) {
+        // (tid < L: this thread handled state variable 0 of its lane.)
+        const double f0 = fabs(tc[0]), fp = fabs(tc[static_cast<std::size_t>(p) * n]),
+                     fp1 = fabs(tc[static_cast<std::size_t>(p - 1u) * n]);
+        h = h_from_norms(P, isnan(f0) ? f0 : m0, isnan(fp) ? fp : mp, isnan(fp1) ? fp1 : mp1, max_delta_t);
+    }
+    return h;
 }
 
 // State update of the warp's lanes: item = (state variable, lane); S.h holds the step sizes, S.running
-// which lanes may be written. Returns true if this thread produced a non-finite value for lane `l_out`.
+// which lanes may be written. Sets bit l of nf_mask if this thread produced a non-finite value for lane l.
+// A thread evaluates up to three polynomials side by side (their coefficients come from L2).
 template <int L>
 __device__ __forceinline__ void coop_update_state(const program &P, const batch &D, const coop_smem<L> &S,
                                                   std::uint32_t lane0, unsigned &nf_mask)
 {
-    const std::uint32_t pp1 = P.order + 1u;
-    for (std::uint32_t it = threadIdx.x & 31u; it < P.n_eq * L; it += 32u) {
-        const std::uint32_t sv = it / L, l = it % L;
-        const std::uint32_t glane = lane0 + l;
-        if (glane < D.n && S.running[l]) {
-            const double *c = D.tc + static_cast<std::size_t>(sv) * pp1 * D.n + glane;
-            const std::size_t n = D.n;
-            const double res = eval_poly(P, [c, n](std::uint32_t o) { return c[static_cast<std::size_t>(o) * n]; },
-                                         S.h[l]);
-            D.state[static_cast<std::size_t>(sv) * D.n + glane] = res;
-            if (!isfinite(res)) {
-                nf_mask |= 1u << l;
+    constexpr int K = 3;
+    const std::uint32_t pp1 = P.order + 1u, tid = threadIdx.x & 31u;
+    const std::uint32_t l = tid % L, n_items = P.n_eq * L;
+    const std::uint32_t glane_raw = lane0 + l;
+    const bool lane_active = glane_raw < D.n && S.running[l] != 0;
+    const std::uint32_t glane = glane_raw < D.n ? glane_raw : D.n - 1u;
+    const double h = S.h[l];
+    const std::size_t n = D.n;
+    for (std::uint32_t base = tid; base < n_items; base += 32u * K) {
+        const double *c[K];
+        bool act[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const std::uint32_t it = base + 32u * static_cast<std::uint32_t>(k);
+            act[k] = it < n_items;
+            const std::uint32_t sv = act[k] ? it / L : 0u;
+            c[k] = D.tc + static_cast<std::size_t>(sv) * pp1 * n + glane;
+        }
+        double res[K];
+        eval_poly_k<K>(P, c, n, h, res);
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            if (act[k] && lane_active) {
+                const std::uint32_t sv = (base + 32u * static_cast<std::uint32_t>(k)) / L;
+                D.state[static_cast<std::size_t>(sv) * n + glane] = res[k];
+                if (!isfinite(res[k])) {
+                    nf_mask |= 1u << l;
+                }
             }
         }
     }
 }
 
-template <int L, int N, bool PROP>
-__global__ void __launch_bounds__(512)
+// MAXT: upper bound on the threads per CTA. With at most 8 resident warps (tapes of more than ~14 KB per warp)
+// the 256-thread instantiation lets the compiler use up to 255 registers per thread instead of 128.
+template <int L, int N, bool PROP, int MAXT, bool GEN>
+__global__ void __launch_bounds__(MAXT, 1)
     k_coop(program P, const std::uint32_t *blob, batch D, run_args R, double *gscratch)
 {
     extern __shared__ __align__(16) double smem_raw[];
@@ -713,10 +754,9 @@ __global__ void __launch_bounds__(512)
                 S.running[tid] = 1;
             }
             __syncwarp();
-            coop_jet<L, N>(P, H, tab, D, S, lane0, gtape);
-            double h = 0.;
+            coop_jet<L, N, GEN>(P, H, tab, D, S, lane0, gtape);
+            const double h = coop_determine_h<L>(P, D, lane0, mdt);
             if (owner) {
-                h = coop_determine_h(P, D, lane, mdt);
                 S.h[tid] = h;
             }
             __syncwarp();
@@ -746,10 +786,9 @@ __global__ void __launch_bounds__(512)
                     S.running[tid] = lp.running ? 1 : 0;
                 }
                 __syncwarp();
-                coop_jet<L, N>(P, H, tab, D, S, lane0, gtape);
-                double h = 0.;
+                coop_jet<L, N, GEN>(P, H, tab, D, S, lane0, gtape);
+                const double h = coop_determine_h<L>(P, D, lane0, cur_max);
                 if (owner) {
-                    h = coop_determine_h(P, D, lane, cur_max);
                     S.h[tid] = h;
                 }
                 __syncwarp();
@@ -765,30 +804,6 @@ __global__ void __launch_bounds__(512)
             }
         }
         __syncwarp();
-    }
-}
-
-__global__ void k_fill_outcome(long long *out, std::uint32_t n, long long value)
-{
-    const std::uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) {
-        out[i] = value;
-    }
-}
-
-// Dense output (src/taylor_01.cpp:1015-1185): Horner, or compensated summation in high-accuracy mode.
-__global__ void k_d_output(program P, std::uint32_t n, const double *tc, const double *tau, double *out)
-{
-    const std::uint32_t lane = blockIdx.x * blockDim.x + threadIdx.x;
-    if (lane >= n) {
-        return;
-    }
-    const double h = tau[lane];
-    const std::size_t nn = n;
-    for (std::uint32_t i = 0; i < P.n_eq; ++i) {
-        const double *c = tc + static_cast<std::size_t>(i) * (P.order + 1u) * n + lane;
-        out[static_cast<std::size_t>(i) * n + lane]
-            = eval_poly(P, [c, nn](std::uint32_t o) { return c[static_cast<std::size_t>(o) * nn]; }, h);
     }
 }
 

@@ -546,7 +546,7 @@ __device__ __forceinline__ double div_small_int(double x, std::uint32_t n)
 }
 // The (cold) IEEE division fallback, kept out of line: the division routine is ~40 instructions and would be
 // inlined at every call site otherwise.
-__device__ __noinline__ double div_fallback(double x, double nd)
+static __device__ __noinline__ double div_fallback(double x, double nd)
 {
     return x / nd;
 }
@@ -629,6 +629,46 @@ __device__ __forceinline__ double eval_poly(const program &P, const F &cf, doubl
         }
     }
     return res;
+}
+
+// K polynomials evaluated side by side (same operations per polynomial as eval_poly(); the K chains are
+// independent, so that the loads of their coefficients overlap). c[k] points to the order-0 coefficient,
+// consecutive orders are `stride` doubles apart.
+template <int K>
+__device__ __forceinline__ void eval_poly_k(const program &P, const double *const (&c)[K], std::size_t stride, double h,
+                                            double (&res)[K])
+{
+    const std::uint32_t p = P.order;
+    if (!P.high_accuracy) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            res[k] = c[k][static_cast<std::size_t>(p) * stride];
+        }
+        for (std::uint32_t o = 1; o <= p; ++o) {
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                res[k] = ::fma(res[k], h, c[k][static_cast<std::size_t>(p - o) * stride]);
+            }
+        }
+    } else {
+        double comp[K], cur_h = h;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            res[k] = c[k][0];
+            comp[k] = 0.;
+        }
+        for (std::uint32_t o = 1; o <= p; ++o) {
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const double tmp = __dmul_rn(c[k][static_cast<std::size_t>(o) * stride], cur_h);
+                const double y = __dsub_rn(tmp, comp[k]);
+                const double tt = __dadd_rn(res[k], y);
+                comp[k] = __dsub_rn(__dsub_rn(tt, res[k]), y);
+                res[k] = tt;
+            }
+            cur_h = __dmul_rn(cur_h, h);
+        }
+    }
 }
 
 // Double-length time arithmetic (include/heyoka/detail/dfloat.hpp:104-169).

@@ -2,9 +2,11 @@
 #include "smem_plan.hpp"
 
 #include <algorithm>
+#include <cstring>
 #include <map>
 #include <numeric>
 #include <stdexcept>
+#include <utility>
 
 namespace heyoka_b200::detail
 {
@@ -165,6 +167,7 @@ smem_plan make_smem_plan(const hy_program &p, bool fuse, bool fuse_sv, bool spil
         }
         return true;
     };
+    std::vector<std::pair<double, std::uint32_t>> pow_tabs; // (alpha, index of its table in the constant pool)
     if (fuse) {
         for (std::uint32_t qi = 0; qi < n_ops; ++qi) {
             const auto &qop = p.ops[qi];
@@ -286,7 +289,28 @@ smem_plan make_smem_plan(const hy_program &p, bool fuse, bool fuse_sv, bool spil
             push_u(qu);
             pl.aux.push_back(qop.b); // exponent (constant index)
             pl.aux.push_back(qop.c); // order-0 evaluation algorithm
-            pl.aux.push_back(0u);    // (f is never stored: f^[j] = c1 q^[j] / -q^[j] is recomputed on the fly)
+            // (f is never stored: f^[j] = c1 q^[j] / -q^[j] is recomputed on the fly.) Index in the constant pool
+            // of the table j * (alpha + 1) of the pow recurrence (shared by the pairs with the same exponent).
+            {
+                const double alpha = p.consts[qop.b];
+                std::uint32_t tab_idx = 0;
+                bool found = false;
+                for (const auto &[a_bits, idx] : pow_tabs) {
+                    if (std::memcmp(&a_bits, &alpha, sizeof(double)) == 0) {
+                        tab_idx = idx;
+                        found = true;
+                    }
+                }
+                if (!found) {
+                    tab_idx = static_cast<std::uint32_t>(p.consts.size() + pl.extra_consts.size());
+                    const double ap1 = alpha + 1.;
+                    for (std::uint32_t j = 0; j <= order; ++j) {
+                        pl.extra_consts.push_back(static_cast<double>(j) * ap1);
+                    }
+                    pow_tabs.emplace_back(alpha, tab_idx);
+                }
+                pl.aux.push_back(tab_idx);
+            }
             pl.aux.push_back(c1);
             for (std::uint32_t k = 0; k < 3u; ++k) {
                 const auto &mop = op_of(mu[k]);
@@ -361,7 +385,7 @@ smem_plan make_smem_plan(const hy_program &p, bool fuse, bool fuse_sv, bool spil
         next += n;
         return r;
     };
-    for (std::uint32_t i = 0; i < n_uvars; ++i) {
+    const auto assign = [&](std::uint32_t i) {
         if (dropped[i]) {
             row[i] = 0u;
         } else if (in_global[i]) {
@@ -374,6 +398,48 @@ smem_plan make_smem_plan(const hy_program &p, bool fuse, bool fuse_sv, bool spil
             row[i] = alloc(ROW_SV, 2u);
         } else {
             row[i] = alloc(ROW_T, 1u);
+        }
+    };
+    // The threads of a warp run consecutive items of a level, and at any instant they all touch the row that
+    // plays the same role in their own item: rows are laid out so that those rows are hstride (odd) or 1 slots
+    // apart, i.e. in different bank groups for 8 consecutive threads (a slot is 16 bytes with 2 lanes per warp).
+    //   state variables: one pad slot per group of 6 (x, y, z, vx, vy, vz of one particle), so that the same
+    //                    coordinate of different particles is an odd number of slots apart;
+    //   superinstructions: role-major (all the dx rows, then all the dy rows, ...), in execution order;
+    //   elementary ops: program order (= execution order inside a level for ops of the same kind).
+    for (std::uint32_t i = 0; i < n_eq; ++i) {
+        assign(i);
+        if (n_eq % 6u == 0u && i % 6u == 5u) {
+            next += 1u;
+        }
+    }
+    std::sort(items.begin(), items.end(), [](const item &x, const item &y) { return x.first_op < y.first_op; });
+    {
+        std::vector<std::uint8_t> done(items.size(), 0);
+        for (std::size_t k = 0; k < items.size(); ++k) {
+            if (done[k] || items[k].op.opcode < HY_FOP_FIRST) {
+                continue;
+            }
+            std::vector<std::size_t> grp;
+            for (std::size_t k2 = k; k2 < items.size(); ++k2) {
+                if (!done[k2] && items[k2].op.opcode == items[k].op.opcode
+                    && items[k2].defs.size() == items[k].defs.size()) {
+                    grp.push_back(k2);
+                    done[k2] = 1;
+                }
+            }
+            for (std::size_t r = 0; r < items[k].defs.size(); ++r) {
+                for (const auto g : grp) {
+                    assign(items[g].defs[r]);
+                }
+            }
+        }
+        for (std::size_t k = 0; k < items.size(); ++k) {
+            if (!done[k]) {
+                for (const auto d : items[k].defs) {
+                    assign(d);
+                }
+            }
         }
     }
     if (next >= (1u << ROW_SLOT_BITS)) {

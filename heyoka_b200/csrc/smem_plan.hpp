@@ -30,7 +30,7 @@ constexpr std::uint32_t ROW_SLOT_BITS = 27u;
 // Superinstructions (internal to the plan, never part of a hy_program): opcodes >= HY_FOP_FIRST.
 //   HY_FOP_NBODY_PAIR  the gravitational pair interaction of model::nbody (src/model/nbody.cpp:97-153): 3 sub,
 //                      sum_sq, pow, optional scaling, 3 products, optional 3 scalings run by ONE work item.
-//                      op.a = offset into aux (27 words, see make_smem_plan()), op.b = kind of the scaling of
+//                      op.a = offset into aux (33 words, see make_smem_plan()), op.b = kind of the scaling of
 //                      r^alpha (0 none, 1 constant, 2 negation), op.c = 1 if the products are rescaled.
 //   HY_FOP_SUM_T       a sum whose terms are all single-slot rows (argument table entries = slots).
 constexpr std::uint32_t HY_FOP_FIRST = 0x100u, HY_FOP_NBODY_PAIR = 0x100u, HY_FOP_SUM_T = 0x101u;
@@ -55,6 +55,9 @@ struct smem_plan {
     std::vector<std::uint32_t> sv_rows;     // row reference of each state variable
     std::vector<std::uint32_t> aux;         // operand tables of the superinstructions
     std::uint32_t n_fused = 0;              // number of superinstructions
+    // Constants appended to the program's pool (indices start at n_consts): per distinct exponent alpha of the
+    // pair interactions, the table j * (alpha + 1), j = 0..order, of the pow recurrence.
+    std::vector<double> extra_consts;
     // State-variable propagation fused into the producers. When u^[n] is the right-hand side of state variable
     // s, the work item that produces it also writes x_s^[n+1] = u^[n] / (n + 1) (and x_s2^[n+2] for a state
     // variable s2 whose derivative is s, e.g. positions whose derivative is a velocity): no separate pass and
