@@ -299,7 +299,7 @@ class Batch:
         check(lib.hy_batch_set_launch_config(self._h, int(block_threads), int(blocks_per_sm)))
 
     def set_kernel(self, tape="auto", lanes_per_warp=0, lanes_per_thread=0, block_threads=0, blocks_per_sm=0):
-        mode = {"auto": 0, "hbm": 1, "smem": 2}[tape]
+        mode = {"auto": 0, "hbm": 1, "smem": 2, "smem-notmem": 3}[tape]
         check(lib.hy_batch_set_kernel(self._h, mode, int(lanes_per_warp), int(lanes_per_thread), int(block_threads),
                                       int(blocks_per_sm)))
 

@@ -43,7 +43,8 @@ class hy_kernel_info(C.Structure):
     _fields_ = [("tape_mode", C.c_int32), ("lanes_per_warp", C.c_uint32), ("lanes_per_thread", C.c_uint32),
                 ("block_threads", C.c_uint32), ("blocks_per_sm", C.c_uint32), ("grid", C.c_uint32),
                 ("smem_bytes", C.c_uint64), ("tape_slots_per_lane", C.c_uint32), ("n_segments", C.c_uint32),
-                ("n_fused", C.c_uint32), ("n_sms", C.c_uint32)]
+                ("n_fused", C.c_uint32), ("n_sms", C.c_uint32), ("tmem_cols_per_warp", C.c_uint32),
+                ("reserved", C.c_uint32)]
 
 
 _dp = C.POINTER(C.c_double)

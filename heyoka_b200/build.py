@@ -21,9 +21,10 @@ LIB = os.path.join(LIBDIR, "libheyoka_b200.so")
 HOST_SOURCES = ["expression.cpp", "decompose.cpp", "model.cpp", "lower.cpp", "smem_plan.cpp", "capi_host.cpp",
                 "taylor_adaptive_batch.cpp"]
 CUDA_SOURCES = ["batch.cu"]
-# The cooperative kernel is instantiated per (lanes per thread, max threads per CTA, generic ops) family, one
+# The cooperative kernel is instantiated per (lanes per thread, max threads per CTA, mode) family, one
 # object each (built in parallel).
-COOP_FAMILIES = [(n, m, g) for n in (1, 2, 4) for m in (512, 256) for g in (1, 0)]
+COOP_FAMILIES = ([(n, m, g) for n in (1, 2, 4) for m in (512, 256) for g in (1, 0)]
+                 + [(n, m, 2) for n in (1, 2) for m in (512, 384, 256)])
 
 NVCC_ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 CUDA_FLAGS = ["-lineinfo", "-fmad=false", "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
@@ -68,9 +69,9 @@ def build(force=False, verbose=True):
         jobs.append((obj, path, cmd))
     inst = os.path.join(CSRC, "coop_inst.cu")
     for n_lanes, maxt, gen in COOP_FAMILIES:
-        obj = os.path.join(OBJDIR, "coop_inst_n%d_%d_g%d.o" % (n_lanes, maxt, gen))
+        obj = os.path.join(OBJDIR, "coop_inst_n%d_%d_m%d.o" % (n_lanes, maxt, gen))
         cmd = [nvcc] + NVCC_ARCH + COMMON + CUDA_FLAGS + ["-DHY_COOP_N=%d" % n_lanes, "-DHY_COOP_MAXT=%d" % maxt,
-                                                          "-DHY_COOP_GEN=%d" % gen, "-c", inst, "-o", obj]
+                                                          "-DHY_COOP_MODE=%d" % gen, "-c", inst, "-o", obj]
         jobs.append((obj, inst, cmd))
     objs = [j[0] for j in jobs]
     todo = [j for j in jobs if force or _deps_newer(j[0], [j[1]] + hdrs)]

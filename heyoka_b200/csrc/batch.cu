@@ -46,26 +46,32 @@ namespace
 
 using hy::detail::coop_variant;
 
-// maxt: 256 when the CTA has at most 8 warps (up to 255 registers per thread), else 512. gen: the plan contains
-// elementary ops (not only superinstructions).
-const coop_variant *find_variant(int L, int N, int maxt, bool gen)
+// maxt: upper bound on the threads per CTA the variant was compiled for (256: up to 255 registers per thread).
+// mode: 1 = the plan contains elementary ops, 0 = superinstructions only, 2 = idem with tensor memory.
+const coop_variant *find_variant(int L, int N, int maxt, int mode)
 {
     const hy::detail::coop_family fams[] = {
-        hy::detail::coop_family_n1_512_g1(),
-        hy::detail::coop_family_n1_512_g0(),
-        hy::detail::coop_family_n1_256_g1(),
-        hy::detail::coop_family_n1_256_g0(),
-        hy::detail::coop_family_n2_512_g1(),
-        hy::detail::coop_family_n2_512_g0(),
-        hy::detail::coop_family_n2_256_g1(),
-        hy::detail::coop_family_n2_256_g0(),
-        hy::detail::coop_family_n4_512_g1(),
-        hy::detail::coop_family_n4_512_g0(),
-        hy::detail::coop_family_n4_256_g1(),
-        hy::detail::coop_family_n4_256_g0()};
+        hy::detail::coop_family_n1_512_m1(),
+        hy::detail::coop_family_n1_512_m0(),
+        hy::detail::coop_family_n1_256_m1(),
+        hy::detail::coop_family_n1_256_m0(),
+        hy::detail::coop_family_n2_512_m1(),
+        hy::detail::coop_family_n2_512_m0(),
+        hy::detail::coop_family_n2_256_m1(),
+        hy::detail::coop_family_n2_256_m0(),
+        hy::detail::coop_family_n4_512_m1(),
+        hy::detail::coop_family_n4_512_m0(),
+        hy::detail::coop_family_n4_256_m1(),
+        hy::detail::coop_family_n4_256_m0(),
+        hy::detail::coop_family_n1_512_m2(),
+        hy::detail::coop_family_n1_384_m2(),
+        hy::detail::coop_family_n1_256_m2(),
+        hy::detail::coop_family_n2_512_m2(),
+        hy::detail::coop_family_n2_384_m2(),
+        hy::detail::coop_family_n2_256_m2()};
     for (const auto &f : fams) {
         for (std::size_t i = 0; i < f.n; ++i) {
-            if (f.v[i].L == L && f.v[i].N == N && f.v[i].maxt == maxt && f.v[i].gen == gen) {
+            if (f.v[i].L == L && f.v[i].N == N && f.v[i].maxt == maxt && f.v[i].mode == mode) {
                 return f.v + i;
             }
         }
@@ -91,6 +97,7 @@ std::vector<std::uint32_t> make_plan_blob(const hy::detail::smem_plan &pl, const
     h.n_eq = p.n_eq;
     h.n_slots = pl.n_slots;
     h.n_gslots = pl.n_gslots;
+    h.tmem = pl.tmem ? 1u : 0u;
     align(4);
     h.off_ops = static_cast<std::uint32_t>(b.size());
     for (std::size_t i = 0; i < pl.ops.size(); ++i) {
@@ -175,7 +182,8 @@ struct hy_batch {
     std::shared_ptr<const hy_program> prog_host; // kept for re-planning
     bool opt_fuse = true, opt_fuse_sv = true;
     int opt_spill = -1; // -1 automatic, 0 never, 1 always
-    void replan(bool spill);
+    bool opt_tmem = true, allow_tmem = true;
+    void replan(bool spill, std::uint32_t tmem_max_pairs = 0);
 
     // Resident arrays.
     double *d_state = nullptr, *d_pars = nullptr, *d_t_hi = nullptr, *d_t_lo = nullptr, *d_last_h = nullptr,
@@ -310,9 +318,9 @@ void hy_batch::setup_hbm(std::uint32_t threads, std::uint32_t blocks_per_sm)
     mode = 1;
 }
 
-void hy_batch::replan(bool spill)
+void hy_batch::replan(bool spill, std::uint32_t tmem_max_pairs)
 {
-    plan = hy::detail::make_smem_plan(*prog_host, opt_fuse, opt_fuse_sv, spill);
+    plan = hy::detail::make_smem_plan(*prog_host, opt_fuse, opt_fuse_sv, spill, tmem_max_pairs);
     const auto blob = make_plan_blob(plan, *prog_host);
     if (d_blob != nullptr) {
         HY_CUDA_CHECK(cudaFree(d_blob));
@@ -338,8 +346,8 @@ bool hy_batch::setup_coop(int L, int N, std::uint32_t threads, std::uint32_t cta
     {
         const bool have_spill = plan.n_gslots != 0u;
         const bool want_spill = opt_spill > 0;
-        if (want_spill != have_spill) {
-            replan(want_spill);
+        if (want_spill != have_spill || plan.tmem) {
+            replan(want_spill); // (the tensor-memory decision is taken again below for this L, N)
         }
     }
     if (L == 0) {
@@ -367,24 +375,65 @@ bool hy_batch::setup_coop(int L, int N, std::uint32_t threads, std::uint32_t cta
             L = N;
         }
     }
+    // Warps per CTA that fit next to one copy of the tables (at most 16).
+    const auto fit_warps = [&](std::uint32_t n_slots) -> std::size_t {
+        const auto wb = coop_warp_bytes(n_slots, L);
+        if (blob_bytes + wb + reserve > smem_per_block_max) {
+            return 0u;
+        }
+        return std::min<std::size_t>((smem_per_block_max - reserve - blob_bytes) / wb, 16u);
+    };
+    // Tensor memory (HEYOKA_B200_TMEM=0 disables): if the program consists of superinstructions only, with at
+    // most one pair interaction per thread of a warp, the r^2 and r^alpha histories that only their own thread
+    // touches can live in TMEM (one TMEM lane per thread, 512 columns shared by the warps of a quadrant)
+    // instead of shared memory. Taken when it lets more warps reside on an SM (6-body system: 12 instead of 8).
+    {
+        const std::uint32_t G = static_cast<std::uint32_t>(L / N);
+        const std::uint32_t cols_per_warp = 2u * (order + 1u) * 2u * static_cast<std::uint32_t>(N);
+        const std::size_t tm_warps = cols_per_warp <= 512u ? 4u * (512u / cols_per_warp) : 0u;
+        bool want = opt_tmem && allow_tmem && N <= 2 && G != 0u && 32u / G != 0u && tm_warps != 0u && opt_spill <= 0
+                    && find_variant(L, N, 512, 2) != nullptr;
+        if (want) {
+            const auto cur_warps = fit_warps(plan.n_slots);
+            const auto cand = hy::detail::make_smem_plan(*prog_host, opt_fuse, opt_fuse_sv, false, 32u / G);
+            want = cand.tmem && std::min(fit_warps(cand.n_slots), tm_warps) > cur_warps;
+            if (want) {
+                replan(false, 32u / G);
+            }
+        }
+        if (plan.tmem) {
+            // Level 0 must be exactly the pair interactions, at most one per thread.
+            const auto b0 = plan.seg_offsets[0], e0 = plan.seg_offsets[1];
+            bool ok = (e0 - b0) * G <= 32u;
+            for (std::size_t i = 0; i < plan.ops.size(); ++i) {
+                ok = ok && ((plan.ops[i].opcode == hy::detail::HY_FOP_NBODY_PAIR) == (i >= b0 && i < e0));
+            }
+            if (!ok) {
+                throw std::logic_error("Inconsistent tensor-memory plan");
+            }
+        }
+    }
     const auto warp_bytes = coop_warp_bytes(plan.n_slots, L);
     if (blob_bytes > 24u * 1024u || blob_bytes + warp_bytes + reserve > smem_per_block_max) {
         return false;
     }
+    const std::size_t tm_warp_limit
+        = plan.tmem ? 4u * (512u / (2u * (order + 1u) * 2u * static_cast<std::uint32_t>(N))) : 16u;
     if (threads == 0u) {
-        // One CTA per SM holding as many warps as fit next to one copy of the tables (at most 16 warps).
-        const std::size_t W = std::min<std::size_t>((smem_per_block_max - reserve - blob_bytes) / warp_bytes, 16u);
+        // One CTA per SM holding as many warps as fit (shared memory, tensor-memory columns).
+        const std::size_t W = std::min(fit_warps(plan.n_slots), tm_warp_limit);
         threads = static_cast<std::uint32_t>(32u * std::max<std::size_t>(W, 1u));
     }
-    if (threads % 32u != 0u || threads == 0u || threads > 512u) {
+    if (threads % 32u != 0u || threads == 0u || threads > 512u || threads / 32u > tm_warp_limit) {
         throw std::invalid_argument("Invalid number of threads for the cooperative kernel");
     }
-    // Registers: 65536 / 512 threads = 128 per thread, 255 when the CTA has at most 256 threads.
-    bool gen = false;
+    // Registers: 65536 / 512 threads = 128 per thread, 170 with at most 384 threads, 255 with at most 256.
+    int kmode = plan.tmem ? 2 : 0;
     for (const auto &op : plan.ops) {
-        gen = gen || op.opcode < hy::detail::HY_FOP_FIRST;
+        kmode = op.opcode < hy::detail::HY_FOP_FIRST ? 1 : kmode;
     }
-    const auto *v = find_variant(L, N, threads <= 256u ? 256 : 512, gen);
+    const int maxt = threads <= 256u ? 256 : (threads <= 384u && kmode == 2 ? 384 : 512);
+    const auto *v = find_variant(L, N, maxt, kmode);
     if (v == nullptr) {
         throw std::invalid_argument("Unsupported cooperative kernel configuration: " + std::to_string(L)
                                     + " lanes per warp, " + std::to_string(N) + " lanes per thread");
@@ -425,6 +474,10 @@ void hy_batch::configure(int want_mode, int L, int N, std::uint32_t threads, std
     if (want_mode == 1) {
         setup_hbm(threads, blocks_per_sm);
         return;
+    }
+    allow_tmem = want_mode != 3;
+    if (want_mode == 3) {
+        want_mode = 2;
     }
     if (setup_coop(L, N, threads, blocks_per_sm)) {
         return;
@@ -620,7 +673,8 @@ int hy_batch_create(const hy_program *p, uint32_t batch, int device, hy_batch **
 
         // Cooperative plan.
         // HEYOKA_B200_FUSE=0 disables the superinstructions, HEYOKA_B200_FUSE_SV=0 the fused state-variable
-        // propagation, HEYOKA_B200_SPILL=0/1 forces the overflow tape off/on (diagnostics / tests).
+        // propagation, HEYOKA_B200_SPILL=0/1 forces the overflow tape off/on, HEYOKA_B200_TMEM=0 keeps every
+        // row in shared memory (diagnostics / tests).
         if (const char *env = std::getenv("HEYOKA_B200_FUSE")) {
             b->opt_fuse = std::string{env} != "0";
         }
@@ -629,6 +683,9 @@ int hy_batch_create(const hy_program *p, uint32_t batch, int device, hy_batch **
         }
         if (const char *env = std::getenv("HEYOKA_B200_SPILL")) {
             b->opt_spill = std::string{env} != "0" ? 1 : 0;
+        }
+        if (const char *env = std::getenv("HEYOKA_B200_TMEM")) {
+            b->opt_tmem = std::string{env} != "0";
         }
         b->prog_host = std::make_shared<const hy_program>(*p);
         b->replan(false);
@@ -722,7 +779,7 @@ int hy_batch_set_kernel(hy_batch *b, int tape_mode, uint32_t lanes_per_warp, uin
         if (b == nullptr) {
             throw std::invalid_argument("Null batch");
         }
-        if (tape_mode < 0 || tape_mode > 2) {
+        if (tape_mode < 0 || tape_mode > 3) {
             throw std::invalid_argument("Invalid tape mode");
         }
         device_guard guard(b->device);
@@ -752,6 +809,9 @@ int hy_batch_get_kernel(const hy_batch *b, hy_kernel_info *out)
     out->n_segments = b->plan.n_segments;
     out->n_fused = b->plan.n_fused;
     out->n_sms = b->n_sms;
+    out->tmem_cols_per_warp
+        = b->mode == 2 && b->plan.tmem ? 2u * (b->order + 1u) * 2u * static_cast<uint32_t>(b->cv->N) : 0u;
+    out->reserved = 0u;
     return HY_OK;
 }
 

@@ -3,8 +3,8 @@
 #include "coop_variants.hpp"
 #include "kernels.cuh"
 
-#if !defined(HY_COOP_N) || !defined(HY_COOP_MAXT) || !defined(HY_COOP_GEN)
-#error "HY_COOP_N, HY_COOP_MAXT and HY_COOP_GEN must be defined"
+#if !defined(HY_COOP_N) || !defined(HY_COOP_MAXT) || !defined(HY_COOP_MODE)
+#error "HY_COOP_N, HY_COOP_MAXT and HY_COOP_MODE must be defined"
 #endif
 
 #define HY_CAT_(a, b, c, d, e, f) a##b##c##d##e##f
@@ -19,12 +19,17 @@ namespace
 #define HY_COOP(L)                                                                                                     \
     coop_variant                                                                                                       \
     {                                                                                                                  \
-        L, HY_COOP_N, HY_COOP_MAXT, HY_COOP_GEN != 0, dev::k_coop<L, HY_COOP_N, false, HY_COOP_MAXT, HY_COOP_GEN != 0>, \
-            dev::k_coop<L, HY_COOP_N, true, HY_COOP_MAXT, HY_COOP_GEN != 0>                                            \
+        L, HY_COOP_N, HY_COOP_MAXT, HY_COOP_MODE, dev::k_coop<L, HY_COOP_N, false, HY_COOP_MAXT, HY_COOP_MODE>,           \
+            dev::k_coop<L, HY_COOP_N, true, HY_COOP_MAXT, HY_COOP_MODE>                                                 \
     }
 
 const coop_variant family[] = {
-#if HY_COOP_N == 1
+#if HY_COOP_MODE == 2 && HY_COOP_N == 1
+    // Tensor-memory variants: one pair interaction per thread, hence few lane groups per warp.
+    HY_COOP(1), HY_COOP(2), HY_COOP(4)
+#elif HY_COOP_MODE == 2 && HY_COOP_N == 2
+    HY_COOP(2), HY_COOP(4)
+#elif HY_COOP_N == 1
     HY_COOP(1),  HY_COOP(2), HY_COOP(4), HY_COOP(8), HY_COOP(16), HY_COOP(32)
 #elif HY_COOP_N == 2
     HY_COOP(2), HY_COOP(4), HY_COOP(8), HY_COOP(16), HY_COOP(32)
@@ -37,7 +42,7 @@ const coop_variant family[] = {
 
 } // namespace
 
-coop_family HY_CAT(coop_family_n, HY_COOP_N, _, HY_COOP_MAXT, _g, HY_COOP_GEN)()
+coop_family HY_CAT(coop_family_n, HY_COOP_N, _, HY_COOP_MAXT, _m, HY_COOP_MODE)()
 {
     return {family, sizeof(family) / sizeof(family[0])};
 }

@@ -1,6 +1,6 @@
 // Table of the compiled instantiations of the cooperative kernel dev::k_coop<L, N, PROP, MAXT>. Each (N, MAXT)
 // family is explicitly instantiated in its own translation unit (coop_inst.cu compiled with -DHY_COOP_N=...
-// -DHY_COOP_MAXT=... -DHY_COOP_GEN=...), so that the families build in parallel.
+// -DHY_COOP_MAXT=... -DHY_COOP_MODE=...), so that the families build in parallel.
 #ifndef HEYOKA_B200_CSRC_COOP_VARIANTS_HPP
 #define HEYOKA_B200_CSRC_COOP_VARIANTS_HPP
 
@@ -21,7 +21,7 @@ using coop_fn = void (*)(dev::program, const std::uint32_t *, dev::batch, dev::r
 
 struct coop_variant {
     int L, N, maxt; // lanes per warp, lanes per thread, maximum threads per CTA
-    bool gen;       // handles elementary ops (false: superinstruction-only programs)
+    int mode;       // 1: handles elementary ops, 0: superinstruction-only programs, 2: idem + tensor memory
     coop_fn step, prop;
 };
 
@@ -30,18 +30,24 @@ struct coop_family {
     std::size_t n;
 };
 
-coop_family coop_family_n1_512_g1();
-coop_family coop_family_n1_512_g0();
-coop_family coop_family_n1_256_g1();
-coop_family coop_family_n1_256_g0();
-coop_family coop_family_n2_512_g1();
-coop_family coop_family_n2_512_g0();
-coop_family coop_family_n2_256_g1();
-coop_family coop_family_n2_256_g0();
-coop_family coop_family_n4_512_g1();
-coop_family coop_family_n4_512_g0();
-coop_family coop_family_n4_256_g1();
-coop_family coop_family_n4_256_g0();
+coop_family coop_family_n1_512_m1();
+coop_family coop_family_n1_512_m0();
+coop_family coop_family_n1_256_m1();
+coop_family coop_family_n1_256_m0();
+coop_family coop_family_n2_512_m1();
+coop_family coop_family_n2_512_m0();
+coop_family coop_family_n2_256_m1();
+coop_family coop_family_n2_256_m0();
+coop_family coop_family_n4_512_m1();
+coop_family coop_family_n4_512_m0();
+coop_family coop_family_n4_256_m1();
+coop_family coop_family_n4_256_m0();
+coop_family coop_family_n1_512_m2();
+coop_family coop_family_n1_384_m2();
+coop_family coop_family_n1_256_m2();
+coop_family coop_family_n2_512_m2();
+coop_family coop_family_n2_384_m2();
+coop_family coop_family_n2_256_m2();
 
 } // namespace heyoka_b200::detail
 

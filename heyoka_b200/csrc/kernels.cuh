@@ -337,6 +337,7 @@ struct coop_header {
     std::uint32_t off_ops, off_seg, off_args, off_aux;
     std::uint32_t off_consts, off_sv, n_slots, off_svout;
     std::uint32_t off_svphase, n_svphase, off_rcp, n_gslots;
+    std::uint32_t tmem, reserved0, reserved1, reserved2; // tmem: r^2 / r^alpha of the pair interactions in TMEM
 };
 
 template <int L, int N>
@@ -510,12 +511,16 @@ struct sv_writer {
 };
 
 // Jet of the L lanes starting at global lane `lane0`; the state variables' coefficients go to tc.
-// GEN: the program contains elementary ops (false: superinstructions only; the interpreter of the elementary
-// recurrences is compiled out, which keeps the hot code small).
-template <int L, int N, bool GEN>
+// MODE: 1 = the program contains elementary ops; 0 = superinstructions only (the interpreter of the elementary
+// recurrences is compiled out, which keeps the hot code small); 2 = superinstructions only, with the private
+// history rows of the pair interactions in tensor memory (tm_r2 = TMEM address of this warp's columns): level 0
+// then consists of at most 32 / G pair interactions, one per thread, and is run by the whole warp, converged.
+template <int L, int N, int MODE>
 __device__ __forceinline__ void coop_jet(const program &P, const coop_header &H, const std::uint32_t *tab,
-                                         const batch &D, const coop_smem<L> &S, std::uint32_t lane0, double *gtape)
+                                         const batch &D, const coop_smem<L> &S, std::uint32_t lane0, double *gtape,
+                                         std::uint32_t tm_r2)
 {
+    constexpr bool GEN = MODE == 1;
     constexpr std::uint32_t G = L / N; // lane groups per warp
     const std::uint32_t tid = threadIdx.x & 31u;
     constexpr std::uint32_t nthr = 32u;
@@ -597,6 +602,17 @@ __device__ __forceinline__ void coop_jet(const program &P, const coop_header &H,
         // The other u variables, one dependency level at a time.
         for (std::uint32_t s = 0; s < H.n_segments; ++s) {
             const std::uint32_t b = seg[s], e = seg[s + 1u];
+            if constexpr (MODE == 2) {
+                if (s == 0u) {
+                    const std::uint32_t cnt = (e - b) * G;
+                    const bool active = tid < cnt;
+                    const uint4 op = ops[2u * (b + (active ? tid : cnt - 1u) / G)];
+                    const tm::row<N> R2{tm_r2}, Q{tm_r2 + pp1 * tm::row<N>::W};
+                    fused_nbody_pair_tmem<N>(P, t, aux + op.y, op.z, op.w != 0u, n, sv_out, active, R2, Q);
+                    __syncwarp();
+                    continue;
+                }
+            }
             for (std::uint32_t it = tid; it < (e - b) * G; it += nthr) {
                 const std::uint32_t k = b + it / G;
                 const uint4 op = ops[2u * k];
@@ -708,7 +724,7 @@ __device__ __forceinline__ void coop_update_state(const program &P, const batch 
 
 // MAXT: upper bound on the threads per CTA. With at most 8 resident warps (tapes of more than ~14 KB per warp)
 // the 256-thread instantiation lets the compiler use up to 255 registers per thread instead of 128.
-template <int L, int N, bool PROP, int MAXT, bool GEN>
+template <int L, int N, bool PROP, int MAXT, int MODE>
 __global__ void __launch_bounds__(MAXT, 1)
     k_coop(program P, const std::uint32_t *blob, batch D, run_args R, double *gscratch)
 {
@@ -719,7 +735,23 @@ __global__ void __launch_bounds__(MAXT, 1)
     for (std::uint32_t i = threadIdx.x; i < n_words; i += blockDim.x) {
         tab[i] = __ldg(blob + i);
     }
+    // Tensor memory: warp 0 allocates all the columns; warp w then owns the columns [(w / 4) * cols, ...) of the
+    // 32 TMEM lanes of its quadrant w % 4, one TMEM lane per thread (tmem.cuh).
+    __shared__ std::uint32_t tm_base_smem;
+    std::uint32_t tm_r2 = 0u;
+    if constexpr (MODE == 2) {
+        if ((threadIdx.x >> 5) == 0u) {
+            tm::alloc_all(&tm_base_smem);
+        }
+        tm::fence_before_sync();
+    }
     __syncthreads();
+    if constexpr (MODE == 2) {
+        tm::fence_after_sync();
+        const std::uint32_t w = threadIdx.x >> 5;
+        const std::uint32_t cols_per_warp = 2u * (P.order + 1u) * tm::row<N>::W;
+        tm_r2 = tm_base_smem + (((w & 3u) * 32u) << 16) + (w >> 2) * cols_per_warp;
+    }
     const coop_header H = *reinterpret_cast<const coop_header *>(tab);
 
     const std::uint32_t tid = threadIdx.x & 31u;
@@ -754,7 +786,7 @@ __global__ void __launch_bounds__(MAXT, 1)
                 S.running[tid] = 1;
             }
             __syncwarp();
-            coop_jet<L, N, GEN>(P, H, tab, D, S, lane0, gtape);
+            coop_jet<L, N, MODE>(P, H, tab, D, S, lane0, gtape, tm_r2);
             const double h = coop_determine_h<L>(P, D, lane0, mdt);
             if (owner) {
                 S.h[tid] = h;
@@ -786,7 +818,7 @@ __global__ void __launch_bounds__(MAXT, 1)
                     S.running[tid] = lp.running ? 1 : 0;
                 }
                 __syncwarp();
-                coop_jet<L, N, GEN>(P, H, tab, D, S, lane0, gtape);
+                coop_jet<L, N, MODE>(P, H, tab, D, S, lane0, gtape, tm_r2);
                 const double h = coop_determine_h<L>(P, D, lane0, cur_max);
                 if (owner) {
                     S.h[tid] = h;
@@ -804,6 +836,13 @@ __global__ void __launch_bounds__(MAXT, 1)
             }
         }
         __syncwarp();
+    }
+    if constexpr (MODE == 2) {
+        tm::fence_before_sync();
+        __syncthreads();
+        if ((threadIdx.x >> 5) == 0u) {
+            tm::dealloc_all(tm_base_smem);
+        }
     }
 }
 

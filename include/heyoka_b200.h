@@ -241,7 +241,7 @@ int hy_batch_set_launch_config(hy_batch *, uint32_t block_threads, uint32_t bloc
 
 /* Kernel selection. tape_mode: 0 = automatic (shared-memory tape when the system's tape fits in an SM's shared
  * memory, else the HBM tape), 1 = force the HBM-tape kernel, 2 = force the shared-memory kernel (error if it
- * does not fit). lanes_per_warp (1..32, power of two) / lanes_per_thread (1, 2 or 4, dividing lanes_per_warp)
+ * does not fit), 3 = idem, but never keep rows in tensor memory. lanes_per_warp (1..32, power of two) / lanes_per_thread (1, 2 or 4, dividing lanes_per_warp)
  * only apply to the shared-memory kernel; 0 = automatic. block_threads = 32 x warps per block.
  * The environment variable HEYOKA_B200_TAPE=hbm|smem sets the default. */
 int hy_batch_set_kernel(hy_batch *, int tape_mode, uint32_t lanes_per_warp, uint32_t lanes_per_thread,
@@ -254,6 +254,8 @@ typedef struct hy_kernel_info {
     uint32_t n_segments;          /* dependency levels of the decomposition (cf. src/taylor_02.cpp:105-207) */
     uint32_t n_fused;             /* superinstructions found by the planner (fused N-body pair interactions) */
     uint32_t n_sms;
+    uint32_t tmem_cols_per_warp;  /* tensor-memory columns per warp (0: tensor memory unused) */
+    uint32_t reserved;
 } hy_kernel_info;
 int hy_batch_get_kernel(const hy_batch *, hy_kernel_info *out);
 

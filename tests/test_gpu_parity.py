@@ -22,7 +22,8 @@ OC = {"success": hb.taylor_outcome.success, "time_limit": hb.taylor_outcome.time
 # Every parity test runs on both tape strategies and a few cooperative-kernel shapes (see kernels.cuh).
 KERNELS = {
     "hbm": dict(tape="hbm"),
-    "smem-auto": dict(tape="smem"),
+    "smem-auto": dict(tape="smem"),  # tensor memory for the pair interactions where it applies
+    "smem-notmem": dict(tape="smem-notmem"),
     "smem-L8N2": dict(tape="smem", lanes_per_warp=8, lanes_per_thread=2),
     "smem-L2N1": dict(tape="smem", lanes_per_warp=2, lanes_per_thread=1, block_threads=64),
     "smem-L4N4": dict(tape="smem", lanes_per_warp=4, lanes_per_thread=4, block_threads=32),
@@ -293,6 +294,12 @@ def test_kernel_selection_info():
     ki = b.kernel_info()
     assert ki["tape"] == "smem" and ki["tape_slots_per_lane"] < 234 * 21 / 2
     assert ki["smem_bytes"] <= 227 * 1024
+    # 15 pair interactions, one per thread: their private histories (r^2, r^-3: 2 x 21 orders x 2 lanes x 2 words)
+    # live in tensor memory, which lets 12 warps of 2 lanes reside on an SM instead of 8.
+    assert ki["tmem_cols_per_warp"] == 168 and ki["block_threads"] == 384
+    b.set_kernel("smem-notmem")
+    ki = b.kernel_info()
+    assert ki["tmem_cols_per_warp"] == 0 and ki["block_threads"] == 256
     b.set_kernel("hbm")
     assert b.kernel_info()["tape"] == "hbm"
     big = hb.Batch(hb.Program(hb.model.nbody(32)), 32)
