@@ -47,7 +47,7 @@ namespace
 using hy::detail::coop_variant;
 
 // maxt: upper bound on the threads per CTA the variant was compiled for (256: up to 255 registers per thread).
-// mode: 1 = the plan contains elementary ops, 0 = superinstructions only, 2 = idem with tensor memory.
+// mode: 1 = the plan contains elementary ops, 0 = superinstructions only, 2 / 3 = idem with tensor memory.
 const coop_variant *find_variant(int L, int N, int maxt, int mode)
 {
     const hy::detail::coop_family fams[] = {
@@ -64,11 +64,17 @@ const coop_variant *find_variant(int L, int N, int maxt, int mode)
         hy::detail::coop_family_n4_256_m1(),
         hy::detail::coop_family_n4_256_m0(),
         hy::detail::coop_family_n1_512_m2(),
+        hy::detail::coop_family_n1_512_m3(),
         hy::detail::coop_family_n1_384_m2(),
+        hy::detail::coop_family_n1_384_m3(),
         hy::detail::coop_family_n1_256_m2(),
+        hy::detail::coop_family_n1_256_m3(),
         hy::detail::coop_family_n2_512_m2(),
+        hy::detail::coop_family_n2_512_m3(),
         hy::detail::coop_family_n2_384_m2(),
-        hy::detail::coop_family_n2_256_m2()};
+        hy::detail::coop_family_n2_384_m3(),
+        hy::detail::coop_family_n2_256_m2(),
+        hy::detail::coop_family_n2_256_m3()};
     for (const auto &f : fams) {
         for (std::size_t i = 0; i < f.n; ++i) {
             if (f.v[i].L == L && f.v[i].N == N && f.v[i].maxt == maxt && f.v[i].mode == mode) {
@@ -97,7 +103,7 @@ std::vector<std::uint32_t> make_plan_blob(const hy::detail::smem_plan &pl, const
     h.n_eq = p.n_eq;
     h.n_slots = pl.n_slots;
     h.n_gslots = pl.n_gslots;
-    h.tmem = pl.tmem ? 1u : 0u;
+    h.tmem = pl.tmem;
     align(4);
     h.off_ops = static_cast<std::uint32_t>(b.size());
     for (std::size_t i = 0; i < pl.ops.size(); ++i) {
@@ -183,7 +189,8 @@ struct hy_batch {
     bool opt_fuse = true, opt_fuse_sv = true;
     int opt_spill = -1; // -1 automatic, 0 never, 1 always
     bool opt_tmem = true, allow_tmem = true;
-    void replan(bool spill, std::uint32_t tmem_max_pairs = 0);
+    std::uint32_t opt_tmem_rows = 0; // 0: automatic, 2 / 3: forced (HEYOKA_B200_TMEM_ROWS)
+    void replan(bool spill, std::uint32_t tmem_max_pairs = 0, std::uint32_t tmem_rows = 2);
 
     // Resident arrays.
     double *d_state = nullptr, *d_pars = nullptr, *d_t_hi = nullptr, *d_t_lo = nullptr, *d_last_h = nullptr,
@@ -318,9 +325,9 @@ void hy_batch::setup_hbm(std::uint32_t threads, std::uint32_t blocks_per_sm)
     mode = 1;
 }
 
-void hy_batch::replan(bool spill, std::uint32_t tmem_max_pairs)
+void hy_batch::replan(bool spill, std::uint32_t tmem_max_pairs, std::uint32_t tmem_rows)
 {
-    plan = hy::detail::make_smem_plan(*prog_host, opt_fuse, opt_fuse_sv, spill, tmem_max_pairs);
+    plan = hy::detail::make_smem_plan(*prog_host, opt_fuse, opt_fuse_sv, spill, tmem_max_pairs, tmem_rows);
     const auto blob = make_plan_blob(plan, *prog_host);
     if (d_blob != nullptr) {
         HY_CUDA_CHECK(cudaFree(d_blob));
@@ -335,6 +342,7 @@ void hy_batch::replan(bool spill, std::uint32_t tmem_max_pairs)
 bool hy_batch::setup_coop(int L, int N, std::uint32_t threads, std::uint32_t ctas_per_sm)
 {
     const std::size_t reserve = 1024u; // per-block reservation of the driver
+    const bool auto_shape = N == 0 && L == 0;
     if (N == 0) {
         // Two lanes per thread: the interpreter's per-item overhead is shared and the recurrences get ILP 2.
         N = (L == 0 || L >= 2) ? 2 : 1;
@@ -376,35 +384,65 @@ bool hy_batch::setup_coop(int L, int N, std::uint32_t threads, std::uint32_t cta
         }
     }
     // Warps per CTA that fit next to one copy of the tables (at most 16).
-    const auto fit_warps = [&](std::uint32_t n_slots) -> std::size_t {
-        const auto wb = coop_warp_bytes(n_slots, L);
+    const auto fit_warps = [&](std::uint32_t n_slots, int lanes) -> std::size_t {
+        const auto wb = coop_warp_bytes(n_slots, lanes);
         if (blob_bytes + wb + reserve > smem_per_block_max) {
             return 0u;
         }
         return std::min<std::size_t>((smem_per_block_max - reserve - blob_bytes) / wb, 16u);
     };
     // Tensor memory (HEYOKA_B200_TMEM=0 disables): if the program consists of superinstructions only, with at
-    // most one pair interaction per thread of a warp, the r^2 and r^alpha histories that only their own thread
-    // touches can live in TMEM (one TMEM lane per thread, 512 columns shared by the warps of a quadrant)
-    // instead of shared memory. Taken when it lets more warps reside on an SM (6-body system: 12 instead of 8).
-    {
-        const std::uint32_t G = static_cast<std::uint32_t>(L / N);
-        const std::uint32_t cols_per_warp = 2u * (order + 1u) * 2u * static_cast<std::uint32_t>(N);
-        const std::size_t tm_warps = cols_per_warp <= 512u ? 4u * (512u / cols_per_warp) : 0u;
-        bool want = opt_tmem && allow_tmem && N <= 2 && G != 0u && 32u / G != 0u && tm_warps != 0u && opt_spill <= 0
-                    && find_variant(L, N, 512, 2) != nullptr;
-        if (want) {
-            const auto cur_warps = fit_warps(plan.n_slots);
-            const auto cand = hy::detail::make_smem_plan(*prog_host, opt_fuse, opt_fuse_sv, false, 32u / G);
-            want = cand.tmem && std::min(fit_warps(cand.n_slots), tm_warps) > cur_warps;
-            if (want) {
-                replan(false, 32u / G);
+    // most one pair interaction per thread of a warp, the history rows that only their own thread touches (r^2,
+    // r^alpha, optionally one of the coordinate differences) can live in TMEM (one TMEM lane per thread, 512
+    // columns shared by the warps of a quadrant) instead of shared memory. Taken when it lets more warps reside
+    // on an SM. 6-body system, order 20: 8 warps of 2 lanes without TMEM; 12 with two rows of 2 lanes per thread
+    // in TMEM; 16 with three rows of 1 lane per thread (2 lanes per warp, 30 busy threads in the pair level).
+    const auto tm_warps_of = [&](int lanes_per_thread, std::uint32_t rows) -> std::size_t {
+        const std::uint32_t cols = rows * (order + 1u) * 2u * static_cast<std::uint32_t>(lanes_per_thread);
+        return cols <= 512u ? 4u * (512u / cols) : 0u;
+    };
+    struct tm_choice {
+        std::uint32_t rows = 0;
+        std::size_t warps = 0;
+    };
+    const auto best_tmem = [&](int lanes, int lanes_per_thread) {
+        tm_choice best;
+        const std::uint32_t G = static_cast<std::uint32_t>(lanes / lanes_per_thread);
+        if (!(opt_tmem && allow_tmem && lanes_per_thread <= 2 && G != 0u && G <= 32u && opt_spill <= 0
+              && find_variant(lanes, lanes_per_thread, 512, 2) != nullptr)) {
+            return best;
+        }
+        for (const std::uint32_t rows : {2u, 3u}) {
+            if (opt_tmem_rows != 0u && rows != opt_tmem_rows) {
+                continue;
+            }
+            const auto cand = hy::detail::make_smem_plan(*prog_host, opt_fuse, opt_fuse_sv, false, 32u / G, rows);
+            if (cand.tmem != rows) {
+                continue;
+            }
+            const auto w = std::min(fit_warps(cand.n_slots, lanes), tm_warps_of(lanes_per_thread, rows));
+            if (w > best.warps) {
+                best = tm_choice{rows, w};
             }
         }
-        if (plan.tmem) {
+        return best;
+    };
+    {
+        tm_choice pick = best_tmem(L, N);
+        if (auto_shape) {
+            // The tensor-memory shape of choice: 2 lanes per warp, 1 lane per thread.
+            const auto alt = best_tmem(2, 1);
+            if (alt.warps * 2u > std::max(pick.warps, fit_warps(plan.n_slots, L)) * static_cast<std::size_t>(L)) {
+                pick = alt;
+                L = 2;
+                N = 1;
+            }
+        }
+        if (pick.rows != 0u && pick.warps > fit_warps(plan.n_slots, L)) {
+            replan(false, 32u / static_cast<std::uint32_t>(L / N), pick.rows);
             // Level 0 must be exactly the pair interactions, at most one per thread.
             const auto b0 = plan.seg_offsets[0], e0 = plan.seg_offsets[1];
-            bool ok = (e0 - b0) * G <= 32u;
+            bool ok = plan.tmem == pick.rows && (e0 - b0) * static_cast<std::uint32_t>(L / N) <= 32u;
             for (std::size_t i = 0; i < plan.ops.size(); ++i) {
                 ok = ok && ((plan.ops[i].opcode == hy::detail::HY_FOP_NBODY_PAIR) == (i >= b0 && i < e0));
             }
@@ -417,22 +455,21 @@ bool hy_batch::setup_coop(int L, int N, std::uint32_t threads, std::uint32_t cta
     if (blob_bytes > 24u * 1024u || blob_bytes + warp_bytes + reserve > smem_per_block_max) {
         return false;
     }
-    const std::size_t tm_warp_limit
-        = plan.tmem ? 4u * (512u / (2u * (order + 1u) * 2u * static_cast<std::uint32_t>(N))) : 16u;
+    const std::size_t tm_warp_limit = plan.tmem != 0u ? tm_warps_of(N, plan.tmem) : 16u;
     if (threads == 0u) {
         // One CTA per SM holding as many warps as fit (shared memory, tensor-memory columns).
-        const std::size_t W = std::min(fit_warps(plan.n_slots), tm_warp_limit);
+        const std::size_t W = std::min(fit_warps(plan.n_slots, L), tm_warp_limit);
         threads = static_cast<std::uint32_t>(32u * std::max<std::size_t>(W, 1u));
     }
     if (threads % 32u != 0u || threads == 0u || threads > 512u || threads / 32u > tm_warp_limit) {
         throw std::invalid_argument("Invalid number of threads for the cooperative kernel");
     }
     // Registers: 65536 / 512 threads = 128 per thread, 170 with at most 384 threads, 255 with at most 256.
-    int kmode = plan.tmem ? 2 : 0;
+    int kmode = static_cast<int>(plan.tmem); // 0, 2 or 3
     for (const auto &op : plan.ops) {
         kmode = op.opcode < hy::detail::HY_FOP_FIRST ? 1 : kmode;
     }
-    const int maxt = threads <= 256u ? 256 : (threads <= 384u && kmode == 2 ? 384 : 512);
+    const int maxt = threads <= 256u ? 256 : (threads <= 384u && kmode >= 2 ? 384 : 512);
     const auto *v = find_variant(L, N, maxt, kmode);
     if (v == nullptr) {
         throw std::invalid_argument("Unsupported cooperative kernel configuration: " + std::to_string(L)
@@ -687,6 +724,9 @@ int hy_batch_create(const hy_program *p, uint32_t batch, int device, hy_batch **
         if (const char *env = std::getenv("HEYOKA_B200_TMEM")) {
             b->opt_tmem = std::string{env} != "0";
         }
+        if (const char *env = std::getenv("HEYOKA_B200_TMEM_ROWS")) {
+            b->opt_tmem_rows = std::string{env} == "3" ? 3u : (std::string{env} == "2" ? 2u : 0u);
+        }
         b->prog_host = std::make_shared<const hy_program>(*p);
         b->replan(false);
 
@@ -810,7 +850,7 @@ int hy_batch_get_kernel(const hy_batch *b, hy_kernel_info *out)
     out->n_fused = b->plan.n_fused;
     out->n_sms = b->n_sms;
     out->tmem_cols_per_warp
-        = b->mode == 2 && b->plan.tmem ? 2u * (b->order + 1u) * 2u * static_cast<uint32_t>(b->cv->N) : 0u;
+        = b->mode == 2 && b->plan.tmem != 0u ? b->plan.tmem * (b->order + 1u) * 2u * static_cast<uint32_t>(b->cv->N) : 0u;
     out->reserved = 0u;
     return HY_OK;
 }

@@ -24,10 +24,10 @@ namespace
     }
 
 const coop_variant family[] = {
-#if HY_COOP_MODE == 2 && HY_COOP_N == 1
+#if HY_COOP_MODE >= 2 && HY_COOP_N == 1
     // Tensor-memory variants: one pair interaction per thread, hence few lane groups per warp.
     HY_COOP(1), HY_COOP(2), HY_COOP(4)
-#elif HY_COOP_MODE == 2 && HY_COOP_N == 2
+#elif HY_COOP_MODE >= 2 && HY_COOP_N == 2
     HY_COOP(2), HY_COOP(4)
 #elif HY_COOP_N == 1
     HY_COOP(1),  HY_COOP(2), HY_COOP(4), HY_COOP(8), HY_COOP(16), HY_COOP(32)

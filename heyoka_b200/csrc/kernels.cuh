@@ -337,7 +337,7 @@ struct coop_header {
     std::uint32_t off_ops, off_seg, off_args, off_aux;
     std::uint32_t off_consts, off_sv, n_slots, off_svout;
     std::uint32_t off_svphase, n_svphase, off_rcp, n_gslots;
-    std::uint32_t tmem, reserved0, reserved1, reserved2; // tmem: r^2 / r^alpha of the pair interactions in TMEM
+    std::uint32_t tmem, reserved0, reserved1, reserved2; // tmem: rows per pair interaction kept in TMEM (0, 2, 3)
 };
 
 template <int L, int N>
@@ -512,9 +512,9 @@ struct sv_writer {
 
 // Jet of the L lanes starting at global lane `lane0`; the state variables' coefficients go to tc.
 // MODE: 1 = the program contains elementary ops; 0 = superinstructions only (the interpreter of the elementary
-// recurrences is compiled out, which keeps the hot code small); 2 = superinstructions only, with the private
-// history rows of the pair interactions in tensor memory (tm_r2 = TMEM address of this warp's columns): level 0
-// then consists of at most 32 / G pair interactions, one per thread, and is run by the whole warp, converged.
+// recurrences is compiled out, which keeps the hot code small); 2 / 3 = superinstructions only, with two / three
+// private history rows of the pair interactions in tensor memory (tm_r2 = TMEM address of this warp's columns):
+// level 0 then consists of at most 32 / G pair interactions, one per thread, run by the whole warp, converged.
 template <int L, int N, int MODE>
 __device__ __forceinline__ void coop_jet(const program &P, const coop_header &H, const std::uint32_t *tab,
                                          const batch &D, const coop_smem<L> &S, std::uint32_t lane0, double *gtape,
@@ -602,13 +602,12 @@ __device__ __forceinline__ void coop_jet(const program &P, const coop_header &H,
         // The other u variables, one dependency level at a time.
         for (std::uint32_t s = 0; s < H.n_segments; ++s) {
             const std::uint32_t b = seg[s], e = seg[s + 1u];
-            if constexpr (MODE == 2) {
+            if constexpr (MODE >= 2) {
                 if (s == 0u) {
                     const std::uint32_t cnt = (e - b) * G;
                     const bool active = tid < cnt;
                     const uint4 op = ops[2u * (b + (active ? tid : cnt - 1u) / G)];
-                    const tm::row<N> R2{tm_r2}, Q{tm_r2 + pp1 * tm::row<N>::W};
-                    fused_nbody_pair_tmem<N>(P, t, aux + op.y, op.z, op.w != 0u, n, sv_out, active, R2, Q);
+                    fused_nbody_pair_tmem<N, MODE - 2>(P, t, aux + op.y, op.z, op.w != 0u, n, sv_out, active, tm_r2);
                     __syncwarp();
                     continue;
                 }
@@ -739,17 +738,17 @@ __global__ void __launch_bounds__(MAXT, 1)
     // 32 TMEM lanes of its quadrant w % 4, one TMEM lane per thread (tmem.cuh).
     __shared__ std::uint32_t tm_base_smem;
     std::uint32_t tm_r2 = 0u;
-    if constexpr (MODE == 2) {
+    if constexpr (MODE >= 2) {
         if ((threadIdx.x >> 5) == 0u) {
             tm::alloc_all(&tm_base_smem);
         }
         tm::fence_before_sync();
     }
     __syncthreads();
-    if constexpr (MODE == 2) {
+    if constexpr (MODE >= 2) {
         tm::fence_after_sync();
         const std::uint32_t w = threadIdx.x >> 5;
-        const std::uint32_t cols_per_warp = 2u * (P.order + 1u) * tm::row<N>::W;
+        const std::uint32_t cols_per_warp = static_cast<std::uint32_t>(MODE) * (P.order + 1u) * tm::row<N>::W;
         tm_r2 = tm_base_smem + (((w & 3u) * 32u) << 16) + (w >> 2) * cols_per_warp;
     }
     const coop_header H = *reinterpret_cast<const coop_header *>(tab);
@@ -837,7 +836,7 @@ __global__ void __launch_bounds__(MAXT, 1)
         }
         __syncwarp();
     }
-    if constexpr (MODE == 2) {
+    if constexpr (MODE >= 2) {
         tm::fence_before_sync();
         __syncthreads();
         if ((threadIdx.x >> 5) == 0u) {

@@ -107,7 +107,7 @@ struct item {
 } // namespace
 
 smem_plan make_smem_plan(const hy_program &p, bool fuse, bool fuse_sv, bool spill_private,
-                         std::uint32_t tmem_max_pairs)
+                         std::uint32_t tmem_max_pairs, std::uint32_t tmem_rows)
 {
     smem_plan pl;
     const auto n_eq = p.n_eq, n_uvars = p.n_uvars, order = p.order;
@@ -385,12 +385,17 @@ smem_plan make_smem_plan(const hy_program &p, bool fuse, bool fuse_sv, bool spil
             // (Sums of single-slot rows become superinstructions further down: checked again at the end.)
             only_fused = only_fused && (it.op.opcode >= HY_FOP_FIRST || it.op.opcode == HY_OP_SUM);
         }
-        pl.tmem = tmem_max_pairs != 0u && !spill_private && only_fused && n_pairs != 0u && n_pairs <= tmem_max_pairs;
-        if (pl.tmem) {
+        const bool use_tmem
+            = tmem_max_pairs != 0u && !spill_private && only_fused && n_pairs != 0u && n_pairs <= tmem_max_pairs;
+        pl.tmem = use_tmem ? (tmem_rows >= 3u ? 3u : 2u) : 0u;
+        if (use_tmem) {
             for (const auto &it : items) {
                 if (it.op.opcode == HY_FOP_NBODY_PAIR) {
                     dropped[it.defs[3]] = 1; // r^2
                     dropped[it.defs[4]] = 1; // r^alpha
+                    if (pl.tmem == 3u) {
+                        dropped[it.defs[2]] = 1; // d_2
+                    }
                 }
             }
         }
@@ -689,11 +694,11 @@ smem_plan make_smem_plan(const hy_program &p, bool fuse, bool fuse_sv, bool spil
         pl.seg_offsets.push_back(static_cast<std::uint32_t>(pl.ops.size()));
     }
 
-    if (pl.tmem) {
+    if (pl.tmem != 0u) {
         for (const auto &op : pl.ops) {
             if (op.opcode < HY_FOP_FIRST) {
                 // An elementary op survived: the tensor-memory kernel does not interpret those.
-                return make_smem_plan(p, fuse, fuse_sv, spill_private, 0u);
+                return make_smem_plan(p, fuse, fuse_sv, spill_private, 0u, 2u);
             }
         }
     }

@@ -26,6 +26,7 @@ KERNELS = {
     "smem-notmem": dict(tape="smem-notmem"),
     "smem-L8N2": dict(tape="smem", lanes_per_warp=8, lanes_per_thread=2),
     "smem-L2N1": dict(tape="smem", lanes_per_warp=2, lanes_per_thread=1, block_threads=64),
+    "smem-L2N2": dict(tape="smem", lanes_per_warp=2, lanes_per_thread=2),  # two rows per pair in tensor memory
     "smem-L4N4": dict(tape="smem", lanes_per_warp=4, lanes_per_thread=4, block_threads=32),
 }
 
@@ -294,8 +295,11 @@ def test_kernel_selection_info():
     ki = b.kernel_info()
     assert ki["tape"] == "smem" and ki["tape_slots_per_lane"] < 234 * 21 / 2
     assert ki["smem_bytes"] <= 227 * 1024
-    # 15 pair interactions, one per thread: their private histories (r^2, r^-3: 2 x 21 orders x 2 lanes x 2 words)
-    # live in tensor memory, which lets 12 warps of 2 lanes reside on an SM instead of 8.
+    # 15 pair interactions x 2 lanes, one per thread: their private histories (r^2, r^-3, dz: 3 rows x 21 orders x
+    # 2 words) live in tensor memory, which lets 16 warps of 2 lanes reside on an SM instead of 8.
+    assert ki["tmem_cols_per_warp"] == 126 and ki["block_threads"] == 512 and ki["lanes_per_thread"] == 1
+    b.set_kernel("smem", lanes_per_warp=2, lanes_per_thread=2)
+    ki = b.kernel_info()
     assert ki["tmem_cols_per_warp"] == 168 and ki["block_threads"] == 384
     b.set_kernel("smem-notmem")
     ki = b.kernel_info()
