@@ -283,7 +283,6 @@ def main():
     for _ in range(args.warmup):
         device_step(False)
     sync_all()
-    lane_steps_rank = int(t_nsteps.sum().item())
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -297,6 +296,7 @@ def main():
     ev1.record(stream)
     sync_all()
     elapsed_ms = ev0.elapsed_time(ev1)
+    lane_steps_rank = int(t_nsteps.sum().item())  # of one bench step (every step repeats the same work)
     launches = b.launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
 
