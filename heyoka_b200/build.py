@@ -58,6 +58,9 @@ def build(force=False, verbose=True):
     os.makedirs(LIBDIR, exist_ok=True)
     os.makedirs(OBJDIR, exist_ok=True)
     hdrs = _all_headers()
+    srcs = [os.path.join(CSRC, f) for f in HOST_SOURCES + CUDA_SOURCES + ["coop_inst.cu"]]
+    if not force and not _deps_newer(LIB, srcs + hdrs + [os.path.abspath(__file__)]):
+        return LIB  # up to date (the objects under build/ do not travel to the GPU box)
     jobs = []  # (obj, deps, cmd)
     for src in HOST_SOURCES + CUDA_SOURCES:
         path = os.path.join(CSRC, src)
