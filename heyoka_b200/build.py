@@ -59,7 +59,7 @@ def build(force=False, verbose=True):
     os.makedirs(OBJDIR, exist_ok=True)
     hdrs = _all_headers()
     srcs = [os.path.join(CSRC, f) for f in HOST_SOURCES + CUDA_SOURCES + ["coop_inst.cu"]]
-    if not force and not _deps_newer(LIB, srcs + hdrs + [os.path.abspath(__file__)]):
+    if not force and not _deps_newer(LIB, srcs + hdrs):
         return LIB  # up to date (the objects under build/ do not travel to the GPU box)
     jobs = []  # (obj, deps, cmd)
     for src in HOST_SOURCES + CUDA_SOURCES:
