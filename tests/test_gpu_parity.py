@@ -310,3 +310,24 @@ def test_kernel_selection_info():
     assert big.kernel_info()["tape"] == "hbm"
     with pytest.raises(ValueError, match="does not fit in shared memory"):
         big.set_kernel("smem")
+
+
+def _closed_form_cases():
+    from closed_form_cases import CASES
+    from common import golden
+    g = golden("closed_form_jets.json")
+    return list(zip(CASES, g["cases"]))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case,gold", _closed_form_cases(), ids=lambda v: v[0] if isinstance(v, tuple) else "")
+def test_closed_form_jets_gpu(case, gold, kernel):
+    """The reference's closed-form jet blocks (test/taylor_*.cpp, see tests/closed_form_cases.py) on the GPU:
+    one step with write_tc, jets against the symbolic closed forms to the reference's tolerance."""
+    from closed_form_cases import BATCH, EPS_MUL, ORDER, TOL, hb_system
+    from test_oracle_golden import approximately
+    ta = hb.taylor_adaptive_batch(hb_system(hb, case), np.array(gold["state"], dtype=float).reshape(2, BATCH), BATCH,
+                                  time=gold["time"] if gold["time"] else 0.0, tol=TOL, kernel=kernel)
+    assert ta.get_order() == ORDER
+    ta.step(write_tc=True)
+    assert approximately(ta.tc, gold["tc"], EPS_MUL.get(case[0], 100.0)), (case[0], ta.tc, gold["tc"])

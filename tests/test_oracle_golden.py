@@ -3,6 +3,7 @@
 Fixtures:
   1. doc/tut_batch_mode.rst printed output (tests/golden/tut_batch_mode.json)
   2. README.md scalar pendulum (tests/golden/readme_pendulum.json)
+  3. closed-form jets of test/taylor_*.cpp (tests/closed_form_cases.py, tests/golden/closed_form_jets.json)
   4. test/timestep_check.cpp:33-86 (step-size formula recomputed from the Taylor coefficients)
   5. test/taylor_adaptive_batch.cpp:586-598 (exact step counts under max_delta_t, exact final times)
 All three summation modes of the oracle must satisfy them, like the reference sweeps compact_mode/opt_level.
@@ -141,3 +142,34 @@ def test_vector_width_port_matches_scalar():
     assert np.array_equal(a.n_steps, b.n_steps)
     assert np.max(np.abs(a.state - b.state) / np.maximum(np.abs(a.state), 1e-3)) < 1e-13
     assert np.all(b.t_hi == 20.)
+
+
+# ---- 3. closed-form jets of the reference's per-operation tests (test/taylor_*.cpp) ----
+
+def approximately(cmp, value, eps_mul=100.0):
+    """test/test_utils.hpp:47-80: relative to the computed value, absolute below the tolerance."""
+    cmp, value = np.asarray(cmp, dtype=float), np.asarray(value, dtype=float)
+    tol = np.finfo(float).eps * eps_mul
+    err = np.where(np.abs(cmp) < tol, np.abs(cmp - value), np.abs((cmp - value) / np.where(cmp == 0, 1.0, cmp)))
+    return bool(np.all(err <= tol))
+
+
+def closed_form_cases():
+    from closed_form_cases import CASES
+    g = golden("closed_form_jets.json")
+    assert [c["name"] for c in g["cases"]] == [c[0] for c in CASES]
+    return list(zip(CASES, g["cases"]))
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("case,gold", closed_form_cases(), ids=lambda v: v[0] if isinstance(v, tuple) else "")
+def test_closed_form_jets(case, gold, mode):
+    """Every batch-3 / order-3 block of test/taylor_{sincos,tanh,exp,log,sqrt,square,pow,div,mul,sub,sum_sq,neg,
+    time}.cpp (file:line in tests/closed_form_cases.py): the jet of one step against the closed forms, to the
+    reference's own 100 epsilon."""
+    from closed_form_cases import BATCH, EPS_MUL, ORDER, TOL, hb_system
+    P = hb.Program(hb_system(hb, case), tol=TOL)
+    assert P.order == ORDER
+    o = oracle.OracleIntegrator(P, gold["state"], BATCH, time=gold["time"] if gold["time"] else 0.0, mode=mode)
+    o.step(write_tc=True)
+    assert approximately(o.tc, gold["tc"], EPS_MUL.get(case[0], 100.0)), (case[0], o.tc, gold["tc"])
