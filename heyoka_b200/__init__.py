@@ -365,6 +365,16 @@ class Batch:
                                                int(write_tc), C.byref(flag)))
         return flag.value
 
+    def propagate_grid(self, grid, max_delta_t=None, max_steps=0):
+        """grid: [n_pts, batch]; returns the states at the grid points, [n_pts, n_eq, batch] (NaN where not reached)."""
+        grid = np.ascontiguousarray(grid, dtype=np.float64)
+        n_pts = grid.size // self.n
+        md = None if max_delta_t is None else np.ascontiguousarray(max_delta_t, dtype=np.float64)
+        out = np.empty((n_pts, self.program.n_eq, self.n))
+        check(lib.hy_batch_propagate_grid(self._h, _dptr(grid), n_pts, None if md is None else _dptr(md),
+                                          int(max_steps), _dptr(out)))
+        return out
+
     def d_output(self, tau):
         P = self.program
         tau = np.ascontiguousarray(np.broadcast_to(tau, (self.n,)), dtype=np.float64)
@@ -574,6 +584,34 @@ class taylor_adaptive_batch:
         self._pull(write_tc)
         oc, mn, mx, ns = self._b.prop_res()
         self._prop_res = list(zip(oc.tolist(), mn.tolist(), mx.tolist(), ns.tolist()))
+
+    def propagate_grid(self, grid, max_steps=0, max_delta_t=None, callback=None):
+        """States at the grid points, shape [n_pts, n_eq, batch] (src/taylor_adaptive_batch.cpp:1545-2055).
+        grid: [n_pts, batch] (or flat, point-major like the reference's std::vector)."""
+        if callback is not None:
+            raise NotImplementedError("Callbacks are not supported by propagate_grid()")
+        n = self._batch_size
+        g = np.asarray(grid, dtype=np.float64).reshape(-1)
+        if g.size == 0:
+            raise ValueError("Cannot invoke propagate_grid() in an adaptive Taylor integrator in batch mode if the "
+                             "time grid is empty")
+        if g.size % n != 0:
+            raise ValueError("Invalid grid size detected in propagate_grid() for an adaptive Taylor integrator in "
+                             "batch mode: the grid has a size of %d, which is not a multiple of the batch size (%d)"
+                             % (g.size, n))
+        if max_delta_t is not None:
+            md = np.broadcast_to(np.asarray(max_delta_t, dtype=np.float64), (n,)) if np.ndim(max_delta_t) == 0 else \
+                np.asarray(max_delta_t, dtype=np.float64)
+            if md.size != n:
+                raise ValueError("Invalid number of max timesteps specified in a Taylor integrator in batch mode: the "
+                                 "batch size is %d, but the number of specified timesteps is %d" % (n, md.size))
+            max_delta_t = np.ascontiguousarray(md)
+        self._push()
+        out = self._b.propagate_grid(g.reshape(-1, n), max_delta_t, max_steps)
+        self._pull(True)
+        oc, mn, mx, ns = self._b.prop_res()
+        self._prop_res = list(zip(oc.tolist(), mn.tolist(), mx.tolist(), ns.tolist()))
+        return out
 
     def propagate_for(self, delta_ts, **kw):
         n = self._batch_size

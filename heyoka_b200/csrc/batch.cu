@@ -1062,6 +1062,209 @@ int hy_batch_propagate_until_dev(hy_batch *b, const double *d_t_final_hi, const 
     }
 }
 
+// propagate_grid() (src/taylor_adaptive_batch.cpp:1545-2055). The reference's algorithm is kept as it is: an
+// initial propagate_until(grid[0]) with write_tc, then lock-step iterations of {dense output at every grid point
+// covered by the last step; one step clamped to the last grid point}. The per-lane work runs on the device (one
+// step launch + two small kernels per iteration); the host only reads the two loop flags.
+int hy_batch_propagate_grid(hy_batch *b, const double *grid, uint64_t n_pts, const double *max_delta_t,
+                            uint64_t max_steps, double *out)
+{
+    double *d_grid = nullptr, *d_out = nullptr, *d_lane = nullptr;
+    std::uint32_t *d_idx = nullptr;
+    unsigned char *d_dir = nullptr;
+    unsigned *d_gflags = nullptr;
+    const auto cleanup = [&]() {
+        for (void *ptr : {static_cast<void *>(d_grid), static_cast<void *>(d_out), static_cast<void *>(d_lane),
+                          static_cast<void *>(d_idx), static_cast<void *>(d_dir), static_cast<void *>(d_gflags)}) {
+            if (ptr != nullptr) {
+                cudaFree(ptr);
+            }
+        }
+    };
+    try {
+        if (b == nullptr || grid == nullptr || out == nullptr) {
+            throw std::invalid_argument("Null pointer passed to hy_batch_propagate_grid()");
+        }
+        device_guard guard(b->device);
+        const std::uint32_t n = b->n;
+        if (n_pts == 0u) {
+            throw std::invalid_argument("Cannot invoke propagate_grid() in an adaptive Taylor integrator in batch mode "
+                                        "if the time grid is empty");
+        }
+        if (n_pts > 0xffffffffull) {
+            throw std::overflow_error("Too many grid points passed to propagate_grid()");
+        }
+        // The current time must be finite (:1590-1594).
+        std::vector<double> t_hi(n), t_lo(n);
+        {
+            HY_CUDA_CHECK(cudaMemcpyAsync(t_hi.data(), b->d_t_hi, sizeof(double) * n, cudaMemcpyDeviceToHost, b->stream));
+            HY_CUDA_CHECK(cudaMemcpyAsync(t_lo.data(), b->d_t_lo, sizeof(double) * n, cudaMemcpyDeviceToHost, b->stream));
+            HY_CUDA_CHECK(cudaStreamSynchronize(b->stream));
+            for (std::uint32_t i = 0; i < n; ++i) {
+                if (!std::isfinite(t_hi[i]) || !std::isfinite(t_lo[i])) {
+                    throw std::invalid_argument("Cannot invoke propagate_grid() in an adaptive Taylor integrator in "
+                                                "batch mode if the current time is not finite");
+                }
+            }
+        }
+        if (max_delta_t != nullptr) {
+            for (std::uint32_t i = 0; i < n; ++i) {
+                if (std::isnan(max_delta_t[i])) {
+                    throw std::invalid_argument("A nan max_delta_t was passed to the propagate_grid() function of an "
+                                                "adaptive Taylor integrator in batch mode");
+                }
+                if (max_delta_t[i] <= 0) {
+                    throw std::invalid_argument("A non-positive max_delta_t was passed to the propagate_grid() "
+                                                "function of an adaptive Taylor integrator in batch mode");
+                }
+            }
+        }
+        // Grid checks, :1619-1656: finite, strictly monotonic, same direction in every lane.
+        constexpr auto nf_err_msg
+            = "A non-finite time value was passed to propagate_grid() in an adaptive Taylor integrator in batch mode";
+        constexpr auto ig_err_msg = "A non-monotonic time grid was passed to propagate_grid() in an adaptive "
+                                    "Taylor integrator in batch mode";
+        const auto batch_nf = [&](std::uint64_t k) {
+            return std::any_of(grid + k * n, grid + (k + 1u) * n, [](double t) { return !std::isfinite(t); });
+        };
+        if (batch_nf(0)) {
+            throw std::invalid_argument(nf_err_msg);
+        }
+        if (n_pts > 1u) {
+            // The direction is established from the first two points of lane 0.
+            if (batch_nf(1)) {
+                throw std::invalid_argument(nf_err_msg);
+            }
+            if (grid[n] == grid[0]) {
+                throw std::invalid_argument(ig_err_msg);
+            }
+            const bool dir = grid[n] > grid[0];
+            for (std::uint64_t k = 1; k < n_pts; ++k) {
+                if (k > 1u && batch_nf(k)) {
+                    throw std::invalid_argument(nf_err_msg);
+                }
+                for (std::uint32_t i = 0; i < n; ++i) {
+                    if ((grid[k * n + i] > grid[(k - 1u) * n + i]) != dir) {
+                        throw std::invalid_argument(ig_err_msg);
+                    }
+                }
+            }
+        }
+        // The grid must start at the current time (:1660-1670).
+        for (std::uint32_t i = 0; i < n; ++i) {
+            if (t_hi[i] != grid[i]) {
+                throw std::invalid_argument(
+                    "When invoking propagate_grid(), the first element of the time grid must match the current "
+                    "time coordinate - however, the first element of the time grid at batch index "
+                    + std::to_string(i) + " has a value of " + hy::detail::fmt_double(grid[i])
+                    + ", while the current time coordinate is " + hy::detail::fmt_double(t_hi[i]));
+            }
+        }
+
+        const std::size_t n_out = static_cast<std::size_t>(n_pts) * b->n_eq * n, state_doubles = std::size_t(b->n_eq) * n;
+        HY_CUDA_CHECK(cudaMalloc(&d_grid, sizeof(double) * n_pts * n));
+        HY_CUDA_CHECK(cudaMalloc(&d_out, sizeof(double) * n_out));
+        HY_CUDA_CHECK(cudaMalloc(&d_lane, sizeof(double) * 4u * n)); // rem_hi, rem_lo, dt_limit, max_delta_t
+        HY_CUDA_CHECK(cudaMalloc(&d_idx, sizeof(std::uint32_t) * n));
+        HY_CUDA_CHECK(cudaMalloc(&d_dir, n));
+        HY_CUDA_CHECK(cudaMalloc(&d_gflags, sizeof(unsigned) * 4u));
+        HY_CUDA_CHECK(cudaMemcpyAsync(d_grid, grid, sizeof(double) * n_pts * n, cudaMemcpyHostToDevice, b->stream));
+        if (max_delta_t != nullptr) {
+            HY_CUDA_CHECK(cudaMemcpyAsync(d_lane + 3u * n, max_delta_t, sizeof(double) * n, cudaMemcpyHostToDevice,
+                                          b->stream));
+        }
+        dev::k_fill_double<<<static_cast<unsigned>((n_out + 255u) / 256u), 256, 0, b->stream>>>(
+            d_out, n_out, std::numeric_limits<double>::quiet_NaN());
+        HY_CUDA_CHECK(cudaGetLastError());
+        const unsigned gb = (n + 127u) / 128u;
+        const auto finish = [&]() {
+            HY_CUDA_CHECK(cudaMemcpyAsync(out, d_out, sizeof(double) * n_out, cudaMemcpyDeviceToHost, b->stream));
+            HY_CUDA_CHECK(cudaStreamSynchronize(b->stream));
+            cleanup();
+            return HY_OK;
+        };
+
+        // Up to the first grid point (a zero-length step when the time is already there: it brings the Taylor
+        // coefficients up to date), :1697-1706.
+        {
+            const double *d_mdt = max_delta_t != nullptr ? d_lane + 3u * n : nullptr;
+            const int rc = propagate_impl(b, d_grid, nullptr, d_mdt, max_steps, 1, nullptr);
+            if (rc != HY_OK) {
+                cleanup();
+                return rc;
+            }
+            std::vector<long long> oc(n);
+            HY_CUDA_CHECK(cudaMemcpyAsync(oc.data(), b->d_prop_outcome, sizeof(long long) * n, cudaMemcpyDeviceToHost,
+                                          b->stream));
+            HY_CUDA_CHECK(cudaStreamSynchronize(b->stream));
+            if (std::any_of(oc.begin(), oc.end(), [](long long v) { return v != HY_OUTCOME_TIME_LIMIT; })) {
+                // Outcomes kept, counters reset (:1709-1722).
+                dev::k_fill_double<<<gb, 128, 0, b->stream>>>(b->d_prop_min_h, n, std::numeric_limits<double>::infinity());
+                dev::k_fill_double<<<gb, 128, 0, b->stream>>>(b->d_prop_max_h, n, 0.);
+                HY_CUDA_CHECK(cudaMemsetAsync(b->d_prop_n_steps, 0, sizeof(unsigned long long) * n, b->stream));
+                return finish();
+            }
+        }
+        HY_CUDA_CHECK(cudaMemcpyAsync(d_out, b->d_state, sizeof(double) * state_doubles, cudaMemcpyDeviceToDevice,
+                                      b->stream));
+
+        dev::grid_state G{};
+        G.grid = d_grid;
+        G.n_pts = static_cast<std::uint32_t>(n_pts);
+        G.out = d_out;
+        G.max_delta_t = max_delta_t != nullptr ? d_lane + 3u * n : nullptr;
+        G.cur_idx = d_idx;
+        G.rem_hi = d_lane;
+        G.rem_lo = d_lane + n;
+        G.t_dir = d_dir;
+        G.dt_limit = d_lane + 2u * n;
+        G.flags = d_gflags;
+        unsigned hflags[4] = {0u, 0u, 0u, 0u};
+        const auto read_flags = [&]() {
+            HY_CUDA_CHECK(cudaMemcpyAsync(hflags, d_gflags, sizeof(hflags), cudaMemcpyDeviceToHost, b->stream));
+            HY_CUDA_CHECK(cudaStreamSynchronize(b->stream));
+        };
+        HY_CUDA_CHECK(cudaMemsetAsync(d_gflags, 0, sizeof(hflags), b->stream));
+        dev::k_grid_init<<<gb, 128, 0, b->stream>>>(b->view(), G, b->d_prop_min_h, b->d_prop_max_h, b->d_prop_n_steps);
+        dev::k_grid_sample<<<gb, 128, 0, b->stream>>>(b->prog, b->view(), G);
+        HY_CUDA_CHECK(cudaGetLastError());
+        read_flags();
+        if (hflags[2] != 0u) {
+            throw std::invalid_argument("The final time passed to the propagate_grid() function of an adaptive Taylor "
+                                        "integrator in batch mode results in an overflow condition");
+        }
+        std::uint64_t iter = 0;
+        bool interrupted = false;
+        while (hflags[0] != 0u && !interrupted) {
+            dev::run_args R{};
+            R.max_delta_t = G.dt_limit;
+            R.default_max_delta_t = std::numeric_limits<double>::infinity();
+            R.write_tc = 1;
+            R.flags = b->d_flags;
+            R.counter = b->d_counter;
+            b->launch(false, R);
+            HY_CUDA_CHECK(cudaMemsetAsync(d_gflags, 0, sizeof(unsigned) * 2u, b->stream));
+            dev::k_grid_book<<<gb, 128, 0, b->stream>>>(b->view(), G, b->d_prop_outcome, b->d_prop_min_h,
+                                                         b->d_prop_max_h, b->d_prop_n_steps);
+            dev::k_grid_sample<<<gb, 128, 0, b->stream>>>(b->prog, b->view(), G);
+            HY_CUDA_CHECK(cudaGetLastError());
+            read_flags();
+            if (hflags[1] != 0u) {
+                break; // non-finite state: nothing further is written (:1973-1978)
+            }
+            if (++iter == max_steps) {
+                dev::k_fill_outcome<<<(n + 255u) / 256u, 256, 0, b->stream>>>(b->d_prop_outcome, n,
+                                                                              HY_OUTCOME_STEP_LIMIT);
+                interrupted = true;
+            }
+        }
+        return finish();
+    } catch (...) {
+        cleanup();
+        return translate_exception();
+    }
+}
+
 int hy_batch_d_output(hy_batch *b, const double *tau, double *out)
 {
     try {

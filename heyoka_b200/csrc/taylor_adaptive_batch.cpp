@@ -524,6 +524,45 @@ taylor_adaptive_batch<double>::propagate_until_vec(const std::vector<double> &ts
     return propagate_until_impl(ts, std::vector<double>(m.batch_size, 0.), std::move(o));
 }
 
+// propagate_grid(): src/taylor_adaptive_batch.cpp:1545-2055. The size checks that need the reference's wording are
+// done here, the grid checks and the integration by hy_batch_propagate_grid().
+std::tuple<step_callback_batch<double>, std::vector<double>>
+taylor_adaptive_batch<double>::propagate_grid_impl(const std::vector<double> &grid, prop_opts o)
+{
+    auto &m = *m_impl;
+    const auto n = m.batch_size;
+    if (o.cb) {
+        throw not_implemented_error("Callbacks are not supported by propagate_grid() in the B200 batch integrator");
+    }
+    if (grid.empty()) {
+        throw std::invalid_argument(
+            "Cannot invoke propagate_grid() in an adaptive Taylor integrator in batch mode if the time grid is empty");
+    }
+    if (grid.size() % n != 0u) {
+        throw std::invalid_argument(
+            "Invalid grid size detected in propagate_grid() for an adaptive Taylor integrator in batch mode: "
+            "the grid has a size of "
+            + std::to_string(grid.size()) + ", which is not a multiple of the batch size (" + std::to_string(n) + ")");
+    }
+    if (!o.max_delta_t.empty() && o.max_delta_t.size() != n) {
+        throw std::invalid_argument("Invalid number of max timesteps specified in a Taylor integrator in batch mode: "
+                                    "the batch size is "
+                                    + std::to_string(n) + ", but the number of specified timesteps is "
+                                    + std::to_string(o.max_delta_t.size()));
+    }
+    std::vector<double> retval(grid.size() * m.dim);
+    m.push();
+    check(hy_batch_propagate_grid(m.batch, grid.data(), grid.size() / n,
+                                  o.max_delta_t.empty() ? nullptr : o.max_delta_t.data(), o.max_steps, retval.data()));
+    m.pull(true);
+    check(hy_batch_download_prop_res(m.batch, m.oc.data(), m.tmp_a.data(), m.tmp_b.data(), m.tmp_n.data()));
+    for (std::uint32_t i = 0; i < n; ++i) {
+        m.prop_res[i] = std::tuple{static_cast<taylor_outcome>(m.oc[i]), m.tmp_a[i], m.tmp_b[i],
+                                   static_cast<std::size_t>(m.tmp_n[i])};
+    }
+    return {std::move(o.cb), std::move(retval)};
+}
+
 std::tuple<std::optional<continuous_output_batch<double>>, step_callback_batch<double>>
 taylor_adaptive_batch<double>::propagate_until_impl(const std::vector<double> &hi, const std::vector<double> &lo,
                                                     prop_opts o)

@@ -228,6 +228,14 @@ int hy_batch_propagate_until(hy_batch *, const double *t_final_hi, const double 
 int hy_batch_propagate_until_dev(hy_batch *, const double *d_t_final_hi, const double *d_t_final_lo,
                                  const double *d_max_delta_t, uint64_t max_steps, int write_tc, int *any_nf_or_limit);
 
+/* propagate_grid() (src/taylor_adaptive_batch.cpp:1545-2055): dense-output sampling on per-lane time grids.
+ * grid[k * batch + lane], k < n_pts: finite, strictly monotonic with the same direction in every lane, and
+ * grid[lane] == current time (hi part) of the lane. out[(k * n_eq + var) * batch + lane] receives the state at
+ * grid point k; entries not reached (early exit: step limit, non-finite state) are NaN. The integrator ends at
+ * the last grid point with outcome time_limit; results via hy_batch_download_prop_res(). host arrays. */
+int hy_batch_propagate_grid(hy_batch *, const double *grid, uint64_t n_pts, const double *max_delta_t,
+                            uint64_t max_steps, double *out);
+
 /* Dense output from the last written tc: out[var * batch + lane] = sum_o tc[var][o][lane] * tau[lane]^o
  * (src/taylor_01.cpp:1015-1185; tau relative to the start of the last step). out/tau are host arrays. */
 int hy_batch_d_output(hy_batch *, const double *tau, double *out);

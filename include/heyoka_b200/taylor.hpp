@@ -99,6 +99,8 @@ private:
     void step_impl(const std::vector<double> *, bool backward, bool wtc);
     std::tuple<std::optional<continuous_output_batch<double>>, step_callback_batch<double>>
     propagate_until_impl(const std::vector<double> &hi, const std::vector<double> &lo, prop_opts);
+    std::tuple<step_callback_batch<double>, std::vector<double>> propagate_grid_impl(const std::vector<double> &,
+                                                                                     prop_opts);
 
     template <typename... KwArgs>
     static ctor_opts parse_ctor(const KwArgs &...kw_args)
@@ -237,6 +239,15 @@ public:
     propagate_for(double delta_t, const KwArgs &...kw_args)
     {
         return propagate_for_vec(std::vector<double>(get_batch_size(), delta_t), parse_prop(kw_args...));
+    }
+    // propagate_grid() (include/heyoka/taylor.hpp, src/taylor_adaptive_batch.cpp:1545-2055): grid[k * batch + lane];
+    // returns the callback and the states at the grid points, [n_pts][dim][batch], NaN where not reached.
+    // kw::max_steps, kw::max_delta_t; a non-empty kw::callback is rejected with not_implemented_error.
+    template <typename... KwArgs>
+    std::tuple<step_callback_batch<double>, std::vector<double>> propagate_grid(const std::vector<double> &grid,
+                                                                                const KwArgs &...kw_args)
+    {
+        return propagate_grid_impl(grid, parse_prop(kw_args...));
     }
     [[nodiscard]] const std::vector<std::tuple<taylor_outcome, double, double, std::size_t>> &
     get_propagate_res() const;

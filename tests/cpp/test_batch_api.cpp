@@ -248,6 +248,75 @@ static void test_models_and_dense_output()
     REQUIRE(psys.size() == 2u);
 }
 
+// test/taylor_adaptive_batch.cpp:162-323 ("propagate grid"): error messages, trivial grids, the harmonic
+// oscillator on a dense grid forward and backward against the closed form (10000 eps).
+static void test_propagate_grid()
+{
+    auto [x, v] = make_vars("x", "v");
+    const double inf = std::numeric_limits<double>::infinity();
+    taylor_adaptive_batch<double> ta{{prime(x) = v, prime(v) = -9.8 * sin(x)},
+                                     {0.05, 0.025, 0.051, 0.0251, 0.052, 0.0252, 0.053, 0.0253},
+                                     4u};
+    REQUIRE_THROWS_MSG(ta.propagate_grid({}), std::invalid_argument,
+                       "Cannot invoke propagate_grid() in an adaptive Taylor integrator in batch mode "
+                       "if the time grid is empty");
+    REQUIRE_THROWS_MSG(ta.propagate_grid({1., 2., 3., 4., 5.}), std::invalid_argument,
+                       "the grid has a size of 5, which is not a multiple of the batch size (4)");
+    REQUIRE_THROWS_MSG(ta.propagate_grid({0., 0., 1., 4.}), std::invalid_argument,
+                       "batch index 2 has a value of 1, while the current time coordinate is 0");
+    ta.set_time({0., 0., inf, 0.});
+    REQUIRE_THROWS_MSG(ta.propagate_grid({0., 0., 0., 0.}), std::invalid_argument, "the current time is not finite");
+    ta.set_time({0., 0., 0., 0.});
+    REQUIRE_THROWS_MSG(ta.propagate_grid({0., 0., inf, 0.}), std::invalid_argument, "A non-finite time value");
+    REQUIRE_THROWS_MSG(ta.propagate_grid({0., 0., 0., 0., 1., 1., -1., 1.}), std::invalid_argument,
+                       "A non-monotonic time grid");
+    REQUIRE_THROWS_MSG(ta.propagate_grid({0., 0., 0., 0., 1., 1., 1., 1., 2., 2., 1., 2.}), std::invalid_argument,
+                       "A non-monotonic time grid");
+    {
+        auto [cb, ret] = ta.propagate_grid({0., 0., 0., 0.});
+        REQUIRE(!cb);
+        REQUIRE((ret == std::vector<double>{0.05, 0.025, 0.051, 0.0251, 0.052, 0.0252, 0.053, 0.0253}));
+        for (const auto &[oc, min_h, max_h, nsteps] : ta.get_propagate_res()) {
+            REQUIRE(oc == taylor_outcome::time_limit);
+            REQUIRE(min_h == inf);
+            REQUIRE(max_h == 0);
+            REQUIRE(nsteps == 0u);
+        }
+    }
+    for (const double sign : {1., -1.}) {
+        taylor_adaptive_batch<double> osc{{prime(x) = v, prime(v) = -x}, {0., 0., 0., 0., 1., 1.1, 1.2, 1.3}, 4u};
+        std::vector<double> grid;
+        for (auto i = 0u; i < 1000u; ++i) {
+            for (auto j = 0; j < 4; ++j) {
+                grid.push_back(sign * (i / 100.));
+                if (i != 0u) {
+                    grid.back() += sign * (j / 10.);
+                }
+            }
+        }
+        auto [cb, ret] = osc.propagate_grid(grid);
+        REQUIRE(!cb);
+        REQUIRE(ret.size() == 8000u);
+        for (auto i = 0u; i < 4u; ++i) {
+            REQUIRE(std::get<0>(osc.get_propagate_res()[i]) == taylor_outcome::time_limit);
+            REQUIRE(osc.get_time()[i] == grid[3996u + i]);
+        }
+        bool ok = true;
+        for (auto i = 0u; i < 1000u; ++i) {
+            for (auto j = 0u; j < 4u; ++j) {
+                const double sv = (1 + j / 10.) * std::sin(grid[i * 4u + j]), cv = (1 + j / 10.) * std::cos(grid[i * 4u + j]);
+                // approximately(): relative to the computed value, absolute below the tolerance.
+                const double tol = std::numeric_limits<double>::epsilon() * 10000.;
+                const auto near = [tol](double c, double e) {
+                    return std::abs(c) < tol ? std::abs(c - e) <= tol : std::abs((c - e) / c) <= tol;
+                };
+                ok = ok && near(ret[8u * i + j], sv) && near(ret[8u * i + j + 4u], cv);
+            }
+        }
+        REQUIRE(ok);
+    }
+}
+
 int main(int argc, char **argv)
 {
     const bool gpu = argc > 1 && std::strcmp(argv[1], "gpu") == 0;
@@ -257,6 +326,7 @@ int main(int argc, char **argv)
         test_propagate_for_until();
         test_ensemble();
         test_models_and_dense_output();
+        test_propagate_grid();
     }
     if (n_fail == 0) {
         std::printf("ALL PASSED (%s)\n", gpu ? "gpu" : "cpu");

@@ -141,3 +141,101 @@ class OracleIntegrator:
         rc = lib.oracle_d_output_w1(_desc_ptr(self.P), C.c_uint32(self.n), _arr(self.tc), _arr(tau), _arr(out))
         assert rc == 0
         return out
+
+    def propagate_grid(self, grid, max_delta_t=None, max_steps=0):
+        """propagate_grid_impl(), src/taylor_adaptive_batch.cpp:1545-2055, restated with the oracle's step() and
+        dense output (argument checks left to the product's tests). grid: [n_pts, batch]. Returns [n_pts, n_eq, batch]."""
+        import heyoka_b200 as hb
+        n, n_eq = self.n, self.P.n_eq
+        grid = np.asarray(grid, dtype=np.float64).reshape(-1, n)
+        n_pts = grid.shape[0]
+        mdt = np.full(n, np.inf) if max_delta_t is None else np.broadcast_to(np.asarray(max_delta_t, float), (n,))
+        ret = np.full((n_pts, n_eq, n), np.nan)
+        TL, SUCCESS, NF, STEP_LIMIT = (hb.taylor_outcome.time_limit, hb.taylor_outcome.success,
+                                       hb.taylor_outcome.err_nf_state, hb.taylor_outcome.step_limit)
+
+        def dsub(ahi, alo, bhi, blo):  # dfloat a - b (include/heyoka/detail/dfloat.hpp:157-186)
+            return hb._dfloat_add(np.atleast_1d(ahi), np.atleast_1d(alo), -np.atleast_1d(bhi), -np.atleast_1d(blo))
+
+        def dlt(ahi, alo, bhi, blo):
+            return (ahi < bhi) | ((ahi == bhi) & (alo < blo))
+
+        # :1697-1722
+        self.propagate_until(grid[0], max_delta_t=None if max_delta_t is None else mdt, max_steps=max_steps,
+                             write_tc=True)
+        if np.any(self.prop_outcome != TL):
+            self.min_h[:] = np.inf
+            self.max_h[:] = 0
+            self.n_steps[:] = 0
+            return ret
+        ret[0] = self.state
+        rem_hi, rem_lo = dsub(grid[-1], np.zeros(n), self.t_hi, self.t_lo)  # :1728-1739
+        t_dir = (rem_hi > 0) | ((rem_hi == 0) & (rem_lo >= 0))
+        self.n_steps[:] = 0
+        self.min_h[:] = np.inf
+        self.max_h[:] = 0
+        cur = np.ones(n, dtype=np.int64)
+        it = 0
+        while np.any(cur < n_pts):
+            # time range of the last step, :1795-1803
+            c_hi, c_lo = dsub(self.t_hi, self.t_lo, self.last_h, np.zeros(n))
+            cmp_lt_t = dlt(c_hi, c_lo, self.t_hi, self.t_lo)
+            t_lt_cmp = dlt(self.t_hi, self.t_lo, c_hi, c_lo)
+            t0h, t0l = np.where(cmp_lt_t, c_hi, self.t_hi), np.where(cmp_lt_t, c_lo, self.t_lo)
+            t1h, t1l = np.where(t_lt_cmp, c_hi, self.t_hi), np.where(t_lt_cmp, c_lo, self.t_lo)
+            dflags = np.ones(n, dtype=bool)
+            while True:  # :1811-1886
+                tmp = np.zeros(n)
+                for i in range(n):
+                    if dflags[i] and cur[i] < n_pts:
+                        g = grid[cur[i], i]
+                        ge_t0 = not dlt(g, 0.0, t0h[i], t0l[i])
+                        le_t1 = not dlt(t1h[i], t1l[i], g, 0.0)
+                        dflags[i] = (ge_t0 and le_t1) or (rem_hi[i] == 0 and rem_lo[i] == 0)
+                        tmp[i] = g
+                    else:
+                        dflags[i] = False
+                if not dflags.any():
+                    break
+                tau = dsub(tmp, np.zeros(n), c_hi, c_lo)[0]  # update_d_output(), :2283-2287
+                d = self.d_output(tau)
+                for i in range(n):
+                    if dflags[i]:
+                        ret[cur[i], :, i] = d[:, i]
+                        cur[i] += 1
+                if not np.any(cur < n_pts):
+                    break
+            if not np.any(cur < n_pts):
+                break
+            if np.any(self.prop_outcome == STEP_LIMIT):
+                break
+            # next step, :1899-1913
+            lim = np.empty(n)
+            for i in range(n):
+                if t_dir[i]:
+                    lim[i] = rem_hi[i] if dlt(rem_hi[i], rem_lo[i], mdt[i], 0.0) else mdt[i]
+                else:
+                    lim[i] = rem_hi[i] if dlt(-mdt[i], 0.0, rem_hi[i], rem_lo[i]) else -mdt[i]
+            self.step(max_delta_t=lim, write_tc=True)
+            nfs = False
+            for i in range(n):  # :1922-1971
+                oc, h = self.step_outcome[i], self.last_h[i]
+                if oc == NF:
+                    nfs = True
+                else:
+                    self.n_steps[i] += int(h != 0)
+                    if oc == SUCCESS:
+                        self.min_h[i] = min(self.min_h[i], abs(h))
+                        self.max_h[i] = max(self.max_h[i], abs(h))
+                    if h == rem_hi[i]:
+                        rem_hi[i] = rem_lo[i] = 0.0
+                    else:
+                        r = dsub(grid[-1, i], 0.0, self.t_hi[i], self.t_lo[i])
+                        rem_hi[i], rem_lo[i] = r[0][0], r[1][0]
+                self.prop_outcome[i] = oc
+            if nfs:
+                break
+            it += 1
+            if it == max_steps:
+                self.prop_outcome[:] = STEP_LIMIT
+        return ret

@@ -331,3 +331,96 @@ def test_closed_form_jets_gpu(case, gold, kernel):
     assert ta.get_order() == ORDER
     ta.step(write_tc=True)
     assert approximately(ta.tc, gold["tc"], EPS_MUL.get(case[0], 100.0)), (case[0], ta.tc, gold["tc"])
+
+
+# ---- propagate_grid (src/taylor_adaptive_batch.cpp:1545-2055) ----
+
+@pytest.mark.gpu
+def test_propagate_grid_oscillator_gpu(kernel):
+    """test/taylor_adaptive_batch.cpp:269-385: regular and random grids, forward and backward, against the closed
+    form (the reference's tolerances) and against the oracle's restatement (step counts, outcomes, values)."""
+    from test_oracle_golden import OSC_STATE, approximately, grid_fixtures, sys_oscillator
+    for name, grid, tol in grid_fixtures():
+        ta = hb.taylor_adaptive_batch(sys_oscillator(), OSC_STATE, 4, kernel=kernel)
+        ret = ta.propagate_grid(grid)
+        assert ret.shape == (1000, 2, 4)
+        assert [r[0] for r in ta.propagate_res] == [hb.taylor_outcome.time_limit] * 4
+        assert np.array_equal(ta.time, grid[-1])
+        amp = 1.0 + np.arange(4) / 10.0
+        assert approximately(ret[:, 0, :], amp * np.sin(grid), tol), name
+        assert approximately(ret[:, 1, :], amp * np.cos(grid), tol), name
+        o = oracle.OracleIntegrator(hb.Program(sys_oscillator()), OSC_STATE, 4, mode=oracle.FMA)
+        oret = o.propagate_grid(grid)
+        assert np.max(np.abs(ret - oret)) < 1e-13, name
+        assert [r[3] for r in ta.propagate_res] == [int(s) for s in o.n_steps], name
+        assert np.allclose([r[1] for r in ta.propagate_res], o.min_h, rtol=1e-9)
+        assert np.allclose([r[2] for r in ta.propagate_res], o.max_h, rtol=1e-9)
+        assert lane_err(ta.state, o.state) < 1e-12
+
+
+@pytest.mark.gpu
+def test_propagate_grid_errors_and_trivial_cases():
+    """test/taylor_adaptive_batch.cpp:162-268: argument checks (the reference's messages), a non-finite state, a
+    grid made of the current time only."""
+    st = np.array([0.05, 0.025, 0.051, 0.0251, 0.052, 0.0252, 0.053, 0.0253]).reshape(2, 4)
+    ta = hb.taylor_adaptive_batch(sys_pendulum(), st, 4)
+    inf = float("inf")
+    with pytest.raises(ValueError, match="if the time grid is empty"):
+        ta.propagate_grid([])
+    for bad in ([1.0], [1.0, 2.0], [1.0, 2.0, 3.0, 4.0, 5.0]):
+        with pytest.raises(ValueError, match=r"the grid has a size of %d, which is not a multiple of the batch size \(4\)"
+                           % len(bad)):
+            ta.propagate_grid(bad)
+    with pytest.raises(ValueError, match="the first element of the time grid at batch index 2 has a value of 1, while "
+                                         "the current time coordinate is 0"):
+        ta.propagate_grid([0.0, 0.0, 1.0, 4.0])
+    ta.set_time([0.0, 0.0, inf, 0.0])
+    with pytest.raises(ValueError, match="if the current time is not finite"):
+        ta.propagate_grid([0.0, 0.0, 0.0, 0.0])
+    ta.set_time([0.0, 0.0, 0.0, 0.0])
+    nf = "A non-finite time value was passed to propagate_grid"
+    nm = "A non-monotonic time grid was passed to propagate_grid"
+    for grid, msg in (([0, 0, inf, 0], nf), ([0, 0, 0, 0, 0, inf, 0, 0], nf), ([0, 0, 0, 0, 1, 1, -1, 1], nm),
+                      ([0, 0, 0, 0, 1, 1, 1, 1, 0, 0, 0, inf], nf), ([0, 0, 0, 0, 1, 1, 1, 1, 2, 0, 0, 2], nm),
+                      ([0, 0, 0, 0, 0, 1, 1, 1, 2, 2, 2, 2], nm), ([0, 0, 0, 0, 1, 0, 1, 1, 2, 2, 2, 2], nm),
+                      ([0, 0, 0, 0, 1, 1, 1, 0, 2, 2, 2, 2], nm), ([0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 1, 2], nm)):
+        with pytest.raises(ValueError, match=msg):
+            ta.propagate_grid(np.array(grid, dtype=float))
+    with pytest.raises(ValueError, match="A non-positive max_delta_t was passed to the propagate_grid"):
+        ta.propagate_grid([0.0] * 4 + [1.0] * 4, max_delta_t=[1.0, 0.0, 1.0, 1.0])
+
+    # An infinity in the state: lane 0 fails, the output stays NaN.
+    st_inf = st.copy()
+    st_inf[0, 0] = inf
+    ta = hb.taylor_adaptive_batch(sys_pendulum(), st_inf, 4)
+    ret = ta.propagate_grid([0.0, 0.0, 0.0, 0.0])
+    assert ret.shape == (1, 2, 4) and np.all(np.isnan(ret))
+    assert [r[0] for r in ta.propagate_res] == [hb.taylor_outcome.err_nf_state] + [hb.taylor_outcome.time_limit] * 3
+
+    # Propagate to the initial time.
+    ta = hb.taylor_adaptive_batch(sys_pendulum(), st, 4)
+    ret = ta.propagate_grid([0.0, 0.0, 0.0, 0.0])
+    assert np.array_equal(ret[0], st)
+    for oc, min_h, max_h, nsteps in ta.propagate_res:
+        assert (oc, min_h, max_h, nsteps) == (hb.taylor_outcome.time_limit, inf, 0.0, 0)
+
+
+@pytest.mark.gpu
+def test_propagate_grid_limits_match_oracle(kernel):
+    """max_delta_t and max_steps (early exit: remaining rows NaN, every outcome step_limit), 6-body system."""
+    st = outer_ss_batch_state(5, perturb=1e-3, seed=3)
+    grid = np.linspace(0.0, 4.0, 41)[:, None] * np.array([1.0, 1.1, 0.9, 1.05, 0.95])[None, :]
+    for kw in (dict(max_delta_t=[0.05, 0.2, 0.3, 0.11, 1.0]), dict(max_steps=5), dict()):
+        ta = hb.taylor_adaptive_batch(sys_outer_ss(), st, 5, high_accuracy=True, kernel=kernel)
+        o = oracle.OracleIntegrator(hb.Program(sys_outer_ss(), high_accuracy=True), st, 5, mode=oracle.FMA)
+        ret = ta.propagate_grid(grid, **kw)
+        oret = o.propagate_grid(grid, **kw)
+        assert np.array_equal(np.isnan(ret), np.isnan(oret)), kw
+        if "max_steps" in kw:
+            assert np.isnan(ret).any() and not np.isnan(ret[:2]).any()
+        m = ~np.isnan(oret)
+        scale = np.max(np.abs(oret[m]))
+        assert np.max(np.abs(ret[m] - oret[m])) < 1e-12 * scale, kw
+        assert [r[0] for r in ta.propagate_res] == [int(x) for x in o.prop_outcome], kw
+        assert [r[3] for r in ta.propagate_res] == [int(x) for x in o.n_steps], kw
+        assert np.array_equal(ta.time, o.t_hi)

@@ -173,3 +173,45 @@ def test_closed_form_jets(case, gold, mode):
     o = oracle.OracleIntegrator(P, gold["state"], BATCH, time=gold["time"] if gold["time"] else 0.0, mode=mode)
     o.step(write_tc=True)
     assert approximately(o.tc, gold["tc"], EPS_MUL.get(case[0], 100.0)), (case[0], o.tc, gold["tc"])
+
+
+# ---- propagate_grid: the harmonic-oscillator fixtures of test/taylor_adaptive_batch.cpp ----
+
+def grid_fixtures():
+    """(name, grid [1000, 4], tolerance in epsilon): test/taylor_adaptive_batch.cpp:269-323 (regular grids, forward
+    and backward, 10000 eps) and :332-385 (random grids, 400000 / 800000 eps; mt19937 replaced by numpy's
+    generator: the closed form does not depend on the draws)."""
+    out = []
+    for sign, nm in ((1.0, "fwd"), (-1.0, "bwd")):
+        g = np.zeros((1000, 4))
+        for i in range(1000):
+            for j in range(4):
+                g[i, j] = sign * (i / 100.0) + (sign * (j / 10.0) if i != 0 else 0.0)
+        out.append(("regular-" + nm, g, 10000.0))
+    rng = np.random.default_rng(20240924)
+    for sign, nm, tol in ((1.0, "fwd", 400000.0), (-1.0, "bwd", 800000.0)):
+        g = np.zeros((1000, 4))
+        g[1:] = np.cumsum(sign * rng.uniform(0.0, 0.1, (999, 4)), axis=0)
+        out.append(("random-" + nm, g, tol))
+    return out
+
+
+def sys_oscillator():
+    x, v = hb.make_vars("x", "v")
+    return [(x, v), (v, -x)]
+
+
+OSC_STATE = [[0.0, 0.0, 0.0, 0.0], [1.0, 1.1, 1.2, 1.3]]
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("name,grid,tol", grid_fixtures(), ids=lambda v: v if isinstance(v, str) else "")
+def test_propagate_grid_oscillator(name, grid, tol, mode):
+    o = oracle.OracleIntegrator(hb.Program(sys_oscillator()), OSC_STATE, 4, mode=mode)
+    ret = o.propagate_grid(grid)
+    assert ret.shape == (1000, 2, 4)
+    assert np.all(o.prop_outcome == hb.taylor_outcome.time_limit)
+    assert np.array_equal(o.t_hi, grid[-1])
+    amp = 1.0 + np.arange(4) / 10.0
+    assert approximately(ret[:, 0, :], amp * np.sin(grid), tol)
+    assert approximately(ret[:, 1, :], amp * np.cos(grid), tol)
