@@ -390,9 +390,8 @@ def test_propagate_grid_errors_and_trivial_cases():
         ta.propagate_grid([0.0] * 4 + [1.0] * 4, max_delta_t=[1.0, 0.0, 1.0, 1.0])
 
     # An infinity in the state: lane 0 fails, the output stays NaN.
-    st_inf = st.copy()
-    st_inf[0, 0] = inf
-    ta = hb.taylor_adaptive_batch(sys_pendulum(), st_inf, 4)
+    ta = hb.taylor_adaptive_batch(sys_pendulum(), st, 4)
+    ta.state[0, 0] = inf  # (like the reference's ta.get_state_data()[0] = inf)
     ret = ta.propagate_grid([0.0, 0.0, 0.0, 0.0])
     assert ret.shape == (1, 2, 4) and np.all(np.isnan(ret))
     assert [r[0] for r in ta.propagate_res] == [hb.taylor_outcome.err_nf_state] + [hb.taylor_outcome.time_limit] * 3
