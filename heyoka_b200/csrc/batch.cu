@@ -185,6 +185,7 @@ struct hy_batch {
     std::uint32_t *d_blob = nullptr;
     std::size_t blob_bytes = 0; // rounded up to 16 bytes
     double *d_gscratch = nullptr; // overflow tape of the cooperative kernels (spilled private rows)
+    double *d_cscratch = nullptr; // private per-warp coefficient store of the cooperative kernels (see dev::coef_view)
     std::shared_ptr<const hy_program> prog_host; // kept for re-planning
     bool opt_fuse = true, opt_fuse_sv = true;
     int opt_spill = -1; // -1 automatic, 0 never, 1 always
@@ -253,6 +254,7 @@ void hy_batch::free_all() noexcept
     for (void *p :
          {static_cast<void *>(d_ops), static_cast<void *>(d_args), static_cast<void *>(d_sv_defs),
           static_cast<void *>(d_consts), static_cast<void *>(d_blob), static_cast<void *>(d_gscratch),
+          static_cast<void *>(d_cscratch),
           static_cast<void *>(d_state),
           static_cast<void *>(d_pars),
           static_cast<void *>(d_t_hi), static_cast<void *>(d_t_lo), static_cast<void *>(d_last_h),
@@ -491,6 +493,10 @@ bool hy_batch::setup_coop(int L, int N, std::uint32_t threads, std::uint32_t cta
         HY_CUDA_CHECK(cudaFree(d_gscratch));
         d_gscratch = nullptr;
     }
+    if (d_cscratch != nullptr) {
+        HY_CUDA_CHECK(cudaFree(d_cscratch));
+        d_cscratch = nullptr;
+    }
     cv = v;
     c_threads = threads;
     c_smem = bytes;
@@ -502,6 +508,8 @@ bool hy_batch::setup_coop(int L, int N, std::uint32_t threads, std::uint32_t cta
         d_gscratch = dalloc<double>(static_cast<std::size_t>(c_grid) * (threads / 32u) * plan.n_gslots
                                     * static_cast<std::size_t>(L));
     }
+    d_cscratch = dalloc<double>(static_cast<std::size_t>(c_grid) * (threads / 32u) * (order + 1u) * n_eq
+                                * static_cast<std::size_t>(L));
     mode = 2;
     return true;
 }
@@ -530,7 +538,9 @@ void hy_batch::launch(bool prop, const dev::run_args &R)
 {
     HY_CUDA_CHECK(cudaMemsetAsync(d_counter, 0, sizeof(unsigned int), stream));
     if (mode == 2) {
-        (prop ? cv->prop : cv->step)<<<c_grid, c_threads, c_smem, stream>>>(prog, d_blob, view(), R, d_gscratch);
+        dev::run_args R2 = R;
+        R2.coef_scratch = d_cscratch;
+        (prop ? cv->prop : cv->step)<<<c_grid, c_threads, c_smem, stream>>>(prog, d_blob, view(), R2, d_gscratch);
     } else if (prop) {
         dev::k_hbm<true><<<h_grid, h_threads, 0, stream>>>(prog, view(), R, d_scratch, slab_doubles);
     } else {

@@ -43,6 +43,9 @@ struct run_args {
     int write_tc;
     run_flags *flags;
     unsigned int *counter;
+    // Cooperative kernels: private per-warp store for the state variables' coefficients (used instead of the
+    // public tc array when write_tc == 0), (order + 1) * n_eq * L doubles per warp; nullptr = always use tc.
+    double *coef_scratch;
 };
 
 // ================================================================================================
@@ -466,24 +469,39 @@ struct coop_smem {
     }
 };
 
-// Writes of state-variable coefficients: into the tape row and, streamed, into tc.
+// Where the state variables' coefficients of the current step go (they are needed once more, for the step size
+// and the state update): the public tc array, [(sv * (p + 1) + o) * batch + lane], when the caller asked for it
+// (write_tc), otherwise a private per-warp store [(o * n_eq + sv) * L + l] that stays in L2 and is read back with
+// contiguous accesses. One addressing formula serves both: base + sv * stride_sv + o * stride_o + lane offset.
+struct coef_view {
+    double *base;
+    std::size_t stride_sv, stride_o;
+    bool pub;
+    __device__ __forceinline__ std::size_t lane_off(std::uint32_t glane, std::uint32_t l) const
+    {
+        return pub ? glane : l;
+    }
+};
+
+// Writes of state-variable coefficients: into the tape row and, streamed, into the coefficient store.
 template <int L, int N>
 struct sv_writer {
     const smem_tape<L, N> &t;
-    double *tc;
+    coef_view cv;
     const std::uint32_t *svout;
     const double *rcp;
-    std::uint32_t pp1, n_batch, p;
+    std::uint32_t p;
+    std::size_t loff[N]; // lane offsets into the coefficient store
     bool lane_ok[N];
 
-    // Stream the coefficient of state variable sv at order n to tc (valid lanes only).
+    // Stream the coefficient of state variable sv at order n (valid lanes only).
     __device__ __forceinline__ void write_tc(std::uint32_t sv, std::uint32_t n, const vd<N> &v) const
     {
-        double *dst = tc + (static_cast<std::size_t>(sv) * pp1 + n) * n_batch;
+        double *dst = cv.base + sv * cv.stride_sv + n * cv.stride_o;
 #pragma unroll
         for (int i = 0; i < N; ++i) {
             if (lane_ok[i]) {
-                dst[t.glane[i]] = v.v[i];
+                dst[loff[i]] = v.v[i];
             }
         }
     }
@@ -518,7 +536,7 @@ struct sv_writer {
 template <int L, int N, int MODE>
 __device__ __forceinline__ void coop_jet(const program &P, const coop_header &H, const std::uint32_t *tab,
                                          const batch &D, const coop_smem<L> &S, std::uint32_t lane0, double *gtape,
-                                         std::uint32_t tm_r2)
+                                         std::uint32_t tm_r2, const coef_view &cv)
 {
     constexpr bool GEN = MODE == 1;
     constexpr std::uint32_t G = L / N; // lane groups per warp
@@ -550,11 +568,13 @@ __device__ __forceinline__ void coop_jet(const program &P, const coop_header &H,
         t.glane[i] = lane_ok[i] ? l : D.n - 1u;
         t.tm.v[i] = S.time[g * N + i];
     }
-    const sv_writer<L, N> sv_out{t, D.tc, svout, rcp, pp1, D.n, p, {}};
+    sv_writer<L, N> sv_out_{t, cv, svout, rcp, p, {}, {}};
 #pragma unroll
     for (int i = 0; i < N; ++i) {
-        const_cast<bool &>(sv_out.lane_ok[i]) = lane_ok[i];
+        sv_out_.lane_ok[i] = lane_ok[i];
+        sv_out_.loff[i] = cv.lane_off(t.glane[i], g * N + i);
     }
+    const sv_writer<L, N> &sv_out = sv_out_;
     const auto write_tc = [&](std::uint32_t sv, std::uint32_t n, const vd<N> &v) { sv_out.write_tc(sv, n, v); };
 
     // Order 0 of the state variables: the state itself; order 1 of those that derive from another state
@@ -650,20 +670,20 @@ __device__ __forceinline__ void coop_jet(const program &P, const coop_header &H,
 // The sequential reference loop m = (m < |x|) ? |x| : m, started from |x_0|, yields NaN iff x_0 is NaN and
 // ignores every other NaN: that is fmax() over all the elements plus a check of the first one.
 template <int L>
-__device__ __forceinline__ double coop_determine_h(const program &P, const batch &D, std::uint32_t lane0,
-                                                   double max_delta_t)
+__device__ __forceinline__ double coop_determine_h(const program &P, const batch &D, const coef_view &cv,
+                                                   std::uint32_t lane0, double max_delta_t)
 {
     const std::uint32_t tid = threadIdx.x & 31u, l = tid % L;
-    const std::uint32_t pp1 = P.order + 1u, p = P.order;
-    const std::size_t n = D.n;
+    const std::uint32_t p = P.order;
     const std::uint32_t glane = lane0 + l < D.n ? lane0 + l : D.n - 1u;
-    const double *tc = D.tc + glane;
+    const double *tc = cv.base + cv.lane_off(glane, l);
+    const std::size_t so = cv.stride_o;
     double m0 = 0., mp = 0., mp1 = 0.;
     for (std::uint32_t sv = tid / L; sv < P.n_eq; sv += 32u / L) {
-        const double *c = tc + static_cast<std::size_t>(sv) * pp1 * n;
+        const double *c = tc + sv * cv.stride_sv;
         m0 = fmax(m0, fabs(c[0]));
-        mp = fmax(mp, fabs(c[static_cast<std::size_t>(p) * n]));
-        mp1 = fmax(mp1, fabs(c[static_cast<std::size_t>(p - 1u) * n]));
+        mp = fmax(mp, fabs(c[p * so]));
+        mp1 = fmax(mp1, fabs(c[(p - 1u) * so]));
     }
 #pragma unroll
     for (std::uint32_t off = 16u; off >= L; off >>= 1) {
@@ -674,8 +694,7 @@ __device__ __forceinline__ double coop_determine_h(const program &P, const batch
     double h = 0.;
     if (tid < L) {
         // (tid < L: this thread handled state variable 0 of its lane.)
-        const double f0 = fabs(tc[0]), fp = fabs(tc[static_cast<std::size_t>(p) * n]),
-                     fp1 = fabs(tc[static_cast<std::size_t>(p - 1u) * n]);
+        const double f0 = fabs(tc[0]), fp = fabs(tc[p * so]), fp1 = fabs(tc[(p - 1u) * so]);
         h = h_from_norms(P, isnan(f0) ? f0 : m0, isnan(fp) ? fp : mp, isnan(fp1) ? fp1 : mp1, max_delta_t);
     }
     return h;
@@ -686,10 +705,10 @@ __device__ __forceinline__ double coop_determine_h(const program &P, const batch
 // A thread evaluates up to three polynomials side by side (their coefficients come from L2).
 template <int L>
 __device__ __forceinline__ void coop_update_state(const program &P, const batch &D, const coop_smem<L> &S,
-                                                  std::uint32_t lane0, unsigned &nf_mask)
+                                                  const coef_view &cv, std::uint32_t lane0, unsigned &nf_mask)
 {
     constexpr int K = 3;
-    const std::uint32_t pp1 = P.order + 1u, tid = threadIdx.x & 31u;
+    const std::uint32_t tid = threadIdx.x & 31u;
     const std::uint32_t l = tid % L, n_items = P.n_eq * L;
     const std::uint32_t glane_raw = lane0 + l;
     const bool lane_active = glane_raw < D.n && S.running[l] != 0;
@@ -704,10 +723,10 @@ __device__ __forceinline__ void coop_update_state(const program &P, const batch 
             const std::uint32_t it = base + 32u * static_cast<std::uint32_t>(k);
             act[k] = it < n_items;
             const std::uint32_t sv = act[k] ? it / L : 0u;
-            c[k] = D.tc + static_cast<std::size_t>(sv) * pp1 * n + glane;
+            c[k] = cv.base + sv * cv.stride_sv + cv.lane_off(glane, l);
         }
         double res[K];
-        eval_poly_k<K>(P, c, n, h, res);
+        eval_poly_k<K>(P, c, cv.stride_o, h, res);
 #pragma unroll
         for (int k = 0; k < K; ++k) {
             if (act[k] && lane_active) {
@@ -768,6 +787,16 @@ __global__ void __launch_bounds__(MAXT, 1)
                                     * (static_cast<std::size_t>(H.n_gslots) * L)
                         : nullptr;
 
+    // Coefficient store: public tc or the warp's private slice (see coef_view).
+    const std::uint32_t pp1_ = P.order + 1u;
+    const bool cv_pub = R.write_tc != 0 || R.coef_scratch == nullptr;
+    const coef_view cv{cv_pub ? D.tc
+                              : R.coef_scratch
+                                    + ((static_cast<std::size_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5)
+                                          * (static_cast<std::size_t>(pp1_) * P.n_eq * L),
+                       cv_pub ? static_cast<std::size_t>(pp1_) * D.n : static_cast<std::size_t>(L),
+                       cv_pub ? static_cast<std::size_t>(D.n) : static_cast<std::size_t>(P.n_eq) * L, cv_pub};
+
     for (std::uint32_t chunk = claim_chunk_warp(R.counter); chunk < n_chunks; chunk = claim_chunk_warp(R.counter)) {
         const std::uint32_t lane0 = chunk * L;
         // Owner threads (one per lane) do the scalar bookkeeping of their lane.
@@ -785,14 +814,14 @@ __global__ void __launch_bounds__(MAXT, 1)
                 S.running[tid] = 1;
             }
             __syncwarp();
-            coop_jet<L, N, MODE>(P, H, tab, D, S, lane0, gtape, tm_r2);
-            const double h = coop_determine_h<L>(P, D, lane0, mdt);
+            coop_jet<L, N, MODE>(P, H, tab, D, S, lane0, gtape, tm_r2, cv);
+            const double h = coop_determine_h<L>(P, D, cv, lane0, mdt);
             if (owner) {
                 S.h[tid] = h;
             }
             __syncwarp();
             unsigned nf_mask = 0u;
-            coop_update_state<L>(P, D, S, lane0, nf_mask);
+            coop_update_state<L>(P, D, S, cv, lane0, nf_mask);
             nf_mask = __reduce_or_sync(0xffffffffu, nf_mask);
             if (valid) {
                 const dfl nt = dfl_add(t0, dfl{h, 0.});
@@ -817,14 +846,14 @@ __global__ void __launch_bounds__(MAXT, 1)
                     S.running[tid] = lp.running ? 1 : 0;
                 }
                 __syncwarp();
-                coop_jet<L, N, MODE>(P, H, tab, D, S, lane0, gtape, tm_r2);
-                const double h = coop_determine_h<L>(P, D, lane0, cur_max);
+                coop_jet<L, N, MODE>(P, H, tab, D, S, lane0, gtape, tm_r2, cv);
+                const double h = coop_determine_h<L>(P, D, cv, lane0, cur_max);
                 if (owner) {
                     S.h[tid] = h;
                 }
                 __syncwarp();
                 unsigned nf_mask = 0u;
-                coop_update_state<L>(P, D, S, lane0, nf_mask);
+                coop_update_state<L>(P, D, S, cv, lane0, nf_mask);
                 nf_mask = __reduce_or_sync(0xffffffffu, nf_mask);
                 if (owner && lp.running) {
                     lp.advance(h, cur_max, ((nf_mask >> tid) & 1u) != 0u, R, valid);
