@@ -577,6 +577,31 @@ __device__ __forceinline__ void coop_jet(const program &P, const coop_header &H,
     const sv_writer<L, N> &sv_out = sv_out_;
     const auto write_tc = [&](std::uint32_t sv, std::uint32_t n, const vd<N> &v) { sv_out.write_tc(sv, n, v); };
 
+    // Tensor-memory modes run the pair level with one pair interaction per thread (N lanes each); the levels after
+    // it (sums of the pairs' outputs, a handful of items) are run with NS >= N lanes per thread, so that e.g. the
+    // 18 sums x 2 lanes of the 6-body system are one round of 18 threads instead of 32 + 4. A slot holds the L
+    // lanes of the warp contiguously, so the two views of the tape differ only in the lanes a thread touches.
+    constexpr int NS = (MODE >= 2 && N == 1 && L >= 2) ? 2 : N;
+    constexpr std::uint32_t GS = L / NS;
+    smem_tape<L, NS> ts;
+    const std::uint32_t gs = tid % GS;
+    ts.base = S.tape + gs * NS;
+    ts.gbase = nullptr;
+    ts.args = t.args;
+    ts.consts = t.consts;
+    ts.pars = D.pars;
+    ts.batch = D.n;
+    sv_writer<L, NS> sv_out_s_{ts, cv, svout, rcp, p, {}, {}};
+#pragma unroll
+    for (int i = 0; i < NS; ++i) {
+        const std::uint32_t l = lane0 + gs * NS + i;
+        sv_out_s_.lane_ok[i] = l < D.n;
+        ts.glane[i] = l < D.n ? l : D.n - 1u;
+        ts.tm.v[i] = S.time[gs * NS + i];
+        sv_out_s_.loff[i] = cv.lane_off(ts.glane[i], gs * NS + i);
+    }
+    const sv_writer<L, NS> &sv_out_s = sv_out_s_;
+
     // Order 0 of the state variables: the state itself; order 1 of those that derive from another state
     // variable (x^[1] = v^[0]). (it % G == g because nthr is a multiple of G.)
     for (std::uint32_t it = tid; it < P.n_eq * G; it += nthr) {
@@ -631,6 +656,18 @@ __device__ __forceinline__ void coop_jet(const program &P, const coop_header &H,
                     __syncwarp();
                     continue;
                 }
+                // The other levels of a superinstruction-only program: sums of single-slot rows.
+                for (std::uint32_t it = tid; it < (e - b) * GS; it += nthr) {
+                    const std::uint32_t k = b + it / GS;
+                    const uint4 op = ops[2u * k], op2 = ops[2u * k + 1u];
+                    const vd<NS> v = sum_single_slot<NS>(ts, op.y, op.z);
+                    ts.row(op2.x).set(n, v);
+                    if (op2.y != 0u) {
+                        sv_out_s(op2.y, v, n);
+                    }
+                }
+                __syncwarp();
+                continue;
             }
             for (std::uint32_t it = tid; it < (e - b) * G; it += nthr) {
                 const std::uint32_t k = b + it / G;
