@@ -539,7 +539,13 @@ void hy_batch::launch(bool prop, const dev::run_args &R)
     HY_CUDA_CHECK(cudaMemsetAsync(d_counter, 0, sizeof(unsigned int), stream));
     if (mode == 2) {
         dev::run_args R2 = R;
-        R2.coef_scratch = d_cscratch;
+        const bool pub = R.write_tc != 0 || d_cscratch == nullptr;
+        const auto lanes = static_cast<unsigned long long>(cv->L);
+        R2.coef_pub = pub ? 1 : 0;
+        R2.coef_base = pub ? d_tc : d_cscratch;
+        R2.coef_warp_stride = pub ? 0ull : static_cast<unsigned long long>(order + 1u) * n_eq * lanes;
+        R2.coef_stride_sv = pub ? static_cast<unsigned long long>(order + 1u) * n : lanes;
+        R2.coef_stride_o = pub ? static_cast<unsigned long long>(n) : static_cast<unsigned long long>(n_eq) * lanes;
         (prop ? cv->prop : cv->step)<<<c_grid, c_threads, c_smem, stream>>>(prog, d_blob, view(), R2, d_gscratch);
     } else if (prop) {
         dev::k_hbm<true><<<h_grid, h_threads, 0, stream>>>(prog, view(), R, d_scratch, slab_doubles);

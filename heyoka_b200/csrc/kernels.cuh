@@ -43,9 +43,12 @@ struct run_args {
     int write_tc;
     run_flags *flags;
     unsigned int *counter;
-    // Cooperative kernels: private per-warp store for the state variables' coefficients (used instead of the
-    // public tc array when write_tc == 0), (order + 1) * n_eq * L doubles per warp; nullptr = always use tc.
-    double *coef_scratch;
+    // Cooperative kernels: where the state variables' coefficients of the current step go (dev::coef_view). Either
+    // the public tc array (coef_pub = 1, warp stride 0) or a private store of coef_warp_stride doubles per warp,
+    // used when write_tc == 0. Filled in by hy_batch::launch().
+    double *coef_base;
+    unsigned long long coef_warp_stride, coef_stride_sv, coef_stride_o;
+    int coef_pub;
 };
 
 // ================================================================================================
@@ -824,15 +827,11 @@ __global__ void __launch_bounds__(MAXT, 1)
                                     * (static_cast<std::size_t>(H.n_gslots) * L)
                         : nullptr;
 
-    // Coefficient store: public tc or the warp's private slice (see coef_view).
-    const std::uint32_t pp1_ = P.order + 1u;
-    const bool cv_pub = R.write_tc != 0 || R.coef_scratch == nullptr;
-    const coef_view cv{cv_pub ? D.tc
-                              : R.coef_scratch
-                                    + ((static_cast<std::size_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5)
-                                          * (static_cast<std::size_t>(pp1_) * P.n_eq * L),
-                       cv_pub ? static_cast<std::size_t>(pp1_) * D.n : static_cast<std::size_t>(L),
-                       cv_pub ? static_cast<std::size_t>(D.n) : static_cast<std::size_t>(P.n_eq) * L, cv_pub};
+    // Coefficient store: public tc or the warp's private slice (see coef_view; strides precomputed by the host).
+    const coef_view cv{R.coef_base
+                           + ((static_cast<std::size_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5) * R.coef_warp_stride,
+                       static_cast<std::size_t>(R.coef_stride_sv), static_cast<std::size_t>(R.coef_stride_o),
+                       R.coef_pub != 0};
 
     for (std::uint32_t chunk = claim_chunk_warp(R.counter); chunk < n_chunks; chunk = claim_chunk_warp(R.counter)) {
         const std::uint32_t lane0 = chunk * L;
