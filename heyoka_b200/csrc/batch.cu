@@ -192,6 +192,7 @@ struct hy_batch {
     bool opt_tmem = true, allow_tmem = true;
     std::uint32_t opt_tmem_rows = 0; // 0: automatic, 2 / 3: forced (HEYOKA_B200_TMEM_ROWS)
     void replan(bool spill, std::uint32_t tmem_max_pairs = 0, std::uint32_t tmem_rows = 2);
+    void ensure_tc();
 
     // Resident arrays.
     double *d_state = nullptr, *d_pars = nullptr, *d_t_hi = nullptr, *d_t_lo = nullptr, *d_last_h = nullptr,
@@ -323,6 +324,15 @@ void hy_batch::setup_hbm(std::uint32_t threads, std::uint32_t blocks_per_sm)
         d_scratch = nullptr;
     }
     slab_doubles = static_cast<std::size_t>(n_uvars) * (order + 1u) * 32u;
+    // The slabs of the resident warps must fit in (half of the free) device memory: large systems (model::ffnn
+    // 3 x 64: 43 MB per warp) run with fewer resident blocks rather than failing to allocate.
+    {
+        std::size_t free_b = 0, total_b = 0;
+        HY_CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
+        const std::size_t per_block = static_cast<std::size_t>(warps_per_block) * slab_doubles * sizeof(double);
+        const std::size_t max_blocks = std::max<std::size_t>(free_b / 2u / std::max<std::size_t>(per_block, 1u), 1u);
+        h_grid = static_cast<std::uint32_t>(std::min<std::size_t>(h_grid, max_blocks));
+    }
     d_scratch = dalloc<double>(static_cast<std::size_t>(h_grid) * warps_per_block * slab_doubles);
     mode = 1;
 }
@@ -534,8 +544,23 @@ void hy_batch::configure(int want_mode, int L, int N, std::uint32_t threads, std
     setup_hbm(threads, blocks_per_sm);
 }
 
+// The public Taylor-coefficient array, [n_eq][order + 1][batch] (src/taylor_00.cpp:574-580), is allocated the first
+// time something needs it (write_tc, dense output, hy_batch_get_ptrs()): 6-body, 2^20 lanes: 6.3 GB; the
+// cooperative kernels keep the coefficients of the current step in a private per-warp store otherwise.
+void hy_batch::ensure_tc()
+{
+    if (d_tc == nullptr) {
+        const std::size_t sz = static_cast<std::size_t>(n_eq) * (order + 1u) * n;
+        d_tc = dalloc<double>(sz);
+        HY_CUDA_CHECK(cudaMemsetAsync(d_tc, 0, sizeof(double) * sz, stream));
+    }
+}
+
 void hy_batch::launch(bool prop, const dev::run_args &R)
 {
+    if (R.write_tc != 0 || (mode == 2 && d_cscratch == nullptr)) {
+        ensure_tc();
+    }
     HY_CUDA_CHECK(cudaMemsetAsync(d_counter, 0, sizeof(unsigned int), stream));
     if (mode == 2) {
         dev::run_args R2 = R;
@@ -753,7 +778,6 @@ int hy_batch_create(const hy_program *p, uint32_t batch, int device, hy_batch **
         b->d_t_hi = b->dalloc<double>(n);
         b->d_t_lo = b->dalloc<double>(n);
         b->d_last_h = b->dalloc<double>(n);
-        b->d_tc = b->dalloc<double>(tc_size);
         b->d_d_out = b->dalloc<double>(n * p->n_eq);
         b->d_step_outcome = b->dalloc<long long>(n);
         b->d_prop_outcome = b->dalloc<long long>(n);
@@ -770,7 +794,6 @@ int hy_batch_create(const hy_program *p, uint32_t batch, int device, hy_batch **
         HY_CUDA_CHECK(cudaMemset(b->d_t_hi, 0, sizeof(double) * n));
         HY_CUDA_CHECK(cudaMemset(b->d_t_lo, 0, sizeof(double) * n));
         HY_CUDA_CHECK(cudaMemset(b->d_last_h, 0, sizeof(double) * n));
-        HY_CUDA_CHECK(cudaMemset(b->d_tc, 0, sizeof(double) * tc_size));
 
         // Kernel selection: HEYOKA_B200_TAPE = hbm | smem overrides the automatic choice.
         int want = 0;
@@ -974,6 +997,7 @@ int hy_batch_download_tc(hy_batch *b, double *tc)
     try {
         device_guard guard(b->device);
         const std::size_t sz = static_cast<std::size_t>(b->n_eq) * (b->order + 1u) * b->n;
+        b->ensure_tc();
         HY_CUDA_CHECK(cudaMemcpyAsync(tc, b->d_tc, sizeof(double) * sz, cudaMemcpyDeviceToHost, b->stream));
         HY_CUDA_CHECK(cudaStreamSynchronize(b->stream));
         return HY_OK;
@@ -993,7 +1017,7 @@ int hy_batch_get_ptrs(hy_batch *b, hy_batch_ptrs *out)
     out->t_hi = b->d_t_hi;
     out->t_lo = b->d_t_lo;
     out->last_h = b->d_last_h;
-    out->tc = b->d_tc;
+    out->tc = b->d_tc; // null until a step with write_tc / a dense output has been requested
     out->d_out = b->d_d_out;
     out->step_outcome = reinterpret_cast<int64_t *>(b->d_step_outcome);
     out->prop_outcome = reinterpret_cast<int64_t *>(b->d_prop_outcome);
@@ -1286,6 +1310,7 @@ int hy_batch_d_output(hy_batch *b, const double *tau, double *out)
     try {
         device_guard guard(b->device);
         const double *d_tau = stage(b, tau, 0, 0);
+        b->ensure_tc();
         dev::k_d_output<<<(b->n + 127u) / 128u, 128, 0, b->stream>>>(b->prog, b->n, b->d_tc, d_tau, b->d_d_out);
         HY_CUDA_CHECK(cudaGetLastError());
         ++b->n_launches;

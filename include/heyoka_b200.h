@@ -202,7 +202,8 @@ int hy_batch_download_step_res(hy_batch *, int64_t *outcome, double *h);
 int hy_batch_download_prop_res(hy_batch *, int64_t *outcome, double *min_h, double *max_h, uint64_t *n_steps);
 int hy_batch_download_tc(hy_batch *, double *tc /* n_eq * (order + 1) * batch */);
 
-/* Device pointers of the resident arrays, for zero-copy use (torch / NCCL gathers). */
+/* Device pointers of the resident arrays, for zero-copy use (torch / NCCL gathers). tc is allocated lazily
+ * (first step / propagate with write_tc, hy_batch_download_tc(), hy_batch_d_output()) and NULL before that. */
 typedef struct hy_batch_ptrs {
     double *state, *pars, *t_hi, *t_lo, *last_h, *tc, *d_out;
     int64_t *step_outcome;

@@ -130,3 +130,61 @@ def kep_to_cart(a, e, inc, om, Om, nu, mu):
     pos = R @ np.array([x_p, y_p])
     vel = R @ np.array([vx_p, vy_p])
     return pos, vel
+
+
+# ---- BASELINE.json configs[2]: model::nbody N = 32 (SURVEY.md 8(d) "N32") ----
+N32_MASSES = np.array([1.0] + [1e-4 * (1 + i / 32.0) for i in range(1, 32)])
+
+
+def sys_nbody32():
+    return hb.model.nbody(32, masses=N32_MASSES, Gconst=1.0)
+
+
+def nbody32_batch_state(batch, seed=1234):
+    """Planets on a = 1 + 0.5 i, e ~ U(0, 0.05), inc ~ U(0, 0.05), angles ~ U(0, 2 pi) (the formulas of
+    kep_to_cart(), vectorised over the planets); the star is placed so that the centre of mass is at rest at the
+    origin. One generator per lane (seed + lane)."""
+    st = np.zeros((32 * 6, batch))
+    a = 1.0 + 0.5 * np.arange(1, 32)
+    mu = 1.0 + N32_MASSES[1:]
+    for lane in range(batch):
+        rng = np.random.default_rng(seed + lane)
+        e, inc = rng.uniform(0, 0.05, 31), rng.uniform(0, 0.05, 31)
+        om, Om, nu = rng.uniform(0, 2 * np.pi, (3, 31))
+        p = a * (1 - e * e)
+        r = p / (1 + e * np.cos(nu))
+        xp, yp = r * np.cos(nu), r * np.sin(nu)
+        h = np.sqrt(mu * p)
+        vxp, vyp = -mu / h * np.sin(nu), mu / h * (e + np.cos(nu))
+        cO, sO, co, so, ci, si = np.cos(Om), np.sin(Om), np.cos(om), np.sin(om), np.cos(inc), np.sin(inc)
+        R = np.array([[cO * co - sO * so * ci, -cO * so - sO * co * ci], [sO * co + cO * so * ci, -sO * so + cO * co * ci],
+                      [so * si, co * si]])  # [3, 2, planets]
+        pos = R[:, 0] * xp + R[:, 1] * yp
+        vel = R[:, 0] * vxp + R[:, 1] * vyp
+        body = st[6:, lane].reshape(31, 6)
+        body[:, :3] = pos.T
+        body[:, 3:] = vel.T
+        st[6:, lane] = body.reshape(-1)
+        for k in range(6):
+            st[k, lane] = -np.sum(N32_MASSES[1:] * st[6 + k::6, lane]) / N32_MASSES[0]
+    return st
+
+
+# ---- BASELINE.json configs[4]: model::ffnn right-hand side, 3 x 64 tanh (SURVEY.md 8(d) "NN") ----
+FFNN_TOL = 1e-12  # -> order 15
+
+
+def sys_ffnn(seed=11):
+    """x' = ffnn(x): 4 inputs, hidden layers {64, 64, 64} with tanh, 4 linear outputs; weights and biases are numbers
+    ~ N(0, 1 / fan_in) in the layout of src/model/ffnn.cpp:75-78 ([W01, W12, W23, W34 | b1..b4], row-major)."""
+    rng = np.random.default_rng(seed)
+    sizes = [4, 64, 64, 64, 4]
+    w = [rng.normal(0, 1 / np.sqrt(sizes[i]), sizes[i] * sizes[i + 1]) for i in range(4)]
+    b = [rng.normal(0, 0.1, sizes[i + 1]) for i in range(4)]
+    xs = hb.make_vars("x0", "x1", "x2", "x3")
+    out = hb.model.ffnn(list(xs), [64, 64, 64], 4, ["tanh", "tanh", "tanh", "identity"], nn_wb=np.concatenate(w + b))
+    return [(xs[i], out[i]) for i in range(4)]
+
+
+def ffnn_batch_state(batch, seed=13):
+    return np.random.default_rng(seed).uniform(-1, 1, (4, batch))

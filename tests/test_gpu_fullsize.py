@@ -80,3 +80,61 @@ def test_outer_ss_2pow20_energy_and_sample():
     o.propagate_until(5.0)
     assert np.array_equal(o.n_steps, ns[idx])
     assert nbody_rel_err(new[:, idx], o.state) < 1e-12
+
+
+def test_nbody32_shard_8192_energy_and_sample():
+    """model::nbody N = 32, 65,536 ICs sharded over 8 GPUs = 8192 lanes per GPU (BASELINE.json configs[2]); the tape
+    (6624 u variables x 21 orders per lane) lives in HBM. Energy conservation and exact landing on t_final for every
+    lane, a random sample of lanes against the oracle (identical step counts)."""
+    from common import N32_MASSES, nbody32_batch_state, sys_nbody32
+    batch, t_final = 8192, 1.0
+    st = nbody32_batch_state(batch)
+    P = hb.Program(sys_nbody32())
+    b = hb.Batch(P, batch)
+    assert b.kernel_info()["tape"] == "hbm"
+    b.upload(st, None, np.zeros(batch), np.zeros(batch))
+    b.propagate_until(np.full(batch, t_final))
+    new, t_hi, t_lo, _ = b.download()
+    oc, min_h, max_h, ns = b.prop_res()
+    assert np.all(oc == hb.taylor_outcome.time_limit) and np.all(t_hi == t_final) and np.all(np.abs(t_lo) < 1e-15)
+    # (Random phases: a few lanes start with two planets close to each other and need hundreds of steps.)
+    assert ns.min() >= 1 and ns.max() <= 5000
+    e0, e1 = nbody_energy(st, N32_MASSES, 1.0), nbody_energy(new, N32_MASSES, 1.0)
+    de = np.abs(e1 / e0 - 1)
+    # (The close-encounter lanes lose digits in the potential energy itself: bounded separately.)
+    assert np.median(de) < 1e-14 and np.quantile(de, 0.99) < 1e-13 and np.max(de) < 1e-9
+    # Every lane against the oracle's 8-lane port for the step counts, a sample for the states.
+    o = oracle.OracleIntegrator(P, st, batch, mode=oracle.FMA, width=8)
+    o.propagate_until(t_final, lockstep=False, n_threads=8)
+    assert np.array_equal(ns, o.n_steps)
+    idx = np.random.default_rng(1).choice(batch, 64, replace=False)
+    assert nbody_rel_err(new[:, idx], o.state[:, idx]) < 1e-12
+
+
+def test_ffnn_262144_step_and_sample():
+    """model::ffnn right-hand side (3 x 64 tanh, order 15), 262,144 lanes (BASELINE.json configs[4]): 10476 u
+    variables per lane, tape in HBM. One step and a short propagation; every lane lands on t_final; a random sample
+    of lanes against the oracle."""
+    from common import FFNN_TOL, ffnn_batch_state, sys_ffnn
+    batch = 1 << 18
+    st = ffnn_batch_state(batch)
+    P = hb.Program(sys_ffnn(), tol=FFNN_TOL)
+    b = hb.Batch(P, batch)
+    b.upload(st, None, np.zeros(batch), np.zeros(batch))
+    b.step()
+    new, t_hi, _, h = b.download()
+    oc, _ = b.step_res()
+    assert np.all(oc == hb.taylor_outcome.success) and np.array_equal(t_hi, h) and np.all(h > 0)
+    idx = np.random.default_rng(2).choice(batch, 32, replace=False)
+    o = oracle.OracleIntegrator(P, st[:, idx], 32, mode=oracle.FMA)
+    o.step()
+    assert np.max(np.abs(o.last_h / h[idx] - 1)) < 1e-11
+    assert np.max(np.abs(o.state - new[:, idx])) < 1e-13
+    b.propagate_until(np.full(batch, 0.5))
+    new, t_hi, t_lo, _ = b.download()
+    oc, _, _, ns = b.prop_res()
+    assert np.all(oc == hb.taylor_outcome.time_limit) and np.all(t_hi == 0.5) and np.all(np.abs(t_lo) < 1e-15)
+    assert np.all(np.isfinite(new))
+    o.propagate_until(0.5)
+    assert np.array_equal(ns[idx], o.n_steps)
+    assert np.max(np.abs(o.state - new[:, idx])) < 1e-12

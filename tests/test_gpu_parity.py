@@ -423,3 +423,51 @@ def test_propagate_grid_limits_match_oracle(kernel):
         assert [r[0] for r in ta.propagate_res] == [int(x) for x in o.prop_outcome], kw
         assert [r[3] for r in ta.propagate_res] == [int(x) for x in o.n_steps], kw
         assert np.array_equal(ta.time, o.t_hi)
+
+
+# ---- BASELINE.json configs[2] and [4] at oracle-sized batches (the tape of these systems lives in HBM) ----
+
+@pytest.mark.gpu
+def test_nbody32_parity():
+    """model::nbody N = 32 (496 pair interactions, ~0.5 MB of tape per lane): a step and a short propagation
+    against the oracle; identical step counts."""
+    from common import nbody32_batch_state, sys_nbody32
+    batch = 8
+    st = nbody32_batch_state(batch)
+    P = hb.Program(sys_nbody32(), high_accuracy=False)
+    assert (P.n_eq, P.order) == (192, 20)
+    ta = hb.taylor_adaptive_batch(sys_nbody32(), st, batch)
+    assert ta._b.kernel_info()["tape"] == "hbm"
+    o = oracle.OracleIntegrator(P, st, batch, mode=oracle.FMA)
+    ta.step(write_tc=True)
+    o.step(write_tc=True)
+    assert np.max(np.abs(ta.last_h / o.last_h - 1)) < 1e-12
+    assert lane_err(ta.state, o.state) < 1e-13
+    assert tc_err(ta.tc, o.tc, o.last_h) < 1e-12
+    ta.propagate_until(1.5)
+    o.propagate_until(1.5)
+    assert [r[3] for r in ta.propagate_res] == [int(s) for s in o.n_steps]
+    assert np.array_equal(ta.time, o.t_hi)
+    assert lane_err(ta.state, o.state) < 1e-12
+
+
+@pytest.mark.gpu
+def test_ffnn_parity():
+    """model::ffnn right-hand side (3 x 64 tanh, order 15): 10476 u variables per lane, sums of 64 products, tanh
+    recurrences; a step and propagate_until(1) against the oracle; identical step counts."""
+    from common import FFNN_TOL, ffnn_batch_state, sys_ffnn
+    batch = 16
+    st = ffnn_batch_state(batch)
+    P = hb.Program(sys_ffnn(), tol=FFNN_TOL)
+    assert (P.n_eq, P.order) == (4, 15)
+    ta = hb.taylor_adaptive_batch(sys_ffnn(), st, batch, tol=FFNN_TOL)
+    o = oracle.OracleIntegrator(P, st, batch, mode=oracle.FMA)
+    ta.step(write_tc=True)
+    o.step(write_tc=True)
+    assert np.max(np.abs(ta.last_h / o.last_h - 1)) < 1e-11
+    assert lane_err(ta.state, o.state) < 1e-13
+    assert tc_err(ta.tc, o.tc, o.last_h) < 1e-12
+    ta.propagate_until(1.0)
+    o.propagate_until(1.0)
+    assert [r[3] for r in ta.propagate_res] == [int(s) for s in o.n_steps]
+    assert lane_err(ta.state, o.state) < 1e-12

@@ -1,5 +1,4 @@
 set -x
 mkdir -p gpurun_out
-timeout 300 python bench.py --no-cpu-baseline --steps 3 > gpurun_out/bench_a.json 2> gpurun_out/bench_a.err; cut -c1-200 gpurun_out/bench_a.json
-timeout 1500 python -m pytest tests -m gpu -x -q -k "outer_ss or tutorial or global_exits or fullsize or grid" > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" 
-tail -4 gpurun_out/pytest_gpu.log
+timeout 1500 python -m pytest tests -m gpu -x -q -k "nbody32 or ffnn" --durations=5 > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" 
+tail -25 gpurun_out/pytest_gpu.log
