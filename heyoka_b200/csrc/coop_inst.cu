@@ -24,7 +24,12 @@ namespace
     }
 
 const coop_variant family[] = {
-#if HY_COOP_MODE >= 2 && HY_COOP_N == 1
+#if HY_COOP_MODE == 4 && HY_COOP_N == 1
+    // Tape in global memory: a few lanes per warp.
+    HY_COOP(1), HY_COOP(2), HY_COOP(4)
+#elif HY_COOP_MODE == 4 && HY_COOP_N == 2
+    HY_COOP(2), HY_COOP(4), HY_COOP(8)
+#elif HY_COOP_MODE >= 2 && HY_COOP_N == 1
     // Tensor-memory variants: one pair interaction per thread, hence few lane groups per warp.
     HY_COOP(1), HY_COOP(2), HY_COOP(4)
 #elif HY_COOP_MODE >= 2 && HY_COOP_N == 2

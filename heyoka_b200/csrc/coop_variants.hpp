@@ -21,7 +21,7 @@ using coop_fn = void (*)(dev::program, const std::uint32_t *, dev::batch, dev::r
 
 struct coop_variant {
     int L, N, maxt; // lanes per warp, lanes per thread, maximum threads per CTA
-    int mode;       // 1: handles elementary ops, 0: superinstruction-only programs, 2 / 3: idem + two / three rows per pair interaction in tensor memory
+    int mode;       // 1: handles elementary ops, 0: superinstruction-only programs, 2 / 3: idem + two / three rows per pair interaction in tensor memory, 4: tape in global memory
     coop_fn step, prop;
 };
 
@@ -54,6 +54,8 @@ coop_family coop_family_n2_384_m2();
 coop_family coop_family_n2_384_m3();
 coop_family coop_family_n2_256_m2();
 coop_family coop_family_n2_256_m3();
+coop_family coop_family_n1_512_m4();
+coop_family coop_family_n2_512_m4();
 
 } // namespace heyoka_b200::detail
 

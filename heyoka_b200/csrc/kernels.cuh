@@ -541,7 +541,8 @@ __device__ __forceinline__ void coop_jet(const program &P, const coop_header &H,
                                          const batch &D, const coop_smem<L> &S, std::uint32_t lane0, double *gtape,
                                          std::uint32_t tm_r2, const coef_view &cv)
 {
-    constexpr bool GEN = MODE == 1;
+    constexpr bool GEN = MODE == 1 || MODE == 4;
+    constexpr bool TMEM = MODE == 2 || MODE == 3;
     constexpr std::uint32_t G = L / N; // lane groups per warp
     const std::uint32_t tid = threadIdx.x & 31u;
     constexpr std::uint32_t nthr = 32u;
@@ -584,7 +585,7 @@ __device__ __forceinline__ void coop_jet(const program &P, const coop_header &H,
     // it (sums of the pairs' outputs, a handful of items) are run with NS >= N lanes per thread, so that e.g. the
     // 18 sums x 2 lanes of the 6-body system are one round of 18 threads instead of 32 + 4. A slot holds the L
     // lanes of the warp contiguously, so the two views of the tape differ only in the lanes a thread touches.
-    constexpr int NS = (MODE >= 2 && N == 1 && L >= 2) ? 2 : N;
+    constexpr int NS = (TMEM && N == 1 && L >= 2) ? 2 : N;
     constexpr std::uint32_t GS = L / NS;
     smem_tape<L, NS> ts;
     const std::uint32_t gs = tid % GS;
@@ -650,12 +651,12 @@ __device__ __forceinline__ void coop_jet(const program &P, const coop_header &H,
         // The other u variables, one dependency level at a time.
         for (std::uint32_t s = 0; s < H.n_segments; ++s) {
             const std::uint32_t b = seg[s], e = seg[s + 1u];
-            if constexpr (MODE >= 2) {
+            if constexpr (TMEM) {
                 if (s == 0u) {
                     const std::uint32_t cnt = (e - b) * G;
                     const bool active = tid < cnt;
                     const uint4 op = ops[2u * (b + (active ? tid : cnt - 1u) / G)];
-                    fused_nbody_pair_tmem<N, MODE - 2>(P, t, aux + op.y, op.z, op.w != 0u, n, sv_out, active, tm_r2);
+                    fused_nbody_pair_tmem<N, TMEM ? MODE - 2 : 0>(P, t, aux + op.y, op.z, op.w != 0u, n, sv_out, active, tm_r2);
                     __syncwarp();
                     continue;
                 }
@@ -786,25 +787,33 @@ template <int L, int N, bool PROP, int MAXT, int MODE>
 __global__ void __launch_bounds__(MAXT, 1)
     k_coop(program P, const std::uint32_t *blob, batch D, run_args R, double *gscratch)
 {
+    constexpr bool TMEM = MODE == 2 || MODE == 3;
+    // MODE 4: systems whose compact tape does not fit in shared memory. Same kernel, but the warp's tape lives in
+    // a per-warp slab of global memory (gscratch) and the program tables are read in place (L1 / L2).
+    constexpr bool GLOBAL = MODE == 4;
     extern __shared__ __align__(16) double smem_raw[];
-    // Program tables: global -> shared, once per CTA.
-    std::uint32_t *tab = reinterpret_cast<std::uint32_t *>(smem_raw);
     const std::uint32_t n_words = __ldg(blob);
-    for (std::uint32_t i = threadIdx.x; i < n_words; i += blockDim.x) {
-        tab[i] = __ldg(blob + i);
+    const std::uint32_t *tab = blob;
+    if constexpr (!GLOBAL) {
+        // Program tables: global -> shared, once per CTA.
+        std::uint32_t *stab = reinterpret_cast<std::uint32_t *>(smem_raw);
+        for (std::uint32_t i = threadIdx.x; i < n_words; i += blockDim.x) {
+            stab[i] = __ldg(blob + i);
+        }
+        tab = stab;
     }
     // Tensor memory: warp 0 allocates all the columns; warp w then owns the columns [(w / 4) * cols, ...) of the
     // 32 TMEM lanes of its quadrant w % 4, one TMEM lane per thread (tmem.cuh).
     __shared__ std::uint32_t tm_base_smem;
     std::uint32_t tm_r2 = 0u;
-    if constexpr (MODE >= 2) {
+    if constexpr (TMEM) {
         if ((threadIdx.x >> 5) == 0u) {
             tm::alloc_all(&tm_base_smem);
         }
         tm::fence_before_sync();
     }
     __syncthreads();
-    if constexpr (MODE >= 2) {
+    if constexpr (TMEM) {
         tm::fence_after_sync();
         const std::uint32_t w = threadIdx.x >> 5;
         const std::uint32_t cols_per_warp = static_cast<std::uint32_t>(MODE) * (P.order + 1u) * tm::row<N>::W;
@@ -813,15 +822,18 @@ __global__ void __launch_bounds__(MAXT, 1)
     const coop_header H = *reinterpret_cast<const coop_header *>(tab);
 
     const std::uint32_t tid = threadIdx.x & 31u;
-    // Tables rounded up to 16 bytes, then one region per warp.
+    const std::size_t warp_global = (static_cast<std::size_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    // Shared memory: tables rounded up to 16 bytes, then one region per warp. Global mode: one slab per warp.
     const std::size_t tab_doubles = static_cast<std::size_t>(n_words + 3u) / 4u * 2u;
-    const coop_smem<L> S(smem_raw + tab_doubles
-                             + static_cast<std::size_t>(threadIdx.x >> 5) * coop_smem<L>::warp_doubles(H.n_slots),
+    const coop_smem<L> S(GLOBAL ? gscratch + warp_global * coop_smem<L>::warp_doubles(H.n_slots)
+                                : smem_raw + tab_doubles
+                                      + static_cast<std::size_t>(threadIdx.x >> 5)
+                                            * coop_smem<L>::warp_doubles(H.n_slots),
                          H.n_slots);
     const std::uint32_t n_chunks = (D.n + L - 1u) / L;
     const bool owner = tid < L;
     // The warp's slice of the overflow tape.
-    double *gtape = H.n_gslots != 0u
+    double *gtape = (!GLOBAL && H.n_gslots != 0u)
                         ? gscratch
                               + ((static_cast<std::size_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5)
                                     * (static_cast<std::size_t>(H.n_gslots) * L)
@@ -901,7 +913,7 @@ __global__ void __launch_bounds__(MAXT, 1)
         }
         __syncwarp();
     }
-    if constexpr (MODE >= 2) {
+    if constexpr (TMEM) {
         tm::fence_before_sync();
         __syncthreads();
         if ((threadIdx.x >> 5) == 0u) {

@@ -22,6 +22,7 @@ OC = {"success": hb.taylor_outcome.success, "time_limit": hb.taylor_outcome.time
 # Every parity test runs on both tape strategies and a few cooperative-kernel shapes (see kernels.cuh).
 KERNELS = {
     "hbm": dict(tape="hbm"),
+    "global": dict(tape="global"),  # the cooperative kernel with the tape in global memory
     "smem-auto": dict(tape="smem"),  # tensor memory for the pair interactions where it applies
     "smem-notmem": dict(tape="smem-notmem"),
     "smem-L8N2": dict(tape="smem", lanes_per_warp=8, lanes_per_thread=2),
@@ -307,6 +308,8 @@ def test_kernel_selection_info():
     b.set_kernel("hbm")
     assert b.kernel_info()["tape"] == "hbm"
     big = hb.Batch(hb.Program(hb.model.nbody(32)), 32)
+    assert big.kernel_info()["tape"] == "global"
+    big.set_kernel("hbm")
     assert big.kernel_info()["tape"] == "hbm"
     with pytest.raises(ValueError, match="does not fit in shared memory"):
         big.set_kernel("smem")
@@ -437,7 +440,7 @@ def test_nbody32_parity():
     P = hb.Program(sys_nbody32(), high_accuracy=False)
     assert (P.n_eq, P.order) == (192, 20)
     ta = hb.taylor_adaptive_batch(sys_nbody32(), st, batch)
-    assert ta._b.kernel_info()["tape"] == "hbm"
+    assert ta._b.kernel_info()["tape"] == "global"
     o = oracle.OracleIntegrator(P, st, batch, mode=oracle.FMA)
     ta.step(write_tc=True)
     o.step(write_tc=True)
