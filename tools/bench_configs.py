@@ -1,0 +1,79 @@
+#!/usr/bin/env python3
+"""Informational timings of the other BASELINE.json configurations (they are parity-test cases, not bench lines):
+lane-steps/s of one GPU, device-timed around the C-ABI calls with host buffers already uploaded.
+
+    python tools/bench_configs.py [tb] [n32] [nn] [s6step]
+"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import heyoka_b200 as hb  # noqa: E402
+from common import (FFNN_TOL, ffnn_batch_state, nbody32_batch_state, outer_ss_batch_state, sys_ffnn, sys_nbody32,  # noqa: E402
+                    sys_outer_ss, sys_two_body, two_body_batch_state)
+
+
+def timed(fn, reps=3):
+    fn()
+    ts = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        fn()
+        ts.append(time.perf_counter() - t0)
+    return min(ts)
+
+
+def run(name, P, st, t_final=None, **kernel):
+    batch = st.shape[1]
+    b = hb.Batch(P, batch)
+    if kernel:
+        b.set_kernel(**kernel)
+    z = np.zeros(batch)
+    res = {"config": name, "lanes": batch, "kernel": b.kernel_info()["tape"], "costs": P.costs()}
+
+    def step():
+        b.upload(st, None, z, z)
+        b.sync()
+        t0 = time.perf_counter()
+        if t_final is None:
+            b.step()
+        else:
+            b.propagate_until(np.full(batch, t_final))
+        b.sync()
+        step.dt = time.perf_counter() - t0
+
+    timed(step, reps=2)
+    if t_final is None:
+        n_steps = batch
+    else:
+        n_steps = int(b.prop_res()[3].sum())
+    res.update(seconds=step.dt, lane_steps=n_steps, lane_steps_per_s=n_steps / step.dt,
+               b_tape_gbs=n_steps * P.costs()["b_tape"] / step.dt / 1e9)
+    print(json.dumps(res), flush=True)
+
+
+def main():
+    which = sys.argv[1:] or ["tb", "n32", "nn", "s6step"]
+    if "tb" in which:
+        run("two_body_step_batch 2^24 lanes, one step", hb.Program(sys_two_body()), two_body_batch_state(1 << 24))
+    if "s6step" in which:
+        run("outer_ss 6-body 2^20 lanes, one step", hb.Program(sys_outer_ss(), high_accuracy=True),
+            outer_ss_batch_state(1 << 20))
+    if "n32" in which:
+        st = nbody32_batch_state(8192)
+        run("nbody N=32, 8192 lanes, propagate_until(1)", hb.Program(sys_nbody32()), st, 1.0)
+        run("nbody N=32, 8192 lanes, propagate_until(1), thread-per-lane HBM kernel", hb.Program(sys_nbody32()), st, 1.0,
+            tape="hbm")
+    if "nn" in which:
+        run("ffnn 3x64 tanh order 15, 262144 lanes, propagate_until(0.5)", hb.Program(sys_ffnn(), tol=FFNN_TOL),
+            ffnn_batch_state(1 << 18), 0.5)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,4 +1,3 @@
 set -x
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -m gpu -x -q -k "nbody32 or ffnn or global or kernel_selection" --durations=6 > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" 
-tail -25 gpurun_out/pytest_gpu.log
+timeout 900 python tools/bench_configs.py > gpurun_out/r1_other_configs.jsonl 2> gpurun_out/r1_other_configs.err; cat gpurun_out/r1_other_configs.jsonl | cut -c1-400; tail -3 gpurun_out/r1_other_configs.err
