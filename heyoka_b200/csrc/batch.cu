@@ -425,12 +425,12 @@ bool hy_batch::setup_coop(int L, int N, std::uint32_t threads, std::uint32_t cta
     const auto best_tmem = [&](int lanes, int lanes_per_thread) {
         tm_choice best;
         const std::uint32_t G = static_cast<std::uint32_t>(lanes / lanes_per_thread);
-        if (!(opt_tmem && allow_tmem && lanes_per_thread <= 2 && G != 0u && G <= 32u && opt_spill <= 0
-              && find_variant(lanes, lanes_per_thread, 512, 2) != nullptr)) {
+        if (!(opt_tmem && allow_tmem && lanes_per_thread <= 2 && G != 0u && G <= 32u && opt_spill <= 0)) {
             return best;
         }
         for (const std::uint32_t rows : {2u, 3u}) {
-            if (opt_tmem_rows != 0u && rows != opt_tmem_rows) {
+            if ((opt_tmem_rows != 0u && rows != opt_tmem_rows)
+                || find_variant(lanes, lanes_per_thread, 512, static_cast<int>(rows)) == nullptr) {
                 continue;
             }
             const auto cand = hy::detail::make_smem_plan(*prog_host, opt_fuse, opt_fuse_sv, false, 32u / G, rows);
@@ -446,12 +446,19 @@ bool hy_batch::setup_coop(int L, int N, std::uint32_t threads, std::uint32_t cta
     };
     {
         tm_choice pick = best_tmem(L, N);
-        if (auto_shape) {
-            // The tensor-memory shape of choice: 2 lanes per warp, 1 lane per thread.
-            const auto alt = best_tmem(2, 1);
-            if (alt.warps * 2u > std::max(pick.warps, fit_warps(plan.n_slots, L)) * static_cast<std::size_t>(L)) {
+        if (auto_shape && plan.n_fused != 0u && plan.n_fused <= 32u) {
+            // The tensor-memory shape of choice: 1 lane per thread and as many lanes per warp as give every thread
+            // one pair interaction (15 pairs: 2 lanes, 30 busy threads; 1 pair: 32 lanes). Taken when it puts
+            // more lanes in flight on an SM.
+            int alt_l = 1;
+            while (static_cast<std::uint32_t>(2 * alt_l) * plan.n_fused <= 32u) {
+                alt_l *= 2;
+            }
+            const auto alt = best_tmem(alt_l, 1);
+            if (alt.warps * static_cast<std::size_t>(alt_l)
+                > std::max(pick.warps, fit_warps(plan.n_slots, L)) * static_cast<std::size_t>(L)) {
                 pick = alt;
-                L = 2;
+                L = alt_l;
                 N = 1;
             }
         }

@@ -1,17 +1,21 @@
-// The sm_100a kernels of the batch Taylor integrator. Two storage strategies for the derivative tape:
+// The sm_100a kernels of the batch Taylor integrator.
 //
-// "coop" (shared-memory tape, the fast path): a CTA owns L lanes and keeps their tape in shared memory
-//   ([slot][L] doubles, only what is re-read at later orders keeps its history, see smem_plan.hpp). The
-//   threads of the CTA share the work of every dependency segment: one work item = one u variable x N
-//   adjacent lanes, items of a segment are independent, a __syncthreads() separates segments and orders
-//   (the same structure as the reference's compact mode, src/taylor_02.cpp:1147-1185, with its parallel
-//   mode's idea of spreading a segment over workers, src/taylor_01.cpp:1220-1247). HBM traffic per step is
-//   the state in/out plus the state variables' coefficients streamed to tc. CTAs are persistent and claim
-//   groups of L lanes from an atomic counter; a group runs its whole propagate_until() loop in one go.
+// k_coop (the product path): warp-cooperative. A warp owns L lanes and their compact derivative tape ([slot][L]
+//   doubles; only what is re-read at later orders keeps its history, see smem_plan.hpp). Its 32 threads share the
+//   work of every dependency level: one work item = one u variable (or one superinstruction, fused.cuh) x N
+//   adjacent lanes; items of a level are independent, a __syncwarp() separates levels and orders (the structure of
+//   the reference's compact mode, src/taylor_02.cpp:1147-1185, with its parallel mode's idea of spreading a
+//   segment over workers, src/taylor_01.cpp:1220-1247). Warps are persistent, claim groups of L lanes from an
+//   atomic counter and run a group's whole propagate_until() loop in one go; they never wait for each other.
+//   Where the tape lives is the kernel's MODE:
+//     0 / 1  shared memory (0: superinstruction-only programs, no interpreter of the elementary recurrences);
+//     2 / 3  shared memory + tensor memory for the rows only one thread touches (tmem.cuh);
+//     4      a per-warp slab of global memory, tables read in place (systems too large for shared memory).
+//   HBM traffic per step: the state in and out (the state variables' coefficients go to a private L2-resident
+//   store, or to the public tc array on request).
 //
-// "hbm" (tape in HBM, the fallback for programs whose tape does not fit in shared memory, e.g. N = 32
-//   bodies): one thread per lane, a warp owns 32 consecutive lanes, every access is a coalesced 256-byte
-//   row of the warp's private slab; warps are persistent and claim chunks of 32 lanes.
+// k_hbm (the first kernel of the round, kept selectable): one thread per lane, a warp owns 32 consecutive lanes,
+//   every access is a coalesced 256-byte row of the warp's private slab in HBM.
 //
 // Replaces: the JIT'd step function (src/taylor_00.cpp:712-865), step_impl() bookkeeping
 // (src/taylor_adaptive_batch.cpp:632-727), propagate_until_impl() (:1136-1534), d_out_f
