@@ -15,7 +15,7 @@ from . import _capi
 from ._capi import lib, check, HyError  # noqa: F401
 
 __all__ = [
-    "expression", "make_vars", "par", "time", "sin", "cos", "tanh", "exp", "log", "sqrt", "square", "pow", "sum",
+    "expression", "make_vars", "par", "time", "sin", "cos", "tanh", "exp", "log", "sigmoid", "relu", "sqrt", "square", "pow", "sum",
     "prod", "model", "taylor_adaptive_batch", "taylor_outcome", "Program", "Batch", "order_from_tol", "HyError",
 ]
 
@@ -135,6 +135,15 @@ def exp(e):
     return _func("exp", e)
 
 
+def sigmoid(e):
+    return _func("sigmoid", e)
+
+
+def relu(e, slope=0.0):
+    """relu(x) / leaky ReLU (src/math/relu.cpp); slope must be finite and non-negative."""
+    return _func("relu", e) if slope == 0 else _func("leaky_relu", e, float(slope))
+
+
 def log(e):
     return _func("log", e)
 
@@ -182,7 +191,7 @@ class model:
 
     @staticmethod
     def ffnn(inputs, nn_hidden, n_out, activations, nn_wb=None):
-        ids = {"identity": 0, "tanh": 1, "sin": 2, "exp": 3}
+        ids = {"identity": 0, "tanh": 1, "sin": 2, "exp": 3, "sigmoid": 4, "relu": 5}
         ins = [expression._wrap(i) for i in inputs]
         arr = (C.c_void_p * len(ins))(*[i._h for i in ins])
         hid = (C.c_uint32 * len(nn_hidden))(*nn_hidden)

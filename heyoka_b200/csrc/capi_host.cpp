@@ -190,6 +190,18 @@ hy_ex *hy_ex_func(const char *name, const hy_ex *const *args, uint32_t n_args)
         if (s == "exp") {
             return unary([](const auto &x) { return hy::exp(x); });
         }
+        if (s == "sigmoid") {
+            return unary([](const auto &x) { return hy::sigmoid(x); });
+        }
+        if (s == "relu") {
+            return unary([](const auto &x) { return hy::relu(x); });
+        }
+        if (s == "leaky_relu") {
+            if (v.size() != 2u || !v[1].is_number()) {
+                throw std::invalid_argument("leaky_relu needs an argument and a numeric slope");
+            }
+            return hy::relu(v[0], v[1].num());
+        }
         if (s == "log") {
             return unary([](const auto &x) { return hy::log(x); });
         }
@@ -285,6 +297,12 @@ int hy_model_ffnn(const hy_ex *const *inputs, uint32_t n_in, const uint32_t *nn_
                     break;
                 case 3:
                     acts.emplace_back([](const hy::expression &e) { return hy::exp(e); });
+                    break;
+                case 4:
+                    acts.emplace_back([](const hy::expression &e) { return hy::sigmoid(e); });
+                    break;
+                case 5:
+                    acts.emplace_back([](const hy::expression &e) { return hy::relu(e); });
                     break;
                 default:
                     throw std::invalid_argument("Unknown activation id " + std::to_string(act[i]));

@@ -346,6 +346,14 @@ std::size_t func_taylor_decompose(expression fn, taylor_dc_t &dc)
             ret = dc.size() - 2u;
             break;
         }
+        case func_kind::sigmoid: {
+            // sigmoid, then sigmoid**2 as hidden dependency (src/math/sigmoid.cpp:99-113).
+            dc.emplace_back(std::move(fn), std::vector<std::uint32_t>{});
+            dc.emplace_back(pow(uvar(dc.size() - 1u), expression{2.}), std::vector<std::uint32_t>{});
+            (dc.end() - 2)->second.push_back(static_cast<std::uint32_t>(dc.size() - 1u));
+            ret = dc.size() - 2u;
+            break;
+        }
         default:
             ret = dc.size();
             dc.emplace_back(std::move(fn), std::vector<std::uint32_t>{});

@@ -33,6 +33,10 @@ const char *func_kind_name(func_kind k)
             return "cos";
         case func_kind::tanh:
             return "tanh";
+        case func_kind::sigmoid:
+            return "sigmoid";
+        case func_kind::relu:
+            return "relu";
         case func_kind::exp:
             return "exp";
         case func_kind::log:
@@ -390,6 +394,23 @@ expression cos(expression e)
 expression tanh(expression e)
 {
     return unary_builder(func_kind::tanh, std::move(e), [](double x) { return std::tanh(x); });
+}
+expression sigmoid(expression e)
+{
+    // 1 / (1 + exp(-x)), src/math/sigmoid.cpp:69-75.
+    return unary_builder(func_kind::sigmoid, std::move(e), [](double x) { return 1. / (1. + std::exp(-x)); });
+}
+expression relu(expression e, double slope)
+{
+    if (!std::isfinite(slope) || slope < 0) {
+        throw std::invalid_argument("The slope parameter for a leaky ReLU must be finite and non-negative, but the value "
+                                    + std::to_string(slope) + " was provided instead");
+    }
+    if (e.is_number()) {
+        const double x = e.num();
+        return expression{x > 0 ? x : (slope == 0 ? 0. : slope * x)};
+    }
+    return expression{func_kind::relu, {std::move(e), expression{slope}}};
 }
 expression exp(expression e)
 {

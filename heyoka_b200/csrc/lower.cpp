@@ -125,6 +125,10 @@ std::uint32_t cfunc_of(func_kind k)
             return HY_CF_EXP;
         case func_kind::log:
             return HY_CF_LOG;
+        case func_kind::sigmoid:
+            return HY_CF_SIGMOID;
+        case func_kind::relu:
+            return HY_CF_RELU;
         default:
             throw not_implemented_error(std::string("Constant folding of function '") + func_kind_name(k)
                                         + "' is not implemented");
@@ -311,6 +315,21 @@ hy_program lower_decomposition(const taylor_dc_t &dc, std::uint32_t n_eq, std::u
                     op.a = HY_REF_IDX(ctx.ref(a[0]));
                     op.c = need_dep();
                     break;
+                case func_kind::sigmoid:
+                    need_args(1);
+                    op.opcode = HY_OP_SIGMOID;
+                    op.a = HY_REF_IDX(ctx.ref(a[0]));
+                    op.c = need_dep();
+                    break;
+                case func_kind::relu:
+                    need_args(2);
+                    if (!a[1].is_number()) {
+                        throw std::invalid_argument("The slope of a ReLU must be a number");
+                    }
+                    op.opcode = HY_OP_RELU;
+                    op.a = HY_REF_IDX(ctx.ref(a[0]));
+                    op.b = ctx.add_const(a[1].num());
+                    break;
                 case func_kind::exp:
                     need_args(1);
                     op.opcode = HY_OP_EXP;
@@ -448,9 +467,16 @@ void validate_program(const hy_program &p)
                 var(op.a, cur);
                 par(op.b);
                 break;
+            case HY_OP_RELU:
+                var(op.a, cur);
+                if (op.b >= p.consts.size()) {
+                    fail("constant index out of range");
+                }
+                break;
             case HY_OP_SIN:
             case HY_OP_COS:
             case HY_OP_TANH:
+            case HY_OP_SIGMOID:
                 var(op.a, cur);
                 // The hidden dependency may come right after the op (sin/cos pairs, tanh -> tanh^2).
                 if (op.c < p.n_eq || op.c >= p.n_uvars || op.c == cur) {
@@ -460,7 +486,7 @@ void validate_program(const hy_program &p)
             case HY_OP_TIME:
                 break;
             case HY_OP_CFUNC:
-                if (op.a > HY_CF_LOG) {
+                if (op.a > HY_CF_RELU) {
                     fail("invalid constant function");
                 }
                 if (op.c == 0u || static_cast<std::uint64_t>(op.b) + op.c > p.args.size()) {
@@ -535,6 +561,7 @@ program_costs compute_costs(const hy_program &p)
             case HY_OP_TANH:
             case HY_OP_EXP:
             case HY_OP_LOG:
+            case HY_OP_SIGMOID:
                 fl += conv(3., 2.);
                 break;
             case HY_OP_TIME:

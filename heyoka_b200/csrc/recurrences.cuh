@@ -126,6 +126,29 @@ HY_VD_MAP1(vcos, ::cos)
 HY_VD_MAP1(vtanh, ::tanh)
 HY_VD_MAP1(vexp, ::exp)
 HY_VD_MAP1(vlog, ::log)
+// sigmoid(x) = 1 / (1 + exp(-x)) (src/math/sigmoid.cpp:69-75).
+template <int N>
+__device__ __forceinline__ vd<N> vsigmoid(const vd<N> &x)
+{
+    vd<N> r;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        r.v[i] = 1. / (1. + ::exp(-x.v[i]));
+    }
+    return r;
+}
+// (Leaky) ReLU of `val` gated by the sign of `x0` (src/math/relu.cpp:118-128, :157-176): x0 > 0 ? val : slope * val,
+// with an exact 0 for the plain ReLU.
+template <int N>
+__device__ __forceinline__ vd<N> vrelu(const vd<N> &x0, const vd<N> &val, double slope)
+{
+    vd<N> r;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        r.v[i] = x0.v[i] > 0. ? val.v[i] : (slope == 0. ? 0. : slope * val.v[i]);
+    }
+    return r;
+}
 #undef HY_VD_MAP1
 
 template <int N>
@@ -312,6 +335,10 @@ __device__ inline vd<N> cfunc_eval(const program &P, const Tape &t, std::uint32_
             return vexp(v[0]);
         case HY_CF_LOG:
             return vlog(v[0]);
+        case HY_CF_SIGMOID:
+            return vsigmoid(v[0]);
+        case HY_CF_RELU:
+            return vrelu(v[0], v[0], v[1].v[0]);
     }
     return splat<N>(0.);
 }
@@ -524,6 +551,28 @@ __device__ __forceinline__ vd<N> diff_op(const program &P, const Tape &t, const 
             return n == 0u ? t.time() : (n == 1u ? splat<N>(1.) : splat<N>(0.));
         case HY_OP_CFUNC:
             return n == 0u ? cfunc_eval<N>(P, t, a, b, dep) : splat<N>(0.);
+        case HY_OP_SIGMOID: {
+            // (1/n) sum_{j=1..n} j (a^[n-j] - c^[n-j]) b^[j], a = this u variable, c = a^2 (hidden dependency).
+            const Row B = t.row(a);
+            if (n == 0u) {
+                return vsigmoid(B.at(0u));
+            }
+            const Row C = t.row(dep);
+            V acc = splat<N>(0.);
+            constexpr int S = static_cast<int>(Row::stride);
+            const double *pa = self.hptr(n - 1u), *pc = C.hptr(n - 1u), *pb = B.hptr(1u);
+            for (std::uint32_t j = 1; j <= n; ++j) {
+                acc = vfma(static_cast<double>(j), (Row::load(pa) - Row::load(pc)) * Row::load(pb), acc);
+                pa -= S;
+                pc -= S;
+                pb += S;
+            }
+            return acc / static_cast<double>(n);
+        }
+        case HY_OP_RELU: {
+            const Row B = t.row(a);
+            return vrelu(B.at(0u), B.at(n), t.cst(b));
+        }
     }
     return splat<N>(0.);
 }

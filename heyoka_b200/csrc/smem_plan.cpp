@@ -87,6 +87,14 @@ op_uses uses_of(const hy_program &p, const hy_op &op)
             // op.c is the hidden dependency: read at lower orders only, but it needs its history.
             u.hist = {op.a};
             break;
+        case HY_OP_SIGMOID:
+            u.hist = {op.a};
+            u.self_hist = true;
+            break;
+        case HY_OP_RELU:
+            // Reads the order-0 coefficient of its argument at every order: the argument keeps its history.
+            u.hist = {op.a};
+            break;
         default:
             break;
     }
@@ -129,7 +137,8 @@ smem_plan make_smem_plan(const hy_program &p, bool fuse, bool fuse_sv, bool spil
         if (u.self_hist) {
             hist[n_eq + i] = 1;
         }
-        if (op.opcode == HY_OP_SIN || op.opcode == HY_OP_COS || op.opcode == HY_OP_TANH) {
+        if (op.opcode == HY_OP_SIN || op.opcode == HY_OP_COS || op.opcode == HY_OP_TANH
+            || op.opcode == HY_OP_SIGMOID) {
             hist[op.c] = 1;
             users[op.c].push_back(i); // keeps hidden dependencies out of any fusion
         }
@@ -679,8 +688,12 @@ smem_plan make_smem_plan(const hy_program &p, bool fuse, bool fuse_sv, bool spil
                 case HY_OP_SIN:
                 case HY_OP_COS:
                 case HY_OP_TANH:
+                case HY_OP_SIGMOID:
                     var(op.a);
                     var(op.c);
+                    break;
+                case HY_OP_RELU:
+                    var(op.a);
                     break;
                 default:
                     // SUM / SUM_SQ / CFUNC go through the argument table, TIME has no operands, fused

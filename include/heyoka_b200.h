@@ -62,7 +62,8 @@ hy_ex *hy_ex_par(uint32_t idx);
 hy_ex *hy_ex_time(void);
 /* op: '+', '-', '*', '/' (binary, src/expression_ops.cpp:56-92), 'n' = unary minus (b ignored), '^' = pow. */
 hy_ex *hy_ex_binary(char op, const hy_ex *a, const hy_ex *b);
-/* name: "sin","cos","tanh","exp","log","sqrt","square" (unary); "sum","prod" (n-ary). */
+/* name: "sin","cos","tanh","exp","log","sqrt","square","sigmoid","relu" (unary); "sum","prod" (n-ary);
+ * "leaky_relu" (binary: argument, slope as a number). */
 hy_ex *hy_ex_func(const char *name, const hy_ex *const *args, uint32_t n_args);
 hy_ex *hy_ex_copy(const hy_ex *);
 void hy_ex_free(hy_ex *);
@@ -73,7 +74,7 @@ size_t hy_ex_str(const hy_ex *, char *buf, size_t buf_len);
  * They fill lhs[i]/rhs[i] (caller frees each with hy_ex_free). */
 int hy_model_nbody(uint32_t n, const double *masses, uint32_t n_masses, double G, hy_ex **lhs, hy_ex **rhs /* 6n each */);
 int hy_model_pendulum(double g, double l, hy_ex **lhs, hy_ex **rhs /* 2 each */);
-/* act: per layer 0 = identity, 1 = tanh, 2 = sin, 3 = exp. nn_wb == NULL -> weights/biases are par[0..). */
+/* act: per layer 0 = identity, 1 = tanh, 2 = sin, 3 = exp, 4 = sigmoid, 5 = relu. nn_wb == NULL -> weights/biases are par[0..). */
 int hy_model_ffnn(const hy_ex *const *inputs, uint32_t n_in, const uint32_t *nn_hidden, uint32_t n_hidden, uint32_t n_out,
                   const int *act, const double *nn_wb, uint32_t n_wb, hy_ex **out /* n_out */);
 
@@ -125,6 +126,10 @@ enum hy_opcode {
     HY_OP_CFUNC,    /* all arguments are numbers/params: a = function (hy_cfunc), b = offset into
                        args[], c = number of arguments. Order 0: evaluate; higher orders: 0.
                        (include/heyoka/detail/taylor_common.hpp:88-157)                        */
+    HY_OP_SIGMOID,  /* a = argument, c = hidden dependency (the u variable holding sigmoid(a)^2),
+                       src/math/sigmoid.cpp:137-179                                            */
+    HY_OP_RELU,     /* a = argument, b = constant index of the slope of the leaky ReLU (0 = plain),
+                       src/math/relu.cpp:157-176                                               */
     HY_OP_COUNT
 };
 
@@ -136,7 +141,7 @@ enum hy_opcode {
 #define HY_POW_NEG_SMALL_HALF 4u
 
 enum hy_cfunc { HY_CF_IDENTITY = 0, HY_CF_SUM, HY_CF_PROD, HY_CF_SUB, HY_CF_DIV, HY_CF_POW, HY_CF_SUM_SQ,
-                HY_CF_SIN, HY_CF_COS, HY_CF_TANH, HY_CF_EXP, HY_CF_LOG };
+                HY_CF_SIN, HY_CF_COS, HY_CF_TANH, HY_CF_EXP, HY_CF_LOG, HY_CF_SIGMOID, HY_CF_RELU };
 
 typedef struct hy_op {
     uint32_t opcode;

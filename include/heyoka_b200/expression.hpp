@@ -54,6 +54,8 @@ enum class func_kind : std::uint8_t {
     tanh,         // src/math/tanh.cpp
     exp,          // src/math/exp.cpp
     log,          // src/math/log.cpp
+    sigmoid,      // src/math/sigmoid.cpp
+    relu,         // src/math/relu.cpp (args: x, slope as a number)
     time,         // src/math/time.cpp
     num_identity, // src/detail/num_identity.cpp (created by the decomposition only)
 };
@@ -166,6 +168,9 @@ expression square(const expression &);
 expression sin(expression);
 expression cos(expression);
 expression tanh(expression);
+expression sigmoid(expression);
+// relu(x) / leaky ReLU with a finite, non-negative slope (src/math/relu.cpp:51-60).
+expression relu(expression, double slope = 0.);
 expression exp(expression);
 expression log(expression);
 

@@ -118,6 +118,16 @@ static inline real_t r_sqrt(real_t x)
         }                                                                                                              \
     } while (0)
 
+/* src/math/sigmoid.cpp:69-75; src/math/relu.cpp:118-128 (gate on x0, exact 0 for the plain ReLU). */
+static inline double sigmoid_d(double x)
+{
+    return 1. / (1. + exp(-x));
+}
+static inline double relu_d(double x0, double val, double slope)
+{
+    return x0 > 0. ? val : (slope == 0. ? 0. : slope * val);
+}
+
 static inline real_t r_pow(real_t x, real_t y)
 {
     real_t r = R_SPLAT(0.);
@@ -269,6 +279,14 @@ static real_t cfunc_eval(const ctx_t *c, const hy_op *op)
             return r;
         case HY_CF_LOG:
             R_MAP1(log, v[0], r);
+            return r;
+        case HY_CF_SIGMOID:
+            R_MAP1(sigmoid_d, v[0], r);
+            return r;
+        case HY_CF_RELU:
+            for (int l_ = 0; l_ < ORACLE_W; ++l_) {
+                R_SET(r, l_, relu_d(R_GET(v[0], l_), R_GET(v[0], l_), R_GET(v[1], l_)));
+            }
             return r;
     }
     return r;
@@ -525,6 +543,37 @@ static real_t diff_op(const ctx_t *c, const hy_op *op, uint32_t u_idx, uint32_t 
             return n == 0u ? time_v : (n == 1u ? R_SPLAT(1.) : zero);
         case HY_OP_CFUNC:
             return n == 0u ? cfunc_eval(c, op) : zero;
+        case HY_OP_SIGMOID: {
+            /* src/math/sigmoid.cpp:137-179 (default mode, pairwise) / :262-322 (compact mode, sequential):
+             * (1/n) sum_{j=1..n} ((a^[n-j] - c^[n-j]) b^[j]) j, a = this u variable, c = a^2. */
+            if (n == 0u) {
+                R_MAP1(sigmoid_d, TAPE(c, 0, op->a), r);
+                return r;
+            }
+            real_t buf[256];
+            real_t acc = zero;
+            for (uint32_t j = 1; j <= n; ++j) {
+                const real_t t1 = TAPE(c, n - j, u_idx) - TAPE(c, n - j, op->c);
+                const real_t t2 = t1 * TAPE(c, j, op->a);
+                if (c->mode & ORACLE_PAIRWISE) {
+                    buf[j - 1u] = t2 * R_SPLAT((double)j);
+                } else {
+                    acc = r_fma(c, R_SPLAT((double)j), t2, acc);
+                }
+            }
+            if (c->mode & ORACLE_PAIRWISE) {
+                acc = pairwise_sum(buf, n);
+            }
+            return acc / R_SPLAT((double)n);
+        }
+        case HY_OP_RELU: {
+            /* src/math/relu.cpp:157-176: select(u^[0] > 0, u^[n], slope * u^[n]). */
+            const real_t x0 = TAPE(c, 0, op->a), xn = TAPE(c, n, op->a);
+            for (int l_ = 0; l_ < ORACLE_W; ++l_) {
+                R_SET(r, l_, relu_d(R_GET(x0, l_), R_GET(xn, l_), P->consts[op->b]));
+            }
+            return r;
+        }
     }
     return R_SPLAT(NAN);
 }

@@ -42,12 +42,23 @@ CASES = [
      [2, 4, 3, 3, 5, 6], None),
     ("neg_num", "test/taylor_neg.cpp:205", lambda m, x, y: (-m.c(2), x + y), [2, -2, 1, 3, -3, 0], None),
     ("neg_var", "test/taylor_neg.cpp:399", lambda m, x, y: (-y, -x), [2, 4, 3, 3, 5, 6], None),
+    ("sigmoid_num", "test/taylor_sigmoid.cpp:284", lambda m, x, y: (m.sigmoid(m.c(2)), x + y), [2, -4, -1, 3, 5, -2],
+     None),
+    ("sigmoid_var", "test/taylor_sigmoid.cpp:480", lambda m, x, y: (m.sigmoid(y), m.sigmoid(x)),
+     [2, -1, -5, 3, -4, 6], None),
+    # relu / leaky relu: the systems of test/taylor_relu.cpp:112-148 and :223-259 without relup (not implemented).
+    ("relu_var", "test/taylor_relu.cpp:112", lambda m, x, y: (m.relu(x) + y, x + m.relu(y)), [2, -1, 3, 3, 5, -2],
+     None),
+    ("leaky_relu_var", "test/taylor_relu.cpp:223",
+     lambda m, x, y: (m.relu(x, 0.01) * y, x + m.relu(y, 0.02)), [2, -1, -3, -3, 5, 0.5], None),
     ("time", "test/taylor_time.cpp:197", lambda m, x, y: (m.t() + x, x + y), [2, -2, 1, 3, -3, 0], [-5, 6, -1]),
 ]
 
 # Tolerance in units of epsilon: 100 (test/test_utils.hpp:51) unless the reference's block says otherwise
 # (1 - tanh^2 cancels for |x| >= 4: test/taylor_tanh.cpp:489-511 uses 10000).
-EPS_MUL = {"tanh_var": 10000.0}
+# sigmoid: a - a^2 cancels for |x| >= 5 the same way; the reference's expected values (test/taylor_sigmoid.cpp:508-
+# 530) are formed from the computed jets and share that rounding, the exact closed forms used here do not.
+EPS_MUL = {"tanh_var": 10000.0, "sigmoid_var": 1000.0}
 
 BATCH = 3
 TOL = 0.1  # -> order 3 (include/heyoka/detail/taylor_common.hpp:165-191)
@@ -59,7 +70,7 @@ class hb_backend:
 
     def __init__(self, hb):
         self.hb = hb
-        for f in ("sin", "cos", "tanh", "exp", "log", "sqrt", "square", "pow"):
+        for f in ("sin", "cos", "tanh", "exp", "log", "sqrt", "square", "pow", "sigmoid", "relu"):
             setattr(self, f, getattr(hb, f))
 
     def c(self, v):

@@ -27,6 +27,14 @@ class sympy_backend:
         return e ** 2
 
     @staticmethod
+    def sigmoid(e):
+        return 1 / (1 + sp.exp(-e))
+
+    @staticmethod
+    def relu(e, slope=0):
+        return sp.Piecewise((e, e > 0), (sp.nsimplify(slope) * e, True))
+
+    @staticmethod
     def pow(b, e):  # noqa: A003
         return b ** e
 
@@ -52,12 +60,12 @@ def main():
             derivs.append([sp.diff(e, x) * f[0] + sp.diff(e, y) * f[1] + sp.diff(e, t) for e in prev])
         tc = [[[None] * BATCH for _ in range(ORDER + 1)] for _ in range(2)]
         for lane in range(BATCH):
-            subs = {x: sp.Integer(state[lane]), y: sp.Integer(state[BATCH + lane]),
+            subs = {x: sp.nsimplify(state[lane]), y: sp.nsimplify(state[BATCH + lane]),
                     t: sp.Integer(time[lane]) if time else sp.Integer(0)}
             for k in range(ORDER + 1):
                 for i in range(2):
                     val = sp.N(derivs[k][i].subs(subs) / sp.factorial(k), 40)
-                    tc[i][k][lane] = float(val)
+                    tc[i][k][lane] = float(val)  # (Piecewise: the branch of the initial conditions)
         out["cases"].append({"name": name, "cite": cite, "state": state, "time": time, "tc": tc})
     with open(os.path.join(HERE, "closed_form_jets.json"), "w") as fh:
         json.dump(out, fh, indent=1)
