@@ -15,7 +15,7 @@ from . import _capi
 from ._capi import lib, check, HyError  # noqa: F401
 
 __all__ = [
-    "expression", "make_vars", "par", "time", "sin", "cos", "tanh", "exp", "log", "sigmoid", "relu", "sqrt", "square", "pow", "sum",
+    "expression", "make_vars", "par", "time", "sin", "cos", "tanh", "exp", "log", "sigmoid", "relu", "relup", "sqrt", "square", "pow", "sum",
     "prod", "model", "taylor_adaptive_batch", "taylor_outcome", "Program", "Batch", "order_from_tol", "HyError",
 ]
 
@@ -142,6 +142,11 @@ def sigmoid(e):
 def relu(e, slope=0.0):
     """relu(x) / leaky ReLU (src/math/relu.cpp); slope must be finite and non-negative."""
     return _func("relu", e) if slope == 0 else _func("leaky_relu", e, float(slope))
+
+
+def relup(e, slope=0.0):
+    """Derivative of the (leaky) ReLU: 1 for x > 0, slope otherwise (src/math/relu.cpp)."""
+    return _func("relup", e, float(slope))
 
 
 def log(e):

@@ -196,11 +196,11 @@ hy_ex *hy_ex_func(const char *name, const hy_ex *const *args, uint32_t n_args)
         if (s == "relu") {
             return unary([](const auto &x) { return hy::relu(x); });
         }
-        if (s == "leaky_relu") {
+        if (s == "leaky_relu" || s == "relup") {
             if (v.size() != 2u || !v[1].is_number()) {
-                throw std::invalid_argument("leaky_relu needs an argument and a numeric slope");
+                throw std::invalid_argument(s + " needs an argument and a numeric slope");
             }
-            return hy::relu(v[0], v[1].num());
+            return s == "relup" ? hy::relup(v[0], v[1].num()) : hy::relu(v[0], v[1].num());
         }
         if (s == "log") {
             return unary([](const auto &x) { return hy::log(x); });

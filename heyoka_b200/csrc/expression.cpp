@@ -37,6 +37,8 @@ const char *func_kind_name(func_kind k)
             return "sigmoid";
         case func_kind::relu:
             return "relu";
+        case func_kind::relup:
+            return "relup";
         case func_kind::exp:
             return "exp";
         case func_kind::log:
@@ -411,6 +413,17 @@ expression relu(expression e, double slope)
         return expression{x > 0 ? x : (slope == 0 ? 0. : slope * x)};
     }
     return expression{func_kind::relu, {std::move(e), expression{slope}}};
+}
+expression relup(expression e, double slope)
+{
+    if (!std::isfinite(slope) || slope < 0) {
+        throw std::invalid_argument("The slope parameter for a leaky ReLU must be finite and non-negative, but the value "
+                                    + std::to_string(slope) + " was provided instead");
+    }
+    if (e.is_number()) {
+        return expression{e.num() > 0 ? 1. : slope};
+    }
+    return expression{func_kind::relup, {std::move(e), expression{slope}}};
 }
 expression exp(expression e)
 {

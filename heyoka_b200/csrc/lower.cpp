@@ -129,6 +129,8 @@ std::uint32_t cfunc_of(func_kind k)
             return HY_CF_SIGMOID;
         case func_kind::relu:
             return HY_CF_RELU;
+        case func_kind::relup:
+            return HY_CF_RELUP;
         default:
             throw not_implemented_error(std::string("Constant folding of function '") + func_kind_name(k)
                                         + "' is not implemented");
@@ -322,11 +324,12 @@ hy_program lower_decomposition(const taylor_dc_t &dc, std::uint32_t n_eq, std::u
                     op.c = need_dep();
                     break;
                 case func_kind::relu:
+                case func_kind::relup:
                     need_args(2);
                     if (!a[1].is_number()) {
                         throw std::invalid_argument("The slope of a ReLU must be a number");
                     }
-                    op.opcode = HY_OP_RELU;
+                    op.opcode = f.kind == func_kind::relu ? HY_OP_RELU : HY_OP_RELUP;
                     op.a = HY_REF_IDX(ctx.ref(a[0]));
                     op.b = ctx.add_const(a[1].num());
                     break;
@@ -468,6 +471,7 @@ void validate_program(const hy_program &p)
                 par(op.b);
                 break;
             case HY_OP_RELU:
+            case HY_OP_RELUP:
                 var(op.a, cur);
                 if (op.b >= p.consts.size()) {
                     fail("constant index out of range");
@@ -486,7 +490,7 @@ void validate_program(const hy_program &p)
             case HY_OP_TIME:
                 break;
             case HY_OP_CFUNC:
-                if (op.a > HY_CF_RELU) {
+                if (op.a > HY_CF_RELUP) {
                     fail("invalid constant function");
                 }
                 if (op.c == 0u || static_cast<std::uint64_t>(op.b) + op.c > p.args.size()) {

@@ -339,8 +339,22 @@ __device__ inline vd<N> cfunc_eval(const program &P, const Tape &t, std::uint32_
             return vsigmoid(v[0]);
         case HY_CF_RELU:
             return vrelu(v[0], v[0], v[1].v[0]);
+        case HY_CF_RELUP:
+            return vrelup(v[0], v[1].v[0]);
     }
     return splat<N>(0.);
+}
+
+// Derivative of the (leaky) ReLU (src/math/relu.cpp:365-376): x > 0 ? 1 : slope.
+template <int N>
+__device__ __forceinline__ vd<N> vrelup(const vd<N> &x, double slope)
+{
+    vd<N> r;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        r.v[i] = x.v[i] > 0. ? 1. : slope;
+    }
+    return r;
 }
 
 // The order-n coefficient of the u variable defined by `op` (op.x = opcode, op.y/z/w = a/b/c operand
@@ -573,6 +587,9 @@ __device__ __forceinline__ vd<N> diff_op(const program &P, const Tape &t, const 
             const Row B = t.row(a);
             return vrelu(B.at(0u), B.at(n), t.cst(b));
         }
+        case HY_OP_RELUP:
+            // Piecewise constant: relup at order 0, zero afterwards (src/math/relu.cpp:404-424).
+            return n == 0u ? vrelup(t.row(a).at(0u), t.cst(b)) : splat<N>(0.);
     }
     return splat<N>(0.);
 }

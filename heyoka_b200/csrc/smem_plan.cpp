@@ -95,6 +95,9 @@ op_uses uses_of(const hy_program &p, const hy_op &op)
             // Reads the order-0 coefficient of its argument at every order: the argument keeps its history.
             u.hist = {op.a};
             break;
+        case HY_OP_RELUP:
+            u.now = {op.a};
+            break;
         default:
             break;
     }
@@ -693,6 +696,7 @@ smem_plan make_smem_plan(const hy_program &p, bool fuse, bool fuse_sv, bool spil
                     var(op.c);
                     break;
                 case HY_OP_RELU:
+                case HY_OP_RELUP:
                     var(op.a);
                     break;
                 default:

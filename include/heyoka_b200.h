@@ -63,7 +63,7 @@ hy_ex *hy_ex_time(void);
 /* op: '+', '-', '*', '/' (binary, src/expression_ops.cpp:56-92), 'n' = unary minus (b ignored), '^' = pow. */
 hy_ex *hy_ex_binary(char op, const hy_ex *a, const hy_ex *b);
 /* name: "sin","cos","tanh","exp","log","sqrt","square","sigmoid","relu" (unary); "sum","prod" (n-ary);
- * "leaky_relu" (binary: argument, slope as a number). */
+ * "leaky_relu", "relup" (binary: argument, slope as a number). */
 hy_ex *hy_ex_func(const char *name, const hy_ex *const *args, uint32_t n_args);
 hy_ex *hy_ex_copy(const hy_ex *);
 void hy_ex_free(hy_ex *);
@@ -130,6 +130,8 @@ enum hy_opcode {
                        src/math/sigmoid.cpp:137-179                                            */
     HY_OP_RELU,     /* a = argument, b = constant index of the slope of the leaky ReLU (0 = plain),
                        src/math/relu.cpp:157-176                                               */
+    HY_OP_RELUP,    /* derivative of the (leaky) ReLU: a = argument, b = constant index of the slope,
+                       src/math/relu.cpp:404-424                                               */
     HY_OP_COUNT
 };
 
@@ -141,7 +143,7 @@ enum hy_opcode {
 #define HY_POW_NEG_SMALL_HALF 4u
 
 enum hy_cfunc { HY_CF_IDENTITY = 0, HY_CF_SUM, HY_CF_PROD, HY_CF_SUB, HY_CF_DIV, HY_CF_POW, HY_CF_SUM_SQ,
-                HY_CF_SIN, HY_CF_COS, HY_CF_TANH, HY_CF_EXP, HY_CF_LOG, HY_CF_SIGMOID, HY_CF_RELU };
+                HY_CF_SIN, HY_CF_COS, HY_CF_TANH, HY_CF_EXP, HY_CF_LOG, HY_CF_SIGMOID, HY_CF_RELU, HY_CF_RELUP };
 
 typedef struct hy_op {
     uint32_t opcode;

@@ -56,6 +56,7 @@ enum class func_kind : std::uint8_t {
     log,          // src/math/log.cpp
     sigmoid,      // src/math/sigmoid.cpp
     relu,         // src/math/relu.cpp (args: x, slope as a number)
+    relup,        // src/math/relu.cpp (derivative of the ReLU; args: x, slope as a number)
     time,         // src/math/time.cpp
     num_identity, // src/detail/num_identity.cpp (created by the decomposition only)
 };
@@ -171,6 +172,7 @@ expression tanh(expression);
 expression sigmoid(expression);
 // relu(x) / leaky ReLU with a finite, non-negative slope (src/math/relu.cpp:51-60).
 expression relu(expression, double slope = 0.);
+expression relup(expression, double slope = 0.);
 expression exp(expression);
 expression log(expression);
 

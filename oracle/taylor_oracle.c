@@ -288,6 +288,11 @@ static real_t cfunc_eval(const ctx_t *c, const hy_op *op)
                 R_SET(r, l_, relu_d(R_GET(v[0], l_), R_GET(v[0], l_), R_GET(v[1], l_)));
             }
             return r;
+        case HY_CF_RELUP:
+            for (int l_ = 0; l_ < ORACLE_W; ++l_) {
+                R_SET(r, l_, R_GET(v[0], l_) > 0. ? 1. : R_GET(v[1], l_));
+            }
+            return r;
     }
     return r;
 }
@@ -565,6 +570,17 @@ static real_t diff_op(const ctx_t *c, const hy_op *op, uint32_t u_idx, uint32_t 
                 acc = pairwise_sum(buf, n);
             }
             return acc / R_SPLAT((double)n);
+        }
+        case HY_OP_RELUP: {
+            /* src/math/relu.cpp:404-424: relup(u^[0]) at order 0, zero afterwards. */
+            if (n != 0u) {
+                return zero;
+            }
+            const real_t x0 = TAPE(c, 0, op->a);
+            for (int l_ = 0; l_ < ORACLE_W; ++l_) {
+                R_SET(r, l_, R_GET(x0, l_) > 0. ? 1. : P->consts[op->b]);
+            }
+            return r;
         }
         case HY_OP_RELU: {
             /* src/math/relu.cpp:157-176: select(u^[0] > 0, u^[n], slope * u^[n]). */

@@ -1,6 +1,6 @@
 """The systems and initial conditions of the reference's closed-form jet tests (test/taylor_*.cpp), batch 3,
 tol = .1 (order 3), as backend-neutral lambdas: `m` provides sin/cos/.../pow/c(onstant)/t(ime); x, y are the state
-variables. Used by tests/golden/make_closed_form_jets.py (sympy backend -> expected jets) and by the tests
+variables (batch 3; the relu blocks of the reference use batch 2). Used by tests/golden/make_closed_form_jets.py (sympy backend -> expected jets) and by the tests
 (heyoka_b200 backend -> oracle / GPU jets). State layout as in the reference: [x lanes..., y lanes...]."""
 
 CASES = [
@@ -46,11 +46,10 @@ CASES = [
      None),
     ("sigmoid_var", "test/taylor_sigmoid.cpp:480", lambda m, x, y: (m.sigmoid(y), m.sigmoid(x)),
      [2, -1, -5, 3, -4, 6], None),
-    # relu / leaky relu: the systems of test/taylor_relu.cpp:112-148 and :223-259 without relup (not implemented).
-    ("relu_var", "test/taylor_relu.cpp:112", lambda m, x, y: (m.relu(x) + y, x + m.relu(y)), [2, -1, 3, 3, 5, -2],
-     None),
+    # relu / relup and their leaky variants (batch 2 in the reference).
+    ("relu_var", "test/taylor_relu.cpp:112", lambda m, x, y: (m.relu(x) + m.relup(y), x + y), [2, -1, 3, 5], None),
     ("leaky_relu_var", "test/taylor_relu.cpp:223",
-     lambda m, x, y: (m.relu(x, 0.01) * y, x + m.relu(y, 0.02)), [2, -1, -3, -3, 5, 0.5], None),
+     lambda m, x, y: (m.relu(x, 0.01) + m.relup(y, 0.02), x + y), [2, -1, -3, 5], None),
     ("time", "test/taylor_time.cpp:197", lambda m, x, y: (m.t() + x, x + y), [2, -2, 1, 3, -3, 0], [-5, 6, -1]),
 ]
 
@@ -60,7 +59,7 @@ CASES = [
 # 530) are formed from the computed jets and share that rounding, the exact closed forms used here do not.
 EPS_MUL = {"tanh_var": 10000.0, "sigmoid_var": 1000.0}
 
-BATCH = 3
+BATCH = 3  # (2 for the relu blocks: batch_of(case))
 TOL = 0.1  # -> order 3 (include/heyoka/detail/taylor_common.hpp:165-191)
 ORDER = 3
 
@@ -70,7 +69,7 @@ class hb_backend:
 
     def __init__(self, hb):
         self.hb = hb
-        for f in ("sin", "cos", "tanh", "exp", "log", "sqrt", "square", "pow", "sigmoid", "relu"):
+        for f in ("sin", "cos", "tanh", "exp", "log", "sqrt", "square", "pow", "sigmoid", "relu", "relup"):
             setattr(self, f, getattr(hb, f))
 
     def c(self, v):
@@ -84,3 +83,7 @@ def hb_system(hb, case):
     x, y = hb.make_vars("x", "y")
     rx, ry = case[2](hb_backend(hb), x, y)
     return [(x, rx), (y, ry)]
+
+
+def batch_of(case):
+    return len(case[3]) // 2

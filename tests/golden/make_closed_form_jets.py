@@ -15,7 +15,7 @@ import sympy as sp
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(HERE))
-from closed_form_cases import BATCH, CASES, ORDER  # noqa: E402
+from closed_form_cases import CASES, ORDER, batch_of  # noqa: E402
 
 
 class sympy_backend:
@@ -35,6 +35,10 @@ class sympy_backend:
         return sp.Piecewise((e, e > 0), (sp.nsimplify(slope) * e, True))
 
     @staticmethod
+    def relup(e, slope=0):
+        return sp.Piecewise((sp.Integer(1), e > 0), (sp.nsimplify(slope), True))
+
+    @staticmethod
     def pow(b, e):  # noqa: A003
         return b ** e
 
@@ -50,8 +54,10 @@ class sympy_backend:
 def main():
     x, y = sp.symbols("x y")
     t = sympy_backend.T
-    out = {"order": ORDER, "batch": BATCH, "cases": []}
-    for name, cite, rhs, state, time in CASES:
+    out = {"order": ORDER, "cases": []}
+    for case in CASES:
+        name, cite, rhs, state, time = case
+        BATCH = batch_of(case)
         f = [sp.sympify(e) for e in rhs(sympy_backend, x, y)]
         # derivs[k][i] = d^k x_i / dt^k as an expression of (x, y, t)
         derivs = [[x, y], f]

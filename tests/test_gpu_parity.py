@@ -327,8 +327,9 @@ def _closed_form_cases():
 def test_closed_form_jets_gpu(case, gold, kernel):
     """The reference's closed-form jet blocks (test/taylor_*.cpp, see tests/closed_form_cases.py) on the GPU:
     one step with write_tc, jets against the symbolic closed forms to the reference's tolerance."""
-    from closed_form_cases import BATCH, EPS_MUL, ORDER, TOL, hb_system
+    from closed_form_cases import EPS_MUL, ORDER, TOL, batch_of, hb_system
     from test_oracle_golden import approximately
+    BATCH = batch_of(case)
     ta = hb.taylor_adaptive_batch(hb_system(hb, case), np.array(gold["state"], dtype=float).reshape(2, BATCH), BATCH,
                                   time=gold["time"] if gold["time"] else 0.0, tol=TOL, kernel=kernel)
     assert ta.get_order() == ORDER

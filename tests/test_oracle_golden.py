@@ -167,7 +167,8 @@ def test_closed_form_jets(case, gold, mode):
     """Every batch-3 / order-3 block of test/taylor_{sincos,tanh,exp,log,sqrt,square,pow,div,mul,sub,sum_sq,neg,
     time}.cpp (file:line in tests/closed_form_cases.py): the jet of one step against the closed forms, to the
     reference's own 100 epsilon."""
-    from closed_form_cases import BATCH, EPS_MUL, ORDER, TOL, hb_system
+    from closed_form_cases import EPS_MUL, ORDER, TOL, batch_of, hb_system
+    BATCH = batch_of(case)
     P = hb.Program(hb_system(hb, case), tol=TOL)
     assert P.order == ORDER
     o = oracle.OracleIntegrator(P, gold["state"], BATCH, time=gold["time"] if gold["time"] else 0.0, mode=mode)
