@@ -493,8 +493,14 @@ bool hy_batch::setup_coop(int L, int N, std::uint32_t threads, std::uint32_t cta
     for (const auto &op : plan.ops) {
         kmode = op.opcode < hy::detail::HY_FOP_FIRST ? 1 : kmode;
     }
-    const int maxt = threads <= 256u ? 256 : (threads <= 384u && kmode >= 2 ? 384 : 512);
-    const auto *v = find_variant(L, N, maxt, kmode);
+    // (Not every shape is compiled for every CTA size: fall back to the next larger bound.)
+    const int pref_maxt = threads <= 256u ? 256 : (threads <= 384u && kmode >= 2 ? 384 : 512);
+    const coop_variant *v = nullptr;
+    for (const int m : {256, 384, 512}) {
+        if (m >= pref_maxt && v == nullptr) {
+            v = find_variant(L, N, m, kmode);
+        }
+    }
     if (v == nullptr) {
         throw std::invalid_argument("Unsupported cooperative kernel configuration: " + std::to_string(L)
                                     + " lanes per warp, " + std::to_string(N) + " lanes per thread");
