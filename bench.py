@@ -43,7 +43,7 @@ def parse_args():
     ap.add_argument("--perturb", type=float, default=1e-3)
     ap.add_argument("--cpu-lanes", type=int, default=0, help="lanes of the CPU sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--tape", default="auto", choices=["auto", "hbm", "smem", "smem-notmem", "global"])
+    ap.add_argument("--tape", default="auto", choices=["auto", "hbm", "smem", "smem-notmem", "global", "global-cta"])
     ap.add_argument("--lanes-per-warp", type=int, default=0)
     ap.add_argument("--lanes-per-thread", type=int, default=0)
     ap.add_argument("--block-threads", type=int, default=0)

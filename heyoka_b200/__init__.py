@@ -313,7 +313,7 @@ class Batch:
         check(lib.hy_batch_set_launch_config(self._h, int(block_threads), int(blocks_per_sm)))
 
     def set_kernel(self, tape="auto", lanes_per_warp=0, lanes_per_thread=0, block_threads=0, blocks_per_sm=0):
-        mode = {"auto": 0, "hbm": 1, "smem": 2, "smem-notmem": 3, "global": 4}[tape]
+        mode = {"auto": 0, "hbm": 1, "smem": 2, "smem-notmem": 3, "global": 4, "global-cta": 5}[tape]
         check(lib.hy_batch_set_kernel(self._h, mode, int(lanes_per_warp), int(lanes_per_thread), int(block_threads),
                                       int(blocks_per_sm)))
 
@@ -321,7 +321,7 @@ class Batch:
         ki = _capi.hy_kernel_info()
         check(lib.hy_batch_get_kernel(self._h, C.byref(ki)))
         d = {f[0]: getattr(ki, f[0]) for f in ki._fields_}
-        d["tape"] = {1: "hbm", 2: "smem", 4: "global"}.get(ki.tape_mode, "?")
+        d["tape"] = {1: "hbm", 2: "smem", 4: "global", 5: "global-cta"}.get(ki.tape_mode, "?")
         return d
 
     def sync(self):

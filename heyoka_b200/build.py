@@ -25,7 +25,7 @@ CUDA_SOURCES = ["batch.cu"]
 # object each (built in parallel).
 COOP_FAMILIES = ([(n, m, g) for n in (1, 2, 4) for m in (512, 256) for g in (1, 0)]
                  + [(n, m, g) for n in (1, 2) for m in (512, 384, 256) for g in (2, 3)]
-                 + [(1, 512, 4), (2, 512, 4)])
+                 + [(1, 512, 4), (2, 512, 4), (1, 512, 5), (2, 512, 5)])
 
 NVCC_ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 CUDA_FLAGS = ["-lineinfo", "-fmad=false", "-Xcompiler", "-fPIC", "-Xptxas", "-v"]

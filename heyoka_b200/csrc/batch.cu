@@ -48,7 +48,7 @@ using hy::detail::coop_variant;
 
 // maxt: upper bound on the threads per CTA the variant was compiled for (256: up to 255 registers per thread).
 // mode: 1 = the plan contains elementary ops, 0 = superinstructions only, 2 / 3 = idem with tensor memory,
-// 4 = any plan, tape and tables in global memory.
+// 4 = any plan, tape and tables in global memory, 5 = idem with the whole CTA working on one chunk of lanes.
 const coop_variant *find_variant(int L, int N, int maxt, int mode)
 {
     const hy::detail::coop_family fams[] = {
@@ -77,7 +77,9 @@ const coop_variant *find_variant(int L, int N, int maxt, int mode)
         hy::detail::coop_family_n2_256_m2(),
         hy::detail::coop_family_n2_256_m3(),
         hy::detail::coop_family_n1_512_m4(),
-        hy::detail::coop_family_n2_512_m4()};
+        hy::detail::coop_family_n2_512_m4(),
+        hy::detail::coop_family_n1_512_m5(),
+        hy::detail::coop_family_n2_512_m5()};
     for (const auto &f : fams) {
         for (std::size_t i = 0; i < f.n; ++i) {
             if (f.v[i].L == L && f.v[i].N == N && f.v[i].maxt == maxt && f.v[i].mode == mode) {
@@ -196,7 +198,8 @@ struct hy_batch {
     std::uint32_t opt_tmem_rows = 0; // 0: automatic, 2 / 3: forced (HEYOKA_B200_TMEM_ROWS)
     void replan(bool spill, std::uint32_t tmem_max_pairs = 0, std::uint32_t tmem_rows = 2);
     void ensure_tc();
-    void setup_coop_global(int L, int N, std::uint32_t threads);
+    void setup_coop_global(int L, int N, std::uint32_t threads, int cta = -1);
+    bool c_cta = false; // ... and the whole CTA working on one chunk of lanes (kernel mode 5)
     bool c_global = false; // cooperative kernel with the tape in global memory (kernel mode 4)
 
     // Resident arrays.
@@ -546,7 +549,7 @@ bool hy_batch::setup_coop(int L, int N, std::uint32_t threads, std::uint32_t cta
 // bodies: 56k doubles per lane): same program, same planner, but every warp's tape is a slab of global memory and
 // the tables are read in place. Unlike the one-thread-per-lane HBM-tape kernel it fills the GPU with a few
 // thousand lanes (a warp works on L lanes, its threads on different u variables).
-void hy_batch::setup_coop_global(int L, int N, std::uint32_t threads)
+void hy_batch::setup_coop_global(int L, int N, std::uint32_t threads, int cta)
 {
     if (plan.tmem != 0u || plan.n_gslots != 0u) {
         replan(false);
@@ -554,20 +557,32 @@ void hy_batch::setup_coop_global(int L, int N, std::uint32_t threads)
     if (N == 0) {
         N = (L == 0 || L >= 2) ? 2 : 1;
     }
-    if (L == 0) {
-        // As many lanes per warp as still leave a chunk of lanes for every resident warp.
-        L = N;
-        while (2 * L <= 8 && n / static_cast<std::uint32_t>(2 * L) >= n_sms * 16u) {
-            L *= 2;
-        }
-    }
     if (threads == 0u) {
         threads = 512u;
     }
     if (threads % 32u != 0u || threads > 512u) {
         throw std::invalid_argument("Invalid number of threads for the cooperative kernel");
     }
-    const auto *v = find_variant(L, N, 512, 4);
+    const std::uint32_t warps = threads / 32u;
+    if (cta < 0) {
+        // Whole CTAs per chunk of lanes (mode 5) when the levels are wide enough to give work to hundreds of
+        // threads and there are too few lanes to keep every warp of the GPU busy for long: the lane-step latency
+        // drops by the number of warps (a slow lane no longer holds the launch), and the tapes in flight
+        // (n_sms x L lanes) nearly fit in L2. Otherwise one warp per chunk (mode 4).
+        const double avg_width = static_cast<double>(plan.ops.size()) / std::max(1u, plan.n_segments);
+        const std::uint64_t warp_chunks = (n + static_cast<std::uint32_t>(N) - 1u) / static_cast<std::uint32_t>(N);
+        cta = (avg_width >= 128. && warp_chunks < 8ull * n_sms * warps) ? 1 : 0;
+    }
+    if (L == 0) {
+        L = N;
+        if (cta == 0) {
+            // As many lanes per warp as still leave a chunk of lanes for every resident warp.
+            while (2 * L <= 8 && n / static_cast<std::uint32_t>(2 * L) >= n_sms * 16u) {
+                L *= 2;
+            }
+        }
+    }
+    const auto *v = find_variant(L, N, 512, cta != 0 ? 5 : 4);
     if (v == nullptr) {
         throw std::invalid_argument("Unsupported cooperative kernel configuration (global tape): "
                                     + std::to_string(L) + " lanes per warp, " + std::to_string(N)
@@ -579,30 +594,34 @@ void hy_batch::setup_coop_global(int L, int N, std::uint32_t threads)
             *ptr = nullptr;
         }
     }
-    const std::uint32_t warps = threads / 32u;
-    const std::size_t warp_bytes = coop_warp_bytes(plan.n_slots, L);
-    const std::uint32_t lanes_per_block = static_cast<std::uint32_t>(L) * warps;
+    // Teams (warps, or whole CTAs) per block, each with its own slab and private coefficient store.
+    const std::uint32_t teams = cta != 0 ? 1u : warps;
+    const std::size_t team_bytes = coop_warp_bytes(plan.n_slots, L);
+    const std::uint32_t lanes_per_block = static_cast<std::uint32_t>(L) * teams;
     const std::uint32_t n_blocks_needed = (n + lanes_per_block - 1u) / lanes_per_block;
     std::size_t free_b = 0, total_b = 0;
     HY_CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
-    const std::size_t max_blocks = std::max<std::size_t>(free_b / 2u / (warp_bytes * warps), 1u);
+    const std::size_t max_blocks = std::max<std::size_t>(free_b / 2u / (team_bytes * teams), 1u);
     cv = v;
     c_threads = threads;
     c_smem = 0;
     c_ctas_per_sm = 1;
-    c_grid = static_cast<std::uint32_t>(std::max<std::size_t>(1u, std::min<std::size_t>({n_sms, n_blocks_needed, max_blocks})));
-    d_gscratch = dalloc<double>(static_cast<std::size_t>(c_grid) * warps * (warp_bytes / sizeof(double)));
-    d_cscratch = dalloc<double>(static_cast<std::size_t>(c_grid) * warps * (order + 1u) * n_eq
+    c_grid = static_cast<std::uint32_t>(
+        std::max<std::size_t>(1u, std::min<std::size_t>({n_sms, n_blocks_needed, max_blocks})));
+    d_gscratch = dalloc<double>(static_cast<std::size_t>(c_grid) * teams * (team_bytes / sizeof(double)));
+    d_cscratch = dalloc<double>(static_cast<std::size_t>(c_grid) * teams * (order + 1u) * n_eq
                                 * static_cast<std::size_t>(L));
     mode = 2;
     c_global = true;
+    c_cta = cta != 0;
 }
 
 void hy_batch::configure(int want_mode, int L, int N, std::uint32_t threads, std::uint32_t blocks_per_sm)
 {
     c_global = false;
-    if (want_mode == 4) {
-        setup_coop_global(L, N, threads);
+    c_cta = false;
+    if (want_mode == 4 || want_mode == 5) {
+        setup_coop_global(L, N, threads, want_mode == 5 ? 1 : 0);
         return;
     }
     if (want_mode == 1) {
@@ -938,7 +957,7 @@ int hy_batch_set_kernel(hy_batch *b, int tape_mode, uint32_t lanes_per_warp, uin
         if (b == nullptr) {
             throw std::invalid_argument("Null batch");
         }
-        if (tape_mode < 0 || tape_mode > 4) {
+        if (tape_mode < 0 || tape_mode > 5) {
             throw std::invalid_argument("Invalid tape mode");
         }
         device_guard guard(b->device);
@@ -957,7 +976,7 @@ int hy_batch_get_kernel(const hy_batch *b, hy_kernel_info *out)
         hy::detail::set_last_error("Null pointer passed to hy_batch_get_kernel()");
         return HY_ERR_INVALID_ARG;
     }
-    out->tape_mode = b->mode == 2 && b->c_global ? 4 : b->mode;
+    out->tape_mode = b->mode == 2 && b->c_global ? (b->c_cta ? 5 : 4) : b->mode;
     out->lanes_per_warp = b->mode == 2 ? static_cast<uint32_t>(b->cv->L) : 32u;
     out->lanes_per_thread = b->mode == 2 ? static_cast<uint32_t>(b->cv->N) : 1u;
     out->block_threads = b->mode == 2 ? b->c_threads : b->h_threads;

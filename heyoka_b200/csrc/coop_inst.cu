@@ -24,7 +24,12 @@ namespace
     }
 
 const coop_variant family[] = {
-#if HY_COOP_MODE == 4 && HY_COOP_N == 1
+#if HY_COOP_MODE == 5 && HY_COOP_N == 1
+    // Tape in global memory, one CTA per chunk of lanes.
+    HY_COOP(1), HY_COOP(2)
+#elif HY_COOP_MODE == 5 && HY_COOP_N == 2
+    HY_COOP(2), HY_COOP(4)
+#elif HY_COOP_MODE == 4 && HY_COOP_N == 1
     // Tape in global memory: a few lanes per warp.
     HY_COOP(1), HY_COOP(2), HY_COOP(4)
 #elif HY_COOP_MODE == 4 && HY_COOP_N == 2

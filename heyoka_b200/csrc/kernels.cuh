@@ -10,7 +10,8 @@
 //   Where the tape lives is the kernel's MODE:
 //     0 / 1  shared memory (0: superinstruction-only programs, no interpreter of the elementary recurrences);
 //     2 / 3  shared memory + tensor memory for the rows only one thread touches (tmem.cuh);
-//     4      a per-warp slab of global memory, tables read in place (systems too large for shared memory).
+//     4 / 5  a slab of global memory per team, tables read in place (systems too large for shared memory);
+//            4: a team is a warp, 5: a team is the whole CTA (wide levels, few lanes; see team<>).
 //   HBM traffic per step: the state in and out (the state variables' coefficients go to a private L2-resident
 //   store, or to the public tc array on request).
 //
@@ -281,6 +282,73 @@ __device__ __forceinline__ std::uint32_t claim_chunk_warp(unsigned int *counter)
     return __shfl_sync(0xffffffffu, c, 0);
 }
 
+// The threads that work together on one chunk of L lanes: a warp (the default) or, for systems with hundreds of
+// independent items per level and too few lanes to fill the GPU with warps, the whole CTA (kernel MODE 5: the
+// latency of a lane-step drops by the number of warps, and the tapes in flight nearly fit in L2).
+template <bool CTA>
+struct team {
+    __device__ __forceinline__ static std::uint32_t tid()
+    {
+        return CTA ? threadIdx.x : (threadIdx.x & 31u);
+    }
+    __device__ __forceinline__ static std::uint32_t size()
+    {
+        return CTA ? blockDim.x : 32u;
+    }
+    // Index of the team in the grid (slab / private store index).
+    __device__ __forceinline__ static std::size_t index()
+    {
+        return CTA ? static_cast<std::size_t>(blockIdx.x)
+                   : ((static_cast<std::size_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5);
+    }
+    __device__ __forceinline__ static void sync()
+    {
+        if constexpr (CTA) {
+            __syncthreads();
+        } else {
+            __syncwarp();
+        }
+    }
+    __device__ __forceinline__ static bool any(bool pred)
+    {
+        if constexpr (CTA) {
+            return __syncthreads_or(pred ? 1 : 0) != 0;
+        } else {
+            return __any_sync(0xffffffffu, pred) != 0;
+        }
+    }
+    // Bitwise OR of a per-lane mask (bit l = lane l) over the team.
+    template <int L>
+    __device__ __forceinline__ static unsigned reduce_or(unsigned mask)
+    {
+        if constexpr (CTA) {
+            unsigned r = 0u;
+#pragma unroll
+            for (int l = 0; l < L; ++l) {
+                r |= __syncthreads_or(static_cast<int>((mask >> l) & 1u)) != 0 ? (1u << l) : 0u;
+            }
+            return r;
+        } else {
+            return __reduce_or_sync(0xffffffffu, mask);
+        }
+    }
+    __device__ __forceinline__ static std::uint32_t claim(unsigned int *counter)
+    {
+        if constexpr (CTA) {
+            __shared__ unsigned int claimed;
+            if (threadIdx.x == 0u) {
+                claimed = atomicAdd(counter, 1u);
+            }
+            __syncthreads();
+            const unsigned int c = claimed;
+            __syncthreads();
+            return c;
+        } else {
+            return claim_chunk_warp(counter);
+        }
+    }
+};
+
 template <bool PROP>
 __global__ void __launch_bounds__(256) k_hbm(program P, batch D, run_args R, double *scratch, std::size_t slab_doubles)
 {
@@ -545,11 +613,12 @@ __device__ __forceinline__ void coop_jet(const program &P, const coop_header &H,
                                          const batch &D, const coop_smem<L> &S, std::uint32_t lane0, double *gtape,
                                          std::uint32_t tm_r2, const coef_view &cv)
 {
-    constexpr bool GEN = MODE == 1 || MODE == 4;
+    constexpr bool GEN = MODE == 1 || MODE == 4 || MODE == 5;
     constexpr bool TMEM = MODE == 2 || MODE == 3;
+    using T = team<MODE == 5>;
     constexpr std::uint32_t G = L / N; // lane groups per warp
-    const std::uint32_t tid = threadIdx.x & 31u;
-    constexpr std::uint32_t nthr = 32u;
+    const std::uint32_t tid = T::tid();
+    const std::uint32_t nthr = T::size();
     const std::uint32_t pp1 = P.order + 1u, p = P.order;
     const uint4 *ops = reinterpret_cast<const uint4 *>(tab + H.off_ops);
     const std::uint32_t *seg = tab + H.off_seg;
@@ -633,7 +702,7 @@ __device__ __forceinline__ void coop_jet(const program &P, const coop_header &H,
             write_tc(sv, 1u, vp);
         }
     }
-    __syncwarp();
+    T::sync();
 
     // The generic per-order pass for the state variables that no producer takes care of.
     const auto sv_pass = [&](std::uint32_t n) {
@@ -645,7 +714,7 @@ __device__ __forceinline__ void coop_jet(const program &P, const coop_header &H,
             t.row(e.x).set(n, v);
             write_tc(sv, n, v);
         }
-        __syncwarp();
+        T::sync();
     };
 
     for (std::uint32_t n = 0; n < p; ++n) {
@@ -661,7 +730,7 @@ __device__ __forceinline__ void coop_jet(const program &P, const coop_header &H,
                     const bool active = tid < cnt;
                     const uint4 op = ops[2u * (b + (active ? tid : cnt - 1u) / G)];
                     fused_nbody_pair_tmem<N, TMEM ? MODE - 2 : 0>(P, t, aux + op.y, op.z, op.w != 0u, n, sv_out, active, tm_r2);
-                    __syncwarp();
+                    T::sync();
                     continue;
                 }
                 // The other levels of a superinstruction-only program: sums of single-slot rows.
@@ -674,7 +743,7 @@ __device__ __forceinline__ void coop_jet(const program &P, const coop_header &H,
                         sv_out_s(op2.y, v, n);
                     }
                 }
-                __syncwarp();
+                T::sync();
                 continue;
             }
             for (std::uint32_t it = tid; it < (e - b) * G; it += nthr) {
@@ -701,7 +770,7 @@ __device__ __forceinline__ void coop_jet(const program &P, const coop_header &H,
                     }
                 }
             }
-            __syncwarp();
+            T::sync();
         }
     }
     if (H.n_svphase != 0u) {
@@ -748,24 +817,24 @@ __device__ __forceinline__ double coop_determine_h(const program &P, const batch
 // State update of the warp's lanes: item = (state variable, lane); S.h holds the step sizes, S.running
 // which lanes may be written. Sets bit l of nf_mask if this thread produced a non-finite value for lane l.
 // A thread evaluates up to three polynomials side by side (their coefficients come from L2).
-template <int L>
+template <int L, bool CTA = false>
 __device__ __forceinline__ void coop_update_state(const program &P, const batch &D, const coop_smem<L> &S,
                                                   const coef_view &cv, std::uint32_t lane0, unsigned &nf_mask)
 {
     constexpr int K = 3;
-    const std::uint32_t tid = threadIdx.x & 31u;
+    const std::uint32_t tid = CTA ? threadIdx.x : (threadIdx.x & 31u), nthr = CTA ? blockDim.x : 32u;
     const std::uint32_t l = tid % L, n_items = P.n_eq * L;
     const std::uint32_t glane_raw = lane0 + l;
     const bool lane_active = glane_raw < D.n && S.running[l] != 0;
     const std::uint32_t glane = glane_raw < D.n ? glane_raw : D.n - 1u;
     const double h = S.h[l];
     const std::size_t n = D.n;
-    for (std::uint32_t base = tid; base < n_items; base += 32u * K) {
+    for (std::uint32_t base = tid; base < n_items; base += nthr * K) {
         const double *c[K];
         bool act[K];
 #pragma unroll
         for (int k = 0; k < K; ++k) {
-            const std::uint32_t it = base + 32u * static_cast<std::uint32_t>(k);
+            const std::uint32_t it = base + nthr * static_cast<std::uint32_t>(k);
             act[k] = it < n_items;
             const std::uint32_t sv = act[k] ? it / L : 0u;
             c[k] = cv.base + sv * cv.stride_sv + cv.lane_off(glane, l);
@@ -775,7 +844,7 @@ __device__ __forceinline__ void coop_update_state(const program &P, const batch 
 #pragma unroll
         for (int k = 0; k < K; ++k) {
             if (act[k] && lane_active) {
-                const std::uint32_t sv = (base + 32u * static_cast<std::uint32_t>(k)) / L;
+                const std::uint32_t sv = (base + nthr * static_cast<std::uint32_t>(k)) / L;
                 D.state[static_cast<std::size_t>(sv) * n + glane] = res[k];
                 if (!isfinite(res[k])) {
                     nf_mask |= 1u << l;
@@ -794,7 +863,10 @@ __global__ void __launch_bounds__(MAXT, 1)
     constexpr bool TMEM = MODE == 2 || MODE == 3;
     // MODE 4: systems whose compact tape does not fit in shared memory. Same kernel, but the warp's tape lives in
     // a per-warp slab of global memory (gscratch) and the program tables are read in place (L1 / L2).
-    constexpr bool GLOBAL = MODE == 4;
+    constexpr bool GLOBAL = MODE == 4 || MODE == 5;
+    // MODE 5: idem, and the whole CTA works on one chunk of lanes (see team<>).
+    constexpr bool CTA = MODE == 5;
+    using T = team<CTA>;
     extern __shared__ __align__(16) double smem_raw[];
     const std::uint32_t n_words = __ldg(blob);
     const std::uint32_t *tab = blob;
@@ -825,8 +897,8 @@ __global__ void __launch_bounds__(MAXT, 1)
     }
     const coop_header H = *reinterpret_cast<const coop_header *>(tab);
 
-    const std::uint32_t tid = threadIdx.x & 31u;
-    const std::size_t warp_global = (static_cast<std::size_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const std::uint32_t tid = T::tid();
+    const std::size_t warp_global = T::index();
     // Shared memory: tables rounded up to 16 bytes, then one region per warp. Global mode: one slab per warp.
     const std::size_t tab_doubles = static_cast<std::size_t>(n_words + 3u) / 4u * 2u;
     const coop_smem<L> S(GLOBAL ? gscratch + warp_global * coop_smem<L>::warp_doubles(H.n_slots)
@@ -839,17 +911,15 @@ __global__ void __launch_bounds__(MAXT, 1)
     // The warp's slice of the overflow tape.
     double *gtape = (!GLOBAL && H.n_gslots != 0u)
                         ? gscratch
-                              + ((static_cast<std::size_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5)
-                                    * (static_cast<std::size_t>(H.n_gslots) * L)
+                              + warp_global * (static_cast<std::size_t>(H.n_gslots) * L)
                         : nullptr;
 
     // Coefficient store: public tc or the warp's private slice (see coef_view; strides precomputed by the host).
-    const coef_view cv{R.coef_base
-                           + ((static_cast<std::size_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5) * R.coef_warp_stride,
+    const coef_view cv{R.coef_base + warp_global * R.coef_warp_stride,
                        static_cast<std::size_t>(R.coef_stride_sv), static_cast<std::size_t>(R.coef_stride_o),
                        R.coef_pub != 0};
 
-    for (std::uint32_t chunk = claim_chunk_warp(R.counter); chunk < n_chunks; chunk = claim_chunk_warp(R.counter)) {
+    for (std::uint32_t chunk = T::claim(R.counter); chunk < n_chunks; chunk = T::claim(R.counter)) {
         const std::uint32_t lane0 = chunk * L;
         // Owner threads (one per lane) do the scalar bookkeeping of their lane.
         const std::uint32_t lane_raw = lane0 + tid;
@@ -865,16 +935,16 @@ __global__ void __launch_bounds__(MAXT, 1)
                 S.time[tid] = t0.hi;
                 S.running[tid] = 1;
             }
-            __syncwarp();
+            T::sync();
             coop_jet<L, N, MODE>(P, H, tab, D, S, lane0, gtape, tm_r2, cv);
-            const double h = coop_determine_h<L>(P, D, cv, lane0, mdt);
+            const double h = (!CTA || threadIdx.x < 32u) ? coop_determine_h<L>(P, D, cv, lane0, mdt) : 0.;
             if (owner) {
                 S.h[tid] = h;
             }
-            __syncwarp();
+            T::sync();
             unsigned nf_mask = 0u;
-            coop_update_state<L>(P, D, S, cv, lane0, nf_mask);
-            nf_mask = __reduce_or_sync(0xffffffffu, nf_mask);
+            coop_update_state<L, CTA>(P, D, S, cv, lane0, nf_mask);
+            nf_mask = T::template reduce_or<L>(nf_mask);
             if (valid) {
                 const dfl nt = dfl_add(t0, dfl{h, 0.});
                 D.t_hi[lane] = nt.hi;
@@ -890,23 +960,23 @@ __global__ void __launch_bounds__(MAXT, 1)
             if (owner) {
                 lp.init(D, R, lane);
             }
-            while (__any_sync(0xffffffffu, owner && lp.running)) {
+            while (T::any(owner && lp.running)) {
                 double cur_max = 0.;
                 if (owner) {
                     cur_max = lp.cur_max();
                     S.time[tid] = lp.t.hi;
                     S.running[tid] = lp.running ? 1 : 0;
                 }
-                __syncwarp();
+                T::sync();
                 coop_jet<L, N, MODE>(P, H, tab, D, S, lane0, gtape, tm_r2, cv);
-                const double h = coop_determine_h<L>(P, D, cv, lane0, cur_max);
+                const double h = (!CTA || threadIdx.x < 32u) ? coop_determine_h<L>(P, D, cv, lane0, cur_max) : 0.;
                 if (owner) {
                     S.h[tid] = h;
                 }
-                __syncwarp();
+                T::sync();
                 unsigned nf_mask = 0u;
-                coop_update_state<L>(P, D, S, cv, lane0, nf_mask);
-                nf_mask = __reduce_or_sync(0xffffffffu, nf_mask);
+                coop_update_state<L, CTA>(P, D, S, cv, lane0, nf_mask);
+                nf_mask = T::template reduce_or<L>(nf_mask);
                 if (owner && lp.running) {
                     lp.advance(h, cur_max, ((nf_mask >> tid) & 1u) != 0u, R, valid);
                 }
@@ -915,7 +985,7 @@ __global__ void __launch_bounds__(MAXT, 1)
                 lp.store(D, lane);
             }
         }
-        __syncwarp();
+        T::sync();
     }
     if constexpr (TMEM) {
         tm::fence_before_sync();

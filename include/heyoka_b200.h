@@ -258,13 +258,14 @@ int hy_batch_set_launch_config(hy_batch *, uint32_t block_threads, uint32_t bloc
 /* Kernel selection. tape_mode: 0 = automatic (shared-memory tape when the system's tape fits in an SM's shared
  * memory, else mode 4), 1 = force the one-thread-per-lane HBM-tape kernel, 2 = force the shared-memory kernel (error if it
  * does not fit), 3 = idem, but never keep rows in tensor memory, 4 = the same warp-cooperative kernel with the
- * tape in global memory (what the automatic mode picks when shared memory is too small). lanes_per_warp (1..32, power of two) / lanes_per_thread (1, 2 or 4, dividing lanes_per_warp)
+ * tape in global memory, 5 = idem with a whole CTA (instead of a warp) working on a chunk of lanes; the automatic
+ * mode picks 4 or 5 when shared memory is too small. lanes_per_warp (1..32, power of two) / lanes_per_thread (1, 2 or 4, dividing lanes_per_warp)
  * only apply to the shared-memory kernel; 0 = automatic. block_threads = 32 x warps per block.
  * The environment variable HEYOKA_B200_TAPE=hbm|smem sets the default. */
 int hy_batch_set_kernel(hy_batch *, int tape_mode, uint32_t lanes_per_warp, uint32_t lanes_per_thread,
                         uint32_t block_threads, uint32_t blocks_per_sm);
 typedef struct hy_kernel_info {
-    int32_t tape_mode;            /* 1 = HBM tape (thread per lane), 2 = shared-memory tape, 4 = cooperative, global tape */
+    int32_t tape_mode;            /* 1 = HBM tape (thread per lane), 2 = shared-memory tape, 4 / 5 = cooperative, global tape (warp / CTA teams) */
     uint32_t lanes_per_warp, lanes_per_thread, block_threads, blocks_per_sm, grid;
     uint64_t smem_bytes;          /* dynamic shared memory per CTA */
     uint32_t tape_slots_per_lane; /* doubles of tape per lane in the selected strategy */

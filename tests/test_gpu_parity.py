@@ -23,6 +23,7 @@ OC = {"success": hb.taylor_outcome.success, "time_limit": hb.taylor_outcome.time
 KERNELS = {
     "hbm": dict(tape="hbm"),
     "global": dict(tape="global"),  # the cooperative kernel with the tape in global memory
+    "global-cta": dict(tape="global-cta"),  # idem, a whole CTA per chunk of lanes
     "smem-auto": dict(tape="smem"),  # tensor memory for the pair interactions where it applies
     "smem-notmem": dict(tape="smem-notmem"),
     "smem-L8N2": dict(tape="smem", lanes_per_warp=8, lanes_per_thread=2),
@@ -308,7 +309,7 @@ def test_kernel_selection_info():
     b.set_kernel("hbm")
     assert b.kernel_info()["tape"] == "hbm"
     big = hb.Batch(hb.Program(hb.model.nbody(32)), 32)
-    assert big.kernel_info()["tape"] == "global"
+    assert big.kernel_info()["tape"] == "global-cta"  # 496 pair interactions per level, 32 lanes
     big.set_kernel("hbm")
     assert big.kernel_info()["tape"] == "hbm"
     with pytest.raises(ValueError, match="does not fit in shared memory"):
@@ -441,7 +442,7 @@ def test_nbody32_parity():
     P = hb.Program(sys_nbody32(), high_accuracy=False)
     assert (P.n_eq, P.order) == (192, 20)
     ta = hb.taylor_adaptive_batch(sys_nbody32(), st, batch)
-    assert ta._b.kernel_info()["tape"] == "global"
+    assert ta._b.kernel_info()["tape"] == "global-cta"
     o = oracle.OracleIntegrator(P, st, batch, mode=oracle.FMA)
     ta.step(write_tc=True)
     o.step(write_tc=True)
