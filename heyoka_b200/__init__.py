@@ -16,7 +16,7 @@ from ._capi import lib, check, HyError  # noqa: F401
 
 __all__ = [
     "expression", "make_vars", "par", "time", "sin", "cos", "tanh", "exp", "log", "sigmoid", "relu", "relup", "sqrt", "square", "pow", "sum",
-    "prod", "model", "taylor_adaptive_batch", "taylor_outcome", "Program", "Batch", "order_from_tol", "HyError",
+    "prod", "model", "taylor_adaptive_batch", "continuous_output_batch", "taylor_outcome", "Program", "Batch", "order_from_tol", "HyError",
 ]
 
 
@@ -379,6 +379,15 @@ class Batch:
                                                int(write_tc), C.byref(flag)))
         return flag.value
 
+    def propagate_until_cout(self, t_hi, t_lo=None, max_delta_t=None, max_steps=0):
+        """propagate_until() with continuous output (lock-step loop); returns a continuous_output_batch or None."""
+        f = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float64)  # noqa: E731
+        th, tl, md = f(t_hi), f(t_lo), f(max_delta_t)
+        h = C.c_void_p()
+        check(lib.hy_batch_propagate_until_cout(self._h, _dptr(th), None if tl is None else _dptr(tl),
+                                                None if md is None else _dptr(md), int(max_steps), C.byref(h)))
+        return continuous_output_batch(h, self.program.n_eq, self.n) if h.value else None
+
     def propagate_grid(self, grid, max_delta_t=None, max_steps=0):
         """grid: [n_pts, batch]; returns the states at the grid points, [n_pts, n_eq, batch] (NaN where not reached)."""
         grid = np.ascontiguousarray(grid, dtype=np.float64)
@@ -405,6 +414,40 @@ class Batch:
 # ------------------------------------------------------------------------------------------------
 # taylor_adaptive_batch: host-mirrored integrator with the reference's surface.
 # ------------------------------------------------------------------------------------------------
+class continuous_output_batch:
+    """Continuous output of a propagate_until() (include/heyoka/continuous_output.hpp): callable with one time or
+    one time per lane, returns the state [n_eq, batch] at those times (dense output of the step that contains them)."""
+
+    def __init__(self, handle, n_eq, batch):
+        self._h, self._n_eq, self._n = handle, n_eq, batch
+        self._output = np.zeros((n_eq, batch))
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib.hy_cout_destroy(self._h)
+            self._h = None
+
+    def __call__(self, tm):
+        t = np.ascontiguousarray(np.broadcast_to(np.asarray(tm, dtype=np.float64), (self._n,)))
+        check(lib.hy_cout_eval(self._h, _dptr(t), _dptr(self._output)))
+        return self._output
+
+    @property
+    def output(self):
+        return self._output
+
+    def get_bounds(self):
+        lb, ub = np.empty(self._n), np.empty(self._n)
+        check(lib.hy_cout_get_bounds(self._h, _dptr(lb), _dptr(ub)))
+        return lb, ub
+
+    def get_n_steps(self):
+        return int(lib.hy_cout_n_steps(self._h))
+
+    def get_batch_size(self):
+        return self._n
+
+
 class taylor_adaptive_batch:
     """Mirror of heyoka::taylor_adaptive_batch<double> (include/heyoka/taylor.hpp:780-1121).
 
@@ -571,8 +614,8 @@ class taylor_adaptive_batch:
         self._step_res = list(zip(oc.tolist(), h.tolist()))
 
     def propagate_until(self, ts, max_steps=0, max_delta_t=None, write_tc=False, callback=None, c_output=False):
-        if callback is not None or c_output:
-            raise NotImplementedError("Callbacks and continuous output are not supported by the fused propagate kernel")
+        if callback is not None:
+            raise NotImplementedError("Callbacks are not supported by the Python mirror (use the C++ class)")
         n = self._batch_size
         if np.ndim(ts) == 0:
             th, tl = np.full(n, float(ts)), None
@@ -594,10 +637,17 @@ class taylor_adaptive_batch:
                                  "batch size is %d, but the number of specified timesteps is %d" % (n, md.size))
             max_delta_t = md
         self._push()
-        self._b.propagate_until(th, tl, max_delta_t, max_steps, write_tc)
+        c_out = None
+        if c_output:
+            # (The lock-step loop writes the Taylor coefficients at every iteration.)
+            c_out = self._b.propagate_until_cout(th, tl, max_delta_t, max_steps)
+            write_tc = True
+        else:
+            self._b.propagate_until(th, tl, max_delta_t, max_steps, write_tc)
         self._pull(write_tc)
         oc, mn, mx, ns = self._b.prop_res()
         self._prop_res = list(zip(oc.tolist(), mn.tolist(), mx.tolist(), ns.tolist()))
+        return c_out
 
     def propagate_grid(self, grid, max_steps=0, max_delta_t=None, callback=None):
         """States at the grid points, shape [n_pts, n_eq, batch] (src/taylor_adaptive_batch.cpp:1545-2055).
@@ -635,7 +685,7 @@ class taylor_adaptive_batch:
             raise ValueError("Invalid number of time intervals specified in a Taylor integrator in batch mode: the "
                              "batch size is %d, but the number of specified time intervals is %d" % (n, d.size))
         hi, lo = _dfloat_add(self._t_hi, self._t_lo, d, np.zeros(n))
-        self.propagate_until((hi, lo), **kw)
+        return self.propagate_until((hi, lo), **kw)
 
     def update_d_output(self, t, rel_time=False):
         """Dense output at time(s) t from the last written tc (src/taylor_adaptive_batch.cpp:2251-2327)."""

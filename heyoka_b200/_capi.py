@@ -90,6 +90,11 @@ SIGNATURES = {
     "hy_batch_propagate_until": (C.c_int, [_vp, _dp, _dp, _dp, C.c_uint64, C.c_int]),
     "hy_batch_propagate_until_dev": (C.c_int, [_vp, _dp, _dp, _dp, C.c_uint64, C.c_int, C.POINTER(C.c_int)]),
     "hy_batch_propagate_grid": (C.c_int, [_vp, _dp, C.c_uint64, _dp, C.c_uint64, _dp]),
+    "hy_batch_propagate_until_cout": (C.c_int, [_vp, _dp, _dp, _dp, C.c_uint64, _vpp]),
+    "hy_cout_eval": (C.c_int, [_vp, _dp, _dp]),
+    "hy_cout_get_bounds": (C.c_int, [_vp, _dp, _dp]),
+    "hy_cout_n_steps": (C.c_uint64, [_vp]),
+    "hy_cout_destroy": (None, [_vp]),
     "hy_batch_d_output": (C.c_int, [_vp, _dp, _dp]),
     "hy_batch_launch_count": (C.c_int, [_vp, C.POINTER(C.c_uint64)]),
     "hy_batch_set_launch_config": (C.c_int, [_vp, C.c_uint32, C.c_uint32]),

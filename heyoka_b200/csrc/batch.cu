@@ -1404,6 +1404,247 @@ int hy_batch_propagate_grid(hy_batch *b, const double *grid, uint64_t n_pts, con
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Continuous output.
+// ------------------------------------------------------------------------------------------------
+struct hy_cout {
+    int device = 0;
+    std::uint32_t n = 0, n_eq = 0, order = 0;
+    std::uint64_t n_steps = 0; // recorded iterations; times have n_steps + 2 rows (start, ..., padding)
+    dev::program prog{};
+    double *d_tcs = nullptr, *d_t_hi = nullptr, *d_t_lo = nullptr, *d_tm = nullptr, *d_out = nullptr;
+    ~hy_cout()
+    {
+        for (double *ptr : {d_tcs, d_t_hi, d_t_lo, d_tm, d_out}) {
+            if (ptr != nullptr) {
+                cudaFree(ptr);
+            }
+        }
+    }
+};
+
+int hy_batch_propagate_until_cout(hy_batch *b, const double *t_final_hi, const double *t_final_lo,
+                                  const double *max_delta_t, uint64_t max_steps, hy_cout **out)
+{
+    std::vector<double *> tc_blocks, th_blocks; // one device block per recorded iteration
+    double *d_lane = nullptr;
+    unsigned char *d_dir = nullptr;
+    unsigned *d_pflags = nullptr;
+    const auto cleanup = [&]() {
+        for (auto *ptr : tc_blocks) {
+            cudaFree(ptr);
+        }
+        for (auto *ptr : th_blocks) {
+            cudaFree(ptr);
+        }
+        for (void *ptr : {static_cast<void *>(d_lane), static_cast<void *>(d_dir), static_cast<void *>(d_pflags)}) {
+            if (ptr != nullptr) {
+                cudaFree(ptr);
+            }
+        }
+    };
+    try {
+        if (b == nullptr || t_final_hi == nullptr || out == nullptr) {
+            throw std::invalid_argument("Null pointer passed to hy_batch_propagate_until_cout()");
+        }
+        *out = nullptr;
+        device_guard guard(b->device);
+        const std::uint32_t n = b->n;
+        // Argument checks of propagate_until_impl(), src/taylor_adaptive_batch.cpp:1212-1241.
+        for (std::uint32_t i = 0; i < n; ++i) {
+            if (!std::isfinite(t_final_hi[i]) || (t_final_lo != nullptr && !std::isfinite(t_final_lo[i]))) {
+                throw std::invalid_argument("A non-finite time was passed to the propagate_until() function of an "
+                                            "adaptive Taylor integrator in batch mode");
+            }
+            if (max_delta_t != nullptr) {
+                if (std::isnan(max_delta_t[i])) {
+                    throw std::invalid_argument("A nan max_delta_t was passed to the propagate_until() function of an "
+                                                "adaptive Taylor integrator in batch mode");
+                }
+                if (max_delta_t[i] <= 0) {
+                    throw std::invalid_argument("A non-positive max_delta_t was passed to the propagate_until() "
+                                                "function of an adaptive Taylor integrator in batch mode");
+                }
+            }
+        }
+        // rem_hi, rem_lo, dt_limit, max_delta_t, tf_hi, tf_lo
+        HY_CUDA_CHECK(cudaMalloc(&d_lane, sizeof(double) * 6u * n));
+        HY_CUDA_CHECK(cudaMalloc(&d_dir, n));
+        HY_CUDA_CHECK(cudaMalloc(&d_pflags, sizeof(unsigned) * 4u));
+        HY_CUDA_CHECK(cudaMemcpyAsync(d_lane + 4u * n, t_final_hi, sizeof(double) * n, cudaMemcpyHostToDevice, b->stream));
+        if (t_final_lo != nullptr) {
+            HY_CUDA_CHECK(cudaMemcpyAsync(d_lane + 5u * n, t_final_lo, sizeof(double) * n, cudaMemcpyHostToDevice,
+                                          b->stream));
+        }
+        if (max_delta_t != nullptr) {
+            HY_CUDA_CHECK(cudaMemcpyAsync(d_lane + 3u * n, max_delta_t, sizeof(double) * n, cudaMemcpyHostToDevice,
+                                          b->stream));
+        }
+        dev::prop_state G{};
+        G.tf_hi = d_lane + 4u * n;
+        G.tf_lo = t_final_lo != nullptr ? d_lane + 5u * n : nullptr;
+        G.max_delta_t = max_delta_t != nullptr ? d_lane + 3u * n : nullptr;
+        G.rem_hi = d_lane;
+        G.rem_lo = d_lane + n;
+        G.t_dir = d_dir;
+        G.dt_limit = d_lane + 2u * n;
+        G.flags = d_pflags;
+        const unsigned gb = (n + 127u) / 128u;
+        const std::size_t tc_doubles = static_cast<std::size_t>(b->n_eq) * (b->order + 1u) * n;
+        unsigned hflags[4] = {0u, 0u, 0u, 0u};
+        const auto read_flags = [&]() {
+            HY_CUDA_CHECK(cudaMemcpyAsync(hflags, d_pflags, sizeof(hflags), cudaMemcpyDeviceToHost, b->stream));
+            HY_CUDA_CHECK(cudaStreamSynchronize(b->stream));
+        };
+        // Row 0 of the times: the starting time.
+        const auto push_times = [&]() {
+            double *blk = nullptr;
+            HY_CUDA_CHECK(cudaMalloc(&blk, sizeof(double) * 2u * n));
+            th_blocks.push_back(blk);
+            HY_CUDA_CHECK(cudaMemcpyAsync(blk, b->d_t_hi, sizeof(double) * n, cudaMemcpyDeviceToDevice, b->stream));
+            HY_CUDA_CHECK(cudaMemcpyAsync(blk + n, b->d_t_lo, sizeof(double) * n, cudaMemcpyDeviceToDevice, b->stream));
+        };
+        push_times();
+        HY_CUDA_CHECK(cudaMemsetAsync(d_pflags, 0, sizeof(hflags), b->stream));
+        dev::k_prop_init<<<gb, 128, 0, b->stream>>>(b->view(), G, b->d_prop_min_h, b->d_prop_max_h, b->d_prop_n_steps);
+        HY_CUDA_CHECK(cudaGetLastError());
+        read_flags();
+        if (hflags[2] != 0u) {
+            throw std::invalid_argument("The final time passed to the propagate_until() function of an adaptive "
+                                        "Taylor integrator in batch mode results in an overflow condition");
+        }
+        std::uint64_t iter = 0;
+        while (true) {
+            dev::run_args R{};
+            R.max_delta_t = G.dt_limit;
+            R.default_max_delta_t = std::numeric_limits<double>::infinity();
+            R.write_tc = 1;
+            R.flags = b->d_flags;
+            R.counter = b->d_counter;
+            b->launch(false, R);
+            HY_CUDA_CHECK(cudaMemsetAsync(d_pflags, 0, sizeof(unsigned) * 2u, b->stream));
+            dev::k_prop_book<<<gb, 128, 0, b->stream>>>(b->view(), G, b->d_prop_outcome, b->d_prop_min_h,
+                                                         b->d_prop_max_h, b->d_prop_n_steps);
+            HY_CUDA_CHECK(cudaGetLastError());
+            read_flags();
+            if (hflags[1] != 0u) {
+                break; // non-finite state: this iteration is not recorded (:1462-1467)
+            }
+            // update_c_out(), :1320-1346.
+            {
+                double *blk = nullptr;
+                HY_CUDA_CHECK(cudaMalloc(&blk, sizeof(double) * tc_doubles));
+                tc_blocks.push_back(blk);
+                HY_CUDA_CHECK(cudaMemcpyAsync(blk, b->d_tc, sizeof(double) * tc_doubles, cudaMemcpyDeviceToDevice,
+                                              b->stream));
+                push_times();
+            }
+            ++iter;
+            if (hflags[0] == n) {
+                break; // every lane reached its final time
+            }
+            if (iter == max_steps) {
+                dev::k_fill_outcome<<<(n + 255u) / 256u, 256, 0, b->stream>>>(b->d_prop_outcome, n,
+                                                                              HY_OUTCOME_STEP_LIMIT);
+                break;
+            }
+        }
+        if (!tc_blocks.empty()) {
+            // make_c_out(), :1277-1317: contiguous arrays, padding row +-inf by direction.
+            auto co = std::make_unique<hy_cout>();
+            co->device = b->device;
+            co->n = n;
+            co->n_eq = b->n_eq;
+            co->order = b->order;
+            co->n_steps = tc_blocks.size();
+            co->prog = b->prog;
+            const std::size_t rows = tc_blocks.size() + 2u;
+            HY_CUDA_CHECK(cudaMalloc(&co->d_tcs, sizeof(double) * tc_doubles * tc_blocks.size()));
+            HY_CUDA_CHECK(cudaMalloc(&co->d_t_hi, sizeof(double) * rows * n));
+            HY_CUDA_CHECK(cudaMalloc(&co->d_t_lo, sizeof(double) * rows * n));
+            HY_CUDA_CHECK(cudaMalloc(&co->d_tm, sizeof(double) * n));
+            HY_CUDA_CHECK(cudaMalloc(&co->d_out, sizeof(double) * static_cast<std::size_t>(b->n_eq) * n));
+            for (std::size_t k = 0; k < tc_blocks.size(); ++k) {
+                HY_CUDA_CHECK(cudaMemcpyAsync(co->d_tcs + k * tc_doubles, tc_blocks[k], sizeof(double) * tc_doubles,
+                                              cudaMemcpyDeviceToDevice, b->stream));
+            }
+            for (std::size_t k = 0; k < th_blocks.size(); ++k) {
+                HY_CUDA_CHECK(cudaMemcpyAsync(co->d_t_hi + k * n, th_blocks[k], sizeof(double) * n,
+                                              cudaMemcpyDeviceToDevice, b->stream));
+                HY_CUDA_CHECK(cudaMemcpyAsync(co->d_t_lo + k * n, th_blocks[k] + n, sizeof(double) * n,
+                                              cudaMemcpyDeviceToDevice, b->stream));
+            }
+            std::vector<unsigned char> dir(n);
+            HY_CUDA_CHECK(cudaMemcpyAsync(dir.data(), d_dir, n, cudaMemcpyDeviceToHost, b->stream));
+            HY_CUDA_CHECK(cudaStreamSynchronize(b->stream));
+            std::vector<double> pad(n), zero(n, 0.);
+            for (std::uint32_t i = 0; i < n; ++i) {
+                pad[i] = dir[i] != 0 ? std::numeric_limits<double>::infinity() : -std::numeric_limits<double>::infinity();
+            }
+            HY_CUDA_CHECK(cudaMemcpy(co->d_t_hi + (rows - 1u) * n, pad.data(), sizeof(double) * n, cudaMemcpyHostToDevice));
+            HY_CUDA_CHECK(cudaMemcpy(co->d_t_lo + (rows - 1u) * n, zero.data(), sizeof(double) * n, cudaMemcpyHostToDevice));
+            *out = co.release();
+        }
+        HY_CUDA_CHECK(cudaStreamSynchronize(b->stream));
+        cleanup();
+        return HY_OK;
+    } catch (...) {
+        cleanup();
+        return translate_exception();
+    }
+}
+
+int hy_cout_eval(hy_cout *c, const double *tm, double *out)
+{
+    try {
+        if (c == nullptr || tm == nullptr || out == nullptr) {
+            throw std::invalid_argument("Null pointer passed to hy_cout_eval()");
+        }
+        for (std::uint32_t i = 0; i < c->n; ++i) {
+            if (!std::isfinite(tm[i])) {
+                throw std::invalid_argument("Cannot compute the continuous output in batch mode for the batch index "
+                                            + std::to_string(i) + " at the non-finite time "
+                                            + hy::detail::fmt_double(tm[i]));
+            }
+        }
+        device_guard guard(c->device);
+        HY_CUDA_CHECK(cudaMemcpy(c->d_tm, tm, sizeof(double) * c->n, cudaMemcpyHostToDevice));
+        dev::k_cout_eval<<<(c->n + 127u) / 128u, 128>>>(c->prog, c->n, static_cast<std::uint32_t>(c->n_steps + 2u),
+                                                         c->d_tcs, c->d_t_hi, c->d_t_lo, c->d_tm, c->d_out);
+        HY_CUDA_CHECK(cudaGetLastError());
+        HY_CUDA_CHECK(cudaMemcpy(out, c->d_out, sizeof(double) * static_cast<std::size_t>(c->n_eq) * c->n,
+                                 cudaMemcpyDeviceToHost));
+        return HY_OK;
+    } catch (...) {
+        return translate_exception();
+    }
+}
+
+int hy_cout_get_bounds(const hy_cout *c, double *lb, double *ub)
+{
+    try {
+        if (c == nullptr || lb == nullptr || ub == nullptr) {
+            throw std::invalid_argument("Null pointer passed to hy_cout_get_bounds()");
+        }
+        device_guard guard(c->device);
+        HY_CUDA_CHECK(cudaMemcpy(lb, c->d_t_hi, sizeof(double) * c->n, cudaMemcpyDeviceToHost));
+        HY_CUDA_CHECK(cudaMemcpy(ub, c->d_t_hi + c->n_steps * c->n, sizeof(double) * c->n, cudaMemcpyDeviceToHost));
+        return HY_OK;
+    } catch (...) {
+        return translate_exception();
+    }
+}
+
+uint64_t hy_cout_n_steps(const hy_cout *c)
+{
+    return c != nullptr ? c->n_steps : 0u;
+}
+
+void hy_cout_destroy(hy_cout *c)
+{
+    delete c;
+}
+
 int hy_batch_d_output(hy_batch *b, const double *tau, double *out)
 {
     try {

@@ -135,6 +135,112 @@ __global__ void k_grid_sample(program P, batch D, grid_state G)
     G.dt_limit[lane] = step_limit(G.t_dir[lane] != 0, rem, mdt);
 }
 
+// ---- propagate_until() with continuous output: the reference's lock-step loop
+// (src/taylor_adaptive_batch.cpp:1372-1527), per-lane bookkeeping on the device. ----
+struct prop_state {
+    const double *tf_hi, *tf_lo; // final times (tf_lo may be nullptr)
+    const double *max_delta_t;   // positive per-lane limits or nullptr (+inf)
+    double *rem_hi, *rem_lo;
+    unsigned char *t_dir;
+    double *dt_limit;  // signed limit of the next step
+    unsigned *flags;   // [0] number of lanes done at this iteration, [1] non-finite state, [2] overflow of rem
+};
+
+__global__ void k_prop_init(batch D, prop_state G, double *min_h, double *max_h, unsigned long long *ts_count)
+{
+    const std::uint32_t lane = blockIdx.x * blockDim.x + threadIdx.x;
+    if (lane >= D.n) {
+        return;
+    }
+    const dfl rem = dfl_sub(dfl{G.tf_hi[lane], G.tf_lo != nullptr ? G.tf_lo[lane] : 0.}, dfl{D.t_hi[lane], D.t_lo[lane]});
+    if (!(isfinite(rem.hi) && isfinite(rem.lo))) {
+        atomicOr(G.flags + 2, 1u);
+    }
+    G.rem_hi[lane] = rem.hi;
+    G.rem_lo[lane] = rem.lo;
+    const bool dir = dfl_ge0(rem);
+    G.t_dir[lane] = dir ? 1 : 0;
+    min_h[lane] = CUDART_INF;
+    max_h[lane] = 0.;
+    ts_count[lane] = 0ull;
+    G.dt_limit[lane] = step_limit(dir, rem, G.max_delta_t != nullptr ? G.max_delta_t[lane] : CUDART_INF);
+}
+
+// After a lock-step step (:1402-1460): counters, min/max |h|, remaining time, outcome, limit of the next step.
+__global__ void k_prop_book(batch D, prop_state G, long long *outcome, double *min_h, double *max_h,
+                            unsigned long long *ts_count)
+{
+    const std::uint32_t lane = blockIdx.x * blockDim.x + threadIdx.x;
+    if (lane >= D.n) {
+        return;
+    }
+    const long long oc = D.step_outcome[lane];
+    const double h = D.last_h[lane];
+    if (oc == HY_OUTCOME_ERR_NF_STATE) {
+        atomicOr(G.flags + 1, 1u);
+    } else {
+        ts_count[lane] += (h != 0.) ? 1ull : 0ull;
+        if (oc == HY_OUTCOME_SUCCESS) {
+            const double ah = fabs(h);
+            min_h[lane] = fmin(min_h[lane], ah);
+            max_h[lane] = fmax(max_h[lane], ah);
+        }
+        dfl rem{0., 0.};
+        if (h == G.rem_hi[lane]) {
+            atomicAdd(G.flags, 1u);
+        } else {
+            rem = dfl_sub(dfl{G.tf_hi[lane], G.tf_lo != nullptr ? G.tf_lo[lane] : 0.}, dfl{D.t_hi[lane], D.t_lo[lane]});
+        }
+        G.rem_hi[lane] = rem.hi;
+        G.rem_lo[lane] = rem.lo;
+        G.dt_limit[lane]
+            = step_limit(G.t_dir[lane] != 0, rem, G.max_delta_t != nullptr ? G.max_delta_t[lane] : CUDART_INF);
+    }
+    outcome[lane] = oc;
+}
+
+// Evaluation of a continuous output (src/continuous_output.cpp:640-960): per lane, upper_bound of the time in the
+// lane's column of the (padded) times, the Taylor coefficients of the step that contains it, Horner / compensated
+// summation at h = t - start of that step. times: [n_rows][batch] with n_rows = n_steps + 2 (padding included);
+// tcs: [n_steps][n_eq][order + 1][batch].
+__global__ void k_cout_eval(program P, std::uint32_t n, std::uint32_t n_rows, const double *tcs, const double *t_hi,
+                            const double *t_lo, const double *tm, double *out)
+{
+    const std::uint32_t lane = blockIdx.x * blockDim.x + threadIdx.x;
+    if (lane >= n) {
+        return;
+    }
+    const std::size_t nn = n;
+    const auto time_at = [&](std::uint32_t row) { return dfl{t_hi[row * nn + lane], t_lo[row * nn + lane]}; };
+    // Direction: start < padding row (+-inf by direction), src/continuous_output.cpp:684-694.
+    const bool dir = dfl_lt(time_at(0u), time_at(n_rows - 1u));
+    const dfl t{tm[lane], 0.};
+    std::uint32_t first = 0, count = n_rows;
+    while (count != 0u) {
+        const std::uint32_t step = count / 2u;
+        std::uint32_t idx = first + step;
+        const dfl v = time_at(idx);
+        // !(t < v) forward, !(t > v) backward.
+        const bool cond = dir ? !dfl_lt(t, v) : !dfl_lt(v, t);
+        if (cond) {
+            first = idx + 1u;
+            count -= step + 1u;
+        } else {
+            count = step;
+        }
+    }
+    std::uint32_t tc_idx = first;
+    tc_idx -= (tc_idx != 0u) ? 1u : 0u;
+    tc_idx -= (first == n_rows - 1u) ? 1u : 0u;
+    const double h = dfl_sub(t, time_at(tc_idx)).hi;
+    const double *base = tcs + static_cast<std::size_t>(tc_idx) * P.n_eq * (P.order + 1u) * nn + lane;
+    for (std::uint32_t i = 0; i < P.n_eq; ++i) {
+        const double *c = base + static_cast<std::size_t>(i) * (P.order + 1u) * nn;
+        out[static_cast<std::size_t>(i) * nn + lane]
+            = eval_poly(P, [c, nn](std::uint32_t o) { return c[static_cast<std::size_t>(o) * nn]; }, h);
+    }
+}
+
 __global__ void k_fill_double(double *out, std::size_t n, double value)
 {
     const std::size_t i = static_cast<std::size_t>(blockIdx.x) * blockDim.x + threadIdx.x;

@@ -524,6 +524,53 @@ taylor_adaptive_batch<double>::propagate_until_vec(const std::vector<double> &ts
     return propagate_until_impl(ts, std::vector<double>(m.batch_size, 0.), std::move(o));
 }
 
+// ---- continuous_output_batch<double> ----
+continuous_output_batch<double>::continuous_output_batch(hy_cout *h, std::uint32_t batch_size, std::uint32_t dim)
+    : m_h(h, [](hy_cout *p) { hy_cout_destroy(p); }), m_batch_size(batch_size), m_dim(dim),
+      m_output(static_cast<std::size_t>(batch_size) * dim)
+{
+}
+
+void continuous_output_batch<double>::check_valid() const
+{
+    if (!m_h) {
+        throw std::invalid_argument("Cannot use a default-constructed continuous_output_batch object");
+    }
+}
+
+const std::vector<double> &continuous_output_batch<double>::operator()(const std::vector<double> &tm)
+{
+    check_valid();
+    if (tm.size() != m_batch_size) {
+        throw std::invalid_argument("An invalid time vector was passed to the call operator of continuous_output_batch: "
+                                    "the vector size is "
+                                    + std::to_string(tm.size()) + ", but a size of " + std::to_string(m_batch_size)
+                                    + " was expected instead");
+    }
+    check(hy_cout_eval(m_h.get(), tm.data(), m_output.data()));
+    return m_output;
+}
+
+const std::vector<double> &continuous_output_batch<double>::operator()(double tm)
+{
+    check_valid();
+    return (*this)(std::vector<double>(m_batch_size, tm));
+}
+
+std::pair<std::vector<double>, std::vector<double>> continuous_output_batch<double>::get_bounds() const
+{
+    check_valid();
+    std::vector<double> lb(m_batch_size), ub(m_batch_size);
+    check(hy_cout_get_bounds(m_h.get(), lb.data(), ub.data()));
+    return {std::move(lb), std::move(ub)};
+}
+
+std::size_t continuous_output_batch<double>::get_n_steps() const
+{
+    check_valid();
+    return static_cast<std::size_t>(hy_cout_n_steps(m_h.get()));
+}
+
 // propagate_grid(): src/taylor_adaptive_batch.cpp:1545-2055. The size checks that need the reference's wording are
 // done here, the grid checks and the integration by hy_batch_propagate_grid().
 std::tuple<step_callback_batch<double>, std::vector<double>>
@@ -570,8 +617,9 @@ taylor_adaptive_batch<double>::propagate_until_impl(const std::vector<double> &h
     auto &m = *m_impl;
     const auto n = m.batch_size;
 
-    if (o.c_output) {
-        throw not_implemented_error("Continuous output is not supported by the B200 batch integrator");
+    if (o.c_output && o.cb) {
+        throw not_implemented_error("Continuous output together with a callback is not supported by the B200 batch "
+                                    "integrator");
     }
 
     // Validation, src/taylor_adaptive_batch.cpp:1212-1273.
@@ -606,6 +654,25 @@ taylor_adaptive_batch<double>::propagate_until_impl(const std::vector<double> &h
         }
     }
     const double *mdt = o.max_delta_t.empty() ? nullptr : o.max_delta_t.data();
+
+    if (o.c_output) {
+        // The reference's lock-step loop with the recording of the Taylor coefficients, on the device
+        // (hy_batch_propagate_until_cout()).
+        m.push();
+        hy_cout *co = nullptr;
+        check(hy_batch_propagate_until_cout(m.batch, hi.data(), lo.data(), mdt, o.max_steps, &co));
+        std::optional<continuous_output_batch<double>> ret;
+        if (co != nullptr) {
+            ret.emplace(co, n, m.dim);
+        }
+        m.pull(true);
+        check(hy_batch_download_prop_res(m.batch, m.oc.data(), m.tmp_a.data(), m.tmp_b.data(), m.tmp_n.data()));
+        for (std::uint32_t i = 0; i < n; ++i) {
+            m.prop_res[i] = std::tuple{static_cast<taylor_outcome>(m.oc[i]), m.tmp_a[i], m.tmp_b[i],
+                                       static_cast<std::size_t>(m.tmp_n[i])};
+        }
+        return {std::move(ret), std::move(o.cb)};
+    }
 
     if (!o.cb) {
         // Fast path: the whole loop runs on the device.

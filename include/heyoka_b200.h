@@ -244,6 +244,21 @@ int hy_batch_propagate_until_dev(hy_batch *, const double *d_t_final_hi, const d
 int hy_batch_propagate_grid(hy_batch *, const double *grid, uint64_t n_pts, const double *max_delta_t,
                             uint64_t max_steps, double *out);
 
+/* Continuous output (include/heyoka/continuous_output.hpp, producer src/taylor_adaptive_batch.cpp:1246-1346):
+ * hy_batch_propagate_until_cout() runs propagate_until() as the reference's lock-step loop and records, at every
+ * iteration, the Taylor coefficients and the (double-length) times of all lanes in device memory. *out is NULL if
+ * no iteration completed (non-finite state at the first step). The object is independent of the batch afterwards.
+ * hy_cout_eval(): state at per-lane times tm[batch] -> out[n_eq * batch] (host arrays); times outside the
+ * integration range use the first / last step's coefficients, like the reference. */
+typedef struct hy_cout hy_cout;
+int hy_batch_propagate_until_cout(hy_batch *, const double *t_final_hi, const double *t_final_lo,
+                                  const double *max_delta_t, uint64_t max_steps, hy_cout **out);
+int hy_cout_eval(hy_cout *, const double *tm, double *out);
+/* Per-lane time range [lb, ub] covered (the initial and the final time), number of recorded iterations. */
+int hy_cout_get_bounds(const hy_cout *, double *lb, double *ub);
+uint64_t hy_cout_n_steps(const hy_cout *);
+void hy_cout_destroy(hy_cout *);
+
 /* Dense output from the last written tc: out[var * batch + lane] = sum_o tc[var][o][lane] * tau[lane]^o
  * (src/taylor_01.cpp:1015-1185; tau relative to the start of the last step). out/tau are host arrays. */
 int hy_batch_d_output(hy_batch *, const double *tau, double *out);

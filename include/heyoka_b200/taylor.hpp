@@ -14,7 +14,7 @@
 // batch (hy_batch) is shared between copies only in its program: a copy gets its own device buffers.
 //
 // Not supported (out of the hot path): event detection (kw::t_events / kw::nt_events throw),
-// continuous output (kw::c_output = true throws), variational systems, serialisation. kw::compact_mode,
+// variational systems, serialisation. kw::compact_mode,
 // kw::parallel_mode, kw::parjit and the llvm_state options are accepted and ignored (there is no JIT).
 #ifndef HEYOKA_B200_TAYLOR_HPP
 #define HEYOKA_B200_TAYLOR_HPP
@@ -55,11 +55,37 @@ struct not_implemented_error final : std::runtime_error {
 template <typename T>
 class taylor_adaptive_batch;
 
-// Placeholder for the reference's continuous_output_batch<T> (not supported: propagate_*() always return an
-// empty optional).
+// continuous_output_batch<T> (include/heyoka/continuous_output.hpp:157-237): the result of
+// propagate_*(kw::c_output = true). Device-resident (hy_cout); copies share the device data.
 template <typename T>
-class continuous_output_batch
+class continuous_output_batch;
+
+template <>
+class continuous_output_batch<double>
 {
+    std::shared_ptr<hy_cout> m_h;
+    std::uint32_t m_batch_size = 0, m_dim = 0;
+    std::vector<double> m_output;
+
+    void check_valid() const;
+
+public:
+    continuous_output_batch() = default;
+    continuous_output_batch(hy_cout *, std::uint32_t batch_size, std::uint32_t dim);
+
+    // State at one time per lane / at the same time for every lane, [dim][batch].
+    const std::vector<double> &operator()(const std::vector<double> &tm);
+    const std::vector<double> &operator()(double tm);
+    [[nodiscard]] const std::vector<double> &get_output() const
+    {
+        return m_output;
+    }
+    [[nodiscard]] std::pair<std::vector<double>, std::vector<double>> get_bounds() const;
+    [[nodiscard]] std::size_t get_n_steps() const;
+    [[nodiscard]] std::uint32_t get_batch_size() const
+    {
+        return m_batch_size;
+    }
 };
 
 // include/heyoka/step_callback.hpp:57-139 reduced to the call operator: bool(taylor_adaptive_batch<T> &).

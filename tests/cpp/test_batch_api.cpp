@@ -317,6 +317,76 @@ static void test_propagate_grid()
     }
 }
 
+// test/c_output.cpp:289-420 ("batch"): default-constructed object, continuous output against a grid propagation.
+static void test_continuous_output()
+{
+    continuous_output_batch<double> co0;
+    REQUIRE(co0.get_output().empty());
+    REQUIRE(co0.get_batch_size() == 0u);
+    REQUIRE_THROWS_MSG(co0(std::vector<double>{0., 0.}), std::invalid_argument,
+                       "Cannot use a default-constructed continuous_output_batch object");
+    REQUIRE_THROWS_MSG(co0.get_bounds(), std::invalid_argument,
+                       "Cannot use a default-constructed continuous_output_batch object");
+    REQUIRE_THROWS_MSG(co0.get_n_steps(), std::invalid_argument,
+                       "Cannot use a default-constructed continuous_output_batch object");
+
+    auto [x, v] = make_vars("x", "v");
+    const unsigned batch_size = 4;
+    std::vector<double> ic, final_tm, init_tm(batch_size, 0.);
+    for (auto i = 0u; i < batch_size; ++i) {
+        ic.push_back(i / 100.);
+    }
+    for (auto i = 0u; i < batch_size; ++i) {
+        ic.push_back(1 + i / 100.);
+        final_tm.push_back(10. + i / 100.);
+    }
+    const auto n_points = 10u;
+    std::vector<double> grid(batch_size * n_points);
+    for (auto i = 0u; i < batch_size; ++i) {
+        grid[i] = 0;
+        for (auto j = 1u; j + 1u < n_points; ++j) {
+            grid[j * batch_size + i] = final_tm[i] * (j - 0.37 + 0.05 * i) / (n_points - 1.);
+        }
+        grid[grid.size() - batch_size + i] = final_tm[i];
+    }
+    taylor_adaptive_batch<double> ta{{prime(x) = v, prime(v) = -x}, ic, batch_size};
+    auto [d_out, cb] = ta.propagate_until(final_tm, kw::c_output = true);
+    REQUIRE(!cb);
+    REQUIRE(d_out.has_value());
+    REQUIRE(d_out->get_output().size() == 2u * batch_size);
+    REQUIRE(d_out->get_n_steps() > 10u);
+    const auto bounds = d_out->get_bounds();
+    REQUIRE(bounds.first == init_tm);
+    REQUIRE(bounds.second == final_tm);
+    REQUIRE_THROWS_MSG((*d_out)(std::vector<double>{0.}), std::invalid_argument,
+                       "the vector size is 1, but a size of 4 was expected instead");
+
+    std::copy(ic.begin(), ic.end(), ta.get_state_data());
+    ta.set_time(init_tm);
+    auto [cb_grid, grid_out] = ta.propagate_grid(grid);
+    REQUIRE(!cb_grid);
+    bool ok = true;
+    const double tol = std::numeric_limits<double>::epsilon() * 100.;
+    const auto near = [tol](double c, double e) {
+        return std::abs(c) < tol ? std::abs(c - e) <= tol : std::abs((c - e) / c) <= tol;
+    };
+    std::vector<double> loc_time(batch_size);
+    for (auto i = 0u; i < n_points; ++i) {
+        for (auto j = 0u; j < batch_size; ++j) {
+            loc_time[j] = grid[i * batch_size + j];
+        }
+        (*d_out)(loc_time);
+        for (auto j = 0u; j < batch_size; ++j) {
+            ok = ok && near(d_out->get_output()[j], grid_out[2u * i * batch_size + j])
+                 && near(d_out->get_output()[batch_size + j], grid_out[2u * i * batch_size + batch_size + j]);
+        }
+        // The scalar overload.
+        (*d_out)(loc_time[0]);
+        ok = ok && near(d_out->get_output()[0], grid_out[2u * i * batch_size]);
+    }
+    REQUIRE(ok);
+}
+
 int main(int argc, char **argv)
 {
     const bool gpu = argc > 1 && std::strcmp(argv[1], "gpu") == 0;
@@ -327,6 +397,7 @@ int main(int argc, char **argv)
         test_ensemble();
         test_models_and_dense_output();
         test_propagate_grid();
+        test_continuous_output();
     }
     if (n_fail == 0) {
         std::printf("ALL PASSED (%s)\n", gpu ? "gpu" : "cpu");

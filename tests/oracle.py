@@ -239,3 +239,112 @@ class OracleIntegrator:
             if it == max_steps:
                 self.prop_outcome[:] = STEP_LIMIT
         return ret
+
+    def propagate_until_cout(self, t_final, max_delta_t=None, max_steps=0):
+        """propagate_until() as the reference's lock-step loop with continuous-output recording
+        (src/taylor_adaptive_batch.cpp:1246-1527). Returns an OracleCOut, or None if no iteration completed."""
+        import heyoka_b200 as hb
+        n = self.n
+        tf = np.broadcast_to(np.asarray(t_final, dtype=np.float64), (n,)).copy()
+        mdt = np.full(n, np.inf) if max_delta_t is None else np.broadcast_to(np.asarray(max_delta_t, float), (n,))
+        SUCCESS, NF, STEP_LIMIT = hb.taylor_outcome.success, hb.taylor_outcome.err_nf_state, hb.taylor_outcome.step_limit
+
+        def dsub(ahi, alo, bhi, blo):
+            return hb._dfloat_add(np.atleast_1d(ahi), np.atleast_1d(alo), -np.atleast_1d(bhi), -np.atleast_1d(blo))
+
+        def dlt(ahi, alo, bhi, blo):
+            return (ahi < bhi) | ((ahi == bhi) & (alo < blo))
+
+        times_hi, times_lo, tcs = [self.t_hi.copy()], [self.t_lo.copy()], []
+        self.n_steps[:] = 0
+        self.min_h[:] = np.inf
+        self.max_h[:] = 0
+        rem_hi, rem_lo = dsub(tf, np.zeros(n), self.t_hi, self.t_lo)
+        t_dir = (rem_hi > 0) | ((rem_hi == 0) & (rem_lo >= 0))
+        it = 0
+        while True:
+            lim = np.empty(n)
+            for i in range(n):
+                if t_dir[i]:
+                    lim[i] = rem_hi[i] if dlt(rem_hi[i], rem_lo[i], mdt[i], 0.0) else mdt[i]
+                else:
+                    lim[i] = rem_hi[i] if dlt(-mdt[i], 0.0, rem_hi[i], rem_lo[i]) else -mdt[i]
+            self.step(max_delta_t=lim, write_tc=True)
+            n_done, nfs = 0, False
+            for i in range(n):
+                oc, h = self.step_outcome[i], self.last_h[i]
+                if oc == NF:
+                    nfs = True
+                else:
+                    self.n_steps[i] += int(h != 0)
+                    if oc == SUCCESS:
+                        self.min_h[i] = min(self.min_h[i], abs(h))
+                        self.max_h[i] = max(self.max_h[i], abs(h))
+                    if h == rem_hi[i]:
+                        n_done += 1
+                        rem_hi[i] = rem_lo[i] = 0.0
+                    else:
+                        r = dsub(tf[i], 0.0, self.t_hi[i], self.t_lo[i])
+                        rem_hi[i], rem_lo[i] = r[0][0], r[1][0]
+                self.prop_outcome[i] = oc
+            if nfs:
+                break
+            times_hi.append(self.t_hi.copy())
+            times_lo.append(self.t_lo.copy())
+            tcs.append(self.tc.copy())
+            it += 1
+            if n_done == n:
+                break
+            if it == max_steps:
+                self.prop_outcome[:] = STEP_LIMIT
+                break
+        if not tcs:
+            return None
+        times_hi.append(np.where(t_dir, np.inf, -np.inf))
+        times_lo.append(np.zeros(n))
+        return OracleCOut(self.P, np.array(tcs), np.array(times_hi), np.array(times_lo))
+
+
+class OracleCOut:
+    """Evaluation of a continuous output, src/continuous_output.cpp:640-960 (upper_bound per lane, then Horner /
+    compensated summation through the oracle's dense-output function)."""
+
+    def __init__(self, P, tcs, t_hi, t_lo):
+        self.P, self.tcs, self.t_hi, self.t_lo = P, tcs, t_hi, t_lo
+        self.n = t_hi.shape[1]
+
+    def get_n_steps(self):
+        return self.tcs.shape[0]
+
+    def get_bounds(self):
+        return self.t_hi[0].copy(), self.t_hi[-2].copy()
+
+    def __call__(self, tm):
+        import heyoka_b200 as hb
+        tm = np.broadcast_to(np.asarray(tm, dtype=np.float64), (self.n,))
+        rows = self.t_hi.shape[0]
+        out = np.empty((self.P.n_eq, self.n))
+
+        def lt(ahi, alo, bhi, blo):
+            return (ahi < bhi) or (ahi == bhi and alo < blo)
+
+        for i in range(self.n):
+            fwd = lt(self.t_hi[0, i], self.t_lo[0, i], self.t_hi[-1, i], self.t_lo[-1, i])
+            first, count = 0, rows
+            while count:
+                step = count // 2
+                idx = first + step
+                cond = (not lt(tm[i], 0.0, self.t_hi[idx, i], self.t_lo[idx, i])) if fwd else \
+                    (not lt(self.t_hi[idx, i], self.t_lo[idx, i], tm[i], 0.0))
+                if cond:
+                    first, count = idx + 1, count - step - 1
+                else:
+                    count = step
+            k = first - (1 if first != 0 else 0) - (1 if first == rows - 1 else 0)
+            h = hb._dfloat_add(np.array([tm[i]]), np.zeros(1), -self.t_hi[k, i:i + 1], -self.t_lo[k, i:i + 1])[0][0]
+            tc1 = np.ascontiguousarray(self.tcs[k][:, :, i:i + 1])
+            o = np.empty((self.P.n_eq, 1))
+            rc = lib.oracle_d_output_w1(_desc_ptr(self.P), C.c_uint32(1), _arr(tc1), _arr(np.array([h])), _arr(o))
+            assert rc == 0
+            out[:, i] = o[:, 0]
+        return out

@@ -476,3 +476,45 @@ def test_ffnn_parity():
     o.propagate_until(1.0)
     assert [r[3] for r in ta.propagate_res] == [int(s) for s in o.n_steps]
     assert lane_err(ta.state, o.state) < 1e-12
+
+
+# ---- continuous output (include/heyoka/continuous_output.hpp, producer src/taylor_adaptive_batch.cpp:1246-1346) ----
+
+@pytest.mark.gpu
+def test_continuous_output_gpu(kernel):
+    """The batch block of test/c_output.cpp:289-420: the continuous output of propagate_until() against a grid
+    propagation of the same integrator (100 eps), the closed form, and the oracle's restatement (same number of
+    recorded iterations, same values)."""
+    from test_oracle_golden import approximately, cout_fixture, sys_oscillator
+    ic, final_tm, grid = cout_fixture()
+    for ha in (False, True):
+        ta = hb.taylor_adaptive_batch(sys_oscillator(), ic, 4, high_accuracy=ha, kernel=kernel)
+        co = ta.propagate_until(final_tm, c_output=True)
+        assert co is not None and np.array_equal(ta.time, final_tm)
+        assert [r[0] for r in ta.propagate_res] == [hb.taylor_outcome.time_limit] * 4
+        lb, ub = co.get_bounds()
+        assert np.all(lb == 0) and np.array_equal(ub, final_tm)
+        ta2 = hb.taylor_adaptive_batch(sys_oscillator(), ic, 4, high_accuracy=ha, kernel=kernel)
+        grid_out = ta2.propagate_grid(grid)
+        o = oracle.OracleIntegrator(hb.Program(sys_oscillator(), high_accuracy=ha), ic, 4, mode=oracle.FMA)
+        oco = o.propagate_until_cout(final_tm)
+        assert co.get_n_steps() == oco.get_n_steps()
+        assert [r[3] for r in ta.propagate_res] == [int(s) for s in o.n_steps]
+        for k in range(grid.shape[0]):
+            s = co(grid[k]).copy()
+            assert approximately(s, grid_out[k], 100.0)
+            assert np.max(np.abs(s - oco(grid[k]))) < 1e-13
+        for tval in (0.0, 3.3, 9.99, -0.5, 11.0):  # the same time for every lane, also outside the bounds
+            s = co(tval).copy()
+            assert np.max(np.abs(s - oco(tval))) < 1e-12
+        with pytest.raises(ValueError, match="at the non-finite time"):
+            co([0.0, float("inf"), 0.0, 0.0])
+    # max_steps: the recording stops with the loop, outcomes step_limit.
+    ta = hb.taylor_adaptive_batch(sys_oscillator(), ic, 4, kernel=kernel)
+    co = ta.propagate_until(final_tm, c_output=True, max_steps=3)
+    assert co.get_n_steps() == 3 and [r[0] for r in ta.propagate_res] == [hb.taylor_outcome.step_limit] * 4
+    # Non-finite state at the first step: no continuous output.
+    ta = hb.taylor_adaptive_batch(sys_oscillator(), ic, 4, kernel=kernel)
+    ta.state[0, 1] = float("inf")
+    assert ta.propagate_until(final_tm, c_output=True) is None
+    assert ta.propagate_res[1][0] == hb.taylor_outcome.err_nf_state

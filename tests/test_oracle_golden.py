@@ -216,3 +216,42 @@ def test_propagate_grid_oscillator(name, grid, tol, mode):
     amp = 1.0 + np.arange(4) / 10.0
     assert approximately(ret[:, 0, :], amp * np.sin(grid), tol)
     assert approximately(ret[:, 1, :], amp * np.cos(grid), tol)
+
+
+# ---- continuous output: the batch block of test/c_output.cpp:289-420 ----
+
+def cout_fixture(batch_size=4, seed=7):
+    """Harmonic oscillator, ICs x = i / 100, v = 1 + i / 100, final times 10 + i / 100, a random grid per lane
+    (test/c_output.cpp:330-366; numpy's generator instead of mt19937)."""
+    ic = np.array([[i / 100.0 for i in range(batch_size)], [1 + i / 100.0 for i in range(batch_size)]])
+    final_tm = np.array([10.0 + i / 100.0 for i in range(batch_size)])
+    rng = np.random.default_rng(seed)
+    n_points = 10
+    grid = np.zeros((n_points, batch_size))
+    for i in range(batch_size):
+        grid[1:-1, i] = np.sort(rng.uniform(1e-6, 10.0 + i / 100.0 - 1e-6, n_points - 2))
+        grid[-1, i] = final_tm[i]
+    return ic, final_tm, grid
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_continuous_output_oscillator(mode):
+    ic, final_tm, grid = cout_fixture()
+    P = hb.Program(sys_oscillator())
+    o = oracle.OracleIntegrator(P, ic, 4, mode=mode)
+    co = o.propagate_until_cout(final_tm)
+    assert co is not None and np.all(o.prop_outcome == hb.taylor_outcome.time_limit)
+    assert np.array_equal(o.t_hi, final_tm)
+    lb, ub = co.get_bounds()
+    assert np.all(lb == 0) and np.array_equal(ub, final_tm)
+    assert co.t_hi.shape[0] == co.get_n_steps() + 2
+    o2 = oracle.OracleIntegrator(P, ic, 4, mode=mode)
+    grid_out = o2.propagate_grid(grid)
+    for k in range(grid.shape[0]):
+        assert approximately(co(grid[k]), grid_out[k], 100.0)
+    # Closed form: x = x0 cos t + v0 sin t, v = -x0 sin t + v0 cos t.
+    t = np.linspace(0.05, 9.9, 37)[:, None] * np.ones(4)[None, :]
+    for k in range(t.shape[0]):
+        s = co(t[k])
+        assert approximately(s[0], ic[0] * np.cos(t[k]) + ic[1] * np.sin(t[k]), 1e5)
+        assert approximately(s[1], -ic[0] * np.sin(t[k]) + ic[1] * np.cos(t[k]), 1e5)
