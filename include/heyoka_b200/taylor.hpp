@@ -5,7 +5,7 @@
 // (system, state, batch size, kw::time / tol / high_accuracy / compact_mode / pars), same getters, step() /
 // step_backward() / step(max_delta_ts), propagate_for() / propagate_until() with kw::max_steps / max_delta_t /
 // callback / write_tc, get_step_res() / get_propagate_res(), update_d_output(), and ensemble_propagate_*_batch()
-// (include/heyoka/ensemble_propagate.hpp:220-269). Errors are the reference's exceptions with the reference's
+// incl. the grid variant (include/heyoka/ensemble_propagate.hpp:220-269). Errors are the reference's exceptions with the reference's
 // messages (std::invalid_argument, not_implemented_error); numerical failure is taylor_outcome::err_nf_state.
 //
 // Ownership / raw-pointer contract (include/heyoka/taylor.hpp:974-977): the integrator owns host std::vector
@@ -331,6 +331,31 @@ ensemble_propagate_for_batch(
     for (std::size_t i = 0; i < n_iter; ++i) {
         auto local_ta = gen(ta, i);
         auto res = local_ta.propagate_for(delta_t, kw_args...);
+        retval.emplace_back(std::move(local_ta), std::move(std::get<0>(res)), std::move(std::get<1>(res)));
+    }
+    return retval;
+}
+
+// ensemble_propagate_grid_batch() (include/heyoka/ensemble_propagate.hpp:257-269, src/ensemble_propagate.cpp:258-
+// 297): the scalar time grid is splatted over the batch, every member runs propagate_grid().
+template <typename... KwArgs>
+std::vector<std::tuple<taylor_adaptive_batch<double>, step_callback_batch<double>, std::vector<double>>>
+ensemble_propagate_grid_batch(
+    const taylor_adaptive_batch<double> &ta, const std::vector<double> &grid_, std::size_t n_iter,
+    const std::function<taylor_adaptive_batch<double>(taylor_adaptive_batch<double>, std::size_t)> &gen,
+    const KwArgs &...kw_args)
+{
+    const auto batch_size = ta.get_batch_size();
+    std::vector<double> grid;
+    grid.reserve(grid_.size() * batch_size);
+    for (const auto gval : grid_) {
+        grid.insert(grid.end(), batch_size, gval);
+    }
+    std::vector<std::tuple<taylor_adaptive_batch<double>, step_callback_batch<double>, std::vector<double>>> retval;
+    retval.reserve(n_iter);
+    for (std::size_t i = 0; i < n_iter; ++i) {
+        auto local_ta = gen(ta, i);
+        auto res = local_ta.propagate_grid(grid, kw_args...);
         retval.emplace_back(std::move(local_ta), std::move(std::get<0>(res)), std::move(std::get<1>(res)));
     }
     return retval;

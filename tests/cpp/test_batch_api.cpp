@@ -213,6 +213,33 @@ static void test_ensemble()
     }
 }
 
+// test/ensemble_propagate.cpp ("batch grid"): every member of a grid ensemble equals its own sequential run.
+static void test_ensemble_grid()
+{
+    auto [x, v] = make_vars("x", "v");
+    taylor_adaptive_batch<double> ta{{prime(x) = v, prime(v) = -x}, {0., 0., 1., 1.}, 2u};
+    const auto gen = [](taylor_adaptive_batch<double> tint, std::size_t i) {
+        tint.get_state_data()[0] = 0.05 * static_cast<double>(i);
+        tint.get_state_data()[1] = 0.05 * static_cast<double>(i) + 0.01;
+        return tint;
+    };
+    const std::vector<double> grid{0., 1., 2.5, 4., 7.25};
+    auto res = ensemble_propagate_grid_batch(ta, grid, 5u, gen);
+    REQUIRE(res.size() == 5u);
+    for (std::size_t i = 0; i < res.size(); ++i) {
+        auto single = gen(ta, i);
+        std::vector<double> g2;
+        for (const auto t : grid) {
+            g2.push_back(t);
+            g2.push_back(t);
+        }
+        auto [cb, out] = single.propagate_grid(g2);
+        REQUIRE(out == std::get<2>(res[i]));
+        REQUIRE(single.get_state() == std::get<0>(res[i]).get_state());
+        REQUIRE(std::get<2>(res[i]).size() == grid.size() * 2u * 2u);
+    }
+}
+
 static void test_models_and_dense_output()
 {
     const std::vector<double> masses{1.00000597682, 1 / 1047.355, 1 / 3501.6, 1 / 22869., 1 / 19314., 7.4074074e-09};
@@ -398,6 +425,7 @@ int main(int argc, char **argv)
         test_models_and_dense_output();
         test_propagate_grid();
         test_continuous_output();
+        test_ensemble_grid();
     }
     if (n_fail == 0) {
         std::printf("ALL PASSED (%s)\n", gpu ? "gpu" : "cpu");
