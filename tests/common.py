@@ -188,3 +188,61 @@ def sys_ffnn(seed=11):
 
 def ffnn_batch_state(batch, seed=13):
     return np.random.default_rng(seed).uniform(-1, 1, (4, batch))
+
+
+# ---- test/two_body_batch.cpp:60-190: equal-mass two-body problem written by hand, Keplerian elements ----
+def sys_two_body_symmetric():
+    """The system of test/two_body_batch.cpp:63-80 (variables in the reference's order)."""
+    vx0, vx1, vy0, vy1, vz0, vz1, x0, x1, y0, y1, z0, z1 = hb.make_vars("vx0", "vx1", "vy0", "vy1", "vz0", "vz1",
+                                                                        "x0", "x1", "y0", "y1", "z0", "z1")
+    x01, y01, z01 = x1 - x0, y1 - y0, z1 - z0
+    r01_m3 = hb.pow(x01 * x01 + y01 * y01 + z01 * z01, hb.expression(-3.) / hb.expression(2.))
+    return [(vx0, x01 * r01_m3), (vx1, -x01 * r01_m3), (vy0, y01 * r01_m3), (vy1, -y01 * r01_m3),
+            (vz0, z01 * r01_m3), (vz1, -z01 * r01_m3), (x0, vx0), (x1, vx1), (y0, vy0), (y1, vy1), (z0, vz0), (z1, vz1)]
+
+
+def cart_to_kep(x, v, mu):
+    """test/test_utils.hpp:172-202 (Cartesian state -> a, e, i, omega, Omega, nu)."""
+    x, v = np.asarray(x, dtype=float), np.asarray(v, dtype=float)
+    h = np.cross(x, v)
+    e_v = np.cross(v, h) / mu - x / np.linalg.norm(x)
+    n = np.array([-h[1], h[0], 0.0])
+    nu = np.arccos(np.dot(e_v, x) / (np.linalg.norm(e_v) * np.linalg.norm(x)))
+    if np.dot(x, v) < 0:
+        nu = 2 * np.pi - nu
+    inc = np.arccos(h[2] / np.linalg.norm(h))
+    e = np.linalg.norm(e_v)
+    Om = np.arccos(n[0] / np.linalg.norm(n))
+    if n[1] < 0:
+        Om = 2 * np.pi - Om
+    om = np.arccos(np.dot(n, e_v) / (np.linalg.norm(n) * np.linalg.norm(e_v)))
+    if e_v[2] < 0:
+        om = 2 * np.pi - om
+    a = 1 / (2 / np.linalg.norm(x) - np.dot(v, v) / mu)
+    return np.array([a, e, inc, om, Om, nu])
+
+
+def two_body_kepler_fixture(batch=4, seed=5):
+    """Random elements a ~ U(0.1, 10), e ~ U(0.1, 0.5), i ~ U(0.1, 3.0) (3.13 in the reference: the node of a
+    nearly equatorial retrograde orbit is ill-conditioned at the 1e4 eps of the check), angles ~ U(0.1, 6.28); the two bodies sit at
+    +-x, +-v of the Keplerian orbit with mu = 1/4 (test/two_body_batch.cpp:83-112)."""
+    rng = np.random.default_rng(seed)
+    kep = np.column_stack([rng.uniform(0.1, 10, batch), rng.uniform(0.1, 0.5, batch), rng.uniform(0.1, 3.0, batch),
+                           rng.uniform(0.1, 6.28, batch), rng.uniform(0.1, 6.28, batch), rng.uniform(0.1, 6.28, batch)])
+    st = np.zeros((12, batch))
+    for i in range(batch):
+        pos, vel = kep_to_cart(*kep[i], 0.25)
+        for k in range(3):
+            st[2 * k, i], st[2 * k + 1, i] = vel[k], -vel[k]
+            st[6 + 2 * k, i], st[6 + 2 * k + 1, i] = pos[k], -pos[k]
+    return kep, st
+
+
+def check_kepler_conservation(st, kep, approx_fn, tol_mul=1e4):
+    """test/two_body_batch.cpp:166-190 for every lane of st[12, batch]."""
+    for i in range(st.shape[1]):
+        for body in (0, 1):
+            k = cart_to_kep(st[6 + body:12:2, i], st[body:6:2, i], 0.25)
+            assert approx_fn(k[0], kep[i, 0], tol_mul) and approx_fn(k[1], kep[i, 1], tol_mul)
+            assert approx_fn(k[2], kep[i, 2], tol_mul) and approx_fn(k[4], kep[i, 4], tol_mul)
+            assert approx_fn(abs(np.cos(k[3])), abs(np.cos(kep[i, 3])), tol_mul)

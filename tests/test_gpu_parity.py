@@ -518,3 +518,26 @@ def test_continuous_output_gpu(kernel):
     ta.state[0, 1] = float("inf")
     assert ta.propagate_until(final_tm, c_output=True) is None
     assert ta.propagate_res[1][0] == hb.taylor_outcome.err_nf_state
+
+
+@pytest.mark.gpu
+def test_two_body_kepler_conservation_gpu(kernel):
+    """test/two_body_batch.cpp:60-190 on the GPU: 200 steps of the hand-written equal-mass two-body system; every
+    step agrees with a one-lane integrator taking the same step, and the Keplerian elements of both bodies are
+    conserved to 1e4 epsilon."""
+    from common import check_kepler_conservation, sys_two_body_symmetric, two_body_kepler_fixture
+    from test_oracle_golden import approximately
+    kep, st = two_body_kepler_fixture()
+    ta = hb.taylor_adaptive_batch(sys_two_body_symmetric(), st, 4, kernel=kernel)
+    one = [hb.taylor_adaptive_batch(sys_two_body_symmetric(), st[:, i:i + 1], 1, kernel=kernel) for i in range(4)]
+    for _ in range(200):
+        prev, t_prev = ta.state.copy(), np.array(ta.time)
+        ta.step()
+        for i in range(4):
+            one[i].state[:] = prev[:, i:i + 1]
+            one[i].set_time([t_prev[i]])
+            one[i].step()
+            assert one[i].step_res[0][0] == ta.step_res[i][0]
+            assert approximately(one[i].step_res[0][1], ta.step_res[i][1], 1e4)
+            assert approximately(one[i].state[:, 0], ta.state[:, i], 1e5)
+        check_kepler_conservation(ta.state, kep, approximately)

@@ -255,3 +255,25 @@ def test_continuous_output_oscillator(mode):
         s = co(t[k])
         assert approximately(s[0], ic[0] * np.cos(t[k]) + ic[1] * np.sin(t[k]), 1e5)
         assert approximately(s[1], -ic[0] * np.sin(t[k]) + ic[1] * np.cos(t[k]), 1e5)
+
+
+# ---- 6. test/two_body_batch.cpp:60-190: batch vs single-lane agreement, Keplerian elements conserved ----
+
+@pytest.mark.parametrize("mode", MODES)
+def test_two_body_kepler_conservation(mode):
+    from common import check_kepler_conservation, sys_two_body_symmetric, two_body_kepler_fixture
+    kep, st = two_body_kepler_fixture()
+    P = hb.Program(sys_two_body_symmetric())
+    assert (P.n_eq, P.order) == (12, 20)
+    o = oracle.OracleIntegrator(P, st, 4, mode=mode)
+    for _ in range(200):
+        prev, t_prev = o.state.copy(), o.t_hi.copy()
+        o.step()
+        # The same step taken by a one-lane integrator (the reference compares with its scalar class).
+        for i in range(4):
+            s = oracle.OracleIntegrator(P, prev[:, i:i + 1], 1, time=t_prev[i], mode=mode)
+            s.step()
+            assert s.step_outcome[0] == o.step_outcome[i]
+            assert approximately(s.last_h[0], o.last_h[i], 1e4)
+            assert approximately(s.state[:, 0], o.state[:, i], 1e5)
+        check_kepler_conservation(o.state, kep, approximately)
