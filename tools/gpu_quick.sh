@@ -1,3 +1,3 @@
 set -x
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_cpp_api.py -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -6 gpurun_out/pytest_gpu.log
+timeout 900 python -m pytest tests -m gpu -x -q -k "kepler" --durations=3 > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -8 gpurun_out/pytest_gpu.log
