@@ -322,91 +322,144 @@ __device__ __forceinline__ void fused_nbody_pair_tmem(const program &P, const Ta
         R2.set(n, r2n);
     }
 
-    // ---- q^[n] = pow(r2, alpha) ----
-    V q;
-    if (n == 0u) {
-        q = pow_eval(aux[12], r2n, splat<N>(t.cst(aux[11])));
-    } else {
-        const double nd = static_cast<double>(n);
-        const double n_alpha = nd * t.cst(aux[11]);
-        const double *jap1 = t.consts + aux[13];
-        tm::words<2 * N> w0;
-        R2.template issue<1>(0u, w0); // r2^[0] for the final division
-        V acc = splat<N>(0.);
-        std::uint32_t j = 0;
-        for (; j + C <= n; j += C) {
-            tm::words<2 * N * C> wq, wr;
-            Q.template issue<C>(j, wq);
-            R2.template issue<C>(n - j - (C - 1u), wr); // r2^[n - j - i] = rv[C - 1 - i]
-            tm::wait_ld(wq);
-            tm::wait_ld(wr);
-            V qv[C], rv[C];
-            TRow::template unpack<C>(wq, qv);
-            TRow::template unpack<C>(wr, rv);
-#pragma unroll
-            for (int i = 0; i < C; ++i) {
-                const double fac = n_alpha - jap1[j + i];
-                acc = vfma(splat<N>(fac), rv[C - 1 - i] * qv[i], acc);
-            }
-        }
-        for (; j < n; ++j) {
-            tm::words<2 * N> wq, wr;
-            Q.template issue<1>(j, wq);
-            R2.template issue<1>(n - j, wr);
-            tm::wait_ld(wq);
-            tm::wait_ld(wr);
-            V qv[1], rv[1];
-            TRow::template unpack<1>(wq, qv);
-            TRow::template unpack<1>(wr, rv);
-            const double fac = n_alpha - jap1[j];
-            acc = vfma(splat<N>(fac), rv[0] * qv[0], acc);
-        }
-        tm::wait_ld(w0);
-        V r20[1];
-        TRow::template unpack<1>(w0, r20);
-        q = acc / (nd * r20[0]);
-    }
-    Q.set(n, q);
-
-    // ---- m_k^[n] = sum_j A^[n-j] B^[j], (A, B) = (d_k, f) or (f, d_k), f^[j] = c1 q^[j] ----
+    // ---- q^[n] = pow(r2, alpha) and m_k^[n] = sum_j A^[n-j] B^[j], (A, B) = (d_k, f) or (f, d_k), f^[j] = c1 q^[j].
+    // When the products read f ascending ((A, B) = (d_k, f), the n-body case), the terms j < n of the three
+    // products are accumulated in the loop of the pow recurrence, which walks q^[0..n-1] in the same direction:
+    // one pass over the q history instead of two, four independent accumulation chains instead of one. Every
+    // accumulator still sees its own terms in its own order. ----
     const double c1 = fkind == 1u ? t.cst(aux[14]) : (fkind == 2u ? -1. : 1.);
     const bool f_first = aux[16] != 0u;
+    V q;
     V acc[3] = {splat<N>(0.), splat<N>(0.), splat<N>(0.)};
     if (!f_first) {
-        // q ascending, d descending.
         const double *pd0 = d0[0] + n * S, *pd1 = d0[1] + n * S, *pd2 = TD == 0 ? d0[2] + n * S : nullptr;
-        std::uint32_t j = 0;
-        for (; j + C <= n + 1u; j += C) {
-            V qv[C], dv[C];
-            ldc(Q, j, qv);
-            if constexpr (TD == 1) {
-                ldc(D2, n - j - (C - 1u), dv); // d2^[n - j - i] = dv[C - 1 - i]
-            }
+        if (n == 0u) {
+            q = pow_eval(aux[12], r2n, splat<N>(t.cst(aux[11])));
+        } else {
+            const double nd = static_cast<double>(n);
+            const double n_alpha = nd * t.cst(aux[11]);
+            const double *jap1 = t.consts + aux[13];
+            tm::words<2 * N> w0;
+            R2.template issue<1>(0u, w0); // r2^[0] for the final division
+            V accq = splat<N>(0.);
+            std::uint32_t j = 0;
+            for (; j + C <= n; j += C) {
+                tm::words<2 * N * C> wq, wr, wd;
+                Q.template issue<C>(j, wq);
+                R2.template issue<C>(n - j - (C - 1u), wr); // r2^[n - j - i] = rv[C - 1 - i]
+                if constexpr (TD == 1) {
+                    D2.template issue<C>(n - j - (C - 1u), wd); // d2^[n - j - i] = dv[C - 1 - i]
+                }
+                tm::wait_ld(wq);
+                tm::wait_ld(wr);
+                V qv[C], rv[C], dv[C];
+                TRow::template unpack<C>(wq, qv);
+                TRow::template unpack<C>(wr, rv);
+                if constexpr (TD == 1) {
+                    tm::wait_ld(wd);
+                    TRow::template unpack<C>(wd, dv);
+                }
 #pragma unroll
-            for (int i = 0; i < C; ++i) {
-                const V fj = c1 * qv[i];
+                for (int i = 0; i < C; ++i) {
+                    const double fac = n_alpha - jap1[j + i];
+                    accq = vfma(splat<N>(fac), rv[C - 1 - i] * qv[i], accq);
+                    const V fj = c1 * qv[i];
+                    acc[0] = vfma(Row::load(pd0), fj, acc[0]);
+                    acc[1] = vfma(Row::load(pd1), fj, acc[1]);
+                    acc[2] = vfma(TD == 1 ? dv[C - 1 - i] : Row::load(pd2), fj, acc[2]);
+                    pd0 -= S;
+                    pd1 -= S;
+                    if (TD == 0) {
+                        pd2 -= S;
+                    }
+                }
+            }
+            for (; j < n; ++j) {
+                tm::words<2 * N> wq, wr, wd;
+                Q.template issue<1>(j, wq);
+                R2.template issue<1>(n - j, wr);
+                if constexpr (TD == 1) {
+                    D2.template issue<1>(n - j, wd);
+                }
+                tm::wait_ld(wq);
+                tm::wait_ld(wr);
+                V qv[1], rv[1], dv[1];
+                TRow::template unpack<1>(wq, qv);
+                TRow::template unpack<1>(wr, rv);
+                if constexpr (TD == 1) {
+                    tm::wait_ld(wd);
+                    TRow::template unpack<1>(wd, dv);
+                }
+                const double fac = n_alpha - jap1[j];
+                accq = vfma(splat<N>(fac), rv[0] * qv[0], accq);
+                const V fj = c1 * qv[0];
                 acc[0] = vfma(Row::load(pd0), fj, acc[0]);
                 acc[1] = vfma(Row::load(pd1), fj, acc[1]);
-                acc[2] = vfma(TD == 1 ? dv[C - 1 - i] : Row::load(pd2), fj, acc[2]);
+                acc[2] = vfma(TD == 1 ? dv[0] : Row::load(pd2), fj, acc[2]);
                 pd0 -= S;
                 pd1 -= S;
                 if (TD == 0) {
                     pd2 -= S;
                 }
             }
+            tm::wait_ld(w0);
+            V r20[1];
+            TRow::template unpack<1>(w0, r20);
+            q = accq / (nd * r20[0]);
         }
-        for (; j <= n; ++j) {
-            const V fj = c1 * Q.get(j);
+        Q.set(n, q);
+        // The last term of the products, j = n: d_k^[0] f^[n].
+        {
+            const V fj = c1 * q;
             acc[0] = vfma(Row::load(pd0), fj, acc[0]);
             acc[1] = vfma(Row::load(pd1), fj, acc[1]);
-            acc[2] = vfma(TD == 1 ? D2.get(n - j) : Row::load(pd2), fj, acc[2]);
-            pd0 -= S;
-            pd1 -= S;
-            if (TD == 0) {
-                pd2 -= S;
-            }
+            acc[2] = vfma(TD == 1 ? D2.get(0u) : Row::load(pd2), fj, acc[2]);
         }
     } else {
+        if (n == 0u) {
+            q = pow_eval(aux[12], r2n, splat<N>(t.cst(aux[11])));
+        } else {
+            const double nd = static_cast<double>(n);
+            const double n_alpha = nd * t.cst(aux[11]);
+            const double *jap1 = t.consts + aux[13];
+            tm::words<2 * N> w0;
+            R2.template issue<1>(0u, w0); // r2^[0] for the final division
+            V acc = splat<N>(0.);
+            std::uint32_t j = 0;
+            for (; j + C <= n; j += C) {
+                tm::words<2 * N * C> wq, wr;
+                Q.template issue<C>(j, wq);
+                R2.template issue<C>(n - j - (C - 1u), wr); // r2^[n - j - i] = rv[C - 1 - i]
+                tm::wait_ld(wq);
+                tm::wait_ld(wr);
+                V qv[C], rv[C];
+                TRow::template unpack<C>(wq, qv);
+                TRow::template unpack<C>(wr, rv);
+#pragma unroll
+                for (int i = 0; i < C; ++i) {
+                    const double fac = n_alpha - jap1[j + i];
+                    acc = vfma(splat<N>(fac), rv[C - 1 - i] * qv[i], acc);
+                }
+            }
+            for (; j < n; ++j) {
+                tm::words<2 * N> wq, wr;
+                Q.template issue<1>(j, wq);
+                R2.template issue<1>(n - j, wr);
+                tm::wait_ld(wq);
+                tm::wait_ld(wr);
+                V qv[1], rv[1];
+                TRow::template unpack<1>(wq, qv);
+                TRow::template unpack<1>(wr, rv);
+                const double fac = n_alpha - jap1[j];
+                acc = vfma(splat<N>(fac), rv[0] * qv[0], acc);
+            }
+            tm::wait_ld(w0);
+            V r20[1];
+            TRow::template unpack<1>(w0, r20);
+            q = acc / (nd * r20[0]);
+        }
+        Q.set(n, q);
+
         // q descending, d ascending.
         const double *pd0 = d0[0], *pd1 = d0[1], *pd2 = TD == 0 ? d0[2] : nullptr;
         std::uint32_t j = 0;
