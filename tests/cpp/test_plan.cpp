@@ -28,7 +28,7 @@ int main()
     const auto P = detail::lower_decomposition(dc, 36, 0, 20, true);
     REQUIRE(P.n_uvars == 234u);
 
-    // Reference tape: every u variable at every order (src/taylor_02.cpp:1227-1233) = 234 * 21 = 4914 doubles per lane.
+    // Reference tape: n_uvars * order + n_eq (src/taylor_02.cpp:1227-1233) = 234 * 20 + 36 = 4716 doubles per lane.
     const auto plain = detail::make_smem_plan(P, false, false, false, 0);
     const auto fused = detail::make_smem_plan(P, true, true, false, 0);
     const auto tm2 = detail::make_smem_plan(P, true, true, false, 32, 2);
