@@ -59,6 +59,21 @@ int main()
             REQUIRE(banks.size() == 8u);
         }
     }
+    // model::nbody with 32 bodies: 496 pair interactions in level 0 (too many for the one-pair-per-thread tensor-memory
+    // layout), sums of up to 31 terms split at 8 (src/taylor_01.cpp split_sums), a tape far beyond shared memory.
+    {
+        std::vector<double> m32(32, 1e-4);
+        m32[0] = 1.;
+        auto sys32 = model::nbody(32, kw::masses = m32);
+        auto [dc32, sv32] = taylor_decompose_sys(sys32, {});
+        const auto P32 = detail::lower_decomposition(dc32, 192, 0, 20, false);
+        const auto pl = detail::make_smem_plan(P32, true, true, false, 32, 3);
+        std::printf("N = 32: %u u variables, %u superinstructions, %u levels, %u slots per lane\n", P32.n_uvars,
+                    pl.n_fused, pl.n_segments, pl.n_slots);
+        REQUIRE(pl.n_fused == 496u && pl.tmem == 0u);
+        REQUIRE(pl.seg_offsets[1] - pl.seg_offsets[0] == 496u);
+        REQUIRE(pl.n_slots * 8u > 227u * 1024u); // one lane alone does not fit in an SM's shared memory
+    }
     if (n_fail == 0) {
         std::printf("ALL PASSED\n");
         return 0;
