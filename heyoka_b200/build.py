@@ -69,7 +69,7 @@ def build(force=False, verbose=True):
         if src.endswith(".cu"):
             cmd = [nvcc] + NVCC_ARCH + COMMON + CUDA_FLAGS + ["-c", path, "-o", obj]
         else:
-            cmd = [nvcc] + COMMON + ["-Xcompiler", "-fPIC,-Wall,-Wextra", "-c", path, "-o", obj]
+            cmd = [nvcc] + NVCC_ARCH + COMMON + ["-Xcompiler", "-fPIC,-Wall,-Wextra", "-c", path, "-o", obj]
         jobs.append((obj, path, cmd))
     inst = os.path.join(CSRC, "coop_inst.cu")
     for n_lanes, maxt, gen in COOP_FAMILIES:

@@ -619,7 +619,7 @@ __device__ __forceinline__ void coop_jet(const program &P, const coop_header &H,
     constexpr std::uint32_t G = L / N; // lane groups per warp
     const std::uint32_t tid = T::tid();
     const std::uint32_t nthr = T::size();
-    const std::uint32_t pp1 = P.order + 1u, p = P.order;
+    const std::uint32_t p = P.order;
     const uint4 *ops = reinterpret_cast<const uint4 *>(tab + H.off_ops);
     const std::uint32_t *seg = tab + H.off_seg;
     const std::uint32_t *aux = tab + H.off_aux;
