@@ -18,14 +18,17 @@ LIBDIR = os.path.join(HERE, "lib")
 OBJDIR = os.path.join(ROOT, "build", "obj")
 LIB = os.path.join(LIBDIR, "libheyoka_b200.so")
 
-HOST_SOURCES = ["expression.cpp", "decompose.cpp", "model.cpp", "lower.cpp", "smem_plan.cpp", "capi_host.cpp",
-                "taylor_adaptive_batch.cpp"]
+HOST_SOURCES = ["expression.cpp", "decompose.cpp", "model.cpp", "lower.cpp", "smem_plan.cpp", "nb_plan.cpp",
+                "capi_host.cpp", "taylor_adaptive_batch.cpp"]
 CUDA_SOURCES = ["batch.cu"]
 # The cooperative kernel is instantiated per (lanes per thread, max threads per CTA, mode) family, one
 # object each (built in parallel).
 COOP_FAMILIES = ([(n, m, g) for n in (1, 2, 4) for m in (512, 256) for g in (1, 0)]
                  + [(n, m, g) for n in (1, 2) for m in (512, 384, 256) for g in (2, 3)]
                  + [(1, 512, 4), (2, 512, 4), (1, 512, 5), (2, 512, 5)])
+
+# The dedicated N-body kernel: one object per (lanes per team, CTA-wide team) family.
+NB_FAMILIES = [(lt, 0) for lt in (1, 2, 4, 8, 16, 32)] + [(1, 1)]
 
 NVCC_ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 CUDA_FLAGS = ["-lineinfo", "-fmad=false", "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
@@ -59,7 +62,7 @@ def build(force=False, verbose=True):
     os.makedirs(LIBDIR, exist_ok=True)
     os.makedirs(OBJDIR, exist_ok=True)
     hdrs = _all_headers()
-    srcs = [os.path.join(CSRC, f) for f in HOST_SOURCES + CUDA_SOURCES + ["coop_inst.cu"]]
+    srcs = [os.path.join(CSRC, f) for f in HOST_SOURCES + CUDA_SOURCES + ["coop_inst.cu", "nb_inst.cu"]]
     if not force and not _deps_newer(LIB, srcs + hdrs):
         return LIB  # up to date (the objects under build/ do not travel to the GPU box)
     jobs = []  # (obj, deps, cmd)
@@ -77,8 +80,28 @@ def build(force=False, verbose=True):
         cmd = [nvcc] + NVCC_ARCH + COMMON + CUDA_FLAGS + ["-DHY_COOP_N=%d" % n_lanes, "-DHY_COOP_MAXT=%d" % maxt,
                                                           "-DHY_COOP_MODE=%d" % gen, "-c", inst, "-o", obj]
         jobs.append((obj, inst, cmd))
+    nb_inst = os.path.join(CSRC, "nb_inst.cu")
+    for lt, cta in NB_FAMILIES:
+        obj = os.path.join(OBJDIR, "nb_inst_lt%d_cta%d.o" % (lt, cta))
+        cmd = [nvcc] + NVCC_ARCH + COMMON + CUDA_FLAGS + ["-DHY_NB_LT=%d" % lt, "-DHY_NB_CTA=%d" % cta, "-c", nb_inst,
+                                                          "-o", obj]
+        jobs.append((obj, nb_inst, cmd))
     objs = [j[0] for j in jobs]
-    todo = [j for j in jobs if force or _deps_newer(j[0], [j[1]] + hdrs)]
+    # Headers each kind of object depends on (a change in the N-body kernel does not rebuild the cooperative families).
+    nb_only = {"nb_kernel.cuh", "nb_core.hpp", "nb_desc.hpp", "nb_plan.hpp", "nb_variants.hpp"}
+    host_only = {"smem_plan.hpp", "capi_common.hpp", "program.hpp"}
+
+    def deps_of(job):
+        name = os.path.basename(job[0])
+        if name.startswith("coop_inst"):
+            return [h for h in hdrs if os.path.basename(h) not in nb_only | host_only
+                    and not h.startswith(os.path.join(ROOT, "include", "heyoka_b200") + os.sep)]
+        if name.startswith("nb_inst"):
+            return [h for h in hdrs if os.path.basename(h) not in host_only | {"nb_plan.hpp", "coop_variants.hpp"}
+                    and not h.startswith(os.path.join(ROOT, "include", "heyoka_b200") + os.sep)]
+        return hdrs
+
+    todo = [j for j in jobs if force or _deps_newer(j[0], [j[1]] + deps_of(j))]
 
     def run(job):
         if verbose:

@@ -21,6 +21,9 @@
 #include "coop_variants.hpp"
 #include "device_program.cuh"
 #include "kernels.cuh"
+#include "nb_kernel.cuh"
+#include "nb_plan.hpp"
+#include "nb_variants.hpp"
 #include "small_kernels.cuh"
 #include "program.hpp"
 #include "smem_plan.hpp"
@@ -83,6 +86,23 @@ const coop_variant *find_variant(int L, int N, int maxt, int mode)
     for (const auto &f : fams) {
         for (std::size_t i = 0; i < f.n; ++i) {
             if (f.v[i].L == L && f.v[i].N == N && f.v[i].maxt == maxt && f.v[i].mode == mode) {
+                return f.v + i;
+            }
+        }
+    }
+    return nullptr;
+}
+
+// The N-body kernel's instantiations (nb_variants.hpp).
+const hy::detail::nb_variant *find_nb_variant(int LT, bool cta, bool tmem, int maxt)
+{
+    const hy::detail::nb_family fams[] = {hy::detail::nb_family_lt1_cta0(),  hy::detail::nb_family_lt2_cta0(),
+                                          hy::detail::nb_family_lt4_cta0(),  hy::detail::nb_family_lt8_cta0(),
+                                          hy::detail::nb_family_lt16_cta0(), hy::detail::nb_family_lt32_cta0(),
+                                          hy::detail::nb_family_lt1_cta1()};
+    for (const auto &f : fams) {
+        for (std::size_t i = 0; i < f.n; ++i) {
+            if (f.v[i].LT == LT && f.v[i].cta == cta && f.v[i].tmem == tmem && f.v[i].maxt == maxt) {
                 return f.v + i;
             }
         }
@@ -201,6 +221,17 @@ struct hy_batch {
     void setup_coop_global(int L, int N, std::uint32_t threads, int cta = -1);
     bool c_cta = false; // ... and the whole CTA working on one chunk of lanes (kernel mode 5)
     bool c_global = false; // cooperative kernel with the tape in global memory (kernel mode 4)
+    // The dedicated N-body kernel (nb_kernel.cuh): plan, device copies of its tables, selected instantiation.
+    hy::detail::nb_plan nbp;
+    hy::detail::nb_pair_desc *d_nb_pairs = nullptr;
+    std::uint32_t *d_nb_sums = nullptr;
+    double *d_nb_consts = nullptr, *d_nb_fac = nullptr;
+    dev::nb_dev_plan nbd{};
+    const hy::detail::nb_variant *nbv = nullptr;
+    coop_variant nb_cv{}; // (L, N, maxt, mode 6) of the selected N-body instantiation, for the code that reads cv->L
+    bool nb_on = false;
+    int opt_nb = -1; // -1 automatic, 0 never (HEYOKA_B200_NB=0), 1 preferred
+    bool setup_nb(int LT, std::uint32_t threads, int want_tmem, int want_cta);
 
     // Resident arrays.
     double *d_state = nullptr, *d_pars = nullptr, *d_t_hi = nullptr, *d_t_lo = nullptr, *d_last_h = nullptr,
@@ -270,7 +301,9 @@ void hy_batch::free_all() noexcept
           static_cast<void *>(d_tc), static_cast<void *>(d_d_out), static_cast<void *>(d_step_outcome),
           static_cast<void *>(d_prop_outcome), static_cast<void *>(d_prop_min_h), static_cast<void *>(d_prop_max_h),
           static_cast<void *>(d_prop_n_steps), static_cast<void *>(d_scratch), static_cast<void *>(d_tmp),
-          static_cast<void *>(d_snapshot), static_cast<void *>(d_counter), static_cast<void *>(d_flags)}) {
+          static_cast<void *>(d_snapshot), static_cast<void *>(d_counter), static_cast<void *>(d_flags),
+          static_cast<void *>(d_nb_pairs), static_cast<void *>(d_nb_sums), static_cast<void *>(d_nb_consts),
+          static_cast<void *>(d_nb_fac)}) {
         if (p != nullptr) {
             cudaFree(p);
         }
@@ -616,10 +649,193 @@ void hy_batch::setup_coop_global(int L, int N, std::uint32_t threads, int cta)
     c_cta = cta != 0;
 }
 
+// The dedicated N-body kernel. LT = lanes per team (0: as many as give every thread of a warp one pair interaction),
+// threads = CTA size (0: as many warps as fit), want_tmem / want_cta: -1 automatic. Returns false if the program
+// does not qualify or nothing fits.
+bool hy_batch::setup_nb(int LT, std::uint32_t threads, int want_tmem, int want_cta)
+{
+    if (!nbp.ok) {
+        return false;
+    }
+    const std::size_t reserve = 1024u;
+    const std::uint32_t n_pairs = static_cast<std::uint32_t>(nbp.pairs.size());
+    const std::uint32_t npp = (order + 1u) / 2u;
+    bool cta = want_cta > 0 || (want_cta < 0 && n_pairs > 32u);
+    if (!cta && n_pairs > 32u) {
+        return false;
+    }
+    if (LT == 0) {
+        LT = 1;
+        if (!cta) {
+            while (static_cast<std::uint32_t>(2 * LT) * n_pairs <= 32u) {
+                LT *= 2;
+            }
+        }
+    }
+    if (cta && (LT != 1 || n_pairs > 512u)) {
+        return false;
+    }
+    if (!cta && (LT < 1 || LT > 32 || (LT & (LT - 1)) != 0 || static_cast<std::uint32_t>(LT) * n_pairs > 32u)) {
+        return false;
+    }
+    const std::uint32_t TT = cta ? 512u : 32u;
+    const std::uint32_t n_sums = static_cast<std::uint32_t>(nbp.sums.size());
+    const std::uint32_t n_levels = static_cast<std::uint32_t>(nbp.level_offsets.size()) - 1u;
+    if (n_levels > 7u) {
+        return false;
+    }
+    const auto shared_doubles = [&](bool sums_in_smem) {
+        std::size_t d = static_cast<std::size_t>(order + 1u) * nbp.fac_stride + ((order + 5u) & ~1u)
+                        + ((nbp.consts.size() + 1u) & ~std::size_t(1));
+        if (sums_in_smem) {
+            d += static_cast<std::size_t>(n_sums) * 8u;
+        }
+        return d;
+    };
+    const auto team_slots = [&](bool tmem) {
+        const std::size_t d = (static_cast<std::size_t>(nbp.n_pos) + nbp.n_out) * LT * 2u
+                              + static_cast<std::size_t>(tmem ? 2u : 5u) * npp * TT * 2u;
+        return static_cast<std::uint32_t>((d + LT - 1u) / LT);
+    };
+    // Teams (warps) per CTA that fit: shared memory, tensor-memory columns (12 per order pair and thread).
+    struct choice {
+        bool tmem = false, sums_in_smem = false;
+        std::uint32_t warps = 0;
+    };
+    const auto fit = [&](bool tmem) {
+        choice c;
+        c.tmem = tmem;
+        for (const bool sis : {true, false}) {
+            const std::size_t sh = shared_doubles(sis) * sizeof(double);
+            const std::size_t tb = coop_warp_bytes(team_slots(tmem), LT);
+            if (sh + tb + reserve > smem_per_block_max) {
+                continue;
+            }
+            std::uint32_t w = cta ? 16u : static_cast<std::uint32_t>(std::min<std::size_t>((smem_per_block_max - reserve - sh) / tb, 16u));
+            if (tmem) {
+                const std::uint32_t cols = npp * 12u;
+                const std::uint32_t per_quadrant = cols == 0u || cols > 512u ? 0u : 512u / cols;
+                w = std::min(w, 4u * per_quadrant);
+            }
+            if (cta && w < 16u) {
+                w = 0u;
+            }
+            if (w > c.warps) {
+                c.warps = w;
+                c.sums_in_smem = sis;
+            }
+            if (w != 0u) {
+                break;
+            }
+        }
+        return c;
+    };
+    choice pick;
+    if (want_tmem != 0 && opt_tmem) {
+        pick = fit(true);
+    }
+    if (want_tmem <= 0) {
+        const auto alt = fit(false);
+        if (alt.warps > pick.warps) {
+            pick = alt;
+        }
+    }
+    if (pick.warps == 0u) {
+        return false;
+    }
+    if (threads == 0u) {
+        threads = 32u * pick.warps;
+    }
+    if (threads % 32u != 0u || threads == 0u || threads / 32u > pick.warps || (cta && threads != 512u)) {
+        throw std::invalid_argument("Invalid number of threads for the N-body kernel");
+    }
+    const int pref_maxt = threads <= 256u ? 256 : (threads <= 384u ? 384 : 512);
+    const hy::detail::nb_variant *v = nullptr;
+    for (const int mt : {256, 384, 512}) {
+        if (mt >= pref_maxt && v == nullptr) {
+            v = find_nb_variant(LT, cta, pick.tmem, mt);
+        }
+    }
+    if (v == nullptr) {
+        return false;
+    }
+    // Device copies of the tables.
+    if (d_nb_pairs == nullptr) {
+        d_nb_pairs = dupload(nbp.pairs);
+        std::vector<std::uint32_t> words(static_cast<std::size_t>(n_sums) * 16u);
+        static_assert(sizeof(hy::detail::nb_sum_desc) == 64u);
+        std::memcpy(words.data(), nbp.sums.data(), words.size() * 4u);
+        d_nb_sums = dupload(words);
+        d_nb_consts = dupload(nbp.consts);
+        d_nb_fac = dupload(nbp.fac);
+    }
+    nbd = dev::nb_dev_plan{};
+    nbd.pairs = d_nb_pairs;
+    nbd.sums = d_nb_sums;
+    nbd.consts = d_nb_consts;
+    nbd.fac = d_nb_fac;
+    nbd.n_pairs = n_pairs;
+    nbd.n_pos = nbp.n_pos;
+    nbd.n_out = nbp.n_out;
+    nbd.n_levels = n_levels;
+    nbd.n_sums = n_sums;
+    nbd.n_consts = static_cast<std::uint32_t>(nbp.consts.size());
+    nbd.npp = npp;
+    nbd.fac_stride = nbp.fac_stride;
+    for (std::uint32_t i = 0; i <= n_levels; ++i) {
+        nbd.level_offsets[i] = nbp.level_offsets[i];
+    }
+    nbd.alpha = nbp.alpha;
+    nbd.pow_algo = nbp.pow_algo;
+    nbd.sums_in_smem = pick.sums_in_smem ? 1u : 0u;
+    nbd.shared_doubles = static_cast<std::uint32_t>(shared_doubles(pick.sums_in_smem));
+    nbd.n_slots_equiv = team_slots(pick.tmem);
+    const std::size_t team_bytes = coop_warp_bytes(nbd.n_slots_equiv, LT);
+    nbd.team_doubles = static_cast<std::uint32_t>(team_bytes / sizeof(double));
+    const std::uint32_t teams = cta ? 1u : threads / 32u;
+    const std::size_t bytes = static_cast<std::size_t>(nbd.shared_doubles) * sizeof(double) + teams * team_bytes;
+    for (auto fn : {v->step, v->prop}) {
+        HY_CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes)));
+    }
+    for (double **ptr : {&d_gscratch, &d_cscratch}) {
+        if (*ptr != nullptr) {
+            HY_CUDA_CHECK(cudaFree(*ptr));
+            *ptr = nullptr;
+        }
+    }
+    nbv = v;
+    nb_cv = coop_variant{LT, LT >= 2 ? 2 : 1, v->maxt, cta ? 7 : 6, nullptr, nullptr};
+    cv = &nb_cv;
+    c_threads = threads;
+    c_smem = bytes;
+    c_ctas_per_sm = 1;
+    const std::uint32_t lanes_per_block = static_cast<std::uint32_t>(LT) * teams;
+    const std::uint32_t n_blocks_needed = (n + lanes_per_block - 1u) / lanes_per_block;
+    c_grid = std::max(1u, std::min(n_sms, n_blocks_needed));
+    d_cscratch = dalloc<double>(static_cast<std::size_t>(c_grid) * teams * (order + 1u) * n_eq
+                                * static_cast<std::size_t>(LT));
+    mode = 2;
+    nb_on = true;
+    c_cta = cta;
+    return true;
+}
+
 void hy_batch::configure(int want_mode, int L, int N, std::uint32_t threads, std::uint32_t blocks_per_sm)
 {
     c_global = false;
     c_cta = false;
+    nb_on = false;
+    // Mode 6 / 7: the N-body kernel with warp / CTA teams (N: 0 automatic, 1 tensor memory, 2 shared memory only).
+    // Automatic mode takes it whenever the program qualifies (nb_plan.hpp).
+    if (want_mode == 6 || want_mode == 7 || (want_mode == 0 && opt_nb != 0)) {
+        if (setup_nb(L, threads, N == 0 ? -1 : (N == 1 ? 1 : 0), want_mode == 0 ? -1 : (want_mode == 7 ? 1 : 0))) {
+            return;
+        }
+        if (want_mode != 0) {
+            throw std::invalid_argument("The N-body kernel cannot run this program: "
+                                        + (nbp.ok ? std::string("no configuration fits on an SM") : nbp.why));
+        }
+    }
     if (want_mode == 4 || want_mode == 5) {
         setup_coop_global(L, N, threads, want_mode == 5 ? 1 : 0);
         return;
@@ -670,7 +886,11 @@ void hy_batch::launch(bool prop, const dev::run_args &R)
         R2.coef_warp_stride = pub ? 0ull : static_cast<unsigned long long>(order + 1u) * n_eq * lanes;
         R2.coef_stride_sv = pub ? static_cast<unsigned long long>(order + 1u) * n : lanes;
         R2.coef_stride_o = pub ? static_cast<unsigned long long>(n) : static_cast<unsigned long long>(n_eq) * lanes;
-        (prop ? cv->prop : cv->step)<<<c_grid, c_threads, c_smem, stream>>>(prog, d_blob, view(), R2, d_gscratch);
+        if (nb_on) {
+            (prop ? nbv->prop : nbv->step)<<<c_grid, c_threads, c_smem, stream>>>(prog, nbd, view(), R2);
+        } else {
+            (prop ? cv->prop : cv->step)<<<c_grid, c_threads, c_smem, stream>>>(prog, d_blob, view(), R2, d_gscratch);
+        }
     } else if (prop) {
         dev::k_hbm<true><<<h_grid, h_threads, 0, stream>>>(prog, view(), R, d_scratch, slab_doubles);
     } else {
@@ -867,8 +1087,12 @@ int hy_batch_create(const hy_program *p, uint32_t batch, int device, hy_batch **
         if (const char *env = std::getenv("HEYOKA_B200_TMEM_ROWS")) {
             b->opt_tmem_rows = std::string{env} == "3" ? 3u : (std::string{env} == "2" ? 2u : 0u);
         }
+        if (const char *env = std::getenv("HEYOKA_B200_NB")) {
+            b->opt_nb = std::string{env} != "0" ? 1 : 0;
+        }
         b->prog_host = std::make_shared<const hy_program>(*p);
         b->replan(false);
+        b->nbp = hy::detail::make_nb_plan(*p);
 
         // Resident arrays.
         const std::size_t n = batch;
@@ -943,7 +1167,11 @@ int hy_batch_set_launch_config(hy_batch *b, uint32_t block_threads, uint32_t blo
         HY_CUDA_CHECK(cudaStreamSynchronize(b->stream));
         const int L = b->cv != nullptr && b->mode == 2 ? b->cv->L : 0;
         const int N = b->cv != nullptr && b->mode == 2 ? b->cv->N : 0;
-        b->configure(b->mode, L, N, block_threads, blocks_per_sm);
+        if (b->nb_on) {
+            b->configure(b->c_cta ? 7 : 6, L, b->nbv->tmem ? 1 : 2, block_threads, blocks_per_sm);
+        } else {
+            b->configure(b->mode, L, N, block_threads, blocks_per_sm);
+        }
         return HY_OK;
     } catch (...) {
         return translate_exception();
@@ -957,7 +1185,7 @@ int hy_batch_set_kernel(hy_batch *b, int tape_mode, uint32_t lanes_per_warp, uin
         if (b == nullptr) {
             throw std::invalid_argument("Null batch");
         }
-        if (tape_mode < 0 || tape_mode > 5) {
+        if (tape_mode < 0 || tape_mode > 7) {
             throw std::invalid_argument("Invalid tape mode");
         }
         device_guard guard(b->device);
@@ -976,19 +1204,22 @@ int hy_batch_get_kernel(const hy_batch *b, hy_kernel_info *out)
         hy::detail::set_last_error("Null pointer passed to hy_batch_get_kernel()");
         return HY_ERR_INVALID_ARG;
     }
-    out->tape_mode = b->mode == 2 && b->c_global ? (b->c_cta ? 5 : 4) : b->mode;
+    out->tape_mode = b->nb_on ? (b->c_cta ? 7 : 6) : (b->mode == 2 && b->c_global ? (b->c_cta ? 5 : 4) : b->mode);
     out->lanes_per_warp = b->mode == 2 ? static_cast<uint32_t>(b->cv->L) : 32u;
     out->lanes_per_thread = b->mode == 2 ? static_cast<uint32_t>(b->cv->N) : 1u;
     out->block_threads = b->mode == 2 ? b->c_threads : b->h_threads;
     out->blocks_per_sm = b->mode == 2 ? b->c_ctas_per_sm : b->h_blocks_per_sm;
     out->grid = b->mode == 2 ? b->c_grid : b->h_grid;
     out->smem_bytes = b->mode == 2 ? static_cast<uint64_t>(b->c_smem) : 0u;
-    out->tape_slots_per_lane = b->mode == 2 ? b->plan.n_slots : b->n_uvars * (b->order + 1u);
+    out->tape_slots_per_lane = b->nb_on ? b->nbd.n_slots_equiv : (b->mode == 2 ? b->plan.n_slots : b->n_uvars * (b->order + 1u));
     out->n_segments = b->plan.n_segments;
     out->n_fused = b->plan.n_fused;
     out->n_sms = b->n_sms;
     out->tmem_cols_per_warp
-        = b->mode == 2 && b->plan.tmem != 0u ? b->plan.tmem * (b->order + 1u) * 2u * static_cast<uint32_t>(b->cv->N) : 0u;
+        = b->nb_on ? (b->nbv->tmem ? b->nbd.npp * 12u : 0u)
+                   : (b->mode == 2 && b->plan.tmem != 0u
+                          ? b->plan.tmem * (b->order + 1u) * 2u * static_cast<uint32_t>(b->cv->N)
+                          : 0u);
     out->reserved = 0u;
     return HY_OK;
 }
