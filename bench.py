@@ -27,7 +27,7 @@ import time
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
-for p in (ROOT, os.path.join(ROOT, "tests")):
+for p in (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "oracle")):
     if p not in sys.path:
         sys.path.insert(0, p)
 
@@ -43,7 +43,7 @@ def parse_args():
     ap.add_argument("--perturb", type=float, default=1e-3)
     ap.add_argument("--cpu-lanes", type=int, default=0, help="lanes of the CPU sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--tape", default="auto", choices=["auto", "hbm", "smem", "smem-notmem", "global", "global-cta"])
+    ap.add_argument("--tape", default="auto", choices=["auto", "hbm", "smem", "smem-notmem", "global", "global-cta", "nbody", "nbody-cta"])
     ap.add_argument("--lanes-per-warp", type=int, default=0)
     ap.add_argument("--lanes-per-thread", type=int, default=0)
     ap.add_argument("--block-threads", type=int, default=0)
@@ -131,11 +131,12 @@ def workload(args, rank):
     return hb, P, st
 
 
-def cpu_port_run(P, st, tfinal, n_threads):
-    """Time the oracle's 8-lane port (restated CPU baseline, no LLVM JIT) on `st`; returns (lane_steps, seconds)."""
+def cpu_port_run(P, st, tfinal, n_threads, width=8):
+    """Time the oracle's driver on `st` (the jet is whatever is installed: the generated straight-line code of
+    oracle/codegen.py, or the interpreting port); returns (lane_steps, seconds)."""
     import oracle
     n = st.shape[1]
-    o = oracle.OracleIntegrator(P, st, n, mode=oracle.FMA, width=8)
+    o = oracle.OracleIntegrator(P, st, n, mode=oracle.FMA, width=width)
     t0 = time.perf_counter()
     o.propagate_until(tfinal, lockstep=False, n_threads=n_threads)
     dt = time.perf_counter() - t0
@@ -143,12 +144,47 @@ def cpu_port_run(P, st, tfinal, n_threads):
     return int(o.n_steps.sum()), dt
 
 
-def cpu_sample_lanes(args, cores):
+class CpuBaseline:
+    """The CPU arm: generated code (kind "codegen": one straight-line SIMD function per order, gcc -O2 -march=native
+    -ffp-contract=fast, the structure of the reference's LLVM-JIT'd stepper, see oracle/codegen.py) in the 4- and
+    8-lane variants, the faster of the two on this host; plus the interpreting port as a second figure."""
+
+    def __init__(self, P, cores, perturb):
+        import codegen
+        import oracle
+        from common import outer_ss_batch_state
+        self.P, self.cores, self.oracle, self.codegen = P, cores, oracle, codegen
+        self.jets = {w: codegen.Jet(P, w) for w in (4, 8)}  # compiled outside of every timed region
+        cal = outer_ss_batch_state(8 * cores, perturb=perturb, seed=7)
+        self.rates = {}
+        for w, j in self.jets.items():
+            j.install(oracle.lib)
+            cpu_port_run(P, cal, 1.0, cores, w)  # page in
+            s, dt = cpu_port_run(P, cal, 4.0, cores, w)
+            self.rates[w] = s / dt
+        self.width = max(self.rates, key=self.rates.get)
+        # The interpreting port (round 1's baseline), for reference.
+        codegen.Jet.uninstall(oracle.lib, 8)
+        s, dt = cpu_port_run(P, cal, 4.0, cores, 8)
+        self.interp_rate = s / dt
+        self.jets[8].install(oracle.lib)
+
+    def run(self, st, tfinal):
+        return cpu_port_run(self.P, st, tfinal, self.cores, self.width)
+
+    def describe(self, value, sample):
+        return {"value": value, "unit": "lane-steps/s", "cores": self.cores, "kind": "codegen", "simd_lanes": self.width,
+                "calibration_lane_steps_per_s": {"codegen_w%d" % w: r for w, r in self.rates.items()},
+                "interpreting_port_lane_steps_per_s": self.interp_rate,
+                "per_core_us_per_lane_step": 1e6 * self.cores / value, "sample": sample}
+
+
+def cpu_sample_lanes(args, cores, rate_per_core=2.0e5):
     if args.cpu_lanes:
         return args.cpu_lanes
-    # ~15 s of CPU work: a lane-step of the 6-body system costs ~6 us per core in the 8-lane port.
+    # ~15 s of CPU work at the calibrated rate (lane-steps/s per core).
     steps_per_lane = max(args.tfinal / 0.38, 1.0)
-    lanes = int(15.0 * cores / (6e-6 * steps_per_lane))
+    lanes = int(15.0 * cores * rate_per_core / steps_per_lane)
     return int(min(max(lanes // (8 * cores), 1) * 8 * cores, args.batch))
 
 
@@ -171,33 +207,34 @@ def host_cores():
 
 def run_reference(args):
     """--impl reference: the reference's CPU implementation of the path, timed on the host cores. The real
-    reference cannot be built in this image (no LLVM/Boost/fmt/spdlog/TBB), so this is the oracle's 8-lane CPU
-    port (kind: "port"), on a bounded sample of the same workload."""
+    reference cannot be built in this image (no LLVM/Boost/fmt/spdlog/TBB); its stepper is restated as GENERATED
+    straight-line SIMD code (kind: "codegen", see CpuBaseline), on a bounded sample of the same workload."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     _, P, _ = workload(argparse.Namespace(**{**vars(args), "batch": 8}), 0)
     from common import outer_ss_batch_state
     cores = host_cores()
-    lanes = cpu_sample_lanes(args, cores)
+    cb = CpuBaseline(P, cores, args.perturb)
+    lanes = cpu_sample_lanes(args, cores, cb.rates[cb.width] / cores)
     lanes = max(8 * cores, lanes // max(args.steps, 1))
     st = outer_ss_batch_state(lanes, perturb=args.perturb, seed=42)
     for _ in range(min(args.warmup, 1)):
-        cpu_port_run(P, st[:, :8 * cores], min(args.tfinal, 2.0), cores)
+        cb.run(st[:, :8 * cores], min(args.tfinal, 2.0))
     tot_steps, tot_t = 0, 0.0
     for _ in range(args.steps):
-        s, dt = cpu_port_run(P, st, args.tfinal, cores)
+        s, dt = cb.run(st, args.tfinal)
         tot_steps += s
         tot_t += dt
     val = tot_steps / tot_t
-    sample = "%d lanes x propagate_until(%g yr) per step, %d steps" % (lanes, args.tfinal, args.steps)
+    sample = "%d lanes x propagate_until(%g yr) per step, %d steps, %d threads" % (lanes, args.tfinal, args.steps, cores)
     print(json.dumps({
         "impl": "reference", "metric": "taylor_lane_steps_per_s", "value": val, "unit": "lane-steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "outer_ss_long_term_batch 6-body fp64 order 20 high_accuracy, t_final %g yr" % args.tfinal,
                    "lanes": lanes},
-        "cpu_baseline": {"value": val, "unit": "lane-steps/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": cb.describe(val, sample),
         "e2e": {"value": val, "unit": "lane-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
@@ -374,8 +411,9 @@ def main():
             },
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                          "traffic": measured_traffic(kinfo["tape"], lane_steps_rank), "peak_kind": peak_kind,
-                         "kernel": "k_coop<L=%d,N=%d,prop>" % (kinfo["lanes_per_warp"], kinfo["lanes_per_thread"])
-                         if kinfo["tape"] == "smem" else "k_hbm<prop>", "kernel_config": kinfo,
+                         "kernel": ("k_nb<LT=%d,prop>" % kinfo["lanes_per_warp"]) if kinfo["tape"].startswith("nbody")
+                         else ("k_coop<L=%d,N=%d,prop>" % (kinfo["lanes_per_warp"], kinfo["lanes_per_thread"])
+                               if kinfo["tape"] == "smem" else "k_hbm<prop>"), "kernel_config": kinfo,
                          "kernel_ms": k_ms, "b_tape_bytes_per_lane_step": costs["b_tape"],
                          "b_min_bytes_per_lane_step": costs["b_min"],
                          "frac_b_min": lane_steps_rank * costs["b_min"] / (k_ms * 1e-3) / 1e9 / peak,
@@ -388,12 +426,13 @@ def main():
         }
         if not args.no_cpu_baseline and world == 1:
             cores = host_cores()
-            lanes = cpu_sample_lanes(args, cores)
-            s, dt = cpu_port_run(P, st_host[:, :lanes], args.tfinal, cores)
-            out["cpu_baseline"] = {
-                "value": s / dt, "unit": "lane-steps/s", "cores": cores, "kind": "port",
-                "sample": "restated CPU baseline (oracle 8-lane port, no LLVM JIT): first %d lanes of the same batch, "
-                          "propagate_until(%g yr), %d threads, %.1f s" % (lanes, args.tfinal, cores, dt)}
+            cb = CpuBaseline(P, cores, args.perturb)
+            lanes = cpu_sample_lanes(args, cores, cb.rates[cb.width] / cores)
+            s, dt = cb.run(st_host[:, :lanes], args.tfinal)
+            out["cpu_baseline"] = cb.describe(
+                s / dt, "generated straight-line SIMD stepper (oracle/codegen.py; the reference's LLVM JIT is not "
+                        "buildable here): first %d lanes of the same batch, propagate_until(%g yr), %d threads, %.1f s"
+                % (lanes, args.tfinal, cores, dt))
         print(json.dumps(out))
 
     if world > 1:

@@ -313,7 +313,10 @@ class Batch:
         check(lib.hy_batch_set_launch_config(self._h, int(block_threads), int(blocks_per_sm)))
 
     def set_kernel(self, tape="auto", lanes_per_warp=0, lanes_per_thread=0, block_threads=0, blocks_per_sm=0):
-        mode = {"auto": 0, "hbm": 1, "smem": 2, "smem-notmem": 3, "global": 4, "global-cta": 5}[tape]
+        # "nbody" / "nbody-cta": the dedicated N-body kernel (warp / CTA teams); lanes_per_thread then selects the
+        # storage of the private rows: 0 automatic, 1 tensor memory, 2 shared memory only.
+        mode = {"auto": 0, "hbm": 1, "smem": 2, "smem-notmem": 3, "global": 4, "global-cta": 5, "nbody": 6,
+                "nbody-cta": 7}[tape]
         check(lib.hy_batch_set_kernel(self._h, mode, int(lanes_per_warp), int(lanes_per_thread), int(block_threads),
                                       int(blocks_per_sm)))
 
@@ -321,7 +324,7 @@ class Batch:
         ki = _capi.hy_kernel_info()
         check(lib.hy_batch_get_kernel(self._h, C.byref(ki)))
         d = {f[0]: getattr(ki, f[0]) for f in ki._fields_}
-        d["tape"] = {1: "hbm", 2: "smem", 4: "global", 5: "global-cta"}.get(ki.tape_mode, "?")
+        d["tape"] = {1: "hbm", 2: "smem", 4: "global", 5: "global-cta", 6: "nbody", 7: "nbody-cta"}.get(ki.tape_mode, "?")
         return d
 
     def sync(self):
@@ -692,7 +695,8 @@ class taylor_adaptive_batch:
         n = self._batch_size
         t = np.broadcast_to(np.asarray(t, dtype=np.float64), (n,))
         if rel_time:
-            tau = t
+            # Relative to the CURRENT time; the polynomial is expanded about the start of the last step (:2276-2280).
+            tau = self._last_h + t
         else:
             # tau = t - (time - last_h), in double-length arithmetic.
             hi, lo = _dfloat_add(self._t_hi, self._t_lo, -self._last_h, np.zeros(n))

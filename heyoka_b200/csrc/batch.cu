@@ -224,7 +224,8 @@ struct hy_batch {
     // The dedicated N-body kernel (nb_kernel.cuh): plan, device copies of its tables, selected instantiation.
     hy::detail::nb_plan nbp;
     hy::detail::nb_pair_desc *d_nb_pairs = nullptr;
-    std::uint32_t *d_nb_sums = nullptr;
+    hy::detail::nb_role *d_nb_roles = nullptr;
+    std::uint32_t opt_nb_threads = 0; // HEYOKA_B200_NB_THREADS: preferred CTA size of the N-body kernel
     double *d_nb_consts = nullptr, *d_nb_fac = nullptr;
     dev::nb_dev_plan nbd{};
     const hy::detail::nb_variant *nbv = nullptr;
@@ -302,7 +303,7 @@ void hy_batch::free_all() noexcept
           static_cast<void *>(d_prop_outcome), static_cast<void *>(d_prop_min_h), static_cast<void *>(d_prop_max_h),
           static_cast<void *>(d_prop_n_steps), static_cast<void *>(d_scratch), static_cast<void *>(d_tmp),
           static_cast<void *>(d_snapshot), static_cast<void *>(d_counter), static_cast<void *>(d_flags),
-          static_cast<void *>(d_nb_pairs), static_cast<void *>(d_nb_sums), static_cast<void *>(d_nb_consts),
+          static_cast<void *>(d_nb_pairs), static_cast<void *>(d_nb_roles), static_cast<void *>(d_nb_consts),
           static_cast<void *>(d_nb_fac)}) {
         if (p != nullptr) {
             cudaFree(p);
@@ -650,8 +651,8 @@ void hy_batch::setup_coop_global(int L, int N, std::uint32_t threads, int cta)
 }
 
 // The dedicated N-body kernel. LT = lanes per team (0: as many as give every thread of a warp one pair interaction),
-// threads = CTA size (0: as many warps as fit), want_tmem / want_cta: -1 automatic. Returns false if the program
-// does not qualify or nothing fits.
+// threads = CTA size (0: as many warps as fit; HEYOKA_B200_NB_THREADS caps it), want_tmem / want_cta: -1 automatic.
+// Returns false if the program does not qualify or nothing fits.
 bool hy_batch::setup_nb(int LT, std::uint32_t threads, int want_tmem, int want_cta)
 {
     if (!nbp.ok) {
@@ -660,7 +661,7 @@ bool hy_batch::setup_nb(int LT, std::uint32_t threads, int want_tmem, int want_c
     const std::size_t reserve = 1024u;
     const std::uint32_t n_pairs = static_cast<std::uint32_t>(nbp.pairs.size());
     const std::uint32_t npp = (order + 1u) / 2u;
-    bool cta = want_cta > 0 || (want_cta < 0 && n_pairs > 32u);
+    const bool cta = want_cta > 0 || (want_cta < 0 && n_pairs > 32u);
     if (!cta && n_pairs > 32u) {
         return false;
     }
@@ -678,40 +679,45 @@ bool hy_batch::setup_nb(int LT, std::uint32_t threads, int want_tmem, int want_c
     if (!cta && (LT < 1 || LT > 32 || (LT & (LT - 1)) != 0 || static_cast<std::uint32_t>(LT) * n_pairs > 32u)) {
         return false;
     }
-    const std::uint32_t TT = cta ? 512u : 32u;
-    const std::uint32_t n_sums = static_cast<std::uint32_t>(nbp.sums.size());
-    const std::uint32_t n_levels = static_cast<std::uint32_t>(nbp.level_offsets.size()) - 1u;
-    if (n_levels > 7u) {
+    const std::uint32_t TT = cta ? 512u : 32u, NL = LT >= 2 ? 2u : 1u;
+    // The role records address the outputs in 16-bit units of 16 bytes.
+    if (static_cast<std::uint64_t>(nbp.n_out) * LT >= 0xffffu || static_cast<std::uint64_t>(nbp.n_pos) * LT >= 0xffffu) {
         return false;
     }
-    const auto shared_doubles = [&](bool sums_in_smem) {
+    const auto roles = hy::detail::make_nb_roles(nbp, TT, static_cast<std::uint32_t>(LT), NL);
+    if (roles.n_rounds > 32u) {
+        return false;
+    }
+    const auto shared_doubles = [&](bool roles_in_smem) {
         std::size_t d = static_cast<std::size_t>(order + 1u) * nbp.fac_stride + ((order + 5u) & ~1u)
                         + ((nbp.consts.size() + 1u) & ~std::size_t(1));
-        if (sums_in_smem) {
-            d += static_cast<std::size_t>(n_sums) * 8u;
+        if (roles_in_smem) {
+            d += roles.table.size() * 4u;
         }
         return d;
     };
     const auto team_slots = [&](bool tmem) {
         const std::size_t d = (static_cast<std::size_t>(nbp.n_pos) + nbp.n_out) * LT * 2u
-                              + static_cast<std::size_t>(tmem ? 2u : 5u) * npp * TT * 2u;
+                              + static_cast<std::size_t>(tmem ? 2u : 5u) * npp * TT * 2u + (3u + 16u) * LT; // (+ norms, parked bookkeeping)
         return static_cast<std::uint32_t>((d + LT - 1u) / LT);
     };
     // Teams (warps) per CTA that fit: shared memory, tensor-memory columns (12 per order pair and thread).
     struct choice {
-        bool tmem = false, sums_in_smem = false;
+        bool tmem = false, roles_in_smem = false;
         std::uint32_t warps = 0;
     };
     const auto fit = [&](bool tmem) {
         choice c;
         c.tmem = tmem;
-        for (const bool sis : {true, false}) {
-            const std::size_t sh = shared_doubles(sis) * sizeof(double);
+        for (const bool ris : {true, false}) {
+            const std::size_t sh = shared_doubles(ris) * sizeof(double);
             const std::size_t tb = coop_warp_bytes(team_slots(tmem), LT);
             if (sh + tb + reserve > smem_per_block_max) {
                 continue;
             }
-            std::uint32_t w = cta ? 16u : static_cast<std::uint32_t>(std::min<std::size_t>((smem_per_block_max - reserve - sh) / tb, 16u));
+            std::uint32_t w = cta ? 16u
+                                  : static_cast<std::uint32_t>(
+                                        std::min<std::size_t>((smem_per_block_max - reserve - sh) / tb, 16u));
             if (tmem) {
                 const std::uint32_t cols = npp * 12u;
                 const std::uint32_t per_quadrant = cols == 0u || cols > 512u ? 0u : 512u / cols;
@@ -722,7 +728,7 @@ bool hy_batch::setup_nb(int LT, std::uint32_t threads, int want_tmem, int want_c
             }
             if (w > c.warps) {
                 c.warps = w;
-                c.sums_in_smem = sis;
+                c.roles_in_smem = ris;
             }
             if (w != 0u) {
                 break;
@@ -745,6 +751,9 @@ bool hy_batch::setup_nb(int LT, std::uint32_t threads, int want_tmem, int want_c
     }
     if (threads == 0u) {
         threads = 32u * pick.warps;
+        if (!cta && opt_nb_threads != 0u && opt_nb_threads <= threads) {
+            threads = opt_nb_threads;
+        }
     }
     if (threads % 32u != 0u || threads == 0u || threads / 32u > pick.warps || (cta && threads != 512u)) {
         throw std::invalid_argument("Invalid number of threads for the N-body kernel");
@@ -762,33 +771,31 @@ bool hy_batch::setup_nb(int LT, std::uint32_t threads, int want_tmem, int want_c
     // Device copies of the tables.
     if (d_nb_pairs == nullptr) {
         d_nb_pairs = dupload(nbp.pairs);
-        std::vector<std::uint32_t> words(static_cast<std::size_t>(n_sums) * 16u);
-        static_assert(sizeof(hy::detail::nb_sum_desc) == 64u);
-        std::memcpy(words.data(), nbp.sums.data(), words.size() * 4u);
-        d_nb_sums = dupload(words);
         d_nb_consts = dupload(nbp.consts);
         d_nb_fac = dupload(nbp.fac);
     }
+    if (d_nb_roles != nullptr) {
+        HY_CUDA_CHECK(cudaFree(d_nb_roles));
+        d_nb_roles = nullptr;
+    }
+    d_nb_roles = dupload(roles.table);
     nbd = dev::nb_dev_plan{};
     nbd.pairs = d_nb_pairs;
-    nbd.sums = d_nb_sums;
+    nbd.roles = reinterpret_cast<const uint4 *>(d_nb_roles);
     nbd.consts = d_nb_consts;
     nbd.fac = d_nb_fac;
     nbd.n_pairs = n_pairs;
     nbd.n_pos = nbp.n_pos;
     nbd.n_out = nbp.n_out;
-    nbd.n_levels = n_levels;
-    nbd.n_sums = n_sums;
     nbd.n_consts = static_cast<std::uint32_t>(nbp.consts.size());
     nbd.npp = npp;
     nbd.fac_stride = nbp.fac_stride;
-    for (std::uint32_t i = 0; i <= n_levels; ++i) {
-        nbd.level_offsets[i] = nbp.level_offsets[i];
-    }
+    nbd.n_rounds = roles.n_rounds;
+    nbd.round_level_end = roles.round_level_end;
     nbd.alpha = nbp.alpha;
     nbd.pow_algo = nbp.pow_algo;
-    nbd.sums_in_smem = pick.sums_in_smem ? 1u : 0u;
-    nbd.shared_doubles = static_cast<std::uint32_t>(shared_doubles(pick.sums_in_smem));
+    nbd.roles_in_smem = pick.roles_in_smem ? 1u : 0u;
+    nbd.shared_doubles = static_cast<std::uint32_t>(shared_doubles(pick.roles_in_smem));
     nbd.n_slots_equiv = team_slots(pick.tmem);
     const std::size_t team_bytes = coop_warp_bytes(nbd.n_slots_equiv, LT);
     nbd.team_doubles = static_cast<std::uint32_t>(team_bytes / sizeof(double));
@@ -1090,6 +1097,9 @@ int hy_batch_create(const hy_program *p, uint32_t batch, int device, hy_batch **
         if (const char *env = std::getenv("HEYOKA_B200_NB")) {
             b->opt_nb = std::string{env} != "0" ? 1 : 0;
         }
+        if (const char *env = std::getenv("HEYOKA_B200_NB_THREADS")) {
+            b->opt_nb_threads = static_cast<std::uint32_t>(std::atoi(env));
+        }
         b->prog_host = std::make_shared<const hy_program>(*p);
         b->replan(false);
         b->nbp = hy::detail::make_nb_plan(*p);
@@ -1329,6 +1339,23 @@ int hy_batch_download_tc(hy_batch *b, double *tc)
         const std::size_t sz = static_cast<std::size_t>(b->n_eq) * (b->order + 1u) * b->n;
         b->ensure_tc();
         HY_CUDA_CHECK(cudaMemcpyAsync(tc, b->d_tc, sizeof(double) * sz, cudaMemcpyDeviceToHost, b->stream));
+        HY_CUDA_CHECK(cudaStreamSynchronize(b->stream));
+        return HY_OK;
+    } catch (...) {
+        return translate_exception();
+    }
+}
+
+int hy_batch_upload_tc(hy_batch *b, const double *tc)
+{
+    try {
+        if (b == nullptr || tc == nullptr) {
+            throw std::invalid_argument("Null pointer passed to hy_batch_upload_tc()");
+        }
+        device_guard guard(b->device);
+        b->ensure_tc();
+        const std::size_t sz = static_cast<std::size_t>(b->n_eq) * (b->order + 1u) * b->n;
+        HY_CUDA_CHECK(cudaMemcpyAsync(b->d_tc, tc, sizeof(double) * sz, cudaMemcpyHostToDevice, b->stream));
         HY_CUDA_CHECK(cudaStreamSynchronize(b->stream));
         return HY_OK;
     } catch (...) {

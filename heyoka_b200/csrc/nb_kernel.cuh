@@ -3,17 +3,22 @@
 //
 // Same persistent structure as k_coop (kernels.cuh): a team (a warp, or the whole CTA when one lane has hundreds of pair
 // interactions) owns LT lanes, claims chunks of LT lanes from an atomic counter and runs a chunk's whole
-// propagate_until() loop; the step-size estimate, the state update and the per-lane bookkeeping are the functions of
-// kernels.cuh. What differs is the jet:
+// propagate_until() loop; the state update and the per-lane bookkeeping are the functions of kernels.cuh. What
+// differs is the jet:
 //   * the orders are walked two at a time (nb_core.hpp), two synchronisations per PAIR of orders;
-//   * a thread is bound to one (pair interaction, lane) for the whole kernel: its operands' addresses and constants
-//     live in registers, nothing is decoded per order;
+//   * a thread is bound to one (pair interaction, lane) for the whole kernel: its operands' shared-memory addresses
+//     and constants live in registers, nothing is decoded per order;
 //   * its private history rows are stored as (even order, odd order) pairs: d_0, d_1 in shared memory, interleaved by
 //     thread ([order pair][row][thread], one 16-byte access per thread, conflict-free), r^2, d_2 and r^alpha in tensor
 //     memory (12 columns per order pair: one tcgen05.ld.x8 + one .x4 per loop iteration); or all five in shared
 //     memory (TMEM = false);
 //   * shared memory otherwise only holds what threads exchange: the positions of the current order pair and the
-//     outputs of the pair interactions / partial sums.
+//     outputs of the pair interactions / partial sums ([role][pair][lane] so that a warp writes consecutive slots);
+//   * what a thread does in the summation phase is a pre-decoded 32-byte record (nb_role) per round;
+//   * the three infinity norms of the step-size estimate are gathered while the coefficients are produced
+//     (shared-memory atomic max on the bit patterns of |x|): no second pass over the coefficients for h.
+// All shared-memory accesses use 32-bit shared-window addresses (ld.shared / st.shared): no generic addressing, no
+// 64-bit pointer arithmetic in the hot loops.
 // Replaces, for these programs: the JIT'd step function (src/taylor_00.cpp:712-865) and the propagate loop
 // (src/taylor_adaptive_batch.cpp:1136-1534), like k_coop.
 #ifndef HEYOKA_B200_CSRC_NB_KERNEL_CUH
@@ -34,16 +39,16 @@ namespace heyoka_b200::dev
 // Device-side view of an nb_plan (arrays in global memory) + the shared-memory layout chosen by the host.
 struct nb_dev_plan {
     const detail::nb_pair_desc *pairs;
-    const std::uint32_t *sums; // 16 words per item
+    const uint4 *roles; // n_rounds x TT records of 2 x uint4
     const double *consts, *fac;
-    std::uint32_t n_pairs, n_pos, n_out, n_levels, n_sums, n_consts, npp, fac_stride;
-    std::uint32_t level_offsets[8]; // n_levels + 1 offsets into sums
+    std::uint32_t n_pairs, n_pos, n_out, n_consts, npp, fac_stride;
+    std::uint32_t n_rounds, round_level_end; // rounds of the summation phase; bit r: round r ends a level
     double alpha;
     std::uint32_t pow_algo;
-    std::uint32_t sums_in_smem;   // 1: the sum descriptors are copied to shared memory
-    std::uint32_t shared_doubles; // CTA-shared tables: fac | rcp | consts | sums
-    std::uint32_t team_doubles;   // per team: positions | outputs | private rows | scalars
-    std::uint32_t n_slots_equiv;  // team region expressed in coop_smem<LT> slots
+    std::uint32_t roles_in_smem;  // 1: the role table is copied to shared memory
+    std::uint32_t shared_doubles; // CTA-shared tables: fac | rcp | consts | roles
+    std::uint32_t team_doubles;   // per team: positions | outputs | private rows | norms | scalars
+    std::uint32_t n_slots_equiv;  // team region (without the scalars) expressed in coop_smem<LT> slots
 };
 
 namespace nbk
@@ -51,14 +56,35 @@ namespace nbk
 
 using nb::d2;
 
-__device__ __forceinline__ d2 lds2(const char *p)
+__device__ __forceinline__ std::uint32_t saddr(const void *p)
 {
-    const double2 v = *reinterpret_cast<const double2 *>(p);
-    return d2{v.x, v.y};
+    return static_cast<std::uint32_t>(__cvta_generic_to_shared(p));
 }
-__device__ __forceinline__ void sts2(char *p, const d2 &v)
+__device__ __forceinline__ d2 lds2(std::uint32_t a)
 {
-    *reinterpret_cast<double2 *>(p) = make_double2(v.x, v.y);
+    d2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ double lds1(std::uint32_t a)
+{
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint4 lds4u(std::uint32_t a)
+{
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts2(std::uint32_t a, const d2 &v)
+{
+    asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a), "d"(v.x), "d"(v.y) : "memory");
+}
+__device__ __forceinline__ void red_max_u64(std::uint32_t a, unsigned long long v)
+{
+    asm volatile("red.shared.max.u64 [%0], %1;" ::"r"(a), "l"(v) : "memory");
 }
 __device__ __forceinline__ d2 from_words(std::uint32_t a, std::uint32_t b, std::uint32_t c, std::uint32_t d)
 {
@@ -75,8 +101,8 @@ __device__ __forceinline__ tm::words<4> to_words(const d2 &v)
     return w;
 }
 
-// Storage policy of pair_block() (nb_core.hpp). TT = threads per team.
-// Shared-memory private rows: element (order pair op, row r) of this thread at drow + (op * NSR + r) * TT * 16 bytes,
+// Storage policy of pair_block() (nb_core.hpp). TT = threads per team. All members are shared-window addresses.
+// Private rows in shared memory: element (order pair op, row r) of this thread at drow + (op * NSR + r) * TT * 16,
 // rows d_0, d_1 (+ d_2, r^2, r^alpha when TMEM is false). Tensor memory: columns [op * 12, op * 12 + 12) of the
 // thread's TMEM lane = r^2 pair, d_2 pair, r^alpha pair.
 template <int TT, bool TMEM>
@@ -84,26 +110,24 @@ struct pair_mem {
     static constexpr int NSR = TMEM ? 2 : 5;
     static constexpr std::uint32_t OPB = static_cast<std::uint32_t>(NSR) * TT * 16u; // bytes per order pair
     static constexpr std::uint32_t RB = TT * 16u;                                    // bytes per row
-    const char *pos; // team positions + this thread's lane
-    char *outp;      // team outputs + this thread's lane
-    char *drow;      // this thread's slice of the private rows
-    const double *fac_;
-    std::uint32_t fac_stride;
-    std::uint32_t pa[3], pb[3], om[3]; // byte offsets
-    std::uint32_t tmc;                 // TMEM address of this thread's column 0
-    bool active;
+    std::uint32_t pa[3], pb[3]; // the six positions this pair reads (this thread's lane)
+    std::uint32_t om, kstride;  // output m_0 of this (pair, lane); m_k / n_k are k / (3 + k) strides further
+    std::uint32_t drow;         // this thread's slice of the private rows
+    std::uint32_t fac_, fac_stride_b;
+    std::uint32_t tmc; // TMEM address of this thread's column 0
+    std::uint32_t flags; // bit 0: active (owns a pair), bits 1-3: n_k exists
 
     __device__ __forceinline__ d2 pos_a(int k) const
     {
-        return lds2(pos + pa[k]);
+        return lds2(pa[k]);
     }
     __device__ __forceinline__ d2 pos_b(int k) const
     {
-        return lds2(pos + pb[k]);
+        return lds2(pb[k]);
     }
     __device__ __forceinline__ void st_d(std::uint32_t m, const d2 (&D)[3]) const
     {
-        char *p = drow + m * OPB;
+        const std::uint32_t p = drow + m * OPB;
         sts2(p, D[0]);
         sts2(p + RB, D[1]);
         if constexpr (TMEM) {
@@ -130,7 +154,7 @@ struct pair_mem {
     }
     __device__ __forceinline__ void ld_ss(std::uint32_t ai, std::uint32_t li, d2 (&A)[3], d2 (&Lo)[3]) const
     {
-        const char *pa_ = drow + ai * OPB, *pl = drow + li * OPB;
+        const std::uint32_t pa_ = drow + ai * OPB, pl = drow + li * OPB;
         if constexpr (TMEM) {
             tm::words<4> wa, wl;
             tm::ld(tmc + ai * 12u + 4u, wa);
@@ -153,7 +177,7 @@ struct pair_mem {
     }
     __device__ __forceinline__ void ld_a(std::uint32_t ai, d2 (&A)[3]) const
     {
-        const char *pa_ = drow + ai * OPB;
+        const std::uint32_t pa_ = drow + ai * OPB;
         if constexpr (TMEM) {
             tm::words<4> wa;
             tm::ld(tmc + ai * 12u + 4u, wa);
@@ -170,7 +194,7 @@ struct pair_mem {
     }
     __device__ __forceinline__ void ld_main(std::uint32_t qi, std::uint32_t li, d2 &Q, d2 &Rlo, d2 (&Dlo)[3]) const
     {
-        const char *pl = drow + li * OPB;
+        const std::uint32_t pl = drow + li * OPB;
         if constexpr (TMEM) {
             tm::words<8> wl;
             tm::words<4> wq;
@@ -194,66 +218,159 @@ struct pair_mem {
     }
     __device__ __forceinline__ d2 fac(std::uint32_t n, std::uint32_t j) const
     {
-        const double2 v = *reinterpret_cast<const double2 *>(fac_ + n * fac_stride + j);
-        return d2{v.x, v.y};
+        return lds2(fac_ + n * fac_stride_b + j * 8u);
     }
     __device__ __forceinline__ double fac1(std::uint32_t n, std::uint32_t j) const
     {
-        return fac_[n * fac_stride + j];
+        return lds1(fac_ + n * fac_stride_b + j * 8u);
     }
     __device__ __forceinline__ void out(int k, const d2 &v) const
     {
-        if (active) {
-            sts2(outp + om[k], v);
+        if ((flags & 1u) != 0u) {
+            sts2(om + static_cast<std::uint32_t>(k) * kstride, v);
+        }
+    }
+    __device__ __forceinline__ void out_n(int k, const d2 &v) const
+    {
+        if ((flags & (2u << k)) != 0u) {
+            sts2(om + static_cast<std::uint32_t>(3 + k) * kstride, v);
         }
     }
 };
 
-// Storage policy of sum_block() / sum_init(): NL lanes starting at lane l0 of the team's LT lanes.
-template <int LT, int NL>
-struct sum_mem {
-    char *pos, *out; // team bases
-    const double *consts, *rcp_;
-    const batch *D;
-    coef_view cv;
-    std::uint32_t l0;
-    std::uint32_t glane[NL];
-    std::size_t loff[NL];
+// Storage policy of role_block() / role_init(): the thread's NL lanes start at lane l0 of the team's LT lanes (the
+// records' units already include l0).
+template <int NL>
+struct role_mem {
+    std::uint32_t pos_b, out_b;   // team bases
+    std::uint32_t consts, rcp_;   // CTA tables
+    std::uint32_t norms;          // team norms: [3][LT] u64 (|x^[0]|, |x^[p]|, |x^[p-1]|), + lane l0 of this thread
+    std::uint32_t lt8;            // LT * 8: stride between the three norms
+    const double *state0;         // D.state + first global lane of this thread (clamped)
+    std::size_t n_batch;
+    double *cbase;                // coefficient store + lane offset of lane 0 of this thread
+    std::size_t stride_sv, stride_o;
+    std::uint32_t p;
+    bool pub, track;
     bool lane_ok[NL];
+    std::uint32_t ldelta; // offset (in doubles) between the thread's lanes in state / public store (0 if clamped)
 
-    __device__ __forceinline__ d2 out_ld(std::uint32_t slot, int l) const
+    __device__ __forceinline__ d2 out_u(std::uint32_t unit, int l) const
     {
-        return lds2(out + (slot * LT + l0 + l) * 16u);
+        return lds2(out_b + (unit + l) * 16u);
     }
-    __device__ __forceinline__ void out_st(std::uint32_t slot, int l, const d2 &v) const
+    __device__ __forceinline__ void out_st_u(std::uint32_t unit, int l, const d2 &v) const
     {
-        sts2(out + (slot * LT + l0 + l) * 16u, v);
+        sts2(out_b + (unit + l) * 16u, v);
     }
-    __device__ __forceinline__ void pos_st(std::uint32_t slot, int l, const d2 &v) const
+    __device__ __forceinline__ void pos_st_u(std::uint32_t unit, int l, const d2 &v) const
     {
-        sts2(pos + (slot * LT + l0 + l) * 16u, v);
+        sts2(pos_b + (unit + l) * 16u, v);
     }
     __device__ __forceinline__ double cst(std::uint32_t i) const
     {
-        return consts[i];
+        return lds1(consts + i * 8u);
     }
     __device__ __forceinline__ double rcp(std::uint32_t n) const
     {
-        return rcp_[n];
+        return lds1(rcp_ + n * 8u);
     }
-    __device__ __forceinline__ void coef(std::uint32_t sv, std::uint32_t order, int l, double v) const
+    // Norms of the step-size estimate: NaN-skipping maximum of |v| (bit patterns of non-negative doubles order like
+    // unsigned integers). which: 0 = order 0, 1 = order p, 2 = order p - 1.
+    __device__ __forceinline__ void norm(std::uint32_t which, int l, double v) const
     {
-        if (lane_ok[l]) {
-            cv.base[sv * cv.stride_sv + order * cv.stride_o + loff[l]] = v;
+        if (v == v) {
+            red_max_u64(norms + which * lt8 + l * 8u,
+                        static_cast<unsigned long long>(__double_as_longlong(v)) & 0x7fffffffffffffffull);
+        }
+    }
+    __device__ __forceinline__ void track_order(std::uint32_t order, const double (&a)[NL]) const
+    {
+        if (order == 0u || order == p || order + 1u == p) {
+            const std::uint32_t which = order == 0u ? 0u : (order == p ? 1u : 2u);
+#pragma unroll
+            for (int l = 0; l < NL; ++l) {
+                norm(which, l, a[l]);
+            }
+        }
+    }
+    // One order of state variable sv for the thread's lanes at element index idx of the coefficient store.
+    template <typename I>
+    __device__ __forceinline__ void store_lanes(I idx, const double (&a)[NL]) const
+    {
+        if constexpr (NL == 2) {
+            if (!pub) {
+                // Private store: the two lanes are adjacent and 16-byte aligned.
+                *reinterpret_cast<double2 *>(cbase + idx) = make_double2(a[0], a[1]);
+                return;
+            }
+        }
+#pragma unroll
+        for (int l = 0; l < NL; ++l) {
+            if (lane_ok[l]) {
+                cbase[idx + (pub ? l * ldelta : l)] = a[l];
+            }
+        }
+    }
+    __device__ __forceinline__ void coef_pair(std::uint32_t sv, std::uint32_t order, const double (&a)[NL],
+                                              const double (&b)[NL]) const
+    {
+        if (pub) {
+            const std::size_t idx = sv * stride_sv + order * stride_o;
+            if (order <= p) {
+                store_lanes(idx, a);
+            }
+            if (order + 1u <= p) {
+                store_lanes(idx + stride_o, b);
+            }
+        } else {
+            // (The private store has fewer than 2^32 elements.)
+            const std::uint32_t so = static_cast<std::uint32_t>(stride_o);
+            const std::uint32_t idx = sv * static_cast<std::uint32_t>(stride_sv) + order * so;
+            if (order <= p) {
+                store_lanes(idx, a);
+            }
+            if (order + 1u <= p) {
+                store_lanes(idx + so, b);
+            }
+        }
+        if (track) {
+            track_order(order, a);
+            track_order(order + 1u, b);
+        }
+    }
+    __device__ __forceinline__ void coef_one(std::uint32_t sv, std::uint32_t order, const double (&a)[NL]) const
+    {
+        store_lanes(sv * stride_sv + order * stride_o, a);
+        if (track) {
+            track_order(order, a);
         }
     }
     __device__ __forceinline__ double state(std::uint32_t sv, int l) const
     {
-        return D->state[static_cast<std::size_t>(sv) * D->n + glane[l]];
+        return state0[static_cast<std::size_t>(sv) * n_batch + l * ldelta];
     }
 };
 
 } // namespace nbk
+
+// Step size of one lane from the norms gathered during the jet (norms[0], norms[lt], norms[2 lt]: bit patterns of the
+// NaN-skipping maxima of |x^[0]|, |x^[p]|, |x^[p-1]|; reset to 0 here) and the coefficients of the first state
+// variable: the sequential reference loop m = (m < |x|) ? |x| : m, started from |x_0|, yields NaN iff x_0 is NaN and
+// ignores every other NaN (src/taylor_00.cpp:102-273). Once per lane and step: out of line.
+static __device__ __noinline__ double nb_step_size(const program &P, unsigned long long *norms, std::uint32_t lt,
+                                                   const double *c, std::size_t off_p, std::size_t off_pm1,
+                                                   double max_delta_t)
+{
+    const double m0 = __longlong_as_double(static_cast<long long>(norms[0]));
+    const double mp = __longlong_as_double(static_cast<long long>(norms[lt]));
+    const double mp1 = __longlong_as_double(static_cast<long long>(norms[2u * lt]));
+    norms[0] = 0ull;
+    norms[lt] = 0ull;
+    norms[2u * lt] = 0ull;
+    const double f0 = fabs(c[0]), fp = fabs(c[off_p]), fp1 = fabs(c[off_pm1]);
+    return h_from_norms(P, isnan(f0) ? f0 : m0, isnan(fp) ? fp : mp, isnan(fp1) ? fp1 : mp1, max_delta_t);
+}
 
 // LT: lanes per team; CTA: a team is the whole CTA (else a warp); TMEM: r^2, d_2, r^alpha rows in tensor memory.
 template <int LT, bool CTA, bool TMEM, bool PROP, int MAXT>
@@ -261,11 +378,11 @@ __global__ void __launch_bounds__(MAXT, 1) k_nb(program P, nb_dev_plan NP, batch
 {
     using T = team<CTA>;
     constexpr int TT = CTA ? MAXT : 32; // threads per team (CTA teams are launched with exactly MAXT threads)
-    constexpr int NL = LT >= 2 ? 2 : 1; // lanes per thread in the summation levels
+    constexpr int NL = LT >= 2 ? 2 : 1; // lanes per thread in the summation phase
     constexpr std::uint32_t GS = LT / NL;
     extern __shared__ __align__(16) double smem_raw[];
 
-    // ---- CTA-shared tables: fac | rcp | consts | sums ----
+    // ---- CTA-shared tables: fac | rcp | consts | roles ----
     const std::uint32_t p = P.order;
     double *fac_s = smem_raw;
     const std::uint32_t n_fac = (p + 1u) * NP.fac_stride;
@@ -273,7 +390,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_nb(program P, nb_dev_plan NP, batch
     const std::uint32_t n_rcp = (p + 5u) & ~1u;
     double *consts_s = rcp_s + n_rcp;
     const std::uint32_t n_cst = (NP.n_consts + 1u) & ~1u;
-    std::uint32_t *sums_s = reinterpret_cast<std::uint32_t *>(consts_s + n_cst);
+    uint4 *roles_s = reinterpret_cast<uint4 *>(consts_s + n_cst);
     for (std::uint32_t i = threadIdx.x; i < n_fac; i += blockDim.x) {
         fac_s[i] = __ldg(NP.fac + i);
     }
@@ -283,12 +400,10 @@ __global__ void __launch_bounds__(MAXT, 1) k_nb(program P, nb_dev_plan NP, batch
     for (std::uint32_t i = threadIdx.x; i < NP.n_consts; i += blockDim.x) {
         consts_s[i] = __ldg(NP.consts + i);
     }
-    const std::uint32_t *sums = NP.sums;
-    if (NP.sums_in_smem != 0u) {
-        for (std::uint32_t i = threadIdx.x; i < NP.n_sums * 16u; i += blockDim.x) {
-            sums_s[i] = __ldg(NP.sums + i);
+    if (NP.roles_in_smem != 0u) {
+        for (std::uint32_t i = threadIdx.x; i < NP.n_rounds * TT * 2u; i += blockDim.x) {
+            roles_s[i] = __ldg(NP.roles + i);
         }
-        sums = sums_s;
     }
     __shared__ std::uint32_t tm_base_smem;
     if constexpr (TMEM) {
@@ -299,41 +414,55 @@ __global__ void __launch_bounds__(MAXT, 1) k_nb(program P, nb_dev_plan NP, batch
     }
     __syncthreads();
 
-    const std::uint32_t tid = T::tid(), nthr = T::size();
-    const std::size_t team_global = T::index();
+    const std::uint32_t tid = T::tid();
     double *region = smem_raw + NP.shared_doubles
                      + (CTA ? 0u : static_cast<std::size_t>(threadIdx.x >> 5) * NP.team_doubles);
     const coop_smem<LT> S(region, NP.n_slots_equiv);
-    char *pos_b = reinterpret_cast<char *>(region);
-    char *out_b = pos_b + static_cast<std::size_t>(NP.n_pos) * LT * 16u;
-    char *drow_b = out_b + static_cast<std::size_t>(NP.n_out) * LT * 16u;
+    const std::uint32_t pos_b = nbk::saddr(region);
+    const std::uint32_t out_b = pos_b + NP.n_pos * LT * 16u;
+    const std::uint32_t drow_b = out_b + NP.n_out * LT * 16u;
+    const std::uint32_t norms_b = drow_b + NP.npp * nbk::pair_mem<TT, TMEM>::OPB;
+    unsigned long long *norms_p
+        = reinterpret_cast<unsigned long long *>(region + (static_cast<std::size_t>(NP.n_pos) + NP.n_out) * LT * 2u
+                                                 + static_cast<std::size_t>(NP.npp) * nbk::pair_mem<TT, TMEM>::OPB / 8u);
 
     // ---- this thread's pair interaction ----
     nbk::pair_mem<TT, TMEM> PM;
     nb::pair_consts PC;
     {
         const std::uint32_t n_pt = NP.n_pairs * LT;
-        PM.active = tid < n_pt;
+        const bool active = tid < n_pt;
         // Idle threads shadow pair 0 / lane 0 on their own private rows (the tensor-memory accesses are warp-wide).
-        const std::uint32_t pi = PM.active ? tid / LT : 0u, l = PM.active ? tid % LT : 0u;
+        const std::uint32_t pi = active ? tid / LT : 0u, l = active ? tid % LT : 0u;
         const uint4 *dp = reinterpret_cast<const uint4 *>(NP.pairs + pi);
-        const uint4 w0 = __ldg(dp), w1 = __ldg(dp + 1);
+        const uint4 w0 = __ldg(dp), w1 = __ldg(dp + 1), w2 = __ldg(dp + 2), w3 = __ldg(dp + 3);
+        // u16 fields: pa[3] pb[3] om[3] on[3] = words w0.x .. w1.y; flags = w1.z; c1 = w2.xy; c2[3] = w2.zw, w3.xy, w3.zw
         const std::uint32_t h[6] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y};
         const auto u16 = [&](int i) { return (h[i >> 1] >> ((i & 1) * 16)) & 0xffffu; };
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
-            PM.pa[k] = u16(k) * LT * 16u;
-            PM.pb[k] = u16(3 + k) * LT * 16u;
-            PM.om[k] = u16(6 + k) * LT * 16u;
+            PM.pa[k] = pos_b + (u16(k) * LT + l) * 16u;
+            PM.pb[k] = pos_b + (u16(3 + k) * LT + l) * 16u;
         }
-        PC.c1 = __hiloint2double(static_cast<int>(w1.w), static_cast<int>(w1.z));
+        PM.om = out_b + (u16(6) * LT + l) * 16u; // om[k] = k * n_pairs + pair, on[k] = (3 + k) * n_pairs + pair
+        PM.kstride = NP.n_pairs * LT * 16u;
+        PM.flags = (active ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            if (active && u16(9 + k) != 0xffffu) {
+                PM.flags |= 2u << k;
+            }
+        }
+        PC.c1 = __hiloint2double(static_cast<int>(w2.y), static_cast<int>(w2.x));
+        PC.c2[0] = __hiloint2double(static_cast<int>(w2.w), static_cast<int>(w2.z));
+        PC.c2[1] = __hiloint2double(static_cast<int>(w3.y), static_cast<int>(w3.x));
+        PC.c2[2] = __hiloint2double(static_cast<int>(w3.w), static_cast<int>(w3.z));
         PC.alpha = NP.alpha;
         PC.pow_algo = NP.pow_algo;
-        PM.pos = pos_b + l * 16u;
-        PM.outp = out_b + l * 16u;
+        PC.have_n = (w1.z & 1u) != 0u;
         PM.drow = drow_b + tid * 16u;
-        PM.fac_ = fac_s;
-        PM.fac_stride = NP.fac_stride;
+        PM.fac_ = nbk::saddr(fac_s);
+        PM.fac_stride_b = NP.fac_stride * 8u;
         PM.tmc = 0u;
         if constexpr (TMEM) {
             tm::fence_after_sync();
@@ -342,71 +471,114 @@ __global__ void __launch_bounds__(MAXT, 1) k_nb(program P, nb_dev_plan NP, batch
             PM.tmc = tm_base_smem + (((w & 3u) * 32u) << 16) + (w >> 2) * (NP.npp * 12u);
         }
     }
-    // ---- this thread's lanes in the summation levels ----
-    nbk::sum_mem<LT, NL> SM;
-    SM.pos = pos_b;
-    SM.out = out_b;
-    SM.consts = consts_s;
-    SM.rcp_ = rcp_s;
-    SM.D = &D;
-    SM.l0 = (tid % GS) * NL;
+    // ---- this thread's lanes in the summation phase ----
+    const std::uint32_t l0 = (tid % GS) * NL;
+    nbk::role_mem<NL> RM;
+    RM.pos_b = pos_b;
+    RM.out_b = out_b;
+    RM.consts = nbk::saddr(consts_s);
+    RM.rcp_ = nbk::saddr(rcp_s);
+    RM.norms = norms_b + l0 * 8u;
+    RM.lt8 = LT * 8u;
+    RM.n_batch = D.n;
+    RM.p = p;
+    const std::size_t team_global = T::index();
+    const coef_view cv{R.coef_base + team_global * R.coef_warp_stride, static_cast<std::size_t>(R.coef_stride_sv),
+                       static_cast<std::size_t>(R.coef_stride_o), R.coef_pub != 0};
+    RM.stride_sv = cv.stride_sv;
+    RM.stride_o = cv.stride_o;
+    RM.pub = cv.pub;
+    const std::uint32_t roles_sa = nbk::saddr(roles_s) + tid * 32u;
+    const uint4 *roles_g = NP.roles + tid * 2u;
 
     const std::uint32_t n_chunks = (D.n + LT - 1u) / LT;
     const bool owner = tid < LT;
-    const coef_view cv{R.coef_base + team_global * R.coef_warp_stride, static_cast<std::size_t>(R.coef_stride_sv),
-                       static_cast<std::size_t>(R.coef_stride_o), R.coef_pub != 0};
-    SM.cv = cv;
-    const std::uint32_t n_blocks = (p + 1u) / 2u;
+    const std::uint32_t n_blocks = NP.npp;
+
+    const auto load_role = [&](std::uint32_t rd, std::uint32_t (&w)[8]) {
+        uint4 a, b;
+        if (NP.roles_in_smem != 0u) {
+            a = nbk::lds4u(roles_sa + rd * (TT * 32u));
+            b = nbk::lds4u(roles_sa + rd * (TT * 32u) + 16u);
+        } else {
+            a = __ldg(roles_g + static_cast<std::size_t>(rd) * (TT * 2u));
+            b = __ldg(roles_g + static_cast<std::size_t>(rd) * (TT * 2u) + 1);
+        }
+        w[0] = a.x, w[1] = a.y, w[2] = a.z, w[3] = a.w, w[4] = b.x, w[5] = b.y, w[6] = b.z, w[7] = b.w;
+    };
 
     const auto jet = [&](std::uint32_t lane0) {
-#pragma unroll
-        for (int i = 0; i < NL; ++i) {
-            const std::uint32_t l = lane0 + SM.l0 + i;
-            SM.lane_ok[i] = l < D.n;
-            SM.glane[i] = SM.lane_ok[i] ? l : D.n - 1u;
-            SM.loff[i] = cv.lane_off(SM.glane[i], SM.l0 + i);
+        // The thread's lanes: global indices (clamped), offsets into the coefficient store.
+        {
+            const std::uint32_t la = lane0 + l0, lb = la + (NL - 1);
+            const std::uint32_t ga = la < D.n ? la : D.n - 1u, gb = lb < D.n ? lb : D.n - 1u;
+            RM.lane_ok[0] = la < D.n;
+            if constexpr (NL == 2) {
+                RM.lane_ok[1] = lb < D.n;
+            }
+            RM.ldelta = gb - ga;
+            RM.state0 = D.state + ga;
+            RM.cbase = cv.base + cv.lane_off(ga, l0);
         }
-        for (std::uint32_t it = tid; it < NP.n_sums * GS; it += nthr) {
-            nb::sum_init<NL>(SM, sums + (it / GS) * 16u);
+        RM.track = true;
+        for (std::uint32_t rd = 0; rd < NP.n_rounds; ++rd) {
+            std::uint32_t w[8];
+            load_role(rd, w);
+            nb::role_init<NL>(RM, w);
         }
         T::sync();
         for (std::uint32_t m = 0; m < n_blocks; ++m) {
-            if (TMEM || PM.active) {
+            if (TMEM || (PM.flags & 1u) != 0u) {
                 nb::pair_block(PM, PC, m);
             }
             if constexpr (TMEM) {
                 tm::wait_st();
             }
             T::sync();
-            for (std::uint32_t lv = 0; lv < NP.n_levels; ++lv) {
-                const std::uint32_t b = NP.level_offsets[lv], e = NP.level_offsets[lv + 1u];
-                for (std::uint32_t it = tid; it < (e - b) * GS; it += nthr) {
-                    nb::sum_block<NL>(SM, sums + (b + it / GS) * 16u, m, p);
+            RM.track = m + 2u >= n_blocks;
+            for (std::uint32_t rd = 0; rd < NP.n_rounds; ++rd) {
+                std::uint32_t w[8];
+                load_role(rd, w);
+                nb::role_block<NL>(RM, w, m, p);
+                if (((NP.round_level_end >> rd) & 1u) != 0u) {
+                    T::sync();
                 }
-                T::sync();
             }
         }
     };
+
+    // Step size from the norms gathered during the jet (owner threads: one lane each); resets the norms.
+    const auto step_size = [&](std::uint32_t lane, double max_delta_t) {
+        const double *c = cv.base + cv.lane_off(lane, tid);
+        return nb_step_size(P, norms_p + tid, LT, c, p * cv.stride_o, (p - 1u) * cv.stride_o, max_delta_t);
+    };
+    if (owner) {
+        norms_p[tid] = 0ull;
+        norms_p[LT + tid] = 0ull;
+        norms_p[2 * LT + tid] = 0ull;
+    }
+    // The per-lane bookkeeping of propagate_until() is parked in shared memory while the jet runs (it would otherwise
+    // hold ~26 registers of every thread across the hot loops).
+    static_assert(sizeof(lane_prop) <= 128u && alignof(lane_prop) <= 8u);
+    lane_prop *const park = reinterpret_cast<lane_prop *>(norms_p + 3u * LT) + (owner ? tid : 0u);
 
     for (std::uint32_t chunk = T::claim(R.counter); chunk < n_chunks; chunk = T::claim(R.counter)) {
         const std::uint32_t lane0 = chunk * LT;
         const std::uint32_t lane_raw = lane0 + tid;
         const bool valid = owner && lane_raw < D.n;
-        const std::uint32_t lane = valid ? lane_raw : D.n - 1u;
+        const std::uint32_t lane = (owner && lane_raw < D.n) ? lane_raw : D.n - 1u;
 
         if constexpr (!PROP) {
-            double mdt = 0.;
-            dfl t0{0., 0.};
             if (owner) {
-                mdt = R.max_delta_t != nullptr ? R.max_delta_t[lane] : R.default_max_delta_t;
-                t0 = dfl{D.t_hi[lane], D.t_lo[lane]};
-                S.time[tid] = t0.hi;
+                S.time[tid] = D.t_hi[lane];
                 S.running[tid] = 1;
             }
             T::sync();
             jet(lane0);
-            const double h = (!CTA || threadIdx.x < 32u) ? coop_determine_h<LT>(P, D, cv, lane0, mdt) : 0.;
+            double h = 0., mdt = 0.;
             if (owner) {
+                mdt = R.max_delta_t != nullptr ? R.max_delta_t[lane] : R.default_max_delta_t;
+                h = step_size(lane, mdt);
                 S.h[tid] = h;
             }
             T::sync();
@@ -414,7 +586,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_nb(program P, nb_dev_plan NP, batch
             coop_update_state<LT, CTA>(P, D, S, cv, lane0, nf_mask);
             nf_mask = T::template reduce_or<LT>(nf_mask);
             if (valid) {
-                const dfl nt = dfl_add(t0, dfl{h, 0.});
+                const dfl nt = dfl_add(dfl{D.t_hi[lane], D.t_lo[lane]}, dfl{h, 0.});
                 D.t_hi[lane] = nt.hi;
                 D.t_lo[lane] = nt.lo;
                 D.last_h[lane] = h;
@@ -423,34 +595,39 @@ __global__ void __launch_bounds__(MAXT, 1) k_nb(program P, nb_dev_plan NP, batch
                     = nf ? HY_OUTCOME_ERR_NF_STATE : (h == mdt ? HY_OUTCOME_TIME_LIMIT : HY_OUTCOME_SUCCESS);
             }
         } else {
-            lane_prop lp;
-            lp.running = false;
+            bool running = false;
             if (owner) {
+                lane_prop lp;
                 lp.init(D, R, lane);
+                *park = lp;
+                running = lp.running;
             }
-            while (T::any(owner && lp.running)) {
-                double cur_max = 0.;
+            while (T::any(running)) {
                 if (owner) {
-                    cur_max = lp.cur_max();
-                    S.time[tid] = lp.t.hi;
-                    S.running[tid] = lp.running ? 1 : 0;
+                    S.time[tid] = park->t.hi;
+                    S.running[tid] = running ? 1 : 0;
                 }
                 T::sync();
                 jet(lane0);
-                const double h = (!CTA || threadIdx.x < 32u) ? coop_determine_h<LT>(P, D, cv, lane0, cur_max) : 0.;
+                double h = 0., cur_max = 0.;
                 if (owner) {
+                    cur_max = park->cur_max();
+                    h = step_size(lane, cur_max);
                     S.h[tid] = h;
                 }
                 T::sync();
                 unsigned nf_mask = 0u;
                 coop_update_state<LT, CTA>(P, D, S, cv, lane0, nf_mask);
                 nf_mask = T::template reduce_or<LT>(nf_mask);
-                if (owner && lp.running) {
+                if (running) {
+                    lane_prop lp = *park;
                     lp.advance(h, cur_max, ((nf_mask >> tid) & 1u) != 0u, R, valid);
+                    *park = lp;
+                    running = lp.running;
                 }
             }
             if (valid) {
-                lp.store(D, lane);
+                park->store(D, lane);
             }
         }
         T::sync();

@@ -100,9 +100,11 @@ nb_plan make_nb_plan(const hy_program &p)
 
         // ---- pair interactions ----
         std::vector<char> taken(n_ops, 0);
-        // term_of[u]: (output slot, multiplier const index + 1) for the u variables that may appear in sums / as
-        // right-hand sides.
-        std::vector<std::pair<std::uint32_t, std::uint32_t>> term_of(n_uvars, {~0u, 0u});
+        // term_of[u]: output slot of the u variables that may appear in sums / as right-hand sides. While the pair
+        // interactions are being collected the slots are provisional codes: (pair * 3 + k) for m_k, n_flag | the
+        // same for n_k, sum_flag | index for the intermediate sums; final numbers are assigned below.
+        constexpr std::uint32_t n_flag = 1u << 29, sum_flag = 1u << 30;
+        std::vector<std::uint32_t> term_of(n_uvars, ~0u);
         std::vector<std::uint32_t> pos_slot(n_eq, ~0u);
         const auto pos_of = [&](std::uint32_t s) {
             if (role[s] != 2) {
@@ -147,7 +149,7 @@ nb_plan make_nb_plan(const hy_program &p)
             pl.alpha = alpha;
             pl.pow_algo = qop.c;
             nb_pair_desc d{};
-            std::uint32_t du[3];
+            std::uint32_t du[3], mu[3] = {0u, 0u, 0u};
             for (std::uint32_t k = 0; k < 3u; ++k) {
                 du[k] = HY_REF_IDX(p.args[sop.a + k]);
                 if (du[k] < n_eq || op_of(du[k]).opcode != HY_OP_SUB_VV || op_of(du[k]).a >= n_eq
@@ -156,24 +158,21 @@ nb_plan make_nb_plan(const hy_program &p)
                 }
                 d.pa[k] = static_cast<std::uint16_t>(pos_of(op_of(du[k]).a));
                 d.pb[k] = static_cast<std::uint16_t>(pos_of(op_of(du[k]).b));
-                d.u_d[k] = du[k];
+                pl.pair_uvars.push_back(du[k]);
             }
             if (du[0] == du[1] || du[1] == du[2] || du[0] == du[2]) {
                 throw fail{"repeated coordinate difference"};
             }
             // f
             std::uint32_t fu = qu;
-            d.fkind = 0;
             d.c1 = 1.;
             if (users[qu].size() == 1u) {
                 const auto &fop = p.ops[users[qu][0]];
                 if (fop.opcode == HY_OP_MUL_NV && fop.b == qu) {
                     fu = n_eq + users[qu][0];
-                    d.fkind = 1;
                     d.c1 = p.consts[fop.a];
                 } else if (fop.opcode == HY_OP_NEG && fop.a == qu) {
                     fu = n_eq + users[qu][0];
-                    d.fkind = 2;
                     d.c1 = -1.;
                 }
             }
@@ -199,15 +198,15 @@ nb_plan make_nb_plan(const hy_program &p)
                 if (found == ~0u || users[du[k]].size() != 2u) {
                     throw fail{"coordinate difference without its product"};
                 }
-                d.u_m[k] = n_eq + found;
-                d.om[k] = static_cast<std::uint16_t>(n_out);
-                term_of[d.u_m[k]] = {n_out, 0u};
-                ++n_out;
+                mu[k] = n_eq + found;
+                d.on[k] = 0xffffu;
+                term_of[mu[k]] = static_cast<std::uint32_t>(pl.pairs.size()) * 3u + k;
                 taken[found] = 1;
                 taken[du[k] - n_eq] = 1;
             }
-            d.u_r2 = r2u;
-            d.u_q = qu;
+            pl.pair_uvars.push_back(r2u);
+            pl.pair_uvars.push_back(qu);
+            pl.pair_uvars.insert(pl.pair_uvars.end(), {mu[0], mu[1], mu[2]});
             taken[r2u - n_eq] = 1;
             taken[qi] = 1;
             if (fu != qu) {
@@ -218,7 +217,7 @@ nb_plan make_nb_plan(const hy_program &p)
         if (pl.pairs.empty()) {
             throw fail{"no pair interaction"};
         }
-        // ---- scaled outputs n = c * m / -m (read by sums or right-hand sides only) ----
+        // ---- scaled outputs n_k = c * m_k / -m_k (read by sums or right-hand sides only): computed by the pair's thread ----
         for (std::uint32_t i = 0; i < n_ops; ++i) {
             if (taken[i]) {
                 continue;
@@ -235,12 +234,45 @@ nb_plan make_nb_plan(const hy_program &p)
             } else {
                 continue;
             }
-            if (src < n_eq || term_of[src].first == ~0u || term_of[src].second != 0u) {
+            if (src < n_eq || term_of[src] == ~0u || term_of[src] >= n_flag) {
                 throw fail{"scaling of something else than a pair interaction's output"};
             }
-            term_of[n_eq + i] = {term_of[src].first, add_const(c) + 1u};
+            auto &d = pl.pairs[term_of[src] / 3u];
+            const auto k = term_of[src] % 3u;
+            if (d.on[k] != 0xffffu) {
+                throw fail{"a pair interaction's output is rescaled twice"};
+            }
+            d.on[k] = 0u; // (assigned below)
+            d.c2[k] = c;
+            d.flags |= 1u;
+            term_of[n_eq + i] = n_flag | term_of[src];
             taken[i] = 1;
         }
+        // Final output slots: [m_0 of every pair | m_1 | m_2 | n_0 | n_1 | n_2 | intermediate sums]: the threads of a warp
+        // (consecutive pairs) write consecutive 16-byte slots.
+        const std::uint32_t NPR = static_cast<std::uint32_t>(pl.pairs.size());
+        bool any_n = false;
+        for (std::uint32_t pi = 0; pi < NPR; ++pi) {
+            for (std::uint32_t k = 0; k < 3u; ++k) {
+                pl.pairs[pi].om[k] = static_cast<std::uint16_t>(k * NPR + pi);
+                if (pl.pairs[pi].on[k] != 0xffffu) {
+                    pl.pairs[pi].on[k] = static_cast<std::uint16_t>((3u + k) * NPR + pi);
+                    any_n = true;
+                }
+            }
+        }
+        n_out = (any_n ? 6u : 3u) * NPR;
+        if (n_out >= 0xffffu) {
+            throw fail{"too many pair interactions"};
+        }
+        const auto final_slot = [&](std::uint32_t code) {
+            if (code & sum_flag) {
+                return code & ~sum_flag;
+            }
+            const bool isn = (code & n_flag) != 0u;
+            const auto c = code & ~n_flag;
+            return ((isn ? 3u : 0u) + c % 3u) * NPR + c / 3u;
+        };
         // ---- sums ----
         std::vector<std::uint32_t> sum_level(n_uvars, 0u);
         std::vector<std::uint32_t> sum_ops;
@@ -255,10 +287,10 @@ nb_plan make_nb_plan(const hy_program &p)
             std::uint32_t lvl = 0;
             for (std::uint32_t k = 0; k < op.b; ++k) {
                 const auto u = HY_REF_IDX(p.args[op.a + k]);
-                if (u < n_eq || (term_of[u].first == ~0u && (op_of(u).opcode != HY_OP_SUM || taken[u - n_eq]))) {
+                if (u < n_eq || (term_of[u] == ~0u && (op_of(u).opcode != HY_OP_SUM || taken[u - n_eq]))) {
                     throw fail{"sum of something else than pair outputs / sums"};
                 }
-                if (term_of[u].first == ~0u) {
+                if (term_of[u] == ~0u || (term_of[u] & sum_flag)) {
                     lvl = std::max(lvl, sum_level[u] + 1u); // (ops are topologically sorted)
                 }
             }
@@ -275,7 +307,7 @@ nb_plan make_nb_plan(const hy_program &p)
                 if (users[u].empty()) {
                     throw fail{"unused sum"};
                 }
-                term_of[u] = {n_out++, 0u};
+                term_of[u] = sum_flag | n_out++;
             } else if (sv_of_u[u].size() != 1u || !users[u].empty()) {
                 throw fail{"a sum is the right-hand side of several state variables or is reused"};
             }
@@ -288,7 +320,7 @@ nb_plan make_nb_plan(const hy_program &p)
         }
         // Everything that is produced must be consumed by what the kernel computes.
         for (std::uint32_t u = n_eq; u < n_uvars; ++u) {
-            if (term_of[u].first != ~0u && op_of(u).opcode != HY_OP_SUM) {
+            if (term_of[u] != ~0u && op_of(u).opcode != HY_OP_SUM) {
                 for (const auto x : users[u]) {
                     const auto oc = p.ops[x].opcode;
                     if (oc != HY_OP_SUM && oc != HY_OP_MUL_NV && oc != HY_OP_NEG) {
@@ -297,7 +329,7 @@ nb_plan make_nb_plan(const hy_program &p)
                 }
             }
         }
-        if (n_out >= 0xffffu || pl.pos_sv.size() >= 0xffffu || pl.consts.size() >= 0xfffeu || n_eq >= 0xffffu) {
+        if (n_out >= 0xffffu || pl.pos_sv.size() >= 0xffffu || n_eq >= 0xffffu) {
             throw fail{"too large"};
         }
         // ---- emit the levels ----
@@ -313,12 +345,11 @@ nb_plan make_nb_plan(const hy_program &p)
             nb_sum_desc sd{};
             sd.n_terms = op.b;
             for (std::uint32_t k = 0; k < op.b; ++k) {
-                const auto t = term_of[HY_REF_IDX(p.args[op.a + k])];
-                sd.terms[k] = t.first | (t.second << 16);
+                sd.terms[k] = final_slot(term_of[HY_REF_IDX(p.args[op.a + k])]);
             }
             if (sv_of_u[u].empty()) {
                 sd.kind = 0;
-                sd.out = term_of[u].first;
+                sd.out = final_slot(term_of[u]);
             } else {
                 sd.kind = 1;
                 final_fields(sd, sv_of_u[u][0]);
@@ -341,12 +372,12 @@ nb_plan make_nb_plan(const hy_program &p)
                 if (op_of(u).opcode == HY_OP_SUM) {
                     continue; // emitted above
                 }
-                if (term_of[u].first == ~0u) {
+                if (term_of[u] == ~0u) {
                     throw fail{"right-hand side that is neither a sum nor a pair output"};
                 }
                 sd.kind = 1;
                 sd.n_terms = 1;
-                sd.terms[0] = term_of[u].first | (term_of[u].second << 16);
+                sd.terms[0] = final_slot(term_of[u]);
             }
             final_fields(sd, s);
             levels[0].push_back(sd);
@@ -378,6 +409,46 @@ nb_plan make_nb_plan(const hy_program &p)
         pl.why = f.why;
     }
     return pl;
+}
+
+nb_roles make_nb_roles(const nb_plan &pl, std::uint32_t tt, std::uint32_t lt, std::uint32_t nl)
+{
+    nb_roles r;
+    const std::uint32_t gs = lt / nl; // lane groups per team
+    for (std::size_t lv = 0; lv + 1u < pl.level_offsets.size(); ++lv) {
+        const std::uint32_t b = pl.level_offsets[lv], e = pl.level_offsets[lv + 1u];
+        const std::uint32_t n_items = (e - b) * gs;
+        const std::uint32_t rounds = std::max(1u, (n_items + tt - 1u) / tt);
+        for (std::uint32_t rd = 0; rd < rounds; ++rd) {
+            for (std::uint32_t t = 0; t < tt; ++t) {
+                nb_role ro{};
+                const std::uint32_t it = rd * tt + t;
+                if (it < n_items) {
+                    // (tt is a multiple of gs: thread t always works on the lanes (t % gs) * nl ...)
+                    const auto &sd = pl.sums[b + it / gs];
+                    const std::uint32_t l0 = (it % gs) * nl;
+                    const auto unit = [&](std::uint32_t slot) { return slot * lt + l0; };
+                    const std::uint32_t sv1 = sd.out & 0xffffu, sv2p1 = sd.out >> 16;
+                    ro.head = sd.n_terms | ((sd.kind + 1u) << 4) | (sd.kind != 0u && sv2p1 != 0u ? 1u << 6 : 0u)
+                              | (sd.kind != 0u && sd.pos != 0u ? 1u << 7 : 0u);
+                    for (std::uint32_t k = 0; k < sd.n_terms; ++k) {
+                        ro.t[k] = static_cast<std::uint16_t>(unit(sd.terms[k]));
+                    }
+                    if (sd.kind == 0u) {
+                        ro.dst = unit(sd.out);
+                    } else {
+                        ro.dst = sd.pos != 0u ? unit(sd.pos - 1u) : 0xffffu;
+                        ro.sv = sv1 | ((sv2p1 != 0u ? sv2p1 - 1u : 0xffffu) << 16);
+                        ro.cidx = sd.cidx;
+                    }
+                }
+                r.table.push_back(ro);
+            }
+            ++r.n_rounds;
+        }
+        r.round_level_end |= 1u << (r.n_rounds - 1u);
+    }
+    return r;
 }
 
 } // namespace heyoka_b200::detail

@@ -37,6 +37,7 @@ struct nb_plan {
     std::vector<std::uint32_t> level_offsets; // n_levels + 1 offsets into sums
     std::vector<double> consts;              // multipliers and constant right-hand sides
     std::vector<std::uint32_t> pos_sv;       // state variable held by each position slot
+    std::vector<std::uint32_t> pair_uvars;   // per pair: u variable indices of d_0..2, r2, q, m_0..2 (diagnostics / tests)
     // Table fac[n][j] = n alpha - j (alpha + 1) of the pow recurrence (src/math/pow.cpp:618-963),
     // (order + 1) rows of fac_stride doubles.
     std::vector<double> fac;
@@ -44,6 +45,15 @@ struct nb_plan {
 };
 
 nb_plan make_nb_plan(const hy_program &);
+
+// The per-thread role table of the summation phase for a team of `tt` threads owning `lt` lanes, `nl` lanes per thread:
+// rounds x tt records, level after level (every level's items are dealt out to the threads round-robin; a level ends
+// with a synchronisation). round_level_end: bit r is set if round r is the last one of its level.
+struct nb_roles {
+    std::vector<nb_role> table;
+    std::uint32_t n_rounds = 0, round_level_end = 0;
+};
+nb_roles make_nb_roles(const nb_plan &, std::uint32_t tt, std::uint32_t lt, std::uint32_t nl);
 
 } // namespace heyoka_b200::detail
 

@@ -106,6 +106,7 @@ struct taylor_adaptive_batch<double>::impl {
     std::vector<std::int64_t> oc;
     std::vector<double> tmp_a, tmp_b;
     std::vector<std::uint64_t> tmp_n;
+    bool tc_valid = false; // the device holds the Taylor coefficients mirrored in `tc`
 
     impl() = default;
     impl(const impl &o)
@@ -114,12 +115,13 @@ struct taylor_adaptive_batch<double>::impl {
           tape_mode(o.tape_mode), k_lpw(o.k_lpw), k_lpt(o.k_lpt), k_threads(o.k_threads), k_bpsm(o.k_bpsm),
           state(o.state), pars(o.pars), time_hi(o.time_hi), time_lo(o.time_lo), tc(o.tc), last_h(o.last_h),
           d_out(o.d_out), step_res(o.step_res), prop_res(o.prop_res), oc(o.oc), tmp_a(o.tmp_a), tmp_b(o.tmp_b),
-          tmp_n(o.tmp_n)
+          tmp_n(o.tmp_n), tc_valid(o.tc_valid)
     {
         if (prog) {
             make_batch();
-            if (o.batch != nullptr && !tc.empty()) {
-                // (the device tc is refreshed by the next write_tc step; dense output uses the host mirror upload)
+            if (o.batch != nullptr && tc_valid) {
+                // The copy can serve update_d_output() right away (src/detail/i_data.cpp:335-352 copies m_tc).
+                check(hy_batch_upload_tc(batch, tc.data()));
             }
         }
     }
@@ -143,6 +145,7 @@ struct taylor_adaptive_batch<double>::impl {
         check(hy_batch_download(batch, state.data(), time_hi.data(), time_lo.data(), last_h.data()));
         if (wtc) {
             check(hy_batch_download_tc(batch, tc.data()));
+            tc_valid = true;
         }
     }
     void pull_step_res()
@@ -773,7 +776,8 @@ const std::vector<double> &taylor_adaptive_batch<double>::update_d_output(const 
     std::vector<double> tau(m.batch_size);
     for (std::uint32_t i = 0; i < m.batch_size; ++i) {
         if (rel_time) {
-            tau[i] = t[i];
+            // Relative to the CURRENT time; the kernel expands about the start of the last step (:2276-2280).
+            tau[i] = m.last_h[i] + t[i];
         } else {
             // tau = t - (time - last_h) in double-length arithmetic (:2276-2286).
             const auto t0 = dfl_sub(dfl{m.time_hi[i], m.time_lo[i]}, dfl{m.last_h[i], 0.});

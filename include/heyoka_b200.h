@@ -208,6 +208,9 @@ int hy_batch_download(hy_batch *, double *state, double *t_hi, double *t_lo, dou
 int hy_batch_download_step_res(hy_batch *, int64_t *outcome, double *h);
 int hy_batch_download_prop_res(hy_batch *, int64_t *outcome, double *min_h, double *max_h, uint64_t *n_steps);
 int hy_batch_download_tc(hy_batch *, double *tc /* n_eq * (order + 1) * batch */);
+/* Restores the Taylor coefficients of the last step (copies of an integrator: src/detail/i_data.cpp:335-352 copies
+ * m_tc, so that update_d_output() works on the copy before its first write_tc step). */
+int hy_batch_upload_tc(hy_batch *, const double *tc /* n_eq * (order + 1) * batch */);
 
 /* Device pointers of the resident arrays, for zero-copy use (torch / NCCL gathers). tc is allocated lazily
  * (first step / propagate with write_tc, hy_batch_download_tc(), hy_batch_d_output()) and NULL before that. */
@@ -274,13 +277,16 @@ int hy_batch_set_launch_config(hy_batch *, uint32_t block_threads, uint32_t bloc
  * memory, else mode 4), 1 = force the one-thread-per-lane HBM-tape kernel, 2 = force the shared-memory kernel (error if it
  * does not fit), 3 = idem, but never keep rows in tensor memory, 4 = the same warp-cooperative kernel with the
  * tape in global memory, 5 = idem with a whole CTA (instead of a warp) working on a chunk of lanes; the automatic
- * mode picks 4 or 5 when shared memory is too small. lanes_per_warp (1..32, power of two) / lanes_per_thread (1, 2 or 4, dividing lanes_per_warp)
+ * mode picks 4 or 5 when shared memory is too small; 6 / 7 = the dedicated N-body kernel (warp / CTA teams; error if
+ * the program is not N-body-shaped, see csrc/nb_plan.hpp), which the automatic mode prefers whenever the program
+ * qualifies (lanes_per_thread then selects the storage of the private history rows: 0 automatic, 1 tensor memory,
+ * 2 shared memory only; lanes_per_warp = lanes per team). lanes_per_warp (1..32, power of two) / lanes_per_thread (1, 2 or 4, dividing lanes_per_warp)
  * only apply to the shared-memory kernel; 0 = automatic. block_threads = 32 x warps per block.
  * The environment variable HEYOKA_B200_TAPE=hbm|smem sets the default. */
 int hy_batch_set_kernel(hy_batch *, int tape_mode, uint32_t lanes_per_warp, uint32_t lanes_per_thread,
                         uint32_t block_threads, uint32_t blocks_per_sm);
 typedef struct hy_kernel_info {
-    int32_t tape_mode;            /* 1 = HBM tape (thread per lane), 2 = shared-memory tape, 4 / 5 = cooperative, global tape (warp / CTA teams) */
+    int32_t tape_mode;            /* 1 = HBM tape (thread per lane), 2 = shared-memory tape, 4 / 5 = cooperative, global tape (warp / CTA teams), 6 / 7 = N-body kernel (warp / CTA teams) */
     uint32_t lanes_per_warp, lanes_per_thread, block_threads, blocks_per_sm, grid;
     uint64_t smem_bytes;          /* dynamic shared memory per CTA */
     uint32_t tape_slots_per_lane; /* doubles of tape per lane in the selected strategy */

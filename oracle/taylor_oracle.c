@@ -604,6 +604,18 @@ static real_t sv_diff(const ctx_t *c, uint32_t sv, uint32_t n)
     return n == 1u ? numpar_val(c, ref) : R_SPLAT(0.);
 }
 
+#if ORACLE_W != 1
+/* A generated (straight-line, per-order unrolled) jet for the program being run, see oracle/codegen.py: when
+ * installed it replaces the interpreting loop below; the driver (step size, update, propagate loop) stays. The
+ * caller guarantees that the installed function was generated for the program it then runs. */
+typedef void (*jet_fn_t)(real_t *T, const real_t *par, const real_t *tm);
+static jet_fn_t jet_hook = NULL;
+void SYM(oracle_set_jet)(jet_fn_t f)
+{
+    jet_hook = f;
+}
+#endif
+
 /* The whole jet: orders 0..p-1 for every u variable, order p for the state variables. */
 static void compute_jet(ctx_t *c, const double *state, const double *t_hi)
 {
@@ -622,6 +634,18 @@ static void compute_jet(ctx_t *c, const double *state, const double *t_hi)
         }
         TAPE(c, 0, i) = v;
     }
+#if ORACLE_W != 1
+    if (jet_hook != NULL) {
+        real_t parv[64];
+        if (P->n_pars <= 64u) {
+            for (uint32_t k = 0; k < P->n_pars; ++k) {
+                parv[k] = load_par(c, k);
+            }
+            jet_hook(c->T, parv, &time_v);
+            return;
+        }
+    }
+#endif
     for (uint32_t n = 0; n < P->order; ++n) {
         if (n > 0u) {
             for (uint32_t i = 0; i < P->n_eq; ++i) {

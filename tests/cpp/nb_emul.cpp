@@ -1,11 +1,12 @@
 // TEST INFRASTRUCTURE: host emulation of the N-body kernel's jet (heyoka_b200/csrc/nb_core.hpp) on plain arrays.
 //
 // nb_core.hpp is the arithmetic of k_nb (nb_kernel.cuh) written once for host and device; the device only supplies
-// the storage policy (shared memory + tensor memory). This file supplies a storage policy on std::vector, runs the
-// phases in the kernel's order (all pair threads, then the summation levels, one "thread" after the other: the
-// threads of a team only communicate across synchronisation points) and returns every coefficient, so that the
-// two-orders-at-a-time index arithmetic can be checked against the oracle WITHOUT a GPU (tests/test_nb_plan.py).
-// It is never linked into the product library. Build: see tests/test_nb_plan.py (g++ -ffp-contract=off).
+// the storage policy (shared memory + tensor memory). This file supplies a storage policy on std::vector and runs a
+// TEAM of `tt` threads owning `lt` lanes exactly like the kernel does: every thread its pair interaction, then the
+// rounds of the pre-decoded role table (make_nb_roles()), one "thread" after the other (the threads of a team only
+// communicate across synchronisation points). It returns every coefficient, so that the two-orders-at-a-time index
+// arithmetic, the output-slot layout and the role records can be checked against the oracle WITHOUT a GPU
+// (tests/test_nb_plan.py). It is never linked into the product library. Build: g++ -ffp-contract=off.
 #include <cstdint>
 #include <cstring>
 #include <vector>
@@ -23,29 +24,30 @@ namespace
 
 struct emul {
     const hb::detail::nb_plan &pl;
-    std::uint32_t p, npp, n_eq;
-    std::vector<d2> pos, out;
-    std::vector<d2> rows; // [pair][5 rows: d0 d1 d2 r2 q][npp]
-    std::vector<double> coef; // [sv][p + 1]
-    std::vector<double> mk;   // [pair][3][2 * npp]: the products' coefficients (diagnostics)
-    const double *state;
+    std::uint32_t p, npp, n_eq, lt;
+    std::vector<d2> pos, out;   // [slot][lane]
+    std::vector<d2> rows;       // [pair][lane][5 rows: d0 d1 d2 r2 q][npp]
+    std::vector<double> coef;   // [lane][sv][p + 1]
+    std::vector<double> mk;     // [pair][lane][3][2 * npp]: the products' coefficients (diagnostics)
+    const double *state;        // [sv][lane]
 };
 
 struct pair_mem {
     emul &E;
-    std::uint32_t pi;
+    std::uint32_t pi, l;
     const hb::detail::nb_pair_desc &d;
+    std::uint32_t cur_m = 0;
     d2 *row(int r)
     {
-        return E.rows.data() + (static_cast<std::size_t>(pi) * 5u + r) * E.npp;
+        return E.rows.data() + ((static_cast<std::size_t>(pi) * E.lt + l) * 5u + r) * E.npp;
     }
     d2 pos_a(int k)
     {
-        return E.pos[d.pa[k]];
+        return E.pos[d.pa[k] * E.lt + l];
     }
     d2 pos_b(int k)
     {
-        return E.pos[d.pb[k]];
+        return E.pos[d.pb[k] * E.lt + l];
     }
     void st_d(std::uint32_t m, const d2 (&D)[3])
     {
@@ -91,29 +93,36 @@ struct pair_mem {
     {
         return E.pl.fac[static_cast<std::size_t>(n) * E.pl.fac_stride + j];
     }
-    std::uint32_t cur_m = 0;
     void out(int k, const d2 &v)
     {
-        E.out[d.om[k]] = v;
-        double *dst = E.mk.data() + (static_cast<std::size_t>(pi) * 3u + k) * 2u * E.npp + 2u * cur_m;
+        E.out[d.om[k] * E.lt + l] = v;
+        double *dst = E.mk.data() + ((static_cast<std::size_t>(pi) * E.lt + l) * 3u + k) * 2u * E.npp + 2u * cur_m;
         dst[0] = v.x;
         dst[1] = v.y;
     }
+    void out_n(int k, const d2 &v)
+    {
+        if (d.on[k] != 0xffffu) {
+            E.out[d.on[k] * E.lt + l] = v;
+        }
+    }
 };
 
-struct sum_mem {
+// One thread of the summation phase: lanes [l0, l0 + NL).
+struct role_mem {
     emul &E;
-    d2 out_ld(std::uint32_t slot, int)
+    std::uint32_t l0;
+    d2 out_u(std::uint32_t unit, int l)
     {
-        return E.out[slot];
+        return E.out[unit + l];
     }
-    void out_st(std::uint32_t slot, int, const d2 &v)
+    void out_st_u(std::uint32_t unit, int l, const d2 &v)
     {
-        E.out[slot] = v;
+        E.out[unit + l] = v;
     }
-    void pos_st(std::uint32_t slot, int, const d2 &v)
+    void pos_st_u(std::uint32_t unit, int l, const d2 &v)
     {
-        E.pos[slot] = v;
+        E.pos[unit + l] = v;
     }
     double cst(std::uint32_t i)
     {
@@ -123,15 +132,71 @@ struct sum_mem {
     {
         return 1. / static_cast<double>(n);
     }
-    void coef(std::uint32_t sv, std::uint32_t order, int, double v)
+    void coef(std::uint32_t sv, std::uint32_t order, std::uint32_t l, double v)
     {
-        E.coef[static_cast<std::size_t>(sv) * (E.p + 1u) + order] = v;
+        if (order <= E.p) {
+            E.coef[(static_cast<std::size_t>(l0 + l) * E.n_eq + sv) * (E.p + 1u) + order] = v;
+        }
     }
-    double state(std::uint32_t sv, int)
+    template <std::size_t NL>
+    void coef_pair(std::uint32_t sv, std::uint32_t order, const double (&a)[NL], const double (&b)[NL])
     {
-        return E.state[sv];
+        for (std::uint32_t l = 0; l < NL; ++l) {
+            coef(sv, order, l, a[l]);
+            coef(sv, order + 1u, l, b[l]);
+        }
+    }
+    template <std::size_t NL>
+    void coef_one(std::uint32_t sv, std::uint32_t order, const double (&a)[NL])
+    {
+        for (std::uint32_t l = 0; l < NL; ++l) {
+            coef(sv, order, l, a[l]);
+        }
+    }
+    double state(std::uint32_t sv, int l)
+    {
+        return E.state[static_cast<std::size_t>(sv) * E.lt + l0 + l];
     }
 };
+
+template <int NL>
+void run_team(emul &E, std::uint32_t tt)
+{
+    const auto &pl = E.pl;
+    const std::uint32_t lt = E.lt, gs = lt / NL;
+    const auto roles = hb::detail::make_nb_roles(pl, tt, lt, NL);
+    const auto rec = [&](std::uint32_t rd, std::uint32_t t, std::uint32_t (&w)[8]) {
+        static_assert(sizeof(hb::detail::nb_role) == 32u);
+        std::memcpy(w, &roles.table[static_cast<std::size_t>(rd) * tt + t], 32u);
+    };
+    for (std::uint32_t rd = 0; rd < roles.n_rounds; ++rd) {
+        for (std::uint32_t t = 0; t < tt; ++t) {
+            std::uint32_t w[8];
+            rec(rd, t, w);
+            role_mem RM{E, (t % gs) * NL};
+            hb::nb::role_init<NL>(RM, w);
+        }
+    }
+    const std::uint32_t n_pairs = static_cast<std::uint32_t>(pl.pairs.size());
+    for (std::uint32_t m = 0; m < E.npp; ++m) {
+        for (std::uint32_t t = 0; t < n_pairs * lt; ++t) {
+            const std::uint32_t pi = t / lt, l = t % lt;
+            const auto &d = pl.pairs[pi];
+            pair_mem PM{E, pi, l, d};
+            PM.cur_m = m;
+            const hb::nb::pair_consts C{d.c1, {d.c2[0], d.c2[1], d.c2[2]}, pl.alpha, pl.pow_algo, (d.flags & 1u) != 0u};
+            hb::nb::pair_block(PM, C, m);
+        }
+        for (std::uint32_t rd = 0; rd < roles.n_rounds; ++rd) {
+            for (std::uint32_t t = 0; t < tt; ++t) {
+                std::uint32_t w[8];
+                rec(rd, t, w);
+                role_mem RM{E, (t % gs) * NL};
+                hb::nb::role_block<NL>(RM, w, m, E.p);
+            }
+        }
+    }
+}
 
 } // namespace
 
@@ -154,59 +219,51 @@ int nb_emul_plan(const hy_program *p, std::uint32_t *out, char *why, std::size_t
     return static_cast<int>(pl.why.size());
 }
 
-// Jet of ONE lane. state[n_eq] -> coef[n_eq][order + 1] (state variables), and, per pair interaction i:
-// u_idx[i * 8 + {0..2: d_k, 3: r2, 4: q, 5..7: m_k}] = u variable index, u_rows[(i * 8 + r) * n_ord + o] = coefficient
-// of order o (n_ord = 2 * ceil(order / 2)). Returns 0, or -1 if the program does not qualify.
-int nb_emul_jet(const hy_program *p, const double *state, double *coef, std::uint32_t *u_idx, double *u_rows)
+// Jets of the `lt` lanes of ONE team of `tt` threads. state[n_eq][lt] -> coef[lt][n_eq][order + 1] (state variables),
+// and, per pair interaction i and lane l: u_idx[i * 8 + {0..2: d_k, 3: r2, 4: q, 5..7: m_k}] = u variable index,
+// u_rows[((i * lt + l) * 8 + r) * n_ord + o] = coefficient of order o (n_ord = 2 * ceil(order / 2)).
+// Returns 0, -1 if the program does not qualify, -2 for an unsupported team shape.
+int nb_emul_jet(const hy_program *p, std::uint32_t tt, std::uint32_t lt, const double *state, double *coef,
+                std::uint32_t *u_idx, double *u_rows)
 {
     const auto pl = hb::detail::make_nb_plan(*p);
     if (!pl.ok) {
         return -1;
     }
-    emul E{pl, p->order, (p->order + 1u) / 2u, p->n_eq, {}, {}, {}, {}, {}, state};
     const std::uint32_t n_pairs = static_cast<std::uint32_t>(pl.pairs.size());
-    E.pos.assign(pl.n_pos, d2{0., 0.});
-    E.out.assign(pl.n_out, d2{0., 0.});
-    E.rows.assign(static_cast<std::size_t>(n_pairs) * 5u * E.npp, d2{0., 0.});
-    E.coef.assign(static_cast<std::size_t>(p->n_eq) * (p->order + 1u), 0.);
-    E.mk.assign(static_cast<std::size_t>(n_pairs) * 3u * 2u * E.npp, 0.);
-    sum_mem SM{E};
-    const auto words = [&](std::size_t i) { return reinterpret_cast<const std::uint32_t *>(&pl.sums[i]); };
-    for (std::size_t i = 0; i < pl.sums.size(); ++i) {
-        hb::nb::sum_init<1>(SM, words(i));
+    if (lt == 0u || n_pairs * lt > tt || (lt > 1u && lt % 2u != 0u)) {
+        return -2;
     }
-    const hb::nb::pair_consts base{0., pl.alpha, pl.pow_algo};
-    for (std::uint32_t m = 0; m < E.npp; ++m) {
-        for (std::uint32_t pi = 0; pi < n_pairs; ++pi) {
-            pair_mem PM{E, pi, pl.pairs[pi]};
-            PM.cur_m = m;
-            auto C = base;
-            C.c1 = pl.pairs[pi].c1;
-            hb::nb::pair_block(PM, C, m);
-        }
-        for (std::size_t lv = 0; lv + 1u < pl.level_offsets.size(); ++lv) {
-            for (std::size_t i = pl.level_offsets[lv]; i < pl.level_offsets[lv + 1u]; ++i) {
-                hb::nb::sum_block<1>(SM, words(i), m, p->order);
-            }
-        }
+    emul E{pl, p->order, (p->order + 1u) / 2u, p->n_eq, lt, {}, {}, {}, {}, {}, state};
+    E.pos.assign(static_cast<std::size_t>(pl.n_pos) * lt, d2{0., 0.});
+    E.out.assign(static_cast<std::size_t>(pl.n_out) * lt, d2{0., 0.});
+    E.rows.assign(static_cast<std::size_t>(n_pairs) * lt * 5u * E.npp, d2{0., 0.});
+    E.coef.assign(static_cast<std::size_t>(lt) * p->n_eq * (p->order + 1u), 0.);
+    E.mk.assign(static_cast<std::size_t>(n_pairs) * lt * 3u * 2u * E.npp, 0.);
+    if (lt >= 2u) {
+        run_team<2>(E, tt);
+    } else {
+        run_team<1>(E, tt);
     }
     std::memcpy(coef, E.coef.data(), E.coef.size() * sizeof(double));
     const std::uint32_t n_ord = 2u * E.npp;
     for (std::uint32_t pi = 0; pi < n_pairs; ++pi) {
-        const auto &d = pl.pairs[pi];
-        const std::uint32_t us[8] = {d.u_d[0], d.u_d[1], d.u_d[2], d.u_r2, d.u_q, d.u_m[0], d.u_m[1], d.u_m[2]};
         for (std::uint32_t r = 0; r < 8u; ++r) {
-            u_idx[pi * 8u + r] = us[r];
-            double *dst = u_rows + (static_cast<std::size_t>(pi) * 8u + r) * n_ord;
-            if (r < 5u) {
-                const d2 *src = E.rows.data() + (static_cast<std::size_t>(pi) * 5u + r) * E.npp;
-                for (std::uint32_t m = 0; m < E.npp; ++m) {
-                    dst[2u * m] = src[m].x;
-                    dst[2u * m + 1u] = src[m].y;
+            u_idx[pi * 8u + r] = pl.pair_uvars[pi * 8u + r];
+        }
+        for (std::uint32_t l = 0; l < lt; ++l) {
+            for (std::uint32_t r = 0; r < 8u; ++r) {
+                double *dst = u_rows + ((static_cast<std::size_t>(pi) * lt + l) * 8u + r) * n_ord;
+                if (r < 5u) {
+                    const d2 *src = E.rows.data() + ((static_cast<std::size_t>(pi) * lt + l) * 5u + r) * E.npp;
+                    for (std::uint32_t m = 0; m < E.npp; ++m) {
+                        dst[2u * m] = src[m].x;
+                        dst[2u * m + 1u] = src[m].y;
+                    }
+                } else {
+                    std::memcpy(dst, E.mk.data() + ((static_cast<std::size_t>(pi) * lt + l) * 3u + (r - 5u)) * n_ord,
+                                n_ord * sizeof(double));
                 }
-            } else {
-                std::memcpy(dst, E.mk.data() + (static_cast<std::size_t>(pi) * 3u + (r - 5u)) * n_ord,
-                            n_ord * sizeof(double));
             }
         }
     }

@@ -256,12 +256,17 @@ static void test_models_and_dense_output()
     const auto st0 = ta.get_state();
     ta.step(true);
     const auto &h = ta.get_last_h();
-    // dense output at tau = h reproduces the state, at tau = 0 the previous state
-    auto d1 = ta.update_d_output(std::vector<double>(h.begin(), h.end()), true);
+    // Dense output relative to the CURRENT time (src/taylor_adaptive_batch.cpp:2276-2280): 0 reproduces the state,
+    // -last_h the state before the step.
+    auto d1 = ta.update_d_output(0., true);
     for (std::size_t i = 0; i < st.size(); ++i) {
         REQUIRE(approx(d1[i], ta.get_state()[i], 100.));
     }
-    auto d0 = ta.update_d_output(0., true);
+    std::vector<double> mh(h.size());
+    for (std::size_t i = 0; i < h.size(); ++i) {
+        mh[i] = -h[i];
+    }
+    auto d0 = ta.update_d_output(mh, true);
     for (std::size_t i = 0; i < st.size(); ++i) {
         REQUIRE(d0[i] == st0[i]);
     }

@@ -91,7 +91,7 @@ def test_nbody32_shard_8192_energy_and_sample():
     st = nbody32_batch_state(batch)
     P = hb.Program(sys_nbody32())
     b = hb.Batch(P, batch)
-    assert b.kernel_info()["tape"] == "global-cta"
+    assert b.kernel_info()["tape"] == "nbody-cta"
     b.upload(st, None, np.zeros(batch), np.zeros(batch))
     b.propagate_until(np.full(batch, t_final))
     new, t_hi, t_lo, _ = b.download()

@@ -30,6 +30,12 @@ KERNELS = {
     "smem-L2N1": dict(tape="smem", lanes_per_warp=2, lanes_per_thread=1, block_threads=64),
     "smem-L2N2": dict(tape="smem", lanes_per_warp=2, lanes_per_thread=2),  # two rows per pair in tensor memory
     "smem-L4N4": dict(tape="smem", lanes_per_warp=4, lanes_per_thread=4, block_threads=32),
+    # The dedicated N-body kernel (nb_kernel.cuh; N-body-shaped programs only, the other tests skip): private rows in
+    # tensor memory / in shared memory only / 12 warps per CTA (168 registers per thread).
+    "nbody": dict(tape="nbody"),
+    "nbody-smem": dict(tape="nbody", lanes_per_thread=2),
+    "nbody-384": dict(tape="nbody", lanes_per_thread=1, block_threads=384),
+    "nbody-L1": dict(tape="nbody", lanes_per_warp=1, block_threads=128),
 }
 
 
@@ -262,11 +268,15 @@ def test_dense_output(kernel):
     ta.step(write_tc=True)
     tau = 0.37 * o.last_h
     ref = o.d_output(tau)
-    got = ta.update_d_output(tau, rel_time=True)
+    # rel_time is relative to the CURRENT time (src/taylor_adaptive_batch.cpp:2276-2280): the polynomial, expanded about
+    # the start of the last step, is evaluated at last_h + t.
+    got = ta.update_d_output(tau - ta.last_h, rel_time=True)
     assert rel_err(got, ref) < 1e-13
-    # at tau = h the dense output reproduces the new state; at tau = 0 the old one
-    assert rel_err(ta.update_d_output(ta.last_h, rel_time=True), ta.state) < 1e-13
-    assert rel_err(ta.update_d_output(0., rel_time=True), st) < 1e-15
+    got_abs = ta.update_d_output(ta.time - ta.last_h + tau)
+    assert rel_err(got_abs, ref) < 1e-12
+    # rel_time = 0 reproduces the current state, rel_time = -last_h the state before the step
+    assert rel_err(ta.update_d_output(0., rel_time=True), ta.state) < 1e-13
+    assert rel_err(ta.update_d_output(-ta.last_h, rel_time=True), st) < 1e-15
 
 
 def test_raw_program_interface_matches():
@@ -291,14 +301,22 @@ def test_raw_program_interface_matches():
 
 
 def test_kernel_selection_info():
-    """Automatic selection: shared-memory tape for the 6-body system (3 x 4 lanes per SM), HBM tape when the
-    tape cannot fit (32 bodies)."""
+    """Automatic selection: the dedicated N-body kernel for N-body-shaped programs (warp teams for the 6-body system,
+    CTA teams for 32 bodies), the shared-memory tape otherwise; every strategy can be forced."""
     b = hb.Batch(hb.Program(sys_outer_ss(), high_accuracy=True), 64)
+    ki = b.kernel_info()
+    # 15 pair interactions x 2 lanes, one per thread; r^2, d_z, r^-3 live in tensor memory as (even, odd) order pairs:
+    # 10 pairs x 12 columns; 16 warps of 2 lanes per SM.
+    assert ki["tape"] == "nbody" and ki["lanes_per_warp"] == 2 and ki["tmem_cols_per_warp"] == 120
+    assert ki["block_threads"] == 512 and ki["smem_bytes"] <= 227 * 1024
+    b.set_kernel("nbody", lanes_per_thread=2)
+    ki = b.kernel_info()
+    assert ki["tape"] == "nbody" and ki["tmem_cols_per_warp"] == 0
+    b.set_kernel("smem")
     ki = b.kernel_info()
     assert ki["tape"] == "smem" and ki["tape_slots_per_lane"] < 234 * 21 / 2
     assert ki["smem_bytes"] <= 227 * 1024
-    # 15 pair interactions x 2 lanes, one per thread: their private histories (r^2, r^-3, dz: 3 rows x 21 orders x
-    # 2 words) live in tensor memory, which lets 16 warps of 2 lanes reside on an SM instead of 8.
+    # The generic cooperative kernel: 3 rows x 21 orders x 2 words per pair interaction in tensor memory.
     assert ki["tmem_cols_per_warp"] == 126 and ki["block_threads"] == 512 and ki["lanes_per_thread"] == 1
     b.set_kernel("smem", lanes_per_warp=2, lanes_per_thread=2)
     ki = b.kernel_info()
@@ -308,12 +326,19 @@ def test_kernel_selection_info():
     assert ki["tmem_cols_per_warp"] == 0 and ki["block_threads"] == 256
     b.set_kernel("hbm")
     assert b.kernel_info()["tape"] == "hbm"
-    big = hb.Batch(hb.Program(hb.model.nbody(32)), 32)
-    assert big.kernel_info()["tape"] == "global-cta"  # 496 pair interactions per level, 32 lanes
+    from common import sys_nbody32
+    big = hb.Batch(hb.Program(sys_nbody32()), 32)
+    assert big.kernel_info()["tape"] == "nbody-cta"  # 496 pair interactions: one lane per CTA of 512 threads
+    big.set_kernel("global-cta")
+    assert big.kernel_info()["tape"] == "global-cta"
     big.set_kernel("hbm")
     assert big.kernel_info()["tape"] == "hbm"
     with pytest.raises(ValueError, match="does not fit in shared memory"):
         big.set_kernel("smem")
+    pend = hb.Batch(hb.Program(sys_pendulum()), 8)
+    assert pend.kernel_info()["tape"] == "smem"
+    with pytest.raises(ValueError, match="The N-body kernel cannot run this program"):
+        pend.set_kernel("nbody")
 
 
 def _closed_form_cases():
@@ -433,16 +458,19 @@ def test_propagate_grid_limits_match_oracle(kernel):
 # ---- BASELINE.json configs[2] and [4] at oracle-sized batches (the tape of these systems lives in HBM) ----
 
 @pytest.mark.gpu
-def test_nbody32_parity():
+@pytest.mark.parametrize("tape", ["nbody-cta", "global-cta"])
+def test_nbody32_parity(tape):
     """model::nbody N = 32 (496 pair interactions, ~0.5 MB of tape per lane): a step and a short propagation
-    against the oracle; identical step counts."""
+    against the oracle; identical step counts. Automatic selection = the N-body kernel with CTA teams."""
     from common import nbody32_batch_state, sys_nbody32
     batch = 8
     st = nbody32_batch_state(batch)
     P = hb.Program(sys_nbody32(), high_accuracy=False)
     assert (P.n_eq, P.order) == (192, 20)
     ta = hb.taylor_adaptive_batch(sys_nbody32(), st, batch)
-    assert ta._b.kernel_info()["tape"] == "global-cta"
+    assert ta._b.kernel_info()["tape"] == "nbody-cta"
+    ta._b.set_kernel(tape)
+    assert ta._b.kernel_info()["tape"] == tape
     o = oracle.OracleIntegrator(P, st, batch, mode=oracle.FMA)
     ta.step(write_tc=True)
     o.step(write_tc=True)

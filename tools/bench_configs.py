@@ -68,9 +68,12 @@ def main():
     if "n32" in which:
         st = nbody32_batch_state(8192)
         run("nbody N=32, 8192 lanes, propagate_until(1)", hb.Program(sys_nbody32()), st, 1.0)
-        run("nbody N=32, 8192 lanes, propagate_until(1), warp teams", hb.Program(sys_nbody32()), st, 1.0, tape="global")
-        run("nbody N=32, 8192 lanes, propagate_until(1), thread-per-lane HBM kernel", hb.Program(sys_nbody32()), st, 1.0,
-            tape="hbm")
+        run("nbody N=32, 8192 lanes, propagate_until(1), generic cooperative kernel (CTA teams, global tape)",
+            hb.Program(sys_nbody32()), st, 1.0, tape="global-cta")
+        if "n32all" in which:
+            run("nbody N=32, 8192 lanes, propagate_until(1), warp teams", hb.Program(sys_nbody32()), st, 1.0, tape="global")
+            run("nbody N=32, 8192 lanes, propagate_until(1), thread-per-lane HBM kernel", hb.Program(sys_nbody32()), st,
+                1.0, tape="hbm")
     if "nn" in which:
         run("ffnn 3x64 tanh order 15, 262144 lanes, propagate_until(0.5)", hb.Program(sys_ffnn(), tol=FFNN_TOL),
             ffnn_batch_state(1 << 18), 0.5)
