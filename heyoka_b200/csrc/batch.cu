@@ -239,7 +239,8 @@ struct hy_batch {
            *d_tc = nullptr, *d_d_out = nullptr;
     long long *d_step_outcome = nullptr, *d_prop_outcome = nullptr;
     double *d_prop_min_h = nullptr, *d_prop_max_h = nullptr;
-    unsigned long long *d_prop_n_steps = nullptr;
+    unsigned long long *d_prop_n_steps = nullptr, *d_prop_iters = nullptr;
+    unsigned char *d_skip = nullptr; // per-lane mask of the masked zero-length step (propagate_finish())
 
     // Scratch.
     double *d_scratch = nullptr; // per-warp tape slabs ("hbm" strategy only, allocated on demand)
@@ -301,7 +302,8 @@ void hy_batch::free_all() noexcept
           static_cast<void *>(d_t_hi), static_cast<void *>(d_t_lo), static_cast<void *>(d_last_h),
           static_cast<void *>(d_tc), static_cast<void *>(d_d_out), static_cast<void *>(d_step_outcome),
           static_cast<void *>(d_prop_outcome), static_cast<void *>(d_prop_min_h), static_cast<void *>(d_prop_max_h),
-          static_cast<void *>(d_prop_n_steps), static_cast<void *>(d_scratch), static_cast<void *>(d_tmp),
+          static_cast<void *>(d_prop_n_steps), static_cast<void *>(d_prop_iters), static_cast<void *>(d_skip),
+          static_cast<void *>(d_scratch), static_cast<void *>(d_tmp),
           static_cast<void *>(d_snapshot), static_cast<void *>(d_counter), static_cast<void *>(d_flags),
           static_cast<void *>(d_nb_pairs), static_cast<void *>(d_nb_roles), static_cast<void *>(d_nb_consts),
           static_cast<void *>(d_nb_fac)}) {
@@ -336,6 +338,7 @@ dev::batch hy_batch::view() const
     b.prop_min_h = d_prop_min_h;
     b.prop_max_h = d_prop_max_h;
     b.prop_n_steps = d_prop_n_steps;
+    b.prop_iters = d_prop_iters;
     return b;
 }
 
@@ -750,10 +753,15 @@ bool hy_batch::setup_nb(int LT, std::uint32_t threads, int want_tmem, int want_c
         return false;
     }
     if (threads == 0u) {
-        threads = 32u * pick.warps;
-        if (!cta && opt_nb_threads != 0u && opt_nb_threads <= threads) {
+        // Warp teams: 12 warps by default (168 registers per thread: the pair interaction's working set fits without
+        // spilling; measured faster than 16 warps of 128 registers and than 8 of 255).
+        threads = 32u * (cta ? pick.warps : std::min(pick.warps, 12u));
+        if (!cta && opt_nb_threads != 0u) {
             threads = opt_nb_threads;
         }
+    }
+    if (!cta) {
+        threads = std::min(threads, 32u * pick.warps); // (a tuning knob: clamped to what fits)
     }
     if (threads % 32u != 0u || threads == 0u || threads / 32u > pick.warps || (cta && threads != 512u)) {
         throw std::invalid_argument("Invalid number of threads for the N-body kernel");
@@ -939,66 +947,105 @@ const double *stage(hy_batch *b, const double *src, int on_device, std::uint32_t
     return dst;
 }
 
-int propagate_impl(hy_batch *b, const double *d_tf_hi, const double *d_tf_lo, const double *d_mdt, uint64_t max_steps,
-                   int write_tc, int *any_flag)
+// propagate_until() on one device, in three phases so that a multi-device run (hy_multi_*) can apply the reference's
+// GLOBAL exits across its shards:
+//   phase 1  snapshot of (state, time), one launch of the propagate kernel, flags read back (synchronises);
+//   replay   if a lane of ANY shard went non-finite: restore the snapshot and re-run with the iteration count capped at
+//            the first such iteration (the reference stops EVERY lane there, src/taylor_adaptive_batch.cpp:1462-1467;
+//            lanes are independent, so the capped re-run reproduces it exactly);
+//   finish   iteration limit -> every lane reports step_limit (:1516-1526); the lanes that were done before the loop's
+//            last iteration K took zero-length steps in the reference: last_h = 0 and, with write_tc, Taylor
+//            coefficients re-expanded about the final state (one masked zero-length step).
+struct prop_ctx {
+    dev::run_args R{};
+    dev::run_flags fl{};
+};
+
+void propagate_phase1(hy_batch *b, const double *d_tf_hi, const double *d_tf_lo, const double *d_mdt, uint64_t max_steps,
+                      int write_tc, prop_ctx &c)
 {
     const std::size_t state_doubles = static_cast<std::size_t>(b->n_eq) * b->n;
-
-    // Snapshot (state, t_hi, t_lo) so that a global early exit can be replayed exactly.
     HY_CUDA_CHECK(cudaMemcpyAsync(b->d_snapshot, b->d_state, sizeof(double) * state_doubles, cudaMemcpyDeviceToDevice,
                                   b->stream));
     HY_CUDA_CHECK(cudaMemcpyAsync(b->d_snapshot + state_doubles, b->d_t_hi, sizeof(double) * b->n,
                                   cudaMemcpyDeviceToDevice, b->stream));
     HY_CUDA_CHECK(cudaMemcpyAsync(b->d_snapshot + state_doubles + b->n, b->d_t_lo, sizeof(double) * b->n,
                                   cudaMemcpyDeviceToDevice, b->stream));
-
-    const dev::run_flags init{0u, 0u, ~0ull};
+    const dev::run_flags init{0u, 0u, ~0ull, 0ull};
     HY_CUDA_CHECK(cudaMemcpyAsync(b->d_flags, &init, sizeof(init), cudaMemcpyHostToDevice, b->stream));
-
-    dev::run_args R{};
-    R.max_delta_t = d_mdt;
-    R.tf_hi = d_tf_hi;
-    R.tf_lo = d_tf_lo;
-    R.iter_cap = max_steps;
-    R.replay = 0;
-    R.write_tc = write_tc;
-    R.flags = b->d_flags;
-    R.counter = b->d_counter;
-    b->launch(true, R);
-
-    dev::run_flags fl{};
-    HY_CUDA_CHECK(cudaMemcpyAsync(&fl, b->d_flags, sizeof(fl), cudaMemcpyDeviceToHost, b->stream));
+    c.R = dev::run_args{};
+    c.R.max_delta_t = d_mdt;
+    c.R.tf_hi = d_tf_hi;
+    c.R.tf_lo = d_tf_lo;
+    c.R.iter_cap = max_steps;
+    c.R.replay = 0;
+    c.R.write_tc = write_tc;
+    c.R.flags = b->d_flags;
+    c.R.counter = b->d_counter;
+    b->launch(true, c.R);
+    HY_CUDA_CHECK(cudaMemcpyAsync(&c.fl, b->d_flags, sizeof(c.fl), cudaMemcpyDeviceToHost, b->stream));
     HY_CUDA_CHECK(cudaStreamSynchronize(b->stream));
+}
 
-    if (fl.any_nf != 0u) {
-        // The reference stops EVERY lane at the first iteration in which any lane goes non-finite
-        // (src/taylor_adaptive_batch.cpp:1462-1467). Lanes are independent, so re-running from the
-        // snapshot with the iteration count capped at that index reproduces it exactly (the index is
-        // never beyond max_steps, because the first run was capped there).
-        HY_CUDA_CHECK(cudaMemcpyAsync(b->d_state, b->d_snapshot, sizeof(double) * state_doubles,
-                                      cudaMemcpyDeviceToDevice, b->stream));
-        HY_CUDA_CHECK(cudaMemcpyAsync(b->d_t_hi, b->d_snapshot + state_doubles, sizeof(double) * b->n,
-                                      cudaMemcpyDeviceToDevice, b->stream));
-        HY_CUDA_CHECK(cudaMemcpyAsync(b->d_t_lo, b->d_snapshot + state_doubles + b->n, sizeof(double) * b->n,
-                                      cudaMemcpyDeviceToDevice, b->stream));
-        HY_CUDA_CHECK(cudaMemcpyAsync(b->d_flags, &init, sizeof(init), cudaMemcpyHostToDevice, b->stream));
-        R.iter_cap = fl.min_nf_iter;
-        R.replay = 1;
-        b->launch(true, R);
-        HY_CUDA_CHECK(cudaMemcpyAsync(&fl, b->d_flags, sizeof(fl), cudaMemcpyDeviceToHost, b->stream));
-        HY_CUDA_CHECK(cudaStreamSynchronize(b->stream));
-    }
+void propagate_replay(hy_batch *b, prop_ctx &c, unsigned long long cap)
+{
+    const std::size_t state_doubles = static_cast<std::size_t>(b->n_eq) * b->n;
+    HY_CUDA_CHECK(cudaMemcpyAsync(b->d_state, b->d_snapshot, sizeof(double) * state_doubles, cudaMemcpyDeviceToDevice,
+                                  b->stream));
+    HY_CUDA_CHECK(cudaMemcpyAsync(b->d_t_hi, b->d_snapshot + state_doubles, sizeof(double) * b->n,
+                                  cudaMemcpyDeviceToDevice, b->stream));
+    HY_CUDA_CHECK(cudaMemcpyAsync(b->d_t_lo, b->d_snapshot + state_doubles + b->n, sizeof(double) * b->n,
+                                  cudaMemcpyDeviceToDevice, b->stream));
+    const dev::run_flags init{0u, 0u, ~0ull, 0ull};
+    HY_CUDA_CHECK(cudaMemcpyAsync(b->d_flags, &init, sizeof(init), cudaMemcpyHostToDevice, b->stream));
+    c.R.iter_cap = cap;
+    c.R.replay = 1;
+    b->launch(true, c.R);
+    HY_CUDA_CHECK(cudaMemcpyAsync(&c.fl, b->d_flags, sizeof(c.fl), cudaMemcpyDeviceToHost, b->stream));
+    HY_CUDA_CHECK(cudaStreamSynchronize(b->stream));
+}
 
-    if (fl.any_nf == 0u && fl.any_limit != 0u) {
-        // Iteration limit: every lane reports step_limit (src/taylor_adaptive_batch.cpp:1516-1526).
-        dev::k_fill_outcome<<<(b->n + 255u) / 256u, 256, 0, b->stream>>>(b->d_prop_outcome, b->n,
-                                                                         HY_OUTCOME_STEP_LIMIT);
+void propagate_finish(hy_batch *b, bool any_nf, bool any_limit, unsigned long long loop_len, int write_tc)
+{
+    const std::uint32_t gb = (b->n + 255u) / 256u;
+    if (!any_nf && any_limit) {
+        dev::k_fill_outcome<<<gb, 256, 0, b->stream>>>(b->d_prop_outcome, b->n, HY_OUTCOME_STEP_LIMIT);
         HY_CUDA_CHECK(cudaGetLastError());
         ++b->n_launches;
     }
+    // Lanes that were done before the last iteration of the reference's loop.
+    unsigned *d_any = reinterpret_cast<unsigned *>(b->d_flags) + sizeof(dev::run_flags) / sizeof(unsigned);
+    HY_CUDA_CHECK(cudaMemsetAsync(d_any, 0, sizeof(unsigned), b->stream));
+    dev::k_prop_early<<<gb, 256, 0, b->stream>>>(b->d_prop_iters, loop_len, b->n, b->d_last_h, b->d_skip, b->d_tmp, d_any);
+    HY_CUDA_CHECK(cudaGetLastError());
+    ++b->n_launches;
+    if (write_tc != 0) {
+        unsigned any = 0;
+        HY_CUDA_CHECK(cudaMemcpyAsync(&any, d_any, sizeof(any), cudaMemcpyDeviceToHost, b->stream));
+        HY_CUDA_CHECK(cudaStreamSynchronize(b->stream));
+        if (any != 0u) {
+            dev::run_args R{};
+            R.max_delta_t = b->d_tmp; // zeros
+            R.write_tc = 1;
+            R.flags = b->d_flags;
+            R.counter = b->d_counter;
+            R.skip = b->d_skip;
+            b->launch(false, R);
+        }
+    }
+}
 
+int propagate_impl(hy_batch *b, const double *d_tf_hi, const double *d_tf_lo, const double *d_mdt, uint64_t max_steps,
+                   int write_tc, int *any_flag)
+{
+    prop_ctx c;
+    propagate_phase1(b, d_tf_hi, d_tf_lo, d_mdt, max_steps, write_tc, c);
+    if (c.fl.any_nf != 0u) {
+        propagate_replay(b, c, c.fl.min_nf_iter);
+    }
+    propagate_finish(b, c.fl.any_nf != 0u, c.fl.any_limit != 0u, c.fl.max_iter, write_tc);
     if (any_flag != nullptr) {
-        *any_flag = (fl.any_nf != 0u ? 1 : 0) | (fl.any_limit != 0u ? 2 : 0);
+        *any_flag = (c.fl.any_nf != 0u ? 1 : 0) | (c.fl.any_limit != 0u ? 2 : 0);
     }
     return HY_OK;
 }
@@ -1117,10 +1164,12 @@ int hy_batch_create(const hy_program *p, uint32_t batch, int device, hy_batch **
         b->d_prop_min_h = b->dalloc<double>(n);
         b->d_prop_max_h = b->dalloc<double>(n);
         b->d_prop_n_steps = b->dalloc<unsigned long long>(n);
+        b->d_prop_iters = b->dalloc<unsigned long long>(n);
+        b->d_skip = b->dalloc<unsigned char>(n);
         b->d_tmp = b->dalloc<double>(3u * n);
         b->d_snapshot = b->dalloc<double>(n * (p->n_eq + 2u));
         b->d_counter = b->dalloc<unsigned int>(1);
-        b->d_flags = b->dalloc<dev::run_flags>(1);
+        b->d_flags = b->dalloc<dev::run_flags>(2); // (+ scratch words behind the flags)
 
         HY_CUDA_CHECK(cudaMemset(b->d_state, 0, sizeof(double) * n * p->n_eq));
         HY_CUDA_CHECK(cudaMemset(b->d_pars, 0, sizeof(double) * std::max<std::size_t>(n * p->n_pars, 1u)));

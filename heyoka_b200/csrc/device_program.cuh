@@ -31,6 +31,7 @@ struct batch {
     long long *prop_outcome;
     double *prop_min_h, *prop_max_h;
     unsigned long long *prop_n_steps;
+    unsigned long long *prop_iters; // iterations of the lock-step loop each lane was active in (last_h semantics)
 };
 
 // Global flags written by the propagate kernel.
@@ -38,6 +39,7 @@ struct run_flags {
     unsigned int any_nf;               // some lane produced a non-finite state / time
     unsigned int any_limit;            // some lane hit the iteration limit
     unsigned long long min_nf_iter;    // smallest 1-based iteration index at which a lane went non-finite
+    unsigned long long max_iter;       // largest number of iterations any lane took (the reference's loop length)
 };
 
 } // namespace heyoka_b200::dev

@@ -54,6 +54,9 @@ struct run_args {
     double *coef_base;
     unsigned long long coef_warp_stride, coef_stride_sv, coef_stride_o;
     int coef_pub;
+    // step: lanes flagged here are left untouched (no state, time, outcome or tc write). Used for the zero-length
+    // re-expansion of the lanes that finished a propagate_until() early (see batch.cu::propagate_finish()).
+    const unsigned char *skip;
 };
 
 // ================================================================================================
@@ -141,6 +144,12 @@ struct lane_prop {
         D.prop_min_h[lane] = min_h;
         D.prop_max_h[lane] = max_h;
         D.prop_n_steps[lane] = ts_count;
+        D.prop_iters[lane] = iter;
+    }
+    // (Separate from store(): needs the launch's flags.)
+    __device__ __forceinline__ void report_iters(const run_args &R) const
+    {
+        atomicMax(&R.flags->max_iter, iter);
     }
 };
 
@@ -359,8 +368,11 @@ __global__ void __launch_bounds__(256) k_hbm(program P, batch D, run_args R, dou
 
     for (std::uint32_t chunk = claim_chunk_warp(R.counter); chunk < n_chunks; chunk = claim_chunk_warp(R.counter)) {
         const std::uint32_t lane_raw = chunk * 32u + lane_in_warp;
-        const bool valid = lane_raw < D.n;
+        bool valid = lane_raw < D.n;
         const std::uint32_t lane = valid ? lane_raw : D.n - 1u;
+        if constexpr (!PROP) {
+            valid = valid && !(R.skip != nullptr && R.skip[lane] != 0u);
+        }
         hbm_tape tape{slab, P.order + 1u, D.pars, D.n, lane, 0., P.args, P.consts};
 
         if constexpr (!PROP) {
@@ -396,6 +408,7 @@ __global__ void __launch_bounds__(256) k_hbm(program P, batch D, run_args R, dou
             }
             if (valid) {
                 lp.store(D, lane);
+                lp.report_iters(R);
             }
         }
     }
@@ -552,6 +565,7 @@ struct coef_view {
     double *base;
     std::size_t stride_sv, stride_o;
     bool pub;
+    bool mask_idle = false; // lanes that are not running do not write to the store either (step with a skip mask)
     __device__ __forceinline__ std::size_t lane_off(std::uint32_t glane, std::uint32_t l) const
     {
         return pub ? glane : l;
@@ -641,8 +655,8 @@ __device__ __forceinline__ void coop_jet(const program &P, const coop_header &H,
 #pragma unroll
     for (int i = 0; i < N; ++i) {
         const std::uint32_t l = lane0 + g * N + i;
-        lane_ok[i] = l < D.n;
-        t.glane[i] = lane_ok[i] ? l : D.n - 1u;
+        lane_ok[i] = l < D.n && !(cv.mask_idle && S.running[g * N + i] == 0);
+        t.glane[i] = l < D.n ? l : D.n - 1u;
         t.tm.v[i] = S.time[g * N + i];
     }
     sv_writer<L, N> sv_out_{t, cv, svout, rcp, p, {}, {}};
@@ -672,7 +686,7 @@ __device__ __forceinline__ void coop_jet(const program &P, const coop_header &H,
 #pragma unroll
     for (int i = 0; i < NS; ++i) {
         const std::uint32_t l = lane0 + gs * NS + i;
-        sv_out_s_.lane_ok[i] = l < D.n;
+        sv_out_s_.lane_ok[i] = l < D.n && !(cv.mask_idle && S.running[gs * NS + i] == 0);
         ts.glane[i] = l < D.n ? l : D.n - 1u;
         ts.tm.v[i] = S.time[gs * NS + i];
         sv_out_s_.loff[i] = cv.lane_off(ts.glane[i], gs * NS + i);
@@ -917,23 +931,25 @@ __global__ void __launch_bounds__(MAXT, 1)
     // Coefficient store: public tc or the warp's private slice (see coef_view; strides precomputed by the host).
     const coef_view cv{R.coef_base + warp_global * R.coef_warp_stride,
                        static_cast<std::size_t>(R.coef_stride_sv), static_cast<std::size_t>(R.coef_stride_o),
-                       R.coef_pub != 0};
+                       R.coef_pub != 0, !PROP && R.skip != nullptr};
 
     for (std::uint32_t chunk = T::claim(R.counter); chunk < n_chunks; chunk = T::claim(R.counter)) {
         const std::uint32_t lane0 = chunk * L;
         // Owner threads (one per lane) do the scalar bookkeeping of their lane.
         const std::uint32_t lane_raw = lane0 + tid;
-        const bool valid = owner && lane_raw < D.n;
+        bool valid = owner && lane_raw < D.n;
         const std::uint32_t lane = valid ? lane_raw : D.n - 1u;
 
         if constexpr (!PROP) {
             double mdt = 0.;
             dfl t0{0., 0.};
             if (owner) {
+                const bool skipped = R.skip != nullptr && R.skip[lane] != 0u;
+                valid = valid && !skipped;
                 mdt = R.max_delta_t != nullptr ? R.max_delta_t[lane] : R.default_max_delta_t;
                 t0 = dfl{D.t_hi[lane], D.t_lo[lane]};
                 S.time[tid] = t0.hi;
-                S.running[tid] = 1;
+                S.running[tid] = skipped ? 0 : 1;
             }
             T::sync();
             coop_jet<L, N, MODE>(P, H, tab, D, S, lane0, gtape, tm_r2, cv);
@@ -983,6 +999,7 @@ __global__ void __launch_bounds__(MAXT, 1)
             }
             if (valid) {
                 lp.store(D, lane);
+                lp.report_iters(R);
             }
         }
         T::sync();

@@ -60,6 +60,12 @@ __device__ __forceinline__ std::uint32_t saddr(const void *p)
 {
     return static_cast<std::uint32_t>(__cvta_generic_to_shared(p));
 }
+// Pins a loop-invariant value in a register: without it the compiler re-derives shared-window addresses and kernel
+// parameters (a dozen uniform-datapath instructions each) inside the per-order-pair code instead of keeping them.
+__device__ __forceinline__ void keep(std::uint32_t &x)
+{
+    asm volatile("" : "+r"(x));
+}
 __device__ __forceinline__ d2 lds2(std::uint32_t a)
 {
     d2 v;
@@ -418,10 +424,12 @@ __global__ void __launch_bounds__(MAXT, 1) k_nb(program P, nb_dev_plan NP, batch
     double *region = smem_raw + NP.shared_doubles
                      + (CTA ? 0u : static_cast<std::size_t>(threadIdx.x >> 5) * NP.team_doubles);
     const coop_smem<LT> S(region, NP.n_slots_equiv);
-    const std::uint32_t pos_b = nbk::saddr(region);
-    const std::uint32_t out_b = pos_b + NP.n_pos * LT * 16u;
+    std::uint32_t pos_b = nbk::saddr(region);
+    std::uint32_t out_b = pos_b + NP.n_pos * LT * 16u;
     const std::uint32_t drow_b = out_b + NP.n_out * LT * 16u;
     const std::uint32_t norms_b = drow_b + NP.npp * nbk::pair_mem<TT, TMEM>::OPB;
+    nbk::keep(pos_b);
+    nbk::keep(out_b);
     unsigned long long *norms_p
         = reinterpret_cast<unsigned long long *>(region + (static_cast<std::size_t>(NP.n_pos) + NP.n_out) * LT * 2u
                                                  + static_cast<std::size_t>(NP.npp) * nbk::pair_mem<TT, TMEM>::OPB / 8u);
@@ -484,11 +492,16 @@ __global__ void __launch_bounds__(MAXT, 1) k_nb(program P, nb_dev_plan NP, batch
     RM.p = p;
     const std::size_t team_global = T::index();
     const coef_view cv{R.coef_base + team_global * R.coef_warp_stride, static_cast<std::size_t>(R.coef_stride_sv),
-                       static_cast<std::size_t>(R.coef_stride_o), R.coef_pub != 0};
+                       static_cast<std::size_t>(R.coef_stride_o), R.coef_pub != 0, !PROP && R.skip != nullptr};
     RM.stride_sv = cv.stride_sv;
     RM.stride_o = cv.stride_o;
     RM.pub = cv.pub;
-    const std::uint32_t roles_sa = nbk::saddr(roles_s) + tid * 32u;
+    std::uint32_t roles_sa = nbk::saddr(roles_s) + tid * 32u;
+    nbk::keep(roles_sa);
+    nbk::keep(RM.consts);
+    nbk::keep(RM.rcp_);
+    nbk::keep(PM.fac_);
+    const std::uint32_t n_rounds = NP.n_rounds, level_end = NP.round_level_end, roles_smem = NP.roles_in_smem;
     const uint4 *roles_g = NP.roles + tid * 2u;
 
     const std::uint32_t n_chunks = (D.n + LT - 1u) / LT;
@@ -497,7 +510,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_nb(program P, nb_dev_plan NP, batch
 
     const auto load_role = [&](std::uint32_t rd, std::uint32_t (&w)[8]) {
         uint4 a, b;
-        if (NP.roles_in_smem != 0u) {
+        if (roles_smem != 0u) {
             a = nbk::lds4u(roles_sa + rd * (TT * 32u));
             b = nbk::lds4u(roles_sa + rd * (TT * 32u) + 16u);
         } else {
@@ -512,16 +525,17 @@ __global__ void __launch_bounds__(MAXT, 1) k_nb(program P, nb_dev_plan NP, batch
         {
             const std::uint32_t la = lane0 + l0, lb = la + (NL - 1);
             const std::uint32_t ga = la < D.n ? la : D.n - 1u, gb = lb < D.n ? lb : D.n - 1u;
-            RM.lane_ok[0] = la < D.n;
+            // (A step with a skip mask leaves the lanes that are not running untouched, tc included.)
+            RM.lane_ok[0] = la < D.n && !(cv.mask_idle && S.running[l0] == 0);
             if constexpr (NL == 2) {
-                RM.lane_ok[1] = lb < D.n;
+                RM.lane_ok[1] = lb < D.n && !(cv.mask_idle && S.running[l0 + 1] == 0);
             }
             RM.ldelta = gb - ga;
             RM.state0 = D.state + ga;
             RM.cbase = cv.base + cv.lane_off(ga, l0);
         }
         RM.track = true;
-        for (std::uint32_t rd = 0; rd < NP.n_rounds; ++rd) {
+        for (std::uint32_t rd = 0; rd < n_rounds; ++rd) {
             std::uint32_t w[8];
             load_role(rd, w);
             nb::role_init<NL>(RM, w);
@@ -536,11 +550,11 @@ __global__ void __launch_bounds__(MAXT, 1) k_nb(program P, nb_dev_plan NP, batch
             }
             T::sync();
             RM.track = m + 2u >= n_blocks;
-            for (std::uint32_t rd = 0; rd < NP.n_rounds; ++rd) {
+            for (std::uint32_t rd = 0; rd < n_rounds; ++rd) {
                 std::uint32_t w[8];
                 load_role(rd, w);
                 nb::role_block<NL>(RM, w, m, p);
-                if (((NP.round_level_end >> rd) & 1u) != 0u) {
+                if (((level_end >> rd) & 1u) != 0u) {
                     T::sync();
                 }
             }
@@ -565,13 +579,15 @@ __global__ void __launch_bounds__(MAXT, 1) k_nb(program P, nb_dev_plan NP, batch
     for (std::uint32_t chunk = T::claim(R.counter); chunk < n_chunks; chunk = T::claim(R.counter)) {
         const std::uint32_t lane0 = chunk * LT;
         const std::uint32_t lane_raw = lane0 + tid;
-        const bool valid = owner && lane_raw < D.n;
+        bool valid = owner && lane_raw < D.n;
         const std::uint32_t lane = (owner && lane_raw < D.n) ? lane_raw : D.n - 1u;
 
         if constexpr (!PROP) {
             if (owner) {
+                const bool skipped = R.skip != nullptr && R.skip[lane] != 0u;
+                valid = valid && !skipped;
                 S.time[tid] = D.t_hi[lane];
-                S.running[tid] = 1;
+                S.running[tid] = skipped ? 0 : 1;
             }
             T::sync();
             jet(lane0);
@@ -628,6 +644,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_nb(program P, nb_dev_plan NP, batch
             }
             if (valid) {
                 park->store(D, lane);
+                park->report_iters(R);
             }
         }
         T::sync();

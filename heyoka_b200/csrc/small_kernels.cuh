@@ -15,6 +15,24 @@ __global__ void k_fill_outcome(long long *out, std::uint32_t n, long long value)
     }
 }
 
+// After propagate_until(): the lanes that were done before the last iteration (loop_len) of the reference's lock-step
+// loop took zero-length steps there (src/taylor_adaptive_batch.cpp:1372-1397): last_h = 0. Also prepares the masked
+// zero-length step that re-expands their Taylor coefficients (skip = 1 for the lanes to leave alone, limits = 0).
+__global__ void k_prop_early(const unsigned long long *iters, unsigned long long loop_len, std::uint32_t n,
+                             double *last_h, unsigned char *skip, double *zero_limits, unsigned *any_early)
+{
+    const std::uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const bool early = iters[i] < loop_len;
+        if (early) {
+            last_h[i] = 0.;
+            atomicOr(any_early, 1u);
+        }
+        skip[i] = early ? 0u : 1u;
+        zero_limits[i] = 0.;
+    }
+}
+
 // Dense output (src/taylor_01.cpp:1015-1185): Horner, or compensated summation in high-accuracy mode.
 __global__ void k_d_output(program P, std::uint32_t n, const double *tc, const double *tau, double *out)
 {

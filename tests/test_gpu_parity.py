@@ -279,6 +279,32 @@ def test_dense_output(kernel):
     assert rel_err(ta.update_d_output(-ta.last_h, rel_time=True), st) < 1e-15
 
 
+def test_propagate_early_lanes_last_h_and_tc(kernel):
+    """Lanes that reach their final time before the slowest lane take zero-length steps in the reference's lock-step
+    loop (src/taylor_adaptive_batch.cpp:1372-1397): on return last_h = 0 and, with write_tc, the Taylor coefficients
+    are re-expanded about the final state. The device-resident loop reproduces both (one masked zero-length step);
+    compared against the oracle's lock-step loop, then through update_d_output()."""
+    batch = 10
+    st = outer_ss_batch_state(batch)
+    tf = np.linspace(2.0, 11.0, batch)  # different numbers of steps per lane
+    P = hb.Program(sys_outer_ss(), high_accuracy=True)
+    for wtc in (True, False):
+        o = oracle.OracleIntegrator(P, st, batch, mode=oracle.FMA)
+        ta = hb.taylor_adaptive_batch(sys_outer_ss(), st, batch, high_accuracy=True, kernel=kernel)
+        o.propagate_until(tf, write_tc=wtc)
+        ta.propagate_until(tf, write_tc=wtc)
+        assert [r[3] for r in ta.propagate_res] == [int(x) for x in o.n_steps]
+        assert np.count_nonzero(o.last_h == 0.) >= batch - 3          # most lanes finished early
+        assert np.array_equal(ta.last_h == 0., o.last_h == 0.)
+        assert rel_err(ta.last_h, o.last_h, floor=1e-3) < 1e-11
+        assert lane_err(ta.state, o.state) < 1e-12
+        if wtc:
+            assert tc_err(ta.tc, o.tc, np.maximum(np.abs(o.last_h), 0.3)) < 1e-11
+            # Dense output at the current time reproduces the state for every lane (early ones included).
+            assert rel_err(ta.update_d_output(0., rel_time=True), ta.state) < 1e-13
+            assert rel_err(ta.update_d_output(tf), ta.state) < 1e-13
+
+
 def test_raw_program_interface_matches():
     """hy_program_create() from raw arrays gives the same results as the symbolic path."""
     P = hb.Program(sys_two_body())
@@ -306,9 +332,9 @@ def test_kernel_selection_info():
     b = hb.Batch(hb.Program(sys_outer_ss(), high_accuracy=True), 64)
     ki = b.kernel_info()
     # 15 pair interactions x 2 lanes, one per thread; r^2, d_z, r^-3 live in tensor memory as (even, odd) order pairs:
-    # 10 pairs x 12 columns; 16 warps of 2 lanes per SM.
+    # 10 pairs x 12 columns; 12 warps of 2 lanes per SM (168 registers per thread: no spills in the pair interaction).
     assert ki["tape"] == "nbody" and ki["lanes_per_warp"] == 2 and ki["tmem_cols_per_warp"] == 120
-    assert ki["block_threads"] == 512 and ki["smem_bytes"] <= 227 * 1024
+    assert ki["block_threads"] == 384 and ki["smem_bytes"] <= 227 * 1024
     b.set_kernel("nbody", lanes_per_thread=2)
     ki = b.kernel_info()
     assert ki["tape"] == "nbody" and ki["tmem_cols_per_warp"] == 0
