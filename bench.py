@@ -60,16 +60,26 @@ def measured_peaks():
 
 
 def measured_traffic(kernel_kind, lane_steps_per_launch):
-    """DRAM bytes per launch of the dominant kernel, from the committed `ncu --set full` capture: the capture
-    (profiles/r1_traffic.json, written by profiles/summarise_ncu.py) holds dram__bytes_read.sum + dram__bytes_write.sum
-    and the lane-steps of the profiled launch; the traffic of this kernel is proportional to the lane-steps."""
-    path = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    """DRAM bytes per launch of the dominant kernel from this round's committed `ncu --set full` capture
+    (profiles/r2_traffic.json, written by profiles/summarise_ncu.py: dram__bytes_read.sum + dram__bytes_write.sum, the
+    lane-steps of the profiled launch and the FP64 pipe utilisation); the kernel's DRAM traffic is proportional to the
+    lane-steps. Returns (bytes per launch, capture record) or (None, None)."""
+    path = os.path.join(ROOT, "profiles", "r2_traffic.json")
     try:
         with open(path) as f:
             t = json.load(f)[kernel_kind]
-        return float(t["dram_bytes"]) / float(t["lane_steps"]) * lane_steps_per_launch
+        return float(t["dram_bytes"]) / float(t["lane_steps"]) * lane_steps_per_launch, t
     except (OSError, KeyError, ValueError):
-        return None
+        return None, None
+
+
+def measured_fp64_peak():
+    """FP64 peak of the chip, measured by tools/fp64_peak.cu (dependency-free DFMA streams), profiles/r2_fp64_peak.json."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r2_fp64_peak.json")) as f:
+            return float(json.load(f)["dfma_tflops"]), "measured (tools/fp64_peak.cu)"
+    except (OSError, KeyError, ValueError):
+        return 37.0, "fallback"
 
 
 class ClockSampler:
@@ -287,8 +297,12 @@ def main():
     t_thi = as_tensor(ptrs.t_hi, n)
     t_tlo = as_tensor(ptrs.t_lo, n)
     t_nsteps = as_tensor(ptrs.prop_n_steps, n, torch.int64)
-
-    gather_buf = [torch.empty_like(t_state) for _ in range(world)] if world > 1 else None
+    # What the final gather moves: state, time hi / lo, last_h and the propagate results of every lane,
+    # packed into ONE buffer per rank (one all_gather over NVLink).
+    small = [t_thi, t_tlo, as_tensor(ptrs.last_h, n), as_tensor(ptrs.prop_min_h, n), as_tensor(ptrs.prop_max_h, n),
+             as_tensor(ptrs.prop_outcome, n, torch.int64).view(torch.float64), t_nsteps.view(torch.float64)]
+    pack = torch.empty((P.n_eq + len(small)) * n, dtype=torch.float64, device=dev) if world > 1 else None
+    gather_buf = torch.empty(world * (P.n_eq + len(small)) * n, dtype=torch.float64, device=dev) if world > 1 else None
 
     ev_k0, ev_k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     kernel_ms = []
@@ -305,8 +319,11 @@ def main():
             ev_k1.record(stream)
         assert flag == 0, "unexpected non-finite state / step limit"
         if world > 1:
-            # the only exchange of the path: gather of the final state
-            dist.all_gather(gather_buf, t_state)
+            # the only exchange of the path: gather of the final state, times, last_h and propagate results
+            pack[:P.n_eq * n].copy_(t_state)
+            for k, t in enumerate(small):
+                pack[(P.n_eq + k) * n:(P.n_eq + k + 1) * n].copy_(t)
+            dist.all_gather_into_tensor(gather_buf, pack)
         if timed:
             torch.cuda.synchronize()
             kernel_ms.append(ev_k0.elapsed_time(ev_k1))
@@ -396,6 +413,9 @@ def main():
         # roofline of the dominant kernel (k_propagate) on this rank: algorithmic bytes / launch duration
         ach = lane_steps_rank * costs["b_tape"] / (k_ms * 1e-3) / 1e9
         peak = float(peaks["hbm_gbs"])
+        traffic, capture = measured_traffic(kinfo["tape"], lane_steps_rank)
+        fp64_peak, fp64_peak_kind = measured_fp64_peak()
+        fp64_model = lane_steps_rank * costs["flops"] / (k_ms * 1e-3) / 1e12
         out = {
             "metric": "taylor_lane_steps_per_s", "value": value, "unit": "lane-steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps,
@@ -410,7 +430,18 @@ def main():
                 "parallelism": "lanes sharded across %d GPU(s), final-state all_gather" % world,
             },
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                         "traffic": measured_traffic(kinfo["tape"], lane_steps_rank), "peak_kind": peak_kind,
+                         "traffic": traffic, "peak_kind": peak_kind,
+                         # What really bounds the kernel: it moves ~20 B of DRAM traffic per lane-step (the tape lives
+                         # on chip), so the contract's B_tape figure above is an algorithmic equivalent; the binding
+                         # resources are the FP64 pipe and instruction issue.
+                         "true_bound": "fp64 pipe / instruction issue",
+                         "fp64_peak_tflops": fp64_peak, "fp64_peak_kind": fp64_peak_kind,
+                         "fp64_frac": fp64_model / fp64_peak,
+                         "fp64_pipe_pct": None if capture is None else capture.get("fp64_pipe_pct"),
+                         "warp_inst_per_lane_step": None if capture is None else capture.get("warp_inst_per_lane_step"),
+                         "dram_bytes_per_lane_step": None if capture is None
+                         else capture["dram_bytes"] / capture["lane_steps"],
+                         "capture": None if capture is None else capture.get("source"),
                          "kernel": ("k_nb<LT=%d,prop>" % kinfo["lanes_per_warp"]) if kinfo["tape"].startswith("nbody")
                          else ("k_coop<L=%d,N=%d,prop>" % (kinfo["lanes_per_warp"], kinfo["lanes_per_thread"])
                                if kinfo["tape"] == "smem" else "k_hbm<prop>"), "kernel_config": kinfo,
@@ -418,7 +449,7 @@ def main():
                          "b_min_bytes_per_lane_step": costs["b_min"],
                          "frac_b_min": lane_steps_rank * costs["b_min"] / (k_ms * 1e-3) / 1e9 / peak,
                          "model_flops_per_lane_step": costs["flops"],
-                         "fp64_tflops_model": lane_steps_rank * costs["flops"] / (k_ms * 1e-3) / 1e12},
+                         "fp64_tflops_model": fp64_model},
             "e2e": {"value": e2e_val, "unit": "lane-steps/s", "h2d_bytes_per_step": h2d * world,
                     "d2h_bytes_per_step": d2h * world, "ms_per_step": e2e_ms / n_e2e},
             "gpu_launches": launches_all,

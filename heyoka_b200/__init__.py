@@ -294,11 +294,22 @@ class Batch:
     """Device-resident integrator state + kernels (include/heyoka_b200.h, section C)."""
 
     def __init__(self, program, batch, device=-1):
+        """device: a CUDA ordinal (-1 = current device), or a list of ordinals / "all" to shard the lanes over several
+        GPUs of the box (hy_batch_create_multi(): contiguous blocks of lanes, one host thread per device)."""
         self.program = program
         self.n = int(batch)
         h = C.c_void_p()
-        check(lib.hy_batch_create(program._h, self.n, int(device), C.byref(h)))
+        if isinstance(device, str) or hasattr(device, "__len__"):
+            devs = [] if isinstance(device, str) else [int(d) for d in device]
+            arr = (C.c_int * len(devs))(*devs) if devs else None
+            check(lib.hy_batch_create_multi(program._h, self.n, arr, len(devs), C.byref(h)))
+        else:
+            check(lib.hy_batch_create(program._h, self.n, int(device), C.byref(h)))
         self._h = h
+
+    @property
+    def n_shards(self):
+        return lib.hy_batch_n_shards(self._h)
 
     def __del__(self):
         h = getattr(self, "_h", None)

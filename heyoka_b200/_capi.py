@@ -86,6 +86,9 @@ SIGNATURES = {
     "hy_batch_download_prop_res": (C.c_int, [_vp, C.POINTER(C.c_int64), _dp, _dp, C.POINTER(C.c_uint64)]),
     "hy_batch_download_tc": (C.c_int, [_vp, _dp]),
     "hy_batch_upload_tc": (C.c_int, [_vp, _dp]),
+    "hy_batch_create_multi": (C.c_int, [_vp, C.c_uint32, C.POINTER(C.c_int), C.c_uint32, C.POINTER(_vp)]),
+    "hy_batch_n_shards": (C.c_uint32, [_vp]),
+    "hy_device_count": (C.c_int, []),
     "hy_batch_get_ptrs": (C.c_int, [_vp, C.POINTER(hy_batch_ptrs)]),
     "hy_batch_step": (C.c_int, [_vp, _dp, C.c_int, C.c_int, C.c_int]),
     "hy_batch_propagate_until": (C.c_int, [_vp, _dp, _dp, _dp, C.c_uint64, C.c_int]),

@@ -13,6 +13,7 @@
 #include <new>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include <cuda_runtime.h>
@@ -260,6 +261,11 @@ struct hy_batch {
     std::uint32_t h_threads = 256, h_blocks_per_sm = 0, h_grid = 0;
     std::uint64_t n_launches = 0;
 
+    // Multi-device batch (hy_batch_create_multi()): the parent owns no device memory, only one single-device hy_batch
+    // per shard of contiguous lanes [shard_off[i], shard_off[i + 1]).
+    std::vector<hy_batch *> shards;
+    std::vector<std::uint32_t> shard_off;
+
     ~hy_batch();
     void free_all() noexcept;
     dev::batch view() const;
@@ -315,6 +321,12 @@ void hy_batch::free_all() noexcept
 
 hy_batch::~hy_batch()
 {
+    for (auto *sh : shards) {
+        delete sh;
+    }
+    if (!shards.empty()) {
+        return;
+    }
     int cur = 0;
     if (cudaGetDevice(&cur) == cudaSuccess) {
         cudaSetDevice(device);
@@ -1052,6 +1064,99 @@ int propagate_impl(hy_batch *b, const double *d_tf_hi, const double *d_tf_lo, co
 
 } // namespace
 
+// ------------------------------------------------------------------------------------------------
+// Multi-device batches: the lanes are independent ODE systems, so a batch shards over the GPUs of a box with no
+// data-path communication (src/ensemble_propagate.cpp:192-311 partitions its members over TBB threads the same way).
+// Every shard is a single-device hy_batch driven by its own host thread; host arrays are batch-innermost
+// ([row][batch]), so a shard's slice of a row is contiguous and the copies are pitched 2D copies. The only coupling is
+// the reference's GLOBAL exits of propagate_until() (non-finite state anywhere, iteration limit, length of the
+// lock-step loop), applied across the shards between the phases of propagate (see propagate_phase1()).
+// ------------------------------------------------------------------------------------------------
+namespace
+{
+
+template <typename F>
+void for_each_shard(hy_batch *b, F &&fn)
+{
+    const std::size_t ns = b->shards.size();
+    std::vector<std::exception_ptr> errs(ns);
+    std::vector<std::thread> thr;
+    thr.reserve(ns);
+    for (std::size_t i = 0; i < ns; ++i) {
+        thr.emplace_back([&, i] {
+            try {
+                hy_batch *sh = b->shards[i];
+                device_guard guard(sh->device);
+                fn(sh, i);
+            } catch (...) {
+                errs[i] = std::current_exception();
+            }
+        });
+    }
+    for (auto &t : thr) {
+        t.join();
+    }
+    for (const auto &e : errs) {
+        if (e) {
+            std::rethrow_exception(e);
+        }
+    }
+}
+
+// rows x (shard lanes) block of a host array with `pitch` elements per row, starting at column `off`.
+template <typename T>
+void rows_h2d(hy_batch *sh, T *dst, const T *src, std::size_t rows, std::size_t pitch, std::size_t off)
+{
+    if (src != nullptr && rows != 0u) {
+        HY_CUDA_CHECK(cudaMemcpy2DAsync(dst, sizeof(T) * sh->n, src + off, sizeof(T) * pitch, sizeof(T) * sh->n, rows,
+                                        cudaMemcpyHostToDevice, sh->stream));
+    }
+}
+template <typename T>
+void rows_d2h(hy_batch *sh, T *dst, const T *src, std::size_t rows, std::size_t pitch, std::size_t off)
+{
+    if (dst != nullptr && rows != 0u) {
+        HY_CUDA_CHECK(cudaMemcpy2DAsync(dst + off, sizeof(T) * pitch, src, sizeof(T) * sh->n, sizeof(T) * sh->n, rows,
+                                        cudaMemcpyDeviceToHost, sh->stream));
+    }
+}
+
+int multi_propagate(hy_batch *b, const double *tf_hi, const double *tf_lo, const double *mdt, uint64_t max_steps,
+                    int write_tc)
+{
+    const std::size_t ns = b->shards.size();
+    std::vector<prop_ctx> ctx(ns);
+    for_each_shard(b, [&](hy_batch *sh, std::size_t i) {
+        const std::size_t off = b->shard_off[i];
+        const double *d_hi = stage(sh, tf_hi + off, 0, 0);
+        const double *d_lo = stage(sh, tf_lo != nullptr ? tf_lo + off : nullptr, 0, 1);
+        const double *d_mdt = stage(sh, mdt != nullptr ? mdt + off : nullptr, 0, 2);
+        propagate_phase1(sh, d_hi, d_lo, d_mdt, max_steps, write_tc, ctx[i]);
+    });
+    bool any_nf = false;
+    unsigned long long cap = ~0ull;
+    for (const auto &c : ctx) {
+        if (c.fl.any_nf != 0u) {
+            any_nf = true;
+            cap = std::min(cap, c.fl.min_nf_iter);
+        }
+    }
+    if (any_nf) {
+        // Every lane of every shard stops at the first iteration in which any lane went non-finite.
+        for_each_shard(b, [&](hy_batch *sh, std::size_t i) { propagate_replay(sh, ctx[i], cap); });
+    }
+    bool any_limit = false;
+    unsigned long long loop_len = 0;
+    for (const auto &c : ctx) {
+        any_limit = any_limit || c.fl.any_limit != 0u;
+        loop_len = std::max(loop_len, c.fl.max_iter);
+    }
+    for_each_shard(b, [&](hy_batch *sh, std::size_t) { propagate_finish(sh, any_nf, any_limit, loop_len, write_tc); });
+    return HY_OK;
+}
+
+} // namespace
+
 extern "C" {
 
 int hy_batch_create(const hy_program *p, uint32_t batch, int device, hy_batch **out)
@@ -1193,6 +1298,70 @@ int hy_batch_create(const hy_program *p, uint32_t batch, int device, hy_batch **
     }
 }
 
+int hy_batch_create_multi(const hy_program *p, uint32_t batch, const int *devices, uint32_t n_devices, hy_batch **out)
+{
+    hy_batch *b = nullptr;
+    try {
+        if (p == nullptr || out == nullptr) {
+            throw std::invalid_argument("Null pointer passed to hy_batch_create_multi()");
+        }
+        int n_dev = 0;
+        if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) {
+            throw cuda_error("No usable CUDA device: heyoka_b200 has no CPU fallback");
+        }
+        std::vector<int> devs;
+        if (devices == nullptr || n_devices == 0u) {
+            for (int d = 0; d < n_dev; ++d) {
+                devs.push_back(d);
+            }
+        } else {
+            devs.assign(devices, devices + n_devices);
+        }
+        if (batch == 0u) {
+            throw std::invalid_argument("The batch size in an adaptive Taylor integrator cannot be zero");
+        }
+        // Contiguous blocks of lanes, as even as possible; never more shards than lanes.
+        const std::uint32_t ns = std::min<std::uint32_t>(static_cast<std::uint32_t>(devs.size()), batch);
+        b = new hy_batch;
+        b->n = batch;
+        b->n_eq = p->n_eq;
+        b->n_pars = p->n_pars;
+        b->order = p->order;
+        b->n_uvars = p->n_uvars;
+        b->high_accuracy = p->high_accuracy;
+        b->device = devs[0];
+        b->shard_off.push_back(0u);
+        for (std::uint32_t i = 0; i < ns; ++i) {
+            const std::uint32_t lanes = batch / ns + (i < batch % ns ? 1u : 0u);
+            hy_batch *sh = nullptr;
+            if (hy_batch_create(p, lanes, devs[i], &sh) != HY_OK) {
+                throw std::runtime_error(hy_last_error());
+            }
+            b->shards.push_back(sh);
+            b->shard_off.push_back(b->shard_off.back() + lanes);
+        }
+        *out = b;
+        return HY_OK;
+    } catch (...) {
+        delete b;
+        return translate_exception();
+    }
+}
+
+int hy_device_count(void)
+{
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess) {
+        return 0;
+    }
+    return n_dev;
+}
+
+uint32_t hy_batch_n_shards(const hy_batch *b)
+{
+    return b == nullptr ? 0u : static_cast<uint32_t>(b->shards.size());
+}
+
 void hy_batch_destroy(hy_batch *b)
 {
     delete b;
@@ -1200,6 +1369,10 @@ void hy_batch_destroy(hy_batch *b)
 
 int hy_batch_set_stream(hy_batch *b, void *cuda_stream)
 {
+    if (b != nullptr && !b->shards.empty()) {
+        hy::detail::set_last_error("hy_batch_set_stream() is not available on a multi-device batch");
+        return HY_ERR_INVALID_ARG;
+    }
     if (b == nullptr) {
         hy::detail::set_last_error("Null batch");
         return HY_ERR_INVALID_ARG;
@@ -1211,6 +1384,10 @@ int hy_batch_set_stream(hy_batch *b, void *cuda_stream)
 int hy_batch_sync(hy_batch *b)
 {
     try {
+        if (!b->shards.empty()) {
+            for_each_shard(b, [](hy_batch *sh, std::size_t) { HY_CUDA_CHECK(cudaStreamSynchronize(sh->stream)); });
+            return HY_OK;
+        }
         device_guard guard(b->device);
         HY_CUDA_CHECK(cudaStreamSynchronize(b->stream));
         return HY_OK;
@@ -1222,6 +1399,14 @@ int hy_batch_sync(hy_batch *b)
 int hy_batch_set_launch_config(hy_batch *b, uint32_t block_threads, uint32_t blocks_per_sm)
 {
     try {
+        if (!b->shards.empty()) {
+            for (auto *sh : b->shards) {
+                if (hy_batch_set_launch_config(sh, block_threads, blocks_per_sm) != HY_OK) {
+                    throw std::runtime_error(hy_last_error());
+                }
+            }
+            return HY_OK;
+        }
         device_guard guard(b->device);
         HY_CUDA_CHECK(cudaStreamSynchronize(b->stream));
         const int L = b->cv != nullptr && b->mode == 2 ? b->cv->L : 0;
@@ -1247,6 +1432,15 @@ int hy_batch_set_kernel(hy_batch *b, int tape_mode, uint32_t lanes_per_warp, uin
         if (tape_mode < 0 || tape_mode > 7) {
             throw std::invalid_argument("Invalid tape mode");
         }
+        if (!b->shards.empty()) {
+            for (auto *sh : b->shards) {
+                if (hy_batch_set_kernel(sh, tape_mode, lanes_per_warp, lanes_per_thread, block_threads, blocks_per_sm)
+                    != HY_OK) {
+                    throw std::invalid_argument(hy_last_error());
+                }
+            }
+            return HY_OK;
+        }
         device_guard guard(b->device);
         HY_CUDA_CHECK(cudaStreamSynchronize(b->stream));
         b->configure(tape_mode, static_cast<int>(lanes_per_warp), static_cast<int>(lanes_per_thread), block_threads,
@@ -1262,6 +1456,9 @@ int hy_batch_get_kernel(const hy_batch *b, hy_kernel_info *out)
     if (b == nullptr || out == nullptr) {
         hy::detail::set_last_error("Null pointer passed to hy_batch_get_kernel()");
         return HY_ERR_INVALID_ARG;
+    }
+    if (!b->shards.empty()) {
+        return hy_batch_get_kernel(b->shards[0], out); // (every shard runs the same kernel shape)
     }
     out->tape_mode = b->nb_on ? (b->c_cta ? 7 : 6) : (b->mode == 2 && b->c_global ? (b->c_cta ? 5 : 4) : b->mode);
     out->lanes_per_warp = b->mode == 2 ? static_cast<uint32_t>(b->cv->L) : 32u;
@@ -1286,6 +1483,17 @@ int hy_batch_get_kernel(const hy_batch *b, hy_kernel_info *out)
 int hy_batch_upload(hy_batch *b, const double *state, const double *pars, const double *t_hi, const double *t_lo)
 {
     try {
+        if (!b->shards.empty()) {
+            for_each_shard(b, [&](hy_batch *sh, std::size_t i) {
+                const std::size_t off = b->shard_off[i], n = b->n;
+                rows_h2d(sh, sh->d_state, state, sh->n_eq, n, off);
+                rows_h2d(sh, sh->d_pars, pars, sh->n_pars, n, off);
+                rows_h2d(sh, sh->d_t_hi, t_hi, 1u, n, off);
+                rows_h2d(sh, sh->d_t_lo, t_lo, 1u, n, off);
+                HY_CUDA_CHECK(cudaStreamSynchronize(sh->stream));
+            });
+            return HY_OK;
+        }
         device_guard guard(b->device);
         const std::size_t n = b->n;
         if (state != nullptr) {
@@ -1312,6 +1520,17 @@ int hy_batch_upload(hy_batch *b, const double *state, const double *pars, const 
 int hy_batch_download(hy_batch *b, double *state, double *t_hi, double *t_lo, double *last_h)
 {
     try {
+        if (!b->shards.empty()) {
+            for_each_shard(b, [&](hy_batch *sh, std::size_t i) {
+                const std::size_t off = b->shard_off[i], n = b->n;
+                rows_d2h(sh, state, sh->d_state, sh->n_eq, n, off);
+                rows_d2h(sh, t_hi, sh->d_t_hi, 1u, n, off);
+                rows_d2h(sh, t_lo, sh->d_t_lo, 1u, n, off);
+                rows_d2h(sh, last_h, sh->d_last_h, 1u, n, off);
+                HY_CUDA_CHECK(cudaStreamSynchronize(sh->stream));
+            });
+            return HY_OK;
+        }
         device_guard guard(b->device);
         const std::size_t n = b->n;
         if (state != nullptr) {
@@ -1337,6 +1556,15 @@ int hy_batch_download(hy_batch *b, double *state, double *t_hi, double *t_lo, do
 int hy_batch_download_step_res(hy_batch *b, int64_t *outcome, double *h)
 {
     try {
+        if (!b->shards.empty()) {
+            for_each_shard(b, [&](hy_batch *sh, std::size_t i) {
+                const std::size_t off = b->shard_off[i], n = b->n;
+                rows_d2h(sh, reinterpret_cast<long long *>(outcome), sh->d_step_outcome, 1u, n, off);
+                rows_d2h(sh, h, sh->d_last_h, 1u, n, off);
+                HY_CUDA_CHECK(cudaStreamSynchronize(sh->stream));
+            });
+            return HY_OK;
+        }
         device_guard guard(b->device);
         const std::size_t n = b->n;
         if (outcome != nullptr) {
@@ -1356,6 +1584,17 @@ int hy_batch_download_step_res(hy_batch *b, int64_t *outcome, double *h)
 int hy_batch_download_prop_res(hy_batch *b, int64_t *outcome, double *min_h, double *max_h, uint64_t *n_steps)
 {
     try {
+        if (!b->shards.empty()) {
+            for_each_shard(b, [&](hy_batch *sh, std::size_t i) {
+                const std::size_t off = b->shard_off[i], n = b->n;
+                rows_d2h(sh, reinterpret_cast<long long *>(outcome), sh->d_prop_outcome, 1u, n, off);
+                rows_d2h(sh, min_h, sh->d_prop_min_h, 1u, n, off);
+                rows_d2h(sh, max_h, sh->d_prop_max_h, 1u, n, off);
+                rows_d2h(sh, reinterpret_cast<unsigned long long *>(n_steps), sh->d_prop_n_steps, 1u, n, off);
+                HY_CUDA_CHECK(cudaStreamSynchronize(sh->stream));
+            });
+            return HY_OK;
+        }
         device_guard guard(b->device);
         const std::size_t n = b->n;
         if (outcome != nullptr) {
@@ -1384,6 +1623,14 @@ int hy_batch_download_prop_res(hy_batch *b, int64_t *outcome, double *min_h, dou
 int hy_batch_download_tc(hy_batch *b, double *tc)
 {
     try {
+        if (!b->shards.empty()) {
+            for_each_shard(b, [&](hy_batch *sh, std::size_t i) {
+                sh->ensure_tc();
+                rows_d2h(sh, tc, sh->d_tc, static_cast<std::size_t>(sh->n_eq) * (sh->order + 1u), b->n, b->shard_off[i]);
+                HY_CUDA_CHECK(cudaStreamSynchronize(sh->stream));
+            });
+            return HY_OK;
+        }
         device_guard guard(b->device);
         const std::size_t sz = static_cast<std::size_t>(b->n_eq) * (b->order + 1u) * b->n;
         b->ensure_tc();
@@ -1401,6 +1648,14 @@ int hy_batch_upload_tc(hy_batch *b, const double *tc)
         if (b == nullptr || tc == nullptr) {
             throw std::invalid_argument("Null pointer passed to hy_batch_upload_tc()");
         }
+        if (!b->shards.empty()) {
+            for_each_shard(b, [&](hy_batch *sh, std::size_t i) {
+                sh->ensure_tc();
+                rows_h2d(sh, sh->d_tc, tc, static_cast<std::size_t>(sh->n_eq) * (sh->order + 1u), b->n, b->shard_off[i]);
+                HY_CUDA_CHECK(cudaStreamSynchronize(sh->stream));
+            });
+            return HY_OK;
+        }
         device_guard guard(b->device);
         b->ensure_tc();
         const std::size_t sz = static_cast<std::size_t>(b->n_eq) * (b->order + 1u) * b->n;
@@ -1414,6 +1669,10 @@ int hy_batch_upload_tc(hy_batch *b, const double *tc)
 
 int hy_batch_get_ptrs(hy_batch *b, hy_batch_ptrs *out)
 {
+    if (b != nullptr && !b->shards.empty()) {
+        hy::detail::set_last_error("hy_batch_get_ptrs() is not available on a multi-device batch: use the shards");
+        return HY_ERR_INVALID_ARG;
+    }
     if (b == nullptr || out == nullptr) {
         hy::detail::set_last_error("Null pointer passed to hy_batch_get_ptrs()");
         return HY_ERR_INVALID_ARG;
@@ -1436,6 +1695,19 @@ int hy_batch_get_ptrs(hy_batch *b, hy_batch_ptrs *out)
 int hy_batch_step(hy_batch *b, const double *max_delta_t, int on_device, int backward, int write_tc)
 {
     try {
+        if (!b->shards.empty()) {
+            if (on_device) {
+                throw std::invalid_argument("Device-resident step limits are not available on a multi-device batch");
+            }
+            for_each_shard(b, [&](hy_batch *sh, std::size_t i) {
+                if (hy_batch_step(sh, max_delta_t != nullptr ? max_delta_t + b->shard_off[i] : nullptr, 0, backward,
+                                  write_tc)
+                    != HY_OK) {
+                    throw std::invalid_argument(hy_last_error());
+                }
+            });
+            return HY_OK;
+        }
         device_guard guard(b->device);
         if (max_delta_t != nullptr && !on_device) {
             // step(max_delta_ts): NaN limits are rejected (src/taylor_adaptive_batch.cpp:1060-1075).
@@ -1485,6 +1757,9 @@ int hy_batch_propagate_until(hy_batch *b, const double *t_final_hi, const double
                 }
             }
         }
+        if (!b->shards.empty()) {
+            return multi_propagate(b, t_final_hi, t_final_lo, max_delta_t, max_steps, write_tc);
+        }
         const double *d_hi = stage(b, t_final_hi, 0, 0);
         const double *d_lo = stage(b, t_final_lo, 0, 1);
         const double *d_mdt = stage(b, max_delta_t, 0, 2);
@@ -1498,6 +1773,9 @@ int hy_batch_propagate_until_dev(hy_batch *b, const double *d_t_final_hi, const 
                                  const double *d_max_delta_t, uint64_t max_steps, int write_tc, int *any_nf_or_limit)
 {
     try {
+        if (!b->shards.empty()) {
+            throw std::invalid_argument("hy_batch_propagate_until_dev() is not available on a multi-device batch");
+        }
         device_guard guard(b->device);
         if (d_t_final_hi == nullptr) {
             throw std::invalid_argument("Null final times passed to hy_batch_propagate_until_dev()");
@@ -1530,6 +1808,9 @@ int hy_batch_propagate_grid(hy_batch *b, const double *grid, uint64_t n_pts, con
     try {
         if (b == nullptr || grid == nullptr || out == nullptr) {
             throw std::invalid_argument("Null pointer passed to hy_batch_propagate_grid()");
+        }
+        if (!b->shards.empty()) {
+            throw hy::detail::not_implemented_error("propagate_grid() is not available on a multi-device batch");
         }
         device_guard guard(b->device);
         const std::uint32_t n = b->n;
@@ -1751,6 +2032,9 @@ int hy_batch_propagate_until_cout(hy_batch *b, const double *t_final_hi, const d
         }
     };
     try {
+        if (b != nullptr && !b->shards.empty()) {
+            throw hy::detail::not_implemented_error("Continuous output is not available on a multi-device batch");
+        }
         if (b == nullptr || t_final_hi == nullptr || out == nullptr) {
             throw std::invalid_argument("Null pointer passed to hy_batch_propagate_until_cout()");
         }
@@ -1955,6 +2239,19 @@ void hy_cout_destroy(hy_cout *c)
 int hy_batch_d_output(hy_batch *b, const double *tau, double *out)
 {
     try {
+        if (!b->shards.empty()) {
+            for_each_shard(b, [&](hy_batch *sh, std::size_t i) {
+                const double *d_tau = stage(sh, tau + b->shard_off[i], 0, 0);
+                sh->ensure_tc();
+                dev::k_d_output<<<(sh->n + 127u) / 128u, 128, 0, sh->stream>>>(sh->prog, sh->n, sh->d_tc, d_tau,
+                                                                              sh->d_d_out);
+                HY_CUDA_CHECK(cudaGetLastError());
+                ++sh->n_launches;
+                rows_d2h(sh, out, sh->d_d_out, sh->n_eq, b->n, b->shard_off[i]);
+                HY_CUDA_CHECK(cudaStreamSynchronize(sh->stream));
+            });
+            return HY_OK;
+        }
         device_guard guard(b->device);
         const double *d_tau = stage(b, tau, 0, 0);
         b->ensure_tc();
@@ -1979,6 +2276,9 @@ int hy_batch_launch_count(const hy_batch *b, uint64_t *n_launches)
         return HY_ERR_INVALID_ARG;
     }
     *n_launches = b->n_launches;
+    for (const auto *sh : b->shards) {
+        *n_launches += sh->n_launches;
+    }
     return HY_OK;
 }
 

@@ -6,8 +6,10 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <exception>
 #include <limits>
 #include <string>
+#include <thread>
 
 #include "program.hpp"
 
@@ -96,6 +98,7 @@ struct taylor_adaptive_batch<double>::impl {
     double tol = 0;
     bool high_accuracy = false, compact_mode = false;
     int device = -1;
+    std::vector<int> devices; // non-empty: sharded over these GPUs (hy_batch_create_multi())
     int tape_mode = 0;
     std::uint32_t k_lpw = 0, k_lpt = 0, k_threads = 0, k_bpsm = 0;
 
@@ -111,7 +114,7 @@ struct taylor_adaptive_batch<double>::impl {
     impl() = default;
     impl(const impl &o)
         : sys(o.sys), dc(o.dc), prog(o.prog), batch_size(o.batch_size), dim(o.dim), order(o.order), n_pars(o.n_pars),
-          tol(o.tol), high_accuracy(o.high_accuracy), compact_mode(o.compact_mode), device(o.device),
+          tol(o.tol), high_accuracy(o.high_accuracy), compact_mode(o.compact_mode), device(o.device), devices(o.devices),
           tape_mode(o.tape_mode), k_lpw(o.k_lpw), k_lpt(o.k_lpt), k_threads(o.k_threads), k_bpsm(o.k_bpsm),
           state(o.state), pars(o.pars), time_hi(o.time_hi), time_lo(o.time_lo), tc(o.tc), last_h(o.last_h),
           d_out(o.d_out), step_res(o.step_res), prop_res(o.prop_res), oc(o.oc), tmp_a(o.tmp_a), tmp_b(o.tmp_b),
@@ -131,7 +134,12 @@ struct taylor_adaptive_batch<double>::impl {
     }
     void make_batch()
     {
-        check(hy_batch_create(prog.get(), batch_size, device, &batch));
+        if (devices.empty()) {
+            check(hy_batch_create(prog.get(), batch_size, device, &batch));
+        } else {
+            check(hy_batch_create_multi(prog.get(), batch_size, devices.data(), static_cast<std::uint32_t>(devices.size()),
+                                        &batch));
+        }
         if (tape_mode != 0 || k_lpw != 0 || k_lpt != 0 || k_threads != 0 || k_bpsm != 0) {
             check(hy_batch_set_kernel(batch, tape_mode, k_lpw, k_lpt, k_threads, k_bpsm));
         }
@@ -193,6 +201,7 @@ void taylor_adaptive_batch<double>::finalise_ctor(std::vector<std::pair<expressi
     m.high_accuracy = o.high_accuracy;
     m.compact_mode = o.compact_mode;
     m.device = o.device;
+    m.devices = o.devices;
 
     if (batch_size == 0u) {
         throw std::invalid_argument("The batch size in an adaptive Taylor integrator cannot be zero");
@@ -432,6 +441,85 @@ hy_batch *taylor_adaptive_batch<double>::get_device_batch()
 {
     return m_impl->batch;
 }
+int taylor_adaptive_batch<double>::get_device() const
+{
+    return m_impl->device;
+}
+// Re-creates the device-resident batch on another GPU (or sharded over several); the host mirrors are the master
+// copy of state / parameters / time, the Taylor coefficients of the last step are restored if they were valid.
+void taylor_adaptive_batch<double>::set_devices(const std::vector<int> &devices)
+{
+    auto &m = *m_impl;
+    if (devices == m.devices && (!devices.empty() || m.batch != nullptr)) {
+        return;
+    }
+    hy_batch_destroy(m.batch);
+    m.batch = nullptr;
+    m.devices = devices;
+    m.make_batch();
+    if (m.tc_valid) {
+        check(hy_batch_upload_tc(m.batch, m.tc.data()));
+    }
+}
+void taylor_adaptive_batch<double>::set_device(int device)
+{
+    auto &m = *m_impl;
+    if (m.devices.empty() && (device == m.device || device < 0)) {
+        return;
+    }
+    hy_batch_destroy(m.batch);
+    m.batch = nullptr;
+    m.devices.clear();
+    m.device = device;
+    m.make_batch();
+    if (m.tc_valid) {
+        check(hy_batch_upload_tc(m.batch, m.tc.data()));
+    }
+}
+
+namespace detail
+{
+
+int ensemble_device_count()
+{
+    return hy_device_count();
+}
+
+void ensemble_for_each(std::size_t n_iter, const std::function<void(std::size_t, int)> &fn)
+{
+    const int n_dev = std::max(1, ensemble_device_count());
+    const std::size_t n_workers = std::min<std::size_t>(static_cast<std::size_t>(n_dev), n_iter);
+    if (n_workers <= 1u) {
+        for (std::size_t i = 0; i < n_iter; ++i) {
+            fn(i, -1);
+        }
+        return;
+    }
+    std::vector<std::exception_ptr> errs(n_workers);
+    std::vector<std::thread> thr;
+    for (std::size_t w = 0; w < n_workers; ++w) {
+        thr.emplace_back([&, w] {
+            try {
+                for (std::size_t i = w; i < n_iter; i += n_workers) {
+                    fn(i, static_cast<int>(w));
+                }
+            } catch (...) {
+                errs[w] = std::current_exception();
+            }
+        });
+    }
+    for (auto &t : thr) {
+        t.join();
+    }
+    for (const auto &e : errs) {
+        if (e) {
+            std::rethrow_exception(e);
+        }
+    }
+}
+
+} // namespace detail
+
 void taylor_adaptive_batch<double>::set_kernel(int tape_mode, std::uint32_t lpw, std::uint32_t lpt,
                                                std::uint32_t threads, std::uint32_t bpsm)
 {

@@ -197,6 +197,14 @@ typedef struct hy_batch hy_batch;
 
 /* device < 0: current CUDA device. Allocates state, pars, time (hi/lo), last_h, results, tc, scratch. */
 int hy_batch_create(const hy_program *, uint32_t batch, int device, hy_batch **out);
+/* The same object sharded over several devices of the box: contiguous blocks of lanes, one per device (devices == NULL:
+ * every visible device), each driven by its own host thread; lanes are independent, so the results are bit-identical to
+ * a single-device batch, including the reference's global exits of propagate_until(). This is what
+ * src/ensemble_propagate.cpp:192-311 does with TBB threads. Every hy_batch_* function takes the result except
+ * hy_batch_get_ptrs / _set_stream / _propagate_until_dev / _propagate_grid / _propagate_until_cout. */
+int hy_batch_create_multi(const hy_program *, uint32_t batch, const int *devices, uint32_t n_devices, hy_batch **out);
+uint32_t hy_batch_n_shards(const hy_batch *); /* 0 for a single-device batch */
+int hy_device_count(void);                    /* usable CUDA devices (0 if none) */
 void hy_batch_destroy(hy_batch *);
 /* cudaStream_t on which copies and kernels are enqueued (default: the legacy default stream). */
 int hy_batch_set_stream(hy_batch *, void *cuda_stream);

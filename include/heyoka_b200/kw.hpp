@@ -143,6 +143,8 @@ HEYOKA_B200_KWARG(activations);
 HEYOKA_B200_KWARG(nn_wb);
 // Device selection (extension: which GPU owns the batch; default: the current device).
 HEYOKA_B200_KWARG(device);
+// Sharding (extension): the GPUs the lanes of the batch are split over (contiguous blocks, hy_batch_create_multi()).
+HEYOKA_B200_KWARG(devices);
 
 #undef HEYOKA_B200_KWARG
 

@@ -112,6 +112,7 @@ private:
         std::vector<double> pars;
         bool with_events = false;
         int device = -1;
+        std::vector<int> devices; // non-empty: the batch is sharded over these GPUs
     };
     struct prop_opts {
         std::size_t max_steps = 0;
@@ -135,7 +136,7 @@ private:
                                        kw::pars_tag, kw::parallel_mode_tag, kw::parjit_tag, kw::t_events_tag,
                                        kw::nt_events_tag, kw::opt_level_tag, kw::fast_math_tag, kw::force_avx512_tag,
                                        kw::slp_vectorize_tag, kw::mname_tag, kw::code_model_tag,
-                                       kw::device_tag>::template all<KwArgs...>(),
+                                       kw::device_tag, kw::devices_tag>::template all<KwArgs...>(),
                       "Invalid named argument(s) in the construction of a taylor_adaptive_batch");
         ctor_opts o;
         kw::visit(
@@ -154,6 +155,7 @@ private:
         kw::visit(kw::compact_mode, [&o](const auto &v) { o.compact_mode = static_cast<bool>(v); }, kw_args...);
         kw::visit(kw::pars, [&o](const auto &v) { o.pars.assign(std::begin(v), std::end(v)); }, kw_args...);
         kw::visit(kw::device, [&o](const auto &v) { o.device = static_cast<int>(v); }, kw_args...);
+        kw::visit(kw::devices, [&o](const auto &v) { o.devices.assign(std::begin(v), std::end(v)); }, kw_args...);
         o.with_events = kw::has_tag<kw::t_events_tag, KwArgs...>() || kw::has_tag<kw::nt_events_tag, KwArgs...>();
         return o;
     }
@@ -278,8 +280,12 @@ public:
     [[nodiscard]] const std::vector<std::tuple<taylor_outcome, double, double, std::size_t>> &
     get_propagate_res() const;
 
-    // Extensions: the device-resident batch behind this integrator, and kernel selection.
+    // Extensions: the device-resident batch behind this integrator, device placement and kernel selection.
     [[nodiscard]] hy_batch *get_device_batch();
+    // Moves the integrator to another GPU / shards it over several GPUs (the device buffers are re-created there).
+    void set_device(int device);
+    void set_devices(const std::vector<int> &devices);
+    [[nodiscard]] int get_device() const;
     void set_kernel(int tape_mode, std::uint32_t lanes_per_warp = 0, std::uint32_t lanes_per_thread = 0,
                     std::uint32_t block_threads = 0, std::uint32_t blocks_per_sm = 0);
 
@@ -293,9 +299,22 @@ private:
 // ------------------------------------------------------------------------------------------------
 // Ensemble propagation (include/heyoka/ensemble_propagate.hpp:220-269, src/ensemble_propagate.cpp:192-311):
 // n_iter independent copies of an integrator, each customised by gen(ta, i), propagated and returned. The
-// reference runs them under TBB; here every member is a device-resident batch and members are launched one
-// after the other on the GPU(s) (members may be placed on different devices through gen()).
+// reference runs the members under TBB; here the members are dealt out round-robin to the visible GPUs and every GPU
+// is driven by its own host thread (member i lives on device i mod n_devices), so the members of different devices
+// run concurrently. Like in the reference, gen() may be called concurrently and the results do not depend on the
+// partitioning (test/ensemble_propagate.cpp:413-431).
 // ------------------------------------------------------------------------------------------------
+namespace detail
+{
+
+// Number of usable CUDA devices (hy_device_count()).
+int ensemble_device_count();
+
+// Runs fn(i, device) for i in [0, n_iter), one worker thread per device; rethrows the first exception.
+void ensemble_for_each(std::size_t n_iter, const std::function<void(std::size_t, int)> &fn);
+
+} // namespace detail
+
 template <typename... KwArgs>
 std::vector<std::tuple<taylor_adaptive_batch<double>, std::optional<continuous_output_batch<double>>,
                        step_callback_batch<double>>>
@@ -304,14 +323,19 @@ ensemble_propagate_until_batch(
     const std::function<taylor_adaptive_batch<double>(taylor_adaptive_batch<double>, std::size_t)> &gen,
     const KwArgs &...kw_args)
 {
-    std::vector<std::tuple<taylor_adaptive_batch<double>, std::optional<continuous_output_batch<double>>,
-                           step_callback_batch<double>>>
-        retval;
-    retval.reserve(n_iter);
-    for (std::size_t i = 0; i < n_iter; ++i) {
+    using member_t = std::tuple<taylor_adaptive_batch<double>, std::optional<continuous_output_batch<double>>,
+                                step_callback_batch<double>>;
+    std::vector<std::optional<member_t>> tmp(n_iter);
+    detail::ensemble_for_each(n_iter, [&](std::size_t i, int device) {
         auto local_ta = gen(ta, i);
+        local_ta.set_device(device);
         auto res = local_ta.propagate_until(t, kw_args...);
-        retval.emplace_back(std::move(local_ta), std::move(std::get<0>(res)), std::move(std::get<1>(res)));
+        tmp[i].emplace(std::move(local_ta), std::move(std::get<0>(res)), std::move(std::get<1>(res)));
+    });
+    std::vector<member_t> retval;
+    retval.reserve(n_iter);
+    for (auto &m : tmp) {
+        retval.push_back(std::move(*m));
     }
     return retval;
 }
@@ -324,14 +348,19 @@ ensemble_propagate_for_batch(
     const std::function<taylor_adaptive_batch<double>(taylor_adaptive_batch<double>, std::size_t)> &gen,
     const KwArgs &...kw_args)
 {
-    std::vector<std::tuple<taylor_adaptive_batch<double>, std::optional<continuous_output_batch<double>>,
-                           step_callback_batch<double>>>
-        retval;
-    retval.reserve(n_iter);
-    for (std::size_t i = 0; i < n_iter; ++i) {
+    using member_t = std::tuple<taylor_adaptive_batch<double>, std::optional<continuous_output_batch<double>>,
+                                step_callback_batch<double>>;
+    std::vector<std::optional<member_t>> tmp(n_iter);
+    detail::ensemble_for_each(n_iter, [&](std::size_t i, int device) {
         auto local_ta = gen(ta, i);
+        local_ta.set_device(device);
         auto res = local_ta.propagate_for(delta_t, kw_args...);
-        retval.emplace_back(std::move(local_ta), std::move(std::get<0>(res)), std::move(std::get<1>(res)));
+        tmp[i].emplace(std::move(local_ta), std::move(std::get<0>(res)), std::move(std::get<1>(res)));
+    });
+    std::vector<member_t> retval;
+    retval.reserve(n_iter);
+    for (auto &m : tmp) {
+        retval.push_back(std::move(*m));
     }
     return retval;
 }
@@ -351,12 +380,18 @@ ensemble_propagate_grid_batch(
     for (const auto gval : grid_) {
         grid.insert(grid.end(), batch_size, gval);
     }
-    std::vector<std::tuple<taylor_adaptive_batch<double>, step_callback_batch<double>, std::vector<double>>> retval;
-    retval.reserve(n_iter);
-    for (std::size_t i = 0; i < n_iter; ++i) {
+    using member_t = std::tuple<taylor_adaptive_batch<double>, step_callback_batch<double>, std::vector<double>>;
+    std::vector<std::optional<member_t>> tmp(n_iter);
+    detail::ensemble_for_each(n_iter, [&](std::size_t i, int device) {
         auto local_ta = gen(ta, i);
+        local_ta.set_device(device);
         auto res = local_ta.propagate_grid(grid, kw_args...);
-        retval.emplace_back(std::move(local_ta), std::move(std::get<0>(res)), std::move(std::get<1>(res)));
+        tmp[i].emplace(std::move(local_ta), std::move(std::get<0>(res)), std::move(std::get<1>(res)));
+    });
+    std::vector<member_t> retval;
+    retval.reserve(n_iter);
+    for (auto &m : tmp) {
+        retval.push_back(std::move(*m));
     }
     return retval;
 }

@@ -4,7 +4,8 @@
     python profiles/summarise_ncu.py gpurun_out/X.ncu-rep --name r1_coop_final --kind smem --lane-steps 1234567
 
 Writes profiles/<name>_summary.csv (selected metrics of every profiled launch) and, when --lane-steps is given,
-records DRAM bytes / lane-steps of the first launch in profiles/r1_traffic.json under <kind> (read by bench.py for
+records DRAM bytes / lane-steps (+ FP64 pipe utilisation, instructions per lane-step) of the first launch in
+profiles/r2_traffic.json under <kind> (read by bench.py for
 roofline.traffic). Needs only the `ncu` CLI (no GPU)."""
 import argparse
 import csv
@@ -57,6 +58,7 @@ def main():
     ap.add_argument("--kind", default=None, help="smem | hbm: key in r1_traffic.json")
     ap.add_argument("--lane-steps", type=float, default=0.0)
     ap.add_argument("--note", default="")
+    ap.add_argument("--traffic-file", default="r2_traffic.json")
     a = ap.parse_args()
 
     raw = subprocess.run(["ncu", "-i", a.report, "--page", "raw", "--csv"], check=True, capture_output=True,
@@ -80,14 +82,25 @@ def main():
         r = data[0]
         rd = to_bytes(r[col["dram__bytes_read.sum"]], units[col["dram__bytes_read.sum"]])
         wr = to_bytes(r[col["dram__bytes_write.sum"]], units[col["dram__bytes_write.sum"]])
-        tpath = os.path.join(HERE, "r1_traffic.json")
+        tpath = os.path.join(HERE, a.traffic_file)
         t = {}
         if os.path.exists(tpath):
             with open(tpath) as f:
                 t = json.load(f)
+        def num(name):
+            try:
+                return float(r[col[name]].replace(",", ""))
+            except (KeyError, ValueError):
+                return None
+
+        insts = num("smsp__inst_executed.sum")
         t[a.kind] = {"dram_bytes": rd + wr, "dram_bytes_read": rd, "dram_bytes_write": wr, "lane_steps": a.lane_steps,
                      "bytes_per_lane_step": (rd + wr) / a.lane_steps, "kernel": r[col["Kernel Name"]][:80],
-                     "report": os.path.basename(a.report), "note": a.note}
+                     "fp64_pipe_pct": num("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"),
+                     "issue_active": num("smsp__issue_active.avg.per_cycle_active"),
+                     "warp_inst_per_lane_step": None if insts is None else insts / a.lane_steps,
+                     "kernel_ms": num("gpu__time_duration.sum"),
+                     "source": "profiles/%s_summary.csv (%s)" % (a.name, os.path.basename(a.report)), "note": a.note}
         with open(tpath, "w") as f:
             json.dump(t, f, indent=1)
         print("updated", tpath, t[a.kind]["bytes_per_lane_step"], "B/lane-step")

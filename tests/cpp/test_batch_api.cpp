@@ -213,6 +213,52 @@ static void test_ensemble()
     }
 }
 
+// Sharding over devices (kw::devices, set_device()): the lanes of one integrator split over several device-resident
+// batches, bit-identical to the unsharded integrator; copies and moves between devices keep state, time and tc.
+static void test_sharded_and_placement()
+{
+    const std::vector<double> masses{1.00000597682, 1 / 1047.355, 1 / 3501.6, 1 / 22869., 1 / 19314., 7.4074074e-09};
+    const double G = 0.01720209895 * 0.01720209895 * 365 * 365;
+    auto sys = model::nbody(6, kw::masses = masses, kw::Gconst = G);
+    const std::uint32_t B = 7u;
+    std::vector<double> st(36u * B);
+    for (std::size_t i = 0; i < st.size(); ++i) {
+        st[i] = 0.1 + 0.37 * static_cast<double>((i * 7919u) % 101u) / 101.;
+    }
+    taylor_adaptive_batch<double> one{sys, st, B, kw::high_accuracy = true};
+    taylor_adaptive_batch<double> many{sys, st, B, kw::high_accuracy = true, kw::devices = std::vector<int>{0, 0, 0}};
+    REQUIRE(hy_batch_n_shards(many.get_device_batch()) == 3u);
+    one.step(true);
+    many.step(true);
+    REQUIRE(one.get_state() == many.get_state());
+    REQUIRE(one.get_tc() == many.get_tc());
+    REQUIRE(one.get_last_h() == many.get_last_h());
+    std::vector<double> tf(B);
+    for (std::uint32_t i = 0; i < B; ++i) {
+        tf[i] = 1. + 0.7 * i;
+    }
+    one.propagate_until(tf);
+    many.propagate_until(tf);
+    REQUIRE(one.get_state() == many.get_state());
+    REQUIRE(one.get_time() == many.get_time());
+    REQUIRE(one.get_last_h() == many.get_last_h());
+    REQUIRE(one.get_propagate_res() == many.get_propagate_res());
+    // A copy of a sharded integrator is sharded the same way and serves dense output right away (tc is copied).
+    many.step(true);
+    auto cp = many;
+    REQUIRE(hy_batch_n_shards(cp.get_device_batch()) == 3u);
+    REQUIRE(cp.update_d_output(0., true) == many.update_d_output(0., true));
+    for (std::size_t i = 0; i < st.size(); ++i) {
+        REQUIRE(approx(cp.get_d_output()[i], many.get_state()[i], 100.));
+    }
+    // Back to one device.
+    cp.set_device(0);
+    REQUIRE(hy_batch_n_shards(cp.get_device_batch()) == 0u);
+    cp.step();
+    many.step();
+    REQUIRE(cp.get_state() == many.get_state());
+}
+
 // test/ensemble_propagate.cpp ("batch grid"): every member of a grid ensemble equals its own sequential run.
 static void test_ensemble_grid()
 {
@@ -431,6 +477,7 @@ int main(int argc, char **argv)
         test_propagate_grid();
         test_continuous_output();
         test_ensemble_grid();
+        test_sharded_and_placement();
     }
     if (n_fail == 0) {
         std::printf("ALL PASSED (%s)\n", gpu ? "gpu" : "cpu");
