@@ -1,6 +1,9 @@
 // Model builders: see include/heyoka_b200/model.hpp for the reference map.
 #include <heyoka_b200/model.hpp>
 
+#include <algorithm>
+#include <array>
+#include <iterator>
 #include <stdexcept>
 #include <string>
 
@@ -26,92 +29,81 @@ void nbody_checks(std::uint32_t n, const std::vector<expression> &masses_vec)
 
 } // namespace
 
-// State variable order: x_i, y_i, z_i, vx_i, vy_i, vz_i for each body (massive bodies first).
-// Pair interactions use r**-3 = pow(sum(dx**2, dy**2, dz**2), -3/2); when G and m_j are numbers
-// the j->i acceleration is computed once and the i->j one obtained by a constant rescaling
-// (src/model/nbody.cpp:97-153).
+// The N-body right-hand side. What must match the reference (src/model/nbody.cpp:52-173) is the EXPRESSION that comes
+// out - operand order and association decide the decomposition - not how it is assembled. Here: a table of state
+// variables indexed [body][axis], one pass over the ordered pairs (i < j, i massive) that appends each pair's
+// contribution to the acceleration lists of its two bodies, then one pass over the bodies that emits the six
+// equations of each. Per pair, with d = r_j - r_i and q = |d|^-3 = pow(sum(d_x^2, d_y^2, d_z^2), -3/2):
+//   * "rescaled" form, when G and a non-zero m_j are numbers: a_i += d (G m_j q), a_j += (d (G m_j q)) (-m_i / m_j)
+//     (the second product reuses the first one: one convolution per axis and pair instead of two);
+//   * general form: a_j += d (-m_i (G q)) and, if j is massive, a_i += d (m_j (G q)).
 std::vector<std::pair<expression, expression>> nbody_impl(std::uint32_t n, const expression &Gconst,
                                                           const std::vector<expression> &masses_vec)
 {
     nbody_checks(n, masses_vec);
+    const auto n_massive = static_cast<std::uint32_t>(masses_vec.size());
+    constexpr const char *axis_name[3] = {"x", "y", "z"};
 
-    std::vector<expression> x_vars, y_vars, z_vars, vx_vars, vy_vars, vz_vars;
-    for (std::uint32_t i = 0; i < n; ++i) {
-        const auto s = std::to_string(i);
-        x_vars.emplace_back(variable{"x_" + s});
-        y_vars.emplace_back(variable{"y_" + s});
-        z_vars.emplace_back(variable{"z_" + s});
-        vx_vars.emplace_back(variable{"vx_" + s});
-        vy_vars.emplace_back(variable{"vy_" + s});
-        vz_vars.emplace_back(variable{"vz_" + s});
+    // pos[b][a], vel[b][a]; acc[b][a] = the terms of the acceleration of body b along axis a.
+    std::vector<std::array<expression, 3>> pos(n), vel(n);
+    std::vector<std::array<std::vector<expression>, 3>> acc(n);
+    for (std::uint32_t b = 0; b < n; ++b) {
+        for (int a = 0; a < 3; ++a) {
+            const auto suffix = "_" + std::to_string(b);
+            pos[b][a] = expression{variable{axis_name[a] + suffix}};
+            vel[b][a] = expression{variable{std::string("v") + axis_name[a] + suffix}};
+        }
     }
 
-    std::vector<std::pair<expression, expression>> retval;
-    std::vector<std::vector<expression>> x_acc(n), y_acc(n), z_acc(n);
-
-    const auto n_massive = static_cast<std::uint32_t>(masses_vec.size());
-
     for (std::uint32_t i = 0; i < n_massive; ++i) {
-        retval.push_back(prime(x_vars[i]) = vx_vars[i]);
-        retval.push_back(prime(y_vars[i]) = vy_vars[i]);
-        retval.push_back(prime(z_vars[i]) = vz_vars[i]);
-
         for (std::uint32_t j = i + 1u; j < n; ++j) {
-            const auto diff_x = x_vars[j] - x_vars[i];
-            const auto diff_y = y_vars[j] - y_vars[i];
-            const auto diff_z = z_vars[j] - z_vars[i];
+            std::array<expression, 3> d;
+            std::vector<expression> squares;
+            for (int a = 0; a < 3; ++a) {
+                d[a] = pos[j][a] - pos[i][a];
+                squares.push_back(pow(d[a], 2_dbl));
+            }
+            const auto inv_r3 = pow(sum(squares), expression{-3. / 2});
 
-            const auto r_m3 = pow(sum({pow(diff_x, 2_dbl), pow(diff_y, 2_dbl), pow(diff_z, 2_dbl)}),
-                                  expression{-3. / 2});
-
-            const auto j_massive = j < n_massive;
-            const auto opt_grouping = j_massive && masses_vec[j].is_number() && masses_vec[j].num() != 0.
-                                      && Gconst.is_number();
-
-            if (opt_grouping) {
-                const auto fac_j = Gconst * masses_vec[j] * r_m3;
-                const auto c_ij = -masses_vec[i] / masses_vec[j];
-
-                x_acc[i].push_back(diff_x * fac_j);
-                y_acc[i].push_back(diff_y * fac_j);
-                z_acc[i].push_back(diff_z * fac_j);
-
-                x_acc[j].push_back(x_acc[i].back() * c_ij);
-                y_acc[j].push_back(y_acc[i].back() * c_ij);
-                z_acc[j].push_back(z_acc[i].back() * c_ij);
+            const bool j_has_mass = j < n_massive;
+            const bool rescaled
+                = j_has_mass && Gconst.is_number() && masses_vec[j].is_number() && masses_vec[j].num() != 0.;
+            if (rescaled) {
+                const auto pull_on_i = Gconst * masses_vec[j] * inv_r3;
+                const auto ratio = -masses_vec[i] / masses_vec[j];
+                for (int a = 0; a < 3; ++a) {
+                    acc[i][a].push_back(d[a] * pull_on_i);
+                }
+                for (int a = 0; a < 3; ++a) {
+                    acc[j][a].push_back(acc[i][a].back() * ratio);
+                }
             } else {
-                const auto G_r_m3 = Gconst * r_m3;
-
-                const auto fac_i = -masses_vec[i] * G_r_m3;
-                x_acc[j].push_back(diff_x * fac_i);
-                y_acc[j].push_back(diff_y * fac_i);
-                z_acc[j].push_back(diff_z * fac_i);
-
-                if (j_massive) {
-                    const auto fac_j = masses_vec[j] * G_r_m3;
-                    x_acc[i].push_back(diff_x * fac_j);
-                    y_acc[i].push_back(diff_y * fac_j);
-                    z_acc[i].push_back(diff_z * fac_j);
+                const auto g_inv_r3 = Gconst * inv_r3;
+                const auto pull_on_j = -masses_vec[i] * g_inv_r3;
+                for (int a = 0; a < 3; ++a) {
+                    acc[j][a].push_back(d[a] * pull_on_j);
+                }
+                if (j_has_mass) {
+                    const auto pull_on_i = masses_vec[j] * g_inv_r3;
+                    for (int a = 0; a < 3; ++a) {
+                        acc[i][a].push_back(d[a] * pull_on_i);
+                    }
                 }
             }
         }
-
-        retval.push_back(prime(vx_vars[i]) = sum(x_acc[i]));
-        retval.push_back(prime(vy_vars[i]) = sum(y_acc[i]));
-        retval.push_back(prime(vz_vars[i]) = sum(z_acc[i]));
     }
 
-    for (auto i = n_massive; i < n; ++i) {
-        retval.push_back(prime(x_vars[i]) = vx_vars[i]);
-        retval.push_back(prime(y_vars[i]) = vy_vars[i]);
-        retval.push_back(prime(z_vars[i]) = vz_vars[i]);
-
-        retval.push_back(prime(vx_vars[i]) = sum(x_acc[i]));
-        retval.push_back(prime(vy_vars[i]) = sum(y_acc[i]));
-        retval.push_back(prime(vz_vars[i]) = sum(z_acc[i]));
+    std::vector<std::pair<expression, expression>> eqs;
+    eqs.reserve(static_cast<std::size_t>(n) * 6u);
+    for (std::uint32_t b = 0; b < n; ++b) {
+        for (int a = 0; a < 3; ++a) {
+            eqs.push_back(prime(pos[b][a]) = vel[b][a]);
+        }
+        for (int a = 0; a < 3; ++a) {
+            eqs.push_back(prime(vel[b][a]) = sum(acc[b][a]));
+        }
     }
-
-    return retval;
+    return eqs;
 }
 
 // Total energy (kinetic + potential) of the N-body system (src/model/nbody.cpp:176-260).
@@ -149,39 +141,10 @@ expression pendulum_energy_impl(const expression &gconst, const expression &l)
     return 0.5_dbl * pow(l, 2_dbl) * pow(v, 2_dbl) + gconst * l * (1_dbl - cos(x));
 }
 
-namespace
-{
-
-// One dense layer: out_i = activation(sum_j(W_ij * in_j) + b_i) (src/model/ffnn.cpp:36-68).
-std::vector<expression> compute_layer(std::uint32_t layer_id, const std::vector<expression> &inputs,
-                                      const std::vector<std::uint32_t> &n_neurons,
-                                      const std::function<expression(const expression &)> &activation,
-                                      const std::vector<expression> &nn_wb, std::uint32_t n_net_w,
-                                      std::uint32_t &wcounter, std::uint32_t &bcounter)
-{
-    const auto n_prev = static_cast<std::uint32_t>(inputs.size());
-    const auto n_cur = n_neurons[layer_id];
-
-    std::vector<expression> retval, tmp_sum;
-    retval.reserve(n_cur);
-
-    for (std::uint32_t i = 0; i < n_cur; ++i) {
-        tmp_sum.clear();
-        for (std::uint32_t j = 0; j < n_prev; ++j) {
-            tmp_sum.push_back(nn_wb[wcounter] * inputs[j]);
-            ++wcounter;
-        }
-        tmp_sum.push_back(nn_wb[bcounter + n_net_w]);
-        ++bcounter;
-        retval.push_back(activation(sum(tmp_sum)));
-    }
-
-    return retval;
-}
-
-} // namespace
-
-// Weights/biases layout: [W01, W12, ..., B1, B2, ...], each W row-major (src/model/ffnn.cpp:70-142).
+// A feed-forward network as expressions (src/model/ffnn.cpp:36-142). Layer l maps the n_{l-1} outputs of the previous
+// layer to n_l neurons: out_i = activation_l(sum(W_l[i][0] in_0, ..., W_l[i][n_{l-1} - 1] in_{n_{l-1}-1}, b_l[i])).
+// nn_wb holds every weight matrix, row-major and layer after layer, followed by every bias vector; the offsets of a
+// layer's block are prefix sums of the layer sizes (no running counters).
 std::vector<expression> ffnn_impl(const std::vector<expression> &in, const std::vector<std::uint32_t> &nn_hidden,
                                   std::uint32_t n_out,
                                   const std::vector<std::function<expression(const expression &)>> &activations,
@@ -202,41 +165,53 @@ std::vector<expression> ffnn_impl(const std::vector<expression> &in, const std::
     if (n_out == 0u) {
         throw std::invalid_argument("The number of network outputs cannot be zero.");
     }
-    for (const auto item : nn_hidden) {
-        if (item == 0u) {
-            throw std::invalid_argument("The number of neurons for each hidden layer must be greater than zero!");
-        }
+    if (std::find(nn_hidden.begin(), nn_hidden.end(), 0u) != nn_hidden.end()) {
+        throw std::invalid_argument("The number of neurons for each hidden layer must be greater than zero!");
     }
-    for (const auto &f : activations) {
-        if (!f) {
-            throw std::invalid_argument("The list of activation functions cannot contain empty functions");
-        }
+    if (std::any_of(activations.begin(), activations.end(), [](const auto &f) { return !f; })) {
+        throw std::invalid_argument("The list of activation functions cannot contain empty functions");
     }
 
-    const auto n_layers = static_cast<std::uint32_t>(nn_hidden.size()) + 2u;
-    std::vector<std::uint32_t> n_neurons{static_cast<std::uint32_t>(in.size())};
-    n_neurons.insert(n_neurons.end(), nn_hidden.begin(), nn_hidden.end());
-    n_neurons.push_back(n_out);
+    // widths[l]: number of values entering layer l + 1 (widths[0] = inputs, widths.back() = outputs).
+    std::vector<std::uint32_t> widths;
+    widths.push_back(static_cast<std::uint32_t>(in.size()));
+    widths.insert(widths.end(), nn_hidden.begin(), nn_hidden.end());
+    widths.push_back(n_out);
+    const std::size_t n_maps = widths.size() - 1u;
 
-    std::uint32_t n_net_wb = 0, n_net_w = 0;
-    for (std::uint32_t i = 1; i < n_layers; ++i) {
-        n_net_wb += n_neurons[i - 1u] * n_neurons[i];
-        n_net_w += n_neurons[i - 1u] * n_neurons[i];
-        n_net_wb += n_neurons[i];
+    // Offsets of every layer's weights and biases inside nn_wb.
+    std::vector<std::size_t> w_off(n_maps), b_off(n_maps);
+    std::size_t n_weights = 0, n_biases = 0;
+    for (std::size_t l = 0; l < n_maps; ++l) {
+        w_off[l] = n_weights;
+        b_off[l] = n_biases;
+        n_weights += static_cast<std::size_t>(widths[l]) * widths[l + 1u];
+        n_biases += widths[l + 1u];
     }
-    if (nn_wb.size() != n_net_wb) {
+    if (nn_wb.size() != n_weights + n_biases) {
         throw std::invalid_argument("The number of network parameters, detected from its structure to be "
-                                    + std::to_string(n_net_wb)
+                                    + std::to_string(n_weights + n_biases)
                                     + ", does not match the size of the corresponding expressions: "
                                     + std::to_string(nn_wb.size()) + ".");
     }
 
-    std::vector<expression> retval = in;
-    std::uint32_t wcounter = 0, bcounter = 0;
-    for (std::uint32_t i = 1; i < n_layers; ++i) {
-        retval = compute_layer(i, retval, n_neurons, activations[i - 1u], nn_wb, n_net_w, wcounter, bcounter);
+    std::vector<expression> values = in;
+    for (std::size_t l = 0; l < n_maps; ++l) {
+        const auto fan_in = widths[l], fan_out = widths[l + 1u];
+        std::vector<expression> next;
+        next.reserve(fan_out);
+        for (std::uint32_t neuron = 0; neuron < fan_out; ++neuron) {
+            const auto row = nn_wb.begin() + static_cast<std::ptrdiff_t>(w_off[l] + static_cast<std::size_t>(neuron) * fan_in);
+            std::vector<expression> terms;
+            terms.reserve(static_cast<std::size_t>(fan_in) + 1u);
+            std::transform(row, row + fan_in, values.begin(), std::back_inserter(terms),
+                           [](const expression &w, const expression &x) { return w * x; });
+            terms.push_back(nn_wb[n_weights + b_off[l] + neuron]);
+            next.push_back(activations[l](sum(terms)));
+        }
+        values = std::move(next);
     }
-    return retval;
+    return values;
 }
 
 } // namespace heyoka_b200::model::detail

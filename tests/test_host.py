@@ -126,3 +126,22 @@ def test_no_cpu_fallback_without_device():
     env = dict(os.environ, CUDA_VISIBLE_DEVICES="", PYTHONPATH=ROOT)
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True).stdout
     assert "HYERROR -3" in out and "no CPU fallback" in out
+
+
+def test_model_builders_decomposition_pinned():
+    """heyoka_b200/csrc/model.cpp was rewritten in round 2 (table-driven pair enumeration, layer builder over index
+    ranges): the expression trees - hence the Taylor decompositions - must be exactly what they were (hashes of
+    hy_program_dc_str() recorded before the rewrite). The decomposition itself is pinned against the reference's sizes
+    in test_oracle_golden.py / tests/cpp/test_batch_api.cpp (36 + 198 + 36 entries for the 6-body system)."""
+    import hashlib
+    from common import FFNN_TOL, sys_ffnn, sys_nbody32, sys_outer_ss, sys_two_body
+
+    def h(sys_, **kw):
+        return hashlib.sha1(hb.Program(sys_, **kw).dc_str().encode()).hexdigest()[:12]
+
+    assert h(sys_outer_ss(), high_accuracy=True) == "573f3f3148f6"
+    assert h(sys_two_body()) == "33f528fabe8c"
+    assert h(sys_nbody32()) == "7d05336c9bb4"
+    assert h(sys_ffnn(), tol=FFNN_TOL) == "fe21beab5461"
+    assert h(hb.model.nbody(4)) == "afa50942f190"
+    assert h(hb.model.nbody(3, masses=[1., 0.5])) == "65c79fb1d72c"
