@@ -326,8 +326,9 @@ class Batch:
     def set_kernel(self, tape="auto", lanes_per_warp=0, lanes_per_thread=0, block_threads=0, blocks_per_sm=0):
         # "nbody" / "nbody-cta": the dedicated N-body kernel (warp / CTA teams); lanes_per_thread then selects the
         # storage of the private rows: 0 automatic, 1 tensor memory, 2 shared memory only.
+        # "nn": the dense-network kernel (right-hand sides that are feed-forward networks).
         mode = {"auto": 0, "hbm": 1, "smem": 2, "smem-notmem": 3, "global": 4, "global-cta": 5, "nbody": 6,
-                "nbody-cta": 7}[tape]
+                "nbody-cta": 7, "nn": 8}[tape]
         check(lib.hy_batch_set_kernel(self._h, mode, int(lanes_per_warp), int(lanes_per_thread), int(block_threads),
                                       int(blocks_per_sm)))
 
@@ -335,7 +336,7 @@ class Batch:
         ki = _capi.hy_kernel_info()
         check(lib.hy_batch_get_kernel(self._h, C.byref(ki)))
         d = {f[0]: getattr(ki, f[0]) for f in ki._fields_}
-        d["tape"] = {1: "hbm", 2: "smem", 4: "global", 5: "global-cta", 6: "nbody", 7: "nbody-cta"}.get(ki.tape_mode, "?")
+        d["tape"] = {1: "hbm", 2: "smem", 4: "global", 5: "global-cta", 6: "nbody", 7: "nbody-cta", 8: "nn"}.get(ki.tape_mode, "?")
         return d
 
     def sync(self):

@@ -29,8 +29,9 @@ lib = C.CDLL(LIB_PATH)
 class hy_program_desc(C.Structure):
     _fields_ = [
         ("n_eq", C.c_uint32), ("n_uvars", C.c_uint32), ("n_pars", C.c_uint32), ("order", C.c_uint32),
-        ("n_args", C.c_uint32), ("n_consts", C.c_uint32), ("high_accuracy", C.c_int32), ("reserved", C.c_int32),
+        ("n_args", C.c_uint32), ("n_consts", C.c_uint32), ("high_accuracy", C.c_int32), ("n_ev", C.c_uint32),
         ("ops", C.c_void_p), ("args", C.c_void_p), ("consts", C.c_void_p), ("sv_defs", C.c_void_p),
+        ("ev_defs", C.c_void_p),
     ]
 
 

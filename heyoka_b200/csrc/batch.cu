@@ -25,6 +25,9 @@
 #include "nb_kernel.cuh"
 #include "nb_plan.hpp"
 #include "nb_variants.hpp"
+#include "nn_kernel.cuh"
+#include "nn_plan.hpp"
+#include "nn_variants.hpp"
 #include "small_kernels.cuh"
 #include "program.hpp"
 #include "smem_plan.hpp"
@@ -234,6 +237,14 @@ struct hy_batch {
     bool nb_on = false;
     int opt_nb = -1; // -1 automatic, 0 never (HEYOKA_B200_NB=0), 1 preferred
     bool setup_nb(int LT, std::uint32_t threads, int want_tmem, int want_cta);
+    // The dense-network kernel (nn_kernel.cuh): plan, padded weight image, device plan.
+    hy::detail::nn_plan nnp;
+    double *d_nn_wimg = nullptr;
+    std::uint32_t *d_nn_out = nullptr;
+    dev::nn_dev_plan nnd{};
+    bool nn_on = false;
+    int opt_nn = -1; // 0: never (HEYOKA_B200_NN=0)
+    bool setup_nn();
 
     // Resident arrays.
     double *d_state = nullptr, *d_pars = nullptr, *d_t_hi = nullptr, *d_t_lo = nullptr, *d_last_h = nullptr,
@@ -312,7 +323,7 @@ void hy_batch::free_all() noexcept
           static_cast<void *>(d_scratch), static_cast<void *>(d_tmp),
           static_cast<void *>(d_snapshot), static_cast<void *>(d_counter), static_cast<void *>(d_flags),
           static_cast<void *>(d_nb_pairs), static_cast<void *>(d_nb_roles), static_cast<void *>(d_nb_consts),
-          static_cast<void *>(d_nb_fac)}) {
+          static_cast<void *>(d_nb_fac), static_cast<void *>(d_nn_wimg), static_cast<void *>(d_nn_out)}) {
         if (p != nullptr) {
             cudaFree(p);
         }
@@ -847,11 +858,104 @@ bool hy_batch::setup_nb(int LT, std::uint32_t threads, int want_tmem, int want_c
     return true;
 }
 
+// The dense-network kernel: the padded shared-memory image of the weights is prepared here (row pitch = 4 mod 16
+// doubles: the 8 x 4 A fragments of the tensor-core products then read conflict-free), copied once per CTA by the TMA
+// unit. Returns false if the program is not a network or does not fit in shared memory.
+bool hy_batch::setup_nn()
+{
+    if (!nnp.ok || nnp.layers.size() > static_cast<std::size_t>(dev::NN_MAX_LAYERS)) {
+        return false;
+    }
+    dev::nn_dev_plan d{};
+    std::vector<double> img;
+    std::uint32_t hist = 0, max_out = 0;
+    d.n_layers = static_cast<std::uint32_t>(nnp.layers.size());
+    for (std::uint32_t l = 0; l < d.n_layers; ++l) {
+        const auto &L = nnp.layers[l];
+        d.n_in[l] = L.n_in;
+        d.n_out[l] = L.n_out;
+        d.act[l] = static_cast<std::uint32_t>(L.act);
+        d.n_in_pad[l] = (L.n_in + 3u) & ~3u;
+        d.n_out_pad[l] = (L.n_out + 7u) & ~7u;
+        std::uint32_t ldw = d.n_in_pad[l];
+        while (ldw % 16u != 4u) {
+            ++ldw;
+        }
+        d.ldw[l] = ldw;
+        d.w_off[l] = static_cast<std::uint32_t>(img.size());
+        img.resize(img.size() + static_cast<std::size_t>(d.n_out_pad[l]) * ldw, 0.);
+        for (std::uint32_t r = 0; r < L.n_out; ++r) {
+            for (std::uint32_t c = 0; c < L.n_in; ++c) {
+                img[d.w_off[l] + static_cast<std::size_t>(r) * ldw + c] = L.w[static_cast<std::size_t>(r) * L.n_in + c];
+            }
+        }
+        d.b_off[l] = static_cast<std::uint32_t>(img.size());
+        img.insert(img.end(), L.bias.begin(), L.bias.end());
+        img.resize((img.size() + 1u) & ~std::size_t(1), 0.);
+        d.hist_off[l] = hist;
+        if (L.act != 0) {
+            hist += 3u * order * L.n_out * dev::NN_LB;
+        }
+        max_out = std::max(max_out, L.n_out);
+    }
+    d.wimg_doubles = static_cast<std::uint32_t>(img.size());
+    d.hist_doubles = hist;
+    d.max_out = max_out;
+    const std::size_t doubles = img.size() + hist + static_cast<std::size_t>(order + 1u) * n_eq * dev::NN_LB
+                                + static_cast<std::size_t>(max_out) * dev::NN_LB + dev::NN_LB + 4u;
+    const std::size_t bytes = doubles * sizeof(double);
+    if (bytes + 2048u > smem_per_block_max) {
+        return false;
+    }
+    for (void **ptr : {reinterpret_cast<void **>(&d_nn_wimg), reinterpret_cast<void **>(&d_nn_out)}) {
+        if (*ptr != nullptr) {
+            HY_CUDA_CHECK(cudaFree(*ptr));
+            *ptr = nullptr;
+        }
+    }
+    d_nn_wimg = dupload(img);
+    d_nn_out = dupload(nnp.out_of_sv);
+    d.wimg = d_nn_wimg;
+    d.out_of_sv = d_nn_out;
+    nnd = d;
+    for (auto fn : {hy::detail::nn_kernel_step(), hy::detail::nn_kernel_prop()}) {
+        HY_CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes)));
+    }
+    for (double **ptr : {&d_gscratch, &d_cscratch}) {
+        if (*ptr != nullptr) {
+            HY_CUDA_CHECK(cudaFree(*ptr));
+            *ptr = nullptr;
+        }
+    }
+    nb_cv = coop_variant{dev::NN_LB, 1, dev::NN_THREADS, 8, nullptr, nullptr};
+    cv = &nb_cv;
+    c_threads = dev::NN_THREADS;
+    c_smem = bytes;
+    c_ctas_per_sm = 1;
+    const std::uint32_t n_blocks_needed = (n + dev::NN_LB - 1u) / dev::NN_LB;
+    c_grid = std::max(1u, std::min(n_sms, n_blocks_needed));
+    mode = 2;
+    nn_on = true;
+    return true;
+}
+
 void hy_batch::configure(int want_mode, int L, int N, std::uint32_t threads, std::uint32_t blocks_per_sm)
 {
     c_global = false;
     c_cta = false;
     nb_on = false;
+    nn_on = false;
+    // Mode 8: the dense-network kernel (right-hand sides that are feed-forward networks, nn_plan.hpp); the automatic
+    // mode takes it whenever the program qualifies.
+    if (want_mode == 8 || (want_mode == 0 && opt_nn != 0)) {
+        if (setup_nn()) {
+            return;
+        }
+        if (want_mode == 8) {
+            throw std::invalid_argument("The dense-network kernel cannot run this program: "
+                                        + (nnp.ok ? std::string("it does not fit in shared memory") : nnp.why));
+        }
+    }
     // Mode 6 / 7: the N-body kernel with warp / CTA teams (N: 0 automatic, 1 tensor memory, 2 shared memory only).
     // Automatic mode takes it whenever the program qualifies (nb_plan.hpp).
     if (want_mode == 6 || want_mode == 7 || (want_mode == 0 && opt_nb != 0)) {
@@ -900,11 +1004,14 @@ void hy_batch::ensure_tc()
 
 void hy_batch::launch(bool prop, const dev::run_args &R)
 {
-    if (R.write_tc != 0 || (mode == 2 && d_cscratch == nullptr)) {
+    if (R.write_tc != 0 || (mode == 2 && d_cscratch == nullptr && !nn_on)) {
         ensure_tc();
     }
     HY_CUDA_CHECK(cudaMemsetAsync(d_counter, 0, sizeof(unsigned int), stream));
-    if (mode == 2) {
+    if (nn_on) {
+        (prop ? hy::detail::nn_kernel_prop() : hy::detail::nn_kernel_step())<<<c_grid, c_threads, c_smem, stream>>>(
+            prog, nnd, view(), R);
+    } else if (mode == 2) {
         dev::run_args R2 = R;
         const bool pub = R.write_tc != 0 || d_cscratch == nullptr;
         const auto lanes = static_cast<unsigned long long>(cv->L);
@@ -1255,6 +1362,10 @@ int hy_batch_create(const hy_program *p, uint32_t batch, int device, hy_batch **
         b->prog_host = std::make_shared<const hy_program>(*p);
         b->replan(false);
         b->nbp = hy::detail::make_nb_plan(*p);
+        if (const char *env = std::getenv("HEYOKA_B200_NN")) {
+            b->opt_nn = std::string{env} != "0" ? 1 : 0;
+        }
+        b->nnp = hy::detail::make_nn_plan(*p);
 
         // Resident arrays.
         const std::size_t n = batch;
@@ -1411,7 +1522,9 @@ int hy_batch_set_launch_config(hy_batch *b, uint32_t block_threads, uint32_t blo
         HY_CUDA_CHECK(cudaStreamSynchronize(b->stream));
         const int L = b->cv != nullptr && b->mode == 2 ? b->cv->L : 0;
         const int N = b->cv != nullptr && b->mode == 2 ? b->cv->N : 0;
-        if (b->nb_on) {
+        if (b->nn_on) {
+            b->configure(8, 0, 0, 0, 0);
+        } else if (b->nb_on) {
             b->configure(b->c_cta ? 7 : 6, L, b->nbv->tmem ? 1 : 2, block_threads, blocks_per_sm);
         } else {
             b->configure(b->mode, L, N, block_threads, blocks_per_sm);
@@ -1429,7 +1542,7 @@ int hy_batch_set_kernel(hy_batch *b, int tape_mode, uint32_t lanes_per_warp, uin
         if (b == nullptr) {
             throw std::invalid_argument("Null batch");
         }
-        if (tape_mode < 0 || tape_mode > 7) {
+        if (tape_mode < 0 || tape_mode > 8) {
             throw std::invalid_argument("Invalid tape mode");
         }
         if (!b->shards.empty()) {
@@ -1460,7 +1573,7 @@ int hy_batch_get_kernel(const hy_batch *b, hy_kernel_info *out)
     if (!b->shards.empty()) {
         return hy_batch_get_kernel(b->shards[0], out); // (every shard runs the same kernel shape)
     }
-    out->tape_mode = b->nb_on ? (b->c_cta ? 7 : 6) : (b->mode == 2 && b->c_global ? (b->c_cta ? 5 : 4) : b->mode);
+    out->tape_mode = b->nn_on ? 8 : b->nb_on ? (b->c_cta ? 7 : 6) : (b->mode == 2 && b->c_global ? (b->c_cta ? 5 : 4) : b->mode);
     out->lanes_per_warp = b->mode == 2 ? static_cast<uint32_t>(b->cv->L) : 32u;
     out->lanes_per_thread = b->mode == 2 ? static_cast<uint32_t>(b->cv->N) : 1u;
     out->block_threads = b->mode == 2 ? b->c_threads : b->h_threads;

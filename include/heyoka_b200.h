@@ -158,11 +158,13 @@ typedef struct hy_program_desc {
     uint32_t n_args;
     uint32_t n_consts;
     int32_t high_accuracy; /* 0: Horner update, 1: compensated summation (src/taylor_00.cpp:355-460) */
-    int32_t reserved;
+    uint32_t n_ev;     /* number of event equations (terminal events first), 0 if none          */
     const hy_op *ops;        /* n_uvars - n_eq entries, in evaluation order                     */
     const uint32_t *args;    /* argument references for n-ary ops                               */
     const double *consts;    /* constant pool                                                   */
     const uint32_t *sv_defs; /* n_eq references: d(x_i)/dt is a u variable, a number or a param */
+    const uint32_t *ev_defs; /* n_ev indices: the u variable (possibly a state variable) holding each event
+                                equation (sv_funcs_dc of src/taylor_01.cpp:847-1008); NULL if n_ev == 0 */
 } hy_program_desc;
 
 typedef struct hy_program hy_program;

@@ -1044,6 +1044,707 @@ int SYM(oracle_d_output)(const hy_program_desc *P, uint32_t batch, const double 
     return 0;
 }
 
+/* ================================================================================================
+ * Event detection in batch mode (scalar build only): restatement of
+ *   src/taylor_00.cpp:593-710           taylor_add_adaptive_step_with_events(): jet of the state variables AND of the
+ *                                       event equations, step size from both, no propagation of the state;
+ *   src/taylor_adaptive_batch.cpp:728-1035  the events branch of step_impl();
+ *   src/detail/event_detection.cpp:1733-2173  ed_data_batch<T>::detect_events() with its helpers (:171-280 polynomial
+ *                                       utilities, :413-507 translation by 1, :598-697 reverse-translate-count,
+ *                                       :704-816 fast exclusion check, :519-550 automatic cooldown);
+ *   src/detail/llvm_helpers_ed.cpp:58-330  sign-change count, interval enclosure by Horner.
+ * The bracketed root finder is boost::math::tools::toms748_solve (Boost.Math, a dependency that is NOT in
+ * /root/reference; heyoka requires Boost >= 1.69, no pinned version): Algorithm 748 of Alefeld, Potra and Shi (ACM TOMS
+ * 21(3), 1995) restated below from the published algorithm in the arrangement Boost uses (secant, quadratic, two
+ * cubic/quadratic steps, double-length secant, optional bisection per iteration; eps_tolerance = 4 eps). Event times
+ * are therefore pinned to the reference by tolerance (its own tests use 1000 eps, test/batch_event_detection.cpp:158),
+ * not bit for bit.
+ * ============================================================================================== */
+#if ORACLE_W == 1
+
+#include <errno.h>
+#include <float.h>
+
+typedef struct {
+    uint32_t lane;    /* batch index */
+    uint32_t idx;     /* index among the terminal (terminal != 0) or non-terminal events */
+    int32_t terminal;
+    int32_t d_sgn;    /* sign of the time derivative of the event equation at the root */
+    double t;         /* time of the event relative to the beginning of the step */
+    double abs_der;
+} oracle_event;
+
+static inline int sgn_d(double x)
+{
+    return (0. < x) - (x < 0.);
+}
+
+/* :269-280 */
+static double ed_poly_eval(const double *a, double x, uint32_t n)
+{
+    double ret = a[n];
+    for (uint32_t i = 1; i <= n; ++i) {
+        ret = a[n - i] + ret * x;
+    }
+    return ret;
+}
+
+/* :249-264 */
+static double ed_poly_eval_1(const double *a, double x, uint32_t n)
+{
+    double ret1 = a[n] * (double)n;
+    for (uint32_t i = 1; i < n; ++i) {
+        ret1 = a[n - i] * (double)(n - i) + ret1 * x;
+    }
+    return ret1;
+}
+
+/* :171-192 */
+static void ed_poly_rescale(double *ret, const double *a, double scal, uint32_t n)
+{
+    double cur_f = 1.;
+    for (uint32_t i = 0; i <= n; ++i) {
+        ret[i] = a[i] * cur_f;
+        cur_f *= scal;
+    }
+}
+
+/* :197-221 */
+static void ed_poly_rescale_p2(double *ret, const double *a, uint32_t n)
+{
+    double cur_f = 1.;
+    for (uint32_t i = 0; i <= n; ++i) {
+        ret[n - i] = cur_f * a[n - i];
+        cur_f *= 2.;
+    }
+}
+
+/* :413-507 with the binomial table of llvm_helpers_ed.cpp:421-455. */
+static void ed_poly_translate_1(double *out, const double *a, uint32_t n, const double *bc)
+{
+    for (uint32_t i = 0; i <= n; ++i) {
+        out[i] = 0.;
+    }
+    for (uint32_t i = 0; i <= n; ++i) {
+        for (uint32_t k = 0; k <= i; ++k) {
+            out[k] = out[k] + a[i] * bc[i * (n + 1u) + k];
+        }
+    }
+}
+
+/* llvm_helpers_ed.cpp:58-190: number of sign changes, zeros skipped. */
+static uint32_t ed_count_sign_changes(const double *a, uint32_t n)
+{
+    uint32_t last_nz = 0, ret = 0;
+    for (uint32_t i = 1; i <= n; ++i) {
+        const int cur = sgn_d(a[i]), last = sgn_d(a[last_nz]);
+        ret += (last != 0 && cur + last == 0) ? 1u : 0u;
+        if (cur != 0) {
+            last_nz = i;
+        }
+    }
+    return ret;
+}
+
+/* :598-697: reverse a into t1, translate by 1 into t2, count the sign changes of t2. */
+static uint32_t ed_rtscc(double *t1, double *t2, const double *a, uint32_t n, const double *bc)
+{
+    for (uint32_t i = 0; i <= n; ++i) {
+        t1[i] = a[n - i];
+    }
+    ed_poly_translate_1(t2, t1, n, bc);
+    return ed_count_sign_changes(t2, n);
+}
+
+/* :704-816 (use_cs == false) + llvm_helpers_ed.cpp:227-330: enclosure of the polynomial over [0, h] (or [h, 0]) by
+ * Horner's scheme in interval arithmetic; true = no sign change possible. */
+static int ed_fex_check(const double *a, uint32_t n, double h, int back)
+{
+    const double h_lo = back ? h : 0., h_hi = back ? 0. : h;
+    double acc_lo = a[n], acc_hi = a[n];
+    for (uint32_t i = 1; i <= n; ++i) {
+        const double cf = a[n - i];
+        const double t1 = acc_lo * h_lo, t2 = acc_lo * h_hi, t3 = acc_hi * h_lo, t4 = acc_hi * h_hi;
+        const double lo = std_min(std_min(t1, t2), std_min(t3, t4));
+        const double hi = std_max(std_max(t1, t2), std_max(t3, t4));
+        acc_lo = cf + lo;
+        acc_hi = cf + hi;
+    }
+    const int s_lo = sgn_d(acc_lo), s_hi = sgn_d(acc_hi);
+    return s_lo == s_hi && s_lo != 0;
+}
+
+/* ---- TOMS 748 (see the header of this section) ---- */
+typedef struct {
+    const double *poly;
+    uint32_t order;
+} t748_f;
+
+static inline double t748_eval(const t748_f *f, double x)
+{
+    return ed_poly_eval(f->poly, x, f->order);
+}
+static inline int t748_sign(double z)
+{
+    return z == 0. ? 0 : (signbit(z) ? -1 : 1);
+}
+static inline int t748_tol(double a, double b)
+{
+    return fabs(a - b) <= 4. * DBL_EPSILON * fmin(fabs(a), fabs(b));
+}
+static inline double t748_safe_div(double num, double denom, double r)
+{
+    if (fabs(denom) < 1.) {
+        if (fabs(denom * DBL_MAX) <= fabs(num)) {
+            return r;
+        }
+    }
+    return num / denom;
+}
+static void t748_bracket(const t748_f *f, double *a, double *b, double c, double *fa, double *fb, double *d, double *fd)
+{
+    const double tol = DBL_EPSILON * 2.;
+    if ((*b - *a) < 2. * tol * *a) {
+        c = *a + (*b - *a) / 2.;
+    } else if (c <= *a + fabs(*a) * tol) {
+        c = *a + fabs(*a) * tol;
+    } else if (c >= *b - fabs(*b) * tol) {
+        c = *b - fabs(*b) * tol;
+    }
+    const double fc = t748_eval(f, c);
+    if (fc == 0.) {
+        *a = c;
+        *fa = 0.;
+        *d = 0.;
+        *fd = 0.;
+        return;
+    }
+    if (t748_sign(*fa) * t748_sign(fc) < 0) {
+        *d = *b;
+        *fd = *fb;
+        *b = c;
+        *fb = fc;
+    } else {
+        *d = *a;
+        *fd = *fa;
+        *a = c;
+        *fa = fc;
+    }
+}
+static double t748_secant(double a, double b, double fa, double fb)
+{
+    const double tol = DBL_EPSILON * 5.;
+    const double c = a - (fa / (fb - fa)) * (b - a);
+    if (c <= a + fabs(a) * tol || c >= b - fabs(b) * tol) {
+        return (a + b) / 2.;
+    }
+    return c;
+}
+static double t748_quadratic(double a, double b, double d, double fa, double fb, double fd, unsigned count)
+{
+    double B = t748_safe_div(fb - fa, b - a, DBL_MAX);
+    double A = t748_safe_div(fd - fb, d - b, DBL_MAX);
+    A = t748_safe_div(A - B, d - a, 0.);
+    if (A == 0.) {
+        return t748_secant(a, b, fa, fb);
+    }
+    double c = (t748_sign(A) * t748_sign(fa) > 0) ? a : b;
+    for (unsigned i = 1; i <= count; ++i) {
+        c -= t748_safe_div(fa + (B + A * (c - b)) * (c - a), B + A * (2. * c - a - b), 1. + c - a);
+    }
+    if (c <= a || c >= b) {
+        c = t748_secant(a, b, fa, fb);
+    }
+    return c;
+}
+static double t748_cubic(double a, double b, double d, double e, double fa, double fb, double fd, double fe)
+{
+    const double q11 = (d - e) * fd / (fe - fd);
+    const double q21 = (b - d) * fb / (fd - fb);
+    const double q31 = (a - b) * fa / (fb - fa);
+    const double d21 = (b - d) * fd / (fd - fb);
+    const double d31 = (a - b) * fb / (fb - fa);
+    const double q22 = (d21 - q11) * fb / (fe - fb);
+    const double q32 = (d31 - q21) * fa / (fd - fa);
+    const double d32 = (d31 - q21) * fd / (fd - fa);
+    const double q33 = (d32 - q22) * fa / (fe - fa);
+    double c = q31 + q32 + q33 + a;
+    if (c <= a || c >= b) {
+        c = t748_quadratic(a, b, d, fa, fb, fd, 3);
+    }
+    return c;
+}
+static inline int t748_prof(double fa, double fb, double fd, double fe)
+{
+    const double m = DBL_MIN * 32.;
+    return fabs(fa - fb) < m || fabs(fa - fd) < m || fabs(fa - fe) < m || fabs(fb - fd) < m || fabs(fb - fe) < m
+           || fabs(fd - fe) < m;
+}
+/* Returns the bracket [*ra, *rb]; *max_iter in: limit, out: evaluations used; *err = EDOM if [ax, bx] is not a bracket. */
+static void t748_solve(const t748_f *f, double ax, double bx, uint64_t *max_iter, double *ra, double *rb, int *err)
+{
+    *err = 0;
+    if (*max_iter <= 2u) {
+        *ra = ax;
+        *rb = bx;
+        return;
+    }
+    *max_iter -= 2u;
+    uint64_t count = *max_iter;
+    double a = ax, b = bx, fa = t748_eval(f, ax), fb = t748_eval(f, bx), c, u, fu, a0, b0, d, fd, e, fe;
+    const double mu = 0.5;
+    if (a >= b) {
+        *err = EDOM;
+        *ra = *rb = NAN;
+        *max_iter += 2u;
+        return;
+    }
+    if (t748_tol(a, b) || fa == 0. || fb == 0.) {
+        *max_iter = 0;
+        if (fa == 0.) {
+            b = a;
+        } else if (fb == 0.) {
+            a = b;
+        }
+        *ra = a;
+        *rb = b;
+        *max_iter += 2u;
+        return;
+    }
+    if (t748_sign(fa) * t748_sign(fb) > 0) {
+        *err = EDOM;
+        *ra = *rb = NAN;
+        *max_iter += 2u;
+        return;
+    }
+    fe = e = fd = 1e5;
+    d = 0.;
+    if (fa != 0.) {
+        c = t748_secant(a, b, fa, fb);
+        t748_bracket(f, &a, &b, c, &fa, &fb, &d, &fd);
+        --count;
+        if (count && fa != 0. && !t748_tol(a, b)) {
+            c = t748_quadratic(a, b, d, fa, fb, fd, 2);
+            e = d;
+            fe = fd;
+            t748_bracket(f, &a, &b, c, &fa, &fb, &d, &fd);
+            --count;
+        }
+    }
+    while (count && fa != 0. && !t748_tol(a, b)) {
+        a0 = a;
+        b0 = b;
+        if (t748_prof(fa, fb, fd, fe)) {
+            c = t748_quadratic(a, b, d, fa, fb, fd, 2);
+        } else {
+            c = t748_cubic(a, b, d, e, fa, fb, fd, fe);
+        }
+        e = d;
+        fe = fd;
+        t748_bracket(f, &a, &b, c, &fa, &fb, &d, &fd);
+        if (0u == --count || fa == 0. || t748_tol(a, b)) {
+            break;
+        }
+        if (t748_prof(fa, fb, fd, fe)) {
+            c = t748_quadratic(a, b, d, fa, fb, fd, 3);
+        } else {
+            c = t748_cubic(a, b, d, e, fa, fb, fd, fe);
+        }
+        t748_bracket(f, &a, &b, c, &fa, &fb, &d, &fd);
+        if (0u == --count || fa == 0. || t748_tol(a, b)) {
+            break;
+        }
+        if (fabs(fa) < fabs(fb)) {
+            u = a;
+            fu = fa;
+        } else {
+            u = b;
+            fu = fb;
+        }
+        c = u - 2. * (fu / (fb - fa)) * (b - a);
+        if (fabs(c - u) > (b - a) / 2.) {
+            c = a + (b - a) / 2.;
+        }
+        e = d;
+        fe = fd;
+        t748_bracket(f, &a, &b, c, &fa, &fb, &d, &fd);
+        if (0u == --count || fa == 0. || t748_tol(a, b)) {
+            break;
+        }
+        if ((b - a) < mu * (b0 - a0)) {
+            continue;
+        }
+        e = d;
+        fe = fd;
+        t748_bracket(f, &a, &b, a + (b - a) / 2., &fa, &fb, &d, &fd);
+        --count;
+    }
+    *max_iter -= count;
+    if (fa == 0.) {
+        b = a;
+    } else if (fb == 0.) {
+        a = b;
+    }
+    *ra = a;
+    *rb = b;
+    *max_iter += 2u;
+}
+
+/* :307-394: the only root of poly in [lb, ub). cflag: 0 ok, -1 too many iterations, > 0 errno. */
+static double ed_bracketed_root_find(const double *poly, uint32_t order, double lb, double ub, int *cflag)
+{
+    if (isfinite(lb) && isfinite(ub) && ub > lb) {
+        ub = nextafter(ub, lb);
+    }
+    const uint64_t iter_limit = DBL_MANT_DIG;
+    uint64_t max_iter = iter_limit;
+    const t748_f f = {poly, order};
+    double a, b;
+    int err;
+    t748_solve(&f, lb, ub, &max_iter, &a, &b, &err);
+    const double ret = a / 2. + b / 2.;
+    if (err > 0) {
+        *cflag = err;
+        return 0.;
+    }
+    *cflag = max_iter < iter_limit ? 0 : -1;
+    return ret;
+}
+
+/* :519-550 */
+static double ed_deduce_cooldown(double g_eps, double abs_der)
+{
+    const double ret = g_eps / abs_der * 10.;
+    return isfinite(ret) ? ret : 0.;
+}
+
+typedef struct {
+    oracle_event *v;
+    uint32_t n, cap;
+} ev_list;
+
+static void ev_push(ev_list *L, oracle_event e)
+{
+    if (L->n == L->cap) {
+        L->cap = L->cap ? 2u * L->cap : 16u;
+        L->v = (oracle_event *)realloc(L->v, sizeof(oracle_event) * L->cap);
+    }
+    L->v[L->n++] = e;
+}
+
+/* add_d_event (:1841-1912): the root is already rescaled to [0, h). */
+static void ed_add_d_event(const double *ptr, uint32_t order, double h, int dir, oracle_event proto, ev_list *out,
+                           double root)
+{
+    if (!isfinite(root)) {
+        return;
+    }
+    if (fabs(root) >= fabs(h)) {
+        root = nextafter(h, 0.);
+    }
+    const double der = ed_poly_eval_1(ptr, root, order);
+    if (!isfinite(der)) {
+        return;
+    }
+    const int d_sgn = sgn_d(der);
+    if (dir == 0 || d_sgn == dir) {
+        proto.t = root;
+        proto.d_sgn = d_sgn;
+        proto.abs_der = fabs(der);
+        ev_push(out, proto);
+    }
+}
+
+/* The body of run_detection() (:1767-2168) for one batch element and one event: the polynomial of the event is
+ * ptr[0..order], dir the requested direction, cd = {time in cooldown, cooldown} or NULL. */
+static void ed_detect_one(const double *ptr, uint32_t order, double h, double g_eps, int dir, const double *cd,
+                          const double *bc, oracle_event proto, ev_list *out)
+{
+    if (!isfinite(h) || !isfinite(g_eps) || h == 0.) {
+        return;
+    }
+    const uint32_t np1 = order + 1u;
+    double *isol = (double *)malloc(sizeof(double) * 2u * (order + 2u));
+    uint32_t n_isol = 0;
+    /* Working list: (lb, ub, polynomial). */
+    const uint32_t wl_cap = 256u;
+    double *wl_b = (double *)malloc(sizeof(double) * 2u * wl_cap);
+    double *wl_p = (double *)malloc(sizeof(double) * (size_t)np1 * wl_cap);
+    double *tmp = (double *)malloc(sizeof(double) * 3u * np1), *tmp1 = tmp + np1, *tmp2 = tmp1 + np1;
+    uint32_t n_wl = 0;
+
+
+    double lb_offset = 0.;
+    if (cd != NULL) {
+        lb_offset = (h >= 0.) ? (cd[1] - cd[0]) / fabs(h) : (cd[1] + cd[0]) / fabs(h);
+    }
+    if (lb_offset >= 1.) {
+        goto done;
+    }
+    ed_poly_rescale(tmp, ptr, h, order);
+    wl_b[0] = 0.;
+    wl_b[1] = 1.;
+    memcpy(wl_p, tmp, sizeof(double) * np1);
+    n_wl = 1;
+    int loop_failed = 0;
+    do {
+        const double lb = wl_b[2u * (n_wl - 1u)], ub = wl_b[2u * (n_wl - 1u) + 1u];
+        memcpy(tmp, wl_p + (size_t)(n_wl - 1u) * np1, sizeof(double) * np1);
+        --n_wl;
+        int all_fin = 1;
+        for (uint32_t k = 1; k <= order; ++k) {
+            all_fin = all_fin && isfinite(tmp[k]);
+        }
+        if (tmp[0] == 0. && all_fin) {
+            const int skip_event = cd != NULL && lb < lb_offset;
+            if (!skip_event) {
+                ed_add_d_event(ptr, order, h, dir, proto, out, lb * h);
+            }
+        }
+        const uint32_t n_sc = ed_rtscc(tmp1, tmp2, tmp, order, bc);
+        if (n_sc == 1u) {
+            isol[2u * n_isol] = lb;
+            isol[2u * n_isol + 1u] = ub;
+            ++n_isol;
+        } else if (n_sc > 1u) {
+            ed_poly_rescale_p2(tmp1, tmp, order);
+            ed_poly_translate_1(tmp2, tmp1, order, bc);
+            const double mid = lb / 2. + ub / 2.;
+            if (lb_offset < mid) {
+                wl_b[2u * n_wl] = lb;
+                wl_b[2u * n_wl + 1u] = mid;
+                memcpy(wl_p + (size_t)n_wl * np1, tmp1, sizeof(double) * np1);
+                ++n_wl;
+            }
+            wl_b[2u * n_wl] = mid;
+            wl_b[2u * n_wl + 1u] = ub;
+            memcpy(wl_p + (size_t)n_wl * np1, tmp2, sizeof(double) * np1);
+            ++n_wl;
+        }
+        if (n_wl > 250u || n_isol > order) {
+            loop_failed = 1;
+            break;
+        }
+    } while (n_wl != 0u);
+    if (n_isol == 0u || loop_failed) {
+        goto done;
+    }
+    ed_poly_rescale(tmp1, ptr, h, order);
+    for (uint32_t k = 0; k < n_isol; ++k) {
+        double lb = isol[2u * k];
+        const double ub = isol[2u * k + 1u];
+        if (cd != NULL && lb < lb_offset) {
+            lb = lb_offset;
+            const double f_lb = ed_poly_eval(tmp1, lb, order), f_ub = ed_poly_eval(tmp1, ub, order);
+            if (!(f_lb * f_ub < 0.)) {
+                continue;
+            }
+        }
+        int cflag;
+        const double root = ed_bracketed_root_find(tmp1, order, lb, ub, &cflag);
+        if (cflag == 0) {
+            ed_add_d_event(ptr, order, h, dir, proto, out, root * h);
+        }
+    }
+done:
+    free(isol);
+    free(wl_b);
+    free(wl_p);
+    free(tmp);
+}
+
+static int ev_cmp_abs_t(const void *a, const void *b)
+{
+    const double x = fabs(((const oracle_event *)a)->t), y = fabs(((const oracle_event *)b)->t);
+    return (x < y) ? -1 : (y < x ? 1 : 0);
+}
+
+/* One step of a batch integrator with events (the events branch of step_impl()). P->n_ev event equations, the first
+ * n_te of them terminal; dirs[n_ev] in {-1, 0, 1}; cooldowns[n_te] (< 0: automatic); cd[batch][n_te][2] and
+ * cd_on[batch][n_te] the cooldown state ({time spent, cooldown}, active flag), updated in place;
+ * tc[(n_eq + n_ev)][p + 1][batch] written unconditionally (:776). Events out: for every lane (ascending) the
+ * non-terminal events that happen before the first terminal one, in time order, then the first terminal event if
+ * any. outcome[lane] = -idx - 1 for a terminal event (the caller turns it into idx if its callback returns true).
+ * Callbacks and their exceptions are the caller's business. */
+int oracle_step_ev_w1(const hy_program_desc *P, uint32_t batch, double *state, const double *pars, double *t_hi,
+                      double *t_lo, const double *max_delta_t, double tol, uint32_t n_te, const int32_t *dirs,
+                      const double *cooldowns, double *cd, int32_t *cd_on, double *tc, double *last_h, int64_t *outcome,
+                      oracle_event *evs, uint32_t evs_cap, uint32_t *n_evs, int mode)
+{
+    const uint32_t p = P->order, n_eq = P->n_eq, n_ev = P->n_ev, pp1 = p + 1u;
+    real_t *T = alloc_tape(P);
+    double *bc = (double *)malloc(sizeof(double) * pp1 * pp1), *poly = (double *)malloc(sizeof(double) * pp1);
+    if (T == NULL || bc == NULL || poly == NULL) {
+        return 1;
+    }
+    /* Binomial coefficients (exact in double for the orders in use). */
+    for (uint32_t i = 0; i <= p; ++i) {
+        for (uint32_t j = 0; j <= p; ++j) {
+            bc[i * pp1 + j] = j > i ? 0. : (j == 0u ? 1. : bc[(i - 1u) * pp1 + j - 1u] + (j <= i - 1u ? bc[(i - 1u) * pp1 + j] : 0.));
+        }
+    }
+    uint32_t max_svf = 0;
+    for (uint32_t k = 0; k < n_ev; ++k) {
+        max_svf = P->ev_defs[k] > max_svf ? P->ev_defs[k] : max_svf;
+    }
+    *n_evs = 0;
+    int overflow = 0;
+    for (uint32_t lane = 0; lane < batch; ++lane) {
+        ctx_t c = {P, batch, lane, 1, pars, T, mode};
+        /* ---- jet (src/taylor_02.cpp:1211-1330 with sv_funcs: order p of the u variables up to max_svf_idx) ---- */
+        compute_jet(&c, state, t_hi);
+        if (max_svf >= n_eq) {
+            const real_t time_v = t_hi[lane];
+            for (uint32_t i = n_eq; i <= max_svf; ++i) {
+                TAPE(&c, p, i) = diff_op(&c, &P->ops[i - n_eq], i, p, time_v);
+            }
+        }
+        /* ---- step size (src/taylor_00.cpp:102-273, the sv_funcs take part in the three norms) ---- */
+        const double mdt = max_delta_t != NULL ? max_delta_t[lane] : INFINITY;
+        double m0, mp, mp1;
+        {
+            const uint32_t nn = n_eq + n_ev;
+            double *v0 = (double *)malloc(sizeof(double) * 3u * nn), *vp = v0 + nn, *vp1 = vp + nn;
+            for (uint32_t i = 0; i < nn; ++i) {
+                const uint32_t u = i < n_eq ? i : P->ev_defs[i - n_eq];
+                v0[i] = fabs(TAPE(&c, 0, u));
+                vp[i] = fabs(TAPE(&c, p, u));
+                vp1[i] = fabs(TAPE(&c, p - 1u, u));
+            }
+            if (mode & ORACLE_PAIRWISE) {
+                m0 = pairwise_max(v0, nn);
+                mp = pairwise_max(vp, nn);
+                mp1 = pairwise_max(vp1, nn);
+            } else {
+                m0 = v0[0];
+                mp = vp[0];
+                mp1 = vp1[0];
+                for (uint32_t i = 1; i < nn; ++i) {
+                    m0 = std_max(m0, v0[i]);
+                    mp = std_max(mp, vp[i]);
+                    mp1 = std_max(mp1, vp1[i]);
+                }
+            }
+            free(v0);
+        }
+        const double num_rho = (m0 <= 1.) ? 1. : m0;
+        const double rho_m = std_min(pow(num_rho / mp, 1. / (double)p), pow(num_rho / mp1, 1. / (double)(p - 1u)));
+        double h = std_min(rho_m * rhofac_of(p), fabs(mdt));
+        h = (mdt < 0.) ? -1. * h : 1. * h;
+        /* ---- g_eps (src/taylor_adaptive_batch.cpp:746-773) ---- */
+        double g_eps;
+        if (isfinite(m0)) {
+            const double max_r_size = m0 < 1. ? tol : tol * m0;
+            g_eps = max_r_size < DBL_EPSILON * m0 ? DBL_EPSILON * m0 : max_r_size;
+        } else {
+            g_eps = INFINITY;
+        }
+        /* ---- Taylor coefficients of the state variables and of the event equations ---- */
+        for (uint32_t i = 0; i < n_eq + n_ev; ++i) {
+            const uint32_t u = i < n_eq ? i : P->ev_defs[i - n_eq];
+            for (uint32_t o = 0; o <= p; ++o) {
+                tc[((size_t)i * pp1 + o) * batch + lane] = TAPE(&c, o, u);
+            }
+        }
+        /* ---- detection ---- */
+        ev_list d_tes = {NULL, 0, 0}, d_ntes = {NULL, 0, 0};
+        for (uint32_t k = 0; k < n_ev; ++k) {
+            for (uint32_t o = 0; o <= p; ++o) {
+                poly[o] = tc[((size_t)(n_eq + k) * pp1 + o) * batch + lane];
+            }
+            if (ed_fex_check(poly, p, h, h < 0.)) {
+                continue;
+            }
+            const int term = k < n_te;
+            const oracle_event proto = {lane, term ? k : k - n_te, term, 0, 0., 0.};
+            const double *cdp = (term && cd_on[(size_t)lane * n_te + k]) ? cd + ((size_t)lane * n_te + k) * 2u : NULL;
+            ed_detect_one(poly, p, h, g_eps, dirs[k], cdp, bc, proto, term ? &d_tes : &d_ntes);
+        }
+        if (d_tes.n > 1u) {
+            qsort(d_tes.v, d_tes.n, sizeof(oracle_event), ev_cmp_abs_t);
+        }
+        if (d_ntes.n > 1u) {
+            qsort(d_ntes.v, d_ntes.n, sizeof(oracle_event), ev_cmp_abs_t);
+        }
+        if (d_tes.n != 0u) {
+            h = d_tes.v[0].t;
+        }
+        /* ---- state update by the dense-output function (:800), time, outcome ---- */
+        {
+            double *tau = (double *)malloc(sizeof(double) * batch), *out = (double *)malloc(sizeof(double) * (size_t)n_eq * batch);
+            for (uint32_t l = 0; l < batch; ++l) {
+                tau[l] = h;
+            }
+            SYM(oracle_d_output)(P, batch, tc, tau, out);
+            for (uint32_t i = 0; i < n_eq; ++i) {
+                state[(size_t)i * batch + lane] = out[(size_t)i * batch + lane];
+            }
+            free(tau);
+            free(out);
+        }
+        int nf = 0;
+        for (uint32_t i = 0; i < n_eq; ++i) {
+            nf = nf || !isfinite(state[(size_t)i * batch + lane]);
+        }
+        const dfl nt = dfl_add((dfl){t_hi[lane], t_lo[lane]}, (dfl){h, 0.});
+        t_hi[lane] = nt.hi;
+        t_lo[lane] = nt.lo;
+        last_h[lane] = h;
+        if (!(isfinite(nt.hi) && isfinite(nt.lo)) || nf) {
+            outcome[lane] = HY_OUTCOME_ERR_NF_STATE;
+        } else {
+            /* Cooldowns (:848-865). */
+            for (uint32_t k = 0; k < n_te; ++k) {
+                const size_t ci = (size_t)lane * n_te + k;
+                if (cd_on[ci]) {
+                    const double tmpv = cd[2u * ci] + h;
+                    if (fabs(tmpv) >= cd[2u * ci + 1u]) {
+                        cd_on[ci] = 0;
+                    } else {
+                        cd[2u * ci] = tmpv;
+                    }
+                }
+            }
+            /* Non-terminal events before the first terminal one (:871-876). */
+            for (uint32_t k = 0; k < d_ntes.n; ++k) {
+                if (d_tes.n != 0u && !(fabs(d_ntes.v[k].t) < fabs(h))) {
+                    break;
+                }
+                if (*n_evs < evs_cap) {
+                    evs[*n_evs] = d_ntes.v[k];
+                } else {
+                    overflow = 1;
+                }
+                ++*n_evs;
+            }
+            if (d_tes.n != 0u) {
+                const oracle_event te = d_tes.v[0];
+                const size_t ci = (size_t)lane * n_te + te.idx;
+                cd_on[ci] = 1;
+                cd[2u * ci] = 0.;
+                cd[2u * ci + 1u] = cooldowns[te.idx] >= 0. ? cooldowns[te.idx] : ed_deduce_cooldown(g_eps, te.abs_der);
+                if (*n_evs < evs_cap) {
+                    evs[*n_evs] = te;
+                } else {
+                    overflow = 1;
+                }
+                ++*n_evs;
+                outcome[lane] = -(int64_t)te.idx - 1;
+            } else {
+                outcome[lane] = h == mdt ? HY_OUTCOME_TIME_LIMIT : HY_OUTCOME_SUCCESS;
+            }
+        }
+        free(d_tes.v);
+        free(d_ntes.v);
+    }
+    free(T);
+    free(bc);
+    free(poly);
+    return overflow ? 2 : 0;
+}
+
+#endif
+
 /* Raw jet for the closed-form tests: tape[o * n_uvars + u] for lane `lane` (scalar build only). */
 #if ORACLE_W == 1
 int oracle_jet_w1(const hy_program_desc *P, uint32_t batch, const double *state, const double *pars, const double *t_hi,

@@ -39,9 +39,9 @@ def test_sharded_equals_unsharded_bit_for_bit(devs):
     assert many._b.kernel_info()["tape"] == one._b.kernel_info()["tape"] == "nbody"
 
     # step(), step(max_delta_t), step_backward() with write_tc
-    for args in (dict(), dict(max_delta_t=np.linspace(0.01, 0.5, batch)), dict(write_tc=True)):
-        one.step(**args)
-        many.step(**args)
+    for args in ((), (np.linspace(0.01, 0.5, batch),), (None, True)):
+        one.step(*args)
+        many.step(*args)
         _same(one, many)
         assert one.step_res == many.step_res
     assert np.array_equal(one.tc, many.tc)

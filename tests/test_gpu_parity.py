@@ -511,15 +511,22 @@ def test_nbody32_parity(tape):
 
 
 @pytest.mark.gpu
-def test_ffnn_parity():
+@pytest.mark.parametrize("tape", ["nn", "global-cta"])
+def test_ffnn_parity(tape):
     """model::ffnn right-hand side (3 x 64 tanh, order 15): 10476 u variables per lane, sums of 64 products, tanh
-    recurrences; a step and propagate_until(1) against the oracle; identical step counts."""
+    recurrences; a step and propagate_until(1) against the oracle; identical step counts. Automatic selection = the
+    dense-network kernel: its layers are matrix products on the FP64 tensor cores, which sum the same 64 products of a
+    neuron in another association (fused) than the reference's nested 8-term sums (src/math/sum.cpp:185-238) - the
+    tolerances below (the ones of the generic kernel) bound that difference."""
     from common import FFNN_TOL, ffnn_batch_state, sys_ffnn
-    batch = 16
+    batch = 17  # (odd: the last CTA of the dense-network kernel owns one lane only)
     st = ffnn_batch_state(batch)
     P = hb.Program(sys_ffnn(), tol=FFNN_TOL)
     assert (P.n_eq, P.order) == (4, 15)
     ta = hb.taylor_adaptive_batch(sys_ffnn(), st, batch, tol=FFNN_TOL)
+    assert ta._b.kernel_info()["tape"] == "nn"
+    ta._b.set_kernel(tape)
+    assert ta._b.kernel_info()["tape"] == tape
     o = oracle.OracleIntegrator(P, st, batch, mode=oracle.FMA)
     ta.step(write_tc=True)
     o.step(write_tc=True)

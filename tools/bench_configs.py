@@ -74,6 +74,9 @@ def main():
             run("nbody N=32, 8192 lanes, propagate_until(1), warp teams", hb.Program(sys_nbody32()), st, 1.0, tape="global")
             run("nbody N=32, 8192 lanes, propagate_until(1), thread-per-lane HBM kernel", hb.Program(sys_nbody32()), st,
                 1.0, tape="hbm")
+    if "nnsmall" in which:
+        run("ffnn 3x64 tanh order 15, 16384 lanes, propagate_until(0.5)", hb.Program(sys_ffnn(), tol=FFNN_TOL),
+            ffnn_batch_state(1 << 14), 0.5)
     if "nn" in which:
         run("ffnn 3x64 tanh order 15, 262144 lanes, propagate_until(0.5)", hb.Program(sys_ffnn(), tol=FFNN_TOL),
             ffnn_batch_state(1 << 18), 0.5)
