@@ -16,7 +16,7 @@ from ._capi import lib, check, HyError  # noqa: F401
 
 __all__ = [
     "expression", "make_vars", "par", "time", "sin", "cos", "tanh", "exp", "log", "sigmoid", "relu", "relup", "sqrt", "square", "pow", "sum",
-    "prod", "model", "taylor_adaptive_batch", "continuous_output_batch", "taylor_outcome", "Program", "Batch", "order_from_tol", "HyError",
+    "prod", "model", "taylor_adaptive_batch", "t_event_batch", "nt_event_batch", "event_direction", "continuous_output_batch", "taylor_outcome", "Program", "Batch", "order_from_tol", "HyError",
 ]
 
 
@@ -223,22 +223,32 @@ def order_from_tol(tol):
 class Program:
     """The lowered Taylor decomposition of an ODE system (include/heyoka_b200.h, section B)."""
 
-    def __init__(self, sys, tol=0.0, high_accuracy=False, _handle=None):
+    def __init__(self, sys, tol=0.0, high_accuracy=False, _handle=None, events=()):
+        """events: the event equations (terminal events first), decomposed together with the system like
+        taylor_add_adaptive_step_with_events() does (src/taylor_00.cpp:605)."""
         if _handle is not None:
             self._h = _handle
         else:
             n = len(sys)
             self._keep = [(expression._wrap(lhs), expression._wrap(rhs)) for lhs, rhs in sys]
+            self._keep_ev = [expression._wrap(e) for e in events]
             lhs = (C.c_void_p * n)(*[p[0]._h for p in self._keep])
             rhs = (C.c_void_p * n)(*[p[1]._h for p in self._keep])
+            evs = (C.c_void_p * max(len(self._keep_ev), 1))(*[e._h for e in self._keep_ev])
             h = C.c_void_p()
-            check(lib.hy_program_from_sys(lhs, rhs, n, float(tol), int(bool(high_accuracy)), C.byref(h)))
+            check(lib.hy_program_from_sys_ev(lhs, rhs, n, evs, len(self._keep_ev), float(tol), int(bool(high_accuracy)),
+                                             C.byref(h)))
             self._h = h
         d = _capi.hy_program_desc()
         check(lib.hy_program_get_desc(self._h, C.byref(d)))
         self.desc = d
         self.n_eq, self.n_uvars, self.n_pars, self.order = d.n_eq, d.n_uvars, d.n_pars, d.order
         self.high_accuracy = bool(d.high_accuracy)
+        self.n_ev = d.n_ev
+
+    def ev_defs(self):
+        return np.ctypeslib.as_array(C.cast(self.desc.ev_defs, C.POINTER(C.c_uint32)), shape=(self.n_ev,)).copy() \
+            if self.n_ev else np.zeros(0, dtype=np.uint32)
 
     @classmethod
     def from_arrays(cls, n_eq, n_uvars, n_pars, order, ops, args, consts, sv_defs, high_accuracy=False):
@@ -420,6 +430,34 @@ class Batch:
         check(lib.hy_batch_d_output(self._h, _dptr(tau), _dptr(out)))
         return out
 
+    # --- events (include/heyoka_b200.h, section E) ---
+    def set_events(self, n_te, dirs, cooldowns, tol):
+        d = np.ascontiguousarray(dirs, dtype=np.int32)
+        c = np.ascontiguousarray(cooldowns, dtype=np.float64)
+        check(lib.hy_batch_set_events(self._h, int(n_te), d.ctypes.data_as(C.POINTER(C.c_int32)), _dptr(c), float(tol)))
+
+    def events(self):
+        """Events of the last step as (lane, idx, terminal, d_sgn, t, abs_der) tuples, in callback order."""
+        n = lib.hy_batch_n_events(self._h)
+        buf = (_capi.hy_event_rec * max(n, 1))()
+        check(lib.hy_batch_get_events(self._h, buf, n))
+        return [(r.lane, r.idx, bool(r.terminal), r.d_sgn, r.t, r.abs_der) for r in buf[:n]]
+
+    def reset_cooldowns(self, lane=-1):
+        check(lib.hy_batch_reset_cooldowns(self._h, int(lane)))
+
+    def cooldowns(self, n_te):
+        a = np.zeros((max(n_te, 1), self.n), dtype=np.uint8)
+        s, c = np.zeros((max(n_te, 1), self.n)), np.zeros((max(n_te, 1), self.n))
+        check(lib.hy_batch_get_cooldowns(self._h, a.ctypes.data_as(C.POINTER(C.c_uint8)), _dptr(s), _dptr(c)))
+        return a[:n_te], s[:n_te], c[:n_te]
+
+    def tc_events(self, n_ev):
+        """Taylor coefficients of the event equations of the last step, [n_ev, order + 1, batch] (device rows n_eq..)."""
+        out = np.empty((n_ev, self.program.order + 1, self.n))
+        check(lib.hy_batch_download_tc_events(self._h, _dptr(out)))
+        return out
+
     def launch_count(self):
         n = C.c_uint64()
         check(lib.hy_batch_launch_count(self._h, C.byref(n)))
@@ -463,6 +501,40 @@ class continuous_output_batch:
         return self._n
 
 
+class event_direction:
+    """include/heyoka/events.hpp:40-47."""
+    negative = -1
+    any = 0
+    positive = 1
+
+
+class t_event_batch:
+    """Terminal event of a batch integrator (include/heyoka/events.hpp:52-118): callback(ta, d_sgn, batch_idx) -> bool
+    (True: the integration may continue), cooldown < 0 = automatic."""
+
+    def __init__(self, ex, callback=None, cooldown=-1.0, direction=event_direction.any):
+        self.ex = expression._wrap(ex)
+        self.callback = callback
+        cooldown = float(cooldown)
+        if not np.isfinite(cooldown):
+            raise ValueError("Cannot set a non-finite cooldown value for a terminal event")
+        if direction not in (-1, 0, 1):
+            raise ValueError("Invalid value selected for the direction of a terminal event")
+        self.cooldown, self.direction = cooldown, int(direction)
+
+
+class nt_event_batch:
+    """Non-terminal event of a batch integrator (include/heyoka/events.hpp:142-196): callback(ta, t, d_sgn, batch_idx)."""
+
+    def __init__(self, ex, callback, direction=event_direction.any):
+        self.ex = expression._wrap(ex)
+        if callback is None:
+            raise ValueError("Cannot construct a non-terminal event with an empty callback")
+        if direction not in (-1, 0, 1):
+            raise ValueError("Invalid value selected for the direction of a non-terminal event")
+        self.callback, self.direction = callback, int(direction)
+
+
 class taylor_adaptive_batch:
     """Mirror of heyoka::taylor_adaptive_batch<double> (include/heyoka/taylor.hpp:780-1121).
 
@@ -476,9 +548,10 @@ class taylor_adaptive_batch:
         batch_size = int(batch_size)
         if batch_size == 0:
             raise ValueError("The batch size in an adaptive Taylor integrator cannot be zero")
-        if t_events or nt_events:
-            raise NotImplementedError("Event detection is not supported by the B200 batch integrator")
-        self._prog = Program(sys, tol=tol, high_accuracy=high_accuracy)
+        self._tes, self._ntes = list(t_events or []), list(nt_events or [])
+        self._with_events = bool(self._tes or self._ntes)
+        self._prog = Program(sys, tol=tol, high_accuracy=high_accuracy,
+                             events=[e.ex for e in self._tes] + [e.ex for e in self._ntes])
         P = self._prog
         state = np.array(state, dtype=np.float64)
         # Size checks of finalise_ctor_impl(), src/taylor_adaptive_batch.cpp:164-274.
@@ -514,13 +587,19 @@ class taylor_adaptive_batch:
         self._tol = float(tol) if tol > 0 else float(np.finfo(np.float64).eps)
         self._batch_size = batch_size
         self._compact_mode = bool(compact_mode)
-        self._b = Batch(P, batch_size, device)
+        self._b = self._make_batch(P, batch_size, device)
         if kernel is not None:
             self._b.set_kernel(**kernel)
+        if self._with_events:
+            self._b.set_events(len(self._tes), [e.direction for e in self._tes] + [e.direction for e in self._ntes],
+                               [e.cooldown for e in self._tes], self._tol)
         self._last_h = np.zeros(batch_size)
         self._step_res = None
         self._prop_res = None
         self._tc = None
+
+    def _make_batch(self, P, batch_size, device):
+        return Batch(P, batch_size, device)
 
     # --- getters -------------------------------------------------------------------------------
     def get_batch_size(self):
@@ -604,6 +683,82 @@ class taylor_adaptive_batch:
         if wtc:
             self._tc = self._b.tc()
 
+    def with_events(self):
+        return self._with_events
+
+    def get_t_events(self):
+        return self._tes
+
+    def get_nt_events(self):
+        return self._ntes
+
+    def reset_cooldowns(self, i=None):
+        if not self._with_events:
+            raise ValueError("No events were defined for this integrator")
+        self._b.reset_cooldowns(-1 if i is None else int(i))
+
+    def _step_impl(self, max_delta_ts, backward, write_tc):
+        self._push()
+        self._b.step(max_delta_ts, backward=backward, write_tc=write_tc)
+        # With events the Taylor coefficients are written unconditionally (src/taylor_adaptive_batch.cpp:776).
+        self._pull(write_tc or self._with_events)
+        oc, h = self._b.step_res()
+        self._step_res = list(zip(oc.tolist(), h.tolist()))
+        if self._with_events:
+            self._run_event_callbacks()
+
+    def _run_event_callbacks(self):
+        """The callback part of the events branch of step_impl() (src/taylor_adaptive_batch.cpp:803-1033)."""
+        evs = self._b.events()
+        if not evs:
+            return
+        t_copy = (self._t_hi.copy(), self._t_lo.copy())
+        excs = []
+        lanes = sorted({e[0] for e in evs})
+        for lane in lanes:
+            mine = [e for e in evs if e[0] == lane]
+            h = self._last_h[lane]
+            thrown = False
+            for (_, idx, terminal, d_sgn, t, _ad) in mine:
+                if terminal:
+                    continue
+                # new_time - last_h + t in double-length arithmetic (:889).
+                hi, lo = _dfloat_add(t_copy[0][lane], t_copy[1][lane], -h, 0.0)
+                hi, lo = _dfloat_add(hi, lo, t, 0.0)
+                try:
+                    self._ntes[idx].callback(self, float(hi), d_sgn, lane)
+                except Exception as e:  # noqa: BLE001 - collected and re-raised below like the reference
+                    excs.append((lane, e))
+                    thrown = True
+                    break
+            if thrown:
+                continue
+            te = [e for e in mine if e[2]]
+            if te:
+                _, idx, _, d_sgn, _t, _ad = te[0]
+                ret = False
+                cb = self._tes[idx].callback
+                if cb is not None:
+                    try:
+                        ret = bool(cb(self, d_sgn, lane))
+                    except Exception as e:  # noqa: BLE001
+                        excs.append((lane, e))
+                        continue
+                self._step_res[lane] = (idx if ret else -idx - 1, self._step_res[lane][1])
+        if len(excs) == 1:
+            raise excs[0][1]
+        if excs:
+            msg = "Two or more exceptions were raised during the execution of event callbacks in a batch integrator:\n\n"
+            for lane, e in excs:
+                msg += "Batch index #%d:\n    Exception type: %s\n    Exception message: %s\n\n" % (
+                    lane, type(e).__name__, e)
+            raise RuntimeError(msg)
+        same = lambda a, b: np.array_equal(a, b, equal_nan=True)  # noqa: E731
+        if not (same(self._t_hi, t_copy[0]) and same(self._t_lo, t_copy[1])):
+            i = int(np.argmax(~((self._t_hi == t_copy[0]) | (np.isnan(self._t_hi) & np.isnan(t_copy[0])))))
+            raise RuntimeError("The invocation of one or more event callbacks resulted in the alteration of the time "
+                               "coordinate of the integrator at the batch index %d - this is not supported" % i)
+
     def step(self, max_delta_ts=None, write_tc=False):
         if max_delta_ts is not None:
             m = np.asarray(max_delta_ts, dtype=np.float64)
@@ -615,22 +770,83 @@ class taylor_adaptive_batch:
                 raise ValueError("Cannot use a nan max_delta_t in the step() function of an adaptive Taylor "
                                  "integrator in batch mode")
             max_delta_ts = m
-        self._push()
-        self._b.step(max_delta_ts, backward=False, write_tc=write_tc)
-        self._pull(write_tc)
-        oc, h = self._b.step_res()
-        self._step_res = list(zip(oc.tolist(), h.tolist()))
+        self._step_impl(max_delta_ts, False, write_tc)
 
     def step_backward(self, write_tc=False):
-        self._push()
-        self._b.step(None, backward=True, write_tc=write_tc)
-        self._pull(write_tc)
-        oc, h = self._b.step_res()
-        self._step_res = list(zip(oc.tolist(), h.tolist()))
+        self._step_impl(None, True, write_tc)
+
+    def _propagate_until_host(self, th, tl, max_delta_t, max_steps, write_tc, callback):
+        """The reference's lock-step loop (src/taylor_adaptive_batch.cpp:1256-1530) on the host, one device step per
+        iteration: integrators with events (their callbacks are host code) and step callbacks."""
+        n = self._batch_size
+        tl = np.zeros(n) if tl is None else tl
+        if not (np.all(np.isfinite(th)) and np.all(np.isfinite(tl))):
+            raise ValueError("A non-finite time was passed to the propagate_until() function of an adaptive Taylor "
+                             "integrator in batch mode")
+        if max_delta_t is not None:
+            if np.any(np.isnan(max_delta_t)):
+                raise ValueError("A nan max_delta_t was passed to the propagate_until() function of an adaptive Taylor "
+                                 "integrator in batch mode")
+            if np.any(max_delta_t <= 0):
+                raise ValueError("A non-positive max_delta_t was passed to the propagate_until() function of an "
+                                 "adaptive Taylor integrator in batch mode")
+        mdt = np.full(n, np.inf) if max_delta_t is None else np.asarray(max_delta_t, dtype=np.float64)
+        rem_hi, rem_lo = _dfloat_add(th, tl, -self._t_hi, -self._t_lo)
+        if not (np.all(np.isfinite(rem_hi)) and np.all(np.isfinite(rem_lo))):
+            raise OverflowError("The final time passed to the propagate_until() function of an adaptive Taylor "
+                                "integrator in batch mode results in an overflow condition")
+        t_dir = (rem_hi > 0) | ((rem_hi == 0) & (rem_lo >= 0))
+        ts_count = [0] * n
+        min_h, max_h = [float("inf")] * n, [0.0] * n
+        iters = 0
+        SUCCESS, STEP_LIMIT, NF, CB_STOP = _capi.HY_OUTCOME_SUCCESS, _capi.HY_OUTCOME_STEP_LIMIT, \
+            _capi.HY_OUTCOME_ERR_NF_STATE, _capi.HY_OUTCOME_CB_STOP
+        self._prop_res = [(0, 0.0, 0.0, 0)] * n
+        while True:
+            cur = np.empty(n)
+            for i in range(n):
+                # min(dfloat(max_delta_t), rem) forward, max(dfloat(-max_delta_t), rem) backward, cast to double.
+                if t_dir[i]:
+                    cur[i] = mdt[i] if (mdt[i], 0.0) < (rem_hi[i], rem_lo[i]) else rem_hi[i]
+                else:
+                    cur[i] = rem_hi[i] if (-mdt[i], 0.0) < (rem_hi[i], rem_lo[i]) else -mdt[i]
+            self._step_impl(cur, False, write_tc)
+            n_done, nfs, ste = 0, False, False
+            for i in range(n):
+                oc, h = self._step_res[i]
+                if oc == NF:
+                    nfs = True
+                else:
+                    ts_count[i] += int(h != 0)
+                    if oc == SUCCESS:
+                        min_h[i], max_h[i] = min(min_h[i], abs(h)), max(max_h[i], abs(h))
+                    ste = ste or (SUCCESS < oc < 0)
+                    if h == rem_hi[i]:
+                        n_done += 1
+                        rem_hi[i] = rem_lo[i] = 0.0
+                    else:
+                        a, b = _dfloat_add(th[i], tl[i], -self._t_hi[i], -self._t_lo[i])
+                        rem_hi[i], rem_lo[i] = float(a), float(b)
+                self._prop_res[i] = (oc, min_h[i], max_h[i], ts_count[i])
+            if nfs:
+                return
+            iters += 1
+            if callback is not None:
+                t_copy = (self._t_hi.copy(), self._t_lo.copy())
+                ret = callback(self)
+                if not (np.array_equal(self._t_hi, t_copy[0]) and np.array_equal(self._t_lo, t_copy[1])):
+                    raise RuntimeError("The invocation of the callback passed to propagate_until() resulted in the "
+                                       "alteration of the time coordinate of the integrator - this is not supported")
+                if not ret:
+                    self._prop_res = [(CB_STOP,) + r[1:] for r in self._prop_res]
+                    return
+            if n_done == n or ste:
+                return
+            if iters == max_steps:
+                self._prop_res = [(STEP_LIMIT,) + r[1:] for r in self._prop_res]
+                return
 
     def propagate_until(self, ts, max_steps=0, max_delta_t=None, write_tc=False, callback=None, c_output=False):
-        if callback is not None:
-            raise NotImplementedError("Callbacks are not supported by the Python mirror (use the C++ class)")
         n = self._batch_size
         if np.ndim(ts) == 0:
             th, tl = np.full(n, float(ts)), None
@@ -651,6 +867,12 @@ class taylor_adaptive_batch:
                 raise ValueError("Invalid number of max timesteps specified in a Taylor integrator in batch mode: the "
                                  "batch size is %d, but the number of specified timesteps is %d" % (n, md.size))
             max_delta_t = md
+        if self._with_events or callback is not None:
+            if c_output:
+                raise NotImplementedError("Continuous output together with events or a callback is not supported by "
+                                          "the B200 batch integrator")
+            self._propagate_until_host(th, np.zeros(n) if tl is None else tl, max_delta_t, max_steps, write_tc, callback)
+            return None
         self._push()
         c_out = None
         if c_output:

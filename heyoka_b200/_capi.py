@@ -18,6 +18,13 @@ HY_ERR_NOT_IMPLEMENTED = -2
 HY_ERR_CUDA = -3
 HY_ERR_OVERFLOW = -4
 
+# taylor_outcome (include/heyoka/taylor.hpp): values below -2^32 so that they never collide with event indices.
+HY_OUTCOME_SUCCESS = -4294967297
+HY_OUTCOME_STEP_LIMIT = -4294967298
+HY_OUTCOME_TIME_LIMIT = -4294967299
+HY_OUTCOME_ERR_NF_STATE = -4294967300
+HY_OUTCOME_CB_STOP = -4294967301
+
 if not os.path.exists(LIB_PATH):
     raise ImportError(
         "heyoka_b200: native library %s not found. Build it with `python -m heyoka_b200.build` (needs nvcc); "
@@ -33,6 +40,11 @@ class hy_program_desc(C.Structure):
         ("ops", C.c_void_p), ("args", C.c_void_p), ("consts", C.c_void_p), ("sv_defs", C.c_void_p),
         ("ev_defs", C.c_void_p),
     ]
+
+
+class hy_event_rec(C.Structure):
+    _fields_ = [("lane", C.c_uint32), ("idx", C.c_uint32), ("terminal", C.c_int32), ("d_sgn", C.c_int32),
+                ("t", C.c_double), ("abs_der", C.c_double)]
 
 
 class hy_batch_ptrs(C.Structure):
@@ -71,6 +83,7 @@ SIGNATURES = {
                                 C.c_uint32, _vpp]),
     "hy_order_from_tol": (C.c_int, [C.c_double, C.POINTER(C.c_uint32)]),
     "hy_program_from_sys": (C.c_int, [_vpp, _vpp, C.c_uint32, C.c_double, C.c_int, _vpp]),
+    "hy_program_from_sys_ev": (C.c_int, [_vpp, _vpp, C.c_uint32, _vpp, C.c_uint32, C.c_double, C.c_int, _vpp]),
     "hy_program_create": (C.c_int, [C.POINTER(hy_program_desc), _vpp]),
     "hy_program_get_desc": (C.c_int, [_vp, C.POINTER(hy_program_desc)]),
     "hy_program_dc_size": (C.c_uint32, [_vp]),
@@ -101,6 +114,12 @@ SIGNATURES = {
     "hy_cout_n_steps": (C.c_uint64, [_vp]),
     "hy_cout_destroy": (None, [_vp]),
     "hy_batch_d_output": (C.c_int, [_vp, _dp, _dp]),
+    "hy_batch_set_events": (C.c_int, [_vp, C.c_uint32, C.POINTER(C.c_int32), _dp, C.c_double]),
+    "hy_batch_n_events": (C.c_uint32, [_vp]),
+    "hy_batch_get_events": (C.c_int, [_vp, C.POINTER(hy_event_rec), C.c_uint32]),
+    "hy_batch_download_tc_events": (C.c_int, [_vp, _dp]),
+    "hy_batch_reset_cooldowns": (C.c_int, [_vp, C.c_int64]),
+    "hy_batch_get_cooldowns": (C.c_int, [_vp, C.POINTER(C.c_uint8), _dp, _dp]),
     "hy_batch_launch_count": (C.c_int, [_vp, C.POINTER(C.c_uint64)]),
     "hy_batch_set_launch_config": (C.c_int, [_vp, C.c_uint32, C.c_uint32]),
     "hy_batch_set_kernel": (C.c_int, [_vp, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]),

@@ -29,6 +29,7 @@
 #include "nn_plan.hpp"
 #include "nn_variants.hpp"
 #include "small_kernels.cuh"
+#include "ev_kernels.cuh"
 #include "program.hpp"
 #include "smem_plan.hpp"
 
@@ -246,6 +247,16 @@ struct hy_batch {
     int opt_nn = -1; // 0: never (HEYOKA_B200_NN=0)
     bool setup_nn();
 
+    // Event detection (section E of the C ABI; ev_kernels.cuh). n_ev > 0: the program carries event equations, every
+    // step is an event step (jet without propagation + detection + propagation cut at the first terminal event).
+    std::uint32_t n_ev = 0, n_te = 0;
+    bool ev_set = false;
+    dev::ev_args eva{};
+    std::vector<void *> ev_allocs;
+    std::vector<hy_event_rec> ev_host; // the events of the last step, in the order the callbacks must run
+    void ev_setup(std::uint32_t n_te_, const std::int32_t *dirs, const double *cooldowns, double tol);
+    void ev_step(const double *max_delta_t, int on_device, int backward);
+
     // Resident arrays.
     double *d_state = nullptr, *d_pars = nullptr, *d_t_hi = nullptr, *d_t_lo = nullptr, *d_last_h = nullptr,
            *d_tc = nullptr, *d_d_out = nullptr;
@@ -328,6 +339,10 @@ void hy_batch::free_all() noexcept
             cudaFree(p);
         }
     }
+    for (void *p : ev_allocs) {
+        cudaFree(p);
+    }
+    ev_allocs.clear();
 }
 
 hy_batch::~hy_batch()
@@ -996,10 +1011,161 @@ void hy_batch::configure(int want_mode, int L, int N, std::uint32_t threads, std
 void hy_batch::ensure_tc()
 {
     if (d_tc == nullptr) {
-        const std::size_t sz = static_cast<std::size_t>(n_eq) * (order + 1u) * n;
+        // (With events, the rows of the event equations follow those of the state variables.)
+        const std::size_t sz = static_cast<std::size_t>(n_eq + n_ev) * (order + 1u) * n;
         d_tc = dalloc<double>(sz);
         HY_CUDA_CHECK(cudaMemsetAsync(d_tc, 0, sizeof(double) * sz, stream));
     }
+}
+
+// ---- Event detection (ev_kernels.cuh) ----
+void hy_batch::ev_setup(std::uint32_t n_te_, const std::int32_t *dirs, const double *cooldowns, double tol)
+{
+    if (n_ev == 0u) {
+        throw std::invalid_argument("This batch was built from a program without event equations");
+    }
+    if (n_te_ > n_ev) {
+        throw std::invalid_argument("The number of terminal events exceeds the number of event equations");
+    }
+    for (std::uint32_t k = 0; k < n_ev; ++k) {
+        if (dirs[k] < -1 || dirs[k] > 1) {
+            throw std::invalid_argument("Invalid value selected for the direction of an event");
+        }
+    }
+    for (std::uint32_t k = 0; k < n_te_; ++k) {
+        if (!std::isfinite(cooldowns[k])) {
+            throw std::invalid_argument("Cannot set a non-finite cooldown value for a terminal event");
+        }
+    }
+    for (void *q : ev_allocs) {
+        HY_CUDA_CHECK(cudaFree(q));
+    }
+    ev_allocs.clear();
+    const auto keep = [this](auto *q) {
+        ev_allocs.push_back(static_cast<void *>(q));
+        return q;
+    };
+    n_te = n_te_;
+    const std::uint32_t p = order, pp1 = p + 1u;
+    dev::ev_args E{};
+    E.n_ev = n_ev;
+    E.n_te = n_te;
+    E.tol = tol;
+    E.max_svf = *std::max_element(prog_host->ev_defs.begin(), prog_host->ev_defs.end());
+    E.ev_defs = keep(dupload(prog_host->ev_defs));
+    E.dirs = keep(dupload(std::vector<int>(dirs, dirs + n_ev)));
+    E.cooldowns = keep(dupload(std::vector<double>(cooldowns, cooldowns + n_te)));
+    // Binomial coefficients, exact in double precision for the orders in use (src/detail/llvm_helpers_ed.cpp:421-455).
+    std::vector<double> bc(static_cast<std::size_t>(pp1) * pp1, 0.);
+    for (std::uint32_t i = 0; i <= p; ++i) {
+        bc[i * pp1] = 1.;
+        for (std::uint32_t j = 1; j <= i; ++j) {
+            bc[i * pp1 + j] = bc[(i - 1u) * pp1 + j - 1u] + (j < i ? bc[(i - 1u) * pp1 + j] : 0.);
+        }
+    }
+    E.bc = keep(dupload(bc));
+    const std::size_t B = n;
+    E.h = keep(dalloc<double>(B));
+    E.mdt = keep(dalloc<double>(B));
+    E.g_eps = keep(dalloc<double>(B));
+    E.cd = keep(dalloc<double>(B * 2u * std::max(n_te, 1u)));
+    E.cd_on = keep(dalloc<unsigned char>(B * std::max(n_te, 1u)));
+    HY_CUDA_CHECK(cudaMemset(E.cd_on, 0, B * std::max(n_te, 1u)));
+    E.cand = keep(dalloc<std::uint32_t>(B * n_ev));
+    E.counters = keep(dalloc<unsigned>(4));
+    E.rec_cap = static_cast<std::uint32_t>(std::min<std::size_t>(std::max<std::size_t>(B * n_ev, 1024u), 1u << 26));
+    E.rec = keep(dalloc<dev::ev_rec>(E.rec_cap));
+    E.te_key = keep(dalloc<unsigned long long>(B));
+    E.te_sel = keep(dalloc<unsigned long long>(B));
+    // One bisection stack per detecting thread: a fraction of the lanes ever needs one at the same time.
+    E.arena_threads = 64u * std::min<std::uint32_t>(n_sms, static_cast<std::uint32_t>((B * n_ev + 63u) / 64u));
+    E.arena = keep(dalloc<double>(static_cast<std::size_t>(dev::EV_STACK) * (pp1 + 2u) * E.arena_threads));
+    eva = E;
+    ev_set = true;
+    ev_host.clear();
+}
+
+void hy_batch::ev_step(const double *d_mdt, int, int backward)
+{
+    if (!ev_set) {
+        throw std::invalid_argument("hy_batch_set_events() must be called before stepping a batch with event equations");
+    }
+    if (mode != 1 || d_scratch == nullptr) {
+        setup_hbm(0, 0);
+    }
+    ensure_tc();
+    const std::uint32_t B = n;
+    dev::run_args R{};
+    R.max_delta_t = d_mdt;
+    R.default_max_delta_t = backward ? -std::numeric_limits<double>::infinity() : std::numeric_limits<double>::infinity();
+    R.counter = d_counter;
+    R.flags = d_flags;
+    HY_CUDA_CHECK(cudaMemsetAsync(d_counter, 0, sizeof(unsigned int), stream));
+    dev::k_ev_jet<<<h_grid, h_threads, 0, stream>>>(prog, view(), R, eva, d_scratch, slab_doubles);
+    HY_CUDA_CHECK(cudaGetLastError());
+    n_launches += 1;
+    unsigned counters[4] = {0u, 0u, 0u, 0u};
+    for (;;) {
+        HY_CUDA_CHECK(cudaMemsetAsync(eva.counters, 0, 4u * sizeof(unsigned), stream));
+        const std::size_t n_pairs = static_cast<std::size_t>(n_ev) * B;
+        dev::k_ev_fex<<<static_cast<unsigned>((n_pairs + 255u) / 256u), 256, 0, stream>>>(prog, view(), eva);
+        dev::k_ev_detect<<<eva.arena_threads / 64u, 64, 0, stream>>>(prog, view(), eva);
+        HY_CUDA_CHECK(cudaGetLastError());
+        n_launches += 2;
+        HY_CUDA_CHECK(cudaMemcpyAsync(counters, eva.counters, sizeof(counters), cudaMemcpyDeviceToHost, stream));
+        HY_CUDA_CHECK(cudaStreamSynchronize(stream));
+        if (counters[1] <= eva.rec_cap) {
+            break;
+        }
+        // More events than record slots (never seen in practice: one slot per (event, lane) pair): grow and redo the
+        // detection, which only reads the jet.
+        const std::uint32_t new_cap = counters[1] + counters[1] / 2u;
+        dev::ev_rec *nr = dalloc<dev::ev_rec>(new_cap);
+        for (auto &q : ev_allocs) {
+            if (q == static_cast<void *>(eva.rec)) {
+                q = nr;
+            }
+        }
+        HY_CUDA_CHECK(cudaFree(eva.rec));
+        eva.rec = nr;
+        eva.rec_cap = new_cap;
+        HY_CUDA_CHECK(cudaMemsetAsync(eva.te_key, 0xff, sizeof(unsigned long long) * B, stream));
+    }
+    const unsigned n_rec = counters[1];
+    if (n_rec != 0u) {
+        dev::k_ev_first<<<(n_rec + 127u) / 128u, 128, 0, stream>>>(view(), eva);
+        ++n_launches;
+    }
+    dev::k_ev_apply<<<(B + 127u) / 128u, 128, 0, stream>>>(prog, view(), eva);
+    ++n_launches;
+    ev_host.clear();
+    if (n_rec != 0u) {
+        dev::k_ev_filter<<<(n_rec + 127u) / 128u, 128, 0, stream>>>(view(), eva);
+        ++n_launches;
+        std::vector<dev::ev_rec> recs(n_rec);
+        HY_CUDA_CHECK(cudaMemcpyAsync(recs.data(), eva.rec, sizeof(dev::ev_rec) * n_rec, cudaMemcpyDeviceToHost, stream));
+        HY_CUDA_CHECK(cudaStreamSynchronize(stream));
+        for (const auto &r : recs) {
+            if (r.live != 0u) {
+                ev_host.push_back(hy_event_rec{r.lane, r.idx, r.terminal, r.d_sgn, r.t, r.abs_der});
+            }
+        }
+        // Per lane: the non-terminal events in time order (src/taylor_adaptive_batch.cpp:789-790: by |t|; equal times
+        // keep the order of the event indices), then the terminal event.
+        std::sort(ev_host.begin(), ev_host.end(), [](const hy_event_rec &a, const hy_event_rec &b) {
+            if (a.lane != b.lane) {
+                return a.lane < b.lane;
+            }
+            if (a.terminal != b.terminal) {
+                return a.terminal < b.terminal;
+            }
+            if (std::abs(a.t) != std::abs(b.t)) {
+                return std::abs(a.t) < std::abs(b.t);
+            }
+            return a.idx < b.idx;
+        });
+    }
+    HY_CUDA_CHECK(cudaGetLastError());
 }
 
 void hy_batch::launch(bool prop, const dev::run_args &R)
@@ -1398,6 +1564,15 @@ int hy_batch_create(const hy_program *p, uint32_t batch, int device, hy_batch **
         if (const char *env = std::getenv("HEYOKA_B200_TAPE")) {
             const std::string s{env};
             want = s == "hbm" ? 1 : (s == "smem" ? 2 : 0);
+        }
+        b->n_ev = static_cast<std::uint32_t>(p->ev_defs.size());
+        if (b->n_ev != 0u) {
+            // Event detection runs on the thread-per-lane kernel family (ev_kernels.cuh).
+            if (p->order + 1u > static_cast<std::uint32_t>(dev::EV_MAXP1)) {
+                throw hy::detail::not_implemented_error("Event detection supports Taylor orders up to "
+                                                        + std::to_string(dev::EV_MAXP1 - 1));
+            }
+            want = 1;
         }
         b->configure(want, 0, 0, 0, 0);
 
@@ -1831,6 +2006,12 @@ int hy_batch_step(hy_batch *b, const double *max_delta_t, int on_device, int bac
                 }
             }
         }
+        if (b->n_ev != 0u) {
+            // A batch with event equations: every step detects events (the Taylor coefficients are always written,
+            // src/taylor_adaptive_batch.cpp:776); hy_batch_get_events() returns what was found.
+            b->ev_step(stage(b, max_delta_t, on_device, 0), on_device, backward);
+            return HY_OK;
+        }
         dev::run_args R{};
         R.max_delta_t = stage(b, max_delta_t, on_device, 0);
         R.default_max_delta_t
@@ -1849,6 +2030,10 @@ int hy_batch_propagate_until(hy_batch *b, const double *t_final_hi, const double
                              uint64_t max_steps, int write_tc)
 {
     try {
+        if (b->n_ev != 0u) {
+            throw hy::detail::not_implemented_error("A batch with event equations is propagated by the front end's lock-step "
+                                                    "loop over hy_batch_step(), not by the device-resident propagation");
+        }
         device_guard guard(b->device);
         if (t_final_hi == nullptr) {
             throw std::invalid_argument("Null final times passed to hy_batch_propagate_until()");
@@ -1886,6 +2071,10 @@ int hy_batch_propagate_until_dev(hy_batch *b, const double *d_t_final_hi, const 
                                  const double *d_max_delta_t, uint64_t max_steps, int write_tc, int *any_nf_or_limit)
 {
     try {
+        if (b->n_ev != 0u) {
+            throw hy::detail::not_implemented_error("A batch with event equations is propagated by the front end's lock-step "
+                                                    "loop over hy_batch_step(), not by the device-resident propagation");
+        }
         if (!b->shards.empty()) {
             throw std::invalid_argument("hy_batch_propagate_until_dev() is not available on a multi-device batch");
         }
@@ -1919,6 +2108,10 @@ int hy_batch_propagate_grid(hy_batch *b, const double *grid, uint64_t n_pts, con
         }
     };
     try {
+        if (b->n_ev != 0u) {
+            throw hy::detail::not_implemented_error("A batch with event equations is propagated by the front end's lock-step "
+                                                    "loop over hy_batch_step(), not by the device-resident propagation");
+        }
         if (b == nullptr || grid == nullptr || out == nullptr) {
             throw std::invalid_argument("Null pointer passed to hy_batch_propagate_grid()");
         }
@@ -2145,6 +2338,10 @@ int hy_batch_propagate_until_cout(hy_batch *b, const double *t_final_hi, const d
         }
     };
     try {
+        if (b->n_ev != 0u) {
+            throw hy::detail::not_implemented_error("A batch with event equations is propagated by the front end's lock-step "
+                                                    "loop over hy_batch_step(), not by the device-resident propagation");
+        }
         if (b != nullptr && !b->shards.empty()) {
             throw hy::detail::not_implemented_error("Continuous output is not available on a multi-device batch");
         }
@@ -2376,6 +2573,113 @@ int hy_batch_d_output(hy_batch *b, const double *tau, double *out)
                                           b->stream));
         }
         HY_CUDA_CHECK(cudaStreamSynchronize(b->stream));
+        return HY_OK;
+    } catch (...) {
+        return translate_exception();
+    }
+}
+
+/* ---- E. events ---- */
+int hy_batch_set_events(hy_batch *b, uint32_t n_te, const int32_t *dirs, const double *cooldowns, double tol)
+{
+    try {
+        if (b == nullptr || dirs == nullptr || (n_te != 0u && cooldowns == nullptr)) {
+            throw std::invalid_argument("Null pointer passed to hy_batch_set_events()");
+        }
+        if (!b->shards.empty()) {
+            throw hy::detail::not_implemented_error("Event detection is not available on a multi-device batch");
+        }
+        device_guard guard(b->device);
+        HY_CUDA_CHECK(cudaStreamSynchronize(b->stream));
+        b->ev_setup(n_te, dirs, cooldowns, tol);
+        return HY_OK;
+    } catch (...) {
+        return translate_exception();
+    }
+}
+
+uint32_t hy_batch_n_events(const hy_batch *b)
+{
+    return b == nullptr ? 0u : static_cast<uint32_t>(b->ev_host.size());
+}
+
+int hy_batch_get_events(const hy_batch *b, hy_event_rec *out, uint32_t cap)
+{
+    if (b == nullptr || (out == nullptr && cap != 0u)) {
+        hy::detail::set_last_error("Null pointer passed to hy_batch_get_events()");
+        return HY_ERR_INVALID_ARG;
+    }
+    const std::size_t m = std::min<std::size_t>(cap, b->ev_host.size());
+    std::copy(b->ev_host.begin(), b->ev_host.begin() + static_cast<std::ptrdiff_t>(m), out);
+    return HY_OK;
+}
+
+int hy_batch_download_tc_events(hy_batch *b, double *out)
+{
+    try {
+        if (b == nullptr || out == nullptr) {
+            throw std::invalid_argument("Null pointer passed to hy_batch_download_tc_events()");
+        }
+        if (b->n_ev == 0u || b->d_tc == nullptr) {
+            throw std::invalid_argument("No Taylor coefficients of event equations are available");
+        }
+        device_guard guard(b->device);
+        const std::size_t row = static_cast<std::size_t>(b->order + 1u) * b->n;
+        HY_CUDA_CHECK(cudaMemcpyAsync(out, b->d_tc + row * b->n_eq, sizeof(double) * row * b->n_ev, cudaMemcpyDeviceToHost,
+                                      b->stream));
+        HY_CUDA_CHECK(cudaStreamSynchronize(b->stream));
+        return HY_OK;
+    } catch (...) {
+        return translate_exception();
+    }
+}
+
+int hy_batch_reset_cooldowns(hy_batch *b, int64_t lane)
+{
+    try {
+        if (b == nullptr) {
+            throw std::invalid_argument("Null batch");
+        }
+        if (!b->ev_set) {
+            throw std::invalid_argument("No events are defined for this integrator");
+        }
+        if (lane >= static_cast<int64_t>(b->n)) {
+            throw std::invalid_argument("Cannot reset the cooldowns at batch index " + std::to_string(lane)
+                                        + ": the batch size is only " + std::to_string(b->n));
+        }
+        device_guard guard(b->device);
+        const std::size_t m = static_cast<std::size_t>(b->n_te) * b->n;
+        if (m != 0u) {
+            dev::k_ev_reset_cd<<<static_cast<unsigned>((m + 255u) / 256u), 256, 0, b->stream>>>(
+                b->eva, b->n, lane < 0 ? 0xffffffffu : static_cast<std::uint32_t>(lane));
+            HY_CUDA_CHECK(cudaGetLastError());
+        }
+        return HY_OK;
+    } catch (...) {
+        return translate_exception();
+    }
+}
+
+int hy_batch_get_cooldowns(hy_batch *b, uint8_t *active, double *spent, double *cooldown)
+{
+    try {
+        if (b == nullptr || !b->ev_set) {
+            throw std::invalid_argument("No events are defined for this integrator");
+        }
+        device_guard guard(b->device);
+        const std::size_t m = static_cast<std::size_t>(b->n_te) * b->n;
+        std::vector<double> cd(2u * m);
+        if (m != 0u) {
+            HY_CUDA_CHECK(cudaMemcpyAsync(active, b->eva.cd_on, m, cudaMemcpyDeviceToHost, b->stream));
+            HY_CUDA_CHECK(cudaMemcpyAsync(cd.data(), b->eva.cd, sizeof(double) * 2u * m, cudaMemcpyDeviceToHost, b->stream));
+        }
+        HY_CUDA_CHECK(cudaStreamSynchronize(b->stream));
+        for (std::uint32_t k = 0; k < b->n_te; ++k) {
+            for (std::uint32_t l = 0; l < b->n; ++l) {
+                spent[static_cast<std::size_t>(k) * b->n + l] = cd[(static_cast<std::size_t>(k) * 2u) * b->n + l];
+                cooldown[static_cast<std::size_t>(k) * b->n + l] = cd[(static_cast<std::size_t>(k) * 2u + 1u) * b->n + l];
+            }
+        }
         return HY_OK;
     } catch (...) {
         return translate_exception();

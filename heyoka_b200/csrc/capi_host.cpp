@@ -345,15 +345,15 @@ int hy_order_from_tol(double tol, uint32_t *order)
     }
 }
 
-int hy_program_from_sys(const hy_ex *const *lhs, const hy_ex *const *rhs, uint32_t n_eq, double tol, int high_accuracy,
-                        hy_program **out)
+int hy_program_from_sys_ev(const hy_ex *const *lhs, const hy_ex *const *rhs, uint32_t n_eq, const hy_ex *const *evs,
+                           uint32_t n_ev, double tol, int high_accuracy, hy_program **out)
 {
     try {
-        if (lhs == nullptr || rhs == nullptr || out == nullptr) {
+        if (lhs == nullptr || rhs == nullptr || out == nullptr || (n_ev != 0u && evs == nullptr)) {
             throw std::invalid_argument("Null pointer passed to hy_program_from_sys()");
         }
         std::vector<std::pair<hy::expression, hy::expression>> sys;
-        std::vector<hy::expression> all_rhs;
+        std::vector<hy::expression> all_rhs, ev_ex;
         for (uint32_t i = 0; i < n_eq; ++i) {
             if (lhs[i] == nullptr || rhs[i] == nullptr) {
                 throw std::invalid_argument("Null expression handle");
@@ -361,7 +361,15 @@ int hy_program_from_sys(const hy_ex *const *lhs, const hy_ex *const *rhs, uint32
             sys.emplace_back(lhs[i]->ex, rhs[i]->ex);
             all_rhs.push_back(rhs[i]->ex);
         }
-        hy::validate_ode_sys(sys);
+        for (uint32_t i = 0; i < n_ev; ++i) {
+            if (evs[i] == nullptr) {
+                throw std::invalid_argument("Null expression handle");
+            }
+            ev_ex.push_back(evs[i]->ex);
+            // The parameters of the event equations count (test/taylor_adaptive_batch.cpp:1015-1060).
+            all_rhs.push_back(evs[i]->ex);
+        }
+        hy::validate_ode_sys(sys, ev_ex);
 
         // Tolerance checks: src/taylor_adaptive_batch.cpp:225-241.
         if (!(tol == tol) || tol == std::numeric_limits<double>::infinity() || tol < 0) {
@@ -374,14 +382,21 @@ int hy_program_from_sys(const hy_ex *const *lhs, const hy_ex *const *rhs, uint32
         }
         const auto order = hy::detail::taylor_order_from_tol(tol);
 
-        auto [dc, sv] = hy::taylor_decompose_sys(sys, {});
+        auto [dc, sv] = hy::taylor_decompose_sys(sys, ev_ex);
         const auto n_pars = hy::get_param_size(all_rhs);
         auto p = hy::detail::lower_decomposition(dc, n_eq, n_pars, order, high_accuracy != 0);
+        p.ev_defs = std::move(sv);
         *out = new hy_program(std::move(p));
         return HY_OK;
     } catch (...) {
         return translate_exception();
     }
+}
+
+int hy_program_from_sys(const hy_ex *const *lhs, const hy_ex *const *rhs, uint32_t n_eq, double tol, int high_accuracy,
+                        hy_program **out)
+{
+    return hy_program_from_sys_ev(lhs, rhs, n_eq, nullptr, 0u, tol, high_accuracy, out);
 }
 
 int hy_program_create(const hy_program_desc *d, hy_program **out)
@@ -403,6 +418,17 @@ int hy_program_create(const hy_program_desc *d, hy_program **out)
         p.args.assign(d->args, d->args + d->n_args);
         p.consts.assign(d->consts, d->consts + d->n_consts);
         p.sv_defs.assign(d->sv_defs, d->sv_defs + d->n_eq);
+        if (d->n_ev != 0u) {
+            if (d->ev_defs == nullptr) {
+                throw std::invalid_argument("Invalid program: event equations without their definitions");
+            }
+            p.ev_defs.assign(d->ev_defs, d->ev_defs + d->n_ev);
+            for (const auto u : p.ev_defs) {
+                if (u >= p.n_uvars) {
+                    throw std::invalid_argument("Invalid program: an event equation refers to a u variable out of range");
+                }
+            }
+        }
         hy::detail::validate_program(p);
         *out = new hy_program(std::move(p));
         return HY_OK;

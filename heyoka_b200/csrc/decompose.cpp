@@ -574,7 +574,7 @@ void replace_numbers(taylor_dc_t &dc, std::size_t n_eq)
 
 } // namespace
 
-void validate_ode_sys(const std::vector<std::pair<expression, expression>> &sys)
+void validate_ode_sys(const std::vector<std::pair<expression, expression>> &sys, const std::vector<expression> &ev_funcs)
 {
     if (sys.empty()) {
         throw std::invalid_argument("Cannot integrate a system of zero equations");
@@ -598,6 +598,17 @@ void validate_ode_sys(const std::vector<std::pair<expression, expression>> &sys)
             if (lhs_vars.find(var) == lhs_vars.end()) {
                 throw std::invalid_argument("Error in the right-hand side of an ODE system: the variable '" + var
                                             + "' appears in the right-hand side but not in the left-hand side");
+            }
+        }
+    }
+
+    // The event functions may only contain state variables (src/detail/validate_ode_sys.cpp:131-145).
+    for (const auto &ev : ev_funcs) {
+        for (const auto &var : get_variables(ev)) {
+            if (lhs_vars.find(var) == lhs_vars.end()) {
+                throw std::invalid_argument("Invalid system of differential equations detected: an event function "
+                                            "contains the variable '"
+                                            + var + "', which is not a state variable");
             }
         }
     }

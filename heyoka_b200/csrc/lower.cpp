@@ -597,5 +597,7 @@ hy_program_desc hy_program::desc() const
     d.args = args.data();
     d.consts = consts.data();
     d.sv_defs = sv_defs.data();
+    d.n_ev = static_cast<std::uint32_t>(ev_defs.size());
+    d.ev_defs = ev_defs.empty() ? nullptr : ev_defs.data();
     return d;
 }

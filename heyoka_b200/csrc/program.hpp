@@ -16,6 +16,9 @@ struct hy_program {
     std::vector<std::uint32_t> args;
     std::vector<double> consts;
     std::vector<std::uint32_t> sv_defs;
+    // Event equations: the u variable holding each of them (terminal events first), sv_funcs_dc of
+    // src/taylor_01.cpp:847-1008.
+    std::vector<std::uint32_t> ev_defs;
     // Reference-shaped decomposition, kept for diagnostics (empty if built from raw arrays).
     heyoka_b200::taylor_dc_t dc;
 

@@ -176,6 +176,10 @@ int hy_order_from_tol(double tol, uint32_t *order);
  * (src/taylor_adaptive_batch.cpp:237-241). Unsupported functions -> HY_ERR_NOT_IMPLEMENTED. */
 int hy_program_from_sys(const hy_ex *const *lhs, const hy_ex *const *rhs, uint32_t n_eq, double tol,
                         int high_accuracy, hy_program **out);
+/* The same with event equations (terminal events first): the decomposition of src/taylor_00.cpp:605 taylor_decompose_sys(sys,
+ * evs); the program then carries ev_defs and the batch built from it detects events (section E). */
+int hy_program_from_sys_ev(const hy_ex *const *lhs, const hy_ex *const *rhs, uint32_t n_eq, const hy_ex *const *evs,
+                           uint32_t n_ev, double tol, int high_accuracy, hy_program **out);
 /* Build from raw arrays (validated: indices in range, ops only read earlier u variables). */
 int hy_program_create(const hy_program_desc *desc, hy_program **out);
 /* Borrowed view of the program's arrays (valid until hy_program_destroy). */
@@ -275,6 +279,41 @@ void hy_cout_destroy(hy_cout *);
 /* Dense output from the last written tc: out[var * batch + lane] = sum_o tc[var][o][lane] * tau[lane]^o
  * (src/taylor_01.cpp:1015-1185; tau relative to the start of the last step). out/tau are host arrays. */
 int hy_batch_d_output(hy_batch *, const double *tau, double *out);
+
+/* ------------------------------------------------------------------------------------------------
+ * E. Event detection in batch mode.
+ *    Replaces: taylor_add_adaptive_step_with_events() (src/taylor_00.cpp:593-710, the JIT'd stepper that returns the jet
+ *    of the state variables and of the event equations), the events branch of step_impl()
+ *    (src/taylor_adaptive_batch.cpp:728-1035) minus the callbacks, ed_data_batch<T>::detect_events()
+ *    (src/detail/event_detection.cpp:1733-2173) with its JIT'd helpers fex_check / poly_rtscc / poly_translate_1
+ *    (include/heyoka/detail/ed_data.hpp). A program built by hy_program_from_sys_ev() gives a batch whose every
+ *    hy_batch_step() is an event step: jet (Taylor coefficients always written; rows n_eq.. of the device tc array hold
+ *    the event equations), detection, propagation cut at the first terminal event of each lane, cooldowns. Callbacks are
+ *    the caller's: it reads the detected events back and patches the outcome of a terminal event whose callback asks to
+ *    continue (-idx - 1 -> idx). hy_batch_propagate_*() refuse such a batch: the front ends run the reference's
+ *    lock-step loop over hy_batch_step() (a callback per step forces a synchronisation anyway).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct hy_event_rec {
+    uint32_t lane;    /* batch index                                                         */
+    uint32_t idx;     /* index among the terminal (terminal != 0) or the non-terminal events  */
+    int32_t terminal;
+    int32_t d_sgn;    /* sign of the time derivative of the event equation at the event       */
+    double t;         /* time of the event relative to the BEGINNING of the step              */
+    double abs_der;
+} hy_event_rec;
+/* The first n_te event equations of the program are terminal. dirs[n_ev] in {-1, 0, 1} (event_direction); cooldowns[n_te]
+ * (< 0: automatic, src/detail/event_detection.cpp:519-550); tol: the integrator's tolerance (g_eps of :746-773). */
+int hy_batch_set_events(hy_batch *, uint32_t n_te, const int32_t *dirs, const double *cooldowns, double tol);
+/* Events of the last step, ready for the callbacks: lanes ascending; per lane the non-terminal events that precede the
+ * first terminal one, in time order, then that terminal event. */
+uint32_t hy_batch_n_events(const hy_batch *);
+int hy_batch_get_events(const hy_batch *, hy_event_rec *out, uint32_t cap);
+/* Taylor coefficients of the event equations of the last step, out[n_ev * (order + 1) * batch] (host). */
+int hy_batch_download_tc_events(hy_batch *, double *out);
+/* reset_cooldowns() / reset_cooldowns(i) (src/taylor_adaptive_batch.cpp:2300-2330): lane < 0 = every lane. */
+int hy_batch_reset_cooldowns(hy_batch *, int64_t lane);
+/* Cooldown state [n_te][batch]: active flag, time spent in cooldown, cooldown (host arrays). */
+int hy_batch_get_cooldowns(hy_batch *, uint8_t *active, double *spent, double *cooldown);
 
 /* Kernel launch statistics since creation (bench.py's gpu_launches). */
 int hy_batch_launch_count(const hy_batch *, uint64_t *n_launches);

@@ -37,7 +37,8 @@ std::uint32_t uname_to_index(const std::string &);
 
 // Validation of an ODE system (src/detail/validate_ode_sys.cpp): unique variable LHS, RHS only in
 // terms of the LHS variables. Throws std::invalid_argument.
-void validate_ode_sys(const std::vector<std::pair<expression, expression>> &sys);
+void validate_ode_sys(const std::vector<std::pair<expression, expression>> &sys,
+                      const std::vector<expression> &ev_funcs = {});
 
 std::string dc_to_string(const taylor_dc_t &);
 

@@ -1,0 +1,510 @@
+"""The batch blocks of the reference's event-detection tests (test/batch_event_detection.cpp), written once and run
+twice: on the CPU oracle (tests/test_events_cpu.py, which pins the oracle's restatement of detect_events() and TOMS 748
+on the reference's own expectations) and on the GPU (tests/test_gpu_events.py). `make` builds an integrator with the
+signature of heyoka_b200.taylor_adaptive_batch."""
+import numpy as np
+
+import heyoka_b200 as hb
+
+EPS = float(np.finfo(np.float64).eps)
+TO = hb.taylor_outcome
+INF = float("inf")
+
+
+def approx(a, b, tol_eps=100.0):
+    """test/catch.hpp approximately(): |a - b| <= eps * tol * max(|a|, |b|)... (relative, eps-scaled)."""
+    return abs(a - b) <= EPS * tol_eps * max(abs(a), abs(b))
+
+
+def pendulum_sys():
+    x, v = hb.make_vars("x", "v")
+    return x, v, [(x, v), (v, -9.8 * hb.sin(x))]
+
+
+PEND_IC = [0, 0.01, 0.02, 0.03, .25, .26, .27, .28]
+
+
+def case_linear_box(make):
+    """:262-327: an event exactly at the end of a step fires at the beginning of the next one."""
+    x, = hb.make_vars("x")
+    counter = [0]
+    times = []
+
+    def ncb(ta, tm, d_sgn, i):
+        assert approx(tm, 1 / ta.pars[0, i])
+        counter[0] += 1
+
+    ta = make([(x, hb.par[0])], [0., 0., 0., 0.], 4, pars=[1., 2., 4., 8.], nt_events=[hb.nt_event_batch(x - 1., ncb)])
+    lim = [1., 1 / 2., 1 / 4., 1 / 8.]
+    ta.step(lim)
+    assert counter[0] == 0 and all(r[0] == TO.time_limit for r in ta.step_res)
+    ta.step(lim)
+    assert counter[0] == 4 and all(r[0] == TO.time_limit for r in ta.step_res)
+
+    counter[0] = 0
+
+    def tcb(ta, d_sgn, i):
+        counter[0] += 1
+        times.append(ta.time[i])
+        return True
+
+    ta = make([(x, hb.par[0])], [0., 0., 0., 0.], 4, pars=[1., 2., 4., 8.],
+              t_events=[hb.t_event_batch(x - 1., callback=tcb)])
+    ta.step(lim)
+    assert counter[0] == 0 and all(r[0] == TO.time_limit for r in ta.step_res)
+    ta.step(lim)
+    assert counter[0] == 4
+    assert all(r[0] == 0 for r in ta.step_res)
+    assert all(abs(r[1]) <= 100 * EPS for r in ta.step_res)
+    return times
+
+
+def case_glancing_blow(make):
+    """:329-409: two spheres touching tangentially (double root of the distance polynomial) on batch index 1."""
+    names = ["x0", "y0", "x1", "y1", "vx0", "vy0", "vx1", "vy1"]
+    x0, y0, x1, y1, vx0, vy0, vx1, vy1 = hb.make_vars(*names)
+    ic = [0., 0., 0., 0., 0., 0., 0., 0., -10., -10., -10., -10., 6., 2, 7., 8., 0., 0., 0., 0., 0., 0., 0., 0.,
+          1., 1., 1., 1., 0., 0., 0., 0.]
+    out = []
+    for acc in (0., .1):
+        counter = [0]
+
+        def cb(ta, t, d_sgn, i, acc=acc, counter=counter):
+            if acc == 0.:
+                assert (t - 10.) ** 2 <= EPS
+            assert i == 1
+            counter[0] += 1
+
+        zero = hb.expression(0.)
+        sys = [(x0, vx0), (y0, vy0), (x1, vx1), (y1, vy1), (vx0, zero), (vy0, zero), (vx1, hb.expression(acc)), (vy1, zero)]
+        ev = hb.nt_event_batch((x0 - x1) * (x0 - x1) + (y0 - y1) * (y0 - y1) - 4., cb)
+        ta = make(sys, ic, 4, nt_events=[ev])
+        for _ in range(20):
+            ta.step([1.3] * 4)
+            assert all(r[0] == TO.time_limit for r in ta.step_res)
+        assert counter[0] <= 2
+        out.append(counter[0])
+    return out
+
+
+def case_multizero(make, tol=0.0, backward=False):
+    """:411-768: v^2 - 1e-10 and v fire in the same step in the order 0 1 0."""
+    x, v, sys = pendulum_sys()
+    counter = [0] * 4
+    cur_time = [0.] * 4
+    log = [[] for _ in range(4)]
+    sgn = -1. if backward else 1.
+
+    def cb0(ta, t, d_sgn, i):
+        assert sgn * t > sgn * cur_time[i]
+        assert sgn * ta.time[i] > sgn * t
+        assert counter[i] % 3 in (0, 2)
+        vel = ta.update_d_output([t] * 4)[1, i]
+        assert abs(vel * vel - 1e-10) < EPS
+        counter[i] += 1
+        cur_time[i] = t
+        log[i].append((0, t))
+
+    def cb1(ta, t, d_sgn, i):
+        assert sgn * t > sgn * cur_time[i]
+        assert sgn * ta.time[i] > sgn * t
+        assert counter[i] % 3 == 1
+        vel = ta.update_d_output([t] * 4)[1, i]
+        assert abs(vel) <= EPS * 100
+        counter[i] += 1
+        cur_time[i] = t
+        log[i].append((1, t))
+
+    ta = make(sys, PEND_IC, 4, tol=tol, nt_events=[hb.nt_event_batch(v * v - 1e-10, cb0), hb.nt_event_batch(v, cb1)])
+    ta.propagate_until([sgn * 4.] * 4)
+    for i in range(4):
+        assert ta.propagate_res[i][0] == TO.time_limit
+        assert counter[i] == 12
+    return log, ta
+
+
+def case_multizero_dir(make):
+    """:560-690: the same with v only detected when going from positive to negative: 0 1 0 / 0 0 alternating."""
+    x, v, sys = pendulum_sys()
+    counter = [0] * 4
+    cur_time = [0.] * 4
+
+    def cb0(ta, t, d_sgn, i):
+        assert t > cur_time[i] and ta.time[i] > t
+        assert counter[i] == 0 or 2 <= counter[i] <= 9
+        vel = ta.update_d_output([t] * 4)[1, i]
+        assert abs(vel * vel - 1e-10) < EPS
+        counter[i] += 1
+        cur_time[i] = t
+
+    def cb1(ta, t, d_sgn, i):
+        assert t > cur_time[i] and ta.time[i] > t
+        assert counter[i] in (1, 6)
+        assert d_sgn == -1
+        vel = ta.update_d_output([t] * 4)[1, i]
+        assert abs(vel) <= EPS * 100
+        counter[i] += 1
+        cur_time[i] = t
+
+    ta = make(sys, PEND_IC, 4, nt_events=[hb.nt_event_batch(v * v - 1e-10, cb0),
+                                          hb.nt_event_batch(v, cb1, direction=hb.event_direction.negative)])
+    ta.propagate_until([4.] * 4)
+    for i in range(4):
+        assert ta.propagate_res[i][0] == TO.time_limit
+        assert counter[i] == 10
+    return counter
+
+
+PERIODS = [2.0149583072955119566777324135479727911105583481363, 2.015602866455777600694040810649276304933055944554756,
+           2.0162731039077591887007722648120652760856018525920970125217,
+           2.01696906642817313582861191326257261662145101139954930969969]
+
+
+def case_nte_basic(make):
+    """:770-813: the third zero of the velocity of a pendulum is one period after the first (GOLDEN: the periods are
+    the reference's own numbers, to 1000 eps)."""
+    x, v, sys = pendulum_sys()
+    counter = [0] * 4
+    times = [[] for _ in range(4)]
+
+    def cb(ta, t, d_sgn, i):
+        if counter[i] == 0:
+            assert t == 0
+        if counter[i] == 2:
+            assert approx(t, PERIODS[i], 1000.)
+        counter[i] += 1
+        times[i].append(t)
+
+    ta = make(sys, [-0.25, -0.26, -0.27, -0.28, 0., 0., 0., 0.], 4, nt_events=[hb.nt_event_batch(v, cb)])
+    for _ in range(20):
+        ta.step()
+        assert all(r[0] == TO.success for r in ta.step_res)
+    assert counter == [3] * 4
+    return times
+
+
+def _step_until_all_trigger(ta, limit, check):
+    n_trig = 0
+    mdt = [limit] * 4
+    trig = [None] * 4
+    while n_trig < 4:
+        ta.step(mdt)
+        for i in range(4):
+            oc = ta.step_res[i][0]
+            if oc > TO.success:
+                check(oc)
+                n_trig += 1
+                mdt[i] = 0
+                trig[i] = oc
+            else:
+                assert oc in (TO.success, TO.time_limit)
+    return trig
+
+
+def case_te_basic(make, tol=0.0):
+    """:815-980: terminal event v with callbacks, non-terminal v^2 - 1e-10, forwards and backwards."""
+    x, v, sys = pendulum_sys()
+    c_nt, c_t = [0] * 4, [0] * 4
+    cur_time = [0.] * 4
+    direction = [True]
+    ev_times = [[] for _ in range(4)]
+
+    def ncb(ta, t, d_sgn, i):
+        assert (t > cur_time[i]) if direction[0] else (t < cur_time[i])
+        vel = ta.update_d_output([t] * 4)[1, i]
+        assert abs(vel * vel - 1e-10) < EPS
+        c_nt[i] += 1
+        cur_time[i] = t
+
+    def tcb(ta, d_sgn, i):
+        t = ta.time[i]
+        assert (t > cur_time[i]) if direction[0] else (t < cur_time[i])
+        assert abs(ta.state[1, i]) < EPS * 100
+        c_t[i] += 1
+        cur_time[i] = t
+        ev_times[i].append(t)
+        return True
+
+    ta = make(sys, PEND_IC, 4, tol=tol, nt_events=[hb.nt_event_batch(v * v - 1e-10, ncb)],
+              t_events=[hb.t_event_batch(v, callback=tcb)])
+
+    def ge0(oc):
+        assert oc >= 0
+
+    _step_until_all_trigger(ta, INF, ge0)
+    assert c_nt == [1] * 4 and c_t == [1] * 4
+    _step_until_all_trigger(ta, INF, ge0)
+    assert c_nt == [3] * 4 and c_t == [2] * 4
+    direction[0] = False
+    _step_until_all_trigger(ta, -INF, ge0)
+    assert c_nt == [5] * 4 and c_t == [3] * 4
+    _step_until_all_trigger(ta, -INF, ge0)
+    assert c_nt == [7] * 4 and c_t == [4] * 4
+    return ev_times
+
+
+def case_nte_dir(make):
+    """:982-1018: direction filter; the events met forwards are met again, in reverse, backwards."""
+    x, v, sys = pendulum_sys()
+    fwd = [True]
+    tlist = [[] for _ in range(4)]
+    pos = [0] * 4
+
+    def cb(ta, t, d_sgn, i):
+        assert d_sgn == 1
+        if fwd[0]:
+            tlist[i].append(t)
+        elif pos[i] < len(tlist[i]):
+            # (The reference compares relatively; the event at t = 0 comes back as a few 1e-16, which only an absolute
+            # comparison can accept - whether it is met again at all depends on the last bits of the trajectory.)
+            ref = tlist[i][len(tlist[i]) - 1 - pos[i]]
+            assert abs(ref - t) <= 100 * EPS * max(abs(ref), abs(t), 1.)
+            pos[i] += 1
+
+    ta = make(sys, [-0.25, -0.26, -0.27, -0.28, 0., 0., 0., 0.], 4,
+              nt_events=[hb.nt_event_batch(v, cb, direction=hb.event_direction.positive)])
+    ta.propagate_until([20.] * 4)
+    fwd[0] = False
+    ta.propagate_until([0.] * 4)
+    assert all(len(t) >= 9 for t in tlist) and all(p >= len(t) - 1 for p, t in zip(pos, tlist))
+    return tlist
+
+
+def case_te_identical(make):
+    """:1074-1123: two identical terminal events: one of them stops the step, the other may fire right after."""
+    x, v, sys = pendulum_sys()
+    ta = make(sys, PEND_IC, 4, t_events=[hb.t_event_batch(v), hb.t_event_batch(v)])
+    while True:
+        ta.step()
+        if any(r[0] > TO.success for r in ta.step_res):
+            break
+    first = []
+    for i in range(4):
+        oc = ta.step_res[i][0]
+        assert oc > TO.success
+        assert -oc - 1 in (0, 1)
+        first.append(-oc - 1)
+    ta.step()
+    for i in range(4):
+        oc = ta.step_res[i][0]
+        if oc > TO.success:
+            assert -oc - 1 in (0, 1) and -oc - 1 != first[i]
+        else:
+            assert oc == TO.success
+
+
+def case_te_close(make):
+    """:1125-1264: two terminal events 2 eps apart: order of firing, cooldowns, there and back."""
+    x, v, sys = pendulum_sys()
+    ta = make(sys, [0.1, 0.11, 0.12, 0.13, .25, .26, .27, .28], 4,
+              t_events=[hb.t_event_batch(x), hb.t_event_batch(x - EPS * 2, callback=lambda ta, s, i: True)])
+
+    def ge0(oc):
+        assert oc >= 0
+
+    def lt0(oc):
+        assert oc < 0
+
+    assert _step_until_all_trigger(ta, INF, ge0) == [1] * 4
+    assert _step_until_all_trigger(ta, INF, lt0) == [-1] * 4
+    ta.step()
+    assert all(r[0] == TO.success for r in ta.step_res)
+    assert _step_until_all_trigger(ta, -INF, lt0) == [-1] * 4
+    assert _step_until_all_trigger(ta, -INF, ge0) == [1] * 4
+    ta.step()
+    assert all(r[0] == TO.success for r in ta.step_res)
+
+
+def case_te_retrigger(make):
+    """:1266-1315: an event a few eps away from the initial state fires immediately, and again one period later."""
+    x, v, sys = pendulum_sys()
+    ta = make(sys, [1., 1.01, 1.02, 1.03, 0., 0.01, 0.02, 0.03], 4, pars=[1., 1.01, 1.02, 1.03],
+              t_events=[hb.t_event_batch(x - (hb.par[0] - EPS * 6))])
+    ta.step()
+    assert all(r[0] == -1 for r in ta.step_res)
+    assert all(t != 0 for t in ta.time)
+
+    def m1(oc):
+        assert oc == -1
+
+    _step_until_all_trigger(ta, INF, m1)
+    ta.step()
+    assert all(r[0] == -1 for r in ta.step_res)
+
+
+def case_te_dir(make):
+    """:1317-1399: direction filter on a terminal event, zero-length steps, cooldown after the trigger."""
+    x, v, sys = pendulum_sys()
+
+    def pos(ta, d_sgn, i):
+        assert d_sgn == 1
+        return True
+
+    ic = [1., 1.01, 1.02, 1.03, 0., 0., 0., 0.]
+    ta = make(sys, ic, 4, t_events=[hb.t_event_batch(v, callback=pos, direction=hb.event_direction.positive)])
+    ta.step()
+    assert all(r[0] == TO.success for r in ta.step_res)
+    while True:
+        ta.step()
+        if all(r[0] == 0 for r in ta.step_res):
+            break
+    for i in range(4):
+        assert approx(ta.state[0, i], -ic[i])
+
+    def neg(ta, d_sgn, i):
+        assert d_sgn == -1
+        return True
+
+    ta = make(sys, ic, 4, t_events=[hb.t_event_batch(v, callback=neg, direction=hb.event_direction.negative)])
+    ta.step([0.] * 4)
+    assert all(r[0] == TO.time_limit for r in ta.step_res)
+    ta.step()
+    assert all(r[0] == 0 for r in ta.step_res)
+    ta.step()
+    assert all(r[0] == TO.success for r in ta.step_res)
+    while True:
+        ta.step()
+        if all(r[0] == 0 for r in ta.step_res):
+            break
+    for i in range(4):
+        assert approx(ta.state[0, i], ic[i])
+
+
+def case_te_custom_cooldown(make):
+    """:1401-1438: with a cooldown of 0.1 the double root of v^2 - 4 eps fires once."""
+    x, v, sys = pendulum_sys()
+    ta = make(sys, PEND_IC, 4,
+              t_events=[hb.t_event_batch(v * v - EPS * 4, callback=lambda ta, s, i: True, cooldown=1e-1)])
+
+    def is0(oc):
+        assert oc == 0
+
+    _step_until_all_trigger(ta, INF, is0)
+
+
+def case_te_propagate_for(make):
+    """:1440-1477: 100 zero crossings of the velocity in 100 time units; without callback the first one stops."""
+    x, v, sys = pendulum_sys()
+    counter = [0] * 4
+
+    def cb(ta, d_sgn, i):
+        counter[i] += 1
+        return True
+
+    ta = make(sys, PEND_IC, 4, t_events=[hb.t_event_batch(v, callback=cb)])
+    ta.propagate_for([100.] * 4)
+    assert all(r[0] == TO.time_limit for r in ta.propagate_res)
+    assert all(t == 100. for t in ta.time)
+    assert counter == [100] * 4
+    ta = make(sys, PEND_IC, 4, t_events=[hb.t_event_batch(v)])
+    ta.propagate_for([100.] * 4)
+    assert all(r[0] == -1 for r in ta.propagate_res)
+    return ta
+
+
+def case_te_damped_pendulum(make):
+    """:1580-1645: the callback flips a parameter of the system at every zero of the velocity."""
+    x, v = hb.make_vars("x", "v")
+    zvt = [[] for _ in range(4)]
+
+    def cb(ta, d_sgn, i):
+        tm = ta.time[i]
+        ta.pars[0, i] = 1. if ta.pars[0, i] == 0 else 0.
+        zvt[i].append(tm)
+        return True
+
+    ta = make([(x, v), (v, -9.8 * hb.sin(x) - hb.par[0] * v)], [0.05, 0.051, 0.052, 0.053, 0.025, 0.0251, 0.0252, 0.0253],
+              4, t_events=[hb.t_event_batch(v, callback=cb)])
+    ta.propagate_until([100.] * 4)
+    assert [len(z) for z in zvt] == [99] * 4
+    ta.step()
+    assert [len(z) for z in zvt] == [100] * 4
+    return zvt
+
+
+def case_te_boolean_callback(make):
+    """:1647-1721: the fifth invocation of the callback returns false: propagate_until() stops there."""
+    x, v, sys = pendulum_sys()
+    c_t = [0] * 4
+    cur_time = [0.] * 4
+    direction = [True]
+
+    def cb(ta, d_sgn, i):
+        t = ta.time[i]
+        assert (t > cur_time[i]) if direction[0] else (t < cur_time[i])
+        assert abs(ta.state[1, i]) < EPS * 100
+        c_t[i] += 1
+        cur_time[i] = t
+        return c_t[i] != 5
+
+    ta = make(sys, PEND_IC, 4, t_events=[hb.t_event_batch(v, callback=cb)])
+    while True:
+        ta.step()
+        if all(r[0] == 0 for r in ta.step_res):
+            break
+    ta.propagate_until([1000.] * 4)
+    assert all(r[0] == -1 for r in ta.step_res)
+    for i in range(4):
+        c_t[i] = 0
+    direction[0] = False
+    while True:
+        ta.step_backward()
+        if all(r[0] == 0 for r in ta.step_res):
+            break
+    ta.propagate_until([-1000.] * 4)
+    assert all(r[0] == -1 for r in ta.step_res)
+
+
+def case_te_step_end(make):
+    """:1723-1747: an event (time - 1) that falls exactly on the end of a clamped step."""
+    x, v, sys = pendulum_sys()
+    counter = [0] * 4
+
+    def cb(ta, d_sgn, i):
+        counter[i] += 1
+        assert ta.time[i] == 1.
+        return True
+
+    ta = make(sys, PEND_IC, 4, t_events=[hb.t_event_batch(hb.time - 1., callback=cb)])
+    ta.propagate_until([10.] * 4, max_delta_t=[0.005] * 4)
+    assert counter == [1] * 4
+
+
+def case_te_zero_cd(make):
+    """:1749-1785: zero cooldown and a callback that stops."""
+    x, v, sys = pendulum_sys()
+    ta = make(sys, PEND_IC, 4, t_events=[hb.t_event_batch(v, callback=lambda ta, s, i: False, cooldown=0)])
+    ta.propagate_until([10.] * 4)
+    assert all(r[0] == -1 for r in ta.step_res)
+
+
+def case_single_step(make, terminal):
+    """:100-260 (the batch half): driven damped pendulum with time-dependent right-hand side and parameters; returns
+    the trigger times and the velocities at the events for every batch index."""
+    x, v = hb.make_vars("x", "v")
+    sys = [(x, v), (v, hb.cos(hb.time) - hb.par[0] * v - hb.sin(x))]
+    ic = [0.00, 0.01, 0.02, 0.03, 1.85, 1.86, 1.87, 1.88]
+    pars = [0.10, 0.11, 0.12, 0.13]
+    times, vels = [[] for _ in range(4)], [[] for _ in range(4)]
+    if terminal:
+        def cb(ta, d_sgn, i):
+            times[i].append(ta.time[i])
+            vels[i].append(ta.state[1, i])
+            return True
+
+        ta = make(sys, ic, 4, pars=pars,
+                  t_events=[hb.t_event_batch(x + .1, callback=cb, direction=hb.event_direction.negative)])
+    else:
+        def cb(ta, tm, d_sgn, i):
+            times[i].append(tm)
+            vels[i].append(ta.update_d_output([tm] * 4)[1, i])
+
+        ta = make(sys, ic, 4, pars=pars,
+                  nt_events=[hb.nt_event_batch(x + .1, cb, direction=hb.event_direction.negative)])
+    while np.any(ta.time < 20):
+        ta.step()
+        for r in ta.step_res:
+            assert r[0] == TO.success or (terminal and r[0] == 0)
+    if terminal:
+        assert [len(t) for t in times] == [2, 1, 1, 1]  # ex_n_trig, :196
+    return times, vels

@@ -348,3 +348,117 @@ class OracleCOut:
             assert rc == 0
             out[:, i] = o[:, 0]
         return out
+
+
+# ---- event detection (oracle_step_ev_w1) --------------------------------------------------------------------------
+class oracle_event(C.Structure):
+    _fields_ = [("lane", C.c_uint32), ("idx", C.c_uint32), ("terminal", C.c_int32), ("d_sgn", C.c_int32),
+                ("t", C.c_double), ("abs_der", C.c_double)]
+
+
+class OracleBatch:
+    """The surface of heyoka_b200.Batch that an integrator WITH EVENTS uses, served by the CPU oracle. Plugged under
+    the product's Python front end (heyoka_b200.taylor_adaptive_batch._make_batch) by OracleEventIntegrator below, so
+    that the callback / propagate logic of the front end can be exercised on a machine without a GPU and the device
+    kernels can be compared with the oracle step by step."""
+
+    def __init__(self, program, batch, mode=FMA):
+        P = self.program = program
+        self.n, self.mode = batch, mode
+        self.state = np.zeros((P.n_eq, batch))
+        self.pars = np.zeros((max(P.n_pars, 1), batch))
+        self.t_hi, self.t_lo, self.last_h = np.zeros(batch), np.zeros(batch), np.zeros(batch)
+        self._tc = np.zeros((P.n_eq + P.n_ev, P.order + 1, batch))
+        self.outcome = np.zeros(batch, dtype=np.int64)
+        self._events = []
+
+    def set_kernel(self, **kw):
+        pass
+
+    def kernel_info(self):
+        return {"tape": "oracle"}
+
+    def set_events(self, n_te, dirs, cooldowns, tol):
+        self.n_te, self.tol = int(n_te), float(tol)
+        self.dirs = np.ascontiguousarray(dirs, dtype=np.int32)
+        self.cooldowns = np.ascontiguousarray(list(cooldowns) + [0.0], dtype=np.float64)
+        self.cd = np.zeros((self.n, max(self.n_te, 1), 2))
+        self.cd_on = np.zeros((self.n, max(self.n_te, 1)), dtype=np.int32)
+
+    def upload(self, state, pars, t_hi, t_lo):
+        self.state[...] = state
+        if pars is not None:
+            self.pars[...] = pars
+        self.t_hi[...] = t_hi
+        self.t_lo[...] = t_lo
+
+    def download(self):
+        return self.state.copy(), self.t_hi.copy(), self.t_lo.copy(), self.last_h.copy()
+
+    def tc(self):
+        return self._tc[:self.program.n_eq].copy()
+
+    def tc_events(self, n_ev):
+        return self._tc[self.program.n_eq:].copy()
+
+    def step(self, max_delta_t=None, backward=False, write_tc=False):
+        n = self.n
+        mdt = np.full(n, -np.inf if backward else np.inf) if max_delta_t is None else \
+            np.ascontiguousarray(np.broadcast_to(max_delta_t, (n,)), dtype=np.float64)
+        cap = 64 * n * max(self.program.n_ev, 1)
+        buf = (oracle_event * cap)()
+        n_out = C.c_uint32()
+        rc = lib.oracle_step_ev_w1(
+            _desc_ptr(self.program), C.c_uint32(n), _arr(self.state), _arr(self.pars), _arr(self.t_hi), _arr(self.t_lo),
+            _arr(mdt), C.c_double(self.tol), C.c_uint32(self.n_te), self.dirs.ctypes.data_as(C.POINTER(C.c_int32)),
+            _arr(self.cooldowns), _arr(self.cd), self.cd_on.ctypes.data_as(C.POINTER(C.c_int32)), _arr(self._tc),
+            _arr(self.last_h), self.outcome.ctypes.data_as(C.POINTER(C.c_int64)), buf, C.c_uint32(cap), C.byref(n_out),
+            C.c_int(self.mode))
+        assert rc == 0, rc
+        self._events = [(e.lane, e.idx, bool(e.terminal), e.d_sgn, e.t, e.abs_der) for e in buf[:n_out.value]]
+
+    def step_res(self):
+        return self.outcome.copy(), self.last_h.copy()
+
+    def events(self):
+        return list(self._events)
+
+    def reset_cooldowns(self, lane=-1):
+        if lane < 0:
+            self.cd_on[...] = 0
+        else:
+            self.cd_on[lane] = 0
+
+    def cooldowns(self, n_te):
+        return (self.cd_on.T[:n_te].astype(np.uint8), self.cd[:, :, 0].T[:n_te].copy(), self.cd[:, :, 1].T[:n_te].copy())
+
+    def d_output(self, tau):
+        P = self.program
+        tau = np.ascontiguousarray(np.broadcast_to(tau, (self.n,)), dtype=np.float64)
+        out = np.empty((P.n_eq, self.n))
+        tc = np.ascontiguousarray(self._tc[:P.n_eq])
+        rc = lib.oracle_d_output_w1(_desc_ptr(P), C.c_uint32(self.n), _arr(tc), _arr(tau), _arr(out))
+        assert rc == 0
+        return out
+
+
+_OEI = None
+
+
+def OracleEventIntegrator(*args, mode=FMA, **kw):
+    """heyoka_b200.taylor_adaptive_batch (the product's host-side front end: callbacks, lock-step propagation) over the
+    CPU oracle instead of the device."""
+    global _OEI
+    if _OEI is None:
+        import heyoka_b200 as hb
+
+        class _Impl(hb.taylor_adaptive_batch):
+            def __init__(self, *a, mode=FMA, **k):
+                self._oracle_mode = mode
+                super().__init__(*a, **k)
+
+            def _make_batch(self, P, batch_size, device):
+                return OracleBatch(P, batch_size, self._oracle_mode)
+
+        _OEI = _Impl
+    return _OEI(*args, mode=mode, **kw)

@@ -1,0 +1,180 @@
+"""Event detection on the GPU (include/heyoka_b200.h section E; csrc/ev_kernels.cuh): the batch blocks of
+test/batch_event_detection.cpp on the device, and the device against the CPU oracle step by step (same events in the same
+order, event times / Taylor coefficients of the event equations / cooldowns / states to the tolerances written below)."""
+import numpy as np
+import pytest
+
+import event_cases as ec
+import heyoka_b200 as hb
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def make(*a, **k):
+    return hb.taylor_adaptive_batch(*a, **k)
+
+
+def test_linear_box_gpu():
+    times = ec.case_linear_box(make)
+    assert np.allclose(sorted(times), [1 / 8., 1 / 4., 1 / 2., 1.], rtol=1e-15)
+
+
+def test_glancing_blow_gpu():
+    ec.case_glancing_blow(make)
+
+
+@pytest.mark.parametrize("tol", [0.0, ec.EPS / 100])
+def test_multizero_gpu(tol):
+    ec.case_multizero(make, tol=tol)
+
+
+def test_multizero_backward_and_direction_gpu():
+    ec.case_multizero(make, backward=True)
+    ec.case_multizero_dir(make)
+
+
+def test_nte_basic_golden_periods_gpu():
+    ec.case_nte_basic(make)
+
+
+@pytest.mark.parametrize("tol", [0.0, ec.EPS / 100])
+def test_te_basic_gpu(tol):
+    ec.case_te_basic(make, tol=tol)
+
+
+def test_directions_gpu():
+    ec.case_nte_dir(make)
+    ec.case_te_dir(make)
+
+
+def test_te_identical_close_retrigger_gpu():
+    ec.case_te_identical(make)
+    ec.case_te_close(make)
+    ec.case_te_retrigger(make)
+
+
+def test_te_cooldowns_gpu():
+    ec.case_te_custom_cooldown(make)
+    ec.case_te_zero_cd(make)
+
+
+def test_te_propagate_for_gpu():
+    ec.case_te_propagate_for(make)
+
+
+def test_te_damped_pendulum_and_boolean_callback_gpu():
+    ec.case_te_damped_pendulum(make)
+    ec.case_te_boolean_callback(make)
+
+
+def test_te_step_end_gpu():
+    ec.case_te_step_end(make)
+
+
+@pytest.mark.parametrize("terminal", [False, True])
+def test_single_step_gpu_vs_oracle(terminal):
+    """test/batch_event_detection.cpp:100-260 on both: same number of triggers, times to 1000 eps, velocities to 10000
+    eps (the reference's own bars between its batch and scalar integrators)."""
+    tg, vg = ec.case_single_step(make, terminal)
+    to, vo = ec.case_single_step(lambda *a, **k: oracle.OracleEventIntegrator(*a, **k), terminal)
+    for i in range(4):
+        assert len(tg[i]) == len(to[i]) >= 1
+        for a, b, c, d in zip(tg[i], to[i], vg[i], vo[i]):
+            assert ec.approx(a, b, 1000.) and ec.approx(c, d, 10000.)
+
+
+@pytest.mark.parametrize("batch", [5, 257])
+@pytest.mark.parametrize("backward", [False, True])
+def test_event_step_parity_vs_oracle(batch, backward):
+    """Lock-step comparison over 60 steps of a pendulum batch with two terminal (one with an explicit cooldown, one
+    directional) and two non-terminal events: identical event lists (lane, index, kind, derivative sign), event times to
+    1e-13 relative to the step, Taylor coefficients of the event equations to 1e-13 (scaled by h^order), cooldown state,
+    outcomes, step sizes to 1e-12, states to 1e-12."""
+    x, v, sys = ec.pendulum_sys()
+    rng = np.random.default_rng(7)
+    st = np.stack([rng.uniform(-0.5, 0.5, batch), rng.uniform(-1.0, 1.0, batch)])
+
+    def build(mk):
+        return mk(sys, st, batch, t_events=[hb.t_event_batch(v, callback=lambda ta, s, i: True),
+                                            hb.t_event_batch(x - 0.1, callback=lambda ta, s, i: True, cooldown=0.05,
+                                                             direction=hb.event_direction.positive)],
+                  nt_events=[hb.nt_event_batch(v * v - 1e-2, lambda ta, t, s, i: None),
+                             hb.nt_event_batch(x * v + 0.05 * hb.cos(hb.time), lambda ta, t, s, i: None,
+                                               direction=hb.event_direction.negative)])
+
+    g = build(make)
+    o = build(lambda *a, **k: oracle.OracleEventIntegrator(*a, **k))
+    assert g._b.kernel_info()["tape"] == "hbm"
+    n_events = 0
+    for it in range(60):
+        if backward:
+            g.step_backward()
+            o.step_backward()
+        else:
+            g.step()
+            o.step()
+        eg, eo = g._b.events(), o._b.events()
+        assert [e[:4] for e in eg] == [e[:4] for e in eo], it
+        h = o.last_h
+        for a, b in zip(eg, eo):
+            assert abs(a[4] - b[4]) <= 1e-13 * abs(h[a[0]]) + 1e-300
+            assert abs(a[5] - b[5]) <= 1e-10 * max(abs(b[5]), 1.0)
+        n_events += len(eg)
+        assert [r[0] for r in g.step_res] == [r[0] for r in o.step_res], it
+        assert np.max(np.abs(g.last_h / o.last_h - 1)) < 1e-12
+        assert np.max(np.abs(g.state - o.state)) < 1e-12
+        assert np.array_equal(g.time, o.time) or np.max(np.abs(g.time - o.time)) < 1e-12
+        # Taylor coefficients of the event equations, scaled by h^order.
+        tg, to_ = g._b.tc_events(4), o._b.tc_events(4)
+        sc = np.abs(o._b.E_h if hasattr(o._b, "E_h") else 1.0)
+        pw = np.arange(g.get_order() + 1)[None, :, None]
+        hh = np.maximum(np.abs(h), 1e-300)[None, None, :] ** pw
+        assert np.max(np.abs(tg - to_) * np.minimum(hh, 1.0)) < 1e-12
+        ag, sg, cg = g._b.cooldowns(2)
+        ao, so, co = o._b.cooldowns(2)
+        assert np.array_equal(ag, ao), it
+        assert np.allclose(sg[ag == 1], so[ao == 1], rtol=1e-9, atol=1e-13)
+        assert np.allclose(cg[ag == 1], co[ao == 1], rtol=1e-6, atol=1e-15)
+    assert n_events > batch  # (every lane met several events)
+
+
+def test_many_lanes_few_events():
+    """65,537 lanes, a terminal and a non-terminal event: most (event, lane) pairs are discarded by the fast exclusion
+    check; the records that come back are exactly those of the lanes that cross."""
+    x, v, sys = ec.pendulum_sys()
+    batch = 65537
+    rng = np.random.default_rng(3)
+    st = np.stack([rng.uniform(0.05, 0.3, batch), np.zeros(batch)])
+    fired = np.zeros(batch, dtype=np.int64)
+
+    def cb(ta, d_sgn, i):
+        fired[i] += 1
+        return True
+
+    ta = make(sys, st, batch, t_events=[hb.t_event_batch(x, callback=cb)],
+              nt_events=[hb.nt_event_batch(v + 2.0, lambda ta, t, s, i: None)])
+    for _ in range(8):
+        ta.step()
+    # x crosses zero after a quarter period (~0.5): every lane exactly once in 8 steps of ~0.1-0.2.
+    assert np.all(fired <= 1) and fired.sum() > 0
+    idx = np.nonzero(fired)[0]
+    o = oracle.OracleEventIntegrator(sys, st[:, idx[:16]], len(idx[:16]), t_events=[hb.t_event_batch(x, callback=lambda ta, s, i: True)],
+                                     nt_events=[hb.nt_event_batch(v + 2.0, lambda ta, t, s, i: None)])
+    for _ in range(8):
+        o.step()
+    assert np.max(np.abs(o.state - ta.state[:, idx[:16]])) < 1e-12
+
+
+def test_event_api_errors_gpu():
+    x, v, sys = ec.pendulum_sys()
+    ta = make(sys, ec.PEND_IC, 4, t_events=[hb.t_event_batch(v)])
+    with pytest.raises(NotImplementedError, match="lock-step"):
+        ta._b.propagate_until(np.full(4, 1.0))
+    ta.reset_cooldowns()
+    ta.reset_cooldowns(2)
+    with pytest.raises(ValueError, match="batch size is only 4"):
+        ta.reset_cooldowns(4)
+    tb = make(sys, ec.PEND_IC, 4)
+    with pytest.raises(ValueError, match="No events"):
+        tb.reset_cooldowns()
