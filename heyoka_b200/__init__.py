@@ -458,6 +458,11 @@ class Batch:
         check(lib.hy_batch_download_tc_events(self._h, _dptr(out)))
         return out
 
+    def check_grid(self, grid, max_delta_t=None):
+        g = np.ascontiguousarray(grid, dtype=np.float64)
+        m = None if max_delta_t is None else np.ascontiguousarray(max_delta_t, dtype=np.float64)
+        check(lib.hy_batch_check_grid(self._h, _dptr(g), g.shape[0], _dptr(m)))
+
     def launch_count(self):
         n = C.c_uint64()
         check(lib.hy_batch_launch_count(self._h, C.byref(n)))
@@ -889,8 +894,6 @@ class taylor_adaptive_batch:
     def propagate_grid(self, grid, max_steps=0, max_delta_t=None, callback=None):
         """States at the grid points, shape [n_pts, n_eq, batch] (src/taylor_adaptive_batch.cpp:1545-2055).
         grid: [n_pts, batch] (or flat, point-major like the reference's std::vector)."""
-        if callback is not None:
-            raise NotImplementedError("Callbacks are not supported by propagate_grid()")
         n = self._batch_size
         g = np.asarray(grid, dtype=np.float64).reshape(-1)
         if g.size == 0:
@@ -907,11 +910,102 @@ class taylor_adaptive_batch:
                 raise ValueError("Invalid number of max timesteps specified in a Taylor integrator in batch mode: the "
                                  "batch size is %d, but the number of specified timesteps is %d" % (n, md.size))
             max_delta_t = np.ascontiguousarray(md)
+        if self._with_events or callback is not None:
+            return self._propagate_grid_host(g.reshape(-1, n), max_delta_t, max_steps, callback)
         self._push()
         out = self._b.propagate_grid(g.reshape(-1, n), max_delta_t, max_steps)
         self._pull(True)
         oc, mn, mx, ns = self._b.prop_res()
         self._prop_res = list(zip(oc.tolist(), mn.tolist(), mx.tolist(), ns.tolist()))
+        return out
+
+    def _propagate_grid_host(self, grid, max_delta_t, max_steps, callback):
+        """propagate_grid() of an integrator with events / with a step callback: the reference's loop
+        (src/taylor_adaptive_batch.cpp:1696-2053) on the host."""
+        n, n_pts, dim = self._batch_size, grid.shape[0], self._prog.n_eq
+        self._push()
+        self._b.check_grid(grid, max_delta_t)
+        out = np.full((n_pts, dim, n), np.nan)
+        self.propagate_until(grid[0].copy(), max_steps=max_steps, max_delta_t=max_delta_t, write_tc=True)
+        TO = taylor_outcome
+        if any(r[0] != TO.time_limit for r in self._prop_res):
+            self._prop_res = [(r[0], float("inf"), 0.0, 0) for r in self._prop_res]
+            return out
+        out[0] = self._state
+        last = grid[n_pts - 1]
+        rem_hi, rem_lo = _dfloat_add(last, np.zeros(n), -self._t_hi, -self._t_lo)
+        if not (np.all(np.isfinite(rem_hi)) and np.all(np.isfinite(rem_lo))):
+            raise ValueError("The final time passed to the propagate_grid() function of an adaptive Taylor integrator "
+                             "in batch mode results in an overflow condition")
+        t_dir = (rem_hi > 0) | ((rem_hi == 0) & (rem_lo >= 0))
+        mdt = np.full(n, np.inf) if max_delta_t is None else max_delta_t
+        ts_count, min_h, max_h = [0] * n, [float("inf")] * n, [0.0] * n
+        cur = np.ones(n, dtype=np.int64)
+        iters = 0
+        if callback is not None and hasattr(callback, "pre_hook"):
+            callback.pre_hook(self)
+        while np.any(cur < n_pts):
+            c_hi, c_lo = _dfloat_add(self._t_hi, self._t_lo, -self._last_h, np.zeros(n))
+            pairs = [((self._t_hi[i], self._t_lo[i]), (c_hi[i], c_lo[i])) for i in range(n)]
+            t0, t1 = [min(p) for p in pairs], [max(p) for p in pairs]
+            dflags = np.ones(n, dtype=bool)
+            while True:
+                pg = np.zeros(n)
+                for i in range(n):
+                    if dflags[i] and cur[i] < n_pts:
+                        g = grid[cur[i], i]
+                        dflags[i] = (t0[i] <= (g, 0.0) <= t1[i]) or (rem_hi[i] == 0 and rem_lo[i] == 0)
+                        pg[i] = g
+                    else:
+                        dflags[i] = False
+                if not dflags.any():
+                    break
+                d = self.update_d_output(pg)
+                for i in np.nonzero(dflags)[0]:
+                    out[cur[i], :, i] = d[:, i]
+                    cur[i] += 1
+                if not np.any(cur < n_pts):
+                    break
+            if not np.any(cur < n_pts):
+                break
+            if any(r[0] in (TO.cb_stop, TO.step_limit) or TO.success < r[0] < 0 for r in self._prop_res):
+                break
+            lim = np.empty(n)
+            for i in range(n):
+                if t_dir[i]:
+                    lim[i] = mdt[i] if (mdt[i], 0.0) < (rem_hi[i], rem_lo[i]) else rem_hi[i]
+                else:
+                    lim[i] = rem_hi[i] if (-mdt[i], 0.0) < (rem_hi[i], rem_lo[i]) else -mdt[i]
+            self._step_impl(lim, False, True)
+            nfs = False
+            for i in range(n):
+                oc, h = self._step_res[i]
+                if oc == TO.err_nf_state:
+                    nfs = True
+                else:
+                    ts_count[i] += int(h != 0)
+                    if oc == TO.success:
+                        min_h[i], max_h[i] = min(min_h[i], abs(h)), max(max_h[i], abs(h))
+                    if h == rem_hi[i]:
+                        rem_hi[i] = rem_lo[i] = 0.0
+                    else:
+                        a, b = _dfloat_add(last[i], 0.0, -self._t_hi[i], -self._t_lo[i])
+                        rem_hi[i], rem_lo[i] = float(a), float(b)
+                self._prop_res[i] = (oc, min_h[i], max_h[i], ts_count[i])
+            if nfs:
+                break
+            iters += 1
+            if callback is not None:
+                t_copy = (self._t_hi.copy(), self._t_lo.copy())
+                ret = callback(self)
+                if not (np.array_equal(self._t_hi, t_copy[0]) and np.array_equal(self._t_lo, t_copy[1])):
+                    raise RuntimeError("The invocation of the callback passed to propagate_grid() resulted in the "
+                                       "alteration of the time coordinate of the integrator - this is not supported")
+                if not ret:
+                    self._prop_res = [(TO.cb_stop,) + r[1:] for r in self._prop_res]
+                    continue
+            if iters == max_steps:
+                self._prop_res = [(TO.step_limit,) + r[1:] for r in self._prop_res]
         return out
 
     def propagate_for(self, delta_ts, **kw):

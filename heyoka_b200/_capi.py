@@ -108,6 +108,7 @@ SIGNATURES = {
     "hy_batch_propagate_until": (C.c_int, [_vp, _dp, _dp, _dp, C.c_uint64, C.c_int]),
     "hy_batch_propagate_until_dev": (C.c_int, [_vp, _dp, _dp, _dp, C.c_uint64, C.c_int, C.POINTER(C.c_int)]),
     "hy_batch_propagate_grid": (C.c_int, [_vp, _dp, C.c_uint64, _dp, C.c_uint64, _dp]),
+    "hy_batch_check_grid": (C.c_int, [_vp, _dp, C.c_uint64, _dp]),
     "hy_batch_propagate_until_cout": (C.c_int, [_vp, _dp, _dp, _dp, C.c_uint64, _vpp]),
     "hy_cout_eval": (C.c_int, [_vp, _dp, _dp]),
     "hy_cout_get_bounds": (C.c_int, [_vp, _dp, _dp]),

@@ -2030,7 +2030,7 @@ int hy_batch_propagate_until(hy_batch *b, const double *t_final_hi, const double
                              uint64_t max_steps, int write_tc)
 {
     try {
-        if (b->n_ev != 0u) {
+        if (b != nullptr && b->n_ev != 0u) {
             throw hy::detail::not_implemented_error("A batch with event equations is propagated by the front end's lock-step "
                                                     "loop over hy_batch_step(), not by the device-resident propagation");
         }
@@ -2071,7 +2071,7 @@ int hy_batch_propagate_until_dev(hy_batch *b, const double *d_t_final_hi, const 
                                  const double *d_max_delta_t, uint64_t max_steps, int write_tc, int *any_nf_or_limit)
 {
     try {
-        if (b->n_ev != 0u) {
+        if (b != nullptr && b->n_ev != 0u) {
             throw hy::detail::not_implemented_error("A batch with event equations is propagated by the front end's lock-step "
                                                     "loop over hy_batch_step(), not by the device-resident propagation");
         }
@@ -2092,6 +2092,104 @@ int hy_batch_propagate_until_dev(hy_batch *b, const double *d_t_final_hi, const 
 // initial propagate_until(grid[0]) with write_tc, then lock-step iterations of {dense output at every grid point
 // covered by the last step; one step clamped to the last grid point}. The per-lane work runs on the device (one
 // step launch + two small kernels per iteration); the host only reads the two loop flags.
+namespace
+{
+
+// The argument checks of propagate_grid_impl() (src/taylor_adaptive_batch.cpp:1575-1670); reads the current times back.
+void check_grid(hy_batch *b, const double *grid, uint64_t n_pts, const double *max_delta_t)
+{
+    const std::uint32_t n = b->n;
+    if (n_pts == 0u) {
+        throw std::invalid_argument("Cannot invoke propagate_grid() in an adaptive Taylor integrator in batch mode "
+                                    "if the time grid is empty");
+    }
+    if (n_pts > 0xffffffffull) {
+        throw std::overflow_error("Too many grid points passed to propagate_grid()");
+    }
+    // The current time must be finite (:1590-1594).
+    std::vector<double> t_hi(n), t_lo(n);
+    {
+        HY_CUDA_CHECK(cudaMemcpyAsync(t_hi.data(), b->d_t_hi, sizeof(double) * n, cudaMemcpyDeviceToHost, b->stream));
+        HY_CUDA_CHECK(cudaMemcpyAsync(t_lo.data(), b->d_t_lo, sizeof(double) * n, cudaMemcpyDeviceToHost, b->stream));
+        HY_CUDA_CHECK(cudaStreamSynchronize(b->stream));
+        for (std::uint32_t i = 0; i < n; ++i) {
+            if (!std::isfinite(t_hi[i]) || !std::isfinite(t_lo[i])) {
+                throw std::invalid_argument("Cannot invoke propagate_grid() in an adaptive Taylor integrator in "
+                                            "batch mode if the current time is not finite");
+            }
+        }
+    }
+    if (max_delta_t != nullptr) {
+        for (std::uint32_t i = 0; i < n; ++i) {
+            if (std::isnan(max_delta_t[i])) {
+                throw std::invalid_argument("A nan max_delta_t was passed to the propagate_grid() function of an "
+                                            "adaptive Taylor integrator in batch mode");
+            }
+            if (max_delta_t[i] <= 0) {
+                throw std::invalid_argument("A non-positive max_delta_t was passed to the propagate_grid() "
+                                            "function of an adaptive Taylor integrator in batch mode");
+            }
+        }
+    }
+    // Grid checks, :1619-1656: finite, strictly monotonic, same direction in every lane.
+    constexpr auto nf_err_msg
+        = "A non-finite time value was passed to propagate_grid() in an adaptive Taylor integrator in batch mode";
+    constexpr auto ig_err_msg = "A non-monotonic time grid was passed to propagate_grid() in an adaptive "
+                                "Taylor integrator in batch mode";
+    const auto batch_nf = [&](std::uint64_t k) {
+        return std::any_of(grid + k * n, grid + (k + 1u) * n, [](double t) { return !std::isfinite(t); });
+    };
+    if (batch_nf(0)) {
+        throw std::invalid_argument(nf_err_msg);
+    }
+    if (n_pts > 1u) {
+        // The direction is established from the first two points of lane 0.
+        if (batch_nf(1)) {
+            throw std::invalid_argument(nf_err_msg);
+        }
+        if (grid[n] == grid[0]) {
+            throw std::invalid_argument(ig_err_msg);
+        }
+        const bool dir = grid[n] > grid[0];
+        for (std::uint64_t k = 1; k < n_pts; ++k) {
+            if (k > 1u && batch_nf(k)) {
+                throw std::invalid_argument(nf_err_msg);
+            }
+            for (std::uint32_t i = 0; i < n; ++i) {
+                if ((grid[k * n + i] > grid[(k - 1u) * n + i]) != dir) {
+                    throw std::invalid_argument(ig_err_msg);
+                }
+            }
+        }
+    }
+    // The grid must start at the current time (:1660-1670).
+    for (std::uint32_t i = 0; i < n; ++i) {
+        if (t_hi[i] != grid[i]) {
+            throw std::invalid_argument(
+                "When invoking propagate_grid(), the first element of the time grid must match the current "
+                "time coordinate - however, the first element of the time grid at batch index "
+                + std::to_string(i) + " has a value of " + hy::detail::fmt_double(grid[i])
+                + ", while the current time coordinate is " + hy::detail::fmt_double(t_hi[i]));
+        }
+    }
+}
+
+} // namespace
+
+int hy_batch_check_grid(hy_batch *b, const double *grid, uint64_t n_pts, const double *max_delta_t)
+{
+    try {
+        if (b == nullptr || grid == nullptr) {
+            throw std::invalid_argument("Null pointer passed to hy_batch_check_grid()");
+        }
+        device_guard guard(b->device);
+        check_grid(b, grid, n_pts, max_delta_t);
+        return HY_OK;
+    } catch (...) {
+        return translate_exception();
+    }
+}
+
 int hy_batch_propagate_grid(hy_batch *b, const double *grid, uint64_t n_pts, const double *max_delta_t,
                             uint64_t max_steps, double *out)
 {
@@ -2108,7 +2206,7 @@ int hy_batch_propagate_grid(hy_batch *b, const double *grid, uint64_t n_pts, con
         }
     };
     try {
-        if (b->n_ev != 0u) {
+        if (b != nullptr && b->n_ev != 0u) {
             throw hy::detail::not_implemented_error("A batch with event equations is propagated by the front end's lock-step "
                                                     "loop over hy_batch_step(), not by the device-resident propagation");
         }
@@ -2120,79 +2218,7 @@ int hy_batch_propagate_grid(hy_batch *b, const double *grid, uint64_t n_pts, con
         }
         device_guard guard(b->device);
         const std::uint32_t n = b->n;
-        if (n_pts == 0u) {
-            throw std::invalid_argument("Cannot invoke propagate_grid() in an adaptive Taylor integrator in batch mode "
-                                        "if the time grid is empty");
-        }
-        if (n_pts > 0xffffffffull) {
-            throw std::overflow_error("Too many grid points passed to propagate_grid()");
-        }
-        // The current time must be finite (:1590-1594).
-        std::vector<double> t_hi(n), t_lo(n);
-        {
-            HY_CUDA_CHECK(cudaMemcpyAsync(t_hi.data(), b->d_t_hi, sizeof(double) * n, cudaMemcpyDeviceToHost, b->stream));
-            HY_CUDA_CHECK(cudaMemcpyAsync(t_lo.data(), b->d_t_lo, sizeof(double) * n, cudaMemcpyDeviceToHost, b->stream));
-            HY_CUDA_CHECK(cudaStreamSynchronize(b->stream));
-            for (std::uint32_t i = 0; i < n; ++i) {
-                if (!std::isfinite(t_hi[i]) || !std::isfinite(t_lo[i])) {
-                    throw std::invalid_argument("Cannot invoke propagate_grid() in an adaptive Taylor integrator in "
-                                                "batch mode if the current time is not finite");
-                }
-            }
-        }
-        if (max_delta_t != nullptr) {
-            for (std::uint32_t i = 0; i < n; ++i) {
-                if (std::isnan(max_delta_t[i])) {
-                    throw std::invalid_argument("A nan max_delta_t was passed to the propagate_grid() function of an "
-                                                "adaptive Taylor integrator in batch mode");
-                }
-                if (max_delta_t[i] <= 0) {
-                    throw std::invalid_argument("A non-positive max_delta_t was passed to the propagate_grid() "
-                                                "function of an adaptive Taylor integrator in batch mode");
-                }
-            }
-        }
-        // Grid checks, :1619-1656: finite, strictly monotonic, same direction in every lane.
-        constexpr auto nf_err_msg
-            = "A non-finite time value was passed to propagate_grid() in an adaptive Taylor integrator in batch mode";
-        constexpr auto ig_err_msg = "A non-monotonic time grid was passed to propagate_grid() in an adaptive "
-                                    "Taylor integrator in batch mode";
-        const auto batch_nf = [&](std::uint64_t k) {
-            return std::any_of(grid + k * n, grid + (k + 1u) * n, [](double t) { return !std::isfinite(t); });
-        };
-        if (batch_nf(0)) {
-            throw std::invalid_argument(nf_err_msg);
-        }
-        if (n_pts > 1u) {
-            // The direction is established from the first two points of lane 0.
-            if (batch_nf(1)) {
-                throw std::invalid_argument(nf_err_msg);
-            }
-            if (grid[n] == grid[0]) {
-                throw std::invalid_argument(ig_err_msg);
-            }
-            const bool dir = grid[n] > grid[0];
-            for (std::uint64_t k = 1; k < n_pts; ++k) {
-                if (k > 1u && batch_nf(k)) {
-                    throw std::invalid_argument(nf_err_msg);
-                }
-                for (std::uint32_t i = 0; i < n; ++i) {
-                    if ((grid[k * n + i] > grid[(k - 1u) * n + i]) != dir) {
-                        throw std::invalid_argument(ig_err_msg);
-                    }
-                }
-            }
-        }
-        // The grid must start at the current time (:1660-1670).
-        for (std::uint32_t i = 0; i < n; ++i) {
-            if (t_hi[i] != grid[i]) {
-                throw std::invalid_argument(
-                    "When invoking propagate_grid(), the first element of the time grid must match the current "
-                    "time coordinate - however, the first element of the time grid at batch index "
-                    + std::to_string(i) + " has a value of " + hy::detail::fmt_double(grid[i])
-                    + ", while the current time coordinate is " + hy::detail::fmt_double(t_hi[i]));
-            }
-        }
+        check_grid(b, grid, n_pts, max_delta_t);
 
         const std::size_t n_out = static_cast<std::size_t>(n_pts) * b->n_eq * n, state_doubles = std::size_t(b->n_eq) * n;
         HY_CUDA_CHECK(cudaMalloc(&d_grid, sizeof(double) * n_pts * n));
@@ -2338,7 +2364,7 @@ int hy_batch_propagate_until_cout(hy_batch *b, const double *t_final_hi, const d
         }
     };
     try {
-        if (b->n_ev != 0u) {
+        if (b != nullptr && b->n_ev != 0u) {
             throw hy::detail::not_implemented_error("A batch with event equations is propagated by the front end's lock-step "
                                                     "loop over hy_batch_step(), not by the device-resident propagation");
         }

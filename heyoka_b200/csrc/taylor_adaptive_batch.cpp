@@ -110,6 +110,8 @@ struct taylor_adaptive_batch<double>::impl {
     std::vector<double> tmp_a, tmp_b;
     std::vector<std::uint64_t> tmp_n;
     bool tc_valid = false; // the device holds the Taylor coefficients mirrored in `tc`
+    std::vector<t_event_batch<double>> tes;
+    std::vector<nt_event_batch<double>> ntes;
 
     impl() = default;
     impl(const impl &o)
@@ -118,7 +120,7 @@ struct taylor_adaptive_batch<double>::impl {
           tape_mode(o.tape_mode), k_lpw(o.k_lpw), k_lpt(o.k_lpt), k_threads(o.k_threads), k_bpsm(o.k_bpsm),
           state(o.state), pars(o.pars), time_hi(o.time_hi), time_lo(o.time_lo), tc(o.tc), last_h(o.last_h),
           d_out(o.d_out), step_res(o.step_res), prop_res(o.prop_res), oc(o.oc), tmp_a(o.tmp_a), tmp_b(o.tmp_b),
-          tmp_n(o.tmp_n), tc_valid(o.tc_valid)
+          tmp_n(o.tmp_n), tc_valid(o.tc_valid), tes(o.tes), ntes(o.ntes)
     {
         if (prog) {
             make_batch();
@@ -142,6 +144,18 @@ struct taylor_adaptive_batch<double>::impl {
         }
         if (tape_mode != 0 || k_lpw != 0 || k_lpt != 0 || k_threads != 0 || k_bpsm != 0) {
             check(hy_batch_set_kernel(batch, tape_mode, k_lpw, k_lpt, k_threads, k_bpsm));
+        }
+        if (!tes.empty() || !ntes.empty()) {
+            std::vector<std::int32_t> dirs;
+            std::vector<double> cds;
+            for (const auto &e : tes) {
+                dirs.push_back(static_cast<std::int32_t>(e.get_direction()));
+                cds.push_back(e.get_cooldown());
+            }
+            for (const auto &e : ntes) {
+                dirs.push_back(static_cast<std::int32_t>(e.get_direction()));
+            }
+            check(hy_batch_set_events(batch, static_cast<std::uint32_t>(tes.size()), dirs.data(), cds.data(), tol));
         }
     }
     void push()
@@ -192,10 +206,19 @@ void taylor_adaptive_batch<double>::finalise_ctor(std::vector<std::pair<expressi
 {
     auto &m = *m_impl;
 
-    if (o.with_events) {
-        throw not_implemented_error("Event detection is not supported by the B200 batch integrator");
+    std::vector<expression> ev_ex;
+    for (const auto &e : o.tes) {
+        ev_ex.push_back(e.get_expression());
     }
-    validate_ode_sys(sys);
+    for (const auto &e : o.ntes) {
+        ev_ex.push_back(e.get_expression());
+    }
+    if (!ev_ex.empty() && !o.devices.empty()) {
+        throw not_implemented_error("Event detection is not available on an integrator sharded over several devices");
+    }
+    validate_ode_sys(sys, ev_ex);
+    m.tes = std::move(o.tes);
+    m.ntes = std::move(o.ntes);
 
     m.batch_size = batch_size;
     m.high_accuracy = o.high_accuracy;
@@ -249,6 +272,8 @@ void taylor_adaptive_batch<double>::finalise_ctor(std::vector<std::pair<expressi
     for (const auto &p : sys) {
         all_rhs.push_back(p.second);
     }
+    // (The parameters of the event equations count: test/taylor_adaptive_batch.cpp:1015-1060.)
+    all_rhs.insert(all_rhs.end(), ev_ex.begin(), ev_ex.end());
     m.n_pars = get_param_size(all_rhs);
     const auto pars_req = static_cast<std::size_t>(m.n_pars) * batch_size;
     if (o.pars.empty()) {
@@ -266,10 +291,12 @@ void taylor_adaptive_batch<double>::finalise_ctor(std::vector<std::pair<expressi
     m.order = detail::taylor_order_from_tol(m.tol);
 
     // Decompose, lower, create the device-resident batch (replaces taylor_add_adaptive_step() + JIT).
-    m.dc = taylor_decompose_sys(sys, {}).first;
+    auto dc_ev = taylor_decompose_sys(sys, ev_ex);
+    m.dc = std::move(dc_ev.first);
     try {
         m.prog = std::make_shared<hy_program>(
             detail::lower_decomposition(m.dc, m.dim, m.n_pars, m.order, m.high_accuracy));
+        m.prog->ev_defs = std::move(dc_ev.second);
     } catch (const detail::not_implemented_error &e) {
         throw not_implemented_error(e.what());
     }
@@ -539,8 +566,157 @@ void taylor_adaptive_batch<double>::step_impl(const std::vector<double> *max_del
     m.push();
     check(hy_batch_step(m.batch, max_delta_ts != nullptr ? max_delta_ts->data() : nullptr, 0, backward ? 1 : 0,
                         wtc ? 1 : 0));
-    m.pull(wtc);
+    // With events the Taylor coefficients are written unconditionally (src/taylor_adaptive_batch.cpp:776).
+    const bool ev = with_events();
+    m.pull(wtc || ev);
     m.pull_step_res();
+    if (ev) {
+        run_event_callbacks();
+    }
+}
+
+// The callback part of the events branch of step_impl() (src/taylor_adaptive_batch.cpp:803-1033): the detection, the
+// propagation and the cooldowns were done on the device by hy_batch_step().
+void taylor_adaptive_batch<double>::run_event_callbacks()
+{
+    auto &m = *m_impl;
+    const auto n_ev = hy_batch_n_events(m.batch);
+    if (n_ev == 0u) {
+        return;
+    }
+    std::vector<hy_event_rec> evs(n_ev);
+    check(hy_batch_get_events(m.batch, evs.data(), n_ev));
+    const auto t_hi = m.time_hi, t_lo = m.time_lo;
+    std::vector<std::pair<std::uint32_t, std::exception_ptr>> cb_eptrs;
+    for (std::size_t k = 0; k < evs.size();) {
+        const auto lane = evs[k].lane;
+        std::size_t end = k;
+        while (end < evs.size() && evs[end].lane == lane) {
+            ++end;
+        }
+        const double h = m.last_h[lane];
+        bool nt_cb_exception = false;
+        std::size_t j = k;
+        for (; j < end && evs[j].terminal == 0; ++j) {
+            auto &cb = m.ntes[evs[j].idx].get_callback();
+            // new_time - last_h + t in double-length arithmetic (:889).
+            const auto tm = dfl_add(dfl_sub(dfl{t_hi[lane], t_lo[lane]}, dfl{h, 0.}), dfl{evs[j].t, 0.}).hi;
+            try {
+                cb(*this, tm, evs[j].d_sgn, lane);
+            } catch (...) {
+                cb_eptrs.emplace_back(lane, std::current_exception());
+                nt_cb_exception = true;
+                break;
+            }
+        }
+        if (!nt_cb_exception) {
+            for (; j < end; ++j) {
+                if (evs[j].terminal != 0) {
+                    auto &te = m.tes[evs[j].idx];
+                    bool te_cb_ret = false;
+                    bool thrown = false;
+                    if (te.get_callback()) {
+                        try {
+                            te_cb_ret = te.get_callback()(*this, evs[j].d_sgn, lane);
+                        } catch (...) {
+                            cb_eptrs.emplace_back(lane, std::current_exception());
+                            thrown = true;
+                        }
+                    }
+                    if (!thrown) {
+                        const auto ev_idx = static_cast<std::int64_t>(evs[j].idx);
+                        m.step_res[lane] = std::tuple{taylor_outcome{te_cb_ret ? ev_idx : (-ev_idx - 1)}, h};
+                    }
+                    break;
+                }
+            }
+        }
+        k = end;
+    }
+    if (!cb_eptrs.empty()) {
+        if (cb_eptrs.size() == 1u) {
+            std::rethrow_exception(cb_eptrs[0].second);
+        }
+        std::string exc_msg = "Two or more exceptions were raised during the execution of event callbacks in a "
+                              "batch integrator:\n\n";
+        for (auto &[i, eptr] : cb_eptrs) {
+            exc_msg += "Batch index #" + std::to_string(i) + ":\n";
+            try {
+                std::rethrow_exception(eptr);
+            } catch (const std::exception &ex) {
+                exc_msg += std::string("    Exception type: ") + typeid(ex).name() + "\n";
+                exc_msg += std::string("    Exception message: ") + ex.what() + "\n";
+            } catch (...) {
+                exc_msg += "    Exception type: unknown\n    Exception message: unknown\n";
+            }
+            exc_msg += '\n';
+        }
+        throw std::runtime_error(exc_msg);
+    }
+    const auto same = [](double a, double b) { return a == b || (std::isnan(a) && std::isnan(b)); };
+    for (std::uint32_t i = 0; i < m.batch_size; ++i) {
+        if (!same(m.time_hi[i], t_hi[i]) || !same(m.time_lo[i], t_lo[i])) {
+            throw std::runtime_error("The invocation of one or more event callbacks resulted in the alteration of the "
+                                     "time coordinate of the integrator at the batch index "
+                                     + std::to_string(i) + " - this is not supported");
+        }
+    }
+}
+
+bool taylor_adaptive_batch<double>::with_events() const
+{
+    return !m_impl->tes.empty() || !m_impl->ntes.empty();
+}
+const std::vector<t_event_batch<double>> &taylor_adaptive_batch<double>::get_t_events() const
+{
+    return m_impl->tes;
+}
+const std::vector<nt_event_batch<double>> &taylor_adaptive_batch<double>::get_nt_events() const
+{
+    return m_impl->ntes;
+}
+void taylor_adaptive_batch<double>::reset_cooldowns()
+{
+    if (!with_events()) {
+        throw std::invalid_argument("No events were defined for this integrator");
+    }
+    check(hy_batch_reset_cooldowns(m_impl->batch, -1));
+}
+void taylor_adaptive_batch<double>::reset_cooldowns(std::uint32_t i)
+{
+    if (!with_events()) {
+        throw std::invalid_argument("No events were defined for this integrator");
+    }
+    check(hy_batch_reset_cooldowns(m_impl->batch, static_cast<std::int64_t>(i)));
+}
+
+// ---- events (src/t_event.cpp, src/nt_event.cpp) ----
+t_event_batch<double>::t_event_batch() : t_event_batch(expression{}) {}
+void t_event_batch<double>::finalise_ctor(callback_t cb, double cd, event_direction d)
+{
+    callback = std::move(cb);
+    if (!std::isfinite(cd)) {
+        throw std::invalid_argument("Cannot set a non-finite cooldown value for a terminal event");
+    }
+    cooldown = cd;
+    if (d < event_direction::negative || d > event_direction::positive) {
+        throw std::invalid_argument("Invalid value selected for the direction of a terminal event");
+    }
+    dir = d;
+}
+nt_event_batch<double>::nt_event_batch()
+    : nt_event_batch(expression{}, [](taylor_adaptive_batch<double> &, double, int, std::uint32_t) {})
+{
+}
+void nt_event_batch<double>::finalise_ctor(event_direction d)
+{
+    if (!callback) {
+        throw std::invalid_argument("Cannot construct a non-terminal event with an empty callback");
+    }
+    if (d < event_direction::negative || d > event_direction::positive) {
+        throw std::invalid_argument("Invalid value selected for the direction of a non-terminal event");
+    }
+    dir = d;
 }
 
 void taylor_adaptive_batch<double>::step(bool wtc)
@@ -672,6 +848,9 @@ taylor_adaptive_batch<double>::propagate_grid_impl(const std::vector<double> &gr
     if (o.cb) {
         throw not_implemented_error("Callbacks are not supported by propagate_grid() in the B200 batch integrator");
     }
+    if (with_events()) {
+        return propagate_grid_events(grid, std::move(o));
+    }
     if (grid.empty()) {
         throw std::invalid_argument(
             "Cannot invoke propagate_grid() in an adaptive Taylor integrator in batch mode if the time grid is empty");
@@ -701,6 +880,146 @@ taylor_adaptive_batch<double>::propagate_grid_impl(const std::vector<double> &gr
     return {std::move(o.cb), std::move(retval)};
 }
 
+// propagate_grid() of an integrator with events: the reference's loop (src/taylor_adaptive_batch.cpp:1696-2053) on the
+// host - propagate_until() to the first grid point, then lock-step steps (with their event callbacks) interleaved with
+// dense-output sampling of the grid points each step covers.
+std::tuple<step_callback_batch<double>, std::vector<double>>
+taylor_adaptive_batch<double>::propagate_grid_events(const std::vector<double> &grid, prop_opts o)
+{
+    auto &m = *m_impl;
+    const auto n = m.batch_size;
+    const auto n_pts = grid.size() / n;
+    const double *mdt = o.max_delta_t.empty() ? nullptr : o.max_delta_t.data();
+    m.push();
+    check(hy_batch_check_grid(m.batch, grid.data(), n_pts, mdt));
+    std::vector<double> retval(grid.size() * m.dim, std::numeric_limits<double>::quiet_NaN());
+    const double inf = std::numeric_limits<double>::infinity();
+
+    {
+        prop_opts po;
+        po.max_steps = o.max_steps;
+        po.max_delta_t = o.max_delta_t;
+        po.write_tc = true;
+        propagate_until_impl(std::vector<double>(grid.begin(), grid.begin() + n), std::vector<double>(n, 0.), std::move(po));
+    }
+    bool all_tl = true;
+    for (const auto &r : m.prop_res) {
+        all_tl = all_tl && std::get<0>(r) == taylor_outcome::time_limit;
+    }
+    if (!all_tl) {
+        for (auto &r : m.prop_res) {
+            std::get<1>(r) = inf;
+            std::get<2>(r) = 0.;
+            std::get<3>(r) = 0u;
+        }
+        return {std::move(o.cb), std::move(retval)};
+    }
+    std::copy(m.state.begin(), m.state.end(), retval.begin());
+
+    std::vector<dfl> rem(n);
+    std::vector<char> t_dir(n);
+    for (std::uint32_t i = 0; i < n; ++i) {
+        rem[i] = dfl_sub(dfl{grid[(n_pts - 1u) * n + i], 0.}, dfl{m.time_hi[i], m.time_lo[i]});
+        if (!std::isfinite(rem[i].hi) || !std::isfinite(rem[i].lo)) {
+            throw std::invalid_argument("The final time passed to the propagate_grid() function of an adaptive Taylor "
+                                        "integrator in batch mode results in an overflow condition");
+        }
+        t_dir[i] = dfl_ge0(rem[i]) ? 1 : 0;
+    }
+    std::size_t iter_counter = 0;
+    std::vector<std::size_t> ts_count(n, 0), cur_idx(n, 1);
+    std::vector<double> min_h(n, inf), max_h(n, 0.), pgrid(n);
+    std::vector<dfl> t0(n), t1(n);
+    std::vector<unsigned> dflags(n);
+    const auto cont_cond = [&]() {
+        return std::any_of(cur_idx.begin(), cur_idx.end(), [n_pts](auto idx) { return idx < n_pts; });
+    };
+    while (cont_cond()) {
+        for (std::uint32_t i = 0; i < n; ++i) {
+            const dfl cur{m.time_hi[i], m.time_lo[i]}, cmp = dfl_sub(cur, dfl{m.last_h[i], 0.});
+            t0[i] = dfl_lt(cmp, cur) ? cmp : cur;
+            t1[i] = dfl_lt(cur, cmp) ? cmp : cur;
+        }
+        std::fill(dflags.begin(), dflags.end(), 1u);
+        while (true) {
+            std::uint32_t counter = 0;
+            for (std::uint32_t i = 0; i < n; ++i) {
+                const auto gidx = cur_idx[i];
+                if (dflags[i] != 0u && gidx < n_pts) {
+                    const dfl g{grid[gidx * n + i], 0.};
+                    const bool d_avail = (!dfl_lt(g, t0[i]) && !dfl_lt(t1[i], g)) || (rem[i].hi == 0. && rem[i].lo == 0.);
+                    dflags[i] = d_avail ? 1u : 0u;
+                    counter += d_avail ? 1u : 0u;
+                    pgrid[i] = g.hi;
+                } else {
+                    dflags[i] = 0u;
+                }
+            }
+            if (counter == 0u) {
+                break;
+            }
+            update_d_output(pgrid);
+            for (std::uint32_t i = 0; i < n; ++i) {
+                if (dflags[i] != 0u) {
+                    for (std::uint32_t j = 0; j < m.dim; ++j) {
+                        retval[cur_idx[i] * n * m.dim + j * n + i] = m.d_out[j * n + i];
+                    }
+                    ++cur_idx[i];
+                }
+            }
+            if (!cont_cond()) {
+                break;
+            }
+        }
+        if (!cont_cond()) {
+            break;
+        }
+        if (std::any_of(m.prop_res.begin(), m.prop_res.end(), [](const auto &t) {
+                const auto oc = std::get<0>(t);
+                return oc == taylor_outcome::cb_stop || (oc > taylor_outcome::success && oc < taylor_outcome{0})
+                       || oc == taylor_outcome::step_limit;
+            })) {
+            break;
+        }
+        for (std::uint32_t i = 0; i < n; ++i) {
+            const double md = mdt != nullptr ? mdt[i] : inf;
+            const dfl lim = t_dir[i] ? (dfl_lt(rem[i], dfl{md, 0.}) ? rem[i] : dfl{md, 0.})
+                                     : (dfl_lt(rem[i], dfl{-md, 0.}) ? dfl{-md, 0.} : rem[i]);
+            pgrid[i] = lim.hi;
+        }
+        step_impl(&pgrid, false, true);
+        bool nfs = false;
+        for (std::uint32_t i = 0; i < n; ++i) {
+            const auto [oc, h] = m.step_res[i];
+            if (oc == taylor_outcome::err_nf_state) {
+                nfs = true;
+            } else {
+                ts_count[i] += static_cast<std::size_t>(h != 0);
+                if (oc == taylor_outcome::success) {
+                    min_h[i] = std::min(min_h[i], std::abs(h));
+                    max_h[i] = std::max(max_h[i], std::abs(h));
+                }
+                if (h == rem[i].hi) {
+                    rem[i] = dfl{0., 0.};
+                } else {
+                    rem[i] = dfl_sub(dfl{grid[(n_pts - 1u) * n + i], 0.}, dfl{m.time_hi[i], m.time_lo[i]});
+                }
+            }
+            m.prop_res[i] = std::tuple{oc, min_h[i], max_h[i], ts_count[i]};
+        }
+        if (nfs) {
+            break;
+        }
+        ++iter_counter;
+        if (iter_counter == o.max_steps) {
+            for (auto &t : m.prop_res) {
+                std::get<0>(t) = taylor_outcome::step_limit;
+            }
+        }
+    }
+    return {std::move(o.cb), std::move(retval)};
+}
+
 std::tuple<std::optional<continuous_output_batch<double>>, step_callback_batch<double>>
 taylor_adaptive_batch<double>::propagate_until_impl(const std::vector<double> &hi, const std::vector<double> &lo,
                                                     prop_opts o)
@@ -708,9 +1027,9 @@ taylor_adaptive_batch<double>::propagate_until_impl(const std::vector<double> &h
     auto &m = *m_impl;
     const auto n = m.batch_size;
 
-    if (o.c_output && o.cb) {
-        throw not_implemented_error("Continuous output together with a callback is not supported by the B200 batch "
-                                    "integrator");
+    if (o.c_output && (o.cb || with_events())) {
+        throw not_implemented_error("Continuous output together with a callback or with events is not supported by the "
+                                    "B200 batch integrator");
     }
 
     // Validation, src/taylor_adaptive_batch.cpp:1212-1273.
@@ -765,7 +1084,7 @@ taylor_adaptive_batch<double>::propagate_until_impl(const std::vector<double> &h
         return {std::move(ret), std::move(o.cb)};
     }
 
-    if (!o.cb) {
+    if (!o.cb && !with_events()) {
         // Fast path: the whole loop runs on the device.
         m.push();
         check(hy_batch_propagate_until(m.batch, hi.data(), lo.data(), mdt, o.max_steps, o.write_tc ? 1 : 0));
@@ -778,8 +1097,8 @@ taylor_adaptive_batch<double>::propagate_until_impl(const std::vector<double> &h
         return {std::nullopt, std::move(o.cb)};
     }
 
-    // Callback path: the reference's lock-step loop (src/taylor_adaptive_batch.cpp:1372-1527) on the host, one
-    // device step per iteration (a host callback per step forces a synchronisation anyway).
+    // Callback / events path: the reference's lock-step loop (src/taylor_adaptive_batch.cpp:1372-1527) on the host, one
+    // device step per iteration (host callbacks force a synchronisation per step anyway).
     constexpr auto cb_time_errmsg
         = "The invocation of the callback passed to propagate_until() resulted in the alteration of the "
           "time coordinate of the integrator - this is not supported";
@@ -800,12 +1119,14 @@ taylor_adaptive_batch<double>::propagate_until_impl(const std::vector<double> &h
         step_impl(&cur_max, false, o.write_tc);
 
         std::uint32_t n_done = 0;
-        bool nfs = false;
+        bool nfs = false, ste_detected = false;
         for (std::uint32_t i = 0; i < n; ++i) {
             const auto [oc, h] = m.step_res[i];
             if (oc == taylor_outcome::err_nf_state) {
                 nfs = true;
             } else {
+                // A stopping terminal event in any batch element ends the propagation (:1430, :1503).
+                ste_detected = ste_detected || (oc > taylor_outcome::success && oc < taylor_outcome{0});
                 ts_count[i] += static_cast<std::size_t>(h != 0);
                 if (oc == taylor_outcome::success) {
                     const auto ah = std::abs(h);
@@ -826,7 +1147,7 @@ taylor_adaptive_batch<double>::propagate_until_impl(const std::vector<double> &h
             return {std::nullopt, std::move(o.cb)};
         }
         ++iter_counter;
-        {
+        if (o.cb) {
             const auto thi = m.time_hi, tlo = m.time_lo;
             const bool ret_cb = o.cb(*this);
             if (m.time_hi != thi || m.time_lo != tlo) {
@@ -839,7 +1160,7 @@ taylor_adaptive_batch<double>::propagate_until_impl(const std::vector<double> &h
                 return {std::nullopt, std::move(o.cb)};
             }
         }
-        if (n_done == n) {
+        if (n_done == n || ste_detected) {
             return {std::nullopt, std::move(o.cb)};
         }
         if (iter_counter == o.max_steps) {

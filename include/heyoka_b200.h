@@ -261,6 +261,10 @@ int hy_batch_propagate_until_dev(hy_batch *, const double *d_t_final_hi, const d
 int hy_batch_propagate_grid(hy_batch *, const double *grid, uint64_t n_pts, const double *max_delta_t,
                             uint64_t max_steps, double *out);
 
+/* The argument checks of propagate_grid() alone (src/taylor_adaptive_batch.cpp:1575-1670; the current times are those
+ * last uploaded): used by the front ends' host loop for integrators with events. */
+int hy_batch_check_grid(hy_batch *, const double *grid, uint64_t n_pts, const double *max_delta_t);
+
 /* Continuous output (include/heyoka/continuous_output.hpp, producer src/taylor_adaptive_batch.cpp:1246-1346):
  * hy_batch_propagate_until_cout() runs propagate_until() as the reference's lock-step loop and records, at every
  * iteration, the Taylor coefficients and the (double-length) times of all lanes in device memory. *out is NULL if

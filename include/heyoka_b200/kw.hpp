@@ -131,6 +131,9 @@ HEYOKA_B200_KWARG(max_delta_t);
 HEYOKA_B200_KWARG(callback);
 HEYOKA_B200_KWARG(write_tc);
 HEYOKA_B200_KWARG(c_output);
+// Events (include/heyoka/events.hpp:49, include/heyoka/kw.hpp).
+HEYOKA_B200_KWARG(cooldown);
+HEYOKA_B200_KWARG(direction);
 // Models.
 HEYOKA_B200_KWARG(Gconst);
 HEYOKA_B200_KWARG(masses);

@@ -13,8 +13,11 @@
 // calls; they are uploaded at every step()/propagate_*() entry and refreshed on exit. The device-resident
 // batch (hy_batch) is shared between copies only in its program: a copy gets its own device buffers.
 //
-// Not supported (out of the hot path): event detection (kw::t_events / kw::nt_events throw),
-// variational systems, serialisation. kw::compact_mode,
+// Event detection (kw::t_events / kw::nt_events with t_event_batch<double> / nt_event_batch<double>,
+// include/heyoka/events.hpp): the jet of the event equations, the root finding and the cooldown bookkeeping run on the
+// device (include/heyoka_b200.h section E), the callbacks on the host, in the reference's order.
+//
+// Not supported (out of the hot path): variational systems, serialisation. kw::compact_mode,
 // kw::parallel_mode, kw::parjit and the llvm_state options are accepted and ignored (there is no JIT).
 #ifndef HEYOKA_B200_TAYLOR_HPP
 #define HEYOKA_B200_TAYLOR_HPP
@@ -88,6 +91,111 @@ public:
     }
 };
 
+// ---- events (include/heyoka/events.hpp) ----
+enum class event_direction { negative = -1, any = 0, positive = 1 };
+
+template <typename T>
+class t_event_batch;
+template <typename T>
+class nt_event_batch;
+
+// Terminal event (include/heyoka/events.hpp:52-118, src/t_event.cpp): callback(ta, d_sgn, batch_idx) -> true if the
+// integration may continue; kw::cooldown < 0 (default) = automatic; kw::direction.
+template <>
+class t_event_batch<double>
+{
+public:
+    using callback_t = std::function<bool(taylor_adaptive_batch<double> &, int, std::uint32_t)>;
+
+private:
+    expression eq;
+    callback_t callback;
+    double cooldown = -1.;
+    event_direction dir = event_direction::any;
+
+    void finalise_ctor(callback_t, double, event_direction);
+
+public:
+    t_event_batch();
+    template <typename... KwArgs>
+    explicit t_event_batch(expression e, const KwArgs &...kw_args) : eq(std::move(e))
+    {
+        static_assert(kw::allowed_tags<kw::callback_tag, kw::cooldown_tag, kw::direction_tag>::template all<KwArgs...>(),
+                      "Invalid named argument(s) in the construction of a terminal event");
+        callback_t cb;
+        double cd = -1.;
+        event_direction d = event_direction::any;
+        kw::visit(kw::callback, [&cb](const auto &v) { cb = v; }, kw_args...);
+        kw::visit(kw::cooldown, [&cd](const auto &v) { cd = static_cast<double>(v); }, kw_args...);
+        kw::visit(kw::direction, [&d](const auto &v) { d = v; }, kw_args...);
+        finalise_ctor(std::move(cb), cd, d);
+    }
+    [[nodiscard]] const expression &get_expression() const
+    {
+        return eq;
+    }
+    [[nodiscard]] const callback_t &get_callback() const
+    {
+        return callback;
+    }
+    [[nodiscard]] callback_t &get_callback()
+    {
+        return callback;
+    }
+    [[nodiscard]] event_direction get_direction() const
+    {
+        return dir;
+    }
+    [[nodiscard]] double get_cooldown() const
+    {
+        return cooldown;
+    }
+};
+
+// Non-terminal event (include/heyoka/events.hpp:142-196, src/nt_event.cpp): callback(ta, t, d_sgn, batch_idx).
+template <>
+class nt_event_batch<double>
+{
+public:
+    using callback_t = std::function<void(taylor_adaptive_batch<double> &, double, int, std::uint32_t)>;
+
+private:
+    expression eq;
+    callback_t callback;
+    event_direction dir = event_direction::any;
+
+    void finalise_ctor(event_direction);
+
+public:
+    nt_event_batch();
+    template <typename... KwArgs>
+    explicit nt_event_batch(expression e, callback_t cb, const KwArgs &...kw_args)
+        : eq(std::move(e)), callback(std::move(cb))
+    {
+        static_assert(kw::allowed_tags<kw::direction_tag>::template all<KwArgs...>(),
+                      "Invalid named argument(s) in the construction of a non-terminal event");
+        event_direction d = event_direction::any;
+        kw::visit(kw::direction, [&d](const auto &v) { d = v; }, kw_args...);
+        finalise_ctor(d);
+    }
+    [[nodiscard]] const expression &get_expression() const
+    {
+        return eq;
+    }
+    [[nodiscard]] const callback_t &get_callback() const
+    {
+        return callback;
+    }
+    [[nodiscard]] callback_t &get_callback()
+    {
+        return callback;
+    }
+    [[nodiscard]] event_direction get_direction() const
+    {
+        return dir;
+    }
+};
+
 // include/heyoka/step_callback.hpp:57-139 reduced to the call operator: bool(taylor_adaptive_batch<T> &).
 template <typename T>
 using step_callback_batch = std::function<bool(taylor_adaptive_batch<T> &)>;
@@ -97,6 +205,8 @@ class taylor_adaptive_batch<double>
 {
 public:
     using value_type = double;
+    using t_event_t = t_event_batch<double>;
+    using nt_event_t = nt_event_batch<double>;
 
 private:
     struct impl;
@@ -110,7 +220,8 @@ private:
         bool high_accuracy = false;
         bool compact_mode = false;
         std::vector<double> pars;
-        bool with_events = false;
+        std::vector<t_event_t> tes;
+        std::vector<nt_event_t> ntes;
         int device = -1;
         std::vector<int> devices; // non-empty: the batch is sharded over these GPUs
     };
@@ -124,10 +235,13 @@ private:
 
     void finalise_ctor(std::vector<std::pair<expression, expression>>, std::vector<double>, std::uint32_t, ctor_opts);
     void step_impl(const std::vector<double> *, bool backward, bool wtc);
+    void run_event_callbacks();
     std::tuple<std::optional<continuous_output_batch<double>>, step_callback_batch<double>>
     propagate_until_impl(const std::vector<double> &hi, const std::vector<double> &lo, prop_opts);
     std::tuple<step_callback_batch<double>, std::vector<double>> propagate_grid_impl(const std::vector<double> &,
                                                                                      prop_opts);
+    std::tuple<step_callback_batch<double>, std::vector<double>> propagate_grid_events(const std::vector<double> &,
+                                                                                       prop_opts);
 
     template <typename... KwArgs>
     static ctor_opts parse_ctor(const KwArgs &...kw_args)
@@ -156,7 +270,8 @@ private:
         kw::visit(kw::pars, [&o](const auto &v) { o.pars.assign(std::begin(v), std::end(v)); }, kw_args...);
         kw::visit(kw::device, [&o](const auto &v) { o.device = static_cast<int>(v); }, kw_args...);
         kw::visit(kw::devices, [&o](const auto &v) { o.devices.assign(std::begin(v), std::end(v)); }, kw_args...);
-        o.with_events = kw::has_tag<kw::t_events_tag, KwArgs...>() || kw::has_tag<kw::nt_events_tag, KwArgs...>();
+        kw::visit(kw::t_events, [&o](const auto &v) { o.tes.assign(std::begin(v), std::end(v)); }, kw_args...);
+        kw::visit(kw::nt_events, [&o](const auto &v) { o.ntes.assign(std::begin(v), std::end(v)); }, kw_args...);
         return o;
     }
 
@@ -234,10 +349,13 @@ public:
     [[nodiscard]] const std::vector<double> &get_d_output() const;
     const std::vector<double> &update_d_output(const std::vector<double> &, bool rel_time = false);
     const std::vector<double> &update_d_output(double, bool rel_time = false);
-    [[nodiscard]] bool with_events() const
-    {
-        return false;
-    }
+    [[nodiscard]] bool with_events() const;
+    [[nodiscard]] const std::vector<t_event_t> &get_t_events() const;
+    [[nodiscard]] const std::vector<nt_event_t> &get_nt_events() const;
+    // Clears the cooldowns of the terminal events, for every batch element / for one
+    // (src/taylor_adaptive_batch.cpp:2300-2330).
+    void reset_cooldowns();
+    void reset_cooldowns(std::uint32_t);
 
     void step(bool wtc = false);
     void step_backward(bool wtc = false);

@@ -72,8 +72,12 @@ static void test_ctor_errors()
                        "1 parameter value(s) were passed, but the ODE system contains 1 parameter(s) (in batches of 2)");
     REQUIRE_THROWS_MSG((ta_t{{prime(x) = v, prime(x) = x}, {0.05, 0.06, 0.025, 0.026}, 2u}), std::invalid_argument,
                        "appears twice");
-    REQUIRE_THROWS_MSG((ta_t{sys, {0.05, 0.06, 0.025, 0.026}, 2u, kw::t_events = std::vector<int>{1}}),
-                       not_implemented_error, "Event detection is not supported");
+    {
+        auto [y] = make_vars("y");
+        REQUIRE_THROWS_MSG((ta_t{sys, {0.05, 0.06, 0.025, 0.026}, 2u, kw::t_events = {t_event_batch<double>(x + y)}}),
+                           std::invalid_argument,
+                           "an event function contains the variable 'y', which is not a state variable");
+    }
 }
 
 static void test_batch_consistency()
@@ -215,16 +219,31 @@ static void test_ensemble()
 
 // Sharding over devices (kw::devices, set_device()): the lanes of one integrator split over several device-resident
 // batches, bit-identical to the unsharded integrator; copies and moves between devices keep state, time and tc.
+// A star and five planets on circular, coplanar orbits of radii 5, 9.5, 19, 30, 39 (years as time unit), lane i rotated
+// and stretched a little: [x, y, z, vx, vy, vz] per body, batch innermost (the layout of model::nbody).
+static std::vector<double> planetary_ic(std::uint32_t B, double G, double m0)
+{
+    const double radii[6] = {0., 5., 9.5, 19., 30., 39.};
+    std::vector<double> st(36u * B, 0.);
+    for (std::uint32_t l = 0; l < B; ++l) {
+        for (std::uint32_t b = 1; b < 6u; ++b) {
+            const double r = radii[b] * (1. + 1e-3 * l), ph = 0.9 * b + 0.05 * l, vc = std::sqrt(G * m0 / r);
+            st[(b * 6u + 0u) * B + l] = r * std::cos(ph);
+            st[(b * 6u + 1u) * B + l] = r * std::sin(ph);
+            st[(b * 6u + 3u) * B + l] = -vc * std::sin(ph);
+            st[(b * 6u + 4u) * B + l] = vc * std::cos(ph);
+        }
+    }
+    return st;
+}
+
 static void test_sharded_and_placement()
 {
     const std::vector<double> masses{1.00000597682, 1 / 1047.355, 1 / 3501.6, 1 / 22869., 1 / 19314., 7.4074074e-09};
     const double G = 0.01720209895 * 0.01720209895 * 365 * 365;
     auto sys = model::nbody(6, kw::masses = masses, kw::Gconst = G);
     const std::uint32_t B = 7u;
-    std::vector<double> st(36u * B);
-    for (std::size_t i = 0; i < st.size(); ++i) {
-        st[i] = 0.1 + 0.37 * static_cast<double>((i * 7919u) % 101u) / 101.;
-    }
+    const auto st = planetary_ic(B, G, masses[0]);
     taylor_adaptive_batch<double> one{sys, st, B, kw::high_accuracy = true};
     taylor_adaptive_batch<double> many{sys, st, B, kw::high_accuracy = true, kw::devices = std::vector<int>{0, 0, 0}};
     REQUIRE(hy_batch_n_shards(many.get_device_batch()) == 3u);
@@ -235,7 +254,7 @@ static void test_sharded_and_placement()
     REQUIRE(one.get_last_h() == many.get_last_h());
     std::vector<double> tf(B);
     for (std::uint32_t i = 0; i < B; ++i) {
-        tf[i] = 0.02 + 0.01 * i; // (short: these synthetic initial conditions are strongly interacting)
+        tf[i] = 3. + 0.7 * i;
     }
     one.propagate_until(tf);
     many.propagate_until(tf);
@@ -257,9 +276,8 @@ static void test_sharded_and_placement()
     REQUIRE(cp.update_d_output(0., true) == many.update_d_output(0., true));
     REQUIRE(one.update_d_output(0., true) == many.update_d_output(0., true));
     for (std::size_t i = 0, n_shown = 0; i < st.size(); ++i) {
-        // (These initial conditions are close encounters: the Taylor polynomials are summed with cancellation, the
-        // in-kernel update and the dense-output kernel agree to the conditioning of the sum, not to a few ulps.)
-        const bool ok = approx(cp.get_d_output()[i], many.get_state()[i], 1e5);
+        const bool ok = approx(cp.get_d_output()[i], many.get_state()[i], 100.)
+                        || std::abs(cp.get_d_output()[i] - many.get_state()[i]) < 1e-13; // (z components: ~0)
         REQUIRE(ok);
         if (!ok && n_shown++ < 4u) {
             std::fprintf(stderr, "d_output %zu: %.17g vs state %.17g (last_h %.17g)\n", i, cp.get_d_output()[i],
@@ -480,6 +498,167 @@ static void test_continuous_output()
     REQUIRE(ok);
 }
 
+// Event detection through the drop-in class: blocks of test/batch_event_detection.cpp.
+static void test_events()
+{
+    using t_ev_t = taylor_adaptive_batch<double>::t_event_t;
+    using nt_ev_t = taylor_adaptive_batch<double>::nt_event_t;
+    auto [x, v] = make_vars("x", "v");
+    const double inf = std::numeric_limits<double>::infinity();
+
+    // Event classes (src/t_event.cpp, src/nt_event.cpp; "te def ctor" :1818-1826).
+    {
+        t_ev_t te;
+        REQUIRE(!te.get_callback());
+        REQUIRE(te.get_direction() == event_direction::any);
+        REQUIRE(te.get_cooldown() == -1.);
+        REQUIRE_THROWS_MSG(t_ev_t(v, kw::cooldown = inf), std::invalid_argument,
+                           "Cannot set a non-finite cooldown value for a terminal event");
+        REQUIRE_THROWS_MSG(nt_ev_t(v, nt_ev_t::callback_t{}), std::invalid_argument,
+                           "Cannot construct a non-terminal event with an empty callback");
+        REQUIRE_THROWS_MSG(t_ev_t(v, kw::direction = static_cast<event_direction>(5)), std::invalid_argument,
+                           "Invalid value selected for the direction of a terminal event");
+    }
+    // "nte linear box" / "te linear box" (:262-327): an event at the very end of a step fires in the next one.
+    {
+        auto counter = 0u;
+        taylor_adaptive_batch<double> ta{{prime(x) = par[0]},
+                                         {0., 0., 0., 0.},
+                                         4u,
+                                         kw::nt_events = {nt_ev_t(x - 1.,
+                                                                  [&counter](auto &tint, double tm, int, std::uint32_t idx) {
+                                                                      REQUIRE(approx(tm, 1 / tint.get_pars()[idx], 100.));
+                                                                      ++counter;
+                                                                  })},
+                                         kw::pars = {1., 2., 4., 8.}};
+        REQUIRE(ta.with_events());
+        REQUIRE(ta.get_nt_events().size() == 1u);
+        ta.step({1., 1 / 2., 1 / 4., 1 / 8.});
+        REQUIRE(counter == 0u);
+        for (const auto &r : ta.get_step_res()) {
+            REQUIRE(std::get<0>(r) == taylor_outcome::time_limit);
+        }
+        ta.step({1., 1 / 2., 1 / 4., 1 / 8.});
+        REQUIRE(counter == 4u);
+
+        counter = 0u;
+        taylor_adaptive_batch<double> tb{{prime(x) = par[0]},
+                                         {0., 0., 0., 0.},
+                                         4u,
+                                         kw::t_events = {t_ev_t(x - 1., kw::callback =
+                                                                            [&counter](auto &, int, std::uint32_t) {
+                                                                                ++counter;
+                                                                                return true;
+                                                                            })},
+                                         kw::pars = {1., 2., 4., 8.}};
+        tb.step({1., 1 / 2., 1 / 4., 1 / 8.});
+        REQUIRE(counter == 0u);
+        tb.step({1., 1 / 2., 1 / 4., 1 / 8.});
+        REQUIRE(counter == 4u);
+        for (const auto &r : tb.get_step_res()) {
+            REQUIRE(std::get<0>(r) == taylor_outcome{0});
+            REQUIRE(std::abs(std::get<1>(r)) < 1e-14);
+        }
+    }
+    // "te propagate_for" (:1440-1477).
+    {
+        std::vector<unsigned> counter(4u, 0u);
+        t_ev_t ev(v, kw::callback = [&counter](auto &, int, std::uint32_t idx) {
+            ++counter[idx];
+            return true;
+        });
+        taylor_adaptive_batch<double> ta{
+            {prime(x) = v, prime(v) = -9.8 * sin(x)}, {0, 0.01, 0.02, 0.03, .25, .26, .27, .28}, 4u, kw::t_events = {ev}};
+        ta.propagate_for(100.);
+        for (std::uint32_t i = 0; i < 4u; ++i) {
+            REQUIRE(std::get<0>(ta.get_propagate_res()[i]) == taylor_outcome::time_limit);
+            REQUIRE(ta.get_time()[i] == 100.);
+            REQUIRE(counter[i] == 100u);
+        }
+        taylor_adaptive_batch<double> tb{{prime(x) = v, prime(v) = -9.8 * sin(x)},
+                                         {0, 0.01, 0.02, 0.03, .25, .26, .27, .28},
+                                         4u,
+                                         kw::t_events = {t_ev_t(v)}};
+        tb.propagate_for(100.);
+        for (std::uint32_t i = 0; i < 4u; ++i) {
+            REQUIRE(static_cast<std::int64_t>(std::get<0>(tb.get_propagate_res()[i])) == -1);
+        }
+        // Cooldowns can be cleared for one batch element or for all of them.
+        tb.reset_cooldowns(1u);
+        tb.reset_cooldowns();
+        REQUIRE_THROWS_MSG(tb.reset_cooldowns(4u), std::invalid_argument,
+                           "Cannot reset the cooldowns at batch index 4: the batch size is only 4");
+    }
+    // "te propagate_grid" (:1479-1534).
+    {
+        std::vector<unsigned> counter(4u, 0u);
+        t_ev_t ev(v, kw::callback = [&counter](auto &, int, std::uint32_t idx) {
+            ++counter[idx];
+            return true;
+        });
+        taylor_adaptive_batch<double> ta{
+            {prime(x) = v, prime(v) = -9.8 * sin(x)}, {0, 0.01, 0.02, 0.03, .25, .26, .27, .28}, 4u, kw::t_events = {ev}};
+        std::vector<double> grid;
+        for (auto i = 0; i < 101; ++i) {
+            grid.insert(grid.end(), 4u, static_cast<double>(i));
+        }
+        auto [cb, out] = ta.propagate_grid(grid);
+        REQUIRE(!cb);
+        REQUIRE(out.size() == 202u * 4u);
+        REQUIRE(std::all_of(out.begin() + 1, out.end(), [](const auto &val) { return val != 0 && std::isfinite(val); }));
+        for (std::uint32_t i = 0; i < 4u; ++i) {
+            REQUIRE(counter[i] == 100u);
+            REQUIRE(std::get<0>(ta.get_propagate_res()[i]) == taylor_outcome::time_limit);
+        }
+        taylor_adaptive_batch<double> tb{{prime(x) = v, prime(v) = -9.8 * sin(x)},
+                                         {0, 0.01, 0.02, 0.03, .25, .26, .27, .28},
+                                         4u,
+                                         kw::t_events = {t_ev_t(v)}};
+        std::tie(cb, out) = tb.propagate_grid(grid);
+        REQUIRE(std::all_of(out.begin() + 8, out.end(), [](const auto &val) { return std::isnan(val); }));
+        for (std::uint32_t i = 0; i < 4u; ++i) {
+            REQUIRE(static_cast<std::int64_t>(std::get<0>(tb.get_propagate_res()[i])) == -1);
+        }
+    }
+    // "te damped pendulum" (:1580-1645): the callback changes a parameter through get_pars_data().
+    {
+        std::vector<std::vector<double>> zero_vel_times(4u);
+        t_ev_t ev(v, kw::callback = [&zero_vel_times](auto &ta, int, std::uint32_t idx) {
+            ta.get_pars_data()[idx] = ta.get_pars()[idx] == 0 ? 1. : 0.;
+            zero_vel_times[idx].push_back(ta.get_time()[idx]);
+            return true;
+        });
+        taylor_adaptive_batch<double> ta{{prime(x) = v, prime(v) = -9.8 * sin(x) - par[0] * v},
+                                         {0.05, 0.051, 0.052, 0.053, 0.025, 0.0251, 0.0252, 0.0253},
+                                         4u,
+                                         kw::t_events = {ev}};
+        ta.propagate_until(100.);
+        for (auto i = 0u; i < 4u; ++i) {
+            REQUIRE(zero_vel_times[i].size() == 99u);
+        }
+        ta.step();
+        for (auto i = 0u; i < 4u; ++i) {
+            REQUIRE(zero_vel_times[i].size() == 100u);
+        }
+        // A copy carries the events (callbacks included) and detects on its own.
+        auto cp = ta;
+        REQUIRE(cp.with_events());
+        cp.propagate_for(1.);
+        for (auto i = 0u; i < 4u; ++i) {
+            REQUIRE(zero_vel_times[i].size() == 101u);
+        }
+    }
+    // An event function must be written in terms of the state variables (src/detail/validate_ode_sys.cpp:131-145).
+    {
+        auto [y] = make_vars("y");
+        REQUIRE_THROWS_MSG((taylor_adaptive_batch<double>{{prime(x) = v, prime(v) = -x}, {0., 1.}, 1u,
+                                                          kw::t_events = {t_ev_t(x + y)}}),
+                           std::invalid_argument,
+                           "Invalid system of differential equations detected: an event function contains the variable "
+                           "'y', which is not a state variable");
+    }
+}
+
 int main(int argc, char **argv)
 {
     const bool gpu = argc > 1 && std::strcmp(argv[1], "gpu") == 0;
@@ -493,6 +672,7 @@ int main(int argc, char **argv)
         test_continuous_output();
         test_ensemble_grid();
         test_sharded_and_placement();
+        test_events();
     }
     if (n_fail == 0) {
         std::printf("ALL PASSED (%s)\n", gpu ? "gpu" : "cpu");

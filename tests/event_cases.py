@@ -508,3 +508,36 @@ def case_single_step(make, terminal):
     if terminal:
         assert [len(t) for t in times] == [2, 1, 1, 1]  # ex_n_trig, :196
     return times, vels
+
+
+def case_te_propagate_grid(make):
+    """:1479-1578: propagate_grid() with a terminal event: with a callback that continues every grid point is reached,
+    without callback everything after the first trigger stays NaN."""
+    x, v, sys = pendulum_sys()
+    counter = [0] * 4
+
+    def cb(ta, d_sgn, i):
+        counter[i] += 1
+        return True
+
+    ta = make(sys, PEND_IC, 4, t_events=[hb.t_event_batch(v, callback=cb)])
+    grid = np.repeat(np.arange(101.)[:, None], 4, axis=1)
+    out = ta.propagate_grid(grid)
+    assert out.shape == (101, 2, 4)
+    assert np.all(out.reshape(-1)[1:] != 0) and np.all(np.isfinite(out))
+    assert counter == [100] * 4
+    assert all(r[0] == TO.time_limit for r in ta.propagate_res)
+    ta2 = make(sys, PEND_IC, 4, t_events=[hb.t_event_batch(v)])
+    out2 = ta2.propagate_grid(grid)
+    assert np.all(np.isnan(out2.reshape(-1)[8:]))
+    assert all(r[0] == -1 for r in ta2.propagate_res)
+    # "first step bug" (:1536-1578): the event triggers before the second grid point.
+    grid3 = np.repeat((5 / 100. * np.arange(100.))[:, None], 4, axis=1)
+    ic = [0.05, 0.051, 0.052, 0.053, 0.025, 0.0251, 0.0252, 0.0253]
+    ta3 = make(sys, ic, 4, t_events=[hb.t_event_batch(v, callback=lambda ta, s, i: True)])
+    out3 = ta3.propagate_grid(grid3)
+    assert np.all(out3 != 0) and np.all(np.isfinite(out3))
+    ta4 = make(sys, ic, 4, t_events=[hb.t_event_batch(v)])
+    out4 = ta4.propagate_grid(grid3)
+    assert np.all(np.isnan(out4.reshape(-1)[32:]))
+    return out

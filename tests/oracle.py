@@ -378,10 +378,13 @@ class OracleBatch:
     def kernel_info(self):
         return {"tape": "oracle"}
 
+    def check_grid(self, grid, max_delta_t=None):
+        pass
+
     def set_events(self, n_te, dirs, cooldowns, tol):
         self.n_te, self.tol = int(n_te), float(tol)
         self.dirs = np.ascontiguousarray(dirs, dtype=np.int32)
-        self.cooldowns = np.ascontiguousarray(list(cooldowns) + [0.0], dtype=np.float64)
+        self.cd_vals = np.ascontiguousarray(list(cooldowns) + [0.0], dtype=np.float64)
         self.cd = np.zeros((self.n, max(self.n_te, 1), 2))
         self.cd_on = np.zeros((self.n, max(self.n_te, 1)), dtype=np.int32)
 
@@ -411,7 +414,7 @@ class OracleBatch:
         rc = lib.oracle_step_ev_w1(
             _desc_ptr(self.program), C.c_uint32(n), _arr(self.state), _arr(self.pars), _arr(self.t_hi), _arr(self.t_lo),
             _arr(mdt), C.c_double(self.tol), C.c_uint32(self.n_te), self.dirs.ctypes.data_as(C.POINTER(C.c_int32)),
-            _arr(self.cooldowns), _arr(self.cd), self.cd_on.ctypes.data_as(C.POINTER(C.c_int32)), _arr(self._tc),
+            _arr(self.cd_vals), _arr(self.cd), self.cd_on.ctypes.data_as(C.POINTER(C.c_int32)), _arr(self._tc),
             _arr(self.last_h), self.outcome.ctypes.data_as(C.POINTER(C.c_int64)), buf, C.c_uint32(cap), C.byref(n_out),
             C.c_int(self.mode))
         assert rc == 0, rc

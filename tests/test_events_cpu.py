@@ -75,6 +75,10 @@ def test_te_step_end():
     ec.case_te_step_end(make)
 
 
+def test_te_propagate_grid():
+    ec.case_te_propagate_grid(make)
+
+
 @pytest.mark.parametrize("terminal", [False, True])
 def test_single_step_batch_vs_scalar(terminal):
     """:100-260: every batch element agrees with the same system integrated alone (batch of one), event times to 1000 eps

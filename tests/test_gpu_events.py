@@ -72,6 +72,10 @@ def test_te_step_end_gpu():
     ec.case_te_step_end(make)
 
 
+def test_te_propagate_grid_gpu():
+    ec.case_te_propagate_grid(make)
+
+
 @pytest.mark.parametrize("terminal", [False, True])
 def test_single_step_gpu_vs_oracle(terminal):
     """test/batch_event_detection.cpp:100-260 on both: same number of triggers, times to 1000 eps, velocities to 10000
@@ -127,7 +131,6 @@ def test_event_step_parity_vs_oracle(batch, backward):
         assert np.array_equal(g.time, o.time) or np.max(np.abs(g.time - o.time)) < 1e-12
         # Taylor coefficients of the event equations, scaled by h^order.
         tg, to_ = g._b.tc_events(4), o._b.tc_events(4)
-        sc = np.abs(o._b.E_h if hasattr(o._b, "E_h") else 1.0)
         pw = np.arange(g.get_order() + 1)[None, :, None]
         hh = np.maximum(np.abs(h), 1e-300)[None, None, :] ** pw
         assert np.max(np.abs(tg - to_) * np.minimum(hh, 1.0)) < 1e-12
@@ -156,9 +159,9 @@ def test_many_lanes_few_events():
               nt_events=[hb.nt_event_batch(v + 2.0, lambda ta, t, s, i: None)])
     for _ in range(8):
         ta.step()
-    # x crosses zero after a quarter period (~0.5): every lane exactly once in 8 steps of ~0.1-0.2.
-    assert np.all(fired <= 1) and fired.sum() > 0
-    idx = np.nonzero(fired)[0]
+    # x crosses zero after a quarter period (~0.5), then every half period.
+    assert np.all(fired <= 3) and np.all(fired >= 1)
+    idx = np.arange(0, batch, 4099)
     o = oracle.OracleEventIntegrator(sys, st[:, idx[:16]], len(idx[:16]), t_events=[hb.t_event_batch(x, callback=lambda ta, s, i: True)],
                                      nt_events=[hb.nt_event_batch(v + 2.0, lambda ta, t, s, i: None)])
     for _ in range(8):
