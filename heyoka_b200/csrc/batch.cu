@@ -2332,10 +2332,20 @@ struct hy_cout {
     std::uint32_t n = 0, n_eq = 0, order = 0;
     std::uint64_t n_steps = 0; // recorded iterations; times have n_steps + 2 rows (start, ..., padding)
     dev::program prog{};
-    double *d_tcs = nullptr, *d_t_hi = nullptr, *d_t_lo = nullptr, *d_tm = nullptr, *d_out = nullptr;
+    // The Taylor coefficients of the recorded iterations live in slabs of slab_iters iterations each, written in
+    // place by the step kernel (no copy, no final re-pack); d_slabs is the device-side table of the slab pointers.
+    std::vector<double *> slabs;
+    double **d_slabs = nullptr;
+    std::uint32_t slab_iters = 1;
+    cudaStream_t stream = nullptr;
+    double *d_t_hi = nullptr, *d_t_lo = nullptr, *d_tm = nullptr, *d_out = nullptr;
     ~hy_cout()
     {
-        for (double *ptr : {d_tcs, d_t_hi, d_t_lo, d_tm, d_out}) {
+        for (double *ptr : slabs) {
+            cudaFree(ptr);
+        }
+        for (void *ptr : {static_cast<void *>(d_slabs), static_cast<void *>(d_t_hi), static_cast<void *>(d_t_lo),
+                          static_cast<void *>(d_tm), static_cast<void *>(d_out)}) {
             if (ptr != nullptr) {
                 cudaFree(ptr);
             }
@@ -2346,18 +2356,20 @@ struct hy_cout {
 int hy_batch_propagate_until_cout(hy_batch *b, const double *t_final_hi, const double *t_final_lo,
                                   const double *max_delta_t, uint64_t max_steps, hy_cout **out)
 {
-    std::vector<double *> tc_blocks, th_blocks; // one device block per recorded iteration
-    double *d_lane = nullptr;
+    // The recording (hy_cout) owns its device memory from the start: slabs of Taylor coefficients the step kernel
+    // writes into directly, and the times of the iterations in a geometrically grown array.
+    std::unique_ptr<hy_cout> co;
+    double *d_lane = nullptr, *d_times = nullptr, *own_tc = nullptr;
+    std::size_t times_cap = 0, times_rows = 0; // rows of 2 * n doubles (hi, lo)
     unsigned char *d_dir = nullptr;
     unsigned *d_pflags = nullptr;
+    bool tc_swapped = false;
     const auto cleanup = [&]() {
-        for (auto *ptr : tc_blocks) {
-            cudaFree(ptr);
+        if (tc_swapped) {
+            b->d_tc = own_tc;
         }
-        for (auto *ptr : th_blocks) {
-            cudaFree(ptr);
-        }
-        for (void *ptr : {static_cast<void *>(d_lane), static_cast<void *>(d_dir), static_cast<void *>(d_pflags)}) {
+        for (void *ptr : {static_cast<void *>(d_lane), static_cast<void *>(d_dir), static_cast<void *>(d_pflags),
+                          static_cast<void *>(d_times)}) {
             if (ptr != nullptr) {
                 cudaFree(ptr);
             }
@@ -2423,15 +2435,40 @@ int hy_batch_propagate_until_cout(hy_batch *b, const double *t_final_hi, const d
             HY_CUDA_CHECK(cudaMemcpyAsync(hflags, d_pflags, sizeof(hflags), cudaMemcpyDeviceToHost, b->stream));
             HY_CUDA_CHECK(cudaStreamSynchronize(b->stream));
         };
+        co = std::make_unique<hy_cout>();
+        co->device = b->device;
+        co->n = n;
+        co->n_eq = b->n_eq;
+        co->order = b->order;
+        co->prog = b->prog;
+        co->stream = b->stream;
+        // Slabs of about 64 MB (at least one iteration each).
+        co->slab_iters = static_cast<std::uint32_t>(
+            std::min<std::size_t>(std::max<std::size_t>((std::size_t(64) << 20) / (tc_doubles * sizeof(double)), 1u), 4096u));
         // Row 0 of the times: the starting time.
         const auto push_times = [&]() {
-            double *blk = nullptr;
-            HY_CUDA_CHECK(cudaMalloc(&blk, sizeof(double) * 2u * n));
-            th_blocks.push_back(blk);
+            if (times_rows == times_cap) {
+                const std::size_t new_cap = std::max<std::size_t>(2u * times_cap, 64u);
+                double *nt = nullptr;
+                HY_CUDA_CHECK(cudaMalloc(&nt, sizeof(double) * 2u * n * new_cap));
+                if (d_times != nullptr) {
+                    HY_CUDA_CHECK(cudaMemcpyAsync(nt, d_times, sizeof(double) * 2u * n * times_rows, cudaMemcpyDeviceToDevice,
+                                                  b->stream));
+                    HY_CUDA_CHECK(cudaStreamSynchronize(b->stream));
+                    HY_CUDA_CHECK(cudaFree(d_times));
+                }
+                d_times = nt;
+                times_cap = new_cap;
+            }
+            double *blk = d_times + 2u * n * times_rows;
             HY_CUDA_CHECK(cudaMemcpyAsync(blk, b->d_t_hi, sizeof(double) * n, cudaMemcpyDeviceToDevice, b->stream));
             HY_CUDA_CHECK(cudaMemcpyAsync(blk + n, b->d_t_lo, sizeof(double) * n, cudaMemcpyDeviceToDevice, b->stream));
+            ++times_rows;
         };
         push_times();
+        b->ensure_tc();
+        own_tc = b->d_tc;
+        tc_swapped = true;
         HY_CUDA_CHECK(cudaMemsetAsync(d_pflags, 0, sizeof(hflags), b->stream));
         dev::k_prop_init<<<gb, 128, 0, b->stream>>>(b->view(), G, b->d_prop_min_h, b->d_prop_max_h, b->d_prop_n_steps);
         HY_CUDA_CHECK(cudaGetLastError());
@@ -2442,6 +2479,13 @@ int hy_batch_propagate_until_cout(hy_batch *b, const double *t_final_hi, const d
         }
         std::uint64_t iter = 0;
         while (true) {
+            // The step kernel writes the coefficients of this iteration straight into their slot of the recording.
+            if (iter / co->slab_iters == co->slabs.size()) {
+                double *slab = nullptr;
+                HY_CUDA_CHECK(cudaMalloc(&slab, sizeof(double) * tc_doubles * co->slab_iters));
+                co->slabs.push_back(slab);
+            }
+            b->d_tc = co->slabs[iter / co->slab_iters] + (iter % co->slab_iters) * tc_doubles;
             dev::run_args R{};
             R.max_delta_t = G.dt_limit;
             R.default_max_delta_t = std::numeric_limits<double>::infinity();
@@ -2458,14 +2502,7 @@ int hy_batch_propagate_until_cout(hy_batch *b, const double *t_final_hi, const d
                 break; // non-finite state: this iteration is not recorded (:1462-1467)
             }
             // update_c_out(), :1320-1346.
-            {
-                double *blk = nullptr;
-                HY_CUDA_CHECK(cudaMalloc(&blk, sizeof(double) * tc_doubles));
-                tc_blocks.push_back(blk);
-                HY_CUDA_CHECK(cudaMemcpyAsync(blk, b->d_tc, sizeof(double) * tc_doubles, cudaMemcpyDeviceToDevice,
-                                              b->stream));
-                push_times();
-            }
+            push_times();
             ++iter;
             if (hflags[0] == n) {
                 break; // every lane reached its final time
@@ -2476,31 +2513,25 @@ int hy_batch_propagate_until_cout(hy_batch *b, const double *t_final_hi, const d
                 break;
             }
         }
-        if (!tc_blocks.empty()) {
-            // make_c_out(), :1277-1317: contiguous arrays, padding row +-inf by direction.
-            auto co = std::make_unique<hy_cout>();
-            co->device = b->device;
-            co->n = n;
-            co->n_eq = b->n_eq;
-            co->order = b->order;
-            co->n_steps = tc_blocks.size();
-            co->prog = b->prog;
-            const std::size_t rows = tc_blocks.size() + 2u;
-            HY_CUDA_CHECK(cudaMalloc(&co->d_tcs, sizeof(double) * tc_doubles * tc_blocks.size()));
+        // The batch's own tc array ends up with the coefficients of the last step taken, like m_tc in the reference.
+        HY_CUDA_CHECK(cudaMemcpyAsync(own_tc, b->d_tc, sizeof(double) * tc_doubles, cudaMemcpyDeviceToDevice, b->stream));
+        b->d_tc = own_tc;
+        tc_swapped = false;
+        if (iter != 0u) {
+            // make_c_out(), :1277-1317: the times get a padding row, +-inf by direction.
+            co->n_steps = iter;
+            const std::size_t rows = iter + 2u;
             HY_CUDA_CHECK(cudaMalloc(&co->d_t_hi, sizeof(double) * rows * n));
             HY_CUDA_CHECK(cudaMalloc(&co->d_t_lo, sizeof(double) * rows * n));
             HY_CUDA_CHECK(cudaMalloc(&co->d_tm, sizeof(double) * n));
             HY_CUDA_CHECK(cudaMalloc(&co->d_out, sizeof(double) * static_cast<std::size_t>(b->n_eq) * n));
-            for (std::size_t k = 0; k < tc_blocks.size(); ++k) {
-                HY_CUDA_CHECK(cudaMemcpyAsync(co->d_tcs + k * tc_doubles, tc_blocks[k], sizeof(double) * tc_doubles,
-                                              cudaMemcpyDeviceToDevice, b->stream));
-            }
-            for (std::size_t k = 0; k < th_blocks.size(); ++k) {
-                HY_CUDA_CHECK(cudaMemcpyAsync(co->d_t_hi + k * n, th_blocks[k], sizeof(double) * n,
-                                              cudaMemcpyDeviceToDevice, b->stream));
-                HY_CUDA_CHECK(cudaMemcpyAsync(co->d_t_lo + k * n, th_blocks[k] + n, sizeof(double) * n,
-                                              cudaMemcpyDeviceToDevice, b->stream));
-            }
+            HY_CUDA_CHECK(cudaMemcpy2DAsync(co->d_t_hi, sizeof(double) * n, d_times, sizeof(double) * 2u * n,
+                                            sizeof(double) * n, iter + 1u, cudaMemcpyDeviceToDevice, b->stream));
+            HY_CUDA_CHECK(cudaMemcpy2DAsync(co->d_t_lo, sizeof(double) * n, d_times + n, sizeof(double) * 2u * n,
+                                            sizeof(double) * n, iter + 1u, cudaMemcpyDeviceToDevice, b->stream));
+            HY_CUDA_CHECK(cudaMalloc(&co->d_slabs, sizeof(double *) * co->slabs.size()));
+            HY_CUDA_CHECK(cudaMemcpyAsync(co->d_slabs, co->slabs.data(), sizeof(double *) * co->slabs.size(),
+                                          cudaMemcpyHostToDevice, b->stream));
             std::vector<unsigned char> dir(n);
             HY_CUDA_CHECK(cudaMemcpyAsync(dir.data(), d_dir, n, cudaMemcpyDeviceToHost, b->stream));
             HY_CUDA_CHECK(cudaStreamSynchronize(b->stream));
@@ -2535,12 +2566,14 @@ int hy_cout_eval(hy_cout *c, const double *tm, double *out)
             }
         }
         device_guard guard(c->device);
-        HY_CUDA_CHECK(cudaMemcpy(c->d_tm, tm, sizeof(double) * c->n, cudaMemcpyHostToDevice));
-        dev::k_cout_eval<<<(c->n + 127u) / 128u, 128>>>(c->prog, c->n, static_cast<std::uint32_t>(c->n_steps + 2u),
-                                                         c->d_tcs, c->d_t_hi, c->d_t_lo, c->d_tm, c->d_out);
+        HY_CUDA_CHECK(cudaMemcpyAsync(c->d_tm, tm, sizeof(double) * c->n, cudaMemcpyHostToDevice, c->stream));
+        dev::k_cout_eval<<<(c->n + 127u) / 128u, 128, 0, c->stream>>>(
+            c->prog, c->n, static_cast<std::uint32_t>(c->n_steps + 2u), c->d_slabs, c->slab_iters, c->d_t_hi, c->d_t_lo,
+            c->d_tm, c->d_out);
         HY_CUDA_CHECK(cudaGetLastError());
-        HY_CUDA_CHECK(cudaMemcpy(out, c->d_out, sizeof(double) * static_cast<std::size_t>(c->n_eq) * c->n,
-                                 cudaMemcpyDeviceToHost));
+        HY_CUDA_CHECK(cudaMemcpyAsync(out, c->d_out, sizeof(double) * static_cast<std::size_t>(c->n_eq) * c->n,
+                                      cudaMemcpyDeviceToHost, c->stream));
+        HY_CUDA_CHECK(cudaStreamSynchronize(c->stream));
         return HY_OK;
     } catch (...) {
         return translate_exception();

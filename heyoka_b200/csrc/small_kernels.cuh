@@ -220,9 +220,10 @@ __global__ void k_prop_book(batch D, prop_state G, long long *outcome, double *m
 // Evaluation of a continuous output (src/continuous_output.cpp:640-960): per lane, upper_bound of the time in the
 // lane's column of the (padded) times, the Taylor coefficients of the step that contains it, Horner / compensated
 // summation at h = t - start of that step. times: [n_rows][batch] with n_rows = n_steps + 2 (padding included);
-// tcs: [n_steps][n_eq][order + 1][batch].
-__global__ void k_cout_eval(program P, std::uint32_t n, std::uint32_t n_rows, const double *tcs, const double *t_hi,
-                            const double *t_lo, const double *tm, double *out)
+// tcs: [n_steps][n_eq][order + 1][batch], in slabs of slab_iters iterations (slabs[k] = iterations k * slab_iters ...).
+__global__ void k_cout_eval(program P, std::uint32_t n, std::uint32_t n_rows, const double *const *slabs,
+                            std::uint32_t slab_iters, const double *t_hi, const double *t_lo, const double *tm,
+                            double *out)
 {
     const std::uint32_t lane = blockIdx.x * blockDim.x + threadIdx.x;
     if (lane >= n) {
@@ -251,7 +252,8 @@ __global__ void k_cout_eval(program P, std::uint32_t n, std::uint32_t n_rows, co
     tc_idx -= (tc_idx != 0u) ? 1u : 0u;
     tc_idx -= (first == n_rows - 1u) ? 1u : 0u;
     const double h = dfl_sub(t, time_at(tc_idx)).hi;
-    const double *base = tcs + static_cast<std::size_t>(tc_idx) * P.n_eq * (P.order + 1u) * nn + lane;
+    const double *base
+        = slabs[tc_idx / slab_iters] + static_cast<std::size_t>(tc_idx % slab_iters) * P.n_eq * (P.order + 1u) * nn + lane;
     for (std::uint32_t i = 0; i < P.n_eq; ++i) {
         const double *c = base + static_cast<std::size_t>(i) * (P.order + 1u) * nn;
         out[static_cast<std::size_t>(i) * nn + lane]
