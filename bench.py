@@ -42,6 +42,7 @@ def parse_args():
     ap.add_argument("--tfinal", type=float, default=20.0, help="years propagated per bench step")
     ap.add_argument("--perturb", type=float, default=1e-3)
     ap.add_argument("--cpu-lanes", type=int, default=0, help="lanes of the CPU sample (0 = auto)")
+    ap.add_argument("--no-cpp-e2e", action="store_true", help="skip the leg through the drop-in C++ class")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--tape", default="auto", choices=["auto", "hbm", "smem", "smem-notmem", "global", "global-cta", "nbody", "nbody-cta"])
     ap.add_argument("--lanes-per-warp", type=int, default=0)
@@ -250,6 +251,25 @@ def run_reference(args):
     }))
 
 
+def cpp_class_e2e(batch, tfinal, perturb):
+    """The same workload through the drop-in C++ class (tools/bench_cpp_e2e.cpp): host std::vector buffers in and out,
+    the call a heyoka user makes. One line per host_sync mode; None if the tool cannot be built."""
+    exe = os.path.join(ROOT, "build", "bench_cpp_e2e")
+    src = os.path.join(ROOT, "tools", "bench_cpp_e2e.cpp")
+    lib = os.path.join(ROOT, "heyoka_b200", "lib")
+    try:
+        if not os.path.exists(exe) or os.path.getmtime(exe) < max(os.path.getmtime(src), os.path.getmtime(
+                os.path.join(lib, "libheyoka_b200.so"))):
+            os.makedirs(os.path.dirname(exe), exist_ok=True)
+            subprocess.run(["g++", "-std=c++17", "-O2", "-I" + os.path.join(ROOT, "include"), src, "-o", exe, "-L" + lib,
+                            "-lheyoka_b200", "-Wl,-rpath," + lib], check=True, capture_output=True)
+        res = subprocess.run([exe, str(batch), "2", repr(float(tfinal)), repr(float(perturb))], capture_output=True,
+                             text=True, timeout=600, check=True)
+        return [json.loads(line) for line in res.stdout.splitlines() if line.startswith("{")]
+    except Exception as e:  # noqa: BLE001 - a reported extra, never fatal for the bench line
+        return {"error": "%s: %s" % (type(e).__name__, e)}
+
+
 def main():
     args = parse_args()
     if args.impl == "reference":
@@ -455,6 +475,8 @@ def main():
             "gpu_launches": launches_all,
             "clocks": clocks,
         }
+        if world == 1 and not args.no_cpp_e2e:
+            out["e2e_cpp_class"] = cpp_class_e2e(n, args.tfinal, args.perturb)
         if not args.no_cpu_baseline and world == 1:
             cores = host_cores()
             cb = CpuBaseline(P, cores, args.perturb)

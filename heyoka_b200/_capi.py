@@ -92,6 +92,8 @@ SIGNATURES = {
     "hy_program_destroy": (None, [_vp]),
     "hy_batch_create": (C.c_int, [_vp, C.c_uint32, C.c_int, _vpp]),
     "hy_batch_destroy": (None, [_vp]),
+    "hy_host_pin": (C.c_int, [_vp, C.c_size_t]),
+    "hy_host_unpin": (C.c_int, [_vp]),
     "hy_batch_set_stream": (C.c_int, [_vp, _vp]),
     "hy_batch_sync": (C.c_int, [_vp]),
     "hy_batch_upload": (C.c_int, [_vp, _dp, _dp, _dp, _dp]),

@@ -1653,6 +1653,28 @@ void hy_batch_destroy(hy_batch *b)
     delete b;
 }
 
+int hy_host_pin(void *ptr, size_t bytes)
+{
+    if (ptr == nullptr || bytes == 0u) {
+        return HY_OK;
+    }
+    if (cudaHostRegister(ptr, bytes, cudaHostRegisterDefault) != cudaSuccess) {
+        cudaGetLastError(); // (not fatal: the copies then go through the driver's staging buffers)
+        hy::detail::set_last_error("cudaHostRegister() failed");
+        return HY_ERR_CUDA;
+    }
+    return HY_OK;
+}
+
+int hy_host_unpin(void *ptr)
+{
+    if (ptr != nullptr && cudaHostUnregister(ptr) != cudaSuccess) {
+        cudaGetLastError();
+        return HY_ERR_CUDA;
+    }
+    return HY_OK;
+}
+
 int hy_batch_set_stream(hy_batch *b, void *cuda_stream)
 {
     if (b != nullptr && !b->shards.empty()) {

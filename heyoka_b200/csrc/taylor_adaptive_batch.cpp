@@ -112,6 +112,42 @@ struct taylor_adaptive_batch<double>::impl {
     bool tc_valid = false; // the device holds the Taylor coefficients mirrored in `tc`
     std::vector<t_event_batch<double>> tes;
     std::vector<nt_event_batch<double>> ntes;
+    // Host <-> device synchronisation (see host_sync in taylor.hpp). strict: everything is uploaded at the entry of
+    // every call and refreshed at its exit (the reference's raw-pointer contract). lazy: an array is uploaded only
+    // after the user could have written it (non-const getters, setters), and the mirrors are refreshed when a getter
+    // asks for them.
+    bool lazy = false;
+    bool host_new_state = true, host_new_pars = true, host_new_time = true;
+    bool dev_new_state = false, dev_new_time = false, dev_new_tc = false, dev_new_step = false, dev_new_prop = false;
+    // The storage of the mirrors is page-locked in place (hy_host_pin()).
+    std::vector<void *> pinned;
+    void pin(void *ptr, std::size_t bytes)
+    {
+        if (ptr != nullptr && bytes != 0u && std::find(pinned.begin(), pinned.end(), ptr) == pinned.end()
+            && hy_host_pin(ptr, bytes) == HY_OK) {
+            pinned.push_back(ptr);
+        }
+    }
+    void pin_mirrors()
+    {
+        pin(state.data(), state.size() * sizeof(double));
+        pin(pars.data(), pars.size() * sizeof(double));
+        pin(time_hi.data(), time_hi.size() * sizeof(double));
+        pin(time_lo.data(), time_lo.size() * sizeof(double));
+        pin(last_h.data(), last_h.size() * sizeof(double));
+        pin(d_out.data(), d_out.size() * sizeof(double));
+        pin(oc.data(), oc.size() * sizeof(std::int64_t));
+        pin(tmp_a.data(), tmp_a.size() * sizeof(double));
+        pin(tmp_b.data(), tmp_b.size() * sizeof(double));
+        pin(tmp_n.data(), tmp_n.size() * sizeof(std::uint64_t));
+    }
+    void unpin_all()
+    {
+        for (void *p : pinned) {
+            hy_host_unpin(p);
+        }
+        pinned.clear();
+    }
 
     impl() = default;
     impl(const impl &o)
@@ -120,10 +156,11 @@ struct taylor_adaptive_batch<double>::impl {
           tape_mode(o.tape_mode), k_lpw(o.k_lpw), k_lpt(o.k_lpt), k_threads(o.k_threads), k_bpsm(o.k_bpsm),
           state(o.state), pars(o.pars), time_hi(o.time_hi), time_lo(o.time_lo), tc(o.tc), last_h(o.last_h),
           d_out(o.d_out), step_res(o.step_res), prop_res(o.prop_res), oc(o.oc), tmp_a(o.tmp_a), tmp_b(o.tmp_b),
-          tmp_n(o.tmp_n), tc_valid(o.tc_valid), tes(o.tes), ntes(o.ntes)
+          tmp_n(o.tmp_n), tc_valid(o.tc_valid), tes(o.tes), ntes(o.ntes), lazy(o.lazy)
     {
         if (prog) {
             make_batch();
+            pin_mirrors();
             if (o.batch != nullptr && tc_valid) {
                 // The copy can serve update_d_output() right away (src/detail/i_data.cpp:335-352 copies m_tc).
                 check(hy_batch_upload_tc(batch, tc.data()));
@@ -132,6 +169,7 @@ struct taylor_adaptive_batch<double>::impl {
     }
     ~impl()
     {
+        unpin_all();
         hy_batch_destroy(batch);
     }
     void make_batch()
@@ -160,29 +198,119 @@ struct taylor_adaptive_batch<double>::impl {
     }
     void push()
     {
-        check(hy_batch_upload(batch, state.data(), n_pars ? pars.data() : nullptr, time_hi.data(), time_lo.data()));
+        const bool st = !lazy || host_new_state, pr = n_pars != 0u && (!lazy || host_new_pars), tm = !lazy || host_new_time;
+        if (st || pr || tm) {
+            check(hy_batch_upload(batch, st ? state.data() : nullptr, pr ? pars.data() : nullptr,
+                                  tm ? time_hi.data() : nullptr, tm ? time_lo.data() : nullptr));
+        }
+        host_new_state = host_new_pars = host_new_time = false;
     }
+    // The mirrors the user can see, refreshed from the device if it holds something newer.
+    void refresh_state()
+    {
+        if (dev_new_state) {
+            check(hy_batch_download(batch, state.data(), nullptr, nullptr, nullptr));
+            dev_new_state = false;
+        }
+    }
+    void refresh_time()
+    {
+        if (dev_new_time) {
+            check(hy_batch_download(batch, nullptr, time_hi.data(), time_lo.data(), last_h.data()));
+            dev_new_time = false;
+        }
+    }
+    void refresh_tc()
+    {
+        if (dev_new_tc) {
+            pin(tc.data(), tc.size() * sizeof(double));
+            check(hy_batch_download_tc(batch, tc.data()));
+            dev_new_tc = false;
+        }
+    }
+    void refresh_step_res()
+    {
+        if (dev_new_step) {
+            check(hy_batch_download_step_res(batch, oc.data(), tmp_a.data()));
+            for (std::uint32_t i = 0; i < batch_size; ++i) {
+                step_res[i] = std::tuple{static_cast<taylor_outcome>(oc[i]), tmp_a[i]};
+            }
+            dev_new_step = false;
+        }
+    }
+    void refresh_prop_res()
+    {
+        if (dev_new_prop) {
+            check(hy_batch_download_prop_res(batch, oc.data(), tmp_a.data(), tmp_b.data(), tmp_n.data()));
+            for (std::uint32_t i = 0; i < batch_size; ++i) {
+                prop_res[i] = std::tuple{static_cast<taylor_outcome>(oc[i]), tmp_a[i], tmp_b[i],
+                                         static_cast<std::size_t>(tmp_n[i])};
+            }
+            dev_new_prop = false;
+        }
+    }
+    void refresh_all()
+    {
+        refresh_state();
+        refresh_time();
+        refresh_tc();
+        refresh_step_res();
+        refresh_prop_res();
+    }
+    // After a device operation.
     void pull(bool wtc)
     {
-        check(hy_batch_download(batch, state.data(), time_hi.data(), time_lo.data(), last_h.data()));
+        dev_new_state = dev_new_time = true;
         if (wtc) {
-            check(hy_batch_download_tc(batch, tc.data()));
+            dev_new_tc = true;
             tc_valid = true;
+        }
+        if (!lazy) {
+            refresh_state();
+            refresh_time();
+            refresh_tc();
         }
     }
     void pull_step_res()
     {
-        check(hy_batch_download_step_res(batch, oc.data(), tmp_a.data()));
-        for (std::uint32_t i = 0; i < batch_size; ++i) {
-            step_res[i] = std::tuple{static_cast<taylor_outcome>(oc[i]), tmp_a[i]};
+        dev_new_step = true;
+        if (!lazy) {
+            refresh_step_res();
+        }
+    }
+    void pull_prop_res()
+    {
+        dev_new_prop = true;
+        if (!lazy) {
+            refresh_prop_res();
         }
     }
 };
 
+namespace
+{
+
+// The code paths that work on the host mirrors between device calls (callbacks, events, grids) run in strict mode.
+struct strict_scope {
+    bool *flag, was;
+    template <typename Impl>
+    explicit strict_scope(Impl &m) : flag(&m.lazy), was(m.lazy)
+    {
+        m.refresh_all();
+        m.lazy = false;
+    }
+    ~strict_scope()
+    {
+        *flag = was;
+    }
+};
+
+} // namespace
+
 taylor_adaptive_batch<double>::taylor_adaptive_batch() : m_impl(std::make_unique<impl>()) {}
 
 taylor_adaptive_batch<double>::taylor_adaptive_batch(const taylor_adaptive_batch &o)
-    : m_impl(std::make_unique<impl>(*o.m_impl))
+    : m_impl((o.m_impl->refresh_all(), std::make_unique<impl>(*o.m_impl)))
 {
 }
 
@@ -314,6 +442,7 @@ void taylor_adaptive_batch<double>::finalise_ctor(std::vector<std::pair<expressi
     m.tmp_a.assign(n, 0.);
     m.tmp_b.assign(n, 0.);
     m.tmp_n.assign(n, 0);
+    m.pin_mirrors();
 
     // Non-finite initial conditions are rejected (src/taylor_adaptive_batch.cpp:404-423).
     for (const auto x : m.state) {
@@ -364,10 +493,12 @@ const std::vector<std::pair<expression, expression>> &taylor_adaptive_batch<doub
 }
 const std::vector<double> &taylor_adaptive_batch<double>::get_time() const
 {
+    m_impl->refresh_time();
     return m_impl->time_hi;
 }
 const double *taylor_adaptive_batch<double>::get_time_data() const
 {
+    m_impl->refresh_time();
     return m_impl->time_hi.data();
 }
 
@@ -381,16 +512,21 @@ void taylor_adaptive_batch<double>::set_time(const std::vector<double> &t)
                                     + std::to_string(m.batch_size) + ", but the number of specified times is "
                                     + std::to_string(t.size()));
     }
-    m.time_hi = t;
+    m.refresh_time(); // (last_h travels with the times)
+    std::copy(t.begin(), t.end(), m.time_hi.begin());
     std::fill(m.time_lo.begin(), m.time_lo.end(), 0.);
+    m.host_new_time = true;
 }
 void taylor_adaptive_batch<double>::set_time(double t)
 {
+    m_impl->refresh_time();
     std::fill(m_impl->time_hi.begin(), m_impl->time_hi.end(), t);
     std::fill(m_impl->time_lo.begin(), m_impl->time_lo.end(), 0.);
+    m_impl->host_new_time = true;
 }
 std::pair<const std::vector<double> &, const std::vector<double> &> taylor_adaptive_batch<double>::get_dtime() const
 {
+    m_impl->refresh_time();
     return {m_impl->time_hi, m_impl->time_lo};
 }
 void taylor_adaptive_batch<double>::set_dtime(const std::vector<double> &hi, const std::vector<double> &lo)
@@ -408,11 +544,13 @@ void taylor_adaptive_batch<double>::set_dtime(const std::vector<double> &hi, con
                                         "magnitude than the second");
         }
     }
+    m.refresh_time();
     for (std::uint32_t i = 0; i < m.batch_size; ++i) {
         const auto r = eft_dekker(hi[i], lo[i]); // normalise
         m.time_hi[i] = r.hi;
         m.time_lo[i] = r.lo;
     }
+    m.host_new_time = true;
 }
 void taylor_adaptive_batch<double>::set_dtime(double hi, double lo)
 {
@@ -421,14 +559,19 @@ void taylor_adaptive_batch<double>::set_dtime(double hi, double lo)
 
 const std::vector<double> &taylor_adaptive_batch<double>::get_state() const
 {
+    m_impl->refresh_state();
     return m_impl->state;
 }
 const double *taylor_adaptive_batch<double>::get_state_data() const
 {
+    m_impl->refresh_state();
     return m_impl->state.data();
 }
 double *taylor_adaptive_batch<double>::get_state_data()
 {
+    // The caller may write through the pointer: the host copy is the one that counts at the next call.
+    m_impl->refresh_state();
+    m_impl->host_new_state = true;
     return m_impl->state.data();
 }
 const std::vector<double> &taylor_adaptive_batch<double>::get_pars() const
@@ -441,15 +584,29 @@ const double *taylor_adaptive_batch<double>::get_pars_data() const
 }
 double *taylor_adaptive_batch<double>::get_pars_data()
 {
+    m_impl->host_new_pars = true;
     return m_impl->pars.data();
 }
 const std::vector<double> &taylor_adaptive_batch<double>::get_tc() const
 {
+    m_impl->refresh_tc();
     return m_impl->tc;
 }
 const std::vector<double> &taylor_adaptive_batch<double>::get_last_h() const
 {
+    m_impl->refresh_time();
     return m_impl->last_h;
+}
+host_sync taylor_adaptive_batch<double>::get_host_sync() const
+{
+    return m_impl->lazy ? host_sync::lazy : host_sync::strict;
+}
+void taylor_adaptive_batch<double>::set_host_sync(host_sync hs)
+{
+    auto &m = *m_impl;
+    m.refresh_all();
+    m.lazy = hs == host_sync::lazy;
+    // (Coming back to strict mode: everything is uploaded at the next call anyway.)
 }
 const std::vector<double> &taylor_adaptive_batch<double>::get_d_output() const
 {
@@ -457,11 +614,13 @@ const std::vector<double> &taylor_adaptive_batch<double>::get_d_output() const
 }
 const std::vector<std::tuple<taylor_outcome, double>> &taylor_adaptive_batch<double>::get_step_res() const
 {
+    m_impl->refresh_step_res();
     return m_impl->step_res;
 }
 const std::vector<std::tuple<taylor_outcome, double, double, std::size_t>> &
 taylor_adaptive_batch<double>::get_propagate_res() const
 {
+    m_impl->refresh_prop_res();
     return m_impl->prop_res;
 }
 hy_batch *taylor_adaptive_batch<double>::get_device_batch()
@@ -480,10 +639,14 @@ void taylor_adaptive_batch<double>::set_devices(const std::vector<int> &devices)
     if (devices == m.devices && (!devices.empty() || m.batch != nullptr)) {
         return;
     }
+    if (m.batch != nullptr) {
+        m.refresh_all();
+    }
     hy_batch_destroy(m.batch);
     m.batch = nullptr;
     m.devices = devices;
     m.make_batch();
+    m.host_new_state = m.host_new_pars = m.host_new_time = true;
     if (m.tc_valid) {
         check(hy_batch_upload_tc(m.batch, m.tc.data()));
     }
@@ -494,11 +657,15 @@ void taylor_adaptive_batch<double>::set_device(int device)
     if (m.devices.empty() && (device == m.device || device < 0)) {
         return;
     }
+    if (m.batch != nullptr) {
+        m.refresh_all();
+    }
     hy_batch_destroy(m.batch);
     m.batch = nullptr;
     m.devices.clear();
     m.device = device;
     m.make_batch();
+    m.host_new_state = m.host_new_pars = m.host_new_time = true;
     if (m.tc_valid) {
         check(hy_batch_upload_tc(m.batch, m.tc.data()));
     }
@@ -563,11 +730,15 @@ void taylor_adaptive_batch<double>::set_kernel(int tape_mode, std::uint32_t lpw,
 void taylor_adaptive_batch<double>::step_impl(const std::vector<double> *max_delta_ts, bool backward, bool wtc)
 {
     auto &m = *m_impl;
+    const bool ev = with_events();
+    std::optional<strict_scope> strict;
+    if (ev && m.lazy) {
+        strict.emplace(m); // (the callbacks work on the host mirrors)
+    }
     m.push();
     check(hy_batch_step(m.batch, max_delta_ts != nullptr ? max_delta_ts->data() : nullptr, 0, backward ? 1 : 0,
                         wtc ? 1 : 0));
     // With events the Taylor coefficients are written unconditionally (src/taylor_adaptive_batch.cpp:776).
-    const bool ev = with_events();
     m.pull(wtc || ev);
     m.pull_step_res();
     if (ev) {
@@ -769,6 +940,7 @@ taylor_adaptive_batch<double>::propagate_for_vec(const std::vector<double> &delt
                                     + ", but the number of specified time intervals is "
                                     + std::to_string(delta_ts.size()));
     }
+    m.refresh_time();
     std::vector<double> hi(m.batch_size), lo(m.batch_size);
     for (std::uint32_t i = 0; i < m.batch_size; ++i) {
         const auto r = dfl_add(dfl{m.time_hi[i], m.time_lo[i]}, dfl{delta_ts[i], 0.});
@@ -845,6 +1017,7 @@ taylor_adaptive_batch<double>::propagate_grid_impl(const std::vector<double> &gr
 {
     auto &m = *m_impl;
     const auto n = m.batch_size;
+    const strict_scope strict(m);
     if (o.cb) {
         throw not_implemented_error("Callbacks are not supported by propagate_grid() in the B200 batch integrator");
     }
@@ -872,11 +1045,7 @@ taylor_adaptive_batch<double>::propagate_grid_impl(const std::vector<double> &gr
     check(hy_batch_propagate_grid(m.batch, grid.data(), grid.size() / n,
                                   o.max_delta_t.empty() ? nullptr : o.max_delta_t.data(), o.max_steps, retval.data()));
     m.pull(true);
-    check(hy_batch_download_prop_res(m.batch, m.oc.data(), m.tmp_a.data(), m.tmp_b.data(), m.tmp_n.data()));
-    for (std::uint32_t i = 0; i < n; ++i) {
-        m.prop_res[i] = std::tuple{static_cast<taylor_outcome>(m.oc[i]), m.tmp_a[i], m.tmp_b[i],
-                                   static_cast<std::size_t>(m.tmp_n[i])};
-    }
+    m.pull_prop_res();
     return {std::move(o.cb), std::move(retval)};
 }
 
@@ -1033,6 +1202,7 @@ taylor_adaptive_batch<double>::propagate_until_impl(const std::vector<double> &h
     }
 
     // Validation, src/taylor_adaptive_batch.cpp:1212-1273.
+    m.refresh_time();
     for (std::uint32_t i = 0; i < n; ++i) {
         if (!std::isfinite(m.time_hi[i]) || !std::isfinite(m.time_lo[i])) {
             throw std::invalid_argument("Cannot invoke the propagate_until() function of an adaptive Taylor "
@@ -1076,11 +1246,7 @@ taylor_adaptive_batch<double>::propagate_until_impl(const std::vector<double> &h
             ret.emplace(co, n, m.dim);
         }
         m.pull(true);
-        check(hy_batch_download_prop_res(m.batch, m.oc.data(), m.tmp_a.data(), m.tmp_b.data(), m.tmp_n.data()));
-        for (std::uint32_t i = 0; i < n; ++i) {
-            m.prop_res[i] = std::tuple{static_cast<taylor_outcome>(m.oc[i]), m.tmp_a[i], m.tmp_b[i],
-                                       static_cast<std::size_t>(m.tmp_n[i])};
-        }
+        m.pull_prop_res();
         return {std::move(ret), std::move(o.cb)};
     }
 
@@ -1089,14 +1255,11 @@ taylor_adaptive_batch<double>::propagate_until_impl(const std::vector<double> &h
         m.push();
         check(hy_batch_propagate_until(m.batch, hi.data(), lo.data(), mdt, o.max_steps, o.write_tc ? 1 : 0));
         m.pull(o.write_tc);
-        check(hy_batch_download_prop_res(m.batch, m.oc.data(), m.tmp_a.data(), m.tmp_b.data(), m.tmp_n.data()));
-        for (std::uint32_t i = 0; i < n; ++i) {
-            m.prop_res[i] = std::tuple{static_cast<taylor_outcome>(m.oc[i]), m.tmp_a[i], m.tmp_b[i],
-                                       static_cast<std::size_t>(m.tmp_n[i])};
-        }
+        m.pull_prop_res();
         return {std::nullopt, std::move(o.cb)};
     }
 
+    const strict_scope strict(m);
     // Callback / events path: the reference's lock-step loop (src/taylor_adaptive_batch.cpp:1372-1527) on the host, one
     // device step per iteration (host callbacks force a synchronisation per step anyway).
     constexpr auto cb_time_errmsg
@@ -1182,6 +1345,7 @@ const std::vector<double> &taylor_adaptive_batch<double>::update_d_output(const 
                                     + std::to_string(m.batch_size) + ", but the number of time coordinates is "
                                     + std::to_string(t.size()));
     }
+    m.refresh_time();
     std::vector<double> tau(m.batch_size);
     for (std::uint32_t i = 0; i < m.batch_size; ++i) {
         if (rel_time) {

@@ -212,6 +212,12 @@ int hy_batch_create_multi(const hy_program *, uint32_t batch, const int *devices
 uint32_t hy_batch_n_shards(const hy_batch *); /* 0 for a single-device batch */
 int hy_device_count(void);                    /* usable CUDA devices (0 if none) */
 void hy_batch_destroy(hy_batch *);
+/* Page-locks (cudaHostRegister) / releases a host buffer the caller keeps copying from / to: the reference hands out
+ * plain std::vector storage (include/heyoka/taylor.hpp:974-977), the drop-in class pins it in place so that the
+ * uploads / downloads of every call run at full PCIe speed. A failure is not fatal (returns HY_ERR_CUDA). */
+int hy_host_pin(void *ptr, size_t bytes);
+int hy_host_unpin(void *ptr);
+
 /* cudaStream_t on which copies and kernels are enqueued (default: the legacy default stream). */
 int hy_batch_set_stream(hy_batch *, void *cuda_stream);
 int hy_batch_sync(hy_batch *);

@@ -91,6 +91,18 @@ public:
     }
 };
 
+// Host <-> device synchronisation of the integrator's host mirrors (extension; default strict).
+//   strict  the reference's raw-pointer contract (include/heyoka/taylor.hpp:974-977): whatever the user wrote through
+//           get_state_data() / get_pars_data() / references obtained earlier is picked up at the entry of every call,
+//           and every mirror is up to date at its exit: state, parameters and times are uploaded and downloaded on
+//           every step() / propagate_*() (from / to page-locked memory: the storage of the std::vectors is pinned).
+//   lazy    an array is uploaded only after a call that lets the user write it (the non-const get_state_data() /
+//           get_pars_data(), set_time() / set_dtime()) - call the getter again before writing again - and a mirror is
+//           refreshed from the device when a getter asks for it (references obtained BEFORE a step are not refreshed
+//           by the step: call the getter again). Sequences of steps / propagations then move no state over PCIe.
+//           Integrators with events, step callbacks and propagate_grid() always run strict.
+enum class host_sync { strict, lazy };
+
 // ---- events (include/heyoka/events.hpp) ----
 enum class event_direction { negative = -1, any = 0, positive = 1 };
 
@@ -397,6 +409,10 @@ public:
     }
     [[nodiscard]] const std::vector<std::tuple<taylor_outcome, double, double, std::size_t>> &
     get_propagate_res() const;
+
+    // Extension: see host_sync above.
+    [[nodiscard]] host_sync get_host_sync() const;
+    void set_host_sync(host_sync);
 
     // Extensions: the device-resident batch behind this integrator, device placement and kernel selection.
     [[nodiscard]] hy_batch *get_device_batch();
