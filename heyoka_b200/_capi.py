@@ -92,6 +92,7 @@ SIGNATURES = {
     "hy_program_destroy": (None, [_vp]),
     "hy_batch_create": (C.c_int, [_vp, C.c_uint32, C.c_int, _vpp]),
     "hy_batch_destroy": (None, [_vp]),
+    "hy_selftest_div": (C.c_int, [C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64)]),
     "hy_host_pin": (C.c_int, [_vp, C.c_size_t]),
     "hy_host_unpin": (C.c_int, [_vp]),
     "hy_batch_set_stream": (C.c_int, [_vp, _vp]),
@@ -123,6 +124,7 @@ SIGNATURES = {
     "hy_batch_download_tc_events": (C.c_int, [_vp, _dp]),
     "hy_batch_reset_cooldowns": (C.c_int, [_vp, C.c_int64]),
     "hy_batch_get_cooldowns": (C.c_int, [_vp, C.POINTER(C.c_uint8), _dp, _dp]),
+    "hy_batch_set_cooldowns": (C.c_int, [_vp, C.POINTER(C.c_uint8), _dp, _dp]),
     "hy_batch_launch_count": (C.c_int, [_vp, C.POINTER(C.c_uint64)]),
     "hy_batch_set_launch_config": (C.c_int, [_vp, C.c_uint32, C.c_uint32]),
     "hy_batch_set_kernel": (C.c_int, [_vp, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]),

@@ -1653,6 +1653,27 @@ void hy_batch_destroy(hy_batch *b)
     delete b;
 }
 
+int hy_selftest_div(uint64_t n, uint64_t seed, uint64_t *mismatches)
+{
+    try {
+        if (mismatches == nullptr) {
+            throw std::invalid_argument("Null pointer passed to hy_selftest_div()");
+        }
+        unsigned long long *d = nullptr;
+        HY_CUDA_CHECK(cudaMalloc(&d, sizeof(unsigned long long)));
+        HY_CUDA_CHECK(cudaMemset(d, 0, sizeof(unsigned long long)));
+        dev::k_selftest_div<<<148 * 8, 256>>>(n, seed, d);
+        HY_CUDA_CHECK(cudaGetLastError());
+        unsigned long long h = 0;
+        HY_CUDA_CHECK(cudaMemcpy(&h, d, sizeof(h), cudaMemcpyDeviceToHost));
+        HY_CUDA_CHECK(cudaFree(d));
+        *mismatches = h;
+        return HY_OK;
+    } catch (...) {
+        return translate_exception();
+    }
+}
+
 int hy_host_pin(void *ptr, size_t bytes)
 {
     if (ptr == nullptr || bytes == 0u) {
@@ -2760,6 +2781,35 @@ int hy_batch_get_cooldowns(hy_batch *b, uint8_t *active, double *spent, double *
                 spent[static_cast<std::size_t>(k) * b->n + l] = cd[(static_cast<std::size_t>(k) * 2u) * b->n + l];
                 cooldown[static_cast<std::size_t>(k) * b->n + l] = cd[(static_cast<std::size_t>(k) * 2u + 1u) * b->n + l];
             }
+        }
+        return HY_OK;
+    } catch (...) {
+        return translate_exception();
+    }
+}
+
+int hy_batch_set_cooldowns(hy_batch *b, const uint8_t *active, const double *spent, const double *cooldown)
+{
+    try {
+        if (b == nullptr || !b->ev_set) {
+            throw std::invalid_argument("No events are defined for this integrator");
+        }
+        device_guard guard(b->device);
+        const std::size_t m = static_cast<std::size_t>(b->n_te) * b->n;
+        if (m != 0u) {
+            if (active == nullptr || spent == nullptr || cooldown == nullptr) {
+                throw std::invalid_argument("Null pointer passed to hy_batch_set_cooldowns()");
+            }
+            std::vector<double> cd(2u * m);
+            for (std::uint32_t k = 0; k < b->n_te; ++k) {
+                for (std::uint32_t l = 0; l < b->n; ++l) {
+                    cd[(static_cast<std::size_t>(k) * 2u) * b->n + l] = spent[static_cast<std::size_t>(k) * b->n + l];
+                    cd[(static_cast<std::size_t>(k) * 2u + 1u) * b->n + l] = cooldown[static_cast<std::size_t>(k) * b->n + l];
+                }
+            }
+            HY_CUDA_CHECK(cudaMemcpyAsync(b->eva.cd_on, active, m, cudaMemcpyHostToDevice, b->stream));
+            HY_CUDA_CHECK(cudaMemcpyAsync(b->eva.cd, cd.data(), sizeof(double) * 2u * m, cudaMemcpyHostToDevice, b->stream));
+            HY_CUDA_CHECK(cudaStreamSynchronize(b->stream));
         }
         return HY_OK;
     } catch (...) {

@@ -3,6 +3,7 @@
 #define HEYOKA_B200_CSRC_SMALL_KERNELS_CUH
 
 #include "kernels.cuh"
+#include "nb_core.hpp"
 
 namespace heyoka_b200::dev
 {
@@ -258,6 +259,36 @@ __global__ void k_cout_eval(program P, std::uint32_t n, std::uint32_t n_rows, co
         const double *c = base + static_cast<std::size_t>(i) * (P.order + 1u) * nn;
         out[static_cast<std::size_t>(i) * nn + lane]
             = eval_poly(P, [c, nn](std::uint32_t o) { return c[static_cast<std::size_t>(o) * nn]; }, h);
+    }
+}
+
+// Self-test of the lean correctly-rounded division of the N-body kernel (nb::div_rn, nb_core.hpp) against the
+// compiler's IEEE division: n pseudo-random pairs (splitmix64), three quarters with exponents within 2^+-300 (the
+// fast path), one quarter over the whole range incl. zeros, denormals and infinities (the out-of-line division).
+__global__ void k_selftest_div(unsigned long long n, unsigned long long seed, unsigned long long *mismatches)
+{
+    const auto mix = [](unsigned long long z) {
+        z += 0x9e3779b97f4a7c15ull;
+        z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+        z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+        return z ^ (z >> 31);
+    };
+    unsigned long long bad = 0;
+    for (unsigned long long i = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+         i += static_cast<unsigned long long>(gridDim.x) * blockDim.x) {
+        const unsigned long long r0 = mix(seed + 3ull * i), r1 = mix(seed + 3ull * i + 1ull), r2 = mix(seed + 3ull * i + 2ull);
+        const auto make = [&](unsigned long long r, unsigned long long e) {
+            const bool wide = (r2 & 3ull) == 0ull;
+            const unsigned long long ex = wide ? (e % 2047ull) : (1023ull - 300ull + e % 601ull);
+            return __longlong_as_double(static_cast<long long>((r & 0x800fffffffffffffull) | (ex << 52)));
+        };
+        const double a = make(r0, r2 >> 8), b = make(r1, r2 >> 24);
+        const double q0 = nb::div_rn(a, b), q1 = __ddiv_rn(a, b);
+        const bool same = __double_as_longlong(q0) == __double_as_longlong(q1) || (isnan(q0) && isnan(q1));
+        bad += same ? 0ull : 1ull;
+    }
+    if (bad != 0ull) {
+        atomicAdd(mismatches, bad);
     }
 }
 

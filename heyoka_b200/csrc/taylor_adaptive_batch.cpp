@@ -165,12 +165,27 @@ struct taylor_adaptive_batch<double>::impl {
                 // The copy can serve update_d_output() right away (src/detail/i_data.cpp:335-352 copies m_tc).
                 check(hy_batch_upload_tc(batch, tc.data()));
             }
+            if (o.batch != nullptr) {
+                copy_cooldowns(o.batch, batch);
+            }
         }
     }
     ~impl()
     {
         unpin_all();
         hy_batch_destroy(batch);
+    }
+    // The cooldowns of the terminal events travel with copies and device changes (src/detail/event_detection.cpp:1622-1645).
+    void copy_cooldowns(hy_batch *from, hy_batch *to) const
+    {
+        if (tes.empty()) {
+            return;
+        }
+        const std::size_t m = tes.size() * batch_size;
+        std::vector<std::uint8_t> act(m);
+        std::vector<double> spent(m), cd(m);
+        check(hy_batch_get_cooldowns(from, act.data(), spent.data(), cd.data()));
+        check(hy_batch_set_cooldowns(to, act.data(), spent.data(), cd.data()));
     }
     void make_batch()
     {
@@ -642,10 +657,14 @@ void taylor_adaptive_batch<double>::set_devices(const std::vector<int> &devices)
     if (m.batch != nullptr) {
         m.refresh_all();
     }
-    hy_batch_destroy(m.batch);
+    hy_batch *old = m.batch;
     m.batch = nullptr;
     m.devices = devices;
     m.make_batch();
+    if (old != nullptr) {
+        m.copy_cooldowns(old, m.batch);
+    }
+    hy_batch_destroy(old);
     m.host_new_state = m.host_new_pars = m.host_new_time = true;
     if (m.tc_valid) {
         check(hy_batch_upload_tc(m.batch, m.tc.data()));
@@ -660,11 +679,15 @@ void taylor_adaptive_batch<double>::set_device(int device)
     if (m.batch != nullptr) {
         m.refresh_all();
     }
-    hy_batch_destroy(m.batch);
+    hy_batch *old = m.batch;
     m.batch = nullptr;
     m.devices.clear();
     m.device = device;
     m.make_batch();
+    if (old != nullptr) {
+        m.copy_cooldowns(old, m.batch);
+    }
+    hy_batch_destroy(old);
     m.host_new_state = m.host_new_pars = m.host_new_time = true;
     if (m.tc_valid) {
         check(hy_batch_upload_tc(m.batch, m.tc.data()));

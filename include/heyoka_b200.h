@@ -212,6 +212,10 @@ int hy_batch_create_multi(const hy_program *, uint32_t batch, const int *devices
 uint32_t hy_batch_n_shards(const hy_batch *); /* 0 for a single-device batch */
 int hy_device_count(void);                    /* usable CUDA devices (0 if none) */
 void hy_batch_destroy(hy_batch *);
+/* Diagnostics: compares the lean correctly-rounded division used inside the N-body kernel with the compiler's IEEE
+ * division on n pseudo-random pairs; *mismatches must come back 0 (tests/test_gpu_parity.py). */
+int hy_selftest_div(uint64_t n, uint64_t seed, uint64_t *mismatches);
+
 /* Page-locks (cudaHostRegister) / releases a host buffer the caller keeps copying from / to: the reference hands out
  * plain std::vector storage (include/heyoka/taylor.hpp:974-977), the drop-in class pins it in place so that the
  * uploads / downloads of every call run at full PCIe speed. A failure is not fatal (returns HY_ERR_CUDA). */
@@ -324,6 +328,9 @@ int hy_batch_download_tc_events(hy_batch *, double *out);
 int hy_batch_reset_cooldowns(hy_batch *, int64_t lane);
 /* Cooldown state [n_te][batch]: active flag, time spent in cooldown, cooldown (host arrays). */
 int hy_batch_get_cooldowns(hy_batch *, uint8_t *active, double *spent, double *cooldown);
+/* Restores a cooldown state (copies of an integrator carry the cooldowns of the original: the reference copies
+ * m_te_cooldowns, src/detail/event_detection.cpp:1622-1645). */
+int hy_batch_set_cooldowns(hy_batch *, const uint8_t *active, const double *spent, const double *cooldown);
 
 /* Kernel launch statistics since creation (bench.py's gpu_launches). */
 int hy_batch_launch_count(const hy_batch *, uint64_t *n_launches);

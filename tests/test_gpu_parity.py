@@ -602,3 +602,13 @@ def test_two_body_kepler_conservation_gpu(kernel):
             assert approximately(one[i].step_res[0][1], ta.step_res[i][1], 1e4)
             assert approximately(one[i].state[:, 0], ta.state[:, i], 1e5)
         check_kepler_conservation(ta.state, kep, approximately)
+
+
+@pytest.mark.gpu
+def test_lean_division_is_ieee():
+    """The N-body kernel's own correctly-rounded division (nb_core.hpp div_rn: reciprocal seed + Newton + Markstein)
+    returns the bits of the IEEE division on 2^30 pseudo-random pairs (fast path and out-of-line path)."""
+    import ctypes as C
+    bad = C.c_uint64(123)
+    hb.check(hb.lib.hy_selftest_div(1 << 30, 20260924, C.byref(bad)))
+    assert bad.value == 0

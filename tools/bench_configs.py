@@ -60,6 +60,8 @@ def run(name, P, st, t_final=None, **kernel):
 
 def main():
     which = sys.argv[1:] or ["tb", "n32", "nn", "s6step"]
+    if "tbsmall" in which:
+        run("two_body_step_batch 2^22 lanes, one step", hb.Program(sys_two_body()), two_body_batch_state(1 << 22))
     if "tb" in which:
         run("two_body_step_batch 2^24 lanes, one step", hb.Program(sys_two_body()), two_body_batch_state(1 << 24))
     if "s6step" in which:
