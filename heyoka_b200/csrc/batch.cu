@@ -2069,6 +2069,35 @@ int hy_batch_step(hy_batch *b, const double *max_delta_t, int on_device, int bac
     }
 }
 
+namespace
+{
+
+// The checks of propagate_until_impl() that need the CURRENT times (src/taylor_adaptive_batch.cpp:1212-1273): finite,
+// and final time - current time representable. 16 bytes per lane come back from the device for them.
+void check_prop_times(hy_batch *b, const double *tf_hi, const double *tf_lo)
+{
+    std::vector<double> t_hi(b->n), t_lo(b->n);
+    if (hy_batch_download(b, nullptr, t_hi.data(), t_lo.data(), nullptr) != HY_OK) {
+        throw cuda_error(hy_last_error());
+    }
+    for (std::uint32_t i = 0; i < b->n; ++i) {
+        if (!std::isfinite(t_hi[i]) || !std::isfinite(t_lo[i])) {
+            throw std::invalid_argument("Cannot invoke the propagate_until() function of an adaptive Taylor integrator "
+                                        "in batch mode if one of the current times is not finite");
+        }
+    }
+    for (std::uint32_t i = 0; i < b->n; ++i) {
+        // (Same arithmetic as the device: Knuth two-sum of the high parts is enough to detect the overflow.)
+        const double rem = tf_hi[i] - t_hi[i] + ((tf_lo != nullptr ? tf_lo[i] : 0.) - t_lo[i]);
+        if (!std::isfinite(rem)) {
+            throw std::invalid_argument("The final time passed to the propagate_until() function of an adaptive Taylor "
+                                        "integrator in batch mode results in an overflow condition");
+        }
+    }
+}
+
+} // namespace
+
 int hy_batch_propagate_until(hy_batch *b, const double *t_final_hi, const double *t_final_lo, const double *max_delta_t,
                              uint64_t max_steps, int write_tc)
 {
@@ -2098,6 +2127,7 @@ int hy_batch_propagate_until(hy_batch *b, const double *t_final_hi, const double
                 }
             }
         }
+        check_prop_times(b, t_final_hi, t_final_lo);
         if (!b->shards.empty()) {
             return multi_propagate(b, t_final_hi, t_final_lo, max_delta_t, max_steps, write_tc);
         }
