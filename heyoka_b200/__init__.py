@@ -338,7 +338,7 @@ class Batch:
         # storage of the private rows: 0 automatic, 1 tensor memory, 2 shared memory only.
         # "nn": the dense-network kernel (right-hand sides that are feed-forward networks).
         mode = {"auto": 0, "hbm": 1, "smem": 2, "smem-notmem": 3, "global": 4, "global-cta": 5, "nbody": 6,
-                "nbody-cta": 7, "nn": 8}[tape]
+                "nbody-cta": 7, "nn": 8, "nbody-lane": 9}[tape]
         check(lib.hy_batch_set_kernel(self._h, mode, int(lanes_per_warp), int(lanes_per_thread), int(block_threads),
                                       int(blocks_per_sm)))
 
@@ -346,7 +346,7 @@ class Batch:
         ki = _capi.hy_kernel_info()
         check(lib.hy_batch_get_kernel(self._h, C.byref(ki)))
         d = {f[0]: getattr(ki, f[0]) for f in ki._fields_}
-        d["tape"] = {1: "hbm", 2: "smem", 4: "global", 5: "global-cta", 6: "nbody", 7: "nbody-cta", 8: "nn"}.get(ki.tape_mode, "?")
+        d["tape"] = {1: "hbm", 2: "smem", 4: "global", 5: "global-cta", 6: "nbody", 7: "nbody-cta", 8: "nn", 9: "nbody-lane"}.get(ki.tape_mode, "?")
         return d
 
     def sync(self):

@@ -20,7 +20,7 @@ LIB = os.path.join(LIBDIR, "libheyoka_b200.so")
 
 HOST_SOURCES = ["expression.cpp", "decompose.cpp", "model.cpp", "lower.cpp", "smem_plan.cpp", "nb_plan.cpp", "nn_plan.cpp",
                 "capi_host.cpp", "taylor_adaptive_batch.cpp"]
-CUDA_SOURCES = ["batch.cu", "nn_inst.cu"]
+CUDA_SOURCES = ["batch.cu", "nn_inst.cu", "nb1_inst.cu"]
 # The cooperative kernel is instantiated per (lanes per thread, max threads per CTA, mode) family, one
 # object each (built in parallel).
 COOP_FAMILIES = ([(n, m, g) for n in (1, 2, 4) for m in (512, 256) for g in (1, 0)]
@@ -88,7 +88,7 @@ def build(force=False, verbose=True):
         jobs.append((obj, nb_inst, cmd))
     objs = [j[0] for j in jobs]
     # Headers each kind of object depends on (a change in the N-body kernel does not rebuild the cooperative families).
-    nb_only = {"nb_kernel.cuh", "nb_core.hpp", "nb_desc.hpp", "nb_plan.hpp", "nb_variants.hpp", "nn_kernel.cuh", "nn_plan.hpp",
+    nb_only = {"nb_kernel.cuh", "nb1_kernel.cuh", "nb_core.hpp", "nb_desc.hpp", "nb_plan.hpp", "nb_variants.hpp", "nn_kernel.cuh", "nn_plan.hpp",
                "nn_variants.hpp"}
     host_only = {"smem_plan.hpp", "capi_common.hpp", "program.hpp"}
 

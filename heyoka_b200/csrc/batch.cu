@@ -99,15 +99,16 @@ const coop_variant *find_variant(int L, int N, int maxt, int mode)
 }
 
 // The N-body kernel's instantiations (nb_variants.hpp).
-const hy::detail::nb_variant *find_nb_variant(int LT, bool cta, bool tmem, int maxt)
+const hy::detail::nb_variant *find_nb_variant(int LT, bool cta, bool tmem, int maxt, bool lane = false)
 {
     const hy::detail::nb_family fams[] = {hy::detail::nb_family_lt1_cta0(),  hy::detail::nb_family_lt2_cta0(),
                                           hy::detail::nb_family_lt4_cta0(),  hy::detail::nb_family_lt8_cta0(),
                                           hy::detail::nb_family_lt16_cta0(), hy::detail::nb_family_lt32_cta0(),
-                                          hy::detail::nb_family_lt1_cta1()};
+                                          hy::detail::nb_family_lt1_cta1(),  hy::detail::nb_family_lane()};
     for (const auto &f : fams) {
         for (std::size_t i = 0; i < f.n; ++i) {
-            if (f.v[i].LT == LT && f.v[i].cta == cta && f.v[i].tmem == tmem && f.v[i].maxt == maxt) {
+            if (f.v[i].LT == LT && f.v[i].cta == cta && f.v[i].tmem == tmem && f.v[i].maxt == maxt
+                && f.v[i].lane == lane) {
                 return f.v + i;
             }
         }
@@ -237,7 +238,9 @@ struct hy_batch {
     coop_variant nb_cv{}; // (L, N, maxt, mode 6) of the selected N-body instantiation, for the code that reads cv->L
     bool nb_on = false;
     int opt_nb = -1; // -1 automatic, 0 never (HEYOKA_B200_NB=0), 1 preferred
-    bool setup_nb(int LT, std::uint32_t threads, int want_tmem, int want_cta);
+    bool setup_nb(int LT, std::uint32_t threads, int want_tmem, int want_cta, int want_lane = 0);
+    int opt_nb_lane = -1; // one thread per lane for single-pair systems: -1 automatic, 0 never (HEYOKA_B200_NB_LANE=0)
+    bool nb_lane = false;
     // The dense-network kernel (nn_kernel.cuh): plan, padded weight image, device plan.
     hy::detail::nn_plan nnp;
     double *d_nn_wimg = nullptr;
@@ -691,10 +694,59 @@ void hy_batch::setup_coop_global(int L, int N, std::uint32_t threads, int cta)
     c_cta = cta != 0;
 }
 
+// The table of the one-thread-per-lane N-body kernel (nb1_kernel.cuh) for a plan with ONE pair interaction whose six
+// positions each belong to a velocity driven by a single pair output of the same coordinate, or by a number. Returns
+// false for anything else (such plans run on k_nb with 32 lanes per warp).
+static bool make_nb1_tab(const hy::detail::nb_plan &pl, std::uint32_t n_eq, dev::nb1_tab &tab)
+{
+    if (!pl.ok || pl.pairs.size() != 1u || pl.sums.size() != 6u || pl.level_offsets.size() != 2u || n_eq != 12u) {
+        return false;
+    }
+    const auto &pr = pl.pairs[0];
+    bool seen[12] = {};
+    for (std::uint32_t s = 0; s < 6u; ++s) {
+        const std::uint32_t k = s % 3u, ps = s < 3u ? pr.pa[k] : pr.pb[k];
+        const hy::detail::nb_sum_desc *sd = nullptr;
+        for (const auto &cand : pl.sums) {
+            if (cand.kind != 0u && cand.pos == ps + 1u) {
+                if (sd != nullptr) {
+                    return false;
+                }
+                sd = &cand;
+            }
+        }
+        if (sd == nullptr || (sd->out >> 16) == 0u || ps >= pl.pos_sv.size()) {
+            return false;
+        }
+        tab.v_sv[s] = sd->out & 0xffffu;
+        tab.x_sv[s] = (sd->out >> 16) - 1u;
+        if (tab.x_sv[s] != pl.pos_sv[ps] || tab.v_sv[s] >= 12u || tab.x_sv[s] >= 12u || seen[tab.v_sv[s]]
+            || seen[tab.x_sv[s]]) {
+            return false;
+        }
+        seen[tab.v_sv[s]] = seen[tab.x_sv[s]] = true;
+        tab.cval[s] = 0.;
+        if (sd->kind == 2u) {
+            if (sd->cidx >= pl.consts.size()) {
+                return false;
+            }
+            tab.kind[s] = 2u;
+            tab.cval[s] = pl.consts[sd->cidx];
+        } else if (sd->kind == 1u && sd->n_terms == 1u && sd->terms[0] == pr.om[k]) {
+            tab.kind[s] = 0u;
+        } else if (sd->kind == 1u && sd->n_terms == 1u && pr.on[k] != 0xffffu && sd->terms[0] == pr.on[k]) {
+            tab.kind[s] = 1u;
+        } else {
+            return false;
+        }
+    }
+    return true;
+}
+
 // The dedicated N-body kernel. LT = lanes per team (0: as many as give every thread of a warp one pair interaction),
 // threads = CTA size (0: as many warps as fit; HEYOKA_B200_NB_THREADS caps it), want_tmem / want_cta: -1 automatic.
 // Returns false if the program does not qualify or nothing fits.
-bool hy_batch::setup_nb(int LT, std::uint32_t threads, int want_tmem, int want_cta)
+bool hy_batch::setup_nb(int LT, std::uint32_t threads, int want_tmem, int want_cta, int want_lane)
 {
     if (!nbp.ok) {
         return false;
@@ -720,14 +772,23 @@ bool hy_batch::setup_nb(int LT, std::uint32_t threads, int want_tmem, int want_c
     if (!cta && (LT < 1 || LT > 32 || (LT & (LT - 1)) != 0 || static_cast<std::uint32_t>(LT) * n_pairs > 32u)) {
         return false;
     }
+    // One pair interaction, 32 lanes per warp: one thread per lane, nothing exchanged (nb1_kernel.cuh).
+    dev::nb1_tab l1{};
+    const bool lane = want_lane != 0 && !cta && LT == 32 && make_nb1_tab(nbp, n_eq, l1);
+    if (want_lane > 0 && !lane) {
+        return false;
+    }
     const std::uint32_t TT = cta ? 512u : 32u, NL = LT >= 2 ? 2u : 1u;
     // The role records address the outputs in 16-bit units of 16 bytes.
     if (static_cast<std::uint64_t>(nbp.n_out) * LT >= 0xffffu || static_cast<std::uint64_t>(nbp.n_pos) * LT >= 0xffffu) {
         return false;
     }
-    const auto roles = hy::detail::make_nb_roles(nbp, TT, static_cast<std::uint32_t>(LT), NL);
+    auto roles = hy::detail::make_nb_roles(nbp, TT, static_cast<std::uint32_t>(LT), NL);
     if (roles.n_rounds > 32u) {
         return false;
+    }
+    if (lane) {
+        roles = hy::detail::nb_roles{};
     }
     const auto shared_doubles = [&](bool roles_in_smem) {
         std::size_t d = static_cast<std::size_t>(order + 1u) * nbp.fac_stride + ((order + 5u) & ~1u)
@@ -738,7 +799,8 @@ bool hy_batch::setup_nb(int LT, std::uint32_t threads, int want_tmem, int want_c
         return d;
     };
     const auto team_slots = [&](bool tmem) {
-        const std::size_t d = (static_cast<std::size_t>(nbp.n_pos) + nbp.n_out) * LT * 2u
+        // (The one-thread-per-lane kernel keeps positions, pair outputs and norms in registers.)
+        const std::size_t d = (lane ? 0u : (static_cast<std::size_t>(nbp.n_pos) + nbp.n_out) * LT * 2u)
                               + static_cast<std::size_t>(tmem ? 2u : 5u) * npp * TT * 2u + (3u + 16u) * LT; // (+ norms, parked bookkeeping)
         return static_cast<std::uint32_t>((d + LT - 1u) / LT);
     };
@@ -808,7 +870,7 @@ bool hy_batch::setup_nb(int LT, std::uint32_t threads, int want_tmem, int want_c
     const hy::detail::nb_variant *v = nullptr;
     for (const int mt : {256, 384, 512}) {
         if (mt >= pref_maxt && v == nullptr) {
-            v = find_nb_variant(LT, cta, pick.tmem, mt);
+            v = find_nb_variant(LT, cta, pick.tmem, mt, lane);
         }
     }
     if (v == nullptr) {
@@ -843,6 +905,8 @@ bool hy_batch::setup_nb(int LT, std::uint32_t threads, int want_tmem, int want_c
     nbd.roles_in_smem = pick.roles_in_smem ? 1u : 0u;
     nbd.shared_doubles = static_cast<std::uint32_t>(shared_doubles(pick.roles_in_smem));
     nbd.n_slots_equiv = team_slots(pick.tmem);
+    nbd.l1 = l1;
+    nb_lane = lane;
     const std::size_t team_bytes = coop_warp_bytes(nbd.n_slots_equiv, LT);
     nbd.team_doubles = static_cast<std::uint32_t>(team_bytes / sizeof(double));
     const std::uint32_t teams = cta ? 1u : threads / 32u;
@@ -959,6 +1023,7 @@ void hy_batch::configure(int want_mode, int L, int N, std::uint32_t threads, std
     c_global = false;
     c_cta = false;
     nb_on = false;
+    nb_lane = false;
     nn_on = false;
     // Mode 8: the dense-network kernel (right-hand sides that are feed-forward networks, nn_plan.hpp); the automatic
     // mode takes it whenever the program qualifies.
@@ -973,8 +1038,12 @@ void hy_batch::configure(int want_mode, int L, int N, std::uint32_t threads, std
     }
     // Mode 6 / 7: the N-body kernel with warp / CTA teams (N: 0 automatic, 1 tensor memory, 2 shared memory only).
     // Automatic mode takes it whenever the program qualifies (nb_plan.hpp).
-    if (want_mode == 6 || want_mode == 7 || (want_mode == 0 && opt_nb != 0)) {
-        if (setup_nb(L, threads, N == 0 ? -1 : (N == 1 ? 1 : 0), want_mode == 0 ? -1 : (want_mode == 7 ? 1 : 0))) {
+    if (want_mode == 6 || want_mode == 7 || want_mode == 9 || (want_mode == 0 && opt_nb != 0)) {
+        // Mode 9: one thread per lane (systems with one pair interaction); the automatic mode takes it when it applies,
+        // an explicit mode 6 never does (it selects k_nb with the given team shape).
+        const int want_lane = want_mode == 9 ? 1 : (want_mode == 0 ? (opt_nb_lane != 0 ? -1 : 0) : 0);
+        if (setup_nb(want_mode == 9 ? 32 : L, threads, N == 0 ? -1 : (N == 1 ? 1 : 0),
+                     want_mode == 0 ? -1 : (want_mode == 7 ? 1 : 0), want_lane)) {
             return;
         }
         if (want_mode != 0) {
@@ -1522,6 +1591,9 @@ int hy_batch_create(const hy_program *p, uint32_t batch, int device, hy_batch **
         if (const char *env = std::getenv("HEYOKA_B200_NB")) {
             b->opt_nb = std::string{env} != "0" ? 1 : 0;
         }
+        if (const char *env = std::getenv("HEYOKA_B200_NB_LANE")) {
+            b->opt_nb_lane = std::string{env} != "0" ? 1 : 0;
+        }
         if (const char *env = std::getenv("HEYOKA_B200_NB_THREADS")) {
             b->opt_nb_threads = static_cast<std::uint32_t>(std::atoi(env));
         }
@@ -1743,7 +1815,7 @@ int hy_batch_set_launch_config(hy_batch *b, uint32_t block_threads, uint32_t blo
         if (b->nn_on) {
             b->configure(8, 0, 0, 0, 0);
         } else if (b->nb_on) {
-            b->configure(b->c_cta ? 7 : 6, L, b->nbv->tmem ? 1 : 2, block_threads, blocks_per_sm);
+            b->configure(b->nb_lane ? 9 : (b->c_cta ? 7 : 6), L, b->nbv->tmem ? 1 : 2, block_threads, blocks_per_sm);
         } else {
             b->configure(b->mode, L, N, block_threads, blocks_per_sm);
         }
@@ -1760,7 +1832,7 @@ int hy_batch_set_kernel(hy_batch *b, int tape_mode, uint32_t lanes_per_warp, uin
         if (b == nullptr) {
             throw std::invalid_argument("Null batch");
         }
-        if (tape_mode < 0 || tape_mode > 8) {
+        if (tape_mode < 0 || tape_mode > 9) {
             throw std::invalid_argument("Invalid tape mode");
         }
         if (!b->shards.empty()) {
@@ -1791,7 +1863,7 @@ int hy_batch_get_kernel(const hy_batch *b, hy_kernel_info *out)
     if (!b->shards.empty()) {
         return hy_batch_get_kernel(b->shards[0], out); // (every shard runs the same kernel shape)
     }
-    out->tape_mode = b->nn_on ? 8 : b->nb_on ? (b->c_cta ? 7 : 6) : (b->mode == 2 && b->c_global ? (b->c_cta ? 5 : 4) : b->mode);
+    out->tape_mode = b->nn_on ? 8 : b->nb_on ? (b->nb_lane ? 9 : (b->c_cta ? 7 : 6)) : (b->mode == 2 && b->c_global ? (b->c_cta ? 5 : 4) : b->mode);
     out->lanes_per_warp = b->mode == 2 ? static_cast<uint32_t>(b->cv->L) : 32u;
     out->lanes_per_thread = b->mode == 2 ? static_cast<uint32_t>(b->cv->N) : 1u;
     out->block_threads = b->mode == 2 ? b->c_threads : b->h_threads;

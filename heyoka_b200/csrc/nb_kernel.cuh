@@ -36,6 +36,14 @@
 namespace heyoka_b200::dev
 {
 
+// Systems with ONE pair interaction run one thread per lane (k_nb1, nb1_kernel.cuh). Slot s = 3 * side + k: side 0 /
+// 1 = the body whose positions are the pair's pa / pb, k = coordinate. The acceleration of the slot's velocity v_sv
+// (whose position child is x_sv) is the pair output m_k (kind 0), n_k (kind 1) or the number cval (kind 2).
+struct nb1_tab {
+    std::uint32_t v_sv[6], x_sv[6], kind[6];
+    double cval[6];
+};
+
 // Device-side view of an nb_plan (arrays in global memory) + the shared-memory layout chosen by the host.
 struct nb_dev_plan {
     const detail::nb_pair_desc *pairs;
@@ -49,6 +57,7 @@ struct nb_dev_plan {
     std::uint32_t shared_doubles; // CTA-shared tables: fac | rcp | consts | roles
     std::uint32_t team_doubles;   // per team: positions | outputs | private rows | norms | scalars
     std::uint32_t n_slots_equiv;  // team region (without the scalars) expressed in coop_smem<LT> slots
+    nb1_tab l1;                   // k_nb1 only
 };
 
 namespace nbk

@@ -25,6 +25,7 @@ struct nb_variant {
     bool tmem; // r^2, d_2, r^alpha rows in tensor memory
     int maxt;  // maximum threads per CTA (256: up to 255 registers per thread, 384: 168, 512: 128)
     nb_fn step, prop;
+    bool lane = false; // one thread per lane, systems with one pair interaction (k_nb1, nb1_kernel.cuh)
 };
 
 struct nb_family {
@@ -39,6 +40,7 @@ nb_family nb_family_lt8_cta0();
 nb_family nb_family_lt16_cta0();
 nb_family nb_family_lt32_cta0();
 nb_family nb_family_lt1_cta1();
+nb_family nb_family_lane();
 
 } // namespace heyoka_b200::detail
 

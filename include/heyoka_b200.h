@@ -346,13 +346,15 @@ int hy_batch_set_launch_config(hy_batch *, uint32_t block_threads, uint32_t bloc
  * mode picks 4 or 5 when shared memory is too small; 6 / 7 = the dedicated N-body kernel (warp / CTA teams; error if
  * the program is not N-body-shaped, see csrc/nb_plan.hpp), which the automatic mode prefers whenever the program
  * qualifies (lanes_per_thread then selects the storage of the private history rows: 0 automatic, 1 tensor memory,
- * 2 shared memory only; lanes_per_warp = lanes per team). lanes_per_warp (1..32, power of two) / lanes_per_thread (1, 2 or 4, dividing lanes_per_warp)
+ * 2 shared memory only; lanes_per_warp = lanes per team); 8 = the dense-network kernel; 9 = the N-body kernel with one
+ * thread per lane (programs with ONE pair interaction, e.g. the two-body problem; the automatic mode takes it when it
+ * applies, HEYOKA_B200_NB_LANE=0 turns that off). lanes_per_warp (1..32, power of two) / lanes_per_thread (1, 2 or 4, dividing lanes_per_warp)
  * only apply to the shared-memory kernel; 0 = automatic. block_threads = 32 x warps per block.
  * The environment variable HEYOKA_B200_TAPE=hbm|smem sets the default. */
 int hy_batch_set_kernel(hy_batch *, int tape_mode, uint32_t lanes_per_warp, uint32_t lanes_per_thread,
                         uint32_t block_threads, uint32_t blocks_per_sm);
 typedef struct hy_kernel_info {
-    int32_t tape_mode;            /* 1 = HBM tape (thread per lane), 2 = shared-memory tape, 4 / 5 = cooperative, global tape (warp / CTA teams), 6 / 7 = N-body kernel (warp / CTA teams) */
+    int32_t tape_mode;            /* 1 = HBM tape (thread per lane), 2 = shared-memory tape, 4 / 5 = cooperative, global tape (warp / CTA teams), 6 / 7 = N-body kernel (warp / CTA teams), 8 = dense-network kernel, 9 = N-body kernel, one thread per lane (one pair interaction) */
     uint32_t lanes_per_warp, lanes_per_thread, block_threads, blocks_per_sm, grid;
     uint64_t smem_bytes;          /* dynamic shared memory per CTA */
     uint32_t tape_slots_per_lane; /* doubles of tape per lane in the selected strategy */
