@@ -697,13 +697,15 @@ void hy_batch::setup_coop_global(int L, int N, std::uint32_t threads, int cta)
 // The table of the one-thread-per-lane N-body kernel (nb1_kernel.cuh) for a plan with ONE pair interaction whose six
 // positions each belong to a velocity driven by a single pair output of the same coordinate, or by a number. Returns
 // false for anything else (such plans run on k_nb with 32 lanes per warp).
-static bool make_nb1_tab(const hy::detail::nb_plan &pl, std::uint32_t n_eq, dev::nb1_tab &tab)
+static bool make_nb1_tab(const hy::detail::nb_plan &pl, std::uint32_t n_eq, std::uint32_t order, dev::nb1_tab &tab)
 {
-    if (!pl.ok || pl.pairs.size() != 1u || pl.sums.size() != 6u || pl.level_offsets.size() != 2u || n_eq != 12u) {
+    if (!pl.ok || pl.pairs.size() != 1u || pl.sums.size() != 6u || pl.level_offsets.size() != 2u || n_eq != 12u
+        || order < 4u) {
         return false;
     }
     const auto &pr = pl.pairs[0];
     bool seen[12] = {};
+    std::uint32_t kinds[6];
     for (std::uint32_t s = 0; s < 6u; ++s) {
         const std::uint32_t k = s % 3u, ps = s < 3u ? pr.pa[k] : pr.pb[k];
         const hy::detail::nb_sum_desc *sd = nullptr;
@@ -725,20 +727,29 @@ static bool make_nb1_tab(const hy::detail::nb_plan &pl, std::uint32_t n_eq, dev:
             return false;
         }
         seen[tab.v_sv[s]] = seen[tab.x_sv[s]] = true;
-        tab.cval[s] = 0.;
+        if (tab.v_sv[s] == 0u || tab.x_sv[s] == 0u) {
+            tab.sv0_slot = s;
+            tab.sv0_is_x = tab.x_sv[s] == 0u ? 1u : 0u;
+        }
         if (sd->kind == 2u) {
-            if (sd->cidx >= pl.consts.size()) {
+            // (Only the right-hand side +0: what model::nbody produces for a body that nothing pulls on.)
+            if (sd->cidx >= pl.consts.size() || pl.consts[sd->cidx] != 0. || std::signbit(pl.consts[sd->cidx])) {
                 return false;
             }
-            tab.kind[s] = 2u;
-            tab.cval[s] = pl.consts[sd->cidx];
+            kinds[s] = 2u;
         } else if (sd->kind == 1u && sd->n_terms == 1u && sd->terms[0] == pr.om[k]) {
-            tab.kind[s] = 0u;
+            kinds[s] = 0u;
         } else if (sd->kind == 1u && sd->n_terms == 1u && pr.on[k] != 0xffffu && sd->terms[0] == pr.on[k]) {
-            tab.kind[s] = 1u;
+            kinds[s] = 1u;
         } else {
             return false;
         }
+    }
+    for (std::uint32_t side = 0; side < 2u; ++side) {
+        if (kinds[3u * side] != kinds[3u * side + 1u] || kinds[3u * side] != kinds[3u * side + 2u]) {
+            return false;
+        }
+        tab.kind[side] = kinds[3u * side];
     }
     return true;
 }
@@ -774,7 +785,7 @@ bool hy_batch::setup_nb(int LT, std::uint32_t threads, int want_tmem, int want_c
     }
     // One pair interaction, 32 lanes per warp: one thread per lane, nothing exchanged (nb1_kernel.cuh).
     dev::nb1_tab l1{};
-    const bool lane = want_lane != 0 && !cta && LT == 32 && make_nb1_tab(nbp, n_eq, l1);
+    const bool lane = want_lane != 0 && !cta && LT == 32 && make_nb1_tab(nbp, n_eq, order, l1);
     if (want_lane > 0 && !lane) {
         return false;
     }
@@ -1255,6 +1266,13 @@ void hy_batch::launch(bool prop, const dev::run_args &R)
         R2.coef_warp_stride = pub ? 0ull : static_cast<unsigned long long>(order + 1u) * n_eq * lanes;
         R2.coef_stride_sv = pub ? static_cast<unsigned long long>(order + 1u) * n : lanes;
         R2.coef_stride_o = pub ? static_cast<unsigned long long>(n) : static_cast<unsigned long long>(n_eq) * lanes;
+        if (nb_on && nb_lane) {
+            // k_nb1 always works on its private store ([order][slot][32 lanes], velocities only) and publishes the
+            // coefficients to tc on request.
+            R2.coef_base = d_cscratch;
+            R2.coef_warp_stride = static_cast<unsigned long long>(order + 1u) * n_eq * lanes;
+            R2.coef_pub = R.write_tc != 0 ? 1 : 0;
+        }
         if (nb_on) {
             (prop ? nbv->prop : nbv->step)<<<c_grid, c_threads, c_smem, stream>>>(prog, nbd, view(), R2);
         } else {

@@ -10,11 +10,16 @@
 // of a body that only massless bodies pull on), so the thread that owns the lane keeps everything in registers:
 //   * the six positions of the current order pair, the outputs m_k / n_k of the pair interaction (nb_core.hpp's
 //     pair_block() with a register policy), v^[n+1] = a^[n] / (n + 1), x^[n+2] = v^[n+1] / (n + 2) in straight-line code;
-//   * the three infinity norms of the step-size estimate (NaN-skipping maxima, like nb_step_size());
 //   * its history rows d_0, d_1 in shared memory and r^2, d_2, r^alpha in tensor memory, exactly as in k_nb;
-//   * the state variables' coefficients go to the private per-warp store (or to the public tc array), 256-byte rows.
-// No __syncwarp() inside a step. Same arithmetic, same order of operations as k_nb / k_coop: bit-identical results
-// (tests/test_gpu_parity.py runs both on the same inputs).
+//   * of the state variables' coefficients only the velocities' orders 1..p are kept, in a private per-warp store
+//     [order][slot][32 lanes] with compile-time strides (one store instruction per coefficient, 256-byte rows, 0.5 KB
+//     per lane of the two-body benchmark: the stores of all resident warps stay in L2). The positions' coefficients are
+//     their quotients x^[o] = v^[o-1] / o, recomputed (correctly rounded either way) where they are needed again: the
+//     step-size norms, the state update, the public tc array when the caller asks for it. A body that nothing pulls
+//     on (right-hand side 0) stores nothing: its velocity row is (v_0, 0, 0, ...).
+// No exchange between threads; a __syncwarp() per order pair only keeps the warp converged for the tensor-memory
+// accesses. Same arithmetic, same order of operations as k_nb / k_coop: bit-identical results (tests/test_gpu_parity.py
+// runs both on the same inputs).
 // Replaces, for these programs: the JIT'd step function (src/taylor_00.cpp:712-865) and the propagate loop
 // (src/taylor_adaptive_batch.cpp:1136-1534).
 #ifndef HEYOKA_B200_CSRC_NB1_KERNEL_CUH
@@ -59,10 +64,21 @@ struct pair_mem1 : pair_mem<32, TMEM> {
 
 } // namespace nbk
 
-// NaN-skipping running maximum of |v| (fmax() returns its other argument for a NaN).
-__device__ __forceinline__ void nb1_track(double &m, double v)
+// NaN-skipping running maximum of |v| on the bit patterns (non-negative doubles order like unsigned integers).
+__device__ __forceinline__ void nb1_track(unsigned long long &m, double v)
 {
-    m = fmax(m, fabs(v));
+    if (v == v) {
+        const unsigned long long b = static_cast<unsigned long long>(__double_as_longlong(v)) & 0x7fffffffffffffffull;
+        m = b > m ? b : m;
+    }
+}
+// x / n for the recomputed position coefficients: the correctly rounded quotient whichever path produced it in the jet.
+__device__ __forceinline__ double nb1_div(double x, std::uint32_t n, double nd, double rcp)
+{
+    if (n <= 64u && nb::div_si_in_range(x)) {
+        return nb::div_si_fast(x, nd, rcp);
+    }
+    return x == 0. ? x : nb::div_cold(x, nd);
 }
 
 template <bool TMEM, bool PROP, int MAXT>
@@ -70,6 +86,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_nb1(program P, nb_dev_plan NP, batc
 {
     using nb::d2;
     extern __shared__ __align__(16) double smem_raw[];
+    constexpr std::uint32_t SO = 6u * 32u; // doubles per order of the private store: [order - 1][slot][lane]
 
     // ---- CTA-shared tables: fac | rcp ----
     const std::uint32_t p = P.order;
@@ -130,51 +147,27 @@ __global__ void __launch_bounds__(MAXT, 1) k_nb1(program P, nb_dev_plan NP, batc
     static_assert(sizeof(lane_prop) <= 128u && alignof(lane_prop) <= 8u);
 
     const std::size_t team_global = (static_cast<std::size_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    // The private store of this thread's lane: V(o, s) = v_s^[o] (o = 1..p) at cb[(o - 1) * SO + s * 32].
+    double *const cb = R.coef_base + team_global * R.coef_warp_stride + tid;
     const bool pub = R.coef_pub != 0;
-    const bool mask_idle = !PROP && R.skip != nullptr;
-    double *const cstore = R.coef_base + team_global * R.coef_warp_stride;
-    const std::size_t stride_sv = static_cast<std::size_t>(R.coef_stride_sv), stride_o = static_cast<std::size_t>(R.coef_stride_o);
     const std::uint32_t n_chunks = (D.n + 31u) / 32u;
     const std::uint32_t n_blocks = NP.npp;
     const nb1_tab &TB = NP.l1;
+    const std::size_t nb = D.n;
 
-    // The jet of this thread's lane (glane: clamped global lane; ok: the lane may write to the public store).
-    // Returns the step-size norms through m0 / mp / mp1.
-    const auto jet = [&](std::uint32_t glane, bool ok, double &m0, double &mp, double &mp1) {
-        double *const cb = cstore + (pub ? static_cast<std::size_t>(glane) : static_cast<std::size_t>(tid));
-        const auto st = [&](std::uint32_t sv, std::uint32_t order, double v) {
-            if (pub) {
-                if (ok) {
-                    cb[sv * stride_sv + order * stride_o] = v;
-                }
-            } else {
-                cb[sv * static_cast<std::uint32_t>(stride_sv) + order * static_cast<std::uint32_t>(stride_o)] = v;
-            }
-        };
-        m0 = 0., mp = 0., mp1 = 0.;
-        // nb_step_size()'s bookkeeping: order 0 -> m0, order p -> mp, order p - 1 -> mp1 (orders beyond p: dropped).
-        const auto trk = [&](std::uint32_t order, double v) {
-            if (order == 0u) {
-                nb1_track(m0, v);
-            } else if (order == p) {
-                nb1_track(mp, v);
-            } else if (order + 1u == p) {
-                nb1_track(mp1, v);
-            }
-        };
-        // Order 0 (and order 1 of the positions).
+    // The jet of this thread's lane (glane: clamped global lane). Returns the NaN-skipping maximum of the order-0
+    // coefficients (bit pattern).
+    const auto jet = [&](std::uint32_t glane) {
+        unsigned long long m0 = 0ull;
 #pragma unroll
         for (int s = 0; s < 6; ++s) {
-            const double x0 = D.state[static_cast<std::size_t>(TB.x_sv[s]) * D.n + glane];
-            const double v0 = D.state[static_cast<std::size_t>(TB.v_sv[s]) * D.n + glane];
-            st(TB.v_sv[s], 0u, v0);
-            st(TB.x_sv[s], 0u, x0);
-            st(TB.x_sv[s], 1u, v0);
-            trk(0u, v0);
-            trk(0u, x0);
-            trk(1u, v0);
+            const double x0 = D.state[static_cast<std::size_t>(TB.x_sv[s]) * nb + glane];
+            const double v0 = D.state[static_cast<std::size_t>(TB.v_sv[s]) * nb + glane];
+            nb1_track(m0, x0);
+            nb1_track(m0, v0);
             (s < 3 ? PM.xa[s % 3] : PM.xb[s % 3]) = d2{x0, v0};
         }
+        double *vp = cb; // V(n + 1, 0)
         for (std::uint32_t m = 0; m < n_blocks; ++m) {
             __syncwarp(); // (the tensor-memory accesses of pair_block() are warp-wide: converged)
             nb::pair_block(PM, PC, m);
@@ -186,76 +179,181 @@ __global__ void __launch_bounds__(MAXT, 1) k_nb1(program P, nb_dev_plan NP, batc
                          n3 = static_cast<double>(n + 3u);
             const double r1 = nbk::lds1(rcp_a + (n + 1u) * 8u), r2 = nbk::lds1(rcp_a + (n + 2u) * 8u),
                          r3 = nbk::lds1(rcp_a + (n + 3u) * 8u);
-            const bool track = m + 2u >= n_blocks;
+            const bool two = n + 2u <= p;
 #pragma unroll
-            for (int s = 0; s < 6; ++s) {
-                const int k = s % 3;
-                const std::uint32_t kind = TB.kind[s];
-                d2 a;
+            for (int side = 0; side < 2; ++side) {
+                const std::uint32_t kind = TB.kind[side];
                 if (kind == 2u) {
-                    a = d2{n == 0u ? TB.cval[s] : 0., 0.};
-                } else {
-                    a = kind == 1u ? PM.on_[k] : PM.om_[k];
+                    // Right-hand side 0: v = (v_0, 0, ...), x = (x_0, v_0, 0, ...).
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        (side == 0 ? PM.xa[k] : PM.xb[k]) = d2{0., 0.};
+                    }
+                    continue;
                 }
-                double va, vb, xa, xb;
-                if (kind == 2u && n > 0u) {
-                    // A constant right-hand side: every coefficient beyond the first order is an exact zero.
-                    va = vb = xa = xb = 0.;
-                } else if (n + 3u <= 64u && nb::div_si_in_range2(a.x) && nb::div_si_in_range2(a.y)) {
-                    va = nb::div_si_fast(a.x, n1, r1); // v^[n+1]
-                    vb = nb::div_si_fast(a.y, n2, r2); // v^[n+2]
-                    xa = nb::div_si_fast(va, n2, r2);  // x^[n+2]
-                    xb = nb::div_si_fast(vb, n3, r3);  // x^[n+3]
-                } else {
-                    va = a.x == 0. ? a.x : nb::div_cold(a.x, n1);
-                    vb = a.y == 0. ? a.y : nb::div_cold(a.y, n2);
-                    xa = va == 0. ? va : nb::div_cold(va, n2);
-                    xb = vb == 0. ? vb : nb::div_cold(vb, n3);
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const d2 a = kind == 1u ? PM.on_[k] : PM.om_[k];
+                    double va, vb, xa, xb;
+                    if (n + 3u <= 64u && nb::div_si_in_range2(a.x) && nb::div_si_in_range2(a.y)) {
+                        va = nb::div_si_fast(a.x, n1, r1); // v^[n+1]
+                        vb = nb::div_si_fast(a.y, n2, r2); // v^[n+2]
+                        xa = nb::div_si_fast(va, n2, r2);  // x^[n+2]
+                        xb = nb::div_si_fast(vb, n3, r3);  // x^[n+3]
+                    } else {
+                        va = a.x == 0. ? a.x : nb::div_cold(a.x, n1);
+                        vb = a.y == 0. ? a.y : nb::div_cold(a.y, n2);
+                        xa = va == 0. ? va : nb::div_cold(va, n2);
+                        xb = vb == 0. ? vb : nb::div_cold(vb, n3);
+                    }
+                    vp[(side * 3 + k) * 32] = va;
+                    if (two) {
+                        vp[SO + (side * 3 + k) * 32] = vb;
+                    }
+                    (side == 0 ? PM.xa[k] : PM.xb[k]) = d2{xa, xb};
                 }
-                const std::uint32_t vs = TB.v_sv[s], xs = TB.x_sv[s];
-                st(vs, n + 1u, va);
-                if (n + 2u <= p) {
-                    st(vs, n + 2u, vb);
-                    st(xs, n + 2u, xa);
+            }
+            vp += 2u * SO;
+        }
+        return m0;
+    };
+
+    // Step size (nb_step_size()'s semantics: NaN-skipping maxima over the state variables of the orders 0, p, p - 1; a NaN
+    // in the FIRST state variable makes the norm a NaN).
+    const auto step_size = [&](std::uint32_t glane, unsigned long long m0, double max_delta_t) {
+        unsigned long long mp = 0ull, mp1 = 0ull;
+        double fp = 0., fp1 = 0.;
+        const double pd = static_cast<double>(p), pd1 = static_cast<double>(p - 1u);
+        const double rp = nbk::lds1(rcp_a + p * 8u), rp1 = nbk::lds1(rcp_a + (p - 1u) * 8u);
+        const double *top = cb + static_cast<std::size_t>(p - 1u) * SO; // V(p, 0)
+#pragma unroll 1
+        for (std::uint32_t side = 0; side < 2u; ++side) {
+            if (TB.kind[side] == 2u) {
+                continue;
+            }
+#pragma unroll
+            for (std::uint32_t k = 0; k < 3u; ++k) {
+                const std::uint32_t s = side * 3u + k;
+                const double *c = top + s * 32u;
+                const double vp_ = c[0], vp1_ = *(c - SO), vp2_ = *(c - 2u * SO);
+                const double xp_ = nb1_div(vp1_, p, pd, rp), xp1_ = nb1_div(vp2_, p - 1u, pd1, rp1);
+                nb1_track(mp, vp_);
+                nb1_track(mp, xp_);
+                nb1_track(mp1, vp1_);
+                nb1_track(mp1, xp1_);
+                if (s == TB.sv0_slot) {
+                    fp = fabs(TB.sv0_is_x != 0u ? xp_ : vp_);
+                    fp1 = fabs(TB.sv0_is_x != 0u ? xp1_ : vp1_);
                 }
-                if (n + 3u <= p) {
-                    st(xs, n + 3u, xb);
-                }
-                if (track) {
-                    trk(n + 1u, va);
-                    trk(n + 2u, vb);
-                    trk(n + 2u, xa);
-                    trk(n + 3u, xb);
-                }
-                (s < 3 ? PM.xa[k] : PM.xb[k]) = d2{xa, xb};
+            }
+        }
+        const double f0 = fabs(D.state[glane]);
+        return h_from_norms(P, isnan(f0) ? f0 : __longlong_as_double(static_cast<long long>(m0)),
+                            isnan(fp) ? fp : __longlong_as_double(static_cast<long long>(mp)),
+                            isnan(fp1) ? fp1 : __longlong_as_double(static_cast<long long>(mp1)), max_delta_t);
+    };
+
+    // The public Taylor coefficients of the lane (write_tc): tc[(sv (p + 1) + o) batch + lane].
+    const auto publish = [&](std::uint32_t glane) {
+        const std::size_t so = nb, ssv = static_cast<std::size_t>(p + 1u) * nb;
+#pragma unroll 1
+        for (std::uint32_t s = 0; s < 6u; ++s) {
+            const bool stored = TB.kind[s / 3u] != 2u;
+            const std::uint32_t vs = TB.v_sv[s], xs = TB.x_sv[s];
+            double prev = D.state[static_cast<std::size_t>(vs) * nb + glane];
+            double *tv = D.tc + vs * ssv + glane, *tx = D.tc + xs * ssv + glane;
+            tv[0] = prev;
+            tx[0] = D.state[static_cast<std::size_t>(xs) * nb + glane];
+            const double *c = cb + s * 32u;
+            for (std::uint32_t o = 1; o <= p; ++o) {
+                const double cur = stored ? c[static_cast<std::size_t>(o - 1u) * SO] : 0.;
+                tv[o * so] = cur;
+                tx[o * so] = nb1_div(prev, o, static_cast<double>(o), nbk::lds1(rcp_a + o * 8u));
+                prev = cur;
             }
         }
     };
 
-    // Step size from the norms and the coefficients of the first state variable (nb_step_size()'s semantics).
-    const auto step_size = [&](std::uint32_t glane, double m0, double mp, double mp1, double max_delta_t) {
-        const double *c = cstore + (pub ? static_cast<std::size_t>(glane) : static_cast<std::size_t>(tid));
-        const double f0 = fabs(c[0]), fp = fabs(c[p * stride_o]), fp1 = fabs(c[(p - 1u) * stride_o]);
-        return h_from_norms(P, isnan(f0) ? f0 : m0, isnan(fp) ? fp : mp, isnan(fp1) ? fp1 : mp1, max_delta_t);
-    };
-    // State update of the lane; returns true if a non-finite value was produced.
+    // State update of the lane (Horner / compensated summation of recurrences.cuh::eval_poly(), the three coordinates
+    // of a body side by side, velocity and position chains fed by the same loads); returns true if a non-finite
+    // value was produced.
     const auto update = [&](std::uint32_t glane, bool write, double h) {
-        constexpr int K = 4;
-        const double *c0 = cstore + (pub ? static_cast<std::size_t>(glane) : static_cast<std::size_t>(tid));
         bool nf = false;
-        for (std::uint32_t sv = 0; sv < P.n_eq; sv += K) {
-            const double *c[K];
+#pragma unroll 1
+        for (std::uint32_t side = 0; side < 2u; ++side) {
+            const bool stored = TB.kind[side] != 2u;
+            double v0[3], x0[3], rv[3], rx[3];
+            const double *c[3];
 #pragma unroll
-            for (int k = 0; k < K; ++k) {
-                c[k] = c0 + (sv + k < P.n_eq ? sv + k : sv) * stride_sv;
+            for (std::uint32_t k = 0; k < 3u; ++k) {
+                const std::uint32_t s = side * 3u + k;
+                v0[k] = D.state[static_cast<std::size_t>(TB.v_sv[s]) * nb + glane];
+                x0[k] = D.state[static_cast<std::size_t>(TB.x_sv[s]) * nb + glane];
+                c[k] = cb + s * 32u;
             }
-            double res[K];
-            eval_poly_k<K>(P, c, stride_o, h, res);
+            if (!P.high_accuracy) {
+                // v: ((V(p) h + V(p-1)) h + ...) h + v_0;  x: ((x^[p] h + x^[p-1]) h + ...) h + x_0, x^[o] = V(o-1) / o.
 #pragma unroll
-            for (int k = 0; k < K; ++k) {
-                if (write && sv + k < P.n_eq) {
-                    D.state[static_cast<std::size_t>(sv + k) * D.n + glane] = res[k];
-                    nf = nf || !isfinite(res[k]);
+                for (std::uint32_t k = 0; k < 3u; ++k) {
+                    rv[k] = stored ? c[k][static_cast<std::size_t>(p - 1u) * SO] : 0.;
+                    rx[k] = 0.;
+                }
+                for (std::uint32_t o = p; o >= 2u; --o) {
+                    const double od = static_cast<double>(o), ro = nbk::lds1(rcp_a + o * 8u);
+#pragma unroll
+                    for (std::uint32_t k = 0; k < 3u; ++k) {
+                        const double w = stored ? c[k][static_cast<std::size_t>(o - 2u) * SO] : 0.; // V(o - 1)
+                        const double xo = nb1_div(w, o, od, ro);
+                        rv[k] = ::fma(rv[k], h, w);
+                        rx[k] = o == p ? xo : ::fma(rx[k], h, xo);
+                    }
+                }
+#pragma unroll
+                for (std::uint32_t k = 0; k < 3u; ++k) {
+                    rv[k] = ::fma(rv[k], h, v0[k]);
+                    rx[k] = ::fma(::fma(rx[k], h, v0[k]), h, x0[k]);
+                }
+            } else {
+                double cpv[3], cpx[3], prev[3], cur_h = h;
+#pragma unroll
+                for (std::uint32_t k = 0; k < 3u; ++k) {
+                    rv[k] = v0[k];
+                    rx[k] = x0[k];
+                    cpv[k] = cpx[k] = 0.;
+                    prev[k] = v0[k];
+                }
+                for (std::uint32_t o = 1; o <= p; ++o) {
+                    const double od = static_cast<double>(o), ro = nbk::lds1(rcp_a + o * 8u);
+#pragma unroll
+                    for (std::uint32_t k = 0; k < 3u; ++k) {
+                        const double cv_ = stored ? c[k][static_cast<std::size_t>(o - 1u) * SO] : 0.; // V(o)
+                        const double cx_ = nb1_div(prev[k], o, od, ro);                               // x^[o]
+                        prev[k] = cv_;
+                        {
+                            const double tmp = __dmul_rn(cv_, cur_h);
+                            const double y = __dsub_rn(tmp, cpv[k]);
+                            const double tt = __dadd_rn(rv[k], y);
+                            cpv[k] = __dsub_rn(__dsub_rn(tt, rv[k]), y);
+                            rv[k] = tt;
+                        }
+                        {
+                            const double tmp = __dmul_rn(cx_, cur_h);
+                            const double y = __dsub_rn(tmp, cpx[k]);
+                            const double tt = __dadd_rn(rx[k], y);
+                            cpx[k] = __dsub_rn(__dsub_rn(tt, rx[k]), y);
+                            rx[k] = tt;
+                        }
+                    }
+                    cur_h = __dmul_rn(cur_h, h);
+                }
+            }
+            if (write) {
+#pragma unroll
+                for (std::uint32_t k = 0; k < 3u; ++k) {
+                    const std::uint32_t s = side * 3u + k;
+                    D.state[static_cast<std::size_t>(TB.v_sv[s]) * nb + glane] = rv[k];
+                    D.state[static_cast<std::size_t>(TB.x_sv[s]) * nb + glane] = rx[k];
+                    nf = nf || !isfinite(rv[k]) || !isfinite(rx[k]);
                 }
             }
         }
@@ -268,12 +366,15 @@ __global__ void __launch_bounds__(MAXT, 1) k_nb1(program P, nb_dev_plan NP, batc
         const std::uint32_t lane = valid ? lane_raw : D.n - 1u;
 
         if constexpr (!PROP) {
+            // (A step with a skip mask leaves the lanes that are not running untouched, tc included.)
             const bool skipped = R.skip != nullptr && R.skip[lane] != 0u;
             valid = valid && !skipped;
-            double m0, mp, mp1;
-            jet(lane, lane_raw < D.n && !(mask_idle && skipped), m0, mp, mp1);
+            const unsigned long long m0 = jet(lane);
             const double mdt = R.max_delta_t != nullptr ? R.max_delta_t[lane] : R.default_max_delta_t;
-            const double h = step_size(lane, m0, mp, mp1, mdt);
+            const double h = step_size(lane, m0, mdt);
+            if (pub && valid) {
+                publish(lane);
+            }
             const bool state_nf = update(lane, valid, h);
             if (valid) {
                 const dfl nt = dfl_add(dfl{D.t_hi[lane], D.t_lo[lane]}, dfl{h, 0.});
@@ -293,10 +394,12 @@ __global__ void __launch_bounds__(MAXT, 1) k_nb1(program P, nb_dev_plan NP, batc
                 running = lp.running;
             }
             while (__any_sync(0xffffffffu, running)) {
-                double m0, mp, mp1;
-                jet(lane, lane_raw < D.n, m0, mp, mp1);
+                const unsigned long long m0 = jet(lane);
                 const double cur_max = park->cur_max();
-                const double h = step_size(lane, m0, mp, mp1, cur_max);
+                const double h = step_size(lane, m0, cur_max);
+                if (pub && valid) {
+                    publish(lane);
+                }
                 const bool state_nf = update(lane, valid && running, h);
                 if (running) {
                     lane_prop lp = *park;

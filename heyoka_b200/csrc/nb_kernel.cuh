@@ -37,11 +37,12 @@ namespace heyoka_b200::dev
 {
 
 // Systems with ONE pair interaction run one thread per lane (k_nb1, nb1_kernel.cuh). Slot s = 3 * side + k: side 0 /
-// 1 = the body whose positions are the pair's pa / pb, k = coordinate. The acceleration of the slot's velocity v_sv
-// (whose position child is x_sv) is the pair output m_k (kind 0), n_k (kind 1) or the number cval (kind 2).
+// 1 = the body whose positions are the pair's pa / pb, k = coordinate. The accelerations of a side's velocities v_sv
+// (whose position children are x_sv) are the pair outputs m_k (kind 0), n_k (kind 1) or the number 0 (kind 2).
+// sv0_slot / sv0_is_x: where state variable 0 sits (its NaNs are the ones the step-size norms let through).
 struct nb1_tab {
-    std::uint32_t v_sv[6], x_sv[6], kind[6];
-    double cval[6];
+    std::uint32_t v_sv[6], x_sv[6], kind[2];
+    std::uint32_t sv0_slot, sv0_is_x;
 };
 
 // Device-side view of an nb_plan (arrays in global memory) + the shared-memory layout chosen by the host.

@@ -36,6 +36,9 @@ KERNELS = {
     "nbody-smem": dict(tape="nbody", lanes_per_thread=2),
     "nbody-384": dict(tape="nbody", lanes_per_thread=1, block_threads=384),
     "nbody-L1": dict(tape="nbody", lanes_per_warp=1, block_threads=128),
+    # One thread per lane (nb1_kernel.cuh; programs with ONE pair interaction only): tensor memory / shared memory only.
+    "nbody-lane": dict(tape="nbody-lane"),
+    "nbody-lane-smem": dict(tape="nbody-lane", lanes_per_thread=2),
 }
 
 
@@ -142,6 +145,16 @@ def test_step_parity_tutorial_system(kernel, ha):
 @pytest.mark.parametrize("ha", [False, True])
 def test_step_parity_two_body(kernel, ha):
     _step_parity(kernel, sys_two_body(), two_body_batch_state(50), 50, ha=ha)
+
+
+@pytest.mark.parametrize("ha", [False, True])
+@pytest.mark.parametrize("masses", [[1., 0.3], [0.7, 1.1], [0., 2.]])
+def test_step_parity_two_massive_bodies(kernel, ha, masses):
+    """Two bodies that both pull (pair outputs m_k and the rescaled n_k), and the massless body first."""
+    rng = np.random.default_rng(3)
+    batch = 77
+    st = two_body_batch_state(batch) + 0.05 * rng.standard_normal((12, batch))
+    _step_parity(kernel, hb.model.nbody(2, masses=masses), st, batch, ha=ha)
 
 
 @pytest.mark.parametrize("ha", [False, True])
@@ -303,6 +316,59 @@ def test_propagate_early_lanes_last_h_and_tc(kernel):
             # Dense output at the current time reproduces the state for every lane (early ones included).
             assert rel_err(ta.update_d_output(0., rel_time=True), ta.state) < 1e-13
             assert rel_err(ta.update_d_output(tf), ta.state) < 1e-13
+
+
+@pytest.mark.parametrize("masses", [[1., 0.], [1., 0.4]])
+def test_two_body_lane_kernel(masses):
+    """The one-thread-per-lane N-body kernel (k_nb1, nb1_kernel.cuh): selected automatically for systems with one pair
+    interaction; bit-identical to k_nb with 32 lanes per warp (same arithmetic, same order) for steps with and without
+    the public Taylor coefficients, propagate_until() with lanes that finish early, and a masked re-expansion; against
+    the oracle: identical step counts over 40 time units, states to 2e-11."""
+    sys_ = hb.model.nbody(2, masses=masses)
+    batch = 1000  # (not a multiple of 32; several warps and CTAs)
+    rng = np.random.default_rng(11)
+    st = two_body_batch_state(batch) + 0.02 * rng.standard_normal((12, batch))
+    lane = hb.taylor_adaptive_batch(sys_, st, batch)
+    assert lane._b.kernel_info()["tape"] == "nbody-lane" and lane._b.kernel_info()["lanes_per_warp"] == 32
+    team = hb.taylor_adaptive_batch(sys_, st, batch, kernel=dict(tape="nbody"))
+    assert team._b.kernel_info()["tape"] == "nbody" and team._b.kernel_info()["lanes_per_warp"] == 32
+    for wtc in (False, True, False):
+        lane.step(write_tc=wtc)
+        team.step(write_tc=wtc)
+        assert np.array_equal(lane.state, team.state) and np.array_equal(lane.last_h, team.last_h)
+        assert np.array_equal(lane.time, team.time)
+        assert [r[0] for r in lane.step_res] == [r[0] for r in team.step_res]
+        if wtc:
+            assert np.array_equal(lane.tc, team.tc)
+    lim = np.where(np.arange(batch) % 3 == 0, 1e-3, -2e-3)
+    lane.step(lim)
+    team.step(lim)
+    assert np.array_equal(lane.state, team.state) and np.array_equal(lane.last_h, lim)
+    tf = lane.time + np.linspace(5., 40., batch)
+    for wtc in (False, True):
+        lane.propagate_until(tf if not wtc else tf + 3., write_tc=wtc)
+        team.propagate_until(tf if not wtc else tf + 3., write_tc=wtc)
+        assert lane.propagate_res == team.propagate_res
+        assert np.array_equal(lane.state, team.state) and np.array_equal(lane.last_h, team.last_h)
+        assert np.array_equal(lane.time, team.time)
+        if wtc:
+            assert np.array_equal(lane.tc, team.tc)
+    # Against the oracle, from the initial conditions.
+    P = hb.Program(sys_)
+    idx = rng.choice(batch, 96, replace=False)
+    o = oracle.OracleIntegrator(P, st[:, idx], len(idx), mode=oracle.FMA)
+    ta = hb.taylor_adaptive_batch(sys_, st, batch)
+    o.propagate_until(40., lockstep=False)
+    ta.propagate_until(40.)
+    assert [ta.propagate_res[i][3] for i in idx] == [int(x) for x in o.n_steps]
+    assert lane_err(ta.state[:, idx], o.state) < 2e-11  # (~150 steps of ulp-level differences in pow)
+    # A non-finite lane stops alone and is reported (global exit handled by the host replay).
+    bad = st.copy()
+    bad[0:3, 5] = bad[6:9, 5] = 0.  # one body on top of the other: r = 0
+    ta = hb.taylor_adaptive_batch(sys_, bad, batch)
+    ta.step()
+    assert ta.step_res[5][0] == hb.taylor_outcome.err_nf_state
+    assert all(r[0] == hb.taylor_outcome.success for i, r in enumerate(ta.step_res) if i != 5)
 
 
 def test_raw_program_interface_matches():

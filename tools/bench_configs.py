@@ -64,6 +64,14 @@ def main():
         run("two_body_step_batch 2^22 lanes, one step", hb.Program(sys_two_body()), two_body_batch_state(1 << 22))
     if "tb" in which:
         run("two_body_step_batch 2^24 lanes, one step", hb.Program(sys_two_body()), two_body_batch_state(1 << 24))
+    if "tbteam" in which:
+        run("two_body_step_batch 2^24 lanes, one step, k_nb with 32 lanes per warp", hb.Program(sys_two_body()),
+            two_body_batch_state(1 << 24), tape="nbody")
+    if "tbsweep" in which:
+        for kw in (dict(block_threads=256), dict(block_threads=384), dict(block_threads=512),
+                   dict(block_threads=256, lanes_per_thread=2), dict(block_threads=512, lanes_per_thread=2)):
+            run("two_body_step_batch 2^22 lanes, one step, k_nb1 %r" % (kw,), hb.Program(sys_two_body()),
+                two_body_batch_state(1 << 22), tape="nbody-lane", **kw)
     if "s6step" in which:
         run("outer_ss 6-body 2^20 lanes, one step", hb.Program(sys_outer_ss(), high_accuracy=True),
             outer_ss_batch_state(1 << 20))
