@@ -194,18 +194,12 @@ __global__ void __launch_bounds__(MAXT, 1) k_nb1(program P, nb_dev_plan NP, batc
 #pragma unroll
                 for (int k = 0; k < 3; ++k) {
                     const d2 a = kind == 1u ? PM.on_[k] : PM.om_[k];
-                    double va, vb, xa, xb;
-                    if (n + 3u <= 64u && nb::div_si_in_range2(a.x) && nb::div_si_in_range2(a.y)) {
-                        va = nb::div_si_fast(a.x, n1, r1); // v^[n+1]
-                        vb = nb::div_si_fast(a.y, n2, r2); // v^[n+2]
-                        xa = nb::div_si_fast(va, n2, r2);  // x^[n+2]
-                        xb = nb::div_si_fast(vb, n3, r3);  // x^[n+3]
-                    } else {
-                        va = a.x == 0. ? a.x : nb::div_cold(a.x, n1);
-                        vb = a.y == 0. ? a.y : nb::div_cold(a.y, n2);
-                        xa = va == 0. ? va : nb::div_cold(va, n2);
-                        xb = vb == 0. ? vb : nb::div_cold(vb, n3);
-                    }
+                    // (Every quotient takes its own range check: the coefficients of a circular orbit are zero at
+                    // every other order, and a zero next to a regular value must not send both to the true division.)
+                    const double va = nb1_div(a.x, n + 1u, n1, r1); // v^[n+1]
+                    const double vb = nb1_div(a.y, n + 2u, n2, r2); // v^[n+2]
+                    const double xa = nb1_div(va, n + 2u, n2, r2);  // x^[n+2]
+                    const double xb = nb1_div(vb, n + 3u, n3, r3);  // x^[n+3]
                     vp[(side * 3 + k) * 32] = va;
                     if (two) {
                         vp[SO + (side * 3 + k) * 32] = vb;
@@ -298,13 +292,24 @@ __global__ void __launch_bounds__(MAXT, 1) k_nb1(program P, nb_dev_plan NP, batc
                     rv[k] = stored ? c[k][static_cast<std::size_t>(p - 1u) * SO] : 0.;
                     rx[k] = 0.;
                 }
+                // (The loads of the next order are issued before the arithmetic of the current one.)
+                double wn[3];
+#pragma unroll
+                for (std::uint32_t k = 0; k < 3u; ++k) {
+                    wn[k] = stored ? c[k][static_cast<std::size_t>(p - 2u) * SO] : 0.; // V(p - 1)
+                }
                 for (std::uint32_t o = p; o >= 2u; --o) {
                     const double od = static_cast<double>(o), ro = nbk::lds1(rcp_a + o * 8u);
+                    double w[3];
 #pragma unroll
                     for (std::uint32_t k = 0; k < 3u; ++k) {
-                        const double w = stored ? c[k][static_cast<std::size_t>(o - 2u) * SO] : 0.; // V(o - 1)
-                        const double xo = nb1_div(w, o, od, ro);
-                        rv[k] = ::fma(rv[k], h, w);
+                        w[k] = wn[k];
+                        wn[k] = (stored && o > 2u) ? c[k][static_cast<std::size_t>(o - 3u) * SO] : 0.; // V(o - 2)
+                    }
+#pragma unroll
+                    for (std::uint32_t k = 0; k < 3u; ++k) {
+                        const double xo = nb1_div(w[k], o, od, ro);
+                        rv[k] = ::fma(rv[k], h, w[k]);
                         rx[k] = o == p ? xo : ::fma(rx[k], h, xo);
                     }
                 }
