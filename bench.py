@@ -43,6 +43,7 @@ def parse_args():
     ap.add_argument("--perturb", type=float, default=1e-3)
     ap.add_argument("--cpu-lanes", type=int, default=0, help="lanes of the CPU sample (0 = auto)")
     ap.add_argument("--no-cpp-e2e", action="store_true", help="skip the leg through the drop-in C++ class")
+    ap.add_argument("--e2e-sub", type=int, default=1, help="sub-batches the end-to-end leg pipelines through the GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--tape", default="auto", choices=["auto", "hbm", "smem", "smem-notmem", "global", "global-cta", "nbody", "nbody-cta"])
     ap.add_argument("--lanes-per-warp", type=int, default=0)
@@ -391,13 +392,16 @@ def main():
     h2d = state_bytes + 3 * 8 * n
     d2h = state_bytes + 3 * 8 * n + 4 * 8 * n
 
+    # One call of the host-buffer entry point (hy_batch_propagate_until_host) on a batch made of E2E_SUB sub-batches on
+    # this GPU (the same device listed E2E_SUB times): every sub-batch uploads, runs and downloads on its own stream, so
+    # the transfers of one overlap the kernels of the others. Same lanes, same work as the device-timed leg.
+    b2 = hb.Batch(P, n, device=[local_rank] * args.e2e_sub) if args.e2e_sub > 1 else b
+
     def e2e_step():
-        hb.check(hb.lib.hy_batch_upload(b._h, dp(h_state), None, dp(h_zero), dp(h_zero)))
-        hb.check(hb.lib.hy_batch_propagate_until(b._h, dp(h_tf), None, None, 0, 0))
-        hb.check(hb.lib.hy_batch_download(b._h, dp(h_out), dp(h_thi), dp(h_tlo), dp(h_lasth)))
-        hb.check(hb.lib.hy_batch_download_prop_res(b._h, C.cast(C.c_void_p(h_oc.data_ptr()), C.POINTER(C.c_int64)),
-                                                   dp(h_mn), dp(h_mx),
-                                                   C.cast(C.c_void_p(h_ns.data_ptr()), C.POINTER(C.c_uint64))))
+        hb.check(hb.lib.hy_batch_propagate_until_host(
+            b2._h, dp(h_state), None, dp(h_zero), dp(h_zero), dp(h_tf), None, None, 0, dp(h_out), dp(h_thi), dp(h_tlo),
+            dp(h_lasth), C.cast(C.c_void_p(h_oc.data_ptr()), C.POINTER(C.c_int64)), dp(h_mn), dp(h_mx),
+            C.cast(C.c_void_p(h_ns.data_ptr()), C.POINTER(C.c_uint64))))
 
     e2e_step()
     sync_all()
@@ -471,7 +475,8 @@ def main():
                          "model_flops_per_lane_step": costs["flops"],
                          "fp64_tflops_model": fp64_model},
             "e2e": {"value": e2e_val, "unit": "lane-steps/s", "h2d_bytes_per_step": h2d * world,
-                    "d2h_bytes_per_step": d2h * world, "ms_per_step": e2e_ms / n_e2e},
+                    "d2h_bytes_per_step": d2h * world, "ms_per_step": e2e_ms / n_e2e,
+                    "call": "hy_batch_propagate_until_host", "sub_batches_per_gpu": args.e2e_sub},
             "gpu_launches": launches_all,
             "clocks": clocks,
         }

@@ -397,6 +397,24 @@ class Batch:
         th, tl, m = f(t_hi), f(t_lo), f(max_delta_t)
         check(lib.hy_batch_propagate_until(self._h, _dptr(th), _dptr(tl), _dptr(m), int(max_steps), int(write_tc)))
 
+    def propagate_until_host(self, state, t_hi, t_lo, t_final, t_final_lo=None, max_delta_t=None, max_steps=0, pars=None):
+        """hy_batch_propagate_until_host(): upload, propagate, download in one call. state [n_eq, batch], t_hi, t_lo
+        [batch] (C-contiguous float64) are overwritten in place; returns (last_h, outcome, min_h, max_h, n_steps)."""
+        for a in (state, t_hi, t_lo):
+            assert a.dtype == np.float64 and a.flags["C_CONTIGUOUS"]
+        assert state.shape == (self.program.n_eq, self.n) and t_hi.shape == (self.n,) and t_lo.shape == (self.n,)
+        f = lambda a: None if a is None else np.ascontiguousarray(np.broadcast_to(a, (self.n,)), dtype=np.float64)  # noqa
+        tf, tfl, m = f(t_final), f(t_final_lo), f(max_delta_t)
+        pr = None if pars is None else np.ascontiguousarray(pars, dtype=np.float64)
+        last_h, mn, mx = np.empty(self.n), np.empty(self.n), np.empty(self.n)
+        oc, ns = np.empty(self.n, dtype=np.int64), np.empty(self.n, dtype=np.uint64)
+        check(lib.hy_batch_propagate_until_host(self._h, _dptr(state), _dptr(pr), _dptr(t_hi), _dptr(t_lo), _dptr(tf),
+                                                _dptr(tfl), _dptr(m), int(max_steps), _dptr(state), _dptr(t_hi),
+                                                _dptr(t_lo), _dptr(last_h),
+                                                oc.ctypes.data_as(C.POINTER(C.c_int64)), _dptr(mn), _dptr(mx),
+                                                ns.ctypes.data_as(C.POINTER(C.c_uint64))))
+        return last_h, oc, mn, mx, ns
+
     def propagate_until_dev(self, d_t_hi, d_t_lo=0, d_max_delta_t=0, max_steps=0, write_tc=False):
         flag = C.c_int()
         vp = lambda x: C.cast(C.c_void_p(int(x) if x else None), C.POINTER(C.c_double))  # noqa: E731

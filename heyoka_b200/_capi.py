@@ -109,6 +109,8 @@ SIGNATURES = {
     "hy_batch_get_ptrs": (C.c_int, [_vp, C.POINTER(hy_batch_ptrs)]),
     "hy_batch_step": (C.c_int, [_vp, _dp, C.c_int, C.c_int, C.c_int]),
     "hy_batch_propagate_until": (C.c_int, [_vp, _dp, _dp, _dp, C.c_uint64, C.c_int]),
+    "hy_batch_propagate_until_host": (C.c_int, [_vp, _dp, _dp, _dp, _dp, _dp, _dp, _dp, C.c_uint64, _dp, _dp, _dp, _dp,
+                                                C.POINTER(C.c_int64), _dp, _dp, C.POINTER(C.c_uint64)]),
     "hy_batch_propagate_until_dev": (C.c_int, [_vp, _dp, _dp, _dp, C.c_uint64, C.c_int, C.POINTER(C.c_int)]),
     "hy_batch_propagate_grid": (C.c_int, [_vp, _dp, C.c_uint64, _dp, C.c_uint64, _dp]),
     "hy_batch_check_grid": (C.c_int, [_vp, _dp, C.c_uint64, _dp]),

@@ -2163,25 +2163,51 @@ namespace
 {
 
 // The checks of propagate_until_impl() that need the CURRENT times (src/taylor_adaptive_batch.cpp:1212-1273): finite,
-// and final time - current time representable. 16 bytes per lane come back from the device for them.
+// and final time - current time representable (check_prop_times(): 16 bytes per lane come back from the device for them).
+void check_prop_times_host(std::uint32_t n, const double *t_hi, const double *t_lo, const double *tf_hi, const double *tf_lo)
+{
+    for (std::uint32_t i = 0; i < n; ++i) {
+        if (!std::isfinite(t_hi[i]) || !std::isfinite(t_lo[i])) {
+            throw std::invalid_argument("Cannot invoke the propagate_until() function of an adaptive Taylor integrator "
+                                        "in batch mode if one of the current times is not finite");
+        }
+    }
+    for (std::uint32_t i = 0; i < n; ++i) {
+        // (Same arithmetic as the device: Knuth two-sum of the high parts is enough to detect the overflow.)
+        const double rem = tf_hi[i] - t_hi[i] + ((tf_lo != nullptr ? tf_lo[i] : 0.) - t_lo[i]);
+        if (!std::isfinite(rem)) {
+            throw std::invalid_argument("The final time passed to the propagate_until() function of an adaptive Taylor "
+                                        "integrator in batch mode results in an overflow condition");
+        }
+    }
+}
+
 void check_prop_times(hy_batch *b, const double *tf_hi, const double *tf_lo)
 {
     std::vector<double> t_hi(b->n), t_lo(b->n);
     if (hy_batch_download(b, nullptr, t_hi.data(), t_lo.data(), nullptr) != HY_OK) {
         throw cuda_error(hy_last_error());
     }
-    for (std::uint32_t i = 0; i < b->n; ++i) {
-        if (!std::isfinite(t_hi[i]) || !std::isfinite(t_lo[i])) {
-            throw std::invalid_argument("Cannot invoke the propagate_until() function of an adaptive Taylor integrator "
-                                        "in batch mode if one of the current times is not finite");
+    check_prop_times_host(b->n, t_hi.data(), t_lo.data(), tf_hi, tf_lo);
+}
+
+// Argument checks of propagate_until_impl(), src/taylor_adaptive_batch.cpp:1212-1241.
+void check_prop_args(std::uint32_t n, const double *t_final_hi, const double *t_final_lo, const double *max_delta_t)
+{
+    for (std::uint32_t i = 0; i < n; ++i) {
+        if (!std::isfinite(t_final_hi[i]) || (t_final_lo != nullptr && !std::isfinite(t_final_lo[i]))) {
+            throw std::invalid_argument("A non-finite time was passed to the propagate_until() function of an "
+                                        "adaptive Taylor integrator in batch mode");
         }
-    }
-    for (std::uint32_t i = 0; i < b->n; ++i) {
-        // (Same arithmetic as the device: Knuth two-sum of the high parts is enough to detect the overflow.)
-        const double rem = tf_hi[i] - t_hi[i] + ((tf_lo != nullptr ? tf_lo[i] : 0.) - t_lo[i]);
-        if (!std::isfinite(rem)) {
-            throw std::invalid_argument("The final time passed to the propagate_until() function of an adaptive Taylor "
-                                        "integrator in batch mode results in an overflow condition");
+        if (max_delta_t != nullptr) {
+            if (std::isnan(max_delta_t[i])) {
+                throw std::invalid_argument("A nan max_delta_t was passed to the propagate_until() function of an "
+                                            "adaptive Taylor integrator in batch mode");
+            }
+            if (max_delta_t[i] <= 0) {
+                throw std::invalid_argument("A non-positive max_delta_t was passed to the propagate_until() "
+                                            "function of an adaptive Taylor integrator in batch mode");
+            }
         }
     }
 }
@@ -2200,23 +2226,7 @@ int hy_batch_propagate_until(hy_batch *b, const double *t_final_hi, const double
         if (t_final_hi == nullptr) {
             throw std::invalid_argument("Null final times passed to hy_batch_propagate_until()");
         }
-        // Argument checks of propagate_until_impl(), src/taylor_adaptive_batch.cpp:1212-1241.
-        for (std::uint32_t i = 0; i < b->n; ++i) {
-            if (!std::isfinite(t_final_hi[i]) || (t_final_lo != nullptr && !std::isfinite(t_final_lo[i]))) {
-                throw std::invalid_argument("A non-finite time was passed to the propagate_until() function of an "
-                                            "adaptive Taylor integrator in batch mode");
-            }
-            if (max_delta_t != nullptr) {
-                if (std::isnan(max_delta_t[i])) {
-                    throw std::invalid_argument("A nan max_delta_t was passed to the propagate_until() function of an "
-                                                "adaptive Taylor integrator in batch mode");
-                }
-                if (max_delta_t[i] <= 0) {
-                    throw std::invalid_argument("A non-positive max_delta_t was passed to the propagate_until() "
-                                                "function of an adaptive Taylor integrator in batch mode");
-                }
-            }
-        }
+        check_prop_args(b->n, t_final_hi, t_final_lo, max_delta_t);
         check_prop_times(b, t_final_hi, t_final_lo);
         if (!b->shards.empty()) {
             return multi_propagate(b, t_final_hi, t_final_lo, max_delta_t, max_steps, write_tc);
@@ -2225,6 +2235,96 @@ int hy_batch_propagate_until(hy_batch *b, const double *t_final_hi, const double
         const double *d_lo = stage(b, t_final_lo, 0, 1);
         const double *d_mdt = stage(b, max_delta_t, 0, 2);
         return propagate_impl(b, d_hi, d_lo, d_mdt, max_steps, write_tc, nullptr);
+    } catch (...) {
+        return translate_exception();
+    }
+}
+
+// propagate_until() on HOST buffers in one call: upload of state / parameters / times, propagation, download of state,
+// times, last_h and the per-lane results (the outputs may alias the inputs). On a batch made of shards (hy_batch_create_multi(): several devices, or the
+// SAME device listed several times) every shard runs its copies and its kernel on its own stream from its own host
+// thread: with k shards on one device the copies of a shard overlap the kernels of the others, and only 1 / k of the
+// transfers stays exposed. The checks on the current times are done on the caller's arrays (no read-back), the state is
+// downloaded right after the shard's kernel; only last_h (and the outcomes, if the iteration limit was hit) wait for the
+// global exits across the shards.
+int hy_batch_propagate_until_host(hy_batch *b, const double *state_in, const double *pars, const double *t_hi_in,
+                                  const double *t_lo_in, const double *t_final_hi, const double *t_final_lo,
+                                  const double *max_delta_t, uint64_t max_steps, double *state, double *t_hi, double *t_lo,
+                                  double *last_h, int64_t *outcome, double *min_h, double *max_h, uint64_t *n_steps)
+{
+    try {
+        if (b == nullptr || state_in == nullptr || t_hi_in == nullptr || t_lo_in == nullptr || t_final_hi == nullptr) {
+            throw std::invalid_argument("Null pointer passed to hy_batch_propagate_until_host()");
+        }
+        if (b->n_ev != 0u) {
+            throw hy::detail::not_implemented_error("A batch with event equations is propagated by the front end's lock-step "
+                                                    "loop over hy_batch_step(), not by the device-resident propagation");
+        }
+        device_guard guard(b->device);
+        check_prop_args(b->n, t_final_hi, t_final_lo, max_delta_t);
+        check_prop_times_host(b->n, t_hi_in, t_lo_in, t_final_hi, t_final_lo);
+        const bool multi = !b->shards.empty();
+        const std::size_t ns = multi ? b->shards.size() : 1u, pitch = b->n;
+        std::vector<prop_ctx> ctx(ns);
+        const auto shard = [&](std::size_t i) { return multi ? b->shards[i] : b; };
+        const auto offset = [&](std::size_t i) { return multi ? static_cast<std::size_t>(b->shard_off[i]) : std::size_t(0); };
+        const auto each = [&](auto &&fn) {
+            if (multi) {
+                for_each_shard(b, fn);
+            } else {
+                fn(b, std::size_t(0));
+            }
+        };
+        const auto download_main = [&](hy_batch *sh, std::size_t off) {
+            rows_d2h(sh, state, sh->d_state, sh->n_eq, pitch, off);
+            rows_d2h(sh, t_hi, sh->d_t_hi, 1u, pitch, off);
+            rows_d2h(sh, t_lo, sh->d_t_lo, 1u, pitch, off);
+            rows_d2h(sh, reinterpret_cast<long long *>(outcome), sh->d_prop_outcome, 1u, pitch, off);
+            rows_d2h(sh, min_h, sh->d_prop_min_h, 1u, pitch, off);
+            rows_d2h(sh, max_h, sh->d_prop_max_h, 1u, pitch, off);
+            rows_d2h(sh, reinterpret_cast<unsigned long long *>(n_steps), sh->d_prop_n_steps, 1u, pitch, off);
+        };
+        each([&](hy_batch *sh, std::size_t i) {
+            const std::size_t off = offset(i);
+            rows_h2d(sh, sh->d_state, state_in, sh->n_eq, pitch, off);
+            rows_h2d(sh, sh->d_pars, pars, sh->n_pars, pitch, off);
+            rows_h2d(sh, sh->d_t_hi, t_hi_in, 1u, pitch, off);
+            rows_h2d(sh, sh->d_t_lo, t_lo_in, 1u, pitch, off);
+            const double *d_hi = stage(sh, t_final_hi + off, 0, 0);
+            const double *d_lo = stage(sh, t_final_lo != nullptr ? t_final_lo + off : nullptr, 0, 1);
+            const double *d_mdt = stage(sh, max_delta_t != nullptr ? max_delta_t + off : nullptr, 0, 2);
+            propagate_phase1(sh, d_hi, d_lo, d_mdt, max_steps, 0, ctx[i]);
+            // (Speculative: a non-finite lane anywhere makes every shard run again, see below.)
+            download_main(sh, off);
+        });
+        bool any_nf = false, any_limit = false;
+        unsigned long long cap = ~0ull, loop_len = 0;
+        for (const auto &c : ctx) {
+            if (c.fl.any_nf != 0u) {
+                any_nf = true;
+                cap = std::min(cap, c.fl.min_nf_iter);
+            }
+        }
+        if (any_nf) {
+            each([&](hy_batch *sh, std::size_t i) {
+                HY_CUDA_CHECK(cudaStreamSynchronize(sh->stream));
+                propagate_replay(sh, ctx[i], cap);
+            });
+        }
+        for (const auto &c : ctx) {
+            any_limit = any_limit || c.fl.any_limit != 0u;
+            loop_len = std::max(loop_len, c.fl.max_iter);
+        }
+        each([&](hy_batch *sh, std::size_t i) {
+            const std::size_t off = offset(i);
+            propagate_finish(sh, any_nf, any_limit, loop_len, 0);
+            if (any_nf || any_limit) {
+                download_main(sh, off);
+            }
+            rows_d2h(sh, last_h, sh->d_last_h, 1u, pitch, off);
+            HY_CUDA_CHECK(cudaStreamSynchronize(sh->stream));
+        });
+        return HY_OK;
     } catch (...) {
         return translate_exception();
     }

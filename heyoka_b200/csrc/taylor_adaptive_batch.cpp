@@ -1273,6 +1273,22 @@ taylor_adaptive_batch<double>::propagate_until_impl(const std::vector<double> &h
         return {std::move(ret), std::move(o.cb)};
     }
 
+    if (!o.cb && !with_events() && !m.lazy && !o.write_tc) {
+        // Fast path, strict synchronisation: one call uploads the mirrors, runs the whole loop on the device and
+        // brings state, times, last_h and the per-lane results back (no intermediate read-backs).
+        check(hy_batch_propagate_until_host(m.batch, m.state.data(), m.n_pars != 0u ? m.pars.data() : nullptr,
+                                            m.time_hi.data(), m.time_lo.data(), hi.data(), lo.data(), mdt, o.max_steps,
+                                            m.state.data(), m.time_hi.data(), m.time_lo.data(), m.last_h.data(),
+                                            m.oc.data(), m.tmp_a.data(), m.tmp_b.data(), m.tmp_n.data()));
+        for (std::uint32_t i = 0; i < n; ++i) {
+            m.prop_res[i] = std::tuple{static_cast<taylor_outcome>(m.oc[i]), m.tmp_a[i], m.tmp_b[i],
+                                       static_cast<std::size_t>(m.tmp_n[i])};
+        }
+        m.host_new_state = m.host_new_pars = m.host_new_time = false;
+        m.dev_new_state = m.dev_new_time = m.dev_new_prop = false;
+        return {std::nullopt, std::move(o.cb)};
+    }
+
     if (!o.cb && !with_events()) {
         // Fast path: the whole loop runs on the device.
         m.push();

@@ -263,6 +263,20 @@ int hy_batch_propagate_until(hy_batch *, const double *t_final_hi, const double 
 int hy_batch_propagate_until_dev(hy_batch *, const double *d_t_final_hi, const double *d_t_final_lo,
                                  const double *d_max_delta_t, uint64_t max_steps, int write_tc, int *any_nf_or_limit);
 
+/* propagate_until() on HOST buffers in one call - what a caller holding std::vector mirrors does with hy_batch_upload(),
+ * hy_batch_propagate_until(), hy_batch_download() and hy_batch_download_prop_res(): state_in [n_eq][batch], t_hi_in,
+ * t_lo_in [batch] are uploaded (pars may be NULL: unchanged); state, t_hi, t_lo, last_h, outcome, min_h, max_h, n_steps
+ * receive the results (NULL = not wanted; the outputs may alias the inputs). Taylor coefficients are not written
+ * (write_tc = 0). On a batch created by hy_batch_create_multi() every shard runs its transfers and its kernel on its
+ * own stream from its own host thread; listing the SAME device k times pipelines the batch through that device in k
+ * sub-batches (the copies of one overlap the kernels of the others). Page-lock the arrays (hy_host_pin()) for the
+ * copies to be asynchronous. Replaces the host-vector path of taylor_adaptive_batch::propagate_until(),
+ * src/taylor_adaptive_batch.cpp:1136-1534. */
+int hy_batch_propagate_until_host(hy_batch *, const double *state_in, const double *pars, const double *t_hi_in,
+                                  const double *t_lo_in, const double *t_final_hi, const double *t_final_lo,
+                                  const double *max_delta_t, uint64_t max_steps, double *state, double *t_hi, double *t_lo,
+                                  double *last_h, int64_t *outcome, double *min_h, double *max_h, uint64_t *n_steps);
+
 /* propagate_grid() (src/taylor_adaptive_batch.cpp:1545-2055): dense-output sampling on per-lane time grids.
  * grid[k * batch + lane], k < n_pts: finite, strictly monotonic with the same direction in every lane, and
  * grid[lane] == current time (hi part) of the lane. out[(k * n_eq + var) * batch + lane] receives the state at

@@ -109,3 +109,50 @@ def test_sharded_with_parameters_and_time():
     assert one.propagate_res == many.propagate_res
     with pytest.raises(NotImplementedError, match="multi-device"):
         many.propagate_grid(np.array([many.time, many.time + 1.0]))
+
+
+@pytest.mark.parametrize("devs", [None, [0, 0, 0]] + ([[0, 1]] if hb.lib.hy_device_count() >= 2 else []))
+def test_propagate_until_host_one_call(devs):
+    """hy_batch_propagate_until_host(): upload + propagate_until + downloads in one call, on one device, on one device in
+    three pipelined sub-batches (the same device listed three times) and on two devices: bit-identical to the separate
+    calls on a plain batch, global exits included (a non-finite lane in one shard stops the lanes of the others at
+    the same iteration; the iteration limit turns every outcome into step_limit), and the reference's errors on the
+    times."""
+    batch = 50
+    st = outer_ss_batch_state(batch)
+    P = hb.Program(sys_outer_ss(), high_accuracy=True)
+    tf = np.linspace(3., 30., batch)
+
+    def plain(st0, tf_, **kw):
+        b = hb.Batch(P, batch)
+        z = np.zeros(batch)
+        b.upload(st0, None, z, z)
+        b.propagate_until(tf_, **kw)
+        return b.download() + tuple(b.prop_res())
+
+    def fused(st0, tf_, **kw):
+        b = hb.Batch(P, batch) if devs is None else hb.Batch(P, batch, device=devs)
+        assert b.n_shards == (0 if devs is None else len(devs))
+        s, th, tl = st0.copy(), np.zeros(batch), np.zeros(batch)
+        last_h, oc, mn, mx, ns = b.propagate_until_host(s, th, tl, tf_, **kw)
+        return (s, th, tl, last_h, oc, mn, mx, ns)
+
+    def same(a, b):
+        for x, y in zip(a, b):
+            assert np.array_equal(np.asarray(x), np.asarray(y), equal_nan=True)
+
+    same(plain(st, tf), fused(st, tf))
+    same(plain(st, tf, max_delta_t=np.full(batch, 0.11)), fused(st, tf, max_delta_t=np.full(batch, 0.11)))
+    same(plain(st, tf, max_steps=7), fused(st, tf, max_steps=7))  # iteration limit
+    bad = st.copy()
+    bad[0:3, 41] = bad[6:9, 41]  # two bodies on top of each other: lane 41 goes non-finite at its first step
+    ref, got = plain(bad, tf), fused(bad, tf)
+    assert ref[4][41] == hb.taylor_outcome.err_nf_state
+    same(ref[1:], got[1:])
+    ok = np.arange(batch) != 41
+    assert np.array_equal(ref[0][:, ok], got[0][:, ok])
+    b = hb.Batch(P, batch) if devs is None else hb.Batch(P, batch, device=devs)
+    with pytest.raises(ValueError, match="one of the current times is not finite"):
+        b.propagate_until_host(st.copy(), np.full(batch, np.inf), np.zeros(batch), tf)
+    with pytest.raises(ValueError, match="non-finite time was passed"):
+        b.propagate_until_host(st.copy(), np.zeros(batch), np.zeros(batch), np.full(batch, np.nan))
