@@ -958,7 +958,7 @@ bool hy_batch::setup_nn()
     }
     dev::nn_dev_plan d{};
     std::vector<double> img;
-    std::uint32_t hist = 0, max_out = 0;
+    std::uint32_t hist = 0, max_out = 0, n_hidden = 0;
     d.n_layers = static_cast<std::uint32_t>(nnp.layers.size());
     for (std::uint32_t l = 0; l < d.n_layers; ++l) {
         const auto &L = nnp.layers[l];
@@ -984,9 +984,16 @@ bool hy_batch::setup_nn()
         img.resize((img.size() + 1u) & ~std::size_t(1), 0.);
         d.hist_off[l] = hist;
         if (L.act != 0) {
-            hist += 3u * order * L.n_out * dev::NN_LB;
+            hist += 2u * order * L.n_out * dev::NN_LB; // z and the activation (its square lives in tensor memory)
+            d.tm_slot[l] = n_hidden++;
+            d.tm_ipt = std::max(d.tm_ipt, (L.n_out * dev::NN_LB + dev::NN_THREADS - 1u) / dev::NN_THREADS);
         }
         max_out = std::max(max_out, L.n_out);
+    }
+    // Tensor memory: 32 columns per (neuron, lane) item and hidden layer, 256 columns per thread, orders up to 15 (the
+    // history is read back in two loads of eight orders).
+    if (n_hidden * d.tm_ipt * 32u > 256u || order > 16u) {
+        return false;
     }
     d.wimg_doubles = static_cast<std::uint32_t>(img.size());
     d.hist_doubles = hist;
