@@ -75,6 +75,27 @@ def main():
     if "s6step" in which:
         run("outer_ss 6-body 2^20 lanes, one step", hb.Program(sys_outer_ss(), high_accuracy=True),
             outer_ss_batch_state(1 << 20))
+    if "grid" in which:
+        # propagate_grid(): the 6-body system sampled on 1000 grid points per lane over 20 yr (the dense output of
+        # every step goes to a [n_pts][n_eq][batch] array: this one is bandwidth work).
+        batch, n_pts = 16384, 1000
+        st = outer_ss_batch_state(batch)
+        b = hb.Batch(hb.Program(sys_outer_ss(), high_accuracy=True), batch)
+        z = np.zeros(batch)
+        grid = np.ascontiguousarray(np.linspace(0., 20., n_pts)[:, None] * np.ones(batch)[None, :])
+        best = None
+        for _ in range(2):
+            b.upload(st, None, z, z)
+            b.sync()
+            t0 = time.perf_counter()
+            out = b.propagate_grid(grid)
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+        assert np.all(np.isfinite(out)) and np.array_equal(out[0], st)
+        print(json.dumps({"config": "outer_ss 6-body propagate_grid, %d lanes x %d grid points over 20 yr" % (batch, n_pts),
+                          "lanes": batch, "kernel": b.kernel_info()["tape"], "seconds": best,
+                          "lane_steps": int(b.prop_res()[3].sum()), "output_bytes": int(out.nbytes),
+                          "output_gbs_incl_d2h": out.nbytes / best / 1e9}), flush=True)
     if "n32" in which:
         st = nbody32_batch_state(8192)
         run("nbody N=32, 8192 lanes, propagate_until(1)", hb.Program(sys_nbody32()), st, 1.0)
