@@ -372,6 +372,13 @@ def main():
     sync_all()
     elapsed_ms = ev0.elapsed_time(ev1)
     lane_steps_rank = int(t_nsteps.sum().item())  # of one bench step (every step repeats the same work)
+    if world > 1:
+        # The gathered result (after the timed region): every rank's block of the final times is t_final, every state is
+        # finite, and this rank's block of the gather is what this rank computed.
+        g = gather_buf.view(world, -1)
+        assert bool(torch.isfinite(g[:, :P.n_eq * n]).all()), "non-finite state in the gathered result"
+        assert bool((g[:, P.n_eq * n:(P.n_eq + 1) * n] == args.tfinal).all()), "a gathered lane is not at t_final"
+        assert bool(torch.equal(g[rank, :P.n_eq * n], t_state)), "the gathered block differs from the local state"
     launches = b.launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
 

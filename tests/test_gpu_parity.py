@@ -202,6 +202,25 @@ def test_propagate_parity_outer_ss(kernel, ha):
     assert nbody_rel_err(ta.state, st) < 1e-11
 
 
+@pytest.mark.parametrize("mode", ["pairwise", "seq"])
+def test_propagate_parity_reference_default_mode(mode):
+    """The reference's DEFAULT (non-compact) mode sums pairwise, its compact mode sequentially without contraction; the
+    kernels sum sequentially with fused multiply-adds (the third oracle mode, which every other test compares against).
+    Here the GPU meets the other two restatements directly: 64 lanes of the perturbed outer Solar System over 100 years
+    and the two-body problem over 40 time units - identical step counts, final states to 1e-11 (a few hundred steps of
+    reordered sums: the reference's own compact-vs-default tests use 100-1000 eps per step)."""
+    m = oracle.PAIRWISE if mode == "pairwise" else oracle.SEQ
+    for sys_, st, tf, ha in ((sys_outer_ss(), outer_ss_batch_state(64, seed=9), 100., True),
+                             (sys_two_body(), two_body_batch_state(64, seed=3), 40., False)):
+        P = hb.Program(sys_, high_accuracy=ha)
+        o = oracle.OracleIntegrator(P, st, 64, mode=m)
+        ta = hb.taylor_adaptive_batch(sys_, st, 64, high_accuracy=ha)
+        o.propagate_until(tf, lockstep=False)
+        ta.propagate_until(tf)
+        assert [r[3] for r in ta.propagate_res] == [int(x) for x in o.n_steps]
+        assert lane_err(ta.state, o.state) < 1e-11
+
+
 def test_propagate_exact_step_counts_gpu(kernel):
     """test/taylor_adaptive_batch.cpp:586-598 on the GPU."""
     ta = hb.taylor_adaptive_batch(sys_pendulum(), [[0.05, 0.06], [0.025, 0.026]], 2, kernel=kernel)

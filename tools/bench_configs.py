@@ -72,6 +72,10 @@ def main():
                    dict(block_threads=256, lanes_per_thread=2), dict(block_threads=512, lanes_per_thread=2)):
             run("two_body_step_batch 2^22 lanes, one step, k_nb1 %r" % (kw,), hb.Program(sys_two_body()),
                 two_body_batch_state(1 << 22), tape="nbody-lane", **kw)
+    if "s6long" in which:
+        # Long horizon: 1000 yr, ~1370 steps per lane (the bench step propagates 20 yr, ~27 steps).
+        run("outer_ss 6-body 262144 lanes, propagate_until(1000 yr)", hb.Program(sys_outer_ss(), high_accuracy=True),
+            outer_ss_batch_state(1 << 18, perturb=1e-3), 1000.0)
     if "s6step" in which:
         run("outer_ss 6-body 2^20 lanes, one step", hb.Program(sys_outer_ss(), high_accuracy=True),
             outer_ss_batch_state(1 << 20))
