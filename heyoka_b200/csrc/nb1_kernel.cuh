@@ -308,7 +308,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_nb1(program P, nb_dev_plan NP, batc
                     }
 #pragma unroll
                     for (std::uint32_t k = 0; k < 3u; ++k) {
-                        const double xo = nb1_div(w[k], o, od, ro);
+                        const double xo = stored ? nb1_div(w[k], o, od, ro) : 0.; // (0 / o = 0: no division)
                         rv[k] = ::fma(rv[k], h, w[k]);
                         rx[k] = o == p ? xo : ::fma(rx[k], h, xo);
                     }
@@ -332,7 +332,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_nb1(program P, nb_dev_plan NP, batc
 #pragma unroll
                     for (std::uint32_t k = 0; k < 3u; ++k) {
                         const double cv_ = stored ? c[k][static_cast<std::size_t>(o - 1u) * SO] : 0.; // V(o)
-                        const double cx_ = nb1_div(prev[k], o, od, ro);                               // x^[o]
+                        const double cx_ = (stored || o == 1u) ? nb1_div(prev[k], o, od, ro) : 0.;    // x^[o]
                         prev[k] = cv_;
                         {
                             const double tmp = __dmul_rn(cv_, cur_h);
