@@ -11,12 +11,13 @@
 //   * the six positions of the current order pair, the outputs m_k / n_k of the pair interaction (nb_core.hpp's
 //     pair_block() with a register policy), v^[n+1] = a^[n] / (n + 1), x^[n+2] = v^[n+1] / (n + 2) in straight-line code;
 //   * its history rows d_0, d_1 in shared memory and r^2, d_2, r^alpha in tensor memory, exactly as in k_nb;
-//   * of the state variables' coefficients only the velocities' orders 1..p are kept, in a private per-warp store
-//     [order][slot][32 lanes] with compile-time strides (one store instruction per coefficient, 256-byte rows, 0.5 KB
-//     per lane of the two-body benchmark: the stores of all resident warps stay in L2). The positions' coefficients are
-//     their quotients x^[o] = v^[o-1] / o, recomputed (correctly rounded either way) where they are needed again: the
-//     step-size norms, the state update, the public tc array when the caller asks for it. A body that nothing pulls
-//     on (right-hand side 0) stores nothing: its velocity row is (v_0, 0, 0, ...).
+//   * the state variables' coefficients (velocities: orders 1..p, positions: 2..p; the lower ones are the state) go to
+//     a private per-warp store [order][slot][32 lanes] with compile-time strides (one store instruction per
+//     coefficient, 256-byte rows, 1 KB per lane of the two-body benchmark: the stores of all resident warps, 54 MB, stay in
+//     L2), read back for the step-size norms, the state update and the public tc array when the caller asks for it.
+//     A body that nothing pulls on (right-hand side 0) stores nothing: its rows are (v_0, 0, ...), (x_0, v_0, 0, ...).
+//     (HY_NB1_STORE_X=0: only the velocities are stored and the positions' coefficients x^[o] = v^[o-1] / o are
+//     recomputed - correctly rounded either way, hence identical - where they are needed again.)
 // No exchange between threads; a __syncwarp() per order pair only keeps the warp converged for the tensor-memory
 // accesses. Same arithmetic, same order of operations as k_nb / k_coop: bit-identical results (tests/test_gpu_parity.py
 // runs both on the same inputs).
@@ -86,7 +87,14 @@ __global__ void __launch_bounds__(MAXT, 1) k_nb1(program P, nb_dev_plan NP, batc
 {
     using nb::d2;
     extern __shared__ __align__(16) double smem_raw[];
-    constexpr std::uint32_t SO = 6u * 32u; // doubles per order of the private store: [order - 1][slot][lane]
+#if !defined(HY_NB1_STORE_X)
+#define HY_NB1_STORE_X 1
+#endif
+    // SX: the positions' coefficients (orders 2..p) are stored next to the velocities' instead of being recomputed where
+    // they are needed again (1 KB per lane instead of 0.5 KB, 60 quotients per lane-step less).
+    constexpr bool SX = HY_NB1_STORE_X != 0;
+    constexpr std::uint32_t SO = (SX ? 12u : 6u) * 32u; // doubles per order of the private store: [order - 1][slot][lane]
+    constexpr std::uint32_t XO = 6u * 32u;              // X(o, s) at cb[(o - 1) * SO + XO + s * 32] (SX)
 
     // ---- CTA-shared tables: fac | rcp ----
     const std::uint32_t p = P.order;
@@ -203,6 +211,12 @@ __global__ void __launch_bounds__(MAXT, 1) k_nb1(program P, nb_dev_plan NP, batc
                     vp[(side * 3 + k) * 32] = va;
                     if (two) {
                         vp[SO + (side * 3 + k) * 32] = vb;
+                        if constexpr (SX) {
+                            vp[SO + XO + (side * 3 + k) * 32] = xa;
+                            if (n + 3u <= p) {
+                                vp[2u * SO + XO + (side * 3 + k) * 32] = xb;
+                            }
+                        }
                     }
                     (side == 0 ? PM.xa[k] : PM.xb[k]) = d2{xa, xb};
                 }
@@ -229,8 +243,16 @@ __global__ void __launch_bounds__(MAXT, 1) k_nb1(program P, nb_dev_plan NP, batc
             for (std::uint32_t k = 0; k < 3u; ++k) {
                 const std::uint32_t s = side * 3u + k;
                 const double *c = top + s * 32u;
-                const double vp_ = c[0], vp1_ = *(c - SO), vp2_ = *(c - 2u * SO);
-                const double xp_ = nb1_div(vp1_, p, pd, rp), xp1_ = nb1_div(vp2_, p - 1u, pd1, rp1);
+                const double vp_ = c[0], vp1_ = *(c - SO);
+                double xp_, xp1_;
+                if constexpr (SX) {
+                    xp_ = c[XO];
+                    xp1_ = *(c + XO - SO);
+                } else {
+                    const double vp2_ = *(c - 2u * SO);
+                    xp_ = nb1_div(vp1_, p, pd, rp);
+                    xp1_ = nb1_div(vp2_, p - 1u, pd1, rp1);
+                }
                 nb1_track(mp, vp_);
                 nb1_track(mp, xp_);
                 nb1_track(mp1, vp1_);
@@ -262,7 +284,11 @@ __global__ void __launch_bounds__(MAXT, 1) k_nb1(program P, nb_dev_plan NP, batc
             for (std::uint32_t o = 1; o <= p; ++o) {
                 const double cur = stored ? c[static_cast<std::size_t>(o - 1u) * SO] : 0.;
                 tv[o * so] = cur;
-                tx[o * so] = nb1_div(prev, o, static_cast<double>(o), nbk::lds1(rcp_a + o * 8u));
+                if (SX && o >= 2u) {
+                    tx[o * so] = stored ? c[static_cast<std::size_t>(o - 1u) * SO + XO] : 0.;
+                } else {
+                    tx[o * so] = nb1_div(prev, o, static_cast<double>(o), nbk::lds1(rcp_a + o * 8u));
+                }
                 prev = cur;
             }
         }
@@ -293,22 +319,26 @@ __global__ void __launch_bounds__(MAXT, 1) k_nb1(program P, nb_dev_plan NP, batc
                     rx[k] = 0.;
                 }
                 // (The loads of the next order are issued before the arithmetic of the current one.)
-                double wn[3];
+                double wn[3], xn[3];
 #pragma unroll
                 for (std::uint32_t k = 0; k < 3u; ++k) {
                     wn[k] = stored ? c[k][static_cast<std::size_t>(p - 2u) * SO] : 0.; // V(p - 1)
+                    xn[k] = (SX && stored) ? c[k][static_cast<std::size_t>(p - 1u) * SO + XO] : 0.; // X(p)
                 }
                 for (std::uint32_t o = p; o >= 2u; --o) {
                     const double od = static_cast<double>(o), ro = nbk::lds1(rcp_a + o * 8u);
-                    double w[3];
+                    double w[3], xw[3];
 #pragma unroll
                     for (std::uint32_t k = 0; k < 3u; ++k) {
                         w[k] = wn[k];
+                        xw[k] = xn[k];
                         wn[k] = (stored && o > 2u) ? c[k][static_cast<std::size_t>(o - 3u) * SO] : 0.; // V(o - 2)
+                        xn[k] = (SX && stored && o > 2u) ? c[k][static_cast<std::size_t>(o - 2u) * SO + XO] : 0.; // X(o - 1)
                     }
 #pragma unroll
                     for (std::uint32_t k = 0; k < 3u; ++k) {
-                        const double xo = stored ? nb1_div(w[k], o, od, ro) : 0.; // (0 / o = 0: no division)
+                        // x^[o]: stored, or V(o - 1) / o (0 / o = 0 without a division)
+                        const double xo = SX ? xw[k] : (stored ? nb1_div(w[k], o, od, ro) : 0.);
                         rv[k] = ::fma(rv[k], h, w[k]);
                         rx[k] = o == p ? xo : ::fma(rx[k], h, xo);
                     }
@@ -332,7 +362,12 @@ __global__ void __launch_bounds__(MAXT, 1) k_nb1(program P, nb_dev_plan NP, batc
 #pragma unroll
                     for (std::uint32_t k = 0; k < 3u; ++k) {
                         const double cv_ = stored ? c[k][static_cast<std::size_t>(o - 1u) * SO] : 0.; // V(o)
-                        const double cx_ = (stored || o == 1u) ? nb1_div(prev[k], o, od, ro) : 0.;    // x^[o]
+                        double cx_; // x^[o]
+                        if (SX && o >= 2u) {
+                            cx_ = stored ? c[k][static_cast<std::size_t>(o - 1u) * SO + XO] : 0.;
+                        } else {
+                            cx_ = (stored || o == 1u) ? nb1_div(prev[k], o, od, ro) : 0.;
+                        }
                         prev[k] = cv_;
                         {
                             const double tmp = __dmul_rn(cv_, cur_h);
