@@ -2555,7 +2555,8 @@ int hy_batch_propagate_grid(hy_batch *b, const double *grid, uint64_t n_pts, con
         };
         HY_CUDA_CHECK(cudaMemsetAsync(d_gflags, 0, sizeof(hflags), b->stream));
         dev::k_grid_init<<<gb, 128, 0, b->stream>>>(b->view(), G, b->d_prop_min_h, b->d_prop_max_h, b->d_prop_n_steps);
-        dev::k_grid_sample<<<gb, 128, 0, b->stream>>>(b->prog, b->view(), G);
+        dev::k_grid_sample<<<dim3(gb, b->n_eq), 128, 0, b->stream>>>(b->prog, b->view(), G);
+        dev::k_grid_advance<<<gb, 128, 0, b->stream>>>(b->view(), G);
         HY_CUDA_CHECK(cudaGetLastError());
         read_flags();
         if (hflags[2] != 0u) {
@@ -2575,7 +2576,8 @@ int hy_batch_propagate_grid(hy_batch *b, const double *grid, uint64_t n_pts, con
             HY_CUDA_CHECK(cudaMemsetAsync(d_gflags, 0, sizeof(unsigned) * 2u, b->stream));
             dev::k_grid_book<<<gb, 128, 0, b->stream>>>(b->view(), G, b->d_prop_outcome, b->d_prop_min_h,
                                                          b->d_prop_max_h, b->d_prop_n_steps);
-            dev::k_grid_sample<<<gb, 128, 0, b->stream>>>(b->prog, b->view(), G);
+            dev::k_grid_sample<<<dim3(gb, b->n_eq), 128, 0, b->stream>>>(b->prog, b->view(), G);
+            dev::k_grid_advance<<<gb, 128, 0, b->stream>>>(b->view(), G);
             HY_CUDA_CHECK(cudaGetLastError());
             read_flags();
             if (hflags[1] != 0u) {

@@ -117,39 +117,66 @@ __global__ void k_grid_book(batch D, grid_state G, long long *outcome, double *m
     outcome[lane] = oc;
 }
 
-// Dense output at every grid point covered by the last step (:1811-1886), then the limit of the next step
-// (:1899-1912). Does nothing if a non-finite state was detected in this iteration.
+// The grid points covered by the last step of a lane (:1811-1886): [first, last) from the lane's cursor, and the start
+// of the step (the Taylor coefficients are centred there).
+struct grid_window {
+    std::uint32_t first, last;
+    dfl start;
+};
+__device__ __forceinline__ grid_window grid_covered(const batch &D, const grid_state &G, std::uint32_t lane)
+{
+    const std::size_t n = D.n;
+    const dfl t{D.t_hi[lane], D.t_lo[lane]};
+    const dfl cmp = dfl_sub(t, dfl{D.last_h[lane], 0.}); // start of the last step
+    const dfl t0 = dfl_lt(cmp, t) ? cmp : t, t1 = dfl_lt(t, cmp) ? cmp : t;
+    const bool rem0 = G.rem_hi[lane] == 0. && G.rem_lo[lane] == 0.;
+    const std::uint32_t first = G.cur_idx[lane];
+    std::uint32_t idx = first;
+    while (idx < G.n_pts) {
+        const dfl g{G.grid[static_cast<std::size_t>(idx) * n + lane], 0.};
+        if (!((!dfl_lt(g, t0) && !dfl_lt(t1, g)) || rem0)) {
+            break;
+        }
+        ++idx;
+    }
+    return grid_window{first, idx, cmp};
+}
+
+// Dense output at every grid point covered by the last step: one thread per (lane, state variable) - blockIdx.y is the
+// state variable - so that the [n_pts][n_eq][batch] output is written by n_eq times as many threads as there are lanes
+// (a lane covers tens of grid points per step when the grid is dense: 36 x 21 coefficients x points per lane are too
+// much serial work for one thread). Reads the cursors only: k_grid_advance() moves them afterwards. Does nothing if a
+// non-finite state was detected in this iteration.
 __global__ void k_grid_sample(program P, batch D, grid_state G)
+{
+    const std::uint32_t lane = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+    if (lane >= D.n || G.flags[1] != 0u) {
+        return;
+    }
+    const std::size_t n = D.n;
+    const grid_window w = grid_covered(D, G, lane);
+    const double *c = D.tc + static_cast<std::size_t>(i) * (P.order + 1u) * n + lane;
+    for (std::uint32_t idx = w.first; idx < w.last; ++idx) {
+        const dfl g{G.grid[static_cast<std::size_t>(idx) * n + lane], 0.};
+        const double tau = dfl_sub(g, w.start).hi;
+        G.out[(static_cast<std::size_t>(idx) * P.n_eq + i) * n + lane]
+            = eval_poly(P, [c, n](std::uint32_t o) { return c[static_cast<std::size_t>(o) * n]; }, tau);
+    }
+}
+
+// The cursors past the grid points k_grid_sample() has written, then the limit of the next step (:1899-1912).
+__global__ void k_grid_advance(batch D, grid_state G)
 {
     const std::uint32_t lane = blockIdx.x * blockDim.x + threadIdx.x;
     if (lane >= D.n || G.flags[1] != 0u) {
         return;
     }
-    const std::size_t n = D.n;
-    const dfl t{D.t_hi[lane], D.t_lo[lane]};
-    const dfl cmp = dfl_sub(t, dfl{D.last_h[lane], 0.}); // start of the last step
-    const dfl t0 = dfl_lt(cmp, t) ? cmp : t, t1 = dfl_lt(t, cmp) ? cmp : t;
-    const dfl rem{G.rem_hi[lane], G.rem_lo[lane]};
-    const bool rem0 = rem.hi == 0. && rem.lo == 0.;
-    std::uint32_t idx = G.cur_idx[lane];
-    while (idx < G.n_pts) {
-        const dfl g{G.grid[static_cast<std::size_t>(idx) * n + lane], 0.};
-        const bool avail = (!dfl_lt(g, t0) && !dfl_lt(t1, g)) || rem0;
-        if (!avail) {
-            break;
-        }
-        const double tau = dfl_sub(g, cmp).hi;
-        for (std::uint32_t i = 0; i < P.n_eq; ++i) {
-            const double *c = D.tc + static_cast<std::size_t>(i) * (P.order + 1u) * n + lane;
-            G.out[(static_cast<std::size_t>(idx) * P.n_eq + i) * n + lane]
-                = eval_poly(P, [c, n](std::uint32_t o) { return c[static_cast<std::size_t>(o) * n]; }, tau);
-        }
-        ++idx;
-    }
-    G.cur_idx[lane] = idx;
-    if (idx < G.n_pts) {
+    const grid_window w = grid_covered(D, G, lane);
+    G.cur_idx[lane] = w.last;
+    if (w.last < G.n_pts) {
         atomicOr(G.flags, 1u);
     }
+    const dfl rem{G.rem_hi[lane], G.rem_lo[lane]};
     const double mdt = G.max_delta_t != nullptr ? G.max_delta_t[lane] : CUDART_INF;
     G.dt_limit[lane] = step_limit(G.t_dir[lane] != 0, rem, mdt);
 }
