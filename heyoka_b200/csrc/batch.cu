@@ -812,7 +812,8 @@ bool hy_batch::setup_nb(int LT, std::uint32_t threads, int want_tmem, int want_c
     const auto team_slots = [&](bool tmem) {
         // (The one-thread-per-lane kernel keeps positions, pair outputs and norms in registers.)
         const std::size_t d = (lane ? 0u : (static_cast<std::size_t>(nbp.n_pos) + nbp.n_out) * LT * 2u)
-                              + static_cast<std::size_t>(tmem ? 2u : 5u) * npp * TT * 2u + (3u + 16u) * LT; // (+ norms, parked bookkeeping)
+                              + static_cast<std::size_t>(tmem ? 2u : 5u) * npp * TT * 2u
+                              + (3u * hy::detail::nb_norm_copies(static_cast<std::uint32_t>(LT)) + 16u) * LT; // (+ norms, parked bookkeeping)
         return static_cast<std::uint32_t>((d + LT - 1u) / LT);
     };
     // Teams (warps) per CTA that fit: shared memory, tensor-memory columns (12 per order pair and thread).
@@ -2273,7 +2274,6 @@ int hy_batch_propagate_until_host(hy_batch *b, const double *state_in, const dou
         const bool multi = !b->shards.empty();
         const std::size_t ns = multi ? b->shards.size() : 1u, pitch = b->n;
         std::vector<prop_ctx> ctx(ns);
-        const auto shard = [&](std::size_t i) { return multi ? b->shards[i] : b; };
         const auto offset = [&](std::size_t i) { return multi ? static_cast<std::size_t>(b->shard_off[i]) : std::size_t(0); };
         const auto each = [&](auto &&fn) {
             if (multi) {

@@ -7,6 +7,17 @@
 namespace heyoka_b200::detail
 {
 
+// Copies of the three step-size norms of a lane that the threads of the summation phase spread their shared-memory
+// atomics over (64-bit maxima on ONE address per lane and norm serialise: 5 % of the 6-body kernel's stall samples); the
+// owner thread takes the maximum of the copies. lt = lanes per team.
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+constexpr std::uint32_t nb_norm_copies(std::uint32_t lt)
+{
+    return lt <= 2u ? 8u : (lt <= 8u ? 2u : 1u);
+}
+
 // One pair interaction (64 bytes, read once per kernel by the thread that owns the pair).
 // d_k = pos[pa[k]] - pos[pb[k]], r2 = sum_sq(d), q = pow(r2, alpha), f = c1 q, m_k = d_k f -> output slot om[k],
 // and, if flags bit 0 is set, n_k = c2[k] m_k -> output slot on[k] (0xffff: that n_k does not exist).

@@ -261,7 +261,7 @@ struct role_mem {
     std::uint32_t pos_b, out_b;   // team bases
     std::uint32_t consts, rcp_;   // CTA tables
     std::uint32_t norms;          // team norms: [3][LT] u64 (|x^[0]|, |x^[p]|, |x^[p-1]|), + lane l0 of this thread
-    std::uint32_t lt8;            // LT * 8: stride between the three norms
+    std::uint32_t lt8;            // copies * LT * 8: stride between the three norms
     const double *state0;         // D.state + first global lane of this thread (clamped)
     std::size_t n_batch;
     double *cbase;                // coefficient store + lane offset of lane 0 of this thread
@@ -378,12 +378,21 @@ static __device__ __noinline__ double nb_step_size(const program &P, unsigned lo
                                                    const double *c, std::size_t off_p, std::size_t off_pm1,
                                                    double max_delta_t)
 {
-    const double m0 = __longlong_as_double(static_cast<long long>(norms[0]));
-    const double mp = __longlong_as_double(static_cast<long long>(norms[lt]));
-    const double mp1 = __longlong_as_double(static_cast<long long>(norms[2u * lt]));
-    norms[0] = 0ull;
-    norms[lt] = 0ull;
-    norms[2u * lt] = 0ull;
+    // norms[(which * copies + r) * lt]: the maximum over the copies, which are reset.
+    const std::uint32_t copies = detail::nb_norm_copies(lt);
+    unsigned long long n3[3];
+    for (std::uint32_t w = 0; w < 3u; ++w) {
+        unsigned long long v = 0ull;
+        for (std::uint32_t r = 0; r < copies; ++r) {
+            unsigned long long *q = norms + (w * copies + r) * lt;
+            v = *q > v ? *q : v;
+            *q = 0ull;
+        }
+        n3[w] = v;
+    }
+    const double m0 = __longlong_as_double(static_cast<long long>(n3[0]));
+    const double mp = __longlong_as_double(static_cast<long long>(n3[1]));
+    const double mp1 = __longlong_as_double(static_cast<long long>(n3[2]));
     const double f0 = fabs(c[0]), fp = fabs(c[off_p]), fp1 = fabs(c[off_pm1]);
     return h_from_norms(P, isnan(f0) ? f0 : m0, isnan(fp) ? fp : mp, isnan(fp1) ? fp1 : mp1, max_delta_t);
 }
@@ -496,8 +505,9 @@ __global__ void __launch_bounds__(MAXT, 1) k_nb(program P, nb_dev_plan NP, batch
     RM.out_b = out_b;
     RM.consts = nbk::saddr(consts_s);
     RM.rcp_ = nbk::saddr(rcp_s);
-    RM.norms = norms_b + l0 * 8u;
-    RM.lt8 = LT * 8u;
+    constexpr std::uint32_t NC = detail::nb_norm_copies(LT);
+    RM.norms = norms_b + ((tid % NC) * LT + l0) * 8u;
+    RM.lt8 = NC * LT * 8u;
     RM.n_batch = D.n;
     RM.p = p;
     const std::size_t team_global = T::index();
@@ -577,14 +587,14 @@ __global__ void __launch_bounds__(MAXT, 1) k_nb(program P, nb_dev_plan NP, batch
         return nb_step_size(P, norms_p + tid, LT, c, p * cv.stride_o, (p - 1u) * cv.stride_o, max_delta_t);
     };
     if (owner) {
-        norms_p[tid] = 0ull;
-        norms_p[LT + tid] = 0ull;
-        norms_p[2 * LT + tid] = 0ull;
+        for (std::uint32_t i = 0; i < 3u * NC; ++i) {
+            norms_p[i * LT + tid] = 0ull;
+        }
     }
     // The per-lane bookkeeping of propagate_until() is parked in shared memory while the jet runs (it would otherwise
     // hold ~26 registers of every thread across the hot loops).
     static_assert(sizeof(lane_prop) <= 128u && alignof(lane_prop) <= 8u);
-    lane_prop *const park = reinterpret_cast<lane_prop *>(norms_p + 3u * LT) + (owner ? tid : 0u);
+    lane_prop *const park = reinterpret_cast<lane_prop *>(norms_p + 3u * NC * LT) + (owner ? tid : 0u);
 
     for (std::uint32_t chunk = T::claim(R.counter); chunk < n_chunks; chunk = T::claim(R.counter)) {
         const std::uint32_t lane0 = chunk * LT;
