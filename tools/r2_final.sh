@@ -5,7 +5,7 @@ mkdir -p gpurun_out
 timeout 180 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r2_smoke.log 2>&1; echo "smoke rc=$?"; tail -2 gpurun_out/r2_smoke.log
 timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/r2_bench_reference.json 2> gpurun_out/r2_bench_final.err; cut -c1-300 gpurun_out/r2_bench_reference.json
 timeout 900 python bench.py > gpurun_out/r2_bench.json 2>> gpurun_out/r2_bench_final.err; cut -c1-300 gpurun_out/r2_bench.json
-timeout 900 python tools/bench_configs.py tb n32 nn grid > gpurun_out/r2_other_configs.jsonl 2> gpurun_out/r2_other_configs.err; cut -c1-100,200-360 gpurun_out/r2_other_configs.jsonl; tail -3 gpurun_out/r2_other_configs.err
+timeout 900 python tools/bench_configs.py tb n32 nn grid s6long > gpurun_out/r2_other_configs.jsonl 2> gpurun_out/r2_other_configs.err; cut -c1-100,200-360 gpurun_out/r2_other_configs.jsonl; tail -3 gpurun_out/r2_other_configs.err
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-cpp-e2e > gpurun_out/r2_launches_bench.log 2>&1
 tail -3 gpurun_out/r2_launches.csv | cut -c1-300
 tail -3 gpurun_out/r2_bench_final.err
