@@ -991,9 +991,9 @@ bool hy_batch::setup_nn()
         }
         max_out = std::max(max_out, L.n_out);
     }
-    // Tensor memory: 32 columns per (neuron, lane) item and hidden layer, 256 columns per thread, orders up to 15 (the
-    // history is read back in two loads of eight orders).
-    if (n_hidden * d.tm_ipt * 32u > 256u || order > 16u) {
+    // Tensor memory: 48 columns per (neuron, lane) item and hidden layer (16 of padding + 2 per order), 256 columns per
+    // thread, orders up to 16 (the history is read back in two windows of eight orders).
+    if (n_hidden * d.tm_ipt * 48u > 256u || order > 16u) {
         return false;
     }
     d.wimg_doubles = static_cast<std::uint32_t>(img.size());

@@ -11,7 +11,7 @@
 //   * tanh (src/math/tanh.cpp:183-318) and its hidden dependency tanh^2 (src/math/pow.cpp square recurrence) are run by
 //     one thread per (neuron, lane) with the reference's sequential summation order. The histories of z and tanh, which
 //     other threads write / read, are [row][order][neuron][lane] arrays in shared memory; the history of tanh^2, which
-//     only its own thread ever touches, lives in TENSOR MEMORY (32 columns per (neuron, lane, layer), read back eight
+//     only its own thread ever touches, lives in TENSOR MEMORY (48 columns per (neuron, lane, layer), read back eight
 //     orders at a time with tcgen05.ld.x16): a third of the history bytes leaves shared memory, which is what bounds the
 //     lanes per CTA (3 instead of 2);
 //   * the output layer's z^[n] are the derivatives of the state variables: x^[n+1] = z^[n] / (n + 1).
@@ -46,8 +46,8 @@ struct nn_dev_plan {
     std::uint32_t ldw[NN_MAX_LAYERS], w_off[NN_MAX_LAYERS], b_off[NN_MAX_LAYERS]; // doubles, into wimg
     std::uint32_t hist_off[NN_MAX_LAYERS]; // doubles, into the history area: [2][order][n_out][LB] (hidden layers)
     std::uint32_t hist_doubles, max_out;
-    // Tensor memory: thread t keeps the tanh^2 history of its r-th (neuron, lane) item of hidden layer L in the 32
-    // columns starting at (tm_slot[L] * tm_ipt + r) * 32 of its region (256 columns per thread: 2 warps per quadrant).
+    // Tensor memory: thread t keeps the tanh^2 history of its r-th (neuron, lane) item of hidden layer L in the 48
+    // columns starting at (tm_slot[L] * tm_ipt + r) * 48 of its region (256 columns per thread: 2 warps per quadrant).
     std::uint32_t tm_ipt, tm_slot[NN_MAX_LAYERS];
 };
 
@@ -201,7 +201,9 @@ __global__ void __launch_bounds__(NN_THREADS, 1) k_nn(program P, nn_dev_plan NP,
                     for (std::uint32_t r = 0; r < NP.tm_ipt; ++r) {
                         const std::uint32_t it = tid + r * NN_THREADS;
                         const bool act = it < n_items;
-                        const std::uint32_t scol = tmc + (NP.tm_slot[L] * NP.tm_ipt + r) * 32u; // tanh^2: 2 columns per order
+                        // tanh^2: 48 columns, order i at columns 16 + 2 i (the 16 below order 0 are padding: the eight
+                        // orders below order n are read as ONE aligned window whatever n is).
+                        const std::uint32_t scol = tmc + (NP.tm_slot[L] * NP.tm_ipt + r) * 48u;
                         const double *zp = zh + (act ? it : 0u);
                         double *tp = th + (act ? it : 0u);
                         const double z = act ? zp[n * so] : 0.;
@@ -211,23 +213,28 @@ __global__ void __launch_bounds__(NN_THREADS, 1) k_nn(program P, nn_dev_plan NP,
                                 t = ::tanh(z);
                             }
                         } else {
-                            // b^[n] - (1/n) sum_{j=1..n} j (c^[n-j] b^[j]), c = tanh(b)^2 (src/math/tanh.cpp:183-318): j
-                            // ascending = the orders of c descending, eight of them per tensor-memory load.
-                            double acc = 0.;
-                            for (int ch = static_cast<int>((n - 1u) / 8u); ch >= 0; --ch) {
+                            // b^[n] - (1/n) sum_{j=1..n} j (c^[n-j] b^[j]), c = tanh(b)^2 (src/math/tanh.cpp:183-318), j
+                            // ascending: c^[n-j], j = 1..8, is word pair 8 - j of the window that ends below order n
+                            // (j = 9..16: of the window before it). The order is the same for the whole warp: the tests
+                            // on j are uniform branches, nothing is executed for the terms that do not exist. (Threads
+                            // without an item compute on whatever their columns hold; nothing of it is stored.)
+                            double acc = 0., jd = 1.;
+                            const double *zq = zp + so;
+                            for (std::uint32_t base = 0; base < n; base += 8u) {
                                 tm::words<16> w;
                                 __syncwarp();
-                                tm::ld(scol + static_cast<std::uint32_t>(ch) * 16u, w);
+                                tm::ld(scol + 2u * n - 2u * base, w);
                                 tm::wait_ld(w);
 #pragma unroll
-                                for (int u = 7; u >= 0; --u) {
-                                    const std::uint32_t i = static_cast<std::uint32_t>(ch) * 8u + static_cast<std::uint32_t>(u);
-                                    if (act && i < n) {
-                                        const double c_i = __hiloint2double(static_cast<int>(w.w[2 * u + 1]),
-                                                                            static_cast<int>(w.w[2 * u]));
-                                        const std::uint32_t j = n - i;
-                                        acc = ::fma(static_cast<double>(j), c_i * zp[j * so], acc);
+                                for (int jj = 1; jj <= 8; ++jj) {
+                                    if (base + static_cast<std::uint32_t>(jj) > n) {
+                                        break;
                                     }
+                                    const double c_i = __hiloint2double(static_cast<int>(w.w[2 * (8 - jj) + 1]),
+                                                                        static_cast<int>(w.w[2 * (8 - jj)]));
+                                    acc = ::fma(jd, c_i * *zq, acc);
+                                    jd += 1.;
+                                    zq += so;
                                 }
                             }
                             t = z - acc / static_cast<double>(n);
@@ -244,8 +251,11 @@ __global__ void __launch_bounds__(NN_THREADS, 1) k_nn(program P, nn_dev_plan NP,
                                 const bool odd = (n & 1u) != 0u;
                                 const std::uint32_t j1 = odd ? (n - 1u) / 2u : (n - 2u) / 2u;
                                 double acc = 0.;
+                                const double *pa = tp + n * so, *pb = tp;
                                 for (std::uint32_t j = 0; j <= j1; ++j) {
-                                    acc = ::fma(tp[(n - j) * so], tp[j * so], acc);
+                                    acc = ::fma(*pa, *pb, acc);
+                                    pa -= so;
+                                    pb += so;
                                 }
                                 if (odd) {
                                     sq = acc + acc;
@@ -259,7 +269,7 @@ __global__ void __launch_bounds__(NN_THREADS, 1) k_nn(program P, nn_dev_plan NP,
                         ws.w[0] = static_cast<std::uint32_t>(__double2loint(sq));
                         ws.w[1] = static_cast<std::uint32_t>(__double2hiint(sq));
                         __syncwarp();
-                        tm::st(scol + n * 2u, ws);
+                        tm::st(scol + 16u + n * 2u, ws);
                     }
                     tm::wait_st();
                     __syncthreads();
