@@ -115,6 +115,10 @@ __global__ void __launch_bounds__(NN_THREADS, 1) k_nn(program P, nn_dev_plan NP,
     __shared__ unsigned int claimed;
     __shared__ lane_prop parked[LB];
     __shared__ std::uint32_t tm_base_smem;
+    __shared__ double nn_zero;
+    if (tid == 0u) {
+        nn_zero = 0.;
+    }
 
     // ---- tensor memory: all 512 columns, 256 per thread (warps w and w + 4 share a quadrant) ----
     if (warp == 0u) {
@@ -168,6 +172,18 @@ __global__ void __launch_bounds__(NN_THREADS, 1) k_nn(program P, nn_dev_plan NP,
                         const double *wr = wimg + NP.w_off[L] + static_cast<std::size_t>(m * 8u + row_in_tile) * ldw + kk;
                         const double *bp = in + kk * LB + row_in_tile;
                         double c0 = 0., c1 = 0., e0 = 0., e1 = 0.;
+                        if (n_in == kpad && (kpad & 7u) == 0u) {
+                            // Full tiles (the 64-input layers): no tests on k, the B fragment of a thread whose column
+                            // carries no lane is read from a zero (stride 0) instead of selected.
+                            const double *ap = wr, *bq = b_ok ? bp : &nn_zero;
+                            const std::uint32_t bs = b_ok ? 4u * LB : 0u;
+                            for (std::uint32_t k0 = 0; k0 < kpad; k0 += 8u) {
+                                nnk::dmma(c0, c1, ap[0], bq[0]);
+                                nnk::dmma(e0, e1, ap[4], bq[bs]);
+                                ap += 8;
+                                bq += 2u * bs;
+                            }
+                        } else
                         for (std::uint32_t k0 = 0; k0 < kpad; k0 += 8u) {
                             const double a0 = wr[k0];
                             const double b0 = (b_ok && k0 + kk < n_in) ? bp[k0 * LB] : 0.;
