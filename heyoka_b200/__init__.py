@@ -422,13 +422,24 @@ class Batch:
                                                int(write_tc), C.byref(flag)))
         return flag.value
 
-    def propagate_until_cout(self, t_hi, t_lo=None, max_delta_t=None, max_steps=0):
-        """propagate_until() with continuous output (lock-step loop); returns a continuous_output_batch or None."""
+    def propagate_until_cout(self, t_hi, t_lo=None, max_delta_t=None, max_steps=0, step_cb=None):
+        """propagate_until() with continuous output (lock-step loop); returns a continuous_output_batch or None.
+        step_cb: callable() -> int run after every recorded iteration (> 0 continue, 0 stop with cb_stop, < 0 abort:
+        hy_batch_propagate_until_cout_cb)."""
         f = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float64)  # noqa: E731
         th, tl, md = f(t_hi), f(t_lo), f(max_delta_t)
         h = C.c_void_p()
-        check(lib.hy_batch_propagate_until_cout(self._h, _dptr(th), None if tl is None else _dptr(tl),
-                                                None if md is None else _dptr(md), int(max_steps), C.byref(h)))
+        if step_cb is None:
+            check(lib.hy_batch_propagate_until_cout(self._h, _dptr(th), None if tl is None else _dptr(tl),
+                                                    None if md is None else _dptr(md), int(max_steps), C.byref(h)))
+        else:
+            tramp = C.CFUNCTYPE(C.c_int, C.c_void_p)(lambda _user: int(step_cb()))
+            st = lib.hy_batch_propagate_until_cout_cb(self._h, _dptr(th), None if tl is None else _dptr(tl),
+                                                      None if md is None else _dptr(md), int(max_steps),
+                                                      C.cast(tramp, C.c_void_p), None, C.byref(h))
+            if st == _capi.HY_ERR_CALLBACK:
+                return None  # (the caller re-raises what its callback raised)
+            check(st)
         return continuous_output_batch(h, self.program.n_eq, self.n) if h.value else None
 
     def propagate_grid(self, grid, max_delta_t=None, max_steps=0):
@@ -890,17 +901,39 @@ class taylor_adaptive_batch:
                 raise ValueError("Invalid number of max timesteps specified in a Taylor integrator in batch mode: the "
                                  "batch size is %d, but the number of specified timesteps is %d" % (n, md.size))
             max_delta_t = md
-        if self._with_events or callback is not None:
+        if self._with_events or (callback is not None and not c_output):
             if c_output:
-                raise NotImplementedError("Continuous output together with events or a callback is not supported by "
-                                          "the B200 batch integrator")
+                raise NotImplementedError("Continuous output together with events is not supported by the B200 batch "
+                                          "integrator")
             self._propagate_until_host(th, np.zeros(n) if tl is None else tl, max_delta_t, max_steps, write_tc, callback)
             return None
         self._push()
         c_out = None
         if c_output:
             # (The lock-step loop writes the Taylor coefficients at every iteration.)
-            c_out = self._b.propagate_until_cout(th, tl, max_delta_t, max_steps)
+            step_cb, err = None, []
+            if callback is not None:
+                # The step callback after every recorded iteration (src/taylor_adaptive_batch.cpp:1476-1500): the mirrors
+                # are refreshed for it; it may alter state and parameters (uploaded again) but not the time.
+                def step_cb():
+                    try:
+                        self._pull(True)
+                        oc, mn, mx, ns = self._b.prop_res()
+                        self._prop_res = list(zip(oc.tolist(), mn.tolist(), mx.tolist(), ns.tolist()))
+                        t_copy = (self._t_hi.copy(), self._t_lo.copy())
+                        go = callback(self)
+                        if not (np.array_equal(self._t_hi, t_copy[0]) and np.array_equal(self._t_lo, t_copy[1])):
+                            raise RuntimeError("The invocation of the callback passed to propagate_until() resulted in "
+                                               "the alteration of the time coordinate of the integrator - this is not "
+                                               "supported")
+                        self._push()
+                        return 1 if go else 0
+                    except BaseException as e:  # noqa: BLE001 - carried across the C frame, re-raised below
+                        err.append(e)
+                        return -1
+            c_out = self._b.propagate_until_cout(th, tl, max_delta_t, max_steps, step_cb=step_cb)
+            if err:
+                raise err[0]
             write_tc = True
         else:
             self._b.propagate_until(th, tl, max_delta_t, max_steps, write_tc)

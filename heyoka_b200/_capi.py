@@ -17,6 +17,7 @@ HY_ERR_INVALID_ARG = -1
 HY_ERR_NOT_IMPLEMENTED = -2
 HY_ERR_CUDA = -3
 HY_ERR_OVERFLOW = -4
+HY_ERR_CALLBACK = -5
 
 # taylor_outcome (include/heyoka/taylor.hpp): values below -2^32 so that they never collide with event indices.
 HY_OUTCOME_SUCCESS = -4294967297
@@ -115,6 +116,7 @@ SIGNATURES = {
     "hy_batch_propagate_grid": (C.c_int, [_vp, _dp, C.c_uint64, _dp, C.c_uint64, _dp]),
     "hy_batch_check_grid": (C.c_int, [_vp, _dp, C.c_uint64, _dp]),
     "hy_batch_propagate_until_cout": (C.c_int, [_vp, _dp, _dp, _dp, C.c_uint64, _vpp]),
+    "hy_batch_propagate_until_cout_cb": (C.c_int, [_vp, _dp, _dp, _dp, C.c_uint64, C.c_void_p, C.c_void_p, _vpp]),
     "hy_cout_eval": (C.c_int, [_vp, _dp, _dp]),
     "hy_cout_get_bounds": (C.c_int, [_vp, _dp, _dp]),
     "hy_cout_n_steps": (C.c_uint64, [_vp]),

@@ -2625,8 +2625,21 @@ struct hy_cout {
     }
 };
 
+namespace
+{
+struct callback_abort {
+};
+} // namespace
+
 int hy_batch_propagate_until_cout(hy_batch *b, const double *t_final_hi, const double *t_final_lo,
                                   const double *max_delta_t, uint64_t max_steps, hy_cout **out)
+{
+    return hy_batch_propagate_until_cout_cb(b, t_final_hi, t_final_lo, max_delta_t, max_steps, nullptr, nullptr, out);
+}
+
+int hy_batch_propagate_until_cout_cb(hy_batch *b, const double *t_final_hi, const double *t_final_lo,
+                                     const double *max_delta_t, uint64_t max_steps, hy_step_callback cb, void *user,
+                                     hy_cout **out)
 {
     // The recording (hy_cout) owns its device memory from the start: slabs of Taylor coefficients the step kernel
     // writes into directly, and the times of the iterations in a geometrically grown array.
@@ -2776,6 +2789,19 @@ int hy_batch_propagate_until_cout(hy_batch *b, const double *t_final_hi, const d
             // update_c_out(), :1320-1346.
             push_times();
             ++iter;
+            if (cb != nullptr) {
+                // The step callback (:1476-1500), before the exit tests like in the reference.
+                HY_CUDA_CHECK(cudaStreamSynchronize(b->stream));
+                const int r = cb(user);
+                if (r < 0) {
+                    throw callback_abort{};
+                }
+                if (r == 0) {
+                    dev::k_fill_outcome<<<(n + 255u) / 256u, 256, 0, b->stream>>>(b->d_prop_outcome, n,
+                                                                                  HY_OUTCOME_CB_STOP);
+                    break;
+                }
+            }
             if (hflags[0] == n) {
                 break; // every lane reached its final time
             }
@@ -2818,6 +2844,10 @@ int hy_batch_propagate_until_cout(hy_batch *b, const double *t_final_hi, const d
         HY_CUDA_CHECK(cudaStreamSynchronize(b->stream));
         cleanup();
         return HY_OK;
+    } catch (const callback_abort &) {
+        cleanup();
+        hy::detail::set_last_error("A host callback aborted the propagation");
+        return HY_ERR_CALLBACK;
     } catch (...) {
         cleanup();
         return translate_exception();

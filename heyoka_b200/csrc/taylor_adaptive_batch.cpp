@@ -1041,12 +1041,6 @@ taylor_adaptive_batch<double>::propagate_grid_impl(const std::vector<double> &gr
     auto &m = *m_impl;
     const auto n = m.batch_size;
     const strict_scope strict(m);
-    if (o.cb) {
-        throw not_implemented_error("Callbacks are not supported by propagate_grid() in the B200 batch integrator");
-    }
-    if (with_events()) {
-        return propagate_grid_events(grid, std::move(o));
-    }
     if (grid.empty()) {
         throw std::invalid_argument(
             "Cannot invoke propagate_grid() in an adaptive Taylor integrator in batch mode if the time grid is empty");
@@ -1063,6 +1057,11 @@ taylor_adaptive_batch<double>::propagate_grid_impl(const std::vector<double> &gr
                                     + std::to_string(n) + ", but the number of specified timesteps is "
                                     + std::to_string(o.max_delta_t.size()));
     }
+    if (o.cb || with_events()) {
+        // A step callback (or events, whose callbacks also run on the host) after every step: the reference's loop on the
+        // host, one device step per iteration.
+        return propagate_grid_events(grid, std::move(o));
+    }
     std::vector<double> retval(grid.size() * m.dim);
     m.push();
     check(hy_batch_propagate_grid(m.batch, grid.data(), grid.size() / n,
@@ -1072,9 +1071,11 @@ taylor_adaptive_batch<double>::propagate_grid_impl(const std::vector<double> &gr
     return {std::move(o.cb), std::move(retval)};
 }
 
-// propagate_grid() of an integrator with events: the reference's loop (src/taylor_adaptive_batch.cpp:1696-2053) on the
-// host - propagate_until() to the first grid point, then lock-step steps (with their event callbacks) interleaved with
-// dense-output sampling of the grid points each step covers.
+// propagate_grid() of an integrator with events and / or with a step callback: the reference's loop
+// (src/taylor_adaptive_batch.cpp:1696-2053) on the host - propagate_until() to the first grid point (without the
+// callback, :1703-1706), then lock-step steps (with their event callbacks, then the step callback, which may stop the
+// propagation and must not alter the time: :2004-2039) interleaved with dense-output sampling of the grid points each
+// step covers.
 std::tuple<step_callback_batch<double>, std::vector<double>>
 taylor_adaptive_batch<double>::propagate_grid_events(const std::vector<double> &grid, prop_opts o)
 {
@@ -1203,7 +1204,20 @@ taylor_adaptive_batch<double>::propagate_grid_events(const std::vector<double> &
             break;
         }
         ++iter_counter;
-        if (iter_counter == o.max_steps) {
+        bool cb_ok = true;
+        if (o.cb) {
+            const auto thi = m.time_hi, tlo = m.time_lo;
+            cb_ok = o.cb(*this);
+            if (m.time_hi != thi || m.time_lo != tlo) {
+                throw std::runtime_error("The invocation of the callback passed to propagate_grid() resulted in the "
+                                         "alteration of the time coordinate of the integrator - this is not supported");
+            }
+        }
+        if (!cb_ok) {
+            for (auto &t : m.prop_res) {
+                std::get<0>(t) = taylor_outcome::cb_stop;
+            }
+        } else if (iter_counter == o.max_steps) {
             for (auto &t : m.prop_res) {
                 std::get<0>(t) = taylor_outcome::step_limit;
             }
@@ -1219,9 +1233,9 @@ taylor_adaptive_batch<double>::propagate_until_impl(const std::vector<double> &h
     auto &m = *m_impl;
     const auto n = m.batch_size;
 
-    if (o.c_output && (o.cb || with_events())) {
-        throw not_implemented_error("Continuous output together with a callback or with events is not supported by the "
-                                    "B200 batch integrator");
+    if (o.c_output && with_events()) {
+        throw not_implemented_error("Continuous output together with events is not supported by the B200 batch "
+                                    "integrator");
     }
 
     // Validation, src/taylor_adaptive_batch.cpp:1212-1273.
@@ -1263,7 +1277,47 @@ taylor_adaptive_batch<double>::propagate_until_impl(const std::vector<double> &h
         // (hy_batch_propagate_until_cout()).
         m.push();
         hy_cout *co = nullptr;
-        check(hy_batch_propagate_until_cout(m.batch, hi.data(), lo.data(), mdt, o.max_steps, &co));
+        if (o.cb) {
+            // With a step callback (:1476-1500): the library calls back after every recorded iteration; the mirrors are
+            // refreshed for the callback, which may alter state and parameters (uploaded again) but not the time.
+            struct hook_t {
+                taylor_adaptive_batch *self;
+                prop_opts *o;
+                std::exception_ptr err;
+            } hook{this, &o, nullptr};
+            const auto tramp = [](void *user) -> int {
+                auto &h = *static_cast<hook_t *>(user);
+                auto &mm = *h.self->m_impl;
+                const bool was_lazy = mm.lazy;
+                try {
+                    mm.lazy = false;
+                    mm.pull(true);
+                    mm.pull_prop_res();
+                    const auto thi = mm.time_hi, tlo = mm.time_lo;
+                    const bool go = h.o->cb(*h.self);
+                    if (mm.time_hi != thi || mm.time_lo != tlo) {
+                        throw std::runtime_error("The invocation of the callback passed to propagate_until() resulted in "
+                                                 "the alteration of the time coordinate of the integrator - this is not "
+                                                 "supported");
+                    }
+                    mm.host_new_state = mm.host_new_pars = true;
+                    mm.push();
+                    mm.lazy = was_lazy;
+                    return go ? 1 : 0;
+                } catch (...) {
+                    mm.lazy = was_lazy;
+                    h.err = std::current_exception();
+                    return -1;
+                }
+            };
+            const int st = hy_batch_propagate_until_cout_cb(m.batch, hi.data(), lo.data(), mdt, o.max_steps, tramp, &hook, &co);
+            if (hook.err) {
+                std::rethrow_exception(hook.err);
+            }
+            check(st);
+        } else {
+            check(hy_batch_propagate_until_cout(m.batch, hi.data(), lo.data(), mdt, o.max_steps, &co));
+        }
         std::optional<continuous_output_batch<double>> ret;
         if (co != nullptr) {
             ret.emplace(co, n, m.dim);

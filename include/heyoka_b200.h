@@ -38,6 +38,7 @@ extern "C" {
 #define HY_ERR_NOT_IMPLEMENTED (-2) /* maps to heyoka::not_implemented_error (include/heyoka/exceptions.hpp:19) */
 #define HY_ERR_CUDA (-3) /* CUDA runtime failure / no device */
 #define HY_ERR_OVERFLOW (-4) /* maps to std::overflow_error */
+#define HY_ERR_CALLBACK (-5) /* a host callback passed to the library asked to abort (it keeps its own exception) */
 
 const char *hy_last_error(void);
 const char *hy_version(void);
@@ -298,6 +299,14 @@ int hy_batch_check_grid(hy_batch *, const double *grid, uint64_t n_pts, const do
 typedef struct hy_cout hy_cout;
 int hy_batch_propagate_until_cout(hy_batch *, const double *t_final_hi, const double *t_final_lo,
                                   const double *max_delta_t, uint64_t max_steps, hy_cout **out);
+/* Same with a STEP CALLBACK (propagate_until(kw::c_output = true, kw::callback = ...), src/taylor_adaptive_batch.cpp:
+ * 1476-1500): after every recorded iteration the stream is synchronised and cb(user) runs on the host - the batch is
+ * consistent, the caller may download / upload state and parameters (not the time) from inside it. Return value: > 0
+ * continue, 0 stop (every outcome becomes cb_stop, the iteration stays recorded), < 0 abort with HY_ERR_CALLBACK. */
+typedef int (*hy_step_callback)(void *user);
+int hy_batch_propagate_until_cout_cb(hy_batch *, const double *t_final_hi, const double *t_final_lo,
+                                     const double *max_delta_t, uint64_t max_steps, hy_step_callback cb, void *user,
+                                     hy_cout **out);
 int hy_cout_eval(hy_cout *, const double *tm, double *out);
 /* Per-lane time range [lb, ub] covered (the initial and the final time), number of recorded iterations. */
 int hy_cout_get_bounds(const hy_cout *, double *lb, double *ub);

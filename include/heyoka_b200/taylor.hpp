@@ -400,7 +400,8 @@ public:
     }
     // propagate_grid() (include/heyoka/taylor.hpp, src/taylor_adaptive_batch.cpp:1545-2055): grid[k * batch + lane];
     // returns the callback and the states at the grid points, [n_pts][dim][batch], NaN where not reached.
-    // kw::max_steps, kw::max_delta_t; a non-empty kw::callback is rejected with not_implemented_error.
+    // kw::max_steps, kw::max_delta_t, kw::callback (a step callback, like events, runs the reference's loop on the host:
+    // one device step per iteration).
     template <typename... KwArgs>
     std::tuple<step_callback_batch<double>, std::vector<double>> propagate_grid(const std::vector<double> &grid,
                                                                                 const KwArgs &...kw_args)

@@ -426,6 +426,52 @@ static void test_propagate_grid()
         }
         REQUIRE(ok);
     }
+    // A step callback (src/taylor_adaptive_batch.cpp:2004-2039): invoked after every step of the grid loop, the results
+    // are those of the loop without it; returning false stops the propagation with cb_stop in every batch element and
+    // leaves the grid points not reached as NaN; altering the time is an error.
+    {
+        const std::vector<double> ic{0., 0., 0., 0., 1., 1.1, 1.2, 1.3};
+        std::vector<double> grid;
+        for (auto i = 0u; i < 200u; ++i) {
+            for (auto j = 0; j < 4; ++j) {
+                grid.push_back(i / 20. + (i != 0u ? j / 10. : 0.));
+            }
+        }
+        taylor_adaptive_batch<double> ref{{prime(x) = v, prime(v) = -x}, ic, 4u};
+        auto [cb0, out0] = ref.propagate_grid(grid);
+        REQUIRE(!cb0);
+        taylor_adaptive_batch<double> ta{{prime(x) = v, prime(v) = -x}, ic, 4u};
+        std::size_t calls = 0;
+        auto [cb1, out1] = ta.propagate_grid(grid, kw::callback = [&calls](taylor_adaptive_batch<double> &) {
+            ++calls;
+            return true;
+        });
+        REQUIRE(static_cast<bool>(cb1));
+        REQUIRE(calls > 0u);
+        REQUIRE(out1 == out0);
+        REQUIRE(ta.get_state() == ref.get_state());
+        REQUIRE(ta.get_time() == ref.get_time());
+        for (auto i = 0u; i < 4u; ++i) {
+            REQUIRE(ta.get_propagate_res()[i] == ref.get_propagate_res()[i]);
+        }
+        taylor_adaptive_batch<double> tb{{prime(x) = v, prime(v) = -x}, ic, 4u};
+        std::size_t n_cb = 0;
+        auto [cb2, out2] = tb.propagate_grid(grid, kw::callback = [&n_cb](taylor_adaptive_batch<double> &) { return ++n_cb < 3u; });
+        REQUIRE(n_cb == 3u);
+        for (auto i = 0u; i < 4u; ++i) {
+            REQUIRE(std::get<0>(tb.get_propagate_res()[i]) == taylor_outcome::cb_stop);
+            REQUIRE(std::get<3>(tb.get_propagate_res()[i]) == 3u);
+        }
+        REQUIRE(std::isnan(out2.back()));
+        REQUIRE(out2[0] == 0. && out2[4] == 1.);
+        taylor_adaptive_batch<double> tc{{prime(x) = v, prime(v) = -x}, ic, 4u};
+        REQUIRE_THROWS_MSG(tc.propagate_grid(grid, kw::callback =
+                                                       [](taylor_adaptive_batch<double> &t) {
+                                                           t.set_time(-1.);
+                                                           return true;
+                                                       }),
+                           std::runtime_error, "resulted in the alteration of the time coordinate");
+    }
 }
 
 // test/c_output.cpp:289-420 ("batch"): default-constructed object, continuous output against a grid propagation.
@@ -496,6 +542,56 @@ static void test_continuous_output()
         ok = ok && near(d_out->get_output()[0], grid_out[2u * i * batch_size]);
     }
     REQUIRE(ok);
+    // Continuous output TOGETHER with a step callback (src/taylor_adaptive_batch.cpp:1476-1500): the callback runs after
+    // every recorded iteration and sees the integrator's current state; the recording is the one of the run without it;
+    // returning false stops with cb_stop in every batch element and keeps what was recorded; the callback may alter the
+    // state (here: not) but not the time.
+    {
+        auto [x2, v2] = make_vars("x", "v");
+        const std::vector<double> ic2{0., 0.01, 0.02, 0.03, 1., 1.01, 1.02, 1.03}, tf2{10., 10.01, 10.02, 10.03};
+        taylor_adaptive_batch<double> ref{{prime(x2) = v2, prime(v2) = -x2}, ic2, 4u};
+        auto [co_ref, cb_ref] = ref.propagate_until(tf2, kw::c_output = true);
+        REQUIRE(co_ref.has_value() && !cb_ref);
+        taylor_adaptive_batch<double> ta2{{prime(x2) = v2, prime(v2) = -x2}, ic2, 4u};
+        std::size_t calls = 0;
+        double last_seen_t = -1.;
+        auto [co_cb, cb_out] = ta2.propagate_until(
+            tf2, kw::c_output = true, kw::callback = [&](taylor_adaptive_batch<double> &t) {
+                ++calls;
+                last_seen_t = t.get_time()[0];
+                return true;
+            });
+        REQUIRE(co_cb.has_value() && static_cast<bool>(cb_out));
+        REQUIRE(calls == co_ref->get_n_steps() && co_cb->get_n_steps() == co_ref->get_n_steps());
+        REQUIRE(last_seen_t == 10.);
+        REQUIRE(ta2.get_state() == ref.get_state() && ta2.get_time() == ref.get_time());
+        for (const double tq : {0.5, 3.3, 9.99}) {
+            REQUIRE((*co_cb)(tq) == (*co_ref)(tq));
+        }
+        taylor_adaptive_batch<double> ta3{{prime(x2) = v2, prime(v2) = -x2}, ic2, 4u};
+        std::size_t n3 = 0;
+        auto [co3, cb3] = ta3.propagate_until(tf2, kw::c_output = true,
+                                              kw::callback = [&n3](taylor_adaptive_batch<double> &) { return ++n3 < 4u; });
+        REQUIRE(n3 == 4u && co3.has_value() && co3->get_n_steps() == 4u);
+        for (auto i = 0u; i < 4u; ++i) {
+            REQUIRE(std::get<0>(ta3.get_propagate_res()[i]) == taylor_outcome::cb_stop);
+        }
+        REQUIRE(co3->get_bounds().second == ta3.get_time());
+        taylor_adaptive_batch<double> ta4{{prime(x2) = v2, prime(v2) = -x2}, ic2, 4u};
+        REQUIRE_THROWS_MSG(ta4.propagate_until(tf2, kw::c_output = true,
+                                               kw::callback =
+                                                   [](taylor_adaptive_batch<double> &t) {
+                                                       t.set_time(-1.);
+                                                       return true;
+                                                   }),
+                           std::runtime_error, "resulted in the alteration of the time coordinate");
+        taylor_adaptive_batch<double> ta5{{prime(x2) = v2, prime(v2) = -x2}, ic2, 4u};
+        REQUIRE_THROWS_MSG(ta5.propagate_until(tf2, kw::c_output = true,
+                                               kw::callback = [](taylor_adaptive_batch<double> &) -> bool {
+                                                   throw std::domain_error("from the callback");
+                                               }),
+                           std::domain_error, "from the callback");
+    }
 }
 
 // Event detection through the drop-in class: blocks of test/batch_event_detection.cpp.

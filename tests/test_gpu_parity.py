@@ -664,6 +664,26 @@ def test_continuous_output_gpu(kernel):
     ta.state[0, 1] = float("inf")
     assert ta.propagate_until(final_tm, c_output=True) is None
     assert ta.propagate_res[1][0] == hb.taylor_outcome.err_nf_state
+    # Continuous output TOGETHER with a step callback (src/taylor_adaptive_batch.cpp:1476-1500, hy_batch_propagate_until_
+    # cout_cb): called after every recorded iteration, same recording; False stops with cb_stop and keeps what was
+    # recorded; exceptions and alterations of the time come back to the caller.
+    ref = hb.taylor_adaptive_batch(sys_oscillator(), ic, 4, kernel=kernel)
+    co_ref = ref.propagate_until(final_tm, c_output=True)
+    seen = []
+    ta = hb.taylor_adaptive_batch(sys_oscillator(), ic, 4, kernel=kernel)
+    co = ta.propagate_until(final_tm, c_output=True, callback=lambda t: seen.append(t.time.copy()) or True)
+    assert len(seen) == co_ref.get_n_steps() == co.get_n_steps() and np.array_equal(seen[-1], final_tm)
+    assert np.array_equal(ta.state, ref.state) and np.array_equal(co(3.3), co_ref(3.3))
+    ta = hb.taylor_adaptive_batch(sys_oscillator(), ic, 4, kernel=kernel)
+    count = []
+    co = ta.propagate_until(final_tm, c_output=True, callback=lambda t: count.append(1) or len(count) < 3)
+    assert co.get_n_steps() == 3 and [r[0] for r in ta.propagate_res] == [hb.taylor_outcome.cb_stop] * 4
+    ta = hb.taylor_adaptive_batch(sys_oscillator(), ic, 4, kernel=kernel)
+
+    def bad(t):
+        raise KeyError("from the callback")
+    with pytest.raises(KeyError, match="from the callback"):
+        ta.propagate_until(final_tm, c_output=True, callback=bad)
 
 
 @pytest.mark.gpu
