@@ -809,7 +809,7 @@ class taylor_adaptive_batch:
     def step_backward(self, write_tc=False):
         self._step_impl(None, True, write_tc)
 
-    def _propagate_until_host(self, th, tl, max_delta_t, max_steps, write_tc, callback):
+    def _propagate_until_host(self, th, tl, max_delta_t, max_steps, write_tc, callback, c_output=False):
         """The reference's lock-step loop (src/taylor_adaptive_batch.cpp:1256-1530) on the host, one device step per
         iteration: integrators with events (their callbacks are host code) and step callbacks."""
         n = self._batch_size
@@ -830,12 +830,36 @@ class taylor_adaptive_batch:
             raise OverflowError("The final time passed to the propagate_until() function of an adaptive Taylor "
                                 "integrator in batch mode results in an overflow condition")
         t_dir = (rem_hi > 0) | ((rem_hi == 0) & (rem_lo >= 0))
+        self._prop_res = [(0, 0.0, 0.0, 0)] * n
+        # Continuous output (integrators with events): the iterations of this loop are recorded on the device
+        # (hy_cout_rec_*: update_c_out() / make_c_out(), src/taylor_adaptive_batch.cpp:1277-1346).
+        rec = C.c_void_p()
+        if c_output:
+            self._push()
+            check(lib.hy_cout_rec_begin(self._b._h, C.byref(rec)))
+
+        def finish():
+            if not rec.value:
+                return None
+            fwd = np.ascontiguousarray(t_dir, dtype=np.uint8)
+            h, r = C.c_void_p(), C.c_void_p(rec.value)
+            rec.value = None  # (finish destroys the recorder)
+            check(lib.hy_cout_rec_finish(self._b._h, r, fwd.ctypes.data_as(C.POINTER(C.c_uint8)), C.byref(h)))
+            return continuous_output_batch(h, self._prog.n_eq, n) if h.value else None
+        try:
+            return self._propagate_until_host_loop(th, tl, mdt, rem_hi, rem_lo, t_dir, max_steps, write_tc, callback, rec,
+                                                   finish)
+        finally:
+            if rec.value:
+                lib.hy_cout_rec_destroy(rec)
+
+    def _propagate_until_host_loop(self, th, tl, mdt, rem_hi, rem_lo, t_dir, max_steps, write_tc, callback, rec, finish):
+        n = self._batch_size
         ts_count = [0] * n
         min_h, max_h = [float("inf")] * n, [0.0] * n
         iters = 0
         SUCCESS, STEP_LIMIT, NF, CB_STOP = _capi.HY_OUTCOME_SUCCESS, _capi.HY_OUTCOME_STEP_LIMIT, \
             _capi.HY_OUTCOME_ERR_NF_STATE, _capi.HY_OUTCOME_CB_STOP
-        self._prop_res = [(0, 0.0, 0.0, 0)] * n
         while True:
             cur = np.empty(n)
             for i in range(n):
@@ -863,7 +887,9 @@ class taylor_adaptive_batch:
                         rem_hi[i], rem_lo[i] = float(a), float(b)
                 self._prop_res[i] = (oc, min_h[i], max_h[i], ts_count[i])
             if nfs:
-                return
+                return finish()
+            if rec.value:
+                check(lib.hy_cout_rec_append(self._b._h, rec))
             iters += 1
             if callback is not None:
                 t_copy = (self._t_hi.copy(), self._t_lo.copy())
@@ -873,12 +899,12 @@ class taylor_adaptive_batch:
                                        "alteration of the time coordinate of the integrator - this is not supported")
                 if not ret:
                     self._prop_res = [(CB_STOP,) + r[1:] for r in self._prop_res]
-                    return
+                    return finish()
             if n_done == n or ste:
-                return
+                return finish()
             if iters == max_steps:
                 self._prop_res = [(STEP_LIMIT,) + r[1:] for r in self._prop_res]
-                return
+                return finish()
 
     def propagate_until(self, ts, max_steps=0, max_delta_t=None, write_tc=False, callback=None, c_output=False):
         n = self._batch_size
@@ -902,11 +928,8 @@ class taylor_adaptive_batch:
                                  "batch size is %d, but the number of specified timesteps is %d" % (n, md.size))
             max_delta_t = md
         if self._with_events or (callback is not None and not c_output):
-            if c_output:
-                raise NotImplementedError("Continuous output together with events is not supported by the B200 batch "
-                                          "integrator")
-            self._propagate_until_host(th, np.zeros(n) if tl is None else tl, max_delta_t, max_steps, write_tc, callback)
-            return None
+            return self._propagate_until_host(th, np.zeros(n) if tl is None else tl, max_delta_t, max_steps, write_tc,
+                                              callback, c_output)
         self._push()
         c_out = None
         if c_output:

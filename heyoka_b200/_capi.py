@@ -116,6 +116,10 @@ SIGNATURES = {
     "hy_batch_propagate_grid": (C.c_int, [_vp, _dp, C.c_uint64, _dp, C.c_uint64, _dp]),
     "hy_batch_check_grid": (C.c_int, [_vp, _dp, C.c_uint64, _dp]),
     "hy_batch_propagate_until_cout": (C.c_int, [_vp, _dp, _dp, _dp, C.c_uint64, _vpp]),
+    "hy_cout_rec_begin": (C.c_int, [_vp, _vpp]),
+    "hy_cout_rec_append": (C.c_int, [_vp, _vp]),
+    "hy_cout_rec_finish": (C.c_int, [_vp, _vp, C.POINTER(C.c_uint8), _vpp]),
+    "hy_cout_rec_destroy": (None, [_vp]),
     "hy_batch_propagate_until_cout_cb": (C.c_int, [_vp, _dp, _dp, _dp, C.c_uint64, C.c_void_p, C.c_void_p, _vpp]),
     "hy_cout_eval": (C.c_int, [_vp, _dp, _dp]),
     "hy_cout_get_bounds": (C.c_int, [_vp, _dp, _dp]),

@@ -2854,6 +2854,154 @@ int hy_batch_propagate_until_cout_cb(hy_batch *b, const double *t_final_hi, cons
     }
 }
 
+// A recording driven from OUTSIDE the library: the front ends' host lock-step loops (integrators with events, whose
+// callbacks are host code: src/taylor_adaptive_batch.cpp:1372-1527 with update_c_out() at :1320-1346) append the Taylor
+// coefficients and times of every iteration they complete.
+struct hy_cout_rec {
+    std::unique_ptr<hy_cout> co;
+    double *d_times = nullptr; // rows of 2 * n doubles (hi, lo)
+    std::size_t times_cap = 0, times_rows = 0, tc_doubles = 0;
+    std::uint64_t iter = 0;
+    ~hy_cout_rec()
+    {
+        if (d_times != nullptr) {
+            cudaFree(d_times);
+        }
+    }
+};
+
+namespace
+{
+
+void rec_push_times(hy_batch *b, hy_cout_rec *r)
+{
+    const std::uint32_t n = b->n;
+    if (r->times_rows == r->times_cap) {
+        const std::size_t new_cap = std::max<std::size_t>(2u * r->times_cap, 64u);
+        double *nt = nullptr;
+        HY_CUDA_CHECK(cudaMalloc(&nt, sizeof(double) * 2u * n * new_cap));
+        if (r->d_times != nullptr) {
+            HY_CUDA_CHECK(cudaMemcpyAsync(nt, r->d_times, sizeof(double) * 2u * n * r->times_rows, cudaMemcpyDeviceToDevice,
+                                          b->stream));
+            HY_CUDA_CHECK(cudaStreamSynchronize(b->stream));
+            HY_CUDA_CHECK(cudaFree(r->d_times));
+        }
+        r->d_times = nt;
+        r->times_cap = new_cap;
+    }
+    double *blk = r->d_times + 2u * n * r->times_rows;
+    HY_CUDA_CHECK(cudaMemcpyAsync(blk, b->d_t_hi, sizeof(double) * n, cudaMemcpyDeviceToDevice, b->stream));
+    HY_CUDA_CHECK(cudaMemcpyAsync(blk + n, b->d_t_lo, sizeof(double) * n, cudaMemcpyDeviceToDevice, b->stream));
+    ++r->times_rows;
+}
+
+} // namespace
+
+int hy_cout_rec_begin(hy_batch *b, hy_cout_rec **out)
+{
+    try {
+        if (b == nullptr || out == nullptr) {
+            throw std::invalid_argument("Null pointer passed to hy_cout_rec_begin()");
+        }
+        if (!b->shards.empty()) {
+            throw hy::detail::not_implemented_error("Continuous output is not available on a multi-device batch");
+        }
+        *out = nullptr;
+        device_guard guard(b->device);
+        auto r = std::make_unique<hy_cout_rec>();
+        r->tc_doubles = static_cast<std::size_t>(b->n_eq) * (b->order + 1u) * b->n;
+        r->co = std::make_unique<hy_cout>();
+        r->co->device = b->device;
+        r->co->n = b->n;
+        r->co->n_eq = b->n_eq;
+        r->co->order = b->order;
+        r->co->prog = b->prog;
+        r->co->stream = b->stream;
+        r->co->slab_iters = static_cast<std::uint32_t>(std::min<std::size_t>(
+            std::max<std::size_t>((std::size_t(64) << 20) / (r->tc_doubles * sizeof(double)), 1u), 4096u));
+        rec_push_times(b, r.get()); // row 0: the starting time
+        HY_CUDA_CHECK(cudaStreamSynchronize(b->stream));
+        *out = r.release();
+        return HY_OK;
+    } catch (...) {
+        return translate_exception();
+    }
+}
+
+int hy_cout_rec_append(hy_batch *b, hy_cout_rec *r)
+{
+    try {
+        if (b == nullptr || r == nullptr || r->co == nullptr || r->co->n != b->n || b->d_tc == nullptr) {
+            throw std::invalid_argument("Invalid arguments passed to hy_cout_rec_append() (the last step must have "
+                                        "written its Taylor coefficients)");
+        }
+        device_guard guard(b->device);
+        auto &co = *r->co;
+        if (r->iter / co.slab_iters == co.slabs.size()) {
+            double *slab = nullptr;
+            HY_CUDA_CHECK(cudaMalloc(&slab, sizeof(double) * r->tc_doubles * co.slab_iters));
+            co.slabs.push_back(slab);
+        }
+        // (The rows of the state variables come first in the batch's tc array; those of event equations are not recorded.)
+        HY_CUDA_CHECK(cudaMemcpyAsync(co.slabs[r->iter / co.slab_iters] + (r->iter % co.slab_iters) * r->tc_doubles, b->d_tc,
+                                      sizeof(double) * r->tc_doubles, cudaMemcpyDeviceToDevice, b->stream));
+        rec_push_times(b, r);
+        ++r->iter;
+        return HY_OK;
+    } catch (...) {
+        return translate_exception();
+    }
+}
+
+void hy_cout_rec_destroy(hy_cout_rec *r)
+{
+    delete r;
+}
+
+// make_c_out() (:1277-1317): forward[lane] != 0 for lanes integrated forwards in time (the padding row of the times is
+// +-inf by direction). *out = NULL if nothing was recorded. The recorder is destroyed either way.
+int hy_cout_rec_finish(hy_batch *b, hy_cout_rec *rp, const unsigned char *forward, hy_cout **out)
+{
+    std::unique_ptr<hy_cout_rec> r(rp);
+    try {
+        if (b == nullptr || rp == nullptr || forward == nullptr || out == nullptr) {
+            throw std::invalid_argument("Null pointer passed to hy_cout_rec_finish()");
+        }
+        *out = nullptr;
+        device_guard guard(b->device);
+        const std::uint32_t n = b->n;
+        const std::uint64_t iter = r->iter;
+        if (iter != 0u) {
+            auto &co = *r->co;
+            co.n_steps = iter;
+            const std::size_t rows = iter + 2u;
+            HY_CUDA_CHECK(cudaMalloc(&co.d_t_hi, sizeof(double) * rows * n));
+            HY_CUDA_CHECK(cudaMalloc(&co.d_t_lo, sizeof(double) * rows * n));
+            HY_CUDA_CHECK(cudaMalloc(&co.d_tm, sizeof(double) * n));
+            HY_CUDA_CHECK(cudaMalloc(&co.d_out, sizeof(double) * static_cast<std::size_t>(b->n_eq) * n));
+            HY_CUDA_CHECK(cudaMemcpy2DAsync(co.d_t_hi, sizeof(double) * n, r->d_times, sizeof(double) * 2u * n,
+                                            sizeof(double) * n, iter + 1u, cudaMemcpyDeviceToDevice, b->stream));
+            HY_CUDA_CHECK(cudaMemcpy2DAsync(co.d_t_lo, sizeof(double) * n, r->d_times + n, sizeof(double) * 2u * n,
+                                            sizeof(double) * n, iter + 1u, cudaMemcpyDeviceToDevice, b->stream));
+            HY_CUDA_CHECK(cudaMalloc(&co.d_slabs, sizeof(double *) * co.slabs.size()));
+            HY_CUDA_CHECK(cudaMemcpyAsync(co.d_slabs, co.slabs.data(), sizeof(double *) * co.slabs.size(),
+                                          cudaMemcpyHostToDevice, b->stream));
+            HY_CUDA_CHECK(cudaStreamSynchronize(b->stream));
+            std::vector<double> pad(n), zero(n, 0.);
+            for (std::uint32_t i = 0; i < n; ++i) {
+                pad[i] = forward[i] != 0 ? std::numeric_limits<double>::infinity() : -std::numeric_limits<double>::infinity();
+            }
+            HY_CUDA_CHECK(cudaMemcpy(co.d_t_hi + (rows - 1u) * n, pad.data(), sizeof(double) * n, cudaMemcpyHostToDevice));
+            HY_CUDA_CHECK(cudaMemcpy(co.d_t_lo + (rows - 1u) * n, zero.data(), sizeof(double) * n, cudaMemcpyHostToDevice));
+            *out = r->co.release();
+        }
+        HY_CUDA_CHECK(cudaStreamSynchronize(b->stream));
+        return HY_OK;
+    } catch (...) {
+        return translate_exception();
+    }
+}
+
 int hy_cout_eval(hy_cout *c, const double *tm, double *out)
 {
     try {

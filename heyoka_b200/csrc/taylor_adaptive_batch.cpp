@@ -1233,10 +1233,7 @@ taylor_adaptive_batch<double>::propagate_until_impl(const std::vector<double> &h
     auto &m = *m_impl;
     const auto n = m.batch_size;
 
-    if (o.c_output && with_events()) {
-        throw not_implemented_error("Continuous output together with events is not supported by the B200 batch "
-                                    "integrator");
-    }
+
 
     // Validation, src/taylor_adaptive_batch.cpp:1212-1273.
     m.refresh_time();
@@ -1272,7 +1269,7 @@ taylor_adaptive_batch<double>::propagate_until_impl(const std::vector<double> &h
     }
     const double *mdt = o.max_delta_t.empty() ? nullptr : o.max_delta_t.data();
 
-    if (o.c_output) {
+    if (o.c_output && !with_events()) {
         // The reference's lock-step loop with the recording of the Taylor coefficients, on the device
         // (hy_batch_propagate_until_cout()).
         m.push();
@@ -1364,6 +1361,39 @@ taylor_adaptive_batch<double>::propagate_until_impl(const std::vector<double> &h
     for (std::uint32_t i = 0; i < n; ++i) {
         t_dir[i] = dfl_ge0(rem[i]) ? 1 : 0;
     }
+    // Continuous output of an integrator with events: the iterations of this loop are recorded on the device
+    // (update_c_out(), :1320-1346; make_c_out(), :1277-1317), every step of such an integrator writes its Taylor
+    // coefficients.
+    struct rec_guard {
+        hy_cout_rec *r = nullptr;
+        ~rec_guard()
+        {
+            if (r != nullptr) {
+                hy_cout_rec_destroy(r);
+            }
+        }
+    } rec;
+    if (o.c_output) {
+        m.push();
+        check(hy_cout_rec_begin(m.batch, &rec.r));
+    }
+    const auto finish = [&]() -> std::tuple<std::optional<continuous_output_batch<double>>, step_callback_batch<double>> {
+        std::optional<continuous_output_batch<double>> ret;
+        if (rec.r != nullptr) {
+            std::vector<unsigned char> fwd(n);
+            for (std::uint32_t i = 0; i < n; ++i) {
+                fwd[i] = t_dir[i] != 0 ? 1 : 0;
+            }
+            hy_cout *co = nullptr;
+            hy_cout_rec *r = rec.r;
+            rec.r = nullptr; // (finish() destroys the recorder)
+            check(hy_cout_rec_finish(m.batch, r, fwd.data(), &co));
+            if (co != nullptr) {
+                ret.emplace(co, n, m.dim);
+            }
+        }
+        return {std::move(ret), std::move(o.cb)};
+    };
     std::size_t iter_counter = 0;
     while (true) {
         for (std::uint32_t i = 0; i < n; ++i) {
@@ -1400,7 +1430,10 @@ taylor_adaptive_batch<double>::propagate_until_impl(const std::vector<double> &h
             m.prop_res[i] = std::tuple{oc, min_h[i], max_h[i], ts_count[i]};
         }
         if (nfs) {
-            return {std::nullopt, std::move(o.cb)};
+            return finish();
+        }
+        if (rec.r != nullptr) {
+            check(hy_cout_rec_append(m.batch, rec.r));
         }
         ++iter_counter;
         if (o.cb) {
@@ -1413,17 +1446,17 @@ taylor_adaptive_batch<double>::propagate_until_impl(const std::vector<double> &h
                 for (auto &r : m.prop_res) {
                     std::get<0>(r) = taylor_outcome::cb_stop;
                 }
-                return {std::nullopt, std::move(o.cb)};
+                return finish();
             }
         }
         if (n_done == n || ste_detected) {
-            return {std::nullopt, std::move(o.cb)};
+            return finish();
         }
         if (iter_counter == o.max_steps) {
             for (auto &r : m.prop_res) {
                 std::get<0>(r) = taylor_outcome::step_limit;
             }
-            return {std::nullopt, std::move(o.cb)};
+            return finish();
         }
     }
 }

@@ -307,6 +307,16 @@ typedef int (*hy_step_callback)(void *user);
 int hy_batch_propagate_until_cout_cb(hy_batch *, const double *t_final_hi, const double *t_final_lo,
                                      const double *max_delta_t, uint64_t max_steps, hy_step_callback cb, void *user,
                                      hy_cout **out);
+/* A recording driven by the caller's own lock-step loop over hy_batch_step(..., write_tc = 1) (integrators with events:
+ * their callbacks are host code; update_c_out(), src/taylor_adaptive_batch.cpp:1320-1346): begin() notes the starting
+ * times, append() the Taylor coefficients of the state variables and the times after an iteration, finish() builds the
+ * continuous output (forward[lane] != 0: the lane moves forwards in time; *out = NULL if nothing was recorded) and
+ * destroys the recorder; destroy() abandons it. */
+typedef struct hy_cout_rec hy_cout_rec;
+int hy_cout_rec_begin(hy_batch *, hy_cout_rec **out);
+int hy_cout_rec_append(hy_batch *, hy_cout_rec *);
+int hy_cout_rec_finish(hy_batch *, hy_cout_rec *, const unsigned char *forward, hy_cout **out);
+void hy_cout_rec_destroy(hy_cout_rec *);
 int hy_cout_eval(hy_cout *, const double *tm, double *out);
 /* Per-lane time range [lb, ub] covered (the initial and the final time), number of recorded iterations. */
 int hy_cout_get_bounds(const hy_cout *, double *lb, double *ub);

@@ -592,6 +592,35 @@ static void test_continuous_output()
                                                }),
                            std::domain_error, "from the callback");
     }
+    // Continuous output of an integrator WITH events (the host lock-step loop records every iteration on the device,
+    // hy_cout_rec_*): x = sin t, the non-terminal event v = 0 fires at pi / 2 + k pi; a stopping terminal event ends the
+    // recording at the event time.
+    {
+        auto [x3, v3] = make_vars("x", "v");
+        const std::vector<double> ic3{0., 0., 0., 0., 1., 1., 1., 1.};
+        std::size_t n_ev_calls = 0;
+        nt_event_batch<double> nte(v3, [&n_ev_calls](taylor_adaptive_batch<double> &, double, int, std::uint32_t) {
+            ++n_ev_calls;
+        });
+        taylor_adaptive_batch<double> te_ta{{prime(x3) = v3, prime(v3) = -x3}, ic3, 4u, kw::nt_events = {nte}};
+        auto [co_ev, cb_ev] = te_ta.propagate_until(10., kw::c_output = true);
+        REQUIRE(co_ev.has_value());
+        REQUIRE(n_ev_calls == 12u); // three zeros of cos t below 10 in each of the four lanes
+        REQUIRE(co_ev->get_bounds().second == std::vector<double>(4u, 10.));
+        for (const double tq : {0.3, 2., 5.5, 9.9}) {
+            const auto &sv = (*co_ev)(tq);
+            REQUIRE(std::abs(sv[0] - std::sin(tq)) < 1e-13);
+            REQUIRE(std::abs(sv[4] - std::cos(tq)) < 1e-13);
+        }
+        t_event_batch<double> te(x3 + 0.5, kw::direction = event_direction::negative);
+        taylor_adaptive_batch<double> te_tb{{prime(x3) = v3, prime(v3) = -x3}, ic3, 4u, kw::t_events = {te}};
+        auto [co_te, cb_te] = te_tb.propagate_until(20., kw::c_output = true);
+        REQUIRE(co_te.has_value());
+        const double t_ev = 7. * 3.141592653589793 / 6.;
+        REQUIRE(std::abs(te_tb.get_time()[0] - t_ev) < 1e-13);
+        REQUIRE(co_te->get_bounds().second == te_tb.get_time());
+        REQUIRE(static_cast<std::int64_t>(std::get<0>(te_tb.get_propagate_res()[0])) == -1);
+    }
 }
 
 // Event detection through the drop-in class: blocks of test/batch_event_detection.cpp.

@@ -181,3 +181,46 @@ def test_event_api_errors_gpu():
     tb = make(sys, ec.PEND_IC, 4)
     with pytest.raises(ValueError, match="No events"):
         tb.reset_cooldowns()
+
+
+def test_continuous_output_with_events_gpu():
+    """propagate_until(c_output=True) of an integrator WITH events (src/taylor_adaptive_batch.cpp:1320-1346 inside the
+    lock-step loop at :1372-1527): every iteration of the host loop is recorded on the device (hy_cout_rec_*). Harmonic
+    oscillators x = A sin t: the non-terminal event v = 0 fires at pi / 2 + k pi in every lane; the continuous output
+    reproduces A sin t / A cos t over the whole range, its bounds are the initial and the final time, one recorded step per
+    iteration. With a terminal event x = -A / 2 (t = 7 pi / 6) the recording ends at the event time."""
+    from test_oracle_golden import sys_oscillator
+    x, v = hb.make_vars("x", "v")
+    amp = np.array([1.0, 1.1, 1.2, 1.3])
+    ic = np.stack([np.zeros(4), amp])
+    hits = []
+    ev = hb.nt_event_batch(v, lambda ta, t, d_sgn, lane: hits.append((lane, t)))
+    ta = hb.taylor_adaptive_batch(sys_oscillator(), ic, 4, nt_events=[ev])
+    tf = np.array([10.0, 10.5, 11.0, 11.5])
+    calls = []
+    co = ta.propagate_until(tf, c_output=True, callback=lambda t: calls.append(1) or True)
+    assert co is not None and np.array_equal(ta.time, tf)
+    assert co.get_n_steps() == len(calls)
+    lb, ub = co.get_bounds()
+    assert np.all(lb == 0) and np.array_equal(ub, tf)
+    for lane in range(4):
+        got = sorted(t for ln, t in hits if ln == lane)
+        exp = [np.pi / 2 + k * np.pi for k in range(4) if np.pi / 2 + k * np.pi < tf[lane]]
+        assert np.allclose(got, exp, rtol=1e-14)
+    for tq in (0.0, 0.3, 2.0, 5.5, 9.9):
+        s = co(tq)
+        assert np.max(np.abs(s[0] - amp * np.sin(tq))) < 1e-13 and np.max(np.abs(s[1] - amp * np.cos(tq))) < 1e-13
+    # The same propagation without events: the recordings agree to rounding (the step sizes need not be the same: the
+    # event equations take part in the step-size estimate).
+    ref = hb.taylor_adaptive_batch(sys_oscillator(), ic, 4)
+    co_ref = ref.propagate_until(tf, c_output=True)
+    assert np.max(np.abs(co(4.2) - co_ref(4.2))) < 1e-13
+    # A stopping terminal event: the recording ends where the integrator stopped.
+    te = hb.t_event_batch(x + 0.5, direction=hb.event_direction.negative)
+    tb = hb.taylor_adaptive_batch(sys_oscillator(), np.stack([np.zeros(4), np.ones(4)]), 4, t_events=[te])
+    co2 = tb.propagate_until(20.0, c_output=True)
+    assert co2 is not None
+    t_ev = 7 * np.pi / 6
+    assert np.allclose(tb.time, t_ev, rtol=1e-14) and np.array_equal(co2.get_bounds()[1], tb.time)
+    assert np.max(np.abs(co2(3.0)[0] - np.sin(3.0))) < 1e-13
+    assert all(r[0] == -1 for r in tb.propagate_res)  # outcome = -index - 1 of the stopping terminal event
