@@ -1724,6 +1724,7 @@ int hy_batch_create_multi(const hy_program *p, uint32_t batch, const int *device
             b->shards.push_back(sh);
             b->shard_off.push_back(b->shard_off.back() + lanes);
         }
+        b->n_ev = b->shards.empty() ? 0u : b->shards[0]->n_ev; // (event equations: every shard detects its own lanes' events)
         *out = b;
         return HY_OK;
     } catch (...) {
@@ -2135,6 +2136,17 @@ int hy_batch_step(hy_batch *b, const double *max_delta_t, int on_device, int bac
                     throw std::invalid_argument(hy_last_error());
                 }
             });
+            if (b->n_ev != 0u) {
+                // The events of the step, lanes ascending like on one device: the shards' lists one after the other,
+                // with the lanes of the whole batch.
+                b->ev_host.clear();
+                for (std::size_t i = 0; i < b->shards.size(); ++i) {
+                    for (hy_event_rec r : b->shards[i]->ev_host) {
+                        r.lane += b->shard_off[i];
+                        b->ev_host.push_back(r);
+                    }
+                }
+            }
             return HY_OK;
         }
         device_guard guard(b->device);
@@ -2379,9 +2391,10 @@ void check_grid(hy_batch *b, const double *grid, uint64_t n_pts, const double *m
     // The current time must be finite (:1590-1594).
     std::vector<double> t_hi(n), t_lo(n);
     {
-        HY_CUDA_CHECK(cudaMemcpyAsync(t_hi.data(), b->d_t_hi, sizeof(double) * n, cudaMemcpyDeviceToHost, b->stream));
-        HY_CUDA_CHECK(cudaMemcpyAsync(t_lo.data(), b->d_t_lo, sizeof(double) * n, cudaMemcpyDeviceToHost, b->stream));
-        HY_CUDA_CHECK(cudaStreamSynchronize(b->stream));
+        // (Through the download entry point: it also serves a batch made of shards.)
+        if (hy_batch_download(b, nullptr, t_hi.data(), t_lo.data(), nullptr) != HY_OK) {
+            throw cuda_error(hy_last_error());
+        }
         for (std::uint32_t i = 0; i < n; ++i) {
             if (!std::isfinite(t_hi[i]) || !std::isfinite(t_lo[i])) {
                 throw std::invalid_argument("Cannot invoke propagate_grid() in an adaptive Taylor integrator in "
@@ -3096,7 +3109,16 @@ int hy_batch_set_events(hy_batch *b, uint32_t n_te, const int32_t *dirs, const d
             throw std::invalid_argument("Null pointer passed to hy_batch_set_events()");
         }
         if (!b->shards.empty()) {
-            throw hy::detail::not_implemented_error("Event detection is not available on a multi-device batch");
+            // (Directions, cooldowns and tolerance are per event, not per lane: every shard gets them all.)
+            for (auto *sh : b->shards) {
+                if (hy_batch_set_events(sh, n_te, dirs, cooldowns, tol) != HY_OK) {
+                    throw std::invalid_argument(hy_last_error());
+                }
+            }
+            b->n_te = n_te;
+            b->ev_set = true;
+            b->ev_host.clear();
+            return HY_OK;
         }
         device_guard guard(b->device);
         HY_CUDA_CHECK(cudaStreamSynchronize(b->stream));
@@ -3129,6 +3151,18 @@ int hy_batch_download_tc_events(hy_batch *b, double *out)
         if (b == nullptr || out == nullptr) {
             throw std::invalid_argument("Null pointer passed to hy_batch_download_tc_events()");
         }
+        if (!b->shards.empty()) {
+            for_each_shard(b, [&](hy_batch *sh, std::size_t i) {
+                if (sh->n_ev == 0u || sh->d_tc == nullptr) {
+                    throw std::invalid_argument("No Taylor coefficients of event equations are available");
+                }
+                const std::size_t rows = static_cast<std::size_t>(sh->order + 1u) * sh->n_ev;
+                rows_d2h(sh, out, sh->d_tc + static_cast<std::size_t>(sh->order + 1u) * sh->n * sh->n_eq, rows, b->n,
+                         b->shard_off[i]);
+                HY_CUDA_CHECK(cudaStreamSynchronize(sh->stream));
+            });
+            return HY_OK;
+        }
         if (b->n_ev == 0u || b->d_tc == nullptr) {
             throw std::invalid_argument("No Taylor coefficients of event equations are available");
         }
@@ -3156,6 +3190,17 @@ int hy_batch_reset_cooldowns(hy_batch *b, int64_t lane)
             throw std::invalid_argument("Cannot reset the cooldowns at batch index " + std::to_string(lane)
                                         + ": the batch size is only " + std::to_string(b->n));
         }
+        if (!b->shards.empty()) {
+            for (std::size_t i = 0; i < b->shards.size(); ++i) {
+                const auto lo = static_cast<int64_t>(b->shard_off[i]), hi = static_cast<int64_t>(b->shard_off[i + 1u]);
+                if (lane < 0 || (lane >= lo && lane < hi)) {
+                    if (hy_batch_reset_cooldowns(b->shards[i], lane < 0 ? lane : lane - lo) != HY_OK) {
+                        throw std::invalid_argument(hy_last_error());
+                    }
+                }
+            }
+            return HY_OK;
+        }
         device_guard guard(b->device);
         const std::size_t m = static_cast<std::size_t>(b->n_te) * b->n;
         if (m != 0u) {
@@ -3174,6 +3219,28 @@ int hy_batch_get_cooldowns(hy_batch *b, uint8_t *active, double *spent, double *
     try {
         if (b == nullptr || !b->ev_set) {
             throw std::invalid_argument("No events are defined for this integrator");
+        }
+        if (!b->shards.empty()) {
+            // [n_te][batch] arrays: every shard fills its columns.
+            for (std::size_t i = 0; i < b->shards.size(); ++i) {
+                hy_batch *sh = b->shards[i];
+                const std::size_t ms = static_cast<std::size_t>(b->n_te) * sh->n;
+                std::vector<uint8_t> a(ms);
+                std::vector<double> sp(ms), cdw(ms);
+                if (hy_batch_get_cooldowns(sh, a.data(), sp.data(), cdw.data()) != HY_OK) {
+                    throw std::invalid_argument(hy_last_error());
+                }
+                for (std::uint32_t k = 0; k < b->n_te; ++k) {
+                    for (std::uint32_t l = 0; l < sh->n; ++l) {
+                        const std::size_t dst = static_cast<std::size_t>(k) * b->n + b->shard_off[i] + l,
+                                          src = static_cast<std::size_t>(k) * sh->n + l;
+                        active[dst] = a[src];
+                        spent[dst] = sp[src];
+                        cooldown[dst] = cdw[src];
+                    }
+                }
+            }
+            return HY_OK;
         }
         device_guard guard(b->device);
         const std::size_t m = static_cast<std::size_t>(b->n_te) * b->n;
@@ -3200,6 +3267,30 @@ int hy_batch_set_cooldowns(hy_batch *b, const uint8_t *active, const double *spe
     try {
         if (b == nullptr || !b->ev_set) {
             throw std::invalid_argument("No events are defined for this integrator");
+        }
+        if (!b->shards.empty()) {
+            if (b->n_te != 0u && (active == nullptr || spent == nullptr || cooldown == nullptr)) {
+                throw std::invalid_argument("Null pointer passed to hy_batch_set_cooldowns()");
+            }
+            for (std::size_t i = 0; i < b->shards.size(); ++i) {
+                hy_batch *sh = b->shards[i];
+                const std::size_t ms = static_cast<std::size_t>(b->n_te) * sh->n;
+                std::vector<uint8_t> a(ms);
+                std::vector<double> sp(ms), cdw(ms);
+                for (std::uint32_t k = 0; k < b->n_te; ++k) {
+                    for (std::uint32_t l = 0; l < sh->n; ++l) {
+                        const std::size_t src = static_cast<std::size_t>(k) * b->n + b->shard_off[i] + l,
+                                          dst = static_cast<std::size_t>(k) * sh->n + l;
+                        a[dst] = active[src];
+                        sp[dst] = spent[src];
+                        cdw[dst] = cooldown[src];
+                    }
+                }
+                if (hy_batch_set_cooldowns(sh, a.data(), sp.data(), cdw.data()) != HY_OK) {
+                    throw std::invalid_argument(hy_last_error());
+                }
+            }
+            return HY_OK;
         }
         device_guard guard(b->device);
         const std::size_t m = static_cast<std::size_t>(b->n_te) * b->n;

@@ -356,9 +356,6 @@ void taylor_adaptive_batch<double>::finalise_ctor(std::vector<std::pair<expressi
     for (const auto &e : o.ntes) {
         ev_ex.push_back(e.get_expression());
     }
-    if (!ev_ex.empty() && !o.devices.empty()) {
-        throw not_implemented_error("Event detection is not available on an integrator sharded over several devices");
-    }
     validate_ode_sys(sys, ev_ex);
     m.tes = std::move(o.tes);
     m.ntes = std::move(o.ntes);
