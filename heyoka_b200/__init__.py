@@ -984,7 +984,9 @@ class taylor_adaptive_batch:
                 raise ValueError("Invalid number of max timesteps specified in a Taylor integrator in batch mode: the "
                                  "batch size is %d, but the number of specified timesteps is %d" % (n, md.size))
             max_delta_t = np.ascontiguousarray(md)
-        if self._with_events or callback is not None:
+        if self._with_events or callback is not None or self._b.n_shards != 0:
+            # (Host loop: events and step callbacks are host code; a batch sharded over several devices samples its grid
+            # through the dense output of its shards.)
             return self._propagate_grid_host(g.reshape(-1, n), max_delta_t, max_steps, callback)
         self._push()
         out = self._b.propagate_grid(g.reshape(-1, n), max_delta_t, max_steps)

@@ -1054,9 +1054,10 @@ taylor_adaptive_batch<double>::propagate_grid_impl(const std::vector<double> &gr
                                     + std::to_string(n) + ", but the number of specified timesteps is "
                                     + std::to_string(o.max_delta_t.size()));
     }
-    if (o.cb || with_events()) {
+    if (o.cb || with_events() || !m.devices.empty()) {
         // A step callback (or events, whose callbacks also run on the host) after every step: the reference's loop on the
-        // host, one device step per iteration.
+        // host, one device step per iteration. A batch sharded over several devices takes it too (the grid is sampled
+        // through the dense output of the shards).
         return propagate_grid_events(grid, std::move(o));
     }
     std::vector<double> retval(grid.size() * m.dim);
