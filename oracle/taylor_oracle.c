@@ -54,6 +54,8 @@
 
 #define ORACLE_PAIRWISE 1
 #define ORACLE_FMA 2
+/* ORACLE_W != 1 only: run the per-lane scalar tail (step size, state update) instead of the SIMD one (A/B check). */
+#define ORACLE_SCALAR_TAIL 4
 
 #if ORACLE_W == 1
 typedef double real_t;
@@ -79,7 +81,7 @@ typedef struct {
     uint32_t lane0;   /* first lane of this group */
     uint32_t nl;      /* valid lanes in this group (<= ORACLE_W) */
     const double *pars;
-    real_t *T; /* tape: T[o * n_uvars + u] */
+    real_t *T; /* tape: T[o * n_uvars + u]; followed by 3 * n_eq vectors of scratch (alloc_tape()) */
     int mode;
 } ctx_t;
 
@@ -628,6 +630,13 @@ static void compute_jet(ctx_t *c, const double *state, const double *t_hi)
     }
     for (uint32_t i = 0; i < P->n_eq; ++i) {
         real_t v = R_SPLAT(0.);
+#if ORACLE_W != 1
+        if (c->nl == ORACLE_W) {
+            memcpy(&v, state + (size_t)i * c->batch + c->lane0, sizeof(v)); /* the lanes of a variable are contiguous */
+            TAPE(c, 0, i) = v;
+            continue;
+        }
+#endif
         for (uint32_t l = 0; l < ORACLE_W; ++l) {
             const uint32_t ll = l < c->nl ? l : c->nl - 1u;
             R_SET(v, l, state[(size_t)i * c->batch + c->lane0 + ll]);
@@ -768,6 +777,122 @@ static void update_state(const ctx_t *c, uint32_t l, double h, double *state)
     }
 }
 
+#if ORACLE_W != 1
+/* ---- SIMD tail: the same step size and state update on all the lanes of the group at once -----
+ * In the reference the step-size deduction and the state update are part of the JIT-compiled step function and
+ * operate on SIMD vectors of batch_size lanes like the jet (src/taylor_00.cpp:102-460, :712-865). The timed CPU
+ * baseline does the same; the operations of every lane are those of determine_h() / update_state() above, in the
+ * same order (tests/test_codegen_cpu.py checks that the two tails agree to the bit). */
+typedef long long imask_t __attribute__((vector_size(ORACLE_W * 8)));
+
+static inline real_t v_abs(real_t x)
+{
+    const imask_t m = (imask_t){0} + 0x7fffffffffffffffll;
+    return (real_t)((imask_t)x & m);
+}
+/* std::max(a, b) = (a < b) ? b : a, lane by lane. */
+static inline real_t v_std_max(real_t a, real_t b)
+{
+    const imask_t m = a < b;
+    return (real_t)(((imask_t)b & m) | ((imask_t)a & ~m));
+}
+static real_t v_pairwise_max(real_t *v, uint32_t n)
+{
+    while (n != 1u) {
+        uint32_t m = 0;
+        for (uint32_t i = 0; i < n; i += 2u) {
+            v[m++] = (i + 1u == n) ? v[i] : v_std_max(v[i], v[i + 1u]);
+        }
+        n = m;
+    }
+    return v[0];
+}
+
+/* A value the optimiser cannot see through: keeps the product of the compensated summation from being fused
+ * into the subtraction that follows it (-ffp-contract=fast is on in this build). Off the critical path. */
+static inline real_t v_opaque(real_t x)
+{
+    __asm__("" : "+m"(x));
+    return x;
+}
+
+static void step_tail_v(const ctx_t *c, double *state, double *h_inout)
+{
+    const hy_program_desc *P = c->P;
+    const uint32_t p = P->order, n_eq = P->n_eq;
+    real_t m0, mp, mp1, h;
+
+    /* taylor_determine_h(): the three norms by SIMD maxima, the two pow() calls lane by lane. */
+    if (c->mode & ORACLE_PAIRWISE) {
+        real_t *v0 = c->T + (size_t)P->n_uvars * (p + 1u), *vp = v0 + n_eq, *vp1 = vp + n_eq;
+        for (uint32_t i = 0; i < n_eq; ++i) {
+            v0[i] = v_abs(TAPE(c, 0, i));
+            vp[i] = v_abs(TAPE(c, p, i));
+            vp1[i] = v_abs(TAPE(c, p - 1u, i));
+        }
+        m0 = v_pairwise_max(v0, n_eq);
+        mp = v_pairwise_max(vp, n_eq);
+        mp1 = v_pairwise_max(vp1, n_eq);
+    } else {
+        m0 = v_abs(TAPE(c, 0, 0));
+        mp = v_abs(TAPE(c, p, 0));
+        mp1 = v_abs(TAPE(c, p - 1u, 0));
+        for (uint32_t i = 1; i < n_eq; ++i) {
+            m0 = v_std_max(m0, v_abs(TAPE(c, 0, i)));
+            mp = v_std_max(mp, v_abs(TAPE(c, p, i)));
+            mp1 = v_std_max(mp1, v_abs(TAPE(c, p - 1u, i)));
+        }
+    }
+    const double rhofac = rhofac_of(p);
+    h = R_SPLAT(0.);
+    for (uint32_t l = 0; l < ORACLE_W; ++l) {
+        const uint32_t ll = l < c->nl ? l : c->nl - 1u;
+        const double max_delta_t = h_inout[c->lane0 + ll];
+        const double num_rho = (m0[l] <= 1.) ? 1. : m0[l];
+        const double rho_o = pow(num_rho / mp[l], 1. / (double)p);
+        const double rho_om1 = pow(num_rho / mp1[l], 1. / (double)(p - 1u));
+        const double rho_m = std_min(rho_o, rho_om1);
+        double hl = rho_m * rhofac;
+        hl = std_min(hl, fabs(max_delta_t));
+        h[l] = (max_delta_t < 0.) ? -1. * hl : 1. * hl;
+    }
+
+    /* taylor_run_multihorner() / taylor_run_ceval(). */
+    for (uint32_t i = 0; i < n_eq; ++i) {
+        real_t res;
+        if (!P->high_accuracy) {
+            res = TAPE(c, p, i);
+            for (uint32_t o = 1; o <= p; ++o) {
+                res = TAPE(c, p - o, i) + res * h;
+            }
+        } else {
+            real_t comp = R_SPLAT(0.), cur_h = h;
+            res = TAPE(c, 0, i);
+            for (uint32_t o = 1; o <= p; ++o) {
+                const real_t tmp = v_opaque(TAPE(c, o, i) * cur_h);
+                const real_t y = tmp - comp;
+                const real_t t = res + y;
+                const real_t d = t - res;
+                comp = d - y;
+                res = t;
+                cur_h = cur_h * h;
+            }
+        }
+        double *dst = state + (size_t)i * c->batch + c->lane0;
+        if (c->nl == ORACLE_W) {
+            memcpy(dst, &res, sizeof(res));
+        } else {
+            for (uint32_t l = 0; l < c->nl; ++l) {
+                dst[l] = res[l];
+            }
+        }
+    }
+    for (uint32_t l = 0; l < c->nl; ++l) {
+        h_inout[c->lane0 + l] = h[l];
+    }
+}
+#endif
+
 /* ---- double-length time (include/heyoka/detail/dfloat.hpp:104-169) -------------------------- */
 typedef struct {
     double hi, lo;
@@ -818,6 +943,21 @@ static void step_group(ctx_t *c, double *state, const double *t_hi, double *h_in
 
     compute_jet(c, state, t_hi);
 
+#if ORACLE_W != 1
+    if (!(c->mode & ORACLE_SCALAR_TAIL)) {
+        step_tail_v(c, state, h_inout);
+        if (tc != NULL) {
+            for (uint32_t l = 0; l < c->nl; ++l) {
+                for (uint32_t i = 0; i < P->n_eq; ++i) {
+                    for (uint32_t o = 0; o <= P->order; ++o) {
+                        tc[((size_t)i * (P->order + 1u) + o) * c->batch + c->lane0 + l] = R_GET(TAPE(c, o, i), l);
+                    }
+                }
+            }
+        }
+        return;
+    }
+#endif
     for (uint32_t l = 0; l < c->nl; ++l) {
         const size_t lane = c->lane0 + l;
         const double h = determine_h(c, l, h_inout[lane]);
@@ -836,7 +976,7 @@ static void step_group(ctx_t *c, double *state, const double *t_hi, double *h_in
 static real_t *alloc_tape(const hy_program_desc *P)
 {
     void *p = NULL;
-    const size_t n = (size_t)P->n_uvars * (P->order + 1u);
+    const size_t n = (size_t)P->n_uvars * (P->order + 1u) + 3u * (size_t)P->n_eq; /* + scratch of the SIMD tail */
     if (posix_memalign(&p, 64, n * sizeof(real_t)) != 0) {
         return NULL;
     }

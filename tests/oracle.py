@@ -17,6 +17,7 @@ ORACLE_DIR = os.path.join(ROOT, "oracle")
 PAIRWISE = 1  # default-mode (non-compact) summation order of the reference
 FMA = 2       # sequential + fused multiply-add: the order the CUDA kernels use
 SEQ = 0       # compact-mode summation order, no contraction
+SCALAR_TAIL = 4  # width 4 / 8 only: step size and state update lane by lane instead of on SIMD vectors (A/B check)
 
 _dp = C.POINTER(C.c_double)
 

@@ -125,3 +125,30 @@ def test_random_expressions_codegen(seed):
     scale = np.maximum(np.max(np.abs(ref.tc[:, 0, :]), axis=0), 1.0)[None, None, :]
     assert np.max(np.abs(o.tc - ref.tc) * w / scale) < 1e-13, seed
     assert np.max(np.abs(o.last_h / ref.last_h - 1)) < 1e-11
+
+
+@pytest.mark.parametrize("W", WIDTHS)
+@pytest.mark.parametrize("ha", [False, True])
+@pytest.mark.parametrize("mode", [oracle.PAIRWISE, oracle.FMA])
+def test_simd_tail_equals_scalar_tail(W, ha, mode):
+    """The timed ports deduce the step size and update the state on SIMD vectors (oracle/taylor_oracle.c
+    step_tail_v(), like the reference's JIT-compiled step function src/taylor_00.cpp:102-460); the per-lane scalar
+    tail (determine_h() / update_state()) stays selectable: both give the same bits - in particular the compensated
+    summation of high_accuracy is not contracted - on full and on ragged groups of lanes, with step limits of both
+    signs, and over a propagation."""
+    P = hb.Program(sys_outer_ss(), high_accuracy=ha)
+    n = 2 * W + 3
+    st = outer_ss_batch_state(n)
+    lim = np.where(np.arange(n) % 3 == 0, 0.11, np.inf) * np.where(np.arange(n) % 5 == 4, -1., 1.)
+    a = oracle.OracleIntegrator(P, st, n, mode=mode, width=W)
+    b = oracle.OracleIntegrator(P, st, n, mode=mode | oracle.SCALAR_TAIL, width=W)
+    for o in (a, b):
+        o.step(lim, write_tc=True)
+    assert np.array_equal(a.last_h, b.last_h) and np.array_equal(a.state, b.state) and np.array_equal(a.tc, b.tc)
+    assert np.array_equal(a.step_outcome, b.step_outcome)
+    assert np.count_nonzero(a.last_h == lim) >= n // 3 - 1 and np.any(a.last_h < 0)
+    tf = a.t_hi + np.where(a.last_h < 0, -7.0, 7.0)
+    for o in (a, b):
+        o.propagate_until(tf, lockstep=False)
+    assert np.array_equal(a.n_steps, b.n_steps) and np.array_equal(a.state, b.state)
+    assert np.array_equal(a.t_hi, b.t_hi) and np.array_equal(a.t_lo, b.t_lo)
