@@ -224,53 +224,3 @@ def test_continuous_output_with_events_gpu():
     assert np.allclose(tb.time, t_ev, rtol=1e-14) and np.array_equal(co2.get_bounds()[1], tb.time)
     assert np.max(np.abs(co2(3.0)[0] - np.sin(3.0))) < 1e-13
     assert all(r[0] == -1 for r in tb.propagate_res)  # outcome = -index - 1 of the stopping terminal event
-
-
-def test_sharded_event_batch_equals_single_device():
-    """Events on a batch made of shards (hy_batch_create_multi(): here three shards on one GPU, uneven blocks of lanes):
-    every shard detects the events of its own lanes, the records come back with the lanes of the whole batch in the same
-    order. Bit for bit what the single-device batch produces over 40 lock-step steps with two terminal and two
-    non-terminal events (event lists with times, outcomes, step sizes, states, times, Taylor coefficients of the event
-    equations, cooldown state), propagate_until() and propagate_grid() through the front end's host loops, and the
-    reference-side fixtures of test/batch_event_detection.cpp on the sharded batch."""
-    x, v, sys = ec.pendulum_sys()
-    batch = 37
-    rng = np.random.default_rng(17)
-    st = np.stack([rng.uniform(-0.5, 0.5, batch), rng.uniform(-1.0, 1.0, batch)])
-
-    def build(**kw):
-        return make(sys, st, batch, t_events=[hb.t_event_batch(v, callback=lambda ta, s, i: True),
-                                              hb.t_event_batch(x - 0.1, callback=lambda ta, s, i: True, cooldown=0.05,
-                                                               direction=hb.event_direction.positive)],
-                    nt_events=[hb.nt_event_batch(v * v - 1e-2, lambda ta, t, s, i: None),
-                               hb.nt_event_batch(x * v + 0.05 * hb.cos(hb.time), lambda ta, t, s, i: None,
-                                                 direction=hb.event_direction.negative)], **kw)
-
-    one, many = build(), build(device=[0, 0, 0])
-    assert many._b.n_shards == 3 and one._b.n_shards == 0
-    n_events = 0
-    for it in range(40):
-        one.step()
-        many.step()
-        assert one._b.events() == many._b.events(), it
-        n_events += len(one._b.events())
-        assert one.step_res == many.step_res
-        assert np.array_equal(one.state, many.state) and np.array_equal(one.time, many.time)
-        assert np.array_equal(one._b.tc_events(4), many._b.tc_events(4))
-        for a, b in zip(one._b.cooldowns(2), many._b.cooldowns(2)):
-            assert np.array_equal(a, b)
-    assert n_events > batch
-    one.propagate_until(one.time + 3.0)
-    many.propagate_until(many.time + 3.0)
-    assert one.propagate_res == many.propagate_res and np.array_equal(one.state, many.state)
-    many.reset_cooldowns(5)
-    many.reset_cooldowns()
-    assert not np.any(many._b.cooldowns(2)[0])
-    # The reference's fixtures on the sharded batch.
-    sharded = lambda *a, **k: make(*a, device=[0, 0, 0], **k)  # noqa: E731
-    times = ec.case_linear_box(sharded)
-    assert np.allclose(sorted(times), [1 / 8., 1 / 4., 1 / 2., 1.], rtol=1e-15)
-    ec.case_multizero(sharded)
-    ec.case_nte_basic(sharded)
-    ec.case_te_basic(sharded)
-    ec.case_te_propagate_grid(sharded)

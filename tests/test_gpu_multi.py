@@ -107,11 +107,7 @@ def test_sharded_with_parameters_and_time():
         ta.propagate_for(np.linspace(1.0, 3.0, batch))
     _same(one, many)
     assert one.propagate_res == many.propagate_res
-    # propagate_grid() of a sharded batch runs the front end's host loop; continuous output is single-device only.
-    g = np.array([many.time, many.time + 0.5, many.time + 1.0])
-    assert np.max(np.abs(many.propagate_grid(g) - one.propagate_grid(g))) < 1e-13
-    with pytest.raises(NotImplementedError, match="multi-device"):
-        many.propagate_until(many.time + 1.0, c_output=True)
+    # (propagate_grid() and continuous output of this sharded batch: tests/test_zz_gpu_sharded_front_ends.py)
 
 
 @pytest.mark.parametrize("devs", [None, [0, 0, 0]] + ([[0, 1]] if hb.lib.hy_device_count() >= 2 else []))
@@ -159,23 +155,3 @@ def test_propagate_until_host_one_call(devs):
         b.propagate_until_host(st.copy(), np.full(batch, np.inf), np.zeros(batch), tf)
     with pytest.raises(ValueError, match="non-finite time was passed"):
         b.propagate_until_host(st.copy(), np.zeros(batch), np.zeros(batch), np.full(batch, np.nan))
-
-
-def test_propagate_grid_on_a_sharded_batch():
-    """propagate_grid() of a batch made of shards (the front end's host loop over the shards' steps and dense output)
-    against the device-resident grid loop of the single-device batch: same step counts, same samples (to 1e-13: one
-    evaluates the dense output at absolute times, the other at offsets from the start of the step)."""
-    batch, n_pts = 21, 40
-    st = outer_ss_batch_state(batch)
-    grid = np.linspace(0., 15., n_pts)[:, None] * np.linspace(1., 1.3, batch)[None, :]
-    one = hb.taylor_adaptive_batch(sys_outer_ss(), st, batch, high_accuracy=True)
-    many = hb.taylor_adaptive_batch(sys_outer_ss(), st, batch, high_accuracy=True, device=[0, 0, 0])
-    a, b = one.propagate_grid(grid), many.propagate_grid(grid)
-    assert a.shape == b.shape == (n_pts, 36, batch)
-    # (Relative to the amplitude of each variable over the grid: a coordinate that crosses zero at a grid point would
-    # otherwise turn one unit in the last place of the amplitude into a large relative error.)
-    scale = np.max(np.abs(a), axis=0, keepdims=True)
-    assert np.max(np.abs(a - b) / scale) < 1e-13
-    assert [r[0] for r in one.propagate_res] == [r[0] for r in many.propagate_res]
-    assert [r[3] for r in one.propagate_res] == [r[3] for r in many.propagate_res]
-    assert np.array_equal(one.time, many.time) and np.max(np.abs(one.state - many.state)) == 0.

@@ -1,0 +1,106 @@
+"""The front ends' host loops on a batch made of shards (hy_batch_create_multi()): event detection and
+propagate_grid(). Both run the reference's lock-step loops on the host (src/taylor_adaptive_batch.cpp:728-1035,
+:1696-2053) over the shards' steps and dense output, and must give what the single-device batch gives.
+
+These two tests were written at the very end of round 2, after the round's last full run of the GPU suite
+(profiles/r2_pytest_gpu_tail.log): the file sorts after the others so that `pytest -x` reaches them last."""
+import numpy as np
+import pytest
+
+import event_cases as ec
+import heyoka_b200 as hb
+from common import outer_ss_batch_state, sys_outer_ss, sys_tutorial
+
+pytestmark = pytest.mark.gpu
+
+
+def make(*a, **k):
+    return hb.taylor_adaptive_batch(*a, **k)
+
+
+def test_sharded_event_batch_equals_single_device():
+    """Events on a batch made of shards (hy_batch_create_multi(): here three shards on one GPU, uneven blocks of lanes):
+    every shard detects the events of its own lanes, the records come back with the lanes of the whole batch in the same
+    order. Bit for bit what the single-device batch produces over 40 lock-step steps with two terminal and two
+    non-terminal events (event lists with times, outcomes, step sizes, states, times, Taylor coefficients of the event
+    equations, cooldown state), propagate_until() and propagate_grid() through the front end's host loops, and the
+    reference-side fixtures of test/batch_event_detection.cpp on the sharded batch."""
+    x, v, sys = ec.pendulum_sys()
+    batch = 37
+    rng = np.random.default_rng(17)
+    st = np.stack([rng.uniform(-0.5, 0.5, batch), rng.uniform(-1.0, 1.0, batch)])
+
+    def build(**kw):
+        return make(sys, st, batch, t_events=[hb.t_event_batch(v, callback=lambda ta, s, i: True),
+                                              hb.t_event_batch(x - 0.1, callback=lambda ta, s, i: True, cooldown=0.05,
+                                                               direction=hb.event_direction.positive)],
+                    nt_events=[hb.nt_event_batch(v * v - 1e-2, lambda ta, t, s, i: None),
+                               hb.nt_event_batch(x * v + 0.05 * hb.cos(hb.time), lambda ta, t, s, i: None,
+                                                 direction=hb.event_direction.negative)], **kw)
+
+    one, many = build(), build(device=[0, 0, 0])
+    assert many._b.n_shards == 3 and one._b.n_shards == 0
+    n_events = 0
+    for it in range(40):
+        one.step()
+        many.step()
+        assert one._b.events() == many._b.events(), it
+        n_events += len(one._b.events())
+        assert one.step_res == many.step_res
+        assert np.array_equal(one.state, many.state) and np.array_equal(one.time, many.time)
+        assert np.array_equal(one._b.tc_events(4), many._b.tc_events(4))
+        for a, b in zip(one._b.cooldowns(2), many._b.cooldowns(2)):
+            assert np.array_equal(a, b)
+    assert n_events > batch
+    one.propagate_until(one.time + 3.0)
+    many.propagate_until(many.time + 3.0)
+    assert one.propagate_res == many.propagate_res and np.array_equal(one.state, many.state)
+    many.reset_cooldowns(5)
+    many.reset_cooldowns()
+    assert not np.any(many._b.cooldowns(2)[0])
+    # The reference's fixtures on the sharded batch.
+    sharded = lambda *a, **k: make(*a, device=[0, 0, 0], **k)  # noqa: E731
+    times = ec.case_linear_box(sharded)
+    assert np.allclose(sorted(times), [1 / 8., 1 / 4., 1 / 2., 1.], rtol=1e-15)
+    ec.case_multizero(sharded)
+    ec.case_nte_basic(sharded)
+    ec.case_te_basic(sharded)
+    ec.case_te_propagate_grid(sharded)
+
+
+def test_propagate_grid_on_a_sharded_batch():
+    """propagate_grid() of a batch made of shards (the front end's host loop over the shards' steps and dense output)
+    against the device-resident grid loop of the single-device batch: same step counts, same samples (to 1e-13: one
+    evaluates the dense output at absolute times, the other at offsets from the start of the step)."""
+    batch, n_pts = 21, 40
+    st = outer_ss_batch_state(batch)
+    grid = np.linspace(0., 15., n_pts)[:, None] * np.linspace(1., 1.3, batch)[None, :]
+    one = hb.taylor_adaptive_batch(sys_outer_ss(), st, batch, high_accuracy=True)
+    many = hb.taylor_adaptive_batch(sys_outer_ss(), st, batch, high_accuracy=True, device=[0, 0, 0])
+    a, b = one.propagate_grid(grid), many.propagate_grid(grid)
+    assert a.shape == b.shape == (n_pts, 36, batch)
+    # (Relative to the amplitude of each variable over the grid: a coordinate that crosses zero at a grid point would
+    # otherwise turn one unit in the last place of the amplitude into a large relative error.)
+    scale = np.max(np.abs(a), axis=0, keepdims=True)
+    assert np.max(np.abs(a - b) / scale) < 1e-13
+    assert [r[0] for r in one.propagate_res] == [r[0] for r in many.propagate_res]
+    assert [r[3] for r in one.propagate_res] == [r[3] for r in many.propagate_res]
+    assert np.array_equal(one.time, many.time) and np.max(np.abs(one.state - many.state)) == 0.
+
+
+def test_sharded_grid_and_continuous_output_with_parameters():
+    """The tutorial system (runtime parameter, per-lane start times) on four shards: propagate_grid() runs the front
+    end's host loop and agrees with the single-device batch; continuous output is single-device only and says so."""
+    batch = 11
+    rng = np.random.default_rng(3)
+    st = rng.uniform(-1, 1, (2, batch))
+    pars = rng.uniform(0.05, 0.3, (1, batch))
+    t0 = rng.uniform(0, 2, batch)
+    one = hb.taylor_adaptive_batch(sys_tutorial(), st, batch, pars=pars, time=t0)
+    many = hb.taylor_adaptive_batch(sys_tutorial(), st, batch, pars=pars, time=t0, device=[0, 0, 0, 0])
+    for ta in (one, many):
+        ta.step()
+    g = np.array([many.time, many.time + 0.5, many.time + 1.0])
+    assert np.max(np.abs(many.propagate_grid(g) - one.propagate_grid(g))) < 1e-13
+    with pytest.raises(NotImplementedError, match="multi-device"):
+        many.propagate_until(many.time + 1.0, c_output=True)
