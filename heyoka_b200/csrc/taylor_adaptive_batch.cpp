@@ -112,6 +112,7 @@ struct taylor_adaptive_batch<double>::impl {
     bool tc_valid = false; // the device holds the Taylor coefficients mirrored in `tc`
     std::vector<t_event_batch<double>> tes;
     std::vector<nt_event_batch<double>> ntes;
+    std::vector<std::vector<std::optional<std::pair<double, double>>>> te_cooldowns; // filled by get_te_cooldowns()
     // Host <-> device synchronisation (see host_sync in taylor.hpp). strict: everything is uploaded at the entry of
     // every call and refreshed at its exit (the reference's raw-pointer contract). lazy: an array is uploaded only
     // after the user could have written it (non-const getters, setters), and the mirrors are refreshed when a getter
@@ -499,6 +500,14 @@ std::uint32_t taylor_adaptive_batch<double>::get_dim() const
 {
     return m_impl->dim;
 }
+bool taylor_adaptive_batch<double>::is_variational() const noexcept
+{
+    return false;
+}
+std::uint32_t taylor_adaptive_batch<double>::get_n_orig_sv() const noexcept
+{
+    return m_impl->dim;
+}
 const std::vector<std::pair<expression, expression>> &taylor_adaptive_batch<double>::get_sys() const noexcept
 {
     return m_impl->sys;
@@ -540,6 +549,11 @@ std::pair<const std::vector<double> &, const std::vector<double> &> taylor_adapt
 {
     m_impl->refresh_time();
     return {m_impl->time_hi, m_impl->time_lo};
+}
+std::pair<const double *, const double *> taylor_adaptive_batch<double>::get_dtime_data() const
+{
+    m_impl->refresh_time();
+    return {m_impl->time_hi.data(), m_impl->time_lo.data()};
 }
 void taylor_adaptive_batch<double>::set_dtime(const std::vector<double> &hi, const std::vector<double> &lo)
 {
@@ -598,6 +612,18 @@ double *taylor_adaptive_batch<double>::get_pars_data()
 {
     m_impl->host_new_pars = true;
     return m_impl->pars.data();
+}
+taylor_adaptive_batch<double>::range_t taylor_adaptive_batch<double>::get_state_range()
+{
+    // (Writable, like the non-const get_state_data().)
+    m_impl->refresh_state();
+    m_impl->host_new_state = true;
+    return {m_impl->state.begin(), m_impl->state.end()};
+}
+taylor_adaptive_batch<double>::range_t taylor_adaptive_batch<double>::get_pars_range()
+{
+    m_impl->host_new_pars = true;
+    return {m_impl->pars.begin(), m_impl->pars.end()};
 }
 const std::vector<double> &taylor_adaptive_batch<double>::get_tc() const
 {
@@ -865,6 +891,28 @@ const std::vector<t_event_batch<double>> &taylor_adaptive_batch<double>::get_t_e
 const std::vector<nt_event_batch<double>> &taylor_adaptive_batch<double>::get_nt_events() const
 {
     return m_impl->ntes;
+}
+const std::vector<std::vector<std::optional<std::pair<double, double>>>> &
+taylor_adaptive_batch<double>::get_te_cooldowns() const
+{
+    if (!with_events()) {
+        throw std::invalid_argument("No events were defined for this integrator");
+    }
+    auto &m = *m_impl;
+    const std::size_t n_te = m.tes.size(), n = m.batch_size;
+    // The device keeps the cooldown state as [n_te][batch] arrays (hy_batch_get_cooldowns()).
+    std::vector<std::uint8_t> active(n_te * n);
+    std::vector<double> spent(n_te * n), cd(n_te * n);
+    check(hy_batch_get_cooldowns(m.batch, active.data(), spent.data(), cd.data()));
+    m.te_cooldowns.assign(n, std::vector<std::optional<std::pair<double, double>>>(n_te));
+    for (std::size_t k = 0; k < n_te; ++k) {
+        for (std::size_t i = 0; i < n; ++i) {
+            if (active[k * n + i] != 0u) {
+                m.te_cooldowns[i][k].emplace(spent[k * n + i], cd[k * n + i]);
+            }
+        }
+    }
+    return m.te_cooldowns;
 }
 void taylor_adaptive_batch<double>::reset_cooldowns()
 {

@@ -81,6 +81,7 @@ void visit(const detail::named<Tag> &, F &&f, const Args &...args)
             f(a.value);
         }
     };
+    (void)one; // (an empty pack leaves it unused)
     (one(args), ...);
 }
 

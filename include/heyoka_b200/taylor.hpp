@@ -339,6 +339,10 @@ public:
     [[nodiscard]] bool get_high_accuracy() const;
     [[nodiscard]] bool get_compact_mode() const;
     [[nodiscard]] std::uint32_t get_dim() const;
+    // Variational equations are outside this path: never variational, n_orig_sv == dim
+    // (src/taylor_adaptive_batch.cpp:458-468).
+    [[nodiscard]] bool is_variational() const noexcept;
+    [[nodiscard]] std::uint32_t get_n_orig_sv() const noexcept;
     [[nodiscard]] const std::vector<std::pair<expression, expression>> &get_sys() const noexcept;
 
     [[nodiscard]] const std::vector<double> &get_time() const;
@@ -346,6 +350,7 @@ public:
     void set_time(const std::vector<double> &);
     void set_time(double);
     [[nodiscard]] std::pair<const std::vector<double> &, const std::vector<double> &> get_dtime() const;
+    [[nodiscard]] std::pair<const double *, const double *> get_dtime_data() const;
     void set_dtime(const std::vector<double> &, const std::vector<double> &);
     void set_dtime(double, double);
 
@@ -355,6 +360,34 @@ public:
     [[nodiscard]] const std::vector<double> &get_pars() const;
     [[nodiscard]] const double *get_pars_data() const;
     [[nodiscard]] double *get_pars_data();
+    // get_state_range() / get_pars_range() (src/taylor_adaptive_batch.cpp:2142-2175): the reference returns
+    // std::ranges::subrange<std::vector<T>::iterator> (C++20); this header is C++17, so a minimal range with the same
+    // begin() / end() / size() / operator[] stands in. Writable like the non-const get_*_data().
+    struct range_t {
+        std::vector<double>::iterator first, last;
+        [[nodiscard]] std::vector<double>::iterator begin() const
+        {
+            return first;
+        }
+        [[nodiscard]] std::vector<double>::iterator end() const
+        {
+            return last;
+        }
+        [[nodiscard]] std::size_t size() const
+        {
+            return static_cast<std::size_t>(last - first);
+        }
+        [[nodiscard]] bool empty() const
+        {
+            return first == last;
+        }
+        double &operator[](std::size_t i) const
+        {
+            return first[static_cast<std::ptrdiff_t>(i)];
+        }
+    };
+    [[nodiscard]] range_t get_state_range();
+    [[nodiscard]] range_t get_pars_range();
 
     [[nodiscard]] const std::vector<double> &get_tc() const;
     [[nodiscard]] const std::vector<double> &get_last_h() const;
@@ -364,6 +397,9 @@ public:
     [[nodiscard]] bool with_events() const;
     [[nodiscard]] const std::vector<t_event_t> &get_t_events() const;
     [[nodiscard]] const std::vector<nt_event_t> &get_nt_events() const;
+    // Cooldown state of the terminal events, [batch index][event index]: empty = not in cooldown, else
+    // (time spent in cooldown, cooldown) (src/taylor_adaptive_batch.cpp:2212-2219). Read back from the device on request.
+    [[nodiscard]] const std::vector<std::vector<std::optional<std::pair<double, double>>>> &get_te_cooldowns() const;
     // Clears the cooldowns of the terminal events, for every batch element / for one
     // (src/taylor_adaptive_batch.cpp:2300-2330).
     void reset_cooldowns();

@@ -1,0 +1,115 @@
+// The members of the reference's taylor_adaptive_batch<T> added at the end of round 2 (include/heyoka/taylor.hpp:
+// is_variational(), get_n_orig_sv(), get_dtime_data(), get_state_range(), get_pars_range(), get_te_cooldowns()).
+// Run by tests/test_zz_gpu_sharded_front_ends.py (needs a CUDA device: the class owns a device-resident batch).
+#include <cmath>
+#include <cstdio>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include <heyoka_b200/heyoka_b200.hpp>
+
+using namespace heyoka_b200;
+
+static int n_fail = 0;
+#define REQUIRE(cond)                                                                                                  \
+    do {                                                                                                               \
+        if (!(cond)) {                                                                                                 \
+            std::printf("REQUIRE failed at %s:%d: %s\n", __FILE__, __LINE__, #cond);                                   \
+            ++n_fail;                                                                                                  \
+        }                                                                                                              \
+    } while (0)
+
+int main()
+{
+    auto [x, v] = make_vars("x", "v");
+    using t_ev_t = t_event_batch<double>;
+
+    // No events: plain getters; the ranges are writable views of the host mirrors, like the non-const data pointers.
+    {
+        taylor_adaptive_batch<double> ta{{prime(x) = v, prime(v) = -par[0] * sin(x)},
+                                         {0.05, 0.06, 0.07, 0.08, 0.025, 0.026, 0.027, 0.028},
+                                         4u,
+                                         kw::pars = {9.8, 9.9, 10., 10.1},
+                                         kw::time = {0.5, 1., 1.5, 2.}};
+        REQUIRE(!ta.is_variational());
+        REQUIRE(ta.get_n_orig_sv() == 2u && ta.get_n_orig_sv() == ta.get_dim());
+        const auto [hi, lo] = ta.get_dtime_data();
+        REQUIRE(hi == ta.get_time_data());
+        for (int i = 0; i < 4; ++i) {
+            REQUIRE(hi[i] == 0.5 * (i + 1) && lo[i] == 0.);
+        }
+        auto sr = ta.get_state_range();
+        auto pr = ta.get_pars_range();
+        REQUIRE(sr.size() == 8u && pr.size() == 4u && !sr.empty());
+        REQUIRE(&*sr.begin() == ta.get_state_data() && &*pr.begin() == ta.get_pars_data());
+        REQUIRE(sr[5] == 0.026 && pr[2] == 10.);
+        // Writes through the ranges are picked up by the next step, like writes through get_state_data().
+        taylor_adaptive_batch<double> tb = ta;
+        for (auto &val : ta.get_state_range()) {
+            val *= 2.;
+        }
+        ta.get_pars_range()[1] = 12.;
+        for (std::size_t i = 0; i < 8u; ++i) {
+            tb.get_state_data()[i] *= 2.;
+        }
+        tb.get_pars_data()[1] = 12.;
+        ta.step();
+        tb.step();
+        REQUIRE(ta.get_state() == tb.get_state());
+        REQUIRE(ta.get_last_h() == tb.get_last_h());
+        REQUIRE(ta.get_dtime_data().first[3] == tb.get_time()[3]);
+        bool thrown = false;
+        try {
+            (void)ta.get_te_cooldowns();
+        } catch (const std::invalid_argument &e) {
+            thrown = std::string(e.what()).find("No events were defined for this integrator") != std::string::npos;
+        }
+        REQUIRE(thrown);
+    }
+    // Terminal events without callbacks stop the lanes at v = 0 and start a cooldown there; an event that never
+    // triggers stays out of cooldown; reset_cooldowns() clears the state.
+    {
+        taylor_adaptive_batch<double> ta{{prime(x) = v, prime(v) = -9.8 * sin(x)},
+                                         {0, 0.01, 0.02, 0.03, .25, .26, .27, .28},
+                                         4u,
+                                         kw::t_events = {t_ev_t(v), t_ev_t(x - 100.)}};
+        {
+            const auto &cd0 = ta.get_te_cooldowns();
+            REQUIRE(cd0.size() == 4u);
+            for (const auto &lane : cd0) {
+                REQUIRE(lane.size() == 2u && !lane[0] && !lane[1]);
+            }
+        }
+        ta.propagate_for(100.);
+        for (std::uint32_t i = 0; i < 4u; ++i) {
+            REQUIRE(static_cast<std::int64_t>(std::get<0>(ta.get_propagate_res()[i])) == -1);
+        }
+        {
+            const auto &cd = ta.get_te_cooldowns();
+            REQUIRE(cd.size() == 4u);
+            for (const auto &lane : cd) {
+                REQUIRE(lane.size() == 2u);
+                REQUIRE(static_cast<bool>(lane[0]) && !lane[1]);
+                if (lane[0]) {
+                    // (time spent in cooldown, cooldown): just triggered, automatically deduced cooldown.
+                    REQUIRE(lane[0]->first == 0.);
+                    REQUIRE(std::isfinite(lane[0]->second) && lane[0]->second > 0.);
+                }
+            }
+        }
+        ta.reset_cooldowns(2u);
+        {
+            const auto &cd = ta.get_te_cooldowns();
+            REQUIRE(static_cast<bool>(cd[0][0]) && static_cast<bool>(cd[1][0]) && !cd[2][0] && static_cast<bool>(cd[3][0]));
+        }
+        ta.reset_cooldowns();
+        for (const auto &lane : ta.get_te_cooldowns()) {
+            REQUIRE(!lane[0] && !lane[1]);
+        }
+    }
+    if (n_fail == 0) {
+        std::printf("ALL PASSED (getters)\n");
+    }
+    return n_fail == 0 ? 0 : 1;
+}

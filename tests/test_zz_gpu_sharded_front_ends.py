@@ -2,8 +2,13 @@
 propagate_grid(). Both run the reference's lock-step loops on the host (src/taylor_adaptive_batch.cpp:728-1035,
 :1696-2053) over the shards' steps and dense output, and must give what the single-device batch gives.
 
-These two tests were written at the very end of round 2, after the round's last full run of the GPU suite
+Also here: the C++ class's late additions (tests/cpp/test_getters.cpp).
+
+These tests were written at the very end of round 2, after the round's last full run of the GPU suite
 (profiles/r2_pytest_gpu_tail.log): the file sorts after the others so that `pytest -x` reaches them last."""
+import os
+import subprocess
+
 import numpy as np
 import pytest
 
@@ -104,3 +109,16 @@ def test_sharded_grid_and_continuous_output_with_parameters():
     assert np.max(np.abs(many.propagate_grid(g) - one.propagate_grid(g))) < 1e-13
     with pytest.raises(NotImplementedError, match="multi-device"):
         many.propagate_until(many.time + 1.0, c_output=True)
+
+
+def test_cpp_late_getters():
+    """is_variational(), get_n_orig_sv(), get_dtime_data(), get_state_range() / get_pars_range(), get_te_cooldowns() of
+    the drop-in C++ class (include/heyoka/taylor.hpp:961-996 in the reference)."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src, lib = os.path.join(root, "tests", "cpp", "test_getters.cpp"), os.path.join(root, "heyoka_b200", "lib")
+    exe = os.path.join(root, "build", "test_getters")
+    os.makedirs(os.path.dirname(exe), exist_ok=True)
+    subprocess.run(["g++", "-std=c++17", "-O1", "-I" + os.path.join(root, "include"), src, "-o", exe, "-L" + lib,
+                    "-lheyoka_b200", "-Wl,-rpath," + lib], check=True)
+    res = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0 and "ALL PASSED (getters)" in res.stdout, res.stdout[-3000:] + res.stderr[-2000:]
