@@ -731,6 +731,17 @@ class taylor_adaptive_batch:
             raise ValueError("No events were defined for this integrator")
         self._b.reset_cooldowns(-1 if i is None else int(i))
 
+    @property
+    def te_cooldowns(self):
+        """Cooldown state of the terminal events, [batch index][event index]: None = not in cooldown, else
+        (time spent in cooldown, cooldown) (get_te_cooldowns(), src/taylor_adaptive_batch.cpp:2212-2219)."""
+        if not self._with_events:
+            raise ValueError("No events were defined for this integrator")
+        n_te = len(self._tes)
+        a, s, c = self._b.cooldowns(n_te)
+        return [[(float(s[k, i]), float(c[k, i])) if a[k, i] else None for k in range(n_te)]
+                for i in range(self._batch_size)]
+
     def _step_impl(self, max_delta_ts, backward, write_tc):
         self._push()
         self._b.step(max_delta_ts, backward=backward, write_tc=write_tc)

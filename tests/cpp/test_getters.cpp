@@ -82,26 +82,35 @@ int main()
             }
         }
         ta.propagate_for(100.);
+        // (The lock-step loop ends at the first iteration in which a lane is stopped by its terminal event: a lane that
+        // has not reached its own yet ends with `success` and no cooldown.)
+        std::vector<bool> stopped(4u);
+        unsigned n_stopped = 0;
         for (std::uint32_t i = 0; i < 4u; ++i) {
-            REQUIRE(static_cast<std::int64_t>(std::get<0>(ta.get_propagate_res()[i])) == -1);
+            const auto oc = std::get<0>(ta.get_propagate_res()[i]);
+            stopped[i] = static_cast<std::int64_t>(oc) == -1;
+            REQUIRE(stopped[i] || oc == taylor_outcome::success);
+            n_stopped += stopped[i];
         }
-        {
-            const auto &cd = ta.get_te_cooldowns();
-            REQUIRE(cd.size() == 4u);
-            for (const auto &lane : cd) {
-                REQUIRE(lane.size() == 2u);
-                REQUIRE(static_cast<bool>(lane[0]) && !lane[1]);
-                if (lane[0]) {
-                    // (time spent in cooldown, cooldown): just triggered, automatically deduced cooldown.
-                    REQUIRE(lane[0]->first == 0.);
-                    REQUIRE(std::isfinite(lane[0]->second) && lane[0]->second > 0.);
-                }
+        REQUIRE(n_stopped >= 3u);
+        const auto before = ta.get_te_cooldowns(); // (a copy)
+        REQUIRE(before.size() == 4u);
+        for (std::uint32_t i = 0; i < 4u; ++i) {
+            REQUIRE(before[i].size() == 2u && !before[i][1]);
+            REQUIRE(static_cast<bool>(before[i][0]) == stopped[i]);
+            if (before[i][0]) {
+                // (time spent in cooldown, cooldown): just triggered, automatically deduced cooldown.
+                REQUIRE(before[i][0]->first == 0.);
+                REQUIRE(std::isfinite(before[i][0]->second) && before[i][0]->second > 0.);
             }
         }
         ta.reset_cooldowns(2u);
         {
             const auto &cd = ta.get_te_cooldowns();
-            REQUIRE(static_cast<bool>(cd[0][0]) && static_cast<bool>(cd[1][0]) && !cd[2][0] && static_cast<bool>(cd[3][0]));
+            REQUIRE(!cd[2][0] && !cd[2][1]);
+            for (std::uint32_t i : {0u, 1u, 3u}) {
+                REQUIRE(cd[i] == before[i]);
+            }
         }
         ta.reset_cooldowns();
         for (const auto &lane : ta.get_te_cooldowns()) {

@@ -3,6 +3,7 @@ twice: on the CPU oracle (tests/test_events_cpu.py, which pins the oracle's rest
 on the reference's own expectations) and on the GPU (tests/test_gpu_events.py). `make` builds an integrator with the
 signature of heyoka_b200.taylor_adaptive_batch."""
 import numpy as np
+import pytest
 
 import heyoka_b200 as hb
 
@@ -541,3 +542,32 @@ def case_te_propagate_grid(make):
     out4 = ta4.propagate_grid(grid3)
     assert np.all(np.isnan(out4.reshape(-1)[32:]))
     return out
+
+
+def case_te_cooldowns_property(make):
+    """te_cooldowns (the reference's get_te_cooldowns(), src/taylor_adaptive_batch.cpp:2212-2219; the values are set at
+    :936-950): empty before any event, (0, cooldown) for the terminal event that stopped the propagation, untouched
+    for an event that never triggers, cleared by reset_cooldowns(i) / reset_cooldowns()."""
+    x, v, sys = pendulum_sys()
+    ic = np.array(PEND_IC).reshape(2, 4)
+    ta = make(sys, ic, 4, t_events=[hb.t_event_batch(v), hb.t_event_batch(x - 100.)])
+    assert ta.te_cooldowns == [[None, None]] * 4
+    ta.propagate_for(100.)
+    # (The lock-step loop ends at the first iteration in which a lane is stopped by its terminal event: the lanes that
+    # have not reached theirs yet end with `success` and no cooldown.)
+    res = [r[0] for r in ta.propagate_res]
+    assert res.count(-1) >= 3 and all(r in (-1, TO.success) for r in res)
+    before = ta.te_cooldowns
+    for lane, oc in zip(before, res):
+        assert lane[1] is None
+        if oc == -1:
+            assert lane[0][0] == 0. and 0. < lane[0][1] < np.inf
+        else:
+            assert lane[0] is None
+    ta.reset_cooldowns(2)
+    after = ta.te_cooldowns
+    assert after[2] == [None, None] and [after[i] for i in (0, 1, 3)] == [before[i] for i in (0, 1, 3)]
+    ta.reset_cooldowns()
+    assert ta.te_cooldowns == [[None, None]] * 4
+    with pytest.raises(ValueError, match="No events were defined"):
+        make(sys, ic, 4).te_cooldowns

@@ -124,3 +124,7 @@ def test_event_validation_and_decomposition():
     P = hb.Program(sys, events=[v, v - hb.par[3]])
     assert P.n_ev == 2 and P.n_pars == 4
     assert P.ev_defs()[0] == 1 and P.ev_defs()[1] >= P.n_eq
+
+
+def test_te_cooldowns_property():
+    ec.case_te_cooldowns_property(make)

@@ -122,3 +122,9 @@ def test_cpp_late_getters():
                     "-lheyoka_b200", "-Wl,-rpath," + lib], check=True)
     res = subprocess.run([exe], capture_output=True, text=True, timeout=600)
     assert res.returncode == 0 and "ALL PASSED (getters)" in res.stdout, res.stdout[-3000:] + res.stderr[-2000:]
+
+
+def test_te_cooldowns_property():
+    """te_cooldowns of the Python front end (the reference's get_te_cooldowns()) on the device, single and sharded."""
+    ec.case_te_cooldowns_property(make)
+    ec.case_te_cooldowns_property(lambda *a, **k: make(*a, device=[0, 0], **k))
