@@ -1054,7 +1054,13 @@ const std::vector<double> &continuous_output_batch<double>::operator()(const std
                                     + std::to_string(tm.size()) + ", but a size of " + std::to_string(m_batch_size)
                                     + " was expected instead");
     }
-    check(hy_cout_eval(m_h.get(), tm.data(), m_output.data()));
+    return (*this)(tm.data());
+}
+
+const std::vector<double> &continuous_output_batch<double>::operator()(const double *tm)
+{
+    check_valid();
+    check(hy_cout_eval(m_h.get(), tm, m_output.data()));
     return m_output;
 }
 

@@ -76,7 +76,8 @@ public:
     continuous_output_batch() = default;
     continuous_output_batch(hy_cout *, std::uint32_t batch_size, std::uint32_t dim);
 
-    // State at one time per lane / at the same time for every lane, [dim][batch].
+    // State at one time per lane (batch_size values) / at the same time for every lane, [dim][batch].
+    const std::vector<double> &operator()(const double *tm);
     const std::vector<double> &operator()(const std::vector<double> &tm);
     const std::vector<double> &operator()(double tm);
     [[nodiscard]] const std::vector<double> &get_output() const

@@ -1,5 +1,6 @@
 // The members of the reference's taylor_adaptive_batch<T> added at the end of round 2 (include/heyoka/taylor.hpp:
-// is_variational(), get_n_orig_sv(), get_dtime_data(), get_state_range(), get_pars_range(), get_te_cooldowns()).
+// is_variational(), get_n_orig_sv(), get_dtime_data(), get_state_range(), get_pars_range(), get_te_cooldowns();
+// continuous_output_batch::operator()(const T *)).
 // Run by tests/test_zz_gpu_sharded_front_ends.py (needs a CUDA device: the class owns a device-resident batch).
 #include <cmath>
 #include <cstdio>
@@ -115,6 +116,20 @@ int main()
         ta.reset_cooldowns();
         for (const auto &lane : ta.get_te_cooldowns()) {
             REQUIRE(!lane[0] && !lane[1]);
+        }
+    }
+    // continuous_output_batch: the pointer overload of the call operator (include/heyoka/continuous_output.hpp:191).
+    {
+        taylor_adaptive_batch<double> ta{{prime(x) = v, prime(v) = -x}, {0., 0.1, 0.2, 0.3, 1., 1.1, 1.2, 1.3}, 4u};
+        auto [co, cb] = ta.propagate_until(5., kw::c_output = true);
+        REQUIRE(co.has_value());
+        if (co) {
+            const std::vector<double> tm{0.5, 1.5, 2.5, 4.75};
+            const auto by_vec = (*co)(tm);
+            const auto by_ptr = (*co)(tm.data());
+            REQUIRE(by_vec == by_ptr && by_ptr.size() == 8u);
+            // x(t) = x0 cos t + v0 sin t
+            REQUIRE(std::abs(by_ptr[1] - (0.1 * std::cos(1.5) + 1.1 * std::sin(1.5))) < 1e-13);
         }
     }
     if (n_fail == 0) {
