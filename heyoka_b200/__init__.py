@@ -440,7 +440,7 @@ class Batch:
             if st == _capi.HY_ERR_CALLBACK:
                 return None  # (the caller re-raises what its callback raised)
             check(st)
-        return continuous_output_batch(h, self.program.n_eq, self.n) if h.value else None
+        return continuous_output_batch(h, self.program.n_eq, self.n, self.program.order) if h.value else None
 
     def propagate_grid(self, grid, max_delta_t=None, max_steps=0):
         """grid: [n_pts, batch]; returns the states at the grid points, [n_pts, n_eq, batch] (NaN where not reached)."""
@@ -505,8 +505,8 @@ class continuous_output_batch:
     """Continuous output of a propagate_until() (include/heyoka/continuous_output.hpp): callable with one time or
     one time per lane, returns the state [n_eq, batch] at those times (dense output of the step that contains them)."""
 
-    def __init__(self, handle, n_eq, batch):
-        self._h, self._n_eq, self._n = handle, n_eq, batch
+    def __init__(self, handle, n_eq, batch, order):
+        self._h, self._n_eq, self._n, self._order = handle, n_eq, batch, order
         self._output = np.zeros((n_eq, batch))
 
     def __del__(self):
@@ -533,6 +533,19 @@ class continuous_output_batch:
 
     def get_batch_size(self):
         return self._n
+
+    def get_times(self):
+        """The times at the ends of the recorded iterations, [n_steps + 2, batch]: row 0 = the starting times, last row =
+        the +-infinity padding (get_times(), src/continuous_output.cpp:1157-1163)."""
+        out = np.empty((self.get_n_steps() + 2, self._n))
+        check(lib.hy_cout_download(self._h, _dptr(out), None, None))
+        return out
+
+    def get_tcs(self):
+        """The Taylor coefficients of the recorded iterations, [n_steps, n_eq, order + 1, batch] (get_tcs(), :1165-1169)."""
+        out = np.empty((self.get_n_steps(), self._n_eq, self._order + 1, self._n))
+        check(lib.hy_cout_download(self._h, None, None, _dptr(out)))
+        return out
 
 
 class event_direction:
@@ -856,7 +869,7 @@ class taylor_adaptive_batch:
             h, r = C.c_void_p(), C.c_void_p(rec.value)
             rec.value = None  # (finish destroys the recorder)
             check(lib.hy_cout_rec_finish(self._b._h, r, fwd.ctypes.data_as(C.POINTER(C.c_uint8)), C.byref(h)))
-            return continuous_output_batch(h, self._prog.n_eq, n) if h.value else None
+            return continuous_output_batch(h, self._prog.n_eq, n, self._prog.order) if h.value else None
         try:
             return self._propagate_until_host_loop(th, tl, mdt, rem_hi, rem_lo, t_dir, max_steps, write_tc, callback, rec,
                                                    finish)

@@ -124,6 +124,7 @@ SIGNATURES = {
     "hy_cout_eval": (C.c_int, [_vp, _dp, _dp]),
     "hy_cout_get_bounds": (C.c_int, [_vp, _dp, _dp]),
     "hy_cout_n_steps": (C.c_uint64, [_vp]),
+    "hy_cout_download": (C.c_int, [_vp, _dp, _dp, _dp]),
     "hy_cout_destroy": (None, [_vp]),
     "hy_batch_d_output": (C.c_int, [_vp, _dp, _dp]),
     "hy_batch_set_events": (C.c_int, [_vp, C.c_uint32, C.POINTER(C.c_int32), _dp, C.c_double]),

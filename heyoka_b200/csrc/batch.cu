@@ -3058,6 +3058,40 @@ int hy_cout_get_bounds(const hy_cout *c, double *lb, double *ub)
     }
 }
 
+int hy_cout_download(const hy_cout *c, double *times_hi, double *times_lo, double *tcs)
+{
+    try {
+        if (c == nullptr) {
+            throw std::invalid_argument("Null pointer passed to hy_cout_download()");
+        }
+        device_guard guard(c->device);
+        const std::size_t n = c->n, rows = static_cast<std::size_t>(c->n_steps) + 2u;
+        if (times_hi != nullptr) {
+            HY_CUDA_CHECK(cudaMemcpy(times_hi, c->d_t_hi, sizeof(double) * rows * n, cudaMemcpyDeviceToHost));
+        }
+        if (times_lo != nullptr) {
+            HY_CUDA_CHECK(cudaMemcpy(times_lo, c->d_t_lo, sizeof(double) * rows * n, cudaMemcpyDeviceToHost));
+        }
+        if (tcs != nullptr) {
+            // One iteration = [n_eq][order + 1][batch] doubles; the slabs hold slab_iters iterations each, the last
+            // one possibly fewer.
+            const std::size_t it_doubles = static_cast<std::size_t>(c->n_eq) * (c->order + 1u) * n;
+            for (std::size_t s = 0; s < c->slabs.size(); ++s) {
+                const std::size_t first = s * c->slab_iters;
+                if (first >= c->n_steps) {
+                    break;
+                }
+                const std::size_t count = std::min<std::size_t>(c->slab_iters, c->n_steps - first);
+                HY_CUDA_CHECK(cudaMemcpy(tcs + first * it_doubles, c->slabs[s], sizeof(double) * count * it_doubles,
+                                         cudaMemcpyDeviceToHost));
+            }
+        }
+        return HY_OK;
+    } catch (...) {
+        return translate_exception();
+    }
+}
+
 uint64_t hy_cout_n_steps(const hy_cout *c)
 {
     return c != nullptr ? c->n_steps : 0u;

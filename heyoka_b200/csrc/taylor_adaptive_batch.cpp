@@ -1032,8 +1032,9 @@ taylor_adaptive_batch<double>::propagate_until_vec(const std::vector<double> &ts
 }
 
 // ---- continuous_output_batch<double> ----
-continuous_output_batch<double>::continuous_output_batch(hy_cout *h, std::uint32_t batch_size, std::uint32_t dim)
-    : m_h(h, [](hy_cout *p) { hy_cout_destroy(p); }), m_batch_size(batch_size), m_dim(dim),
+continuous_output_batch<double>::continuous_output_batch(hy_cout *h, std::uint32_t batch_size, std::uint32_t dim,
+                                                        std::uint32_t order)
+    : m_h(h, [](hy_cout *p) { hy_cout_destroy(p); }), m_batch_size(batch_size), m_dim(dim), m_order(order),
       m_output(static_cast<std::size_t>(batch_size) * dim)
 {
 }
@@ -1082,6 +1083,26 @@ std::size_t continuous_output_batch<double>::get_n_steps() const
 {
     check_valid();
     return static_cast<std::size_t>(hy_cout_n_steps(m_h.get()));
+}
+
+const std::vector<double> &continuous_output_batch<double>::get_times() const
+{
+    check_valid();
+    if (m_times_hi.empty()) {
+        m_times_hi.resize((get_n_steps() + 2u) * m_batch_size);
+        check(hy_cout_download(m_h.get(), m_times_hi.data(), nullptr, nullptr));
+    }
+    return m_times_hi;
+}
+
+const std::vector<double> &continuous_output_batch<double>::get_tcs() const
+{
+    check_valid();
+    if (m_tcs.empty()) {
+        m_tcs.resize(get_n_steps() * m_dim * (m_order + 1u) * m_batch_size);
+        check(hy_cout_download(m_h.get(), nullptr, nullptr, m_tcs.data()));
+    }
+    return m_tcs;
 }
 
 // propagate_grid(): src/taylor_adaptive_batch.cpp:1545-2055. The size checks that need the reference's wording are
@@ -1369,7 +1390,7 @@ taylor_adaptive_batch<double>::propagate_until_impl(const std::vector<double> &h
         }
         std::optional<continuous_output_batch<double>> ret;
         if (co != nullptr) {
-            ret.emplace(co, n, m.dim);
+            ret.emplace(co, n, m.dim, m.order);
         }
         m.pull(true);
         m.pull_prop_res();
@@ -1441,7 +1462,7 @@ taylor_adaptive_batch<double>::propagate_until_impl(const std::vector<double> &h
             rec.r = nullptr; // (finish() destroys the recorder)
             check(hy_cout_rec_finish(m.batch, r, fwd.data(), &co));
             if (co != nullptr) {
-                ret.emplace(co, n, m.dim);
+                ret.emplace(co, n, m.dim, m.order);
             }
         }
         return {std::move(ret), std::move(o.cb)};

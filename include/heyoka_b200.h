@@ -321,6 +321,11 @@ int hy_cout_eval(hy_cout *, const double *tm, double *out);
 /* Per-lane time range [lb, ub] covered (the initial and the final time), number of recorded iterations. */
 int hy_cout_get_bounds(const hy_cout *, double *lb, double *ub);
 uint64_t hy_cout_n_steps(const hy_cout *);
+/* The recorded data on the host, in the reference's layouts (get_times() / get_tcs(), src/continuous_output.cpp:
+ * 1157-1169): times_hi / times_lo[(n_steps + 2) * batch] (row 0 = the starting times, row k = the times after
+ * iteration k, last row = the +-infinity padding of the binary search), tcs[n_steps][n_eq][order + 1][batch]. NULL
+ * pointers are skipped. */
+int hy_cout_download(const hy_cout *, double *times_hi, double *times_lo, double *tcs);
 void hy_cout_destroy(hy_cout *);
 
 /* Dense output from the last written tc: out[var * batch + lane] = sum_o tc[var][o][lane] * tau[lane]^o

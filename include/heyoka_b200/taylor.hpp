@@ -67,14 +67,15 @@ template <>
 class continuous_output_batch<double>
 {
     std::shared_ptr<hy_cout> m_h;
-    std::uint32_t m_batch_size = 0, m_dim = 0;
+    std::uint32_t m_batch_size = 0, m_dim = 0, m_order = 0;
     std::vector<double> m_output;
+    mutable std::vector<double> m_times_hi, m_tcs; // host copies, fetched on first use (get_times() / get_tcs())
 
     void check_valid() const;
 
 public:
     continuous_output_batch() = default;
-    continuous_output_batch(hy_cout *, std::uint32_t batch_size, std::uint32_t dim);
+    continuous_output_batch(hy_cout *, std::uint32_t batch_size, std::uint32_t dim, std::uint32_t order);
 
     // State at one time per lane (batch_size values) / at the same time for every lane, [dim][batch].
     const std::vector<double> &operator()(const double *tm);
@@ -90,6 +91,11 @@ public:
     {
         return m_batch_size;
     }
+    // The recorded data (include/heyoka/continuous_output.hpp:198-199), copied from the device on first use:
+    // times[(n_steps + 2) * batch] (row 0 = starting times, last row = the +-infinity padding),
+    // tcs[n_steps][dim][order + 1][batch].
+    [[nodiscard]] const std::vector<double> &get_times() const;
+    [[nodiscard]] const std::vector<double> &get_tcs() const;
 };
 
 // Host <-> device synchronisation of the integrator's host mirrors (extension; default strict).

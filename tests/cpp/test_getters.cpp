@@ -2,6 +2,7 @@
 // is_variational(), get_n_orig_sv(), get_dtime_data(), get_state_range(), get_pars_range(), get_te_cooldowns();
 // continuous_output_batch::operator()(const T *)).
 // Run by tests/test_zz_gpu_sharded_front_ends.py (needs a CUDA device: the class owns a device-resident batch).
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <stdexcept>
@@ -130,6 +131,29 @@ int main()
             REQUIRE(by_vec == by_ptr && by_ptr.size() == 8u);
             // x(t) = x0 cos t + v0 sin t
             REQUIRE(std::abs(by_ptr[1] - (0.1 * std::cos(1.5) + 1.1 * std::sin(1.5))) < 1e-13);
+            // get_times() / get_tcs() (include/heyoka/continuous_output.hpp:198-199): (n_steps + 2) rows of times (start,
+            // the end of every iteration, the padding), [n_steps][dim][order + 1][batch] Taylor coefficients; at the
+            // start of an iteration the output is the order-0 coefficients of that iteration.
+            const auto n_steps = co->get_n_steps();
+            const auto &tms = co->get_times();
+            const auto &tcs = co->get_tcs();
+            const std::size_t ord1 = ta.get_order() + 1u;
+            REQUIRE(tms.size() == (n_steps + 2u) * 4u && tcs.size() == n_steps * 2u * ord1 * 4u);
+            for (std::size_t i = 0; i < 4u; ++i) {
+                REQUIRE(tms[i] == 0. && tms[n_steps * 4u + i] == 5. && std::isinf(tms[(n_steps + 1u) * 4u + i]));
+            }
+            for (std::size_t k = 0; k < n_steps; ++k) {
+                const auto out = (*co)(tms.data() + k * 4u);
+                for (std::size_t var = 0; var < 2u; ++var) {
+                    for (std::size_t i = 0; i < 4u; ++i) {
+                        REQUIRE(out[var * 4u + i] == tcs[((k * 2u + var) * ord1) * 4u + i]);
+                    }
+                }
+            }
+            // The last recorded iteration holds the integrator's current Taylor coefficients.
+            const auto &tc = ta.get_tc();
+            REQUIRE(tc.size() == 2u * ord1 * 4u);
+            REQUIRE(std::equal(tc.begin(), tc.end(), tcs.end() - static_cast<std::ptrdiff_t>(tc.size())));
         }
     }
     if (n_fail == 0) {

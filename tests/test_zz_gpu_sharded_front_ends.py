@@ -128,3 +128,33 @@ def test_te_cooldowns_property():
     """te_cooldowns of the Python front end (the reference's get_te_cooldowns()) on the device, single and sharded."""
     ec.case_te_cooldowns_property(make)
     ec.case_te_cooldowns_property(lambda *a, **k: make(*a, device=[0, 0], **k))
+
+
+def test_continuous_output_times_and_tcs():
+    """get_times() / get_tcs() of the continuous output (src/continuous_output.cpp:1157-1169; hy_cout_download()):
+    layouts, consistency with the object's own evaluation (at the start of an iteration the output IS the order-0
+    coefficients of that iteration, bit for bit), with the integrator's final Taylor coefficients, and against the
+    oracle's recording of the same propagation."""
+    import oracle
+    from test_oracle_golden import cout_fixture, sys_oscillator
+    ic, final_tm, _ = cout_fixture()
+    P = hb.Program(sys_oscillator())
+    ta = hb.taylor_adaptive_batch(sys_oscillator(), ic, 4)
+    t0 = np.array(ta.time)
+    co = ta.propagate_until(final_tm, c_output=True)
+    n = co.get_n_steps()
+    tms, tcs = co.get_times(), co.get_tcs()
+    assert tms.shape == (n + 2, 4) and tcs.shape == (n, P.n_eq, P.order + 1, 4)
+    assert np.array_equal(tms[0], t0) and np.array_equal(tms[n], final_tm) and np.all(tms[n + 1] == np.inf)
+    lb, ub = co.get_bounds()
+    assert np.array_equal(lb, tms[0]) and np.array_equal(ub, tms[n])
+    assert np.all(np.diff(tms[:n + 1], axis=0) >= 0)
+    for k in range(n):
+        assert np.array_equal(co(tms[k]), tcs[k][:, 0, :]), k
+    assert np.array_equal(tcs[n - 1], ta.tc)
+    o = oracle.OracleIntegrator(P, ic, 4, mode=oracle.FMA)
+    oco = o.propagate_until_cout(final_tm)
+    assert oco.get_n_steps() == n
+    assert np.max(np.abs(tms[:n + 1] - oco.t_hi[:n + 1])) < 1e-12 and np.array_equal(tms[n + 1], oco.t_hi[n + 1])
+    scale = np.max(np.abs(oco.tcs), axis=(0, 1, 3), keepdims=True)
+    assert np.max(np.abs(tcs - oco.tcs) / scale) < 1e-11
