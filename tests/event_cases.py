@@ -571,3 +571,84 @@ def case_te_cooldowns_property(make):
     assert ta.te_cooldowns == [[None, None]] * 4
     with pytest.raises(ValueError, match="No events were defined"):
         make(sys, ic, 4).te_cooldowns
+
+
+def case_tutorial_events(make, golden):
+    """doc/tut_events.rst (tutorial/event_basic.cpp), GOLDEN: the event times the reference prints with 16 digits, the
+    scalar integrators of the page as batches of 4 identical lanes. Returns the largest relative deviations seen
+    (zero-velocity times, times of the second event of the two-event run, grid output of the terminal-event run)."""
+    g = golden
+    x, v, sys = pendulum_sys()
+    n = 4
+    ic = np.array([[g["x0"]] * n, [g["v0"]] * n])
+    dev = {"nt": 0., "two": 0., "grid": 0.}
+
+    def rel(a, b):
+        return abs(a - b) / abs(b) if b != 0 else abs(a)
+
+    # 1. Non-terminal event v = 0, dense output at the event time from inside the callback.
+    times = [[] for _ in range(n)]
+    xs = [[] for _ in range(n)]
+
+    def cb(ta, t, d_sgn, i):
+        xs[i].append(ta.update_d_output([t] * n)[0, i])
+        times[i].append(t)
+
+    ta = make(sys, ic, n, nt_events=[hb.nt_event_batch(v, cb)])
+    ta.propagate_until(g["t_final"])
+    ref = g["nt_zero_velocity"]
+    for i in range(n):
+        assert len(times[i]) == len(ref["times"]) == 5 and times[i][0] == 0.
+        for t, rt in zip(times[i], ref["times"]):
+            dev["nt"] = max(dev["nt"], rel(t, rt))
+        for xv, rx in zip(xs[i], ref["x_at_events"]):
+            assert abs(xv - rx) < 1e-9           # printed as +-0.05: the amplitude comes back at every turning point
+    assert dev["nt"] < 1e-14
+    # 2. Same with direction = positive: t = 0, T, 2T.
+    times = [[] for _ in range(n)]
+    ta = make(sys, ic, n, nt_events=[hb.nt_event_batch(v, lambda ta, t, d_sgn, i: times[i].append(t),
+                                                       direction=hb.event_direction.positive)])
+    ta.propagate_until(g["t_final"])
+    ref = g["nt_zero_velocity_positive_direction"]["times"]
+    for i in range(n):
+        assert len(times[i]) == 3 and times[i][0] == 0.
+        assert all(rel(t, rt) < 1e-14 for t, rt in zip(times[i], ref))
+    # 3. Two events, v and v*v - 1e-12: callbacks in chronological order.
+    seq = [[] for _ in range(n)]
+    ta = make(sys, ic, n, nt_events=[hb.nt_event_batch(v, lambda ta, t, d_sgn, i: seq[i].append((0, t))),
+                                     hb.nt_event_batch(v * v - 1e-12, lambda ta, t, d_sgn, i: seq[i].append((1, t)))])
+    ta.propagate_until(g["t_final"])
+    ref = g["nt_two_events"]["sequence"]
+    for i in range(n):
+        assert [e for e, _ in seq[i]] == [r["event"] for r in ref]
+        for (e, t), r in zip(seq[i], ref):
+            if e == 0:
+                assert rel(t, r["t"]) < 1e-14
+            else:
+                # (v*v - 1e-12 crosses zero 2e-6 away from the turning point with a slope of 1e-6, and the event
+                # polynomial - coefficients ~1e-2 - is evaluated to ~1e-18: the root moves by ~1e-12 with the rounding
+                # of the evaluation. Observed on the oracle: 1.3e-12.)
+                dev["two"] = max(dev["two"], abs(t - r["t"]))
+    assert dev["two"] < 2e-11, dev
+    # 4. Terminal event toggling the damping parameter; single steps up to the first stop, then propagate_grid().
+    tg = g["terminal_damping_toggle"]
+
+    def tcb(ta, d_sgn, i):
+        ta.pars[0, i] = 1. if ta.pars[0, i] == 0 else 0.
+        return True
+
+    ta = make([(x, v), (v, -9.8 * hb.sin(x) - hb.par[0] * v)], np.array([[tg["x0"]] * n, [tg["v0"]] * n]), n,
+              t_events=[hb.t_event_batch(v, callback=tcb)])
+    while True:
+        ta.step()
+        if any(r[0] != TO.success for r in ta.step_res):
+            break
+    assert [r[0] for r in ta.step_res] == [tg["first_stop_event_index"]] * n   # terminal_event_0 (continuing)
+    ta.propagate_until(1.)
+    out = ta.propagate_grid(np.array(tg["grid"])[:, None] * np.ones(n))
+    ref = np.array(tg["grid_output"])
+    for i in range(n):
+        dev["grid"] = max(dev["grid"], float(np.max(np.abs(out[:, :, i] - ref) / np.abs(ref))))
+    assert dev["grid"] < 1e-12
+    assert np.all(ta.time == tg["final_time"])
+    return dev

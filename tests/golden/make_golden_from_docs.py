@@ -6,6 +6,14 @@ Sources (bluescarni/heyoka @ 9c91f71):
   doc/tut_batch_mode.rst:160-340   output of tutorial/batch_mode.cpp:52-131 (batch 4, order 20,
                                    x' = v, v' = cos(t) - alpha v - sin(x), alpha = par[0])
   README.md:118-139                scalar pendulum x(10), v(10)
+  doc/tut_adaptive.rst:94-325      output of tutorial/adaptive_basic.cpp (scalar pendulum: single steps forwards /
+                                   backwards / clamped, propagate_for(5), propagate_until(20), back to 0, propagate_grid)
+  doc/tut_d_output.rst:64-203      output of tutorial/d_output.cpp (dense output after one step, continuous output of
+                                   propagate_until(10): 48 steps, samples)
+  doc/tut_events.rst:138-400       output of tutorial/event_basic.cpp (non-terminal events: zero-velocity times of the
+                                   pendulum to 16 digits, direction filter, two events in chronological order; terminal
+                                   event toggling a damping parameter: propagate_grid output to 16 digits)
+The scalar integrators of those tutorials are batch integrators of size 1 here.
 """
 import json
 import os
@@ -79,6 +87,98 @@ def main():
     with open(os.path.join(HERE, "readme_pendulum.json"), "w") as f:
         json.dump({"source": "README.md:118-139", "system": "x' = v, v' = -9.8 sin(x)", "x0": 0.05, "v0": 0.025,
                    "t": 10.0, "x": float(m.group(1)), "v": float(m.group(2))}, f, indent=1)
+
+    tutorials()
+
+
+def console_blocks(rst):
+    """The `.. code-block:: console` blocks of a page, in order, as lists of stripped lines."""
+    out = []
+    for m in re.finditer(r"\.\. code-block:: console\n\n((?:(?:   .*)?\n)+)", rst):
+        out.append([ln.strip() for ln in m.group(1).splitlines() if ln.strip()])
+    return out
+
+
+def kv(lines):
+    """'Key : value' lines -> dict of strings."""
+    d = {}
+    for ln in lines:
+        if ":" in ln:
+            k, v = ln.split(":", 1)
+            d.setdefault(k.strip(), []).append(v.strip())
+    return d
+
+
+def tutorials():
+    # ---- tut_adaptive.rst ----
+    blocks = console_blocks(open(os.path.join(REF, "doc", "tut_adaptive.rst")).read())
+    b = [kv(x) for x in blocks]
+    step1 = next(x for x in b if x.get("Timestep") == ["0.216053"])
+    back = next(x for x in b if x.get("Timestep") == ["-0.213123"])
+    clamped = next(x for x in b if x.get("Timestep") == ["0.01", "-0.02"])
+    props = [x for x in b if "Num. of steps" in x]
+    grid_lines = next(bl for bl in blocks if bl and bl[0].startswith("x(0.4)"))
+    out = {
+        "source": "doc/tut_adaptive.rst (output of tutorial/adaptive_basic.cpp)",
+        "system": "x' = v, v' = -9.8 sin(x)", "x0": 0.05, "v0": 0.025, "order": int(step1["Taylor order"][0]),
+        "first_step": {"outcome": step1["Outcome"][0].split("::")[1], "h": float(step1["Timestep"][0]),
+                       "time": float(step1["Time"][0]), "state": json.loads(step1["State"][0])},
+        "step_backward": {"outcome": back["Outcome"][0].split("::")[1], "h": float(back["Timestep"][0])},
+        "clamped_steps": [{"limit": float(h), "outcome": oc.split("::")[1], "h": float(h)}
+                          for oc, h in zip(clamped["Outcome"], clamped["Timestep"])],
+        # propagate_for(5) and propagate_until(20) share a block; propagate_until(0) follows with the final state.
+        "propagate": [{"outcome": oc.split("::")[1], "min_h": float(a), "max_h": float(bb), "n_steps": int(n), "time": float(t)}
+                      for x in props for oc, a, bb, n, t in zip(x["Outcome"], x["Min. timestep"], x["Max. timestep"],
+                                                               x["Num. of steps"], x["Current time"])],
+        "state_back_at_0": json.loads(next(x for x in props if "State" in x)["State"][0]),
+        "grid": {"times": [0.1 * i for i in range(11)], "index": 4,
+                 "x": float(grid_lines[0].split("=")[1]), "v": float(grid_lines[1].split("=")[1])},
+    }
+    assert [r["n_steps"] for r in out["propagate"]] == [24, 72, 97], out["propagate"]
+    with open(os.path.join(HERE, "tut_adaptive.json"), "w") as f:
+        json.dump(out, f, indent=1)
+
+    # ---- tut_d_output.rst ----
+    blocks = console_blocks(open(os.path.join(REF, "doc", "tut_d_output.rst")).read())
+    d01 = next(bl for bl in blocks if bl[0].startswith("x(0.1)"))
+    nst = next(kv(bl) for bl in blocks if any(ln.startswith("N of steps") for ln in bl))
+    samples = next(bl for bl in blocks if bl[0].startswith("time=0,"))
+    out = {
+        "source": "doc/tut_d_output.rst (output of tutorial/d_output.cpp)",
+        "system": "x' = v, v' = -9.8 sin(x)", "x0": 0.05, "v0": 0.025,
+        "d_output_at_0.1": [float(d01[0].split("=")[1]), float(d01[1].split("=")[1])],
+        "c_output": {"t_final": 10.0, "n_steps": int(nst["N of steps"][0]),
+                     "samples": [[float(v.split("=")[1]) for v in ln.split(",")] for ln in samples]},
+    }
+    assert out["c_output"]["n_steps"] == 48 and len(out["c_output"]["samples"]) == 6
+    with open(os.path.join(HERE, "tut_d_output.json"), "w") as f:
+        json.dump(out, f, indent=1)
+
+    # ---- tut_events.rst ----
+    blocks = console_blocks(open(os.path.join(REF, "doc", "tut_events.rst")).read())
+    times = [[float(ln.split(":")[1]) for ln in bl] for bl in blocks if bl[0].startswith("Event detection time")]
+    xs = next([float(ln.split(":")[1]) for ln in bl] for bl in blocks if bl[0].startswith("Value of x when v is zero"))
+    multi = next([(int(re.match(r"Event (\d)", ln).group(1)), float(ln.split("t=")[1])) for ln in bl]
+                 for bl in blocks if bl[0].startswith("Event 0 triggering"))
+    term = next(kv(bl) for bl in blocks if bl[0].startswith("Integration outcome"))
+    grid = next(bl for bl in blocks if bl[0].startswith("[-0.0297"))
+    out = {
+        "source": "doc/tut_events.rst (output of tutorial/event_basic.cpp)",
+        "system": "x' = v, v' = -9.8 sin(x)", "x0": -0.05, "v0": 0.0, "t_final": 5.0,
+        "nt_zero_velocity": {"times": times[0], "x_at_events": xs},
+        "nt_zero_velocity_positive_direction": {"times": times[1]},
+        "nt_two_events": {"second_event": "v*v - 1e-12", "sequence": [{"event": e, "t": t} for e, t in multi]},
+        "terminal_damping_toggle": {
+            "system": "x' = v, v' = -9.8 sin(x) - par[0] v", "x0": 0.05, "v0": 0.025,
+            "first_stop_event_index": int(term["Event index"][0]),
+            "grid": [float(i) for i in range(1, 11)],
+            "grid_output": [json.loads(ln) for ln in grid if ln.startswith("[")],
+            "final_time": float(next(ln for ln in grid if ln.startswith("Final time")).split(":")[1]),
+        },
+    }
+    assert len(times[0]) == 5 and len(times[1]) == 3 and len(multi) == 14 and len(out["terminal_damping_toggle"]["grid_output"]) == 10
+    with open(os.path.join(HERE, "tut_events.json"), "w") as f:
+        json.dump(out, f, indent=1)
 
 
 if __name__ == "__main__":

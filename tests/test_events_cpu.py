@@ -128,3 +128,10 @@ def test_event_validation_and_decomposition():
 
 def test_te_cooldowns_property():
     ec.case_te_cooldowns_property(make)
+
+
+def test_tutorial_events_golden():
+    """doc/tut_events.rst: the event times and the grid output the reference prints with 16 digits."""
+    from common import golden
+    dev = ec.case_tutorial_events(make, golden("tut_events.json"))
+    print(dev)

@@ -6,6 +6,9 @@ Fixtures:
   3. closed-form jets of test/taylor_*.cpp (tests/closed_form_cases.py, tests/golden/closed_form_jets.json)
   4. test/timestep_check.cpp:33-86 (step-size formula recomputed from the Taylor coefficients)
   5. test/taylor_adaptive_batch.cpp:586-598 (exact step counts under max_delta_t, exact final times)
+  6. doc/tut_adaptive.rst and doc/tut_d_output.rst printed outputs (tests/golden/tut_adaptive.json, tut_d_output.json:
+     state after one step to 16 digits, step counts 24 / 72 / 97, reversibility to an ulp, propagate_grid, dense and
+     continuous output: 48 recorded steps and samples); the scalar integrators of those pages as batches
 All three summation modes of the oracle must satisfy them, like the reference sweeps compact_mode/opt_level.
 """
 import numpy as np
@@ -277,3 +280,82 @@ def test_two_body_kepler_conservation(mode):
             assert approximately(s.last_h[0], o.last_h[i], 1e4)
             assert approximately(s.state[:, 0], o.state[:, i], 1e5)
         check_kepler_conservation(o.state, kep, approximately)
+
+
+def _rel(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.max(np.abs(a - b) / np.abs(b)))
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_tutorial_adaptive(mode):
+    """doc/tut_adaptive.rst (tutorial/adaptive_basic.cpp): the scalar pendulum as a batch of 3 identical lanes."""
+    g = golden("tut_adaptive.json")
+    P = hb.Program(sys_pendulum())
+    assert P.order == g["order"]
+    n = 3
+    ic = np.array([[g["x0"]] * n, [g["v0"]] * n])
+    o = oracle.OracleIntegrator(P, ic, n, mode=mode)
+    # step(): printed with 6 digits, then time and state with 16-17 digits (the reference's LLVM build may contract and
+    # order its sums differently from any of the oracle's modes: a few ulp).
+    o.step()
+    fs = g["first_step"]
+    assert [int(x) for x in o.step_outcome] == [OC[fs["outcome"]]] * n
+    assert sig_digits_equal(o.last_h, [fs["h"]] * n)
+    assert _rel(o.t_hi, [fs["time"]] * n) < 1e-14
+    assert _rel(o.state, np.array(fs["state"])[:, None] * np.ones(n)) < 1e-14
+    assert np.all(o.state == o.state[:, :1])  # identical lanes stay identical
+    # step_backward(), step(0.01), step(-0.02)
+    o.step(backward=True)
+    assert [int(x) for x in o.step_outcome] == [OC[g["step_backward"]["outcome"]]] * n
+    assert sig_digits_equal(o.last_h, [g["step_backward"]["h"]] * n)
+    for r in g["clamped_steps"]:
+        o.step(r["limit"])
+        assert [int(x) for x in o.step_outcome] == [OC[r["outcome"]]] * n and np.all(o.last_h == r["h"])
+    # Reset, propagate_for(5), propagate_until(20), propagate_until(0): 24 / 72 / 97 steps.
+    o.state[:] = ic
+    o.t_hi[:] = 0
+    o.t_lo[:] = 0
+    for r, tf in zip(g["propagate"], (5.0, 20.0, 0.0)):
+        o.propagate_until(tf)
+        assert [int(x) for x in o.prop_outcome] == [OC[r["outcome"]]] * n
+        assert [int(x) for x in o.n_steps] == [r["n_steps"]] * n
+        assert sig_digits_equal(o.min_h, [r["min_h"]] * n) and sig_digits_equal(o.max_h, [r["max_h"]] * n)
+        assert np.all(o.t_hi == r["time"])
+    # Back at t = 0 after 193 steps: the reference prints the initial condition to an ulp or two; the oracle's modes
+    # land within 30 ulp of that (observed: 2e-15 .. 6e-15 relative).
+    assert _rel(o.state, np.array(g["state_back_at_0"])[:, None] * np.ones(n)) < 5e-14
+    # propagate_grid({0, 0.1, ..., 1.0}): x(0.4), v(0.4).
+    o.state[:] = ic
+    o.t_hi[:] = 0
+    o.t_lo[:] = 0
+    out = o.propagate_grid(np.array(g["grid"]["times"])[:, None] * np.ones(n))
+    k = g["grid"]["index"]
+    assert sig_digits_equal(out[k, 0], [g["grid"]["x"]] * n) and sig_digits_equal(out[k, 1], [g["grid"]["v"]] * n)
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_tutorial_dense_and_continuous_output(mode):
+    """doc/tut_d_output.rst (tutorial/d_output.cpp): dense output after one step, continuous output of
+    propagate_until(10) - 48 recorded steps, six printed samples."""
+    g = golden("tut_d_output.json")
+    P = hb.Program(sys_pendulum())
+    ic = [[g["x0"]] * 2, [g["v0"]] * 2]
+    o = oracle.OracleIntegrator(P, ic, 2, mode=mode)
+    o.step(write_tc=True)
+    assert np.all(o.tc[:, 0, :] == np.array(ic))           # "TC of order 0": the state at the start of the step
+    # update_d_output(0.1): tau relative to the start of the step (t = 0).
+    d = o.d_output(np.full(2, 0.1))
+    assert sig_digits_equal(d[:, 0], g["d_output_at_0.1"]) and sig_digits_equal(d[:, 1], g["d_output_at_0.1"])
+    # ... at the end of the step it is the current state ("rel. difference: 0").
+    assert _rel(o.d_output(o.last_h.copy()), o.state) < 1e-15
+    o.state[:] = ic
+    o.t_hi[:] = 0
+    o.t_lo[:] = 0
+    co = o.propagate_until_cout(g["c_output"]["t_final"])
+    assert co.get_n_steps() == g["c_output"]["n_steps"] == 48
+    lb, ub = co.get_bounds()
+    assert np.all(lb == 0) and np.all(ub == 10)
+    for tm, x, v in g["c_output"]["samples"]:
+        s = co(tm)
+        assert sig_digits_equal(s[0], [x] * 2) and sig_digits_equal(s[1], [v] * 2), tm

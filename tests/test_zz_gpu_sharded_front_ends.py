@@ -2,7 +2,9 @@
 propagate_grid(). Both run the reference's lock-step loops on the host (src/taylor_adaptive_batch.cpp:728-1035,
 :1696-2053) over the shards' steps and dense output, and must give what the single-device batch gives.
 
-Also here: the C++ class's late additions (tests/cpp/test_getters.cpp).
+Also here: the C++ class's late additions (tests/cpp/test_getters.cpp), and the GPU against the outputs the reference
+prints in doc/tut_adaptive.rst, doc/tut_d_output.rst and doc/tut_events.rst (tests/golden/tut_*.json; the CPU oracle is
+held to the same fixtures in tests/test_oracle_golden.py and tests/test_events_cpu.py).
 
 These tests were written at the very end of round 2, after the round's last full run of the GPU suite
 (profiles/r2_pytest_gpu_tail.log): the file sorts after the others so that `pytest -x` reaches them last."""
@@ -158,3 +160,81 @@ def test_continuous_output_times_and_tcs():
     assert np.max(np.abs(tms[:n + 1] - oco.t_hi[:n + 1])) < 1e-12 and np.array_equal(tms[n + 1], oco.t_hi[n + 1])
     scale = np.max(np.abs(oco.tcs), axis=(0, 1, 3), keepdims=True)
     assert np.max(np.abs(tcs - oco.tcs) / scale) < 1e-11
+
+
+# ---- the reference's tutorial outputs on the GPU (tests/golden/tut_adaptive.json, tut_d_output.json, tut_events.json) ----
+def _rel(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.max(np.abs(a - b) / np.abs(b)))
+
+
+def test_tutorial_adaptive_gpu():
+    """doc/tut_adaptive.rst (tutorial/adaptive_basic.cpp), the scalar pendulum as a batch of 3 identical lanes: state after
+    one step to the 16 digits the reference prints, step counts 24 / 72 / 97, back at the initial condition after 193
+    steps, propagate_grid sample. Same assertions as tests/test_oracle_golden.py::test_tutorial_adaptive."""
+    from common import golden, sig_digits_equal, sys_pendulum
+    g = golden("tut_adaptive.json")
+    TO = hb.taylor_outcome
+    OC = {"success": TO.success, "time_limit": TO.time_limit}
+    n = 3
+    ic = np.array([[g["x0"]] * n, [g["v0"]] * n])
+    ta = hb.taylor_adaptive_batch(sys_pendulum(), ic, n)
+    ta.step()
+    fs = g["first_step"]
+    assert [r[0] for r in ta.step_res] == [OC[fs["outcome"]]] * n
+    assert sig_digits_equal(ta.last_h, [fs["h"]] * n)
+    assert _rel(ta.time, [fs["time"]] * n) < 2e-14
+    assert _rel(ta.state, np.array(fs["state"])[:, None] * np.ones(n)) < 2e-14
+    assert np.all(ta.state == ta.state[:, :1])
+    ta.step_backward()
+    assert [r[0] for r in ta.step_res] == [OC[g["step_backward"]["outcome"]]] * n
+    assert sig_digits_equal(ta.last_h, [g["step_backward"]["h"]] * n)
+    for r in g["clamped_steps"]:
+        ta.step([r["limit"]] * n)
+        assert [x[0] for x in ta.step_res] == [OC[r["outcome"]]] * n and np.all(ta.last_h == r["h"])
+    ta.state[:] = ic
+    ta.set_time(0.)
+    for r, call in zip(g["propagate"], (lambda: ta.propagate_for(5.), lambda: ta.propagate_until(20.),
+                                        lambda: ta.propagate_until(0.))):
+        call()
+        assert [x[0] for x in ta.propagate_res] == [OC[r["outcome"]]] * n
+        assert [x[3] for x in ta.propagate_res] == [r["n_steps"]] * n
+        assert sig_digits_equal([x[1] for x in ta.propagate_res], [r["min_h"]] * n)
+        assert sig_digits_equal([x[2] for x in ta.propagate_res], [r["max_h"]] * n)
+        assert np.all(ta.time == r["time"])
+    assert _rel(ta.state, np.array(g["state_back_at_0"])[:, None] * np.ones(n)) < 5e-14
+    ta.state[:] = ic
+    ta.set_time(0.)
+    out = ta.propagate_grid(np.array(g["grid"]["times"])[:, None] * np.ones(n))
+    k = g["grid"]["index"]
+    assert sig_digits_equal(out[k, 0], [g["grid"]["x"]] * n) and sig_digits_equal(out[k, 1], [g["grid"]["v"]] * n)
+
+
+def test_tutorial_dense_and_continuous_output_gpu():
+    """doc/tut_d_output.rst (tutorial/d_output.cpp): dense output after one step, continuous output of
+    propagate_until(10): 48 recorded steps, the six printed samples."""
+    from common import golden, sig_digits_equal, sys_pendulum
+    g = golden("tut_d_output.json")
+    ic = np.array([[g["x0"]] * 2, [g["v0"]] * 2])
+    ta = hb.taylor_adaptive_batch(sys_pendulum(), ic, 2)
+    ta.step(write_tc=True)
+    assert np.all(ta.tc[:, 0, :] == ic)
+    d = ta.update_d_output(0.1).copy()
+    assert sig_digits_equal(d[:, 0], g["d_output_at_0.1"]) and sig_digits_equal(d[:, 1], g["d_output_at_0.1"])
+    assert _rel(ta.update_d_output(ta.time), ta.state) < 1e-14
+    ta.state[:] = ic
+    ta.set_time(0.)
+    co = ta.propagate_until(g["c_output"]["t_final"], c_output=True)
+    assert co.get_n_steps() == g["c_output"]["n_steps"] == 48
+    lb, ub = co.get_bounds()
+    assert np.all(lb == 0) and np.all(ub == 10)
+    for tm, x, v in g["c_output"]["samples"]:
+        s = co(tm)
+        assert sig_digits_equal(s[0], [x] * 2) and sig_digits_equal(s[1], [v] * 2), tm
+
+
+def test_tutorial_events_golden_gpu():
+    """doc/tut_events.rst (tutorial/event_basic.cpp): the event times and the grid output the reference prints with 16
+    digits, through the device's event detection (tests/event_cases.py::case_tutorial_events, also run on the oracle)."""
+    from common import golden
+    ec.case_tutorial_events(make, golden("tut_events.json"))
