@@ -1,7 +1,7 @@
 // The members of the reference's taylor_adaptive_batch<T> added at the end of round 2 (include/heyoka/taylor.hpp:
 // is_variational(), get_n_orig_sv(), get_dtime_data(), get_state_range(), get_pars_range(), get_te_cooldowns();
 // continuous_output_batch::operator()(const T *)).
-// Run by tests/test_zz_gpu_sharded_front_ends.py (needs a CUDA device: the class owns a device-resident batch).
+// Run by tests/test_zz_gpu_late_additions.py (needs a CUDA device: the class owns a device-resident batch).
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -154,6 +154,34 @@ int main()
             const auto &tc = ta.get_tc();
             REQUIRE(tc.size() == 2u * ord1 * 4u);
             REQUIRE(std::equal(tc.begin(), tc.end(), tcs.end() - static_cast<std::ptrdiff_t>(tc.size())));
+        }
+    }
+    // doc/tut_ensemble.rst (tutorial/ensemble.cpp), GOLDEN: ensemble_propagate_until(20) over the ten initial conditions
+    // (0.05 + i / 100, 0.025 + i / 100); the reference prints member 9: state [0.12257736827306077,
+    // 0.24068377640981869], 124 steps, time_limit. Here: five members of batch size 2 (member k holds the initial
+    // conditions 2k and 2k + 1), through ensemble_propagate_until_batch().
+    {
+        taylor_adaptive_batch<double> ta{{prime(x) = v, prime(v) = -9.8 * sin(x)}, {0., 0., 0., 0.}, 2u};
+        const auto gen = [](taylor_adaptive_batch<double> tc, std::size_t k) {
+            for (std::size_t l = 0; l < 2u; ++l) {
+                const auto i = static_cast<double>(2u * k + l);
+                tc.get_state_data()[l] = 0.05 + i / 100.;
+                tc.get_state_data()[2u + l] = 0.025 + i / 100.;
+            }
+            return tc;
+        };
+        const auto ret = ensemble_propagate_until_batch(ta, 20., 5u, gen);
+        REQUIRE(ret.size() == 5u);
+        if (ret.size() == 5u) {
+            const auto &m = std::get<0>(ret[4]);
+            REQUIRE(m.get_time()[1] == 20.);
+            const auto &pr = m.get_propagate_res()[1];
+            REQUIRE(std::get<0>(pr) == taylor_outcome::time_limit);
+            REQUIRE(std::get<3>(pr) == 124u);
+            REQUIRE(std::abs(std::get<1>(pr) - 0.158147) < 6e-7 && std::abs(std::get<2>(pr) - 0.167025) < 6e-7);
+            REQUIRE(std::abs(m.get_state()[1] / 0.12257736827306077 - 1.) < 1e-12);
+            REQUIRE(std::abs(m.get_state()[3] / 0.24068377640981869 - 1.) < 1e-12);
+            REQUIRE(!std::get<1>(ret[4]).has_value());
         }
     }
     if (n_fail == 0) {

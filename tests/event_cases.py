@@ -573,10 +573,12 @@ def case_te_cooldowns_property(make):
         make(sys, ic, 4).te_cooldowns
 
 
-def case_tutorial_events(make, golden):
+def case_tutorial_events(make, golden, loose=1.0):
     """doc/tut_events.rst (tutorial/event_basic.cpp), GOLDEN: the event times the reference prints with 16 digits, the
     scalar integrators of the page as batches of 4 identical lanes. Returns the largest relative deviations seen
-    (zero-velocity times, times of the second event of the two-event run, grid output of the terminal-event run)."""
+    (zero-velocity times, times of the second event of the two-event run, grid output of the terminal-event run).
+    `loose` scales the tolerances (1 for the oracle, whose arithmetic is the reference's up to contraction; larger for
+    the device, whose sin / cos differ from the host's by an ulp or two per call)."""
     g = golden
     x, v, sys = pendulum_sys()
     n = 4
@@ -603,7 +605,7 @@ def case_tutorial_events(make, golden):
             dev["nt"] = max(dev["nt"], rel(t, rt))
         for xv, rx in zip(xs[i], ref["x_at_events"]):
             assert abs(xv - rx) < 1e-9           # printed as +-0.05: the amplitude comes back at every turning point
-    assert dev["nt"] < 1e-14
+    assert dev["nt"] < 1e-14 * loose, dev
     # 2. Same with direction = positive: t = 0, T, 2T.
     times = [[] for _ in range(n)]
     ta = make(sys, ic, n, nt_events=[hb.nt_event_batch(v, lambda ta, t, d_sgn, i: times[i].append(t),
@@ -612,7 +614,7 @@ def case_tutorial_events(make, golden):
     ref = g["nt_zero_velocity_positive_direction"]["times"]
     for i in range(n):
         assert len(times[i]) == 3 and times[i][0] == 0.
-        assert all(rel(t, rt) < 1e-14 for t, rt in zip(times[i], ref))
+        assert all(rel(t, rt) < 1e-14 * loose for t, rt in zip(times[i], ref))
     # 3. Two events, v and v*v - 1e-12: callbacks in chronological order.
     seq = [[] for _ in range(n)]
     ta = make(sys, ic, n, nt_events=[hb.nt_event_batch(v, lambda ta, t, d_sgn, i: seq[i].append((0, t))),
@@ -623,13 +625,13 @@ def case_tutorial_events(make, golden):
         assert [e for e, _ in seq[i]] == [r["event"] for r in ref]
         for (e, t), r in zip(seq[i], ref):
             if e == 0:
-                assert rel(t, r["t"]) < 1e-14
+                assert rel(t, r["t"]) < 1e-14 * loose
             else:
                 # (v*v - 1e-12 crosses zero 2e-6 away from the turning point with a slope of 1e-6, and the event
                 # polynomial - coefficients ~1e-2 - is evaluated to ~1e-18: the root moves by ~1e-12 with the rounding
                 # of the evaluation. Observed on the oracle: 1.3e-12.)
                 dev["two"] = max(dev["two"], abs(t - r["t"]))
-    assert dev["two"] < 2e-11, dev
+    assert dev["two"] < 2e-11 * loose, dev
     # 4. Terminal event toggling the damping parameter; single steps up to the first stop, then propagate_grid().
     tg = g["terminal_damping_toggle"]
 
@@ -649,6 +651,6 @@ def case_tutorial_events(make, golden):
     ref = np.array(tg["grid_output"])
     for i in range(n):
         dev["grid"] = max(dev["grid"], float(np.max(np.abs(out[:, :, i] - ref) / np.abs(ref))))
-    assert dev["grid"] < 1e-12
+    assert dev["grid"] < 1e-12 * loose, dev
     assert np.all(ta.time == tg["final_time"])
     return dev

@@ -13,6 +13,13 @@ Sources (bluescarni/heyoka @ 9c91f71):
   doc/tut_events.rst:138-400       output of tutorial/event_basic.cpp (non-terminal events: zero-velocity times of the
                                    pendulum to 16 digits, direction filter, two events in chronological order; terminal
                                    event toggling a damping parameter: propagate_grid output to 16 digits)
+  doc/tut_ensemble.rst:118-139     output of tutorial/ensemble.cpp (member 9 of ensemble_propagate_until(20): final state
+                                   to 17 digits, 124 steps, min / max step)
+  doc/tut_param.rst:60-128         output of tutorial/pendulum_param.cpp (runtime parameters: one period of the pendulum
+                                   for g = 9.8 and g = 3.72)
+  doc/tut_nonauto.rst:62-88        output of tutorial/forced_damped_pendulum.cpp (time-dependent right-hand side: x after
+                                   every 2 time units, 25 values)
+  doc/tut_adaptive_custom.rst:38-63 output of tutorial/adaptive_opt.cpp (tol = 1e-9: order 12, state after 0 -> 10 -> 0)
 The scalar integrators of those tutorials are batch integrators of size 1 here.
 """
 import json
@@ -178,6 +185,67 @@ def tutorials():
     }
     assert len(times[0]) == 5 and len(times[1]) == 3 and len(multi) == 14 and len(out["terminal_damping_toggle"]["grid_output"]) == 10
     with open(os.path.join(HERE, "tut_events.json"), "w") as f:
+        json.dump(out, f, indent=1)
+
+    more_tutorials()
+
+
+def more_tutorials():
+    def state_of(block):
+        return json.loads(kv(block)["State"][0])
+
+    # ---- tut_ensemble.rst ----
+    blocks = console_blocks(open(os.path.join(REF, "doc", "tut_ensemble.rst")).read())
+    st = next(bl for bl in blocks if any(ln.startswith("State") for ln in bl))
+    res = kv(next(bl for bl in blocks if bl[0].startswith("Integration outcome")))
+    mn, mx = res["Min/max timesteps"][0].split("/")
+    out = {
+        "source": "doc/tut_ensemble.rst (output of tutorial/ensemble.cpp)",
+        "system": "x' = v, v' = -9.8 sin(x)", "n_iter": 10, "t_final": 20.0,
+        "ics": [[0.05 + i / 100., 0.025 + i / 100.] for i in range(10)],
+        "member": 9, "state": state_of(st), "time": float(kv(st)["Time"][0]),
+        "outcome": res["Integration outcome"][0].split("::")[1], "min_h": float(mn), "max_h": float(mx),
+        "n_steps": int(res["N of timesteps"][0]),
+    }
+    assert out["n_steps"] == 124 and out["time"] == 20.0
+    with open(os.path.join(HERE, "tut_ensemble.json"), "w") as f:
+        json.dump(out, f, indent=1)
+
+    # ---- tut_param.rst ----
+    blocks = [bl for bl in console_blocks(open(os.path.join(REF, "doc", "tut_param.rst")).read())
+              if any(ln.startswith("State") for ln in bl)]
+    out = {
+        "source": "doc/tut_param.rst (output of tutorial/pendulum_param.cpp)",
+        "system": "x' = v, v' = -par[0] / par[1] * sin(x)", "x0": 0.05, "v0": 0.0,
+        "runs": [{"pars": json.loads(kv(bl)["Parameters"][0]), "t_final": float(kv(bl)["Time"][0]), "state": state_of(bl)}
+                 for bl in blocks[1:]],
+        "order": int(kv(blocks[0])["Taylor order"][0]),
+    }
+    assert len(out["runs"]) == 2 and out["runs"][1]["pars"][0] == 3.72
+    with open(os.path.join(HERE, "tut_param.json"), "w") as f:
+        json.dump(out, f, indent=1)
+
+    # ---- tut_nonauto.rst ----
+    blocks = console_blocks(open(os.path.join(REF, "doc", "tut_nonauto.rst")).read())
+    xs = [float(ln.split("=")[1]) for ln in next(bl for bl in blocks if bl[0].startswith("x = "))]
+    out = {
+        "source": "doc/tut_nonauto.rst (output of tutorial/forced_damped_pendulum.cpp)",
+        "system": "x' = v, v' = cos(t) - 0.1 v - sin(x)", "x0": 0.0, "v0": 1.85, "delta_t": 2.0, "x": xs,
+    }
+    assert len(xs) == 25
+    with open(os.path.join(HERE, "tut_nonauto.json"), "w") as f:
+        json.dump(out, f, indent=1)
+
+    # ---- tut_adaptive_custom.rst ----
+    blocks = [bl for bl in console_blocks(open(os.path.join(REF, "doc", "tut_adaptive_custom.rst")).read())
+              if any(ln.startswith("State") for ln in bl)]
+    out = {
+        "source": "doc/tut_adaptive_custom.rst (output of tutorial/adaptive_opt.cpp)",
+        "system": "x' = v, v' = -9.8 sin(x)", "x0": 0.05, "v0": 0.025, "tol": 1e-9,
+        "order": int(kv(blocks[0])["Taylor order"][0]), "times": [10.0, 0.0], "state_back_at_0": state_of(blocks[1]),
+    }
+    assert out["order"] == 12
+    with open(os.path.join(HERE, "tut_adaptive_custom.json"), "w") as f:
         json.dump(out, f, indent=1)
 
 

@@ -107,7 +107,7 @@ def test_sharded_with_parameters_and_time():
         ta.propagate_for(np.linspace(1.0, 3.0, batch))
     _same(one, many)
     assert one.propagate_res == many.propagate_res
-    # (propagate_grid() and continuous output of this sharded batch: tests/test_zz_gpu_sharded_front_ends.py)
+    # (propagate_grid() and continuous output of this sharded batch: tests/test_zz_gpu_late_additions.py)
 
 
 @pytest.mark.parametrize("devs", [None, [0, 0, 0]] + ([[0, 1]] if hb.lib.hy_device_count() >= 2 else []))

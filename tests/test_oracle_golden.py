@@ -9,6 +9,9 @@ Fixtures:
   6. doc/tut_adaptive.rst and doc/tut_d_output.rst printed outputs (tests/golden/tut_adaptive.json, tut_d_output.json:
      state after one step to 16 digits, step counts 24 / 72 / 97, reversibility to an ulp, propagate_grid, dense and
      continuous output: 48 recorded steps and samples); the scalar integrators of those pages as batches
+  7. doc/tut_ensemble.rst (the ensemble's members as the lanes of one batch: member 9 to 16 digits, 124 steps),
+     doc/tut_param.rst (runtime parameters), doc/tut_nonauto.rst (time-dependent right-hand side, 25 printed values),
+     doc/tut_adaptive_custom.rst (tol = 1e-9: order 12, the printed state after 0 -> 10 -> 0)
 All three summation modes of the oracle must satisfy them, like the reference sweeps compact_mode/opt_level.
 """
 import numpy as np
@@ -359,3 +362,67 @@ def test_tutorial_dense_and_continuous_output(mode):
     for tm, x, v in g["c_output"]["samples"]:
         s = co(tm)
         assert sig_digits_equal(s[0], [x] * 2) and sig_digits_equal(s[1], [v] * 2), tm
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_tutorial_ensemble_members_as_lanes(mode):
+    """doc/tut_ensemble.rst (tutorial/ensemble.cpp): ensemble_propagate_until(20) over 10 initial conditions; the members
+    are independent integrations, here the 10 lanes of one batch. Member 9: final state as printed (17 digits), 124
+    steps, min / max step."""
+    g = golden("tut_ensemble.json")
+    P = hb.Program(sys_pendulum())
+    ics = np.array(g["ics"]).T.copy()
+    o = oracle.OracleIntegrator(P, ics, g["n_iter"], mode=mode)
+    o.propagate_until(g["t_final"])
+    m = g["member"]
+    assert np.all(o.t_hi == g["time"]) and int(o.prop_outcome[m]) == OC[g["outcome"]]
+    assert int(o.n_steps[m]) == g["n_steps"]
+    assert sig_digits_equal(o.min_h[m], g["min_h"]) and sig_digits_equal(o.max_h[m], g["max_h"])
+    assert _rel(o.state[:, m], g["state"]) < 2e-14       # 124 steps; observed 3e-16 .. 1.4e-15 in the three modes
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_tutorial_runtime_parameters(mode):
+    """doc/tut_param.rst (tutorial/pendulum_param.cpp): x' = v, v' = -par[0] / par[1] sin(x); after one period (for two
+    values of par[0]) the state is back at (0.05, 0) - the reference prints velocities of 7.6e-17 and 2.2e-16."""
+    g = golden("tut_param.json")
+    x, v = hb.make_vars("x", "v")
+    P = hb.Program([(x, v), (v, -hb.par[0] / hb.par[1] * hb.sin(x))])
+    assert (P.order, P.n_pars) == (g["order"], 2)
+    runs = g["runs"]
+    o = oracle.OracleIntegrator(P, [[g["x0"]] * 2, [g["v0"]] * 2], 2, pars=np.array([r["pars"] for r in runs]).T.copy(),
+                                mode=mode)
+    o.propagate_until([r["t_final"] for r in runs])
+    for i, r in enumerate(runs):
+        assert abs(o.state[0, i] - r["state"][0]) < 1e-16
+        assert abs(o.state[1, i] - r["state"][1]) < 2e-15
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_tutorial_time_dependent_rhs(mode):
+    """doc/tut_nonauto.rst (tutorial/forced_damped_pendulum.cpp): x' = v, v' = cos(t) - 0.1 v - sin(x); x after every
+    propagate_for(2), 25 printed values."""
+    g = golden("tut_nonauto.json")
+    x, v = hb.make_vars("x", "v")
+    P = hb.Program([(x, v), (v, hb.cos(hb.time) - .1 * v - hb.sin(x))])
+    o = oracle.OracleIntegrator(P, [[g["x0"]], [g["v0"]]], 1, mode=mode)
+    for k, xr in enumerate(g["x"]):
+        hi, lo = hb._dfloat_add(o.t_hi, o.t_lo, np.array([g["delta_t"]]), np.zeros(1))
+        o.propagate_until(hi, lo)
+        assert sig_digits_equal(o.state[0, 0], xr), k
+    assert o.t_hi[0] == 50.
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_tutorial_custom_tolerance(mode):
+    """doc/tut_adaptive_custom.rst (tutorial/adaptive_opt.cpp): tol = 1e-9 gives order 12; after 0 -> 10 -> 0 the
+    reference prints [0.050000000001312848, 0.024999999997558649]: the 1e-12 deviation from the initial condition is
+    the truncation error of this tolerance, reproduced here to 1e-15."""
+    g = golden("tut_adaptive_custom.json")
+    P = hb.Program(sys_pendulum(), tol=g["tol"])
+    assert P.order == g["order"] == 12
+    o = oracle.OracleIntegrator(P, [[g["x0"]], [g["v0"]]], 1, mode=mode)
+    for tf in g["times"]:
+        o.propagate_until(tf)
+    assert np.max(np.abs(o.state[:, 0] - np.array(g["state_back_at_0"]))) < 1e-15
+    assert abs(o.state[0, 0] - g["x0"]) > 1e-13       # (the deviation itself is there)
