@@ -10,7 +10,10 @@
  * Boost >= 1.85, fmt, spdlog, oneTBB are absent), so this restatement is checked against the
  * reference's own known answers: the closed-form jets of test/taylor_*.cpp, the step-size formula
  * of test/timestep_check.cpp, the printed outputs of doc/tut_batch_mode.rst and README.md, and the
- * exact step counts of test/taylor_adaptive_batch.cpp:586-598 (see tests/test_oracle_golden.py).
+ * exact step counts of test/taylor_adaptive_batch.cpp:586-598, and the outputs printed in doc/tut_adaptive.rst,
+ * tut_d_output.rst, tut_ensemble.rst, tut_param.rst, tut_nonauto.rst, tut_adaptive_custom.rst and tut_events.rst (states
+ * to the 16-17 printed digits, exact step counts, event times to an ulp; see tests/test_oracle_golden.py,
+ * tests/test_events_cpu.py).
  *
  * What follows what:
  *   jet evaluation order            src/taylor_02.cpp:1339-1418 (default mode), :1147-1185 (compact)

@@ -152,3 +152,30 @@ def test_simd_tail_equals_scalar_tail(W, ha, mode):
         o.propagate_until(tf, lockstep=False)
     assert np.array_equal(a.n_steps, b.n_steps) and np.array_equal(a.state, b.state)
     assert np.array_equal(a.t_hi, b.t_hi) and np.array_equal(a.t_lo, b.t_lo)
+
+
+@pytest.mark.parametrize("W", WIDTHS)
+def test_tutorial_ensemble_codegen(W):
+    """doc/tut_ensemble.rst (tests/golden/tut_ensemble.json): the generated SIMD stepper (with the SIMD tail) on the ten
+    initial conditions of the tutorial as lanes - full and ragged groups; member 9 after propagate_until(20) as the
+    reference prints it (17 digits) to 2e-14, 124 steps. doc/tut_adaptive.rst: time and state after the first step to
+    1e-14, 24 + 72 + 97 steps."""
+    g = golden("tut_ensemble.json")
+    P = hb.Program(sys_pendulum())
+    with installed(P, W):
+        o = oracle.OracleIntegrator(P, np.array(g["ics"]).T.copy(), g["n_iter"], mode=oracle.PAIRWISE, width=W)
+        o.propagate_until(g["t_final"], lockstep=False)
+        m = g["member"]
+        assert int(o.n_steps[m]) == g["n_steps"] and np.all(o.t_hi == 20.)
+        assert sig_digits_equal(o.min_h[m], g["min_h"]) and sig_digits_equal(o.max_h[m], g["max_h"])
+        assert np.max(np.abs(o.state[:, m] / np.array(g["state"]) - 1)) < 2e-14
+        a = golden("tut_adaptive.json")
+        o = oracle.OracleIntegrator(P, [[a["x0"]] * 3, [a["v0"]] * 3], 3, mode=oracle.PAIRWISE, width=W)
+        o.step()
+        assert np.max(np.abs(o.t_hi / a["first_step"]["time"] - 1)) < 1e-14
+        assert np.max(np.abs(o.state / np.array(a["first_step"]["state"])[:, None] - 1)) < 1e-14
+        o.state[:] = np.array([[a["x0"]] * 3, [a["v0"]] * 3])
+        o.t_hi[:] = 0
+        for r, tf in zip(a["propagate"], (5., 20., 0.)):
+            o.propagate_until(tf, lockstep=False)
+            assert [int(x) for x in o.n_steps] == [r["n_steps"]] * 3
