@@ -654,3 +654,90 @@ def case_tutorial_events(make, golden, loose=1.0):
     assert dev["grid"] < 1e-12 * loose, dev
     assert np.all(ta.time == tg["final_time"])
     return dev
+
+
+# ---- regression cases of test/taylor_adaptive_batch.cpp that exercise the front ends' host loops with events ----
+def case_step_count_te_stop_bug(make):
+    """:1819-1844 "propagate step count te stop bug": a terminal event without callback stops propagate_until() and
+    propagate_grid() in the first step; that step is counted."""
+    x, v, sys = pendulum_sys()
+    ic = [0., 0., 0.5, 0.5001]
+    ta = make(sys, ic, 2, t_events=[hb.t_event_batch(x - 1e-6)])
+    ta.propagate_until([10., 10.])
+    assert [r[3] for r in ta.propagate_res] == [1, 1]
+    ta = make(sys, ic, 2, t_events=[hb.t_event_batch(x - 1e-6)])
+    ta.propagate_grid([0., 0., 1., 1., 2., 2.])
+    assert [r[3] for r in ta.propagate_res] == [1, 1]
+    # :1847-1862 "set_time alias bug": set_time(get_time()) leaves the time alone.
+    ta = make(sys, ic, 2, t_events=[hb.t_event_batch(x - 1e-6)])
+    ta.set_time(ta.time)
+    assert list(ta.time) == [0., 0.]
+
+
+def case_callback_ste(make):
+    """:1944-1980 "callback ste": a stopping terminal event in the first iteration of propagate_until(kw::callback): the
+    step callback still runs once; the stopped lane reports -1, the others success, one step each."""
+    x, v, sys = pendulum_sys()
+    ta = make(sys, [-1., -0.0001, -1., -1., 0.025, 0.026, 0.027, 0.028], 4, t_events=[hb.t_event_batch(x)])
+    n_invoked = [0]
+
+    def pcb(t):
+        n_invoked[0] += 1
+        return True
+
+    ta.propagate_until(10., callback=pcb)
+    assert [r[0] for r in ta.propagate_res] == [TO.success, -1, TO.success, TO.success]
+    assert [r[3] for r in ta.propagate_res] == [1, 1, 1, 1]
+    assert n_invoked[0] == 1
+
+
+def case_propagate_grid_ste(make):
+    """:2011-2046 "propagate_grid ste": when propagate_grid() runs into a stopping terminal event, the grid points inside
+    the last step taken are still produced, the later ones stay NaN."""
+    x, v = hb.make_vars("x", "v")
+    ta = make([(x, v), (v, -x)], [0., 0., 1., 1.], 2, t_events=[hb.t_event_batch(hb.time - .1)])
+    grid = [0., 0., .1 - 2e-6, 10., .1 - 1e-6, 20., .1 + 1e-6, 30.]
+    out = np.asarray(ta.propagate_grid(grid))          # [n_pts, dim, batch]
+    assert out.shape == (4, 2, 2)
+    assert [r[0] for r in ta.propagate_res] == [-1, -1]
+    res = out.reshape(-1)                              # the reference's flat layout [pt][var][lane]
+    nan = [bool(np.isnan(r)) for r in res]
+    assert nan == [False, False, False, False, False, True, False, True, False, True, False, True, True, True, True, True]
+
+
+def case_ev_inf_state(make):
+    """:1456-1471 "ev inf state": a non-finite state in one lane is reported for that lane only; the others detect their
+    terminal event."""
+    x, = hb.make_vars("x")
+    ta = make([(x, hb.expression(1.))], [0., 0., 0., 0.], 4, t_events=[hb.t_event_batch(x - 5.)])
+    ta.state[0, 2] = np.inf
+    ta.step([10.] * 4)
+    assert [r[0] for r in ta.step_res] == [-1, -1, TO.err_nf_state, -1]
+
+
+def case_event_cb_time(make):
+    """:1560-1640 "event cb time": event callbacks that alter the time coordinate are an error naming the first altered
+    batch index; every callback of the step has run by then, each with the event's own (finite) time."""
+    x, v = hb.make_vars("x", "v")
+    counts = [0, 0]
+
+    def mk(k, new_t0):
+        def cb(ta, t, d_sgn, i):
+            assert np.isfinite(t)
+            counts[k] += 1
+            ta.set_time([new_t0, ta.time[1]])
+        return cb
+
+    ta = make([(x, v), (v, -x)], [0., 0., 1., -1.], 2,
+              nt_events=[hb.nt_event_batch(x - 1e-5, mk(0, -10.)), hb.nt_event_batch(x - 1e-5, mk(1, -10.))])
+    with pytest.raises(RuntimeError, match="The invocation of one or more event callbacks resulted in the alteration of "
+                                           "the time coordinate of the integrator at the batch index 0 - this is not "
+                                           "supported"):
+        ta.step()
+    assert counts == [1, 1]
+    counts[:] = [0, 0]
+    ta = make([(x, v), (v, -x)], [0., 0., 1., 1.], 2,
+              nt_events=[hb.nt_event_batch(x - 1e-5, mk(0, -np.inf)), hb.nt_event_batch(x - 1e-5, mk(1, np.nan))])
+    with pytest.raises(RuntimeError, match="at the batch index 0 - this is not supported"):
+        ta.step()
+    assert counts == [2, 2]

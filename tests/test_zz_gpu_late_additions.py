@@ -149,6 +149,35 @@ def test_more_tutorials_gpu():
     assert np.max(np.abs(ta.state[:, 0] - np.array(g["state_back_at_0"]))) < 1e-13
 
 
+@pytest.mark.parametrize("case", [ec.case_step_count_te_stop_bug, ec.case_callback_ste, ec.case_propagate_grid_ste,
+                                  ec.case_ev_inf_state, ec.case_event_cb_time], ids=lambda f: f.__name__)
+def test_reference_regression_cases_gpu(case):
+    """Regression cases of test/taylor_adaptive_batch.cpp (:1456-1471, :1560-1640, :1819-1862, :1944-1980, :2011-2046) for the
+    host loops of integrators with events, on the device (tests/test_events_cpu.py runs them on the oracle)."""
+    case(make)
+
+
+def test_step_callback_must_not_alter_the_time_gpu():
+    """:2141-2176 "bug prop_cb time": a step callback of propagate_until() that alters the time coordinate - of every
+    batch element or of one - is an error."""
+    x, v = hb.make_vars("x", "v")
+    msg = ("The invocation of the callback passed to propagate_until\\(\\) resulted in the alteration of the time "
+           "coordinate of the integrator - this is not supported")
+
+    def all_lanes(t):
+        t.set_time(100.)
+        return True
+
+    def one_lane(t):
+        t.set_time([t.time[0], 100.])
+        return True
+
+    for cb in (all_lanes, one_lane):
+        ta = hb.taylor_adaptive_batch([(x, v), (v, -x)], [0., 0.1, 1., 1.1], 2)
+        with pytest.raises(RuntimeError, match=msg):
+            ta.propagate_until(10., callback=cb)
+
+
 # ---- 2. front-end host loops on sharded batches (written after the round's last full GPU run) ----
 def test_sharded_event_batch_equals_single_device():
     """Events on a batch made of shards (hy_batch_create_multi(): here three shards on one GPU, uneven blocks of lanes):
