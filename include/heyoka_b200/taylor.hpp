@@ -333,6 +333,16 @@ public:
     {
         finalise_ctor(std::move(sys), std::move(state), batch_size, parse_ctor(kw_args...));
     }
+    // Without initial conditions: a zeroed state vector (include/heyoka/taylor.hpp:914-921). Taken only when everything
+    // after the batch size is a named argument, like the reference's igor::validate constraint, so that
+    // {sys, {0.}, 1u} keeps meaning (state, batch size).
+    template <typename... KwArgs,
+              std::enable_if_t<(kw::detail::is_tagged<std::decay_t<KwArgs>>::value && ... && true), int> = 0>
+    explicit taylor_adaptive_batch(std::vector<std::pair<expression, expression>> sys, std::uint32_t batch_size,
+                                   const KwArgs &...kw_args)
+        : taylor_adaptive_batch(std::move(sys), std::vector<double>{}, batch_size, kw_args...)
+    {
+    }
     taylor_adaptive_batch(const taylor_adaptive_batch &);
     taylor_adaptive_batch(taylor_adaptive_batch &&) noexcept;
     taylor_adaptive_batch &operator=(const taylor_adaptive_batch &);

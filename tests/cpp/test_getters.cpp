@@ -184,6 +184,19 @@ int main()
             REQUIRE(!std::get<1>(ret[4]).has_value());
         }
     }
+    // test/taylor_adaptive_batch.cpp:2244-2267 ("empty init state", "scalar time ctor"): construction without initial
+    // conditions gives a zeroed state; a scalar kw::time is splatted over the batch. A one-element state list still
+    // means (state, batch size).
+    {
+        const auto dyn = model::pendulum();
+        taylor_adaptive_batch<double> t0{dyn, 2u};
+        REQUIRE((t0.get_state() == std::vector<double>{0., 0., 0., 0.}));
+        taylor_adaptive_batch<double> t1{dyn, 2u, kw::time = 42};
+        REQUIRE((t1.get_time() == std::vector<double>{42., 42.}));
+        REQUIRE((t1.get_state() == std::vector<double>{0., 0., 0., 0.}));
+        taylor_adaptive_batch<double> t2{{prime(x) = x}, {1.}, 1u};
+        REQUIRE((t2.get_batch_size() == 1u && t2.get_state() == std::vector<double>{1.}));
+    }
     if (n_fail == 0) {
         std::printf("ALL PASSED (getters)\n");
     }
