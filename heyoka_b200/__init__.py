@@ -734,9 +734,13 @@ class taylor_adaptive_batch:
         return self._with_events
 
     def get_t_events(self):
+        if not self._with_events:
+            raise ValueError("No events were defined for this integrator")  # src/taylor_adaptive_batch.cpp:2202-2229
         return self._tes
 
     def get_nt_events(self):
+        if not self._with_events:
+            raise ValueError("No events were defined for this integrator")
         return self._ntes
 
     def reset_cooldowns(self, i=None):

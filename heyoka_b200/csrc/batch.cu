@@ -3222,7 +3222,7 @@ int hy_batch_reset_cooldowns(hy_batch *b, int64_t lane)
         }
         if (lane >= static_cast<int64_t>(b->n)) {
             throw std::invalid_argument("Cannot reset the cooldowns at batch index " + std::to_string(lane)
-                                        + ": the batch size is only " + std::to_string(b->n));
+                                        + ": the batch size for this integrator is only " + std::to_string(b->n));
         }
         if (!b->shards.empty()) {
             for (std::size_t i = 0; i < b->shards.size(); ++i) {

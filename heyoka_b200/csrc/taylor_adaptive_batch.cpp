@@ -884,12 +884,19 @@ bool taylor_adaptive_batch<double>::with_events() const
 {
     return !m_impl->tes.empty() || !m_impl->ntes.empty();
 }
+// (Both throw on an integrator without events, src/taylor_adaptive_batch.cpp:2202-2229.)
 const std::vector<t_event_batch<double>> &taylor_adaptive_batch<double>::get_t_events() const
 {
+    if (!with_events()) {
+        throw std::invalid_argument("No events were defined for this integrator");
+    }
     return m_impl->tes;
 }
 const std::vector<nt_event_batch<double>> &taylor_adaptive_batch<double>::get_nt_events() const
 {
+    if (!with_events()) {
+        throw std::invalid_argument("No events were defined for this integrator");
+    }
     return m_impl->ntes;
 }
 const std::vector<std::vector<std::optional<std::pair<double, double>>>> &

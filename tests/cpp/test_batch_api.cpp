@@ -712,7 +712,7 @@ static void test_events()
         tb.reset_cooldowns(1u);
         tb.reset_cooldowns();
         REQUIRE_THROWS_MSG(tb.reset_cooldowns(4u), std::invalid_argument,
-                           "Cannot reset the cooldowns at batch index 4: the batch size is only 4");
+                           "Cannot reset the cooldowns at batch index 4: the batch size for this integrator is only 4");
     }
     // "te propagate_grid" (:1479-1534).
     {

@@ -741,3 +741,64 @@ def case_event_cb_time(make):
     with pytest.raises(RuntimeError, match="at the batch index 0 - this is not supported"):
         ta.step()
     assert counts == [2, 2]
+
+
+def case_ev_exception_callback(make):
+    """:1473-1558 "ev exception callback": exceptions raised by event callbacks in several batch elements are collected
+    into one RuntimeError naming every batch index (the callbacks of the other elements still run; a non-terminal
+    callback that raises keeps the terminal one of that element from running); a single exception is re-raised as is."""
+    x, v, sys = pendulum_sys()
+
+    def raise0(ta, t, d_sgn, i):
+        raise ValueError("hello world 0")
+
+    def raise1(ta, d_sgn, i):
+        raise ValueError("hello world 1")
+
+    ta = make(sys, PEND_IC, 4, nt_events=[hb.nt_event_batch(v * v - 1e-10, raise0)],
+              t_events=[hb.t_event_batch(v, callback=raise1)])
+    with pytest.raises(RuntimeError) as ei:
+        ta.propagate_until([4.] * 4)
+    msg = str(ei.value)
+    assert "Two or more exceptions were raised during the execution of event callbacks in a batch integrator" in msg
+    assert "Batch index #0" not in msg and "hello world 1" not in msg and "hello world 0" in msg
+    assert all("Batch index #%d" % i in msg for i in (1, 2, 3))
+    ta = make(sys, PEND_IC, 4, nt_events=[hb.nt_event_batch(v * v - 1e-10, lambda ta, t, d_sgn, i: None)],
+              t_events=[hb.t_event_batch(v, callback=raise1)])
+    with pytest.raises(RuntimeError) as ei:
+        ta.propagate_until([4.] * 4)
+    msg = str(ei.value)
+    assert "Batch index #0" not in msg and "hello world 1" in msg
+    assert all("Batch index #%d" % i in msg for i in (1, 2, 3))
+    # A single exception comes back as it was raised.
+    ta = make(sys, [0, 0., 0., 0.03, .25, .25, .25, .28], 4,
+              nt_events=[hb.nt_event_batch(v * v - 1e-10, lambda ta, t, d_sgn, i: None)],
+              t_events=[hb.t_event_batch(v, callback=raise1)])
+    with pytest.raises(ValueError, match="hello world 1"):
+        ta.propagate_until([4.] * 4)
+
+
+def case_events_error(make):
+    """:1395-1453 "events error": messages of reset_cooldowns() / the event getters with and without events."""
+    x, v, sys = pendulum_sys()
+    ic = [0.1, 0.2, 0., 0.]
+    msg = "Cannot reset the cooldowns at batch index 2: the batch size for this integrator is only 2"
+    ta = make(sys, ic, 2, t_events=[hb.t_event_batch(x)])
+    assert ta.with_events()
+    with pytest.raises(ValueError, match=msg):
+        ta.reset_cooldowns(2)
+    # No terminal events: nothing to reset, the calls still work; the cooldown lists are empty.
+    ta = make(sys, ic, 2, nt_events=[hb.nt_event_batch(x, lambda ta, t, d_sgn, i: None)])
+    assert ta.with_events() and ta.te_cooldowns == [[], []]
+    ta.reset_cooldowns()
+    ta.reset_cooldowns(0)
+    ta.reset_cooldowns(1)
+    with pytest.raises(ValueError, match=msg):
+        ta.reset_cooldowns(2)
+    assert len(ta.get_nt_events()) == 1 and len(ta.get_t_events()) == 0
+    ta = make(sys, ic, 2)
+    assert not ta.with_events()
+    for call in (ta.get_t_events, ta.get_nt_events, ta.reset_cooldowns, lambda: ta.reset_cooldowns(2),
+                 lambda: ta.te_cooldowns):
+        with pytest.raises(ValueError, match="No events were defined for this integrator"):
+            call()

@@ -428,6 +428,9 @@ class OracleBatch:
         return list(self._events)
 
     def reset_cooldowns(self, lane=-1):
+        if lane >= self.n:  # (hy_batch_reset_cooldowns(), src/taylor_adaptive_batch.cpp:2348-2352)
+            raise ValueError("Cannot reset the cooldowns at batch index %d: the batch size for this integrator is only %d"
+                             % (lane, self.n))
         if lane < 0:
             self.cd_on[...] = 0
         else:

@@ -176,7 +176,7 @@ def test_event_api_errors_gpu():
         ta._b.propagate_until(np.full(4, 1.0))
     ta.reset_cooldowns()
     ta.reset_cooldowns(2)
-    with pytest.raises(ValueError, match="batch size is only 4"):
+    with pytest.raises(ValueError, match="Cannot reset the cooldowns at batch index 4: the batch size for this integrator is only 4"):
         ta.reset_cooldowns(4)
     tb = make(sys, ec.PEND_IC, 4)
     with pytest.raises(ValueError, match="No events"):
