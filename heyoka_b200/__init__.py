@@ -692,12 +692,24 @@ class taylor_adaptive_batch:
         self._t_lo = np.zeros(self._batch_size)
 
     def set_dtime(self, hi, lo):
-        hi = np.broadcast_to(np.asarray(hi, dtype=np.float64), (self._batch_size,)).copy()
-        lo = np.broadcast_to(np.asarray(lo, dtype=np.float64), (self._batch_size,)).copy()
-        # Normalise like set_dtime(), src/taylor_adaptive_batch.cpp:2180-2232.
-        if np.any(np.abs(hi) < np.abs(lo)):
-            raise ValueError("The first component of a double-length time must not be smaller in magnitude than the "
-                             "second")
+        """set_dtime(), src/taylor_adaptive_batch.cpp:562-606: one (hi, lo) pair for every batch element, or one pair per
+        element; checked (dtime_checks(), include/heyoka/detail/taylor_common.hpp:231-249) before the times are touched,
+        then normalised."""
+        n = self._batch_size
+        if np.ndim(hi) == 0 and np.ndim(lo) == 0:
+            hi, lo = np.full(n, float(hi)), np.full(n, float(lo))
+        else:
+            hi, lo = np.array(hi, dtype=np.float64).reshape(-1), np.array(lo, dtype=np.float64).reshape(-1)
+            if hi.size != n or lo.size != n:
+                raise ValueError("Invalid number of new times specified in a Taylor integrator in batch mode: the batch "
+                                 "size is %d, but the number of specified times is (%d, %d)" % (n, hi.size, lo.size))
+        for h, l in zip(hi.tolist(), lo.tolist()):
+            if not (np.isfinite(h) and np.isfinite(l)):
+                raise ValueError("The components of the double-length representation of the time coordinate must both "
+                                 "be finite, but they are %r and %r instead" % (h, l))
+            if abs(h) < abs(l):
+                raise ValueError("The first component of the double-length representation of the time coordinate (%r) "
+                                 "must not be smaller in magnitude than the second component (%r)" % (h, l))
         s = hi + lo
         self._t_lo = (hi - s) + lo
         self._t_hi = s

@@ -11,6 +11,7 @@
 #include <string>
 #include <thread>
 
+#include "capi_common.hpp"
 #include "program.hpp"
 
 namespace heyoka_b200
@@ -564,10 +565,19 @@ void taylor_adaptive_batch<double>::set_dtime(const std::vector<double> &hi, con
                                     + std::to_string(m.batch_size) + ", but the number of specified times is ("
                                     + std::to_string(hi.size()) + ", " + std::to_string(lo.size()) + ")");
     }
+    // dtime_checks(), include/heyoka/detail/taylor_common.hpp:231-249: before the times are touched.
     for (std::uint32_t i = 0; i < m.batch_size; ++i) {
-        if (std::isfinite(hi[i]) && std::isfinite(lo[i]) && std::abs(hi[i]) < std::abs(lo[i])) {
-            throw std::invalid_argument("The first component of a double-length time must not be smaller in "
-                                        "magnitude than the second");
+        if (!std::isfinite(hi[i]) || !std::isfinite(lo[i])) {
+            throw std::invalid_argument("The components of the double-length representation of the time coordinate "
+                                        "must both be finite, but they are "
+                                        + detail::fmt_double(hi[i]) + " and " + detail::fmt_double(lo[i]) + " instead");
+        }
+        if (std::abs(hi[i]) < std::abs(lo[i])) {
+            throw std::invalid_argument("The first component of the double-length representation of the time "
+                                        "coordinate ("
+                                        + detail::fmt_double(hi[i])
+                                        + ") must not be smaller in magnitude than the second component ("
+                                        + detail::fmt_double(lo[i]) + ")");
         }
     }
     m.refresh_time();

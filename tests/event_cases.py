@@ -802,3 +802,38 @@ def case_events_error(make):
                  lambda: ta.te_cooldowns):
         with pytest.raises(ValueError, match="No events were defined for this integrator"):
             call()
+
+
+def case_get_set_dtime(make):
+    """:1864-1941 "get_set_dtime": the double-length time through dtime / set_dtime(): sizes, normalisation, the checks
+    (finite components, |hi| >= |lo|) made before anything is touched."""
+    x, v, sys = pendulum_sys()
+    # (An event that never triggers: the CPU run of this case goes through the oracle-backed front end.)
+    ta = make(sys, [0, 0.01, 0.1, 0.11], 2, nt_events=[hb.nt_event_batch(x - 100., lambda ta, t, d_sgn, i: None)])
+    ta.step()
+    hi, lo = ta.dtime
+    assert hi[0] != 0 and hi[1] != 0 and lo[0] == 0 and lo[1] == 0
+    for _ in range(50):
+        ta.step()
+    with pytest.raises(ValueError, match=r"Invalid number of new times specified in a Taylor integrator in batch mode: "
+                                         r"the batch size is 2, but the number of specified times is \(0, 1\)"):
+        ta.set_dtime([], [1.])
+    hi, lo = (np.array(a) for a in ta.dtime)
+    ta.set_dtime(hi, lo)
+    assert np.array_equal(ta.dtime[0], hi) and np.array_equal(ta.dtime[1], lo)
+    ta.set_dtime([3., -7.], [2., 5.])
+    assert list(ta.dtime[0]) == [5., -2.] and list(ta.dtime[1]) == [0., 0.]
+    ta.set_dtime([3., -3.], [EPS, EPS])
+    assert list(ta.dtime[0]) == [3., -3.] and list(ta.dtime[1]) == [EPS, EPS]
+    ta.set_dtime(4., 3.)
+    assert list(ta.dtime[0]) == [7., 7.] and list(ta.dtime[1]) == [0., 0.]
+    ta.set_dtime(3., EPS)
+    assert list(ta.dtime[0]) == [3., 3.] and list(ta.dtime[1]) == [EPS, EPS]
+    ta.set_dtime([3., 4.], [1., 2.])
+    finite = "The components of the double-length representation of the time coordinate must both be finite"
+    order = "must not be smaller in magnitude than the second component"
+    for args, msg in (((INF, 1.), finite), ((1., INF), finite), ((3., 4.), order), (([1., INF], [1., 2.]), finite),
+                      (([1., .1], [INF, 2.]), finite), (([1., 2.], [1., 3.]), order), (([4., 4.], [8., 3.]), order)):
+        with pytest.raises(ValueError, match=msg):
+            ta.set_dtime(*args)
+    assert list(ta.dtime[0]) == [4., 6.] and list(ta.dtime[1]) == [0., 0.]       # untouched by the failed calls
