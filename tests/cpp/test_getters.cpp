@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <limits>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -196,6 +197,37 @@ int main()
         REQUIRE((t1.get_state() == std::vector<double>{0., 0., 0., 0.}));
         taylor_adaptive_batch<double> t2{{prime(x) = x}, {1.}, 1u};
         REQUIRE((t2.get_batch_size() == 1u && t2.get_state() == std::vector<double>{1.}));
+    }
+    // test/taylor_adaptive_batch.cpp:1864-1941 ("get_set_dtime"): sizes, normalisation and the reference's dtime_checks()
+    // (finite components, |hi| >= |lo|), made before the times are touched.
+    {
+        taylor_adaptive_batch<double> ta{{prime(x) = v, prime(v) = -9.8 * sin(x)}, {0, 0.01, 0.1, 0.11}, 2u};
+        const double eps = std::numeric_limits<double>::epsilon(), inf = std::numeric_limits<double>::infinity();
+        ta.step();
+        REQUIRE(ta.get_dtime().first[0] != 0. && ta.get_dtime().second[0] == 0.);
+        const auto throws = [&](auto &&f, const char *msg) {
+            try {
+                f();
+            } catch (const std::invalid_argument &e) {
+                return std::string(e.what()).find(msg) != std::string::npos;
+            }
+            return false;
+        };
+        REQUIRE(throws([&] { ta.set_dtime(std::vector<double>{}, std::vector<double>{1.}); },
+                       "the batch size is 2, but the number of specified times is (0, 1)"));
+        ta.set_dtime({3., -7.}, {2., 5.});
+        REQUIRE((ta.get_dtime().first == std::vector<double>{5., -2.} && ta.get_dtime().second == std::vector<double>{0., 0.}));
+        ta.set_dtime(3., eps);
+        REQUIRE((ta.get_dtime().first == std::vector<double>{3., 3.} && ta.get_dtime().second == std::vector<double>{eps, eps}));
+        ta.set_dtime({3., 4.}, {1., 2.});
+        const char *finite = "The components of the double-length representation of the time coordinate must both be finite";
+        const char *order = "must not be smaller in magnitude than the second component";
+        REQUIRE(throws([&] { ta.set_dtime(inf, 1.); }, finite));
+        REQUIRE(throws([&] { ta.set_dtime(1., inf); }, finite));
+        REQUIRE(throws([&] { ta.set_dtime(3., 4.); }, order));
+        REQUIRE(throws([&] { ta.set_dtime({1., inf}, {1., 2.}); }, finite));
+        REQUIRE(throws([&] { ta.set_dtime({1., 2.}, {1., 3.}); }, order));
+        REQUIRE((ta.get_dtime().first == std::vector<double>{4., 6.} && ta.get_dtime().second == std::vector<double>{0., 0.}));
     }
     if (n_fail == 0) {
         std::printf("ALL PASSED (getters)\n");
