@@ -837,3 +837,14 @@ def case_get_set_dtime(make):
         with pytest.raises(ValueError, match=msg):
             ta.set_dtime(*args)
     assert list(ta.dtime[0]) == [4., 6.] and list(ta.dtime[1]) == [0., 0.]       # untouched by the failed calls
+
+
+def case_reset_cooldowns(make):
+    """:1726-1751 "reset cooldowns": a terminal event whose callback returns False stops the propagation and leaves a
+    cooldown behind; reset_cooldowns() clears every one."""
+    x, v, sys = pendulum_sys()
+    ta = make(sys, PEND_IC, 4, t_events=[hb.t_event_batch(v, callback=lambda ta, d_sgn, i: False)])
+    ta.propagate_until([100.] * 4)
+    assert any(cd is not None for lane in ta.te_cooldowns for cd in lane)
+    ta.reset_cooldowns()
+    assert all(cd is None for lane in ta.te_cooldowns for cd in lane)
