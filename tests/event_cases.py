@@ -848,3 +848,19 @@ def case_reset_cooldowns(make):
     assert any(cd is not None for lane in ta.te_cooldowns for cd in lane)
     ta.reset_cooldowns()
     assert all(cd is None for lane in ta.te_cooldowns for cd in lane)
+
+
+def case_param_deduction_from_events(make):
+    """:1017-1049 "param deduction from events": the number of runtime parameters is deduced from the event equations
+    too (the largest par[] index anywhere, plus one, per batch element)."""
+    x, v, sys = pendulum_sys()
+    ic = [0.05, 0.06, 0.025, 0.026]
+    ncb = lambda ta, t, d_sgn, i: None  # noqa: E731
+    ta = make(sys, ic, 2, t_events=[hb.t_event_batch(v - hb.par[0])])
+    assert np.asarray(ta.pars).size == 2
+    ta = make(sys, ic, 2, nt_events=[hb.nt_event_batch(v - hb.par[1], ncb)])
+    assert np.asarray(ta.pars).size == 4
+    ta = make(sys, ic, 2, t_events=[hb.t_event_batch(v - hb.par[10])], nt_events=[hb.nt_event_batch(v - hb.par[1], ncb)])
+    assert np.asarray(ta.pars).size == 22
+    ta.step()                # (and the integrator runs with them: v - par[10] = v crosses zero in the first step)
+    assert [r[0] for r in ta.step_res] == [-1, -1] and np.all(np.isfinite(ta.state))

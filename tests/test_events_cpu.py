@@ -139,7 +139,8 @@ def test_tutorial_events_golden():
 
 @pytest.mark.parametrize("case", [ec.case_step_count_te_stop_bug, ec.case_callback_ste, ec.case_propagate_grid_ste,
                                   ec.case_ev_inf_state, ec.case_event_cb_time, ec.case_ev_exception_callback,
-                                  ec.case_events_error, ec.case_get_set_dtime, ec.case_reset_cooldowns], ids=lambda f: f.__name__)
+                                  ec.case_events_error, ec.case_get_set_dtime, ec.case_reset_cooldowns,
+                                  ec.case_param_deduction_from_events], ids=lambda f: f.__name__)
 def test_reference_regression_cases(case):
     """Regression cases of test/taylor_adaptive_batch.cpp for the host loops of integrators with events."""
     case(make)

@@ -151,7 +151,8 @@ def test_more_tutorials_gpu():
 
 @pytest.mark.parametrize("case", [ec.case_step_count_te_stop_bug, ec.case_callback_ste, ec.case_propagate_grid_ste,
                                   ec.case_ev_inf_state, ec.case_event_cb_time, ec.case_ev_exception_callback,
-                                  ec.case_events_error, ec.case_get_set_dtime, ec.case_reset_cooldowns], ids=lambda f: f.__name__)
+                                  ec.case_events_error, ec.case_get_set_dtime, ec.case_reset_cooldowns,
+                                  ec.case_param_deduction_from_events], ids=lambda f: f.__name__)
 def test_reference_regression_cases_gpu(case):
     """Regression cases of test/taylor_adaptive_batch.cpp (:1456-1471, :1560-1640, :1819-1862, :1944-1980, :2011-2046) for the
     host loops of integrators with events, on the device (tests/test_events_cpu.py runs them on the oracle)."""
